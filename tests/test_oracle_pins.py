@@ -1,0 +1,216 @@
+"""Pin the CPU oracle against the reference's OWN assertions (the reference ships no golden
+vectors; its tests are property / known-answer checks at n = 128).
+
+Each test names the reference test it re-runs.  Tolerances are the reference's:
+rtol_dp = sqrt(1e-15), rtol_sp = sqrt(1e-6)  (src/Constants.f90:16-37).
+"""
+import numpy as np
+import pytest
+
+N = 128  # test_size, src/Utilities/TestUtils.fypp:18
+KINDS = ["s", "d", "c", "z"]
+
+
+def _randn(rng, shape, dtype):
+    a = rng.standard_normal(shape)
+    if np.issubdtype(dtype, np.complexfloating):
+        a = a + 1j * rng.standard_normal(shape)
+    return np.asfortranarray(a.astype(dtype))
+
+
+def _start(rng, n, ncols, dtype, oracle):
+    X = np.zeros((n, ncols), dtype=dtype, order="F")
+    X[:, 0] = _randn(rng, n, dtype)
+    oracle.normalize(X[:, 0])
+    return X
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_arnoldi_factorization(oracle, kind):
+    """test/TestKrylov.fypp:194-239  test_arnoldi_factorization: kdim = n = 128."""
+    dt = oracle.DTYPES[kind]; rtol = oracle.RTOL[kind]
+    rng = np.random.default_rng(1)
+    A = _randn(rng, (N, N), dt) / np.sqrt(N).astype(oracle.REAL[kind])
+    kdim = N
+    X = _start(rng, N, kdim + 1, dt, oracle)
+    H = np.zeros((kdim + 1, kdim), dtype=dt, order="F")
+    info = oracle.arnoldi(oracle.Op.dense(A), X, H)
+    assert info >= 0
+    k = kdim if info == 0 else info
+    err = np.abs(A @ X[:, :k] - X[:, :k + 1] @ H[:k + 1, :k]).max()
+    assert err < rtol
+    G = X[:, :k].conj().T @ X[:, :k]
+    assert np.abs(G - np.eye(k)).max() < rtol
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_block_arnoldi_factorization(oracle, kind):
+    """test/TestKrylov.fypp:244-296  block Arnoldi, p = 2, kdim = 64."""
+    dt = oracle.DTYPES[kind]; rtol = oracle.RTOL[kind]
+    rng = np.random.default_rng(2)
+    A = _randn(rng, (N, N), dt) / np.sqrt(N).astype(oracle.REAL[kind])
+    p, kdim = 2, N // 2
+    X = np.zeros((N, p * (kdim + 1)), dtype=dt, order="F")
+    X[:, :p] = _randn(rng, (N, p), dt)
+    info, _ = oracle.qr(X[:, :p])                      # initialize_krylov_subspace orthonormalises X0
+    X[:, :p] = np.asfortranarray(X[:, :p])
+    H = np.zeros((p * (kdim + 1), p * kdim), dtype=dt, order="F")
+    info = oracle.arnoldi(oracle.Op.dense(A), X, H, blksize=p)
+    assert info >= 0
+    k = p * kdim if info == 0 else info
+    err = np.abs(A @ X[:, :k] - X[:, :k + p] @ H[:k + p, :k]).max()
+    assert err < rtol
+    G = X[:, :k].conj().T @ X[:, :k]
+    assert np.abs(G - np.eye(k)).max() < rtol
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_lanczos_tridiagonalization(oracle, kind):
+    """test/TestKrylov.fypp:449-514: A = M M^H / n + 0.01 I (TestUtils.fypp:476-484); A X = X T."""
+    dt = oracle.DTYPES[kind]; rtol = oracle.RTOL[kind]
+    rng = np.random.default_rng(3)
+    M = _randn(rng, (N, N), dt)
+    A = np.asfortranarray((M @ M.conj().T / N + 0.01 * np.eye(N)).astype(dt))
+    kdim = N
+    X = _start(rng, N, kdim + 1, dt, oracle)
+    T = np.zeros((kdim + 1, kdim), dtype=dt, order="F")
+    info = oracle.lanczos(oracle.Op.dense(A), X, T)
+    assert info >= 0
+    k = kdim if info == 0 else info
+    err = np.abs(A @ X[:, :k] - X[:, :k + 1] @ T[:k + 1, :k]).max()
+    assert err < rtol
+    G = X[:, :k].conj().T @ X[:, :k]
+    assert np.abs(G - np.eye(k)).max() < rtol
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_bidiagonalization(oracle, kind):
+    """test/TestKrylov.fypp:365-429: A V = U B, U^H U = I, V^H V = I."""
+    dt = oracle.DTYPES[kind]; rtol = oracle.RTOL[kind]
+    rng = np.random.default_rng(4)
+    A = _randn(rng, (N, N), dt) / np.sqrt(N).astype(oracle.REAL[kind])
+    kdim = N
+    U = _start(rng, N, kdim + 1, dt, oracle)
+    V = np.zeros((N, kdim + 1), dtype=dt, order="F")
+    B = np.zeros((kdim + 1, kdim), dtype=dt, order="F")
+    info = oracle.bidiag(oracle.Op.dense(A), U, V, B)
+    assert info >= 0
+    k = kdim if info == 0 else info - 1
+    err = np.abs(A @ V[:, :k] - U[:, :k + 1] @ B[:k + 1, :k]).max()
+    assert err < rtol
+    assert np.abs(U[:, :k].conj().T @ U[:, :k] - np.eye(k)).max() < rtol
+    assert np.abs(V[:, :k].conj().T @ V[:, :k] - np.eye(k)).max() < rtol
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_qr_factorization(oracle, kind):
+    """test/TestKrylov.fypp:52-110: A = QR, Q^H Q = I."""
+    dt = oracle.DTYPES[kind]; rtol = oracle.RTOL[kind]
+    rng = np.random.default_rng(5)
+    A = _randn(rng, (N, 20), dt)
+    Q = A.copy(order="F")
+    info, R = oracle.qr(Q)
+    assert info == 0
+    assert np.abs(A - Q @ R).max() < rtol
+    assert np.abs(Q.conj().T @ Q - np.eye(20)).max() < rtol
+
+
+def test_qr_breakdown_refill(oracle):
+    """qr.fypp:146-162: a colinear column gets R(j,j) = 0 and is refilled orthonormally.
+
+    Literal reference behaviour: `info = j` is set at :149 but the DGS calls at :156 and :133
+    re-use the same `info` variable and overwrite it, so for j > 1 the routine returns the
+    last DGS info (0 here).  Only a breakdown in column 1 (the Arnoldi p = 1 case) survives."""
+    rng = np.random.default_rng(6)
+    A = _randn(rng, (N, 6), np.float64)
+    A[:, 3] = 2.0 * A[:, 1] - A[:, 0]
+    Q = A.copy(order="F")
+    info, R = oracle.qr(Q, tol=1e-10)
+    assert info == 0 and R[3, 3] == 0.0
+    assert np.abs(Q.T @ Q - np.eye(6)).max() < 1e-12
+    Z = np.zeros((N, 1), order="F")
+    info, R = oracle.qr(Z)
+    assert info == 1 and R[0, 0] == 0.0 and abs(np.linalg.norm(Z) - 1.0) < 1e-14
+
+
+@pytest.mark.parametrize("kind", ["d", "z"])
+def test_arnoldi_invariant_subspace(oracle, kind):
+    """arnoldi.fypp:59-71: breakdown returns info = dimension of the invariant subspace."""
+    dt = oracle.DTYPES[kind]
+    A = np.asfortranarray(np.diag(np.arange(1, N + 1)).astype(dt))
+    X = np.zeros((N, 11), dtype=dt, order="F")
+    X[:3, 0] = 1.0 / np.sqrt(3.0)              # lives in a 3-dim invariant subspace
+    H = np.zeros((11, 10), dtype=dt, order="F")
+    info = oracle.arnoldi(oracle.Op.dense(A), X, H, tol=1e-12)
+    assert info == 3
+    assert np.all(H[:, 3:] == 0)              # later columns untouched
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_gmres(oracle, kind):
+    """test/TestIterativeSolvers.fypp:529-564: ||Ax - b|| < rtol ||b||."""
+    dt = oracle.DTYPES[kind]; rtol = oracle.RTOL[kind]
+    rng = np.random.default_rng(7)
+    A = _randn(rng, (N, N), dt) / np.sqrt(N).astype(oracle.REAL[kind]) + 2 * np.eye(N, dtype=dt)
+    A = np.asfortranarray(A.astype(dt))
+    b = _randn(rng, N, dt)
+    x = np.zeros(N, dtype=dt)
+    info, meta = oracle.gmres(oracle.Op.dense(A), b, x, kdim=N, maxiter=10)
+    assert info > 0 and meta["converged"]
+    assert np.linalg.norm(A @ x - b) < rtol * np.linalg.norm(b) * 10
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_cg(oracle, kind):
+    """test/TestIterativeSolvers.fypp:683-725."""
+    dt = oracle.DTYPES[kind]; rtol = oracle.RTOL[kind]
+    rng = np.random.default_rng(8)
+    M = _randn(rng, (N, N), dt)
+    A = np.asfortranarray((M @ M.conj().T / N + 0.5 * np.eye(N)).astype(dt))
+    b = _randn(rng, N, dt)
+    x = np.zeros(N, dtype=dt)
+    info, meta = oracle.cg(oracle.Op.dense(A), b, x, maxiter=10 * N)
+    assert info > 0
+    assert np.linalg.norm(A @ x - b) < rtol * np.linalg.norm(b) * 10
+
+
+def test_stencil_matches_dense(oracle):
+    """The oracle's matrix-free stencils against an assembled dense matrix (small grids)."""
+    import scipy.sparse as sp
+    nx, ny, nz = 7, 5, 4
+    coef = (6.0, -1.3, -0.7, -1.2, -0.8, -1.1, -0.9)
+    op = oracle.Op.stencil("d", (nx, ny, nz), coef)
+    n = nx * ny * nz
+    D = np.zeros((n, n))
+    for k in range(nz):
+        for j in range(ny):
+            for i in range(nx):
+                p = i + nx * (j + ny * k)
+                D[p, p] = coef[0]
+                if i > 0: D[p, p - 1] = coef[1]
+                if i < nx - 1: D[p, p + 1] = coef[2]
+                if j > 0: D[p, p - nx] = coef[3]
+                if j < ny - 1: D[p, p + nx] = coef[4]
+                if k > 0: D[p, p - nx * ny] = coef[5]
+                if k < nz - 1: D[p, p + nx * ny] = coef[6]
+    x = np.random.default_rng(9).standard_normal(n)
+    assert np.allclose(op.apply(x), D @ x, rtol=1e-13, atol=1e-13)
+    assert np.allclose(op.apply(x, trans=True), D.T @ x, rtol=1e-13, atol=1e-13)
+    # csr against scipy
+    S = sp.random(40, 30, density=0.2, random_state=3, format="csr", dtype=np.float64)
+    S = (S + 1j * sp.random(40, 30, density=0.2, random_state=4, format="csr")).tocsr()
+    S.sort_indices()
+    opc = oracle.Op.csr(40, 30, S.indptr, S.indices, S.data.astype(np.complex128))
+    xc = np.random.default_rng(10).standard_normal(30) + 0j
+    uc = np.random.default_rng(11).standard_normal(40) + 0j
+    assert np.allclose(opc.apply(xc), S @ xc)
+    assert np.allclose(opc.apply(uc, trans=True), S.conj().T @ uc)
+
+
+def test_rng_uniform_is_sharding_independent(oracle):
+    a = oracle.fill(1000, "d", "uniform", 42)
+    b = np.concatenate([oracle.fill(400, "d", "uniform", 42, 0), oracle.fill(600, "d", "uniform", 42, 400)])
+    assert np.array_equal(a, b)
+    assert 0.0 < a.min() and a.max() < 1.0 and abs(a.mean() - 0.5) < 0.05
+    g = oracle.fill(200000, "d", "normal", 7)
+    assert abs(g.mean()) < 0.01 and abs(g.std() - 1.0) < 0.01
