@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- Arnoldi steps/s on BASELINE.json's config C2 (5-point Poisson 4096^2, fp64, kdim=128).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+One bench "step" = one pass of the hot path over one start vector = one full kstart=1..kend=128
+Arnoldi factorisation (128 Arnoldi steps: matvec + CGS2 + Hessenberg update each).  `value` is
+Arnoldi steps per second = 128*K / time, the strong-scaling metric BASELINE.json names (global
+n = 16.8M rows sharded by grid rows over the N ranks).
+
+Prints ONE JSON line on rank 0 (see DESIGN.md "Measurement" for every key).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "arnoldi_steps_per_s"
+UNIT = "steps/s"
+POISSON5 = (4.0, -1.0, -1.0, -1.0, -1.0)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nx", type=int, default=4096)
+    ap.add_argument("--ny", type=int, default=4096)
+    ap.add_argument("--kdim", type=int, default=128)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile-pass", action="store_true")
+    ap.add_argument("--cpu-sample-steps", type=int, default=12)
+    return ap.parse_args()
+
+
+def alg_bytes_step(j: int, n: int, s: int = 8) -> int:
+    """Official algorithmic bytes of one Arnoldi step with j basis vectors."""
+    return 2 * n * s + 4 * j * n * s
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True); self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "power_w_max": max(pw), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (C restatement of the reference's per-vector algorithm) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_arnoldi_sample(nx, ny, kdim, nsteps, threads):
+    """Time oracle Arnoldi steps j = 1..nsteps at full n, fit t(j) = a + b*j, extrapolate to kdim.
+    Returns (steps_per_s, seconds_spent, description)."""
+    from oracle import lk_oracle as lo
+    lo.set_threads(threads)
+    n = nx * ny
+    A = lo.Op.stencil("d", (nx, ny), POISSON5)
+    X = np.zeros((n, nsteps + 1), order="F")
+    X[:, 0] = lo.fill(n, "d", "uniform", 42); lo.normalize(X[:, 0])
+    H = np.zeros((nsteps + 1, nsteps), order="F")
+    ts = []
+    t00 = time.perf_counter()
+    for k in range(1, nsteps + 1):
+        t0 = time.perf_counter()
+        info = lo.arnoldi(A, X, H, kstart=k, kend=k)
+        ts.append(time.perf_counter() - t0)
+        assert info == 0
+    spent = time.perf_counter() - t00
+    js = np.arange(1, nsteps + 1, dtype=float)
+    if nsteps >= 3:
+        b, a = np.polyfit(js, np.array(ts), 1)
+    else:
+        a, b = 0.0, ts[-1] / nsteps
+    total = sum(max(a + b * j, 0.0) for j in range(1, kdim + 1))
+    desc = (f"oracle arnoldi steps j=1..{nsteps} at full n={n} (5-pt Poisson {nx}x{ny}, fp64), per-step times "
+            f"fitted t(j)=a+b*j (a={a:.3f}s, b={b:.4f}s) and summed over j=1..{kdim}")
+    return kdim / total, spent, desc
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import lk_oracle as lo
+    threads = lo.max_threads()
+    vals = []
+    desc = ""
+    nsample = max(3, min(args.cpu_sample_steps, 8))
+    for i in range(args.warmup + args.steps):
+        v, spent, desc = cpu_arnoldi_sample(args.nx, args.ny, args.kdim, nsample, threads)
+        if i >= args.warmup:
+            vals.append((v, spent))
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([s for _, s in vals])) * 1e3
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"arnoldi kdim={args.kdim} on 5-pt Poisson {args.nx}x{args.ny} (n={args.nx * args.ny}) fp64",
+                   "bench_step": "bounded CPU sample: " + desc},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference = CPU oracle (C restatement of LightKrylov's per-vector algorithm, OpenMP); the Fortran "
+                "reference cannot be built in this image (no Fortran compiler / fpm / stdlib)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import lightkrylov_b200 as lk
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        ctx = lk.Context.from_torch_distributed(local)
+    else:
+        ctx = lk.Context(local)
+    assert world == args.gpus or world == 1, "--gpus must equal WORLD_SIZE"
+
+    nx, ny, kdim = args.nx, args.ny, args.kdim
+    n = nx * ny
+    y0, nyl = lk.partition(ny, world, rank)
+    nloc, row0 = nx * nyl, nx * y0
+    A = lk.LinOp.stencil5(ctx, "d", nx, ny, POISSON5)
+    X = lk.Basis(ctx, "d", nloc, kdim + 1, n_global=n, row0=row0)
+    H = np.zeros((kdim + 1, kdim), order="F")
+    x0 = X.col(0)
+    x0.fill_random("uniform", 42)
+    x0.scal(1.0 / x0.norm())
+
+    ext = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.sync()
+
+    def timed(fn, reps):
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(ext):
+            e0.record(ext)
+            for _ in range(reps):
+                fn()
+            e1.record(ext)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=f"cuda:{local}", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- device-resident arm: inputs (operator, start vector) already in HBM -------------------
+    def step_resident():
+        info = lk.arnoldi(A, X, H)
+        assert info == 0
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.kernel_launches
+    ms_total = timed(step_resident, args.steps)
+    launches = ctx.kernel_launches - l0
+    clocks = sampler.stop() if rank == 0 else None
+    value = args.steps * kdim / (ms_total * 1e-3)
+
+    # ---- end-to-end arm: host start vector in pinned memory -> H on the host ---------------------
+    x0_host = torch.empty(nloc, dtype=torch.float64).pin_memory()
+    x0_host.copy_(torch.from_numpy(x0.get()))
+    Hh = np.zeros((kdim + 1, kdim), order="F")
+    lib = ctx.lib
+
+    def step_e2e():
+        # H2D of this step's input, normalisation (eigs' x0 handling), factorisation, H back on the host
+        rc = lib.lkb_vec_put(x0.h, x0_host.data_ptr())
+        assert rc == 0
+        x0.scal(1.0 / x0.norm())
+        info = lk.arnoldi(A, X, Hh)
+        assert info == 0
+
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_value = args.steps * kdim / (ms_e2e * 1e-3)
+    h2d = nloc * 8
+    d2h = (kdim + 1) * kdim * 8 + 32 + 2 * 16      # H columns + flags + norm scalars
+
+    # ---- per-kernel-class device time: separate profiled pass (events on the launching stream) ---
+    peak, peak_src = load_peaks()
+    roof = None
+    kernels = {}
+    if not args.no_profile_pass:
+        ctx.set_profile(True)
+        step_resident()
+        prof = ctx.get_profile()
+        ctx.set_profile(False)
+        s = 8
+        algb = {
+            "matvec": kdim * 2 * nloc * s,
+            "multidot": sum(2 * (j + 1) * nloc * s for j in range(1, kdim + 1)),       # 2 passes x (V_j + w)
+            "multiaxpy": sum(2 * (j + 2) * nloc * s for j in range(1, kdim + 1)),      # 2 passes x (V_j + w r/w)
+            "other": kdim * 2 * nloc * s,                                              # normalisation sweep
+        }
+        for name, (ms, nl) in prof.items():
+            gbs = algb[name] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+            kernels[name] = {"ms_total": ms, "launches": nl, "alg_bytes": algb[name], "GBps": gbs, "frac": gbs / peak}
+        dom = max(("multidot", "multiaxpy"), key=lambda k: kernels[k]["ms_total"])
+        nl = max(kernels[dom]["launches"], 1)
+        roof = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
+                "frac": kernels[dom]["GBps"] / peak, "traffic": None,
+                "alg_bytes_per_launch_avg": algb[dom] / nl, "avg_launch_ms": kernels[dom]["ms_total"] / nl,
+                "peak_source": peak_src,
+                "how": "separate profiled factorisation in the same process: CUDA events on the context stream around "
+                       "every launch of the class (graphs off), algorithmic bytes summed over the 2*kdim launches"}
+    # whole-step roofline with the official per-step bytes (matvec + 4*j*n*s), per GPU
+    total_alg = sum(alg_bytes_step(j, nloc) for j in range(1, kdim + 1))
+    step_gbs = total_alg * args.steps / (ms_total * 1e-3) / 1e9
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import lk_oracle as lo
+        thr = lo.max_threads()
+        v_all, _, desc = cpu_arnoldi_sample(nx, ny, kdim, args.cpu_sample_steps, thr)
+        v_one, _, desc1 = cpu_arnoldi_sample(nx, ny, kdim, 4, 1)
+        cpu = {"value": v_all, "unit": UNIT, "cores": thr, "kind": "port", "sample": desc,
+               "serial": {"value": v_one, "cores": 1, "sample": desc1}}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"arnoldi kdim={kdim} on 5-pt Poisson {nx}x{ny} (n={n}) fp64 [BASELINE configs[1]]",
+                       "bench_step": f"one kstart=1..kend={kdim} factorisation = {kdim} Arnoldi steps",
+                       "partition": f"grid rows over {world} rank(s), {nloc} rows/rank",
+                       "l2": "working set 17.3 GB/GPU-share >> 126 MB L2 (inputs larger than L2, no flush needed)",
+                       "cuda_graph": True},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps,
+                    "what": "pinned host start vector -> H2D -> normalise -> lkb_arnoldi -> Hessenberg matrix on the host"},
+            "gpu_launches": int(launches),
+            "roofline": roof,
+            "step_roofline": {"alg_bytes_per_factorisation_per_gpu": total_alg, "achieved_GBps_per_gpu": step_gbs,
+                              "frac_of_measured": step_gbs / peak, "frac_of_nominal_8TBps": step_gbs / 8000.0},
+            "kernels": kernels,
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.sync()
+    del X, A, x0
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,184 @@
+/* lkb.h -- C ABI of the B200-native Krylov-factorisation hot path (liblkb.so).
+ *
+ * The reference (nekStab/LightKrylov) is pure Fortran and has NO existing FFI: its plugin
+ * boundary is the pair of abstract types `abstract_vector_{rsp,rdp,csp,cdp}` /
+ * `abstract_linop_*` plus the generic procedures `arnoldi`, `lanczos`, `bidiagonalization`,
+ * `double_gram_schmidt_step`, `gmres`, `cg`, ...  The entry points below are exactly what a thin
+ * ISO_C_BINDING shim (fortran/lightkrylov_cuda.f90) binds to so that device-
+ * resident extensions of those types run this library.  Every declaration cites the reference
+ * interface it replaces (paths relative to the reference tree).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types.
+ *   - kind: LKB_S/D/C/Z = rsp/rdp/csp/cdp.  Scalars cross the ABI as `const void*` pointing to one
+ *     element of that kind (float, double, float[2], double[2]); real results as double.
+ *   - Fortran `integer` <-> int32_t, `logical` <-> int32_t (0/1), indices are 1-based where the
+ *     reference's are (kstart, kend, info); sizes of device data are int64_t.
+ *   - all calls are synchronous w.r.t. host-visible results and must come from one host thread
+ *     per context (the reference is serial and not thread-safe).
+ *   - return value: 0 = ok, <0 = fatal (CUDA/NCCL failure, bad argument, NaN norm); the Fortran
+ *     shim maps a non-zero return to `stop_error` (src/Utilities/Logger.f90:290-298).
+ *     `info` out-arguments follow the reference: 0 ok, >0 benign.
+ *   - there is NO CPU fallback: without a CUDA device every entry point fails with LKB_ERR_CUDA.
+ */
+#ifndef LKB_H
+#define LKB_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { LKB_S = 0, LKB_D = 1, LKB_C = 2, LKB_Z = 3 };
+enum { LKB_OK = 0, LKB_ERR_CUDA = -1, LKB_ERR_ARG = -2, LKB_ERR_NCCL = -3, LKB_ERR_NAN = -4,
+       LKB_ERR_LAPACK = -5, LKB_ERR_ALLOC = -6 };
+enum { LKB_DIST_NORMAL = 0, LKB_DIST_UNIFORM = 1 };
+
+typedef struct lkb_ctx_s*   lkb_ctx_t;
+typedef struct lkb_vec_s*   lkb_vec_t;     /* device abstract_vector */
+typedef struct lkb_basis_s* lkb_basis_t;   /* contiguous column-major array of abstract_vectors */
+typedef struct lkb_op_s*    lkb_op_t;      /* device abstract_linop */
+
+/* ---- context -----------------------------------------------------------------------------
+ * One context per process per GPU.  Replaces comm_setup/comm_close (Logger.f90:245-288): the
+ * reference's only parallel hook is MPI init for logging; global reductions were the user's job
+ * inside `dot`.  Here the context owns the stream, workspaces and (optionally) the NCCL
+ * communicator used to all-reduce partial inner products across the row-sharded ranks. */
+int lkb_init(int device, lkb_ctx_t* ctx);
+int lkb_nccl_unique_id(void* id128);                       /* rank 0 creates, caller broadcasts */
+int lkb_init_dist(int device, int rank, int world, const void* id128, lkb_ctx_t* ctx);
+int lkb_finalize(lkb_ctx_t ctx);
+int lkb_sync(lkb_ctx_t ctx);
+void* lkb_stream(lkb_ctx_t ctx);                           /* cudaStream_t of the context */
+const char* lkb_last_error(void);
+int lkb_set_seed(lkb_ctx_t ctx, uint64_t seed);            /* seed of the `rand` TBP stream */
+int lkb_set_graphs(lkb_ctx_t ctx, int enable);             /* CUDA-graph capture of step loops (default on) */
+int lkb_rank(lkb_ctx_t ctx); int lkb_world(lkb_ctx_t ctx);
+
+/* ---- abstract_vector TBPs : src/AbstractTypes/AbstractVectors.fypp:295-381, 424-460 ------
+ * n_local rows live on this GPU and are rows [row0, row0+n_local) of an n_global-row vector. */
+int lkb_vec_create(lkb_ctx_t ctx, int kind, int64_t n_local, int64_t n_global, int64_t row0, lkb_vec_t* v);
+int lkb_vec_wrap(lkb_ctx_t ctx, int kind, int64_t n_local, int64_t n_global, int64_t row0, void* devptr, lkb_vec_t* v);
+int lkb_vec_clone(lkb_vec_t src, lkb_vec_t* dst);          /* allocate(source=) / defined assignment */
+int lkb_vec_destroy(lkb_vec_t v);
+int lkb_vec_zero(lkb_vec_t v);                             /* :304-308 */
+int lkb_vec_rand(lkb_vec_t v, int32_t ifnorm);             /* :310-321 (normal deviates; honours ifnorm) */
+int lkb_vec_fill_random(lkb_vec_t v, int dist, uint64_t seed);  /* seeded, sharding-independent */
+int lkb_vec_scal(lkb_vec_t v, const void* alpha);          /* :323-332 */
+int lkb_vec_axpby(const void* alpha, lkb_vec_t x, const void* beta, lkb_vec_t self); /* :334-348 self = alpha*x + beta*self */
+int lkb_vec_dot(lkb_vec_t self, lkb_vec_t vec, void* out); /* :350-361 out = self^H vec (conj on self) */
+int lkb_vec_norm(lkb_vec_t v, double* out);                /* :424-432 sqrt(abs(dot(v,v))) */
+int64_t lkb_vec_size(lkb_vec_t v);                         /* :363-379 get_size (global) */
+int64_t lkb_vec_local_size(lkb_vec_t v);
+void* lkb_vec_ptr(lkb_vec_t v);                            /* raw device pointer */
+int lkb_vec_put(lkb_vec_t v, const void* host);            /* TestUtils.fypp:391-441 put_data */
+int lkb_vec_get(lkb_vec_t v, void* host);                  /* get_data */
+
+/* ---- basis = X(:) : the contiguous column-major device array that replaces arrays of
+ * polymorphic vectors (AbstractVectors.fypp:571-730 operate on `X(:)`). */
+int lkb_basis_create(lkb_ctx_t ctx, int kind, int64_t n_local, int64_t n_global, int64_t row0, int ncols, lkb_basis_t* b);
+int lkb_basis_destroy(lkb_basis_t b);
+int lkb_basis_col(lkb_basis_t b, int i0, lkb_vec_t* view); /* non-owning view of column i0 (0-based) */
+int lkb_basis_zero(lkb_basis_t b, int col0, int ncols);    /* zero_basis :711-715 */
+int lkb_basis_put(lkb_basis_t b, int col0, int ncols, const void* host, int64_t ldhost);
+int lkb_basis_get(lkb_basis_t b, int col0, int ncols, void* host, int64_t ldhost);
+int lkb_basis_ncols(lkb_basis_t b);
+int64_t lkb_basis_ld(lkb_basis_t b);
+/* innerprod(X(:j), W(:p)) -> out (j x p, ld ldout)              AbstractVectors.fypp:659-695 */
+int lkb_basis_innerprod(lkb_basis_t X, int j, lkb_basis_t W, int wcol0, int p, void* out, int ldout);
+/* W(:, q) -= X(:j) coef(:, q)   = linear_combination + sub      AbstractVectors.fypp:571-643 */
+int lkb_basis_lincomb_sub(lkb_basis_t X, int j, const void* coef, int ldcoef, lkb_basis_t W, int wcol0, int p);
+/* y = X(:j) coef   (linear_combination into an existing vector) */
+int lkb_basis_lincomb(lkb_basis_t X, int j, const void* coef, lkb_vec_t y);
+/* double_gram_schmidt_step(Y(:p), X(:j), info, if_chk_orthonormal, beta)
+ *   src/Krylov/gram_schmidt.fypp:12-105, interface BaseKrylov.fypp:634-712.  beta may be NULL. */
+int lkb_dgs_step(lkb_basis_t X, int j, lkb_basis_t W, int wcol0, int p, int32_t if_chk_orthonormal,
+                 void* beta, int ldbeta, int32_t* info);
+/* orthogonalize_against_basis (one pass)  gram_schmidt.fypp:113-200, BaseKrylov.fypp:601-629 */
+int lkb_orthogonalize_against_basis(lkb_basis_t X, int j, lkb_basis_t W, int wcol0, int p,
+                                    int32_t if_chk_orthonormal, void* beta, int ldbeta, int32_t* info);
+/* qr(Q(:p), R, info, tol)  no pivoting   src/Krylov/qr.fypp:116-167, BaseKrylov.fypp:395-417 */
+int lkb_qr(lkb_basis_t Q, int col0, int p, void* R, int ldr, double tol, int32_t* info);
+
+/* ---- abstract_linop : src/AbstractTypes/AbstractLinops.fypp:58-87, 204-256, 391-461 ----- */
+/* coef = (center, -x, +x, -y, +y[, -z, +z]) of kind `kind`; (nx, ny[, nz]) is the GLOBAL grid,
+ * the slowest axis is sharded: this rank owns `nslow_local` rows/planes starting at `slow0`. */
+int lkb_op_stencil5_create(lkb_ctx_t ctx, int kind, int64_t nx, int64_t ny, const void* coef5,
+                           int64_t slow0, int64_t nslow_local, lkb_op_t* A);
+int lkb_op_stencil7_create(lkb_ctx_t ctx, int kind, int64_t nx, int64_t ny, int64_t nz, const void* coef7,
+                           int64_t slow0, int64_t nslow_local, lkb_op_t* A);
+int lkb_op_csr_create(lkb_ctx_t ctx, int kind, int64_t m, int64_t n, const int64_t* rowptr, const int32_t* col,
+                      const void* val, lkb_op_t* A);
+int lkb_op_dense_create(lkb_ctx_t ctx, int kind, int64_t m, int64_t n, const void* a_colmajor, lkb_op_t* A);
+/* user-supplied device matvec (a Fortran/C extension of abstract_linop): fn launches on `stream` */
+typedef int (*lkb_matvec_fn)(void* user, const void* x_dev, void* y_dev, int32_t trans, void* stream);
+int lkb_op_callback_create(lkb_ctx_t ctx, int kind, int64_t m_local, int64_t n_local, lkb_matvec_fn fn,
+                           void* user, int32_t capturable, lkb_op_t* A);
+int lkb_op_destroy(lkb_op_t A);
+int lkb_op_matvec(lkb_op_t A, lkb_vec_t x, lkb_vec_t y);    /* apply_matvec  :391-407 (bumps counter) */
+int lkb_op_rmatvec(lkb_op_t A, lkb_vec_t x, lkb_vec_t y);   /* apply_rmatvec :409-424 */
+int lkb_op_counters(lkb_op_t A, int64_t* n_matvec, int64_t* n_rmatvec);
+int lkb_op_reset_counters(lkb_op_t A);
+
+/* ---- Krylov processes : src/Krylov ------------------------------------------------------- */
+/* arnoldi(A, X, H, info, kstart, kend, tol, transpose, blksize)
+ *   src/Krylov/arnoldi.fypp:8-76, contract BaseKrylov.fypp:60-155.
+ *   X has (kdim+1)*blksize columns; H is HOST (kdim+1)p x kdim*p column-major with ld ldh, inout:
+ *   only columns kstart..kend are written.  kstart/kend 1-based; pass 0 for "absent"
+ *   (kstart = 1, kend = kdim); tol < 0 = absent (atol_kind). */
+int lkb_arnoldi(lkb_op_t A, lkb_basis_t X, void* H, int ldh, int32_t* info,
+                int32_t kstart, int32_t kend, double tol, int32_t transpose, int32_t blksize);
+/* lanczos(A, X, T, info, kstart, kend, tol)   src/Krylov/lanczos.fypp:7-64, BaseKrylov.fypp:157-237 */
+int lkb_lanczos(lkb_op_t A, lkb_basis_t X, void* T, int ldt, int32_t* info,
+                int32_t kstart, int32_t kend, double tol);
+/* bidiagonalization(A, U, V, B, info, kstart, kend, tol)  golub_kahan.fypp:7-64, BaseKrylov.fypp:239-333 */
+int lkb_bidiag(lkb_op_t A, lkb_basis_t U, lkb_basis_t V, void* B, int ldb, int32_t* info,
+               int32_t kstart, int32_t kend, double tol);
+/* krylov_schur(n, X, H, select)  BaseKrylov.fypp:782-834 with the median selector of eigs */
+int lkb_krylov_schur(lkb_basis_t X, void* H, int ldh, int kdim, int32_t* nkeep);
+
+/* ---- solvers (host shells around the device step) ---------------------------------------- */
+typedef struct {            /* gmres_dp_opts / gmres_dp_metadata : IterativeSolvers.fypp:140-188 */
+    int32_t kdim;           /* default 30 */
+    int32_t maxiter;        /* default 10 */
+    int32_t n_iter, n_inner, n_outer, converged, info;   /* metadata out */
+    double* res; int32_t res_cap, res_len;               /* optional residual history (caller-owned) */
+} lkb_gmres_io;
+/* gmres(A, b, x, info, rtol, atol, preconditioner, options, transpose, meta)  gmres.fypp:65-255
+ * rtol/atol < 0 = absent.  No preconditioner hook in this round. */
+int lkb_gmres(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, double rtol, double atol,
+              int32_t transpose, lkb_gmres_io* io);
+typedef struct {            /* cg_dp_opts / cg_dp_metadata : IterativeSolvers.fypp:467-507 */
+    int32_t maxiter;        /* default 100 */
+    int32_t n_iter, converged, info;
+    double* res; int32_t res_cap, res_len;
+} lkb_cg_io;
+/* cg(A, b, x, info, rtol, atol, preconditioner, options, meta)  CG/CG.fypp:61-196 */
+int lkb_cg(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, double rtol, double atol, lkb_cg_io* io);
+/* eigs(A, X, eigvals, residuals, info, x0, kdim, tolerance, transpose)  IterativeSolvers.fypp:972-1143
+ *   X: nev columns (out); eigvals: nev complex (double[2] each); residuals: nev doubles.
+ *   x0 may be NULL (random start); kdim <= 0 = 4*nev; tolerance < 0 = rtol_kind. */
+int lkb_eigs(lkb_op_t A, lkb_basis_t X, int nev, double* eigvals, double* residuals, int32_t* info,
+             lkb_vec_t x0, int32_t kdim, double tolerance, int32_t transpose);
+/* eighs(A, X, eigvals, residuals, info, x0, kdim, tolerance)  EIGHS/eighs.fypp:29-126 */
+int lkb_eighs(lkb_op_t A, lkb_basis_t X, int nev, double* eigvals, double* residuals, int32_t* info,
+              lkb_vec_t x0, int32_t kdim, double tolerance);
+/* svds(A, U, S, V, residuals, info, u0, kdim, tolerance)  SVDS/svd_solvers.fypp:28-121 */
+int lkb_svds(lkb_op_t A, lkb_basis_t U, double* S, lkb_basis_t V, int nsv, double* residuals, int32_t* info,
+             lkb_vec_t u0, int32_t kdim, double tolerance);
+/* host LAPACK provider for the k x k algebra of eigs/eighs/svds/krylov_schur (geev, gees, trsen,
+ * syev/heev, gesvd): a shared library exporting Fortran-ABI LAPACK, symbol = prefix + name + suffix
+ * (e.g. scipy's bundled OpenBLAS: prefix "scipy_", suffix "_").  The reference gets these from
+ * stdlib_linalg_lapack (submodule_utility_functions.fypp:55-117). */
+int lkb_set_lapack(const char* path, const char* prefix, const char* suffix);
+
+/* ---- measurement helpers ----------------------------------------------------------------- */
+/* per-kernel-class device time (ms) of the LAST process call, measured with CUDA events on the
+ * context stream when profiling is enabled: [0] matvec, [1] multi-dot, [2] multi-axpy, [3] other */
+int lkb_set_profile(lkb_ctx_t ctx, int enable);
+int lkb_get_profile(lkb_ctx_t ctx, double* ms4, int64_t* launches4);
+int64_t lkb_kernel_launches(lkb_ctx_t ctx);               /* kernels launched since context creation */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LKB_H */

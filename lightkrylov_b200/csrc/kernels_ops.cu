@@ -1,0 +1,236 @@
+// kernels_ops.cu -- abstract_linop extensions: matrix-free 5-/7-point stencils and CSR SpMV.
+//
+// Reference contract: src/AbstractTypes/AbstractLinops.fypp:58-87 (matvec / rmatvec, vec_out is
+// intent(out)).  Stencil index convention: p = i + nx*(j + ny*k); coef = (center,-x,+x,-y,+y,-z,+z),
+// homogeneous Dirichlet outside the global grid.  The slowest axis (y in 2-D, z in 3-D) is the
+// row-sharded one: the neighbouring slab's boundary row / plane arrives in halo_lo / halo_hi.
+#include "lkb_kernels.h"
+
+namespace lkb {
+
+template <typename E> struct Coef7 { E c[7]; };
+
+template <typename E, int PW> struct PackOps {
+    using P = Pack<E, PW>;
+    static LKB_DI P ld(const E* p) {
+        if constexpr (sizeof(P) == 16) return ld_pack_nc<P>(p);
+        else { P r;
+#pragma unroll
+            for (int e = 0; e < PW; ++e) r.v[e] = __ldg(p + e);
+            return r; }
+    }
+    static LKB_DI void st(E* p, const P& v) {
+        if constexpr (sizeof(P) == 16) st_pack(p, v);
+        else {
+#pragma unroll
+            for (int e = 0; e < PW; ++e) p[e] = v.v[e];
+        }
+    }
+    static LKB_DI P zero() { P r;
+#pragma unroll
+        for (int e = 0; e < PW; ++e) r.v[e] = zero_v(E());
+        return r; }
+};
+
+// One CTA = 256 threads side by side along x (256*PW points of one grid row), marching RY rows
+// in y with the south/centre/north packs held in registers: every x element is loaded once per
+// CTA (+2 halo rows per RY rows, +2 scalars per pack that hit L1).  HBM traffic ~ 2*n*s.
+template <int K, int PW, int DIM>
+__global__ void __launch_bounds__(256)
+k_stencil(const typename Tr<K>::E* __restrict__ x, typename Tr<K>::E* __restrict__ y,
+          int64_t nx, int64_t ny, int64_t nz, Coef7<typename Tr<K>::E> cf,
+          const typename Tr<K>::E* __restrict__ halo_lo, const typename Tr<K>::E* __restrict__ halo_hi,
+          const int* __restrict__ flags)
+{
+    using E = typename Tr<K>::E;
+    using PO = PackOps<E, PW>;
+    using P = typename PO::P;
+    constexpr int RY = 16;
+    if (flags && flags[F_STOP]) return;
+    const int64_t npk_row = nx / PW;
+    const int64_t ip = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ip >= npk_row) return;
+    const int64_t i0 = ip * PW;
+    const int64_t nyb = (ny + RY - 1) / RY;
+    const int64_t k = (DIM == 3) ? (int64_t)blockIdx.y / nyb : 0;
+    const int64_t j0 = ((int64_t)blockIdx.y % nyb) * RY;
+    const int64_t j1 = min(ny, j0 + RY);
+    const int64_t plane = nx * ny;
+    const E* xk = x + k * plane;
+
+    auto getrow = [&](int64_t j) -> P {
+        if (DIM == 2) {
+            if (j < 0) return halo_lo ? PO::ld(halo_lo + i0) : PO::zero();
+            if (j >= ny) return halo_hi ? PO::ld(halo_hi + i0) : PO::zero();
+        } else {
+            if (j < 0 || j >= ny) return PO::zero();
+        }
+        return PO::ld(xk + j * nx + i0);
+    };
+    P south = getrow(j0 - 1), center = getrow(j0);
+    for (int64_t j = j0; j < j1; ++j) {
+        const P north = getrow(j + 1);
+        const int64_t p = j * nx + i0;
+        const E west = i0 > 0 ? __ldg(xk + p - 1) : zero_v(E());
+        const E east = (i0 + PW < nx) ? __ldg(xk + p + PW) : zero_v(E());
+        P down, up;
+        if (DIM == 3) {
+            down = (k > 0) ? PO::ld(xk + p - plane) : (halo_lo ? PO::ld(halo_lo + p) : PO::zero());
+            up = (k < nz - 1) ? PO::ld(xk + p + plane) : (halo_hi ? PO::ld(halo_hi + p) : PO::zero());
+        }
+        P out;
+#pragma unroll
+        for (int e = 0; e < PW; ++e) {
+            E s = mul_v(cf.c[0], center.v[e]);
+            fmacc(s, (e > 0 ? center.v[e > 0 ? e - 1 : 0] : west), cf.c[1]);
+            fmacc(s, (e < PW - 1 ? center.v[e < PW - 1 ? e + 1 : 0] : east), cf.c[2]);
+            fmacc(s, south.v[e], cf.c[3]);
+            fmacc(s, north.v[e], cf.c[4]);
+            if (DIM == 3) { fmacc(s, down.v[e], cf.c[5]); fmacc(s, up.v[e], cf.c[6]); }
+            out.v[e] = s;
+        }
+        PO::st(y + k * plane + p, out);
+        south = center; center = north;
+    }
+}
+
+template <int K, int PW, int DIM>
+static void stencil_launch(cudaStream_t s, const StencilArgs& a, const void* x, void* y, bool trans, const int* flags) {
+    using E = typename Tr<K>::E;
+    Coef7<E> cf;
+    Scalar c[7];
+    for (int q = 0; q < 7; ++q) c[q] = a.coef[q];
+    if (trans) {  // A^H of a constant-coefficient stencil: swap +/- neighbours, conjugate
+        Scalar t;
+        t = c[1]; c[1] = c[2]; c[2] = t; t = c[3]; c[3] = c[4]; c[4] = t; t = c[5]; c[5] = c[6]; c[6] = t;
+        for (int q = 0; q < 7; ++q) c[q].im = -c[q].im;
+    }
+    for (int q = 0; q < 7; ++q) from_scalar(c[q], cf.c[q]);
+    const int64_t npk_row = a.nx / PW;
+    const int64_t nyb = (a.ny + 15) / 16;
+    dim3 grid((unsigned)((npk_row + 255) / 256), (unsigned)(nyb * (DIM == 3 ? a.nz : 1)));
+    k_stencil<K, PW, DIM><<<grid, 256, 0, s>>>((const E*)x, (E*)y, a.nx, a.ny, a.nz, cf,
+                                               (const E*)a.halo_lo, (const E*)a.halo_hi, flags);
+}
+
+template <int K>
+static void stencil_t(cudaStream_t s, const StencilArgs& a, const void* x, void* y, bool trans, const int* flags) {
+    constexpr int EPP = Tr<K>::EPP;
+    const bool vec = (a.nx % EPP == 0);
+    if (a.dim == 2) {
+        if (vec) stencil_launch<K, EPP, 2>(s, a, x, y, trans, flags);
+        else stencil_launch<K, 1, 2>(s, a, x, y, trans, flags);
+    } else {
+        if (vec) stencil_launch<K, EPP, 3>(s, a, x, y, trans, flags);
+        else stencil_launch<K, 1, 3>(s, a, x, y, trans, flags);
+    }
+}
+void launch_stencil(int kind, cudaStream_t s, const StencilArgs& a, const void* x, void* y, bool trans,
+                    const int* flags, int) {
+    switch (kind) {
+        case KS: stencil_t<KS>(s, a, x, y, trans, flags); break;
+        case KD: stencil_t<KD>(s, a, x, y, trans, flags); break;
+        case KC: stencil_t<KC>(s, a, x, y, trans, flags); break;
+        default: stencil_t<KZ>(s, a, x, y, trans, flags); break;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// CSR SpMV.  LPR lanes cooperate on one row (LPR = 32: warp-per-row; LPR < 32: vector-per-row
+// for short rows).  Fixed shuffle tree => deterministic.  rmatvec uses an explicit transposed
+// copy built at operator creation (no atomics), with conj_vals for A^H.
+// ------------------------------------------------------------------------------------------
+template <int K, int LPR>
+__global__ void __launch_bounds__(256)
+k_csr(int64_t m, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+      const typename Tr<K>::E* __restrict__ val, const typename Tr<K>::E* __restrict__ x,
+      typename Tr<K>::E* __restrict__ y, bool conj_vals, const int* __restrict__ flags)
+{
+    using E = typename Tr<K>::E;
+    if (flags && flags[F_STOP]) return;
+    const int sub = threadIdx.x % LPR;
+    const int64_t rows_per_cta = 256 / LPR;
+    for (int64_t row = (int64_t)blockIdx.x * rows_per_cta + threadIdx.x / LPR; row < m;
+         row += (int64_t)gridDim.x * rows_per_cta) {
+        const int64_t q0 = rowptr[row], q1 = rowptr[row + 1];
+        E acc = zero_v(E());
+        for (int64_t q = q0 + sub; q < q1; q += LPR) {
+            E a = __ldg(val + q);
+            if (conj_vals) a = conj_v(a);
+            fmacc(acc, a, __ldg(x + __ldg(col + q)));
+        }
+        typename Tr<K>::W wv = widen(acc);
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) {
+            if constexpr (Tr<K>::cplx) {
+                wv.x += __shfl_down_sync(0xffffffffu, wv.x, o, LPR);
+                wv.y += __shfl_down_sync(0xffffffffu, wv.y, o, LPR);
+            } else {
+                wv += __shfl_down_sync(0xffffffffu, wv, o, LPR);
+            }
+        }
+        if (sub == 0) { E r; narrow(wv, r); y[row] = r; }
+    }
+}
+
+template <int K>
+static void csr_t(cudaStream_t s, int64_t m, const int64_t* rowptr, const int32_t* col, const void* val,
+                  const void* x, void* y, bool conj_vals, const int* flags, int sms, int lpr) {
+    using E = typename Tr<K>::E;
+    auto grid = [&](int L) { int64_t nb = (m * L + 255) / 256; if (nb < 1) nb = 1; if (nb > (int64_t)sms * 16) nb = (int64_t)sms * 16; return (int)nb; };
+    if (lpr >= 32)      k_csr<K, 32><<<grid(32), 256, 0, s>>>(m, rowptr, col, (const E*)val, (const E*)x, (E*)y, conj_vals, flags);
+    else if (lpr >= 16) k_csr<K, 16><<<grid(16), 256, 0, s>>>(m, rowptr, col, (const E*)val, (const E*)x, (E*)y, conj_vals, flags);
+    else if (lpr >= 8)  k_csr<K, 8><<<grid(8), 256, 0, s>>>(m, rowptr, col, (const E*)val, (const E*)x, (E*)y, conj_vals, flags);
+    else                k_csr<K, 4><<<grid(4), 256, 0, s>>>(m, rowptr, col, (const E*)val, (const E*)x, (E*)y, conj_vals, flags);
+}
+// lanes per row are chosen by the caller from the average row length and passed in `sms >> 16`
+void launch_csr(int kind, cudaStream_t s, int64_t m, const int64_t* rowptr, const int32_t* col, const void* val,
+                const void* x, void* y, bool conj_vals, const int* flags, int sms_lpr) {
+    const int sms = sms_lpr & 0xffff, lpr = sms_lpr >> 16;
+    switch (kind) {
+        case KS: csr_t<KS>(s, m, rowptr, col, val, x, y, conj_vals, flags, sms, lpr); break;
+        case KD: csr_t<KD>(s, m, rowptr, col, val, x, y, conj_vals, flags, sms, lpr); break;
+        case KC: csr_t<KC>(s, m, rowptr, col, val, x, y, conj_vals, flags, sms, lpr); break;
+        default: csr_t<KZ>(s, m, rowptr, col, val, x, y, conj_vals, flags, sms, lpr); break;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// dense_linop (AbstractLinops.fypp:608-671, gemv): only the n = 128 plumbing config uses it.
+template <int K>
+__global__ void k_dense(int64_t m, int64_t n, const typename Tr<K>::E* __restrict__ a,
+                        const typename Tr<K>::E* __restrict__ x, typename Tr<K>::E* __restrict__ y, bool trans,
+                        const int* __restrict__ flags)
+{
+    using E = typename Tr<K>::E;
+    if (flags && flags[F_STOP]) return;
+    if (!trans) {
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+            E s = zero_v(E());
+            for (int64_t j = 0; j < n; ++j) fmacc(s, a[i + m * j], x[j]);
+            y[i] = s;
+        }
+    } else {
+        // one warp per output column
+        const int lane = threadIdx.x & 31;
+        for (int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n; j += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+            E s = zero_v(E());
+            for (int64_t i = lane; i < m; i += 32) fma_conj(s, a[i + m * j], x[i]);
+            typename Tr<K>::W wv = warp_sum(widen(s));
+            if (lane == 0) { E r; narrow(wv, r); y[j] = r; }
+        }
+    }
+}
+void launch_dense(int kind, cudaStream_t s, int64_t m, int64_t n, const void* a, const void* x, void* y, bool trans,
+                  const int* flags) {
+    const int64_t work = trans ? n * 32 : m;
+    int nb = (int)((work + 127) / 128); if (nb < 1) nb = 1; if (nb > 4096) nb = 4096;
+    switch (kind) {
+        case KS: k_dense<KS><<<nb, 128, 0, s>>>(m, n, (const float*)a, (const float*)x, (float*)y, trans, flags); break;
+        case KD: k_dense<KD><<<nb, 128, 0, s>>>(m, n, (const double*)a, (const double*)x, (double*)y, trans, flags); break;
+        case KC: k_dense<KC><<<nb, 128, 0, s>>>(m, n, (const float2*)a, (const float2*)x, (float2*)y, trans, flags); break;
+        default: k_dense<KZ><<<nb, 128, 0, s>>>(m, n, (const double2*)a, (const double2*)x, (double2*)y, trans, flags); break;
+    }
+}
+
+}  // namespace lkb

@@ -1,0 +1,268 @@
+// kernels_vec.cu -- single-vector TBPs of the device abstract_vector (axpby, scal, rand, ...)
+// and the O(kdim) scalar kernels that keep the Hessenberg / tridiagonal / bidiagonal update and
+// the breakdown decision on the device, so a whole factorisation can run as one CUDA graph.
+//
+// Reference semantics: src/AbstractTypes/AbstractVectors.fypp:295-381 (deferred TBPs),
+// :424-460 (norm/sub/chsgn), src/Krylov/qr.fypp:137-164, arnoldi.fypp:59-71,
+// lanczos.fypp:29-40, golub_kahan.fypp:37-59.
+#include "lkb_kernels.h"
+#include "lkb_rng.h"
+
+namespace lkb {
+
+static inline int ew_grid(int64_t npk, int sms) {
+    int64_t nb = (npk + 255) / 256;
+    if (nb < 1) nb = 1;
+    if (nb > (int64_t)sms * 8) nb = (int64_t)sms * 8;
+    return (int)nb;
+}
+
+// y = alpha*x + beta*y ; beta == 0 => overwrite without reading y (copy semantics,
+// AbstractVectors.fypp:717-723: `copy` is axpby(1, from, 0) on an intent(out) target).
+template <int K, bool BETA0>
+__global__ void __launch_bounds__(256)
+k_axpby(typename Tr<K>::E alpha, const typename Tr<K>::E* __restrict__ x, typename Tr<K>::E beta,
+        typename Tr<K>::E* __restrict__ y, int64_t n)
+{
+    using E = typename Tr<K>::E;
+    constexpr int EPP = Tr<K>::EPP;
+    using P = Pack<E, EPP>;
+    const int64_t npk = n / EPP;
+    for (int64_t pk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pk < npk; pk += (int64_t)gridDim.x * blockDim.x) {
+        const P xv = ld_pack_nc<P>(x + pk * EPP);
+        P yv;
+        if (!BETA0) yv = ld_pack<P>(y + pk * EPP);
+#pragma unroll
+        for (int e = 0; e < EPP; ++e) {
+            E r = mul_v(alpha, xv.v[e]);
+            if (!BETA0) r = add_v(r, mul_v(beta, yv.v[e]));
+            yv.v[e] = r;
+        }
+        st_pack(y + pk * EPP, yv);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int64_t t = npk * EPP; t < n; ++t) {
+            E r = mul_v(alpha, x[t]);
+            if (!BETA0) r = add_v(r, mul_v(beta, y[t]));
+            y[t] = r;
+        }
+}
+
+// y += sgn * (*alpha) * x, alpha on the device in W precision
+template <int K>
+__global__ void __launch_bounds__(256)
+k_axpy_dev(const typename Tr<K>::W* __restrict__ alpha_dev, double sgn, const typename Tr<K>::E* __restrict__ x,
+           typename Tr<K>::E* __restrict__ y, int64_t n, const int* __restrict__ flags)
+{
+    using E = typename Tr<K>::E;
+    constexpr int EPP = Tr<K>::EPP;
+    using P = Pack<E, EPP>;
+    if (flags && flags[F_STOP]) return;
+    E alpha; narrow(*alpha_dev, alpha);
+    alpha = rscale(alpha, (typename Tr<K>::Rl)sgn);
+    const int64_t npk = n / EPP;
+    for (int64_t pk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pk < npk; pk += (int64_t)gridDim.x * blockDim.x) {
+        const P xv = ld_pack_nc<P>(x + pk * EPP);
+        P yv = ld_pack<P>(y + pk * EPP);
+#pragma unroll
+        for (int e = 0; e < EPP; ++e) fmacc(yv.v[e], xv.v[e], alpha);
+        st_pack(y + pk * EPP, yv);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int64_t t = npk * EPP; t < n; ++t) { E a = y[t]; fmacc(a, x[t], alpha); y[t] = a; }
+}
+
+template <int K>
+__global__ void __launch_bounds__(256)
+k_scal(typename Tr<K>::E alpha, typename Tr<K>::E* __restrict__ x, int64_t n)
+{
+    using E = typename Tr<K>::E;
+    constexpr int EPP = Tr<K>::EPP;
+    using P = Pack<E, EPP>;
+    const int64_t npk = n / EPP;
+    for (int64_t pk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pk < npk; pk += (int64_t)gridDim.x * blockDim.x) {
+        P xv = ld_pack<P>(x + pk * EPP);
+#pragma unroll
+        for (int e = 0; e < EPP; ++e) xv.v[e] = mul_v(xv.v[e], alpha);
+        st_pack(x + pk * EPP, xv);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int64_t t = npk * EPP; t < n; ++t) x[t] = mul_v(x[t], alpha);
+}
+
+// x *= *inv (real scalar on the device).  Gate: (!stop || info == kstep) && !refill.
+template <int K>
+__global__ void __launch_bounds__(256)
+k_scale_dev(typename Tr<K>::E* __restrict__ x, int64_t n, const double* __restrict__ inv_dev,
+            const int* __restrict__ flags, int kstep)
+{
+    using E = typename Tr<K>::E;
+    using Rl = typename Tr<K>::Rl;
+    constexpr int EPP = Tr<K>::EPP;
+    using P = Pack<E, EPP>;
+    if (flags) {
+        if (flags[F_STOP] && flags[F_INFO] != kstep) return;
+        if (flags[F_REFILL]) return;
+    }
+    const Rl inv = (Rl)(*inv_dev);
+    if (inv == (Rl)1) return;
+    const int64_t npk = n / EPP;
+    for (int64_t pk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pk < npk; pk += (int64_t)gridDim.x * blockDim.x) {
+        P xv = ld_pack<P>(x + pk * EPP);
+#pragma unroll
+        for (int e = 0; e < EPP; ++e) xv.v[e] = rscale(xv.v[e], inv);
+        st_pack(x + pk * EPP, xv);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int64_t t = npk * EPP; t < n; ++t) x[t] = rscale(x[t], inv);
+}
+
+template <int K>
+__global__ void __launch_bounds__(256)
+k_fill(typename Tr<K>::E* __restrict__ x, int64_t n, int64_t row0, int dist, uint64_t seed_mixed)
+{
+    using E = typename Tr<K>::E;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t g = (uint64_t)(row0 + i);
+        Scalar s;
+        s.re = dist == 0 ? rng_normal(seed_mixed, g, 0) : rng_uniform(seed_mixed, g, 0);
+        s.im = 0.0;
+        if (Tr<K>::cplx) s.im = dist == 0 ? rng_normal(seed_mixed, g, 1) : rng_uniform(seed_mixed, g, 1);
+        E v; from_scalar(s, v);
+        x[i] = v;
+    }
+}
+
+// Column update of H / T / B after the second CGS pass; one CTA.
+//   hcol[0..j) = c1 + c2 (if c1),  beta = sqrt(|nrm2|),  hcol[j] = beta (or 0), inv = 1/beta
+template <int K>
+__global__ void k_update(const typename Tr<K>::W* __restrict__ c1, const typename Tr<K>::W* __restrict__ c2, int j,
+                         const typename Tr<K>::W* __restrict__ nrm2, typename Tr<K>::E* __restrict__ hcol,
+                         double tol, double atol, double* __restrict__ inv_dev, int* __restrict__ flags,
+                         int kstep, int mode)
+{
+    using E = typename Tr<K>::E;
+    using W = typename Tr<K>::W;
+    if (flags[F_STOP]) return;
+    if (c1 && hcol)
+        for (int i = threadIdx.x; i < j; i += blockDim.x) {
+            W a = c1[i];
+            if (c2) wadd(a, c2[i]);
+            narrow(a, hcol[i]);
+        }
+    if (threadIdx.x == 0) {
+        const double beta = sqrt(fabs(wreal(nrm2[0])));
+        if (beta != beta) flags[F_NAN] = 1;
+        Scalar hb; hb.re = beta; hb.im = 0.0;
+        double inv = 1.0;
+        if (mode == 0) {
+            // qr_no_pivoting (p = 1) uses its own default tol = atol for the refill decision
+            // (qr.fypp:125,146), arnoldi then tests |H(k+1,k)| < tol (arnoldi.fypp:59-71).
+            double hkk = beta;
+            if (beta < atol) { hkk = 0.0; flags[F_REFILL] = 1; }
+            else inv = 1.0 / beta;
+            hb.re = hkk;
+            if (hkk < tol) { flags[F_STOP] = 1; flags[F_INFO] = kstep; }
+        } else if (mode == 1) {          // lanczos.fypp:29-40: beta < tol => exit, no scaling
+            if (beta < tol) { flags[F_STOP] = 1; flags[F_INFO] = kstep; flags[F_REFILL] = 1; }
+            else inv = 1.0 / beta;
+        } else if (mode == 2) {          // golub_kahan.fypp:37-43: scale iff beta > tol
+            if (beta > tol) inv = 1.0 / beta;
+            else { flags[F_STOP] = 1; flags[F_INFO] = kstep; flags[F_REFILL] = 1; }
+        } else {                         // plain norm: no decision
+            inv = beta > 0.0 ? 1.0 / beta : 1.0;
+        }
+        if (hcol) { E h; from_scalar(hb, h); hcol[j] = h; }
+        *inv_dev = inv;
+    }
+}
+
+__global__ void k_gsinfo(const double* __restrict__ ww, double atol, int* __restrict__ flags) {
+    if (flags[F_STOP]) return;
+    flags[F_GSINFO] = (sqrt(fabs(ww[0])) < atol) ? 1 : 0;
+}
+
+template <int K>
+__global__ void k_wadd(const typename Tr<K>::W* a, const typename Tr<K>::W* b, typename Tr<K>::W* out, int n,
+                       const int* flags) {
+    if (flags && flags[F_STOP]) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        typename Tr<K>::W t = a[i]; wadd(t, b[i]); out[i] = t;
+    }
+}
+template <int K>
+__global__ void k_narrow(const typename Tr<K>::W* src, typename Tr<K>::E* dst, int n, const int* flags) {
+    if (flags && flags[F_STOP]) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) narrow(src[i], dst[i]);
+}
+
+// ------------------------------------------------------------------------------------------
+#define LKB_DISPATCH(kind, ...)                                \
+    switch (kind) {                                            \
+        case KS: { constexpr int K = KS; __VA_ARGS__; } break; \
+        case KD: { constexpr int K = KD; __VA_ARGS__; } break; \
+        case KC: { constexpr int K = KC; __VA_ARGS__; } break; \
+        default: { constexpr int K = KZ; __VA_ARGS__; } break; \
+    }
+
+void launch_axpby(int kind, cudaStream_t s, Scalar alpha, const void* x, Scalar beta, void* y, int64_t n, int sms) {
+    const bool b0 = (beta.re == 0.0 && beta.im == 0.0);
+    LKB_DISPATCH(kind, {
+        using E = typename Tr<K>::E;
+        E a, b; from_scalar(alpha, a); from_scalar(beta, b);
+        const int g = ew_grid(n / Tr<K>::EPP, sms);
+        if (b0) k_axpby<K, true><<<g, 256, 0, s>>>(a, (const E*)x, b, (E*)y, n);
+        else    k_axpby<K, false><<<g, 256, 0, s>>>(a, (const E*)x, b, (E*)y, n);
+    });
+}
+void launch_axpy_dev(int kind, cudaStream_t s, const void* alpha_dev, double sgn, const void* x, void* y, int64_t n,
+                     const int* flags, int sms) {
+    LKB_DISPATCH(kind, {
+        using E = typename Tr<K>::E; using W = typename Tr<K>::W;
+        k_axpy_dev<K><<<ew_grid(n / Tr<K>::EPP, sms), 256, 0, s>>>((const W*)alpha_dev, sgn, (const E*)x, (E*)y, n, flags);
+    });
+}
+void launch_scal(int kind, cudaStream_t s, Scalar alpha, void* x, int64_t n, int sms) {
+    LKB_DISPATCH(kind, {
+        using E = typename Tr<K>::E;
+        E a; from_scalar(alpha, a);
+        k_scal<K><<<ew_grid(n / Tr<K>::EPP, sms), 256, 0, s>>>(a, (E*)x, n);
+    });
+}
+void launch_scale_dev(int kind, cudaStream_t s, void* x, int64_t n, const void* inv_dev, const int* flags, int kstep, int sms) {
+    LKB_DISPATCH(kind, {
+        using E = typename Tr<K>::E;
+        k_scale_dev<K><<<ew_grid(n / Tr<K>::EPP, sms), 256, 0, s>>>((E*)x, n, (const double*)inv_dev, flags, kstep);
+    });
+}
+void launch_fill(int kind, cudaStream_t s, void* x, int64_t n, int64_t row0, int dist, uint64_t seed, int sms) {
+    LKB_DISPATCH(kind, {
+        using E = typename Tr<K>::E;
+        k_fill<K><<<ew_grid(n, sms), 256, 0, s>>>((E*)x, n, row0, dist, mix64(seed));
+    });
+}
+void launch_update(int kind, cudaStream_t s, const void* c1, const void* c2, int j, const void* nrm2, void* hcol,
+                   double tol, double atol, void* inv_dev, int* flags, int kstep, int mode) {
+    LKB_DISPATCH(kind, {
+        using E = typename Tr<K>::E; using W = typename Tr<K>::W;
+        k_update<K><<<1, 128, 0, s>>>((const W*)c1, (const W*)c2, j, (const W*)nrm2, (E*)hcol, tol, atol,
+                                      (double*)inv_dev, flags, kstep, mode);
+    });
+}
+void launch_gsinfo(cudaStream_t s, const void* ww, int, double atol, int* flags) {
+    k_gsinfo<<<1, 1, 0, s>>>((const double*)ww, atol, flags);
+}
+void launch_wadd(int kind, cudaStream_t s, const void* a, const void* b, void* out, int n, const int* flags) {
+    LKB_DISPATCH(kind, {
+        using W = typename Tr<K>::W;
+        k_wadd<K><<<1, 256, 0, s>>>((const W*)a, (const W*)b, (W*)out, n, flags);
+    });
+}
+void launch_narrow(int kind, cudaStream_t s, const void* src, void* dst, int n, const int* flags) {
+    LKB_DISPATCH(kind, {
+        using E = typename Tr<K>::E; using W = typename Tr<K>::W;
+        k_narrow<K><<<1, 256, 0, s>>>((const W*)src, (E*)dst, n, flags);
+    });
+}
+
+}  // namespace lkb

@@ -1,0 +1,574 @@
+// lkb_core.cu -- context, device abstract_vector / basis objects and abstract_linop objects
+// behind the C ABI of include/lkb.h.  No CPU fallback: every entry point needs a CUDA device.
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include "../../include/lkb.h"
+#include "lkb_internal.h"
+
+using namespace lkb;
+
+namespace lkb {
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+}
+
+static NcclApi g_nccl;
+static bool g_nccl_tried = false;
+NcclApi* nccl_api() {
+    if (g_nccl.handle) return &g_nccl;
+    if (g_nccl_tried) return nullptr;
+    g_nccl_tried = true;
+    const char* cands[] = { getenv("LKB_NCCL_LIB"), "libnccl.so.2", "libnccl.so",
+                            "/usr/local/cuda/lib64/libnccl.so.2", "/usr/lib/x86_64-linux-gnu/libnccl.so.2" };
+    void* h = nullptr;
+    for (const char* p : cands) { if (!p) continue; h = dlopen(p, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+    if (!h) { set_error("cannot dlopen libnccl (set LKB_NCCL_LIB): %s", dlerror()); return nullptr; }
+#define LKB_SYM(field, name) *(void**)(&g_nccl.field) = dlsym(h, name); if (!g_nccl.field) { set_error("missing %s", name); return nullptr; }
+    LKB_SYM(GetUniqueId, "ncclGetUniqueId") LKB_SYM(CommInitRank, "ncclCommInitRank") LKB_SYM(CommDestroy, "ncclCommDestroy")
+    LKB_SYM(AllReduce, "ncclAllReduce") LKB_SYM(Send, "ncclSend") LKB_SYM(Recv, "ncclRecv")
+    LKB_SYM(GroupStart, "ncclGroupStart") LKB_SYM(GroupEnd, "ncclGroupEnd") LKB_SYM(GetErrorString, "ncclGetErrorString")
+#undef LKB_SYM
+    g_nccl.handle = h;
+    return &g_nccl;
+}
+#define LKB_NCCL(call) do { int r_ = (call); if (r_ != 0) { \
+    lkb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, nccl_api()->GetErrorString(r_)); return LKB_ERR_NCCL; } } while (0)
+
+int check_launch(lkb_ctx_s*, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("kernel launch failed (%s): %s", what, cudaGetErrorString(e)); return LKB_ERR_CUDA; }
+    return 0;
+}
+
+void prof_begin(lkb_ctx_s* c, int cls) {
+    if (!c->profile || c->capturing) return;
+    lkb_ctx_s::ProfEv ev; ev.cls = cls;
+    cudaEventCreate(&ev.a); cudaEventCreate(&ev.b);
+    cudaEventRecord(ev.a, c->stream);
+    c->prof_evs.push_back(ev);
+}
+void prof_end(lkb_ctx_s* c, int cls, int nlaunch) {
+    c->launches += nlaunch;
+    if (!c->profile || c->capturing) return;
+    cudaEventRecord(c->prof_evs.back().b, c->stream);
+    c->prof_n[cls] += nlaunch;
+}
+int prof_collect(lkb_ctx_s* c) {
+    if (c->prof_evs.empty()) return 0;
+    LKB_CUDA(cudaStreamSynchronize(c->stream));
+    for (auto& ev : c->prof_evs) {
+        float ms = 0.f; cudaEventElapsedTime(&ms, ev.a, ev.b);
+        c->prof_ms[ev.cls] += ms;
+        cudaEventDestroy(ev.a); cudaEventDestroy(ev.b);
+    }
+    c->prof_evs.clear();
+    return 0;
+}
+
+static int grow(void** p, size_t* cur, size_t need) {
+    if (*cur >= need) return 0;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cur = 0;
+    LKB_CUDA(cudaMalloc(p, need));
+    *cur = need;
+    return 0;
+}
+int ensure_ws(lkb_ctx_s* c, int jp) {
+    if (c->capturing) return 0;   // sized before capture begins
+    const size_t need = (size_t)MAX_ROWBLOCKS * (size_t)jp * 16;
+    LKB_TRY(grow(&c->partial, &c->partial_bytes, std::max(need, (size_t)MAX_ROWBLOCKS * 16 * 8)));
+    if (c->cbuf_len < (size_t)jp) {
+        size_t len = std::max((size_t)jp, (size_t)272);
+        if (c->c1) cudaFree(c->c1); if (c->c2) cudaFree(c->c2); if (c->tmpw) cudaFree(c->tmpw);
+        c->c1 = c->c2 = c->tmpw = nullptr; c->cbuf_len = 0;
+        LKB_CUDA(cudaMalloc(&c->c1, len * 16)); LKB_CUDA(cudaMalloc(&c->c2, len * 16)); LKB_CUDA(cudaMalloc(&c->tmpw, len * 16));
+        c->cbuf_len = len;
+    }
+    return 0;
+}
+int ensure_hstage(lkb_ctx_s* c, size_t bytes) {
+    if (c->hstage_bytes >= bytes) return 0;
+    if (c->hstage) cudaFreeHost(c->hstage);
+    c->hstage = nullptr; c->hstage_bytes = 0;
+    LKB_CUDA(cudaMallocHost(&c->hstage, bytes));
+    c->hstage_bytes = bytes;
+    return 0;
+}
+int ensure_Hd(lkb_ctx_s* c, size_t bytes) { return grow(&c->Hd, &c->Hd_bytes, bytes); }
+int ensure_coefd(lkb_ctx_s* c, size_t bytes) { return grow(&c->coefd, &c->coefd_bytes, bytes); }
+
+int allreduce_w(lkb_ctx_s* c, void* buf, size_t ndoubles) {
+    if (c->world == 1) return 0;
+    NcclApi* api = nccl_api();
+    if (!api) return LKB_ERR_NCCL;
+    LKB_NCCL(api->AllReduce(buf, buf, ndoubles, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->comm, c->stream));
+    return 0;
+}
+static uint64_t g_uid = 0;
+uint64_t next_uid() { return ++g_uid; }
+uint64_t next_seed(lkb_ctx_s* c) { return c->seed + 0x9E3779B97F4A7C15ULL * (++c->seed_calls); }
+
+int fetch_flags(lkb_ctx_s* c, int* host_flags) {
+    LKB_TRY(ensure_hstage(c, 4096));
+    LKB_CUDA(cudaMemcpyAsync(c->hstage, c->flags, F_COUNT * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    LKB_CUDA(cudaStreamSynchronize(c->stream));
+    memcpy(host_flags, c->hstage, F_COUNT * sizeof(int));
+    return 0;
+}
+
+int norm2_enqueue(lkb_ctx_s* c, int kind, const void* w, int64_t n, const int* flags) {
+    LKB_TRY(ensure_ws(c, 1));
+    prof_begin(c, PC_DOT);
+    launch_multidot(kind, c->stream, w, n, 0, w, n, c->partial, c->nrm2, c->counter, flags, c->sms);
+    prof_end(c, PC_DOT, 1);
+    LKB_TRY(check_launch(c, "norm2"));
+    return allreduce_w(c, c->nrm2, 1);
+}
+int vec_norm_sync(lkb_ctx_s* c, int kind, const void* w, int64_t n, double* out) {
+    LKB_TRY(norm2_enqueue(c, kind, w, n, nullptr));
+    LKB_TRY(ensure_hstage(c, 4096));
+    LKB_CUDA(cudaMemcpyAsync(c->hstage, c->nrm2, 16, cudaMemcpyDeviceToHost, c->stream));
+    LKB_CUDA(cudaStreamSynchronize(c->stream));
+    *out = sqrt(fabs(*(double*)c->hstage));
+    return 0;
+}
+int vec_dot_sync(lkb_ctx_s* c, int kind, const void* x, const void* y, int64_t n, Scalar* out) {
+    LKB_TRY(ensure_ws(c, 2));
+    prof_begin(c, PC_DOT);
+    launch_multidot(kind, c->stream, x, n, 1, y, n, c->partial, c->tmpw, c->counter, nullptr, c->sms);
+    prof_end(c, PC_DOT, 1);
+    LKB_TRY(check_launch(c, "dot"));
+    LKB_TRY(allreduce_w(c, c->tmpw, kind_cplx(kind) ? 2 : 1));
+    LKB_TRY(ensure_hstage(c, 4096));
+    LKB_CUDA(cudaMemcpyAsync(c->hstage, c->tmpw, 16, cudaMemcpyDeviceToHost, c->stream));
+    LKB_CUDA(cudaStreamSynchronize(c->stream));
+    out->re = ((double*)c->hstage)[0];
+    out->im = kind_cplx(kind) ? ((double*)c->hstage)[1] : 0.0;
+    return 0;
+}
+}  // namespace lkb
+
+static Scalar scalar_from(int kind, const void* p) {
+    Scalar s{0, 0};
+    switch (kind) {
+        case KS: s.re = *(const float*)p; break;
+        case KD: s.re = *(const double*)p; break;
+        case KC: s.re = ((const float*)p)[0]; s.im = ((const float*)p)[1]; break;
+        default: s.re = ((const double*)p)[0]; s.im = ((const double*)p)[1]; break;
+    }
+    return s;
+}
+static void scalar_to(int kind, Scalar s, void* p) {
+    switch (kind) {
+        case KS: *(float*)p = (float)s.re; break;
+        case KD: *(double*)p = s.re; break;
+        case KC: ((float*)p)[0] = (float)s.re; ((float*)p)[1] = (float)s.im; break;
+        default: ((double*)p)[0] = s.re; ((double*)p)[1] = s.im; break;
+    }
+}
+
+extern "C" {
+
+const char* lkb_last_error(void) { return g_err; }
+
+static int ctx_common(int device, lkb_ctx_s* c) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_error("no CUDA device available (%s): liblkb has no CPU fallback", cudaGetErrorString(e));
+        return LKB_ERR_CUDA;
+    }
+    LKB_CUDA(cudaSetDevice(device));
+    c->dev = device;
+    LKB_CUDA(cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, device));
+    LKB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    LKB_CUDA(cudaMalloc(&c->nrm2, 64));
+    LKB_CUDA(cudaMalloc((void**)&c->inv, 64));
+    LKB_CUDA(cudaMalloc((void**)&c->flags, F_COUNT * sizeof(int)));
+    LKB_CUDA(cudaMalloc((void**)&c->counter, 64));
+    LKB_CUDA(cudaMemset(c->flags, 0, F_COUNT * sizeof(int)));
+    LKB_CUDA(cudaMemset(c->counter, 0, 64));
+    LKB_CUDA(cudaMemset(c->nrm2, 0, 64));
+    LKB_TRY(ensure_ws(c, 272));
+    LKB_TRY(ensure_hstage(c, 1 << 20));
+    return 0;
+}
+
+int lkb_init(int device, lkb_ctx_t* ctx) {
+    if (!ctx) return LKB_ERR_ARG;
+    lkb_ctx_s* c = new lkb_ctx_s();
+    int r = ctx_common(device, c);
+    if (r) { delete c; return r; }
+    *ctx = c;
+    return 0;
+}
+int lkb_nccl_unique_id(void* id128) {
+    NcclApi* api = nccl_api();
+    if (!api) return LKB_ERR_NCCL;
+    LKB_NCCL(api->GetUniqueId(id128));
+    return 0;
+}
+int lkb_init_dist(int device, int rank, int world, const void* id128, lkb_ctx_t* ctx) {
+    if (!ctx || world < 1 || rank < 0 || rank >= world) return LKB_ERR_ARG;
+    lkb_ctx_s* c = new lkb_ctx_s();
+    int r = ctx_common(device, c);
+    if (r) { delete c; return r; }
+    c->rank = rank; c->world = world;
+    if (world > 1) {
+        NcclApi* api = nccl_api();
+        if (!api) { delete c; return LKB_ERR_NCCL; }
+        NcclId id; memcpy(&id, id128, sizeof(id));
+        LKB_NCCL(api->CommInitRank(&c->comm, world, id, rank));
+    }
+    *ctx = c;
+    return 0;
+}
+int lkb_finalize(lkb_ctx_t c) {
+    if (!c) return LKB_ERR_ARG;
+    cudaSetDevice(c->dev);
+    cudaStreamSynchronize(c->stream);
+    for (auto& kv : c->graph_cache) cudaGraphExecDestroy(kv.second.exec);
+    if (c->comm && nccl_api()) nccl_api()->CommDestroy(c->comm);
+    void* bufs[] = { c->partial, c->c1, c->c2, c->tmpw, c->nrm2, c->inv, c->flags, c->counter, c->Hd, c->coefd };
+    for (void* b : bufs) if (b) cudaFree(b);
+    if (c->hstage) cudaFreeHost(c->hstage);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+int lkb_sync(lkb_ctx_t c) { LKB_CUDA(cudaStreamSynchronize(c->stream)); return 0; }
+void* lkb_stream(lkb_ctx_t c) { return (void*)c->stream; }
+int lkb_set_seed(lkb_ctx_t c, uint64_t seed) { c->seed = seed; c->seed_calls = 0; return 0; }
+int lkb_set_graphs(lkb_ctx_t c, int enable) { c->graphs = enable != 0; return 0; }
+int lkb_rank(lkb_ctx_t c) { return c->rank; }
+int lkb_world(lkb_ctx_t c) { return c->world; }
+int lkb_set_profile(lkb_ctx_t c, int enable) {
+    c->profile = enable != 0;
+    for (int i = 0; i < PC_COUNT; ++i) { c->prof_ms[i] = 0; c->prof_n[i] = 0; }
+    return 0;
+}
+int lkb_get_profile(lkb_ctx_t c, double* ms4, int64_t* launches4) {
+    LKB_TRY(prof_collect(c));
+    for (int i = 0; i < PC_COUNT; ++i) { if (ms4) ms4[i] = c->prof_ms[i]; if (launches4) launches4[i] = c->prof_n[i]; }
+    return 0;
+}
+int64_t lkb_kernel_launches(lkb_ctx_t c) { return c->launches; }
+
+// ---- vectors --------------------------------------------------------------------------------
+int lkb_vec_create(lkb_ctx_t c, int kind, int64_t n_local, int64_t n_global, int64_t row0, lkb_vec_t* v) {
+    if (!c || !v || kind < 0 || kind > 3 || n_local < 0) return LKB_ERR_ARG;
+    cudaSetDevice(c->dev);
+    lkb_vec_s* h = new lkb_vec_s{c, kind, n_local, n_global, row0, nullptr, true};
+    size_t bytes = std::max((size_t)n_local * kind_size(kind), (size_t)16);
+    cudaError_t e = cudaMalloc(&h->d, bytes);
+    if (e != cudaSuccess) { delete h; set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return LKB_ERR_ALLOC; }
+    cudaMemsetAsync(h->d, 0, bytes, c->stream);
+    *v = h;
+    return 0;
+}
+int lkb_vec_wrap(lkb_ctx_t c, int kind, int64_t n_local, int64_t n_global, int64_t row0, void* devptr, lkb_vec_t* v) {
+    if (!c || !v || !devptr || ((uintptr_t)devptr & 15)) { set_error("lkb_vec_wrap: pointer must be 16-byte aligned"); return LKB_ERR_ARG; }
+    *v = new lkb_vec_s{c, kind, n_local, n_global, row0, devptr, false};
+    return 0;
+}
+int lkb_vec_clone(lkb_vec_t src, lkb_vec_t* dst) {
+    if (!src || !dst) return LKB_ERR_ARG;
+    LKB_TRY(lkb_vec_create(src->ctx, src->kind, src->n, src->n_global, src->row0, dst));
+    LKB_CUDA(cudaMemcpyAsync((*dst)->d, src->d, (size_t)src->n * kind_size(src->kind), cudaMemcpyDeviceToDevice, src->ctx->stream));
+    return 0;
+}
+int lkb_vec_destroy(lkb_vec_t v) {
+    if (!v) return LKB_ERR_ARG;
+    if (v->owns && v->d) { cudaStreamSynchronize(v->ctx->stream); cudaFree(v->d); }
+    delete v;
+    return 0;
+}
+int lkb_vec_zero(lkb_vec_t v) {
+    LKB_CUDA(cudaMemsetAsync(v->d, 0, (size_t)v->n * kind_size(v->kind), v->ctx->stream));
+    return 0;
+}
+int lkb_vec_fill_random(lkb_vec_t v, int dist, uint64_t seed) {
+    prof_begin(v->ctx, PC_OTHER);
+    launch_fill(v->kind, v->ctx->stream, v->d, v->n, v->row0, dist, seed, v->ctx->sms);
+    prof_end(v->ctx, PC_OTHER, 1);
+    return check_launch(v->ctx, "fill");
+}
+int lkb_vec_rand(lkb_vec_t v, int32_t ifnorm) {
+    LKB_TRY(lkb_vec_fill_random(v, LKB_DIST_NORMAL, next_seed(v->ctx)));
+    if (ifnorm) {
+        double nrm = 0;
+        LKB_TRY(vec_norm_sync(v->ctx, v->kind, v->d, v->n, &nrm));
+        Scalar a{1.0 / nrm, 0.0};
+        launch_scal(v->kind, v->ctx->stream, a, v->d, v->n, v->ctx->sms);
+        v->ctx->launches++;
+        return check_launch(v->ctx, "scal");
+    }
+    return 0;
+}
+int lkb_vec_scal(lkb_vec_t v, const void* alpha) {
+    prof_begin(v->ctx, PC_OTHER);
+    launch_scal(v->kind, v->ctx->stream, scalar_from(v->kind, alpha), v->d, v->n, v->ctx->sms);
+    prof_end(v->ctx, PC_OTHER, 1);
+    return check_launch(v->ctx, "scal");
+}
+int lkb_vec_axpby(const void* alpha, lkb_vec_t x, const void* beta, lkb_vec_t self) {
+    if (!x || !self || x->n != self->n || x->kind != self->kind) { set_error("axpby: size/kind mismatch"); return LKB_ERR_ARG; }
+    prof_begin(self->ctx, PC_OTHER);
+    launch_axpby(self->kind, self->ctx->stream, scalar_from(self->kind, alpha), x->d, scalar_from(self->kind, beta),
+                 self->d, self->n, self->ctx->sms);
+    prof_end(self->ctx, PC_OTHER, 1);
+    return check_launch(self->ctx, "axpby");
+}
+int lkb_vec_dot(lkb_vec_t self, lkb_vec_t vec, void* out) {
+    if (!self || !vec || self->n != vec->n || self->kind != vec->kind) { set_error("dot: size/kind mismatch"); return LKB_ERR_ARG; }
+    Scalar s;
+    LKB_TRY(vec_dot_sync(self->ctx, self->kind, self->d, vec->d, self->n, &s));
+    scalar_to(self->kind, s, out);
+    return 0;
+}
+int lkb_vec_norm(lkb_vec_t v, double* out) { return vec_norm_sync(v->ctx, v->kind, v->d, v->n, out); }
+int64_t lkb_vec_size(lkb_vec_t v) { return v->n_global; }
+int64_t lkb_vec_local_size(lkb_vec_t v) { return v->n; }
+void* lkb_vec_ptr(lkb_vec_t v) { return v->d; }
+int lkb_vec_put(lkb_vec_t v, const void* host) {
+    LKB_CUDA(cudaMemcpyAsync(v->d, host, (size_t)v->n * kind_size(v->kind), cudaMemcpyHostToDevice, v->ctx->stream));
+    LKB_CUDA(cudaStreamSynchronize(v->ctx->stream));
+    return 0;
+}
+int lkb_vec_get(lkb_vec_t v, void* host) {
+    LKB_CUDA(cudaMemcpyAsync(host, v->d, (size_t)v->n * kind_size(v->kind), cudaMemcpyDeviceToHost, v->ctx->stream));
+    LKB_CUDA(cudaStreamSynchronize(v->ctx->stream));
+    return 0;
+}
+
+// ---- basis ----------------------------------------------------------------------------------
+int lkb_basis_create(lkb_ctx_t c, int kind, int64_t n_local, int64_t n_global, int64_t row0, int ncols, lkb_basis_t* b) {
+    if (!c || !b || kind < 0 || kind > 3 || n_local < 0 || ncols < 1) return LKB_ERR_ARG;
+    cudaSetDevice(c->dev);
+    // columns padded to 128 B so every column starts on a full cache line / 16-byte pack boundary
+    const int64_t epl = 128 / (int64_t)kind_size(kind);
+    const int64_t ld = ((std::max<int64_t>(n_local, 1) + epl - 1) / epl) * epl;
+    lkb_basis_s* h = new lkb_basis_s{c, kind, n_local, n_global, row0, ld, ncols, nullptr, next_uid()};
+    const size_t bytes = (size_t)ld * (size_t)ncols * kind_size(kind);
+    cudaError_t e = cudaMalloc(&h->d, bytes);
+    if (e != cudaSuccess) { delete h; set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return LKB_ERR_ALLOC; }
+    cudaMemsetAsync(h->d, 0, bytes, c->stream);
+    *b = h;
+    return 0;
+}
+int lkb_basis_destroy(lkb_basis_t b) {
+    if (!b) return LKB_ERR_ARG;
+    cudaStreamSynchronize(b->ctx->stream);
+    cudaFree(b->d);
+    delete b;
+    return 0;
+}
+int lkb_basis_col(lkb_basis_t b, int i0, lkb_vec_t* view) {
+    if (!b || i0 < 0 || i0 >= b->ncols) { set_error("basis_col: column %d out of range", i0); return LKB_ERR_ARG; }
+    *view = new lkb_vec_s{b->ctx, b->kind, b->n, b->n_global, b->row0, col_ptr(b, i0), false};
+    return 0;
+}
+int lkb_basis_zero(lkb_basis_t b, int col0, int ncols) {
+    if (col0 < 0 || col0 + ncols > b->ncols) return LKB_ERR_ARG;
+    LKB_CUDA(cudaMemsetAsync(col_ptr(b, col0), 0, (size_t)b->ld * ncols * kind_size(b->kind), b->ctx->stream));
+    return 0;
+}
+int lkb_basis_put(lkb_basis_t b, int col0, int ncols, const void* host, int64_t ldhost) {
+    if (col0 < 0 || col0 + ncols > b->ncols) return LKB_ERR_ARG;
+    const size_t es = kind_size(b->kind);
+    LKB_CUDA(cudaMemcpy2DAsync(col_ptr(b, col0), (size_t)b->ld * es, host, (size_t)ldhost * es, (size_t)b->n * es, ncols,
+                               cudaMemcpyHostToDevice, b->ctx->stream));
+    LKB_CUDA(cudaStreamSynchronize(b->ctx->stream));
+    return 0;
+}
+int lkb_basis_get(lkb_basis_t b, int col0, int ncols, void* host, int64_t ldhost) {
+    if (col0 < 0 || col0 + ncols > b->ncols) return LKB_ERR_ARG;
+    const size_t es = kind_size(b->kind);
+    LKB_CUDA(cudaMemcpy2DAsync(host, (size_t)ldhost * es, col_ptr(b, col0), (size_t)b->ld * es, (size_t)b->n * es, ncols,
+                               cudaMemcpyDeviceToHost, b->ctx->stream));
+    LKB_CUDA(cudaStreamSynchronize(b->ctx->stream));
+    return 0;
+}
+int lkb_basis_ncols(lkb_basis_t b) { return b->ncols; }
+int64_t lkb_basis_ld(lkb_basis_t b) { return b->ld; }
+
+// ---- operators ------------------------------------------------------------------------------
+static int stencil_create(lkb_ctx_t c, int kind, int dim, int64_t nx, int64_t ny, int64_t nz, const void* coef,
+                          int64_t slow0, int64_t nslow_local, lkb_op_t* A) {
+    if (!c || !A || !coef || nx < 1 || ny < 1 || nz < 1) return LKB_ERR_ARG;
+    const int64_t nslow = dim == 2 ? ny : nz;
+    if (slow0 < 0 || nslow_local < 1 || slow0 + nslow_local > nslow) { set_error("stencil: bad slab [%lld,+%lld) of %lld", (long long)slow0, (long long)nslow_local, (long long)nslow); return LKB_ERR_ARG; }
+    cudaSetDevice(c->dev);
+    lkb_op_s* op = new lkb_op_s();
+    op->ctx = c; op->type = 1; op->kind = kind; op->uid = next_uid();
+    op->st.dim = dim; op->st.nx = nx;
+    op->st.ny = dim == 2 ? nslow_local : ny;
+    op->st.nz = dim == 2 ? 1 : nslow_local;
+    op->slow0 = slow0; op->nslow_global = nslow;
+    const int ncoef = dim == 2 ? 5 : 7;
+    const size_t es = kind_size(kind);
+    for (int q = 0; q < 7; ++q) op->st.coef[q] = q < ncoef ? scalar_from(kind, (const char*)coef + q * es) : Scalar{0, 0};
+    op->m = op->n = nx * op->st.ny * op->st.nz;
+    op->halo_elems = dim == 2 ? nx : nx * ny;
+    op->st.halo_lo = op->st.halo_hi = nullptr;
+    if (c->world > 1) {
+        LKB_CUDA(cudaMalloc(&op->halo_lo, op->halo_elems * es));
+        LKB_CUDA(cudaMalloc(&op->halo_hi, op->halo_elems * es));
+        if (slow0 > 0) op->st.halo_lo = op->halo_lo;
+        if (slow0 + nslow_local < nslow) op->st.halo_hi = op->halo_hi;
+    }
+    const int64_t gy = ((op->st.ny + 15) / 16) * op->st.nz;
+    if (gy > 65535) { delete op; set_error("stencil: grid too large for this kernel (%lld row groups)", (long long)gy); return LKB_ERR_ARG; }
+    *A = op;
+    return 0;
+}
+int lkb_op_stencil5_create(lkb_ctx_t c, int kind, int64_t nx, int64_t ny, const void* coef5, int64_t slow0,
+                           int64_t nslow_local, lkb_op_t* A) {
+    return stencil_create(c, kind, 2, nx, ny, 1, coef5, slow0, nslow_local, A);
+}
+int lkb_op_stencil7_create(lkb_ctx_t c, int kind, int64_t nx, int64_t ny, int64_t nz, const void* coef7, int64_t slow0,
+                           int64_t nslow_local, lkb_op_t* A) {
+    return stencil_create(c, kind, 3, nx, ny, nz, coef7, slow0, nslow_local, A);
+}
+
+static int pick_lpr(int64_t nnz, int64_t rows) {
+    const double avg = rows > 0 ? (double)nnz / (double)rows : 0.0;
+    return avg >= 48 ? 32 : (avg >= 24 ? 16 : (avg >= 10 ? 8 : 4));
+}
+int lkb_op_csr_create(lkb_ctx_t c, int kind, int64_t m, int64_t n, const int64_t* rowptr, const int32_t* col,
+                      const void* val, lkb_op_t* A) {
+    if (!c || !A || !rowptr || m < 1 || n < 1) return LKB_ERR_ARG;
+    if (c->world > 1) { set_error("csr operators are single-rank in this round (SURVEY 8e: allgather/reduce-scatter path is next)"); return LKB_ERR_ARG; }
+    cudaSetDevice(c->dev);
+    const int64_t nnz = rowptr[m];
+    const size_t es = kind_size(kind);
+    lkb_op_s* op = new lkb_op_s();
+    op->ctx = c; op->type = 3; op->kind = kind; op->m = m; op->n = n; op->uid = next_uid();
+    op->lpr = pick_lpr(nnz, m); op->t_lpr = pick_lpr(nnz, n);
+    LKB_CUDA(cudaMalloc((void**)&op->rowptr, (m + 1) * sizeof(int64_t)));
+    LKB_CUDA(cudaMalloc((void**)&op->col, std::max<int64_t>(nnz, 1) * sizeof(int32_t)));
+    LKB_CUDA(cudaMalloc(&op->val, std::max<int64_t>(nnz, 1) * es));
+    LKB_CUDA(cudaMemcpy(op->rowptr, rowptr, (m + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
+    LKB_CUDA(cudaMemcpy(op->col, col, nnz * sizeof(int32_t), cudaMemcpyHostToDevice));
+    LKB_CUDA(cudaMemcpy(op->val, val, nnz * es, cudaMemcpyHostToDevice));
+    // explicit transpose (counting sort, host) so that rmatvec is a gather, not an atomic scatter
+    std::vector<int64_t> trp(n + 1, 0);
+    for (int64_t q = 0; q < nnz; ++q) trp[col[q] + 1]++;
+    for (int64_t j = 0; j < n; ++j) trp[j + 1] += trp[j];
+    std::vector<int32_t> tcol(std::max<int64_t>(nnz, 1));
+    std::vector<char> tval((size_t)std::max<int64_t>(nnz, 1) * es);
+    {
+        std::vector<int64_t> pos(trp.begin(), trp.end() - 1);
+        for (int64_t i = 0; i < m; ++i)
+            for (int64_t q = rowptr[i]; q < rowptr[i + 1]; ++q) {
+                const int64_t d = pos[col[q]]++;
+                tcol[d] = (int32_t)i;
+                memcpy(&tval[(size_t)d * es], (const char*)val + (size_t)q * es, es);
+            }
+    }
+    LKB_CUDA(cudaMalloc((void**)&op->t_rowptr, (n + 1) * sizeof(int64_t)));
+    LKB_CUDA(cudaMalloc((void**)&op->t_col, std::max<int64_t>(nnz, 1) * sizeof(int32_t)));
+    LKB_CUDA(cudaMalloc(&op->t_val, std::max<int64_t>(nnz, 1) * es));
+    LKB_CUDA(cudaMemcpy(op->t_rowptr, trp.data(), (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
+    LKB_CUDA(cudaMemcpy(op->t_col, tcol.data(), nnz * sizeof(int32_t), cudaMemcpyHostToDevice));
+    LKB_CUDA(cudaMemcpy(op->t_val, tval.data(), nnz * es, cudaMemcpyHostToDevice));
+    *A = op;
+    return 0;
+}
+int lkb_op_dense_create(lkb_ctx_t c, int kind, int64_t m, int64_t n, const void* a, lkb_op_t* A) {
+    if (!c || !A || !a || m < 1 || n < 1) return LKB_ERR_ARG;
+    if (c->world > 1) { set_error("dense operators are single-rank (plumbing config only)"); return LKB_ERR_ARG; }
+    cudaSetDevice(c->dev);
+    lkb_op_s* op = new lkb_op_s();
+    op->ctx = c; op->type = 0; op->kind = kind; op->m = m; op->n = n; op->uid = next_uid();
+    LKB_CUDA(cudaMalloc(&op->a, (size_t)m * n * kind_size(kind)));
+    LKB_CUDA(cudaMemcpy(op->a, a, (size_t)m * n * kind_size(kind), cudaMemcpyHostToDevice));
+    *A = op;
+    return 0;
+}
+int lkb_op_callback_create(lkb_ctx_t c, int kind, int64_t m_local, int64_t n_local, lkb_matvec_fn fn, void* user,
+                           int32_t capturable, lkb_op_t* A) {
+    if (!c || !A || !fn) return LKB_ERR_ARG;
+    lkb_op_s* op = new lkb_op_s();
+    op->ctx = c; op->type = 9; op->kind = kind; op->m = m_local; op->n = n_local; op->uid = next_uid();
+    op->fn = fn; op->user = user; op->capturable = capturable != 0;
+    *A = op;
+    return 0;
+}
+int lkb_op_destroy(lkb_op_t A) {
+    if (!A) return LKB_ERR_ARG;
+    cudaStreamSynchronize(A->ctx->stream);
+    void* bufs[] = { A->halo_lo, A->halo_hi, A->rowptr, A->col, A->val, A->t_rowptr, A->t_col, A->t_val, A->a };
+    for (void* b : bufs) if (b) cudaFree(b);
+    delete A;
+    return 0;
+}
+int lkb_op_counters(lkb_op_t A, int64_t* n_matvec, int64_t* n_rmatvec) {
+    if (n_matvec) *n_matvec = A->n_matvec;
+    if (n_rmatvec) *n_rmatvec = A->n_rmatvec;
+    return 0;
+}
+int lkb_op_reset_counters(lkb_op_t A) { A->n_matvec = A->n_rmatvec = 0; return 0; }
+
+}  // extern "C"
+
+namespace lkb {
+int op_apply_enqueue(lkb_op_s* A, const void* x, void* y, bool trans, const int* flags) {
+    lkb_ctx_s* c = A->ctx;
+    const size_t es = kind_size(A->kind);
+    int nl = 1;
+    prof_begin(c, PC_MATVEC);
+    if (A->type == 1) {
+        if (c->world > 1) {
+            // halo exchange over NCCL send/recv: my first row/plane -> rank-1's halo_hi, my last -> rank+1's halo_lo
+            NcclApi* api = nccl_api();
+            if (!api) return LKB_ERR_NCCL;
+            const int64_t he = A->halo_elems;
+            const int64_t nloc = A->m;
+            const size_t cnt = (size_t)he * (kind_cplx(A->kind) ? 2 : 1);
+            const int dt = (A->kind == KS || A->kind == KC) ? 7 : 8;   // ncclFloat32 / ncclFloat64
+            const bool has_lo = A->st.halo_lo != nullptr, has_hi = A->st.halo_hi != nullptr;
+            LKB_NCCL(api->GroupStart());
+            if (has_lo) {
+                LKB_NCCL(api->Send(x, cnt, dt, c->rank - 1, c->comm, c->stream));
+                LKB_NCCL(api->Recv(A->halo_lo, cnt, dt, c->rank - 1, c->comm, c->stream));
+            }
+            if (has_hi) {
+                LKB_NCCL(api->Send((const char*)x + (size_t)(nloc - he) * es, cnt, dt, c->rank + 1, c->comm, c->stream));
+                LKB_NCCL(api->Recv(A->halo_hi, cnt, dt, c->rank + 1, c->comm, c->stream));
+            }
+            LKB_NCCL(api->GroupEnd());
+        }
+        launch_stencil(A->kind, c->stream, A->st, x, y, trans, flags, c->sms);
+    } else if (A->type == 3) {
+        if (!trans) launch_csr(A->kind, c->stream, A->m, A->rowptr, A->col, A->val, x, y, false, flags, c->sms | (A->lpr << 16));
+        else launch_csr(A->kind, c->stream, A->n, A->t_rowptr, A->t_col, A->t_val, x, y, true, flags, c->sms | (A->t_lpr << 16));
+    } else if (A->type == 0) {
+        launch_dense(A->kind, c->stream, A->m, A->n, A->a, x, y, trans, flags);
+    } else {
+        int r = A->fn(A->user, x, y, trans ? 1 : 0, (void*)c->stream);
+        if (r != 0) { set_error("user matvec callback returned %d", r); return LKB_ERR_ARG; }
+        nl = 0;
+    }
+    prof_end(c, PC_MATVEC, nl);
+    return check_launch(c, "matvec");
+}
+}  // namespace lkb
+
+extern "C" {
+static int op_apply_api(lkb_op_t A, lkb_vec_t x, lkb_vec_t y, bool trans) {
+    if (!A || !x || !y) return LKB_ERR_ARG;
+    const int64_t nin = trans ? A->m : A->n, nout = trans ? A->n : A->m;
+    if (x->n != nin || y->n != nout || x->kind != A->kind || y->kind != A->kind) { set_error("matvec: size/kind mismatch"); return LKB_ERR_ARG; }
+    if (x->d == y->d) { set_error("matvec: vec_out must not alias vec_in"); return LKB_ERR_ARG; }
+    if (trans) A->n_rmatvec++; else A->n_matvec++;
+    return op_apply_enqueue(A, x->d, y->d, trans, nullptr);
+}
+int lkb_op_matvec(lkb_op_t A, lkb_vec_t x, lkb_vec_t y) { return op_apply_api(A, x, y, false); }
+int lkb_op_rmatvec(lkb_op_t A, lkb_vec_t x, lkb_vec_t y) { return op_apply_api(A, x, y, true); }
+}  // extern "C"

@@ -1,0 +1,69 @@
+// lkb_kernels.h -- host-callable launchers of the sm_100a kernels (kind-dispatched).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "lkb_types.cuh"
+
+namespace lkb {
+
+// Device-side control block shared by all kernels of one Krylov process.
+//   flags[0] stop      set when a breakdown was detected; kernels of later steps return at once
+//   flags[1] info      step index (1-based) at which stop was raised
+//   flags[2] refill    the new vector was numerically zero (< atol): host must rand-refill it
+//   flags[3] nan       a norm evaluated to NaN (reference: stop_error, qr.fypp:139-145)
+//   flags[4] gs_info   info of the last orthogonalize_against_basis pass (zero-vector check)
+enum { F_STOP = 0, F_INFO = 1, F_REFILL = 2, F_NAN = 3, F_GSINFO = 4, F_COUNT = 8 };
+
+enum { MD_CB = 16 };           // basis columns per multi-dot CTA
+enum { MD_THREADS = 256 };
+enum { MAX_ROWBLOCKS = 1024 }; // upper bound on stage-1 partial rows
+
+struct StencilArgs {
+    int64_t nx, ny, nz;        // local slab: nx fastest; the slowest axis is the sharded one
+    Scalar coef[7];            // center, -x, +x, -y, +y, -z, +z
+    const void* halo_lo;       // previous slab's last row/plane (nullptr = Dirichlet boundary)
+    const void* halo_hi;       // next slab's first row/plane
+    int dim;                   // 2 or 3
+};
+
+// c[0..j) = V(:, 0:j)^H w, c[j] = w^H w.  Two-stage deterministic reduction; the last CTA to
+// finish folds the stage-1 partials in fixed order into out[0..j].
+void launch_multidot(int kind, cudaStream_t s, const void* V, int64_t ld, int j, const void* w, int64_t n,
+                     void* partial, void* out, unsigned* counter, const int* flags, int sms);
+// w -= V(:, 0:j) c ; optionally nrm2_out[0] = ||w_new||^2 (same two-stage scheme).
+void launch_multiaxpy(int kind, cudaStream_t s, const void* V, int64_t ld, int j, const void* c, void* w, int64_t n,
+                      bool want_norm, void* partial, void* nrm2_out, unsigned* counter, const int* flags, int sms);
+// y = alpha*x + beta*y  (beta == 0: y is overwritten without being read)
+void launch_axpby(int kind, cudaStream_t s, Scalar alpha, const void* x, Scalar beta, void* y, int64_t n, int sms);
+// y = sgn * (*alpha_dev) * x + y   with alpha on the device (W type)
+void launch_axpy_dev(int kind, cudaStream_t s, const void* alpha_dev, double sgn, const void* x, void* y, int64_t n,
+                     const int* flags, int sms);
+void launch_scal(int kind, cudaStream_t s, Scalar alpha, void* x, int64_t n, int sms);
+// x *= *inv_dev (real, device); runs when !stop or info == kstep, and never when refill is set
+void launch_scale_dev(int kind, cudaStream_t s, void* x, int64_t n, const void* inv_dev, const int* flags, int kstep, int sms);
+void launch_fill(int kind, cudaStream_t s, void* x, int64_t n, int64_t row0, int dist, uint64_t seed, int sms);
+
+// Hessenberg / tridiagonal / bidiagonal column update (one tiny CTA).
+//   mode 0 arnoldi (qr_no_pivoting p=1 + breakdown test), 1 lanczos (< tol), 2 bidiag (<= tol), 3 plain norm
+void launch_update(int kind, cudaStream_t s, const void* c1, const void* c2, int j, const void* nrm2, void* hcol,
+                   double tol, double atol, void* inv_dev, int* flags, int kstep, int mode);
+// gs_info: flags[F_GSINFO] = (sqrt(|ww|) < atol)
+void launch_gsinfo(cudaStream_t s, const void* ww, int is_cplx, double atol, int* flags);
+// out[i] = a[i] + b[i] (W type, i < n) -- combine the two CGS passes
+void launch_wadd(int kind, cudaStream_t s, const void* a, const void* b, void* out, int n, const int* flags);
+// dst (E type) = src (W type) narrowed, length n
+void launch_narrow(int kind, cudaStream_t s, const void* src, void* dst, int n, const int* flags);
+
+void launch_stencil(int kind, cudaStream_t s, const StencilArgs& a, const void* x, void* y, bool trans,
+                    const int* flags, int sms);
+// CSR SpMV y = A x (vector-per-row); conj_vals: use conj(A) values (for the explicit-transpose rmatvec)
+void launch_csr(int kind, cudaStream_t s, int64_t m, const int64_t* rowptr, const int32_t* col, const void* val,
+                const void* x, void* y, bool conj_vals, const int* flags, int sms);
+// dense column-major m x n operator (plumbing config: n = 128): y = A x or y = A^H x
+void launch_dense(int kind, cudaStream_t s, int64_t m, int64_t n, const void* a, const void* x, void* y, bool trans,
+                  const int* flags);
+// Y(:, 0:p) = X(:, 0:k) Z(0:k, 0:p)   tall-skinny basis update (Z on device, E type, ldz)
+void launch_basis_gemm(int kind, cudaStream_t s, const void* X, int64_t ldx, int k, const void* Z, int ldz, int p,
+                       void* Y, int64_t ldy, int64_t n, int sms);
+
+}  // namespace lkb

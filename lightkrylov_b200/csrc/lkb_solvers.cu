@@ -1,0 +1,247 @@
+// lkb_solvers.cu -- host shells of the iterative solvers around the device Krylov step.
+//
+//   gmres : src/IterativeSolvers/GMRES/gmres.fypp:65-255 (+ Givens, submodule_utility_functions.fypp:169-204)
+//   cg    : src/IterativeSolvers/CG/CG.fypp:61-196
+// The k x k / k-vector algebra (Givens rotations, back substitution) stays on the host exactly as
+// in the reference; every O(n) operation is a device kernel.
+#include <math.h>
+#include <string.h>
+#include <complex>
+#include <vector>
+#include "../../include/lkb.h"
+#include "lkb_internal.h"
+
+using namespace lkb;
+typedef std::complex<double> cd;
+
+namespace {
+
+// LAPACK 3.10 la_lartg (real): c = |f|/d, r = sign(d, f), s = g/r
+void lartg(double f, double g, double& c, double& s, double& r) {
+    if (g == 0.0) { c = 1.0; s = 0.0; r = f; return; }
+    if (f == 0.0) { c = 0.0; s = g > 0 ? 1.0 : -1.0; r = fabs(g); return; }
+    const double d = hypot(f, g);
+    c = fabs(f) / d; r = copysign(d, f); s = g / r;
+}
+// apply_givens_rotation (h has k+1 entries; c, s have k)
+void givens_real(cd* h, cd* c, cd* s, int k) {
+    for (int j = 0; j < k - 1; ++j) {                       // lasr('L','V','F')
+        const double t = h[j + 1].real();
+        h[j + 1] = c[j].real() * t - s[j].real() * h[j].real();
+        h[j] = s[j].real() * t + c[j].real() * h[j].real();
+    }
+    double cc, ss, r;
+    lartg(h[k - 1].real(), h[k].real(), cc, ss, r);
+    c[k - 1] = cc; s[k - 1] = ss; h[k - 1] = r; h[k] = 0.0;
+}
+void givens_cplx(cd* h, cd* c, cd* s, int k) {             // hand-rolled unnormalised-conjugate form
+    for (int i = 0; i < k - 1; ++i) {
+        const cd t = c[i] * h[i] + s[i] * h[i + 1];
+        h[i + 1] = -s[i] * h[i] + c[i] * h[i + 1];
+        h[i] = t;
+    }
+    const double nrm = sqrt(std::norm(h[k - 1]) + std::norm(h[k]));
+    c[k - 1] = h[k - 1] / nrm; s[k - 1] = h[k] / nrm;
+    h[k - 1] = c[k - 1] * h[k - 1] + s[k - 1] * h[k];
+    h[k] = 0.0;
+}
+// element helpers (round through the kind's precision, as the reference stores H / e / c / s in `kind`)
+cd round_kind(int kind, cd v) {
+    if (kind == KS || kind == KC) return cd((double)(float)v.real(), (double)(float)v.imag());
+    return v;
+}
+Scalar to_scalar(cd v) { return Scalar{v.real(), v.imag()}; }
+void store_kind(int kind, cd v, void* p) {
+    switch (kind) {
+        case KS: *(float*)p = (float)v.real(); break;
+        case KD: *(double*)p = v.real(); break;
+        case KC: ((float*)p)[0] = (float)v.real(); ((float*)p)[1] = (float)v.imag(); break;
+        default: ((double*)p)[0] = v.real(); ((double*)p)[1] = v.imag(); break;
+    }
+}
+void push_res(double* res, int32_t cap, int32_t* len, double v) {
+    if (res && *len < cap) res[*len] = v;
+    (*len)++;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lkb_gmres(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, double rtol, double atol, int32_t transpose,
+              lkb_gmres_io* io) {
+    if (!A || !b || !x || !info) { set_error("gmres: null argument"); return LKB_ERR_ARG; }
+    if (b->n != x->n || b->kind != A->kind || x->kind != A->kind || A->m != b->n || A->n != b->n)
+        { set_error("gmres: size/kind mismatch"); return LKB_ERR_ARG; }
+    lkb_ctx_s* c = b->ctx;
+    const int kind = b->kind;
+    const bool cplx = kind_cplx(kind);
+    const bool trans = transpose != 0;
+    lkb_gmres_io local; memset(&local, 0, sizeof(local));
+    if (!io) io = &local;
+    const int kdim = io->kdim > 0 ? io->kdim : 30;
+    const int maxiter = io->maxiter > 0 ? io->maxiter : 10;
+    if (rtol < 0) rtol = rtol_of(kind);
+    if (atol < 0) atol = atol_of(kind);
+    io->n_iter = io->n_inner = io->n_outer = io->converged = 0; io->res_len = 0;
+
+    double bnorm = 0;
+    LKB_TRY(vec_norm_sync(c, kind, b->d, b->n, &bnorm));
+    const double tol = atol + rtol * bnorm;
+
+    lkb_basis_t V = nullptr;
+    LKB_TRY(lkb_basis_create(c, kind, b->n, b->n_global, b->row0, kdim + 1, &V));
+    lkb_vec_t dx = nullptr;
+    LKB_TRY(lkb_vec_create(c, kind, b->n, b->n_global, b->row0, &dx));
+    std::vector<cd> H((size_t)(kdim + 1) * kdim), e(kdim + 1), cs(kdim), sn(kdim), y(kdim);
+    std::vector<Scalar> col;
+    const Scalar one{1, 0}, mone{-1, 0};
+    int hf[F_COUNT];
+    int rc = 0;
+    auto cleanup = [&](int r) { lkb_basis_destroy(V); lkb_vec_destroy(dx); return r; };
+#define GM_TRY(call) do { rc = (call); if (rc) return cleanup(rc); } while (0)
+
+    auto residual_into_v1 = [&](bool skip_if_zero) -> int {
+        // V(1) = b - A x   (gmres.fypp:134-143, 205-214)
+        double xn = 1.0;
+        if (skip_if_zero) LKB_TRY(vec_norm_sync(c, kind, x->d, x->n, &xn));
+        if (xn != 0.0) {
+            if (trans) A->n_rmatvec++; else A->n_matvec++;
+            LKB_TRY(op_apply_enqueue(A, x->d, col_ptr(V, 0), trans, nullptr));
+        }
+        launch_axpby(kind, c->stream, one, b->d, mone, col_ptr(V, 0), b->n, c->sms);   // sub(b); chsgn()
+        c->launches++;
+        return check_launch(c, "gmres residual");
+    };
+
+    while (!io->converged && io->n_outer <= maxiter) {
+        std::fill(H.begin(), H.end(), cd(0));
+        GM_TRY(lkb_basis_zero(V, 0, kdim + 1));
+        GM_TRY(residual_into_v1(true));
+        std::fill(e.begin(), e.end(), cd(0));
+        double beta = 0;
+        GM_TRY(vec_norm_sync(c, kind, col_ptr(V, 0), b->n, &beta));
+        e[0] = round_kind(kind, beta);
+        launch_scal(kind, c->stream, Scalar{1.0 / beta, 0}, col_ptr(V, 0), b->n, c->sms); c->launches++;
+        std::fill(cs.begin(), cs.end(), cd(0)); std::fill(sn.begin(), sn.end(), cd(0));
+        if (io->n_outer == 0) push_res(io->res, io->res_cap, &io->res_len, fabs(beta));
+        int k = 1;
+        for (k = 1; k <= kdim; ++k) {
+            void* w = col_ptr(V, k);
+            if (trans) A->n_rmatvec++; else A->n_matvec++;
+            GM_TRY(op_apply_enqueue(A, col_ptr(V, k - 1), w, trans, nullptr));
+            GM_TRY(cudaMemsetAsync(c->flags, 0, F_COUNT * sizeof(int), c->stream) == cudaSuccess ? 0 : LKB_ERR_CUDA);
+            GM_TRY(dgs_enqueue(c, kind, V->d, V->ld, k, w, b->n, c->flags, true, false));
+            // H(:k, k) = c1 + c2 ; H(k+1, k) = ||V(k+1)||
+            {
+                const size_t wsz = cplx ? 16 : 8;
+                GM_TRY(ensure_hstage(c, 2 * (size_t)(k + 1) * 16 + 4096));
+                char* hs = (char*)c->hstage;
+                cudaMemcpyAsync(hs, c->c1, (size_t)k * wsz, cudaMemcpyDeviceToHost, c->stream);
+                cudaMemcpyAsync(hs + (size_t)k * wsz, c->c2, (size_t)k * wsz, cudaMemcpyDeviceToHost, c->stream);
+                cudaMemcpyAsync(hs + 2 * (size_t)k * wsz, c->nrm2, 16, cudaMemcpyDeviceToHost, c->stream);
+                GM_TRY(cudaStreamSynchronize(c->stream) == cudaSuccess ? 0 : LKB_ERR_CUDA);
+                for (int i = 0; i < k; ++i) {
+                    const double* a = (const double*)(hs + (size_t)i * wsz);
+                    const double* bb = (const double*)(hs + (size_t)(k + i) * wsz);
+                    H[i + (size_t)(kdim + 1) * (k - 1)] = round_kind(kind, cd(a[0] + bb[0], cplx ? a[1] + bb[1] : 0.0));
+                }
+                const double hk = sqrt(fabs(*(const double*)(hs + 2 * (size_t)k * wsz)));
+                H[k + (size_t)(kdim + 1) * (k - 1)] = round_kind(kind, hk);
+                if (hk > tol) { launch_scal(kind, c->stream, Scalar{1.0 / hk, 0}, w, b->n, c->sms); c->launches++; }
+            }
+            cd* hcol = &H[(size_t)(kdim + 1) * (k - 1)];
+            if (cplx) givens_cplx(hcol, cs.data(), sn.data(), k); else givens_real(hcol, cs.data(), sn.data(), k);
+            for (int i = 0; i <= k; ++i) hcol[i] = round_kind(kind, hcol[i]);
+            e[k] = round_kind(kind, -sn[k - 1] * e[k - 1]);
+            e[k - 1] = round_kind(kind, cs[k - 1] * e[k - 1]);
+            beta = std::abs(e[k]);
+            io->n_iter++; io->n_inner++;
+            push_res(io->res, io->res_cap, &io->res_len, fabs(beta));
+            if (fabs(beta) < tol) { io->converged = 1; break; }
+        }
+        k = k < kdim ? k : kdim;
+        // trtrs('u','n','n'): back substitution on H(:k,:k) y = e(:k)
+        for (int i = k - 1; i >= 0; --i) {
+            cd s = e[i];
+            for (int j = i + 1; j < k; ++j) s -= H[i + (size_t)(kdim + 1) * j] * y[j];
+            y[i] = s / H[i + (size_t)(kdim + 1) * i];
+        }
+        {   // dx = V(:k) y ; x += dx
+            std::vector<char> yk((size_t)k * kind_size(kind));
+            for (int i = 0; i < k; ++i) store_kind(kind, y[i], &yk[(size_t)i * kind_size(kind)]);
+            GM_TRY(lkb_basis_lincomb(V, k, yk.data(), dx));
+            launch_axpby(kind, c->stream, one, dx->d, one, x->d, x->n, c->sms); c->launches++;
+        }
+        GM_TRY(residual_into_v1(false));
+        GM_TRY(vec_norm_sync(c, kind, col_ptr(V, 0), b->n, &beta));
+        if (fabs(beta) > 0.0) { launch_scal(kind, c->stream, Scalar{1.0 / beta, 0}, col_ptr(V, 0), b->n, c->sms); c->launches++; }
+        io->n_iter++; io->n_outer++;
+        push_res(io->res, io->res_cap, &io->res_len, fabs(beta));
+        if (fabs(beta) < tol) { io->converged = 1; break; }
+    }
+#undef GM_TRY
+    (void)hf; (void)col;
+    *info = io->converged ? io->n_iter : -io->n_iter;
+    io->info = *info;
+    return cleanup(0);
+}
+
+int lkb_cg(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, double rtol, double atol, lkb_cg_io* io) {
+    if (!A || !b || !x || !info) { set_error("cg: null argument"); return LKB_ERR_ARG; }
+    if (b->n != x->n || b->kind != A->kind || x->kind != A->kind || A->m != b->n || A->n != b->n)
+        { set_error("cg: size/kind mismatch"); return LKB_ERR_ARG; }
+    lkb_ctx_s* c = b->ctx;
+    const int kind = b->kind;
+    lkb_cg_io local; memset(&local, 0, sizeof(local));
+    if (!io) io = &local;
+    const int maxiter = io->maxiter > 0 ? io->maxiter : 100;
+    if (rtol < 0) rtol = rtol_of(kind);
+    if (atol < 0) atol = atol_of(kind);
+    io->n_iter = 0; io->converged = 0; io->res_len = 0;
+    double bnorm = 0;
+    LKB_TRY(vec_norm_sync(c, kind, b->d, b->n, &bnorm));
+    const double tol = atol + rtol * bnorm;
+    lkb_vec_t r = nullptr, p = nullptr, Ap = nullptr;
+    LKB_TRY(lkb_vec_create(c, kind, b->n, b->n_global, b->row0, &r));
+    LKB_TRY(lkb_vec_create(c, kind, b->n, b->n_global, b->row0, &p));
+    LKB_TRY(lkb_vec_create(c, kind, b->n, b->n_global, b->row0, &Ap));
+    int rc = 0;
+    auto cleanup = [&](int rr) { lkb_vec_destroy(r); lkb_vec_destroy(p); lkb_vec_destroy(Ap); return rr; };
+#define CG_TRY(call) do { rc = (call); if (rc) return cleanup(rc); } while (0)
+    const Scalar one{1, 0}, mone{-1, 0}, zero{0, 0};
+    double xn = 0;
+    CG_TRY(vec_norm_sync(c, kind, x->d, x->n, &xn));
+    if (xn > 0) { A->n_matvec++; CG_TRY(op_apply_enqueue(A, x->d, r->d, false, nullptr)); }
+    launch_axpby(kind, c->stream, one, b->d, mone, r->d, b->n, c->sms); c->launches++;      // r = b - A x
+    launch_axpby(kind, c->stream, one, r->d, zero, p->d, b->n, c->sms); c->launches++;      // p = r
+    Scalar rr_old;
+    CG_TRY(vec_dot_sync(c, kind, r->d, r->d, b->n, &rr_old));
+    push_res(io->res, io->res_cap, &io->res_len, sqrt(hypot(rr_old.re, rr_old.im)));
+    for (int it = 1; it <= maxiter; ++it) {
+        A->n_matvec++;
+        CG_TRY(op_apply_enqueue(A, p->d, Ap->d, false, nullptr));
+        Scalar pAp;
+        CG_TRY(vec_dot_sync(c, kind, p->d, Ap->d, b->n, &pAp));
+        const cd alpha = round_kind(kind, cd(rr_old.re, rr_old.im) / cd(pAp.re, pAp.im));
+        launch_axpby(kind, c->stream, to_scalar(alpha), p->d, one, x->d, b->n, c->sms);      // x += alpha p
+        launch_axpby(kind, c->stream, to_scalar(-alpha), Ap->d, one, r->d, b->n, c->sms);    // r -= alpha Ap
+        c->launches += 2;
+        Scalar rr_new;
+        CG_TRY(vec_dot_sync(c, kind, r->d, r->d, b->n, &rr_new));
+        const double residual = sqrt(hypot(rr_new.re, rr_new.im));
+        io->n_iter++;
+        push_res(io->res, io->res_cap, &io->res_len, residual);
+        if (residual < tol) { io->converged = 1; break; }
+        const cd beta = round_kind(kind, cd(rr_new.re, rr_new.im) / cd(rr_old.re, rr_old.im));
+        launch_axpby(kind, c->stream, one, r->d, to_scalar(beta), p->d, b->n, c->sms);       // p = r + beta p
+        c->launches++;
+        rr_old = rr_new;
+    }
+#undef CG_TRY
+    *info = io->converged ? io->n_iter : -io->n_iter;
+    io->info = *info;
+    return cleanup(check_launch(c, "cg"));
+}
+
+}  // extern "C"

@@ -1,0 +1,437 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical seeded
+inputs, plus size-independent properties at the BASELINE.json sizes.
+
+Tolerances (BASELINE.json north_star): Hessenberg entries (normwise) and Ritz values 1e-10 in
+fp64 (1e-4 fp32); ||V^H V - I||_max <= 1e-12 (fp64).
+"""
+import numpy as np
+import pytest
+
+from helpers import CONVDIFF7, LAPLACE7, POISSON5, orth_tol, randn, random_csr, rel_normwise, tol_for
+
+pytestmark = pytest.mark.gpu
+KINDS = ["s", "d", "c", "z"]
+
+
+@pytest.fixture(scope="module")
+def lk():
+    import lightkrylov_b200 as lk
+    return lk
+
+
+@pytest.fixture(scope="module")
+def ctx(lk):
+    c = lk.Context(0)
+    yield c
+    c.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# abstract_vector TBPs (TestVectors.fypp:50-179 + verify_vector_axioms)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("n", [1, 7, 128, 1000003])
+def test_vector_tbps(lk, ctx, oracle, kind, n):
+    dt = lk.DTYPES[kind]
+    rng = np.random.default_rng(n)
+    xh, yh = randn(rng, n, dt), randn(rng, n, dt)
+    x = lk.Vector(ctx, kind, n).put(xh); y = lk.Vector(ctx, kind, n).put(yh)
+    tol = 1e-12 if kind in "dz" else 1e-4
+    ref = np.vdot(xh.astype(np.complex128), yh.astype(np.complex128))
+    got = x.dot(y)
+    assert abs(got - ref) <= tol * max(1.0, abs(ref)) * np.sqrt(n)
+    assert abs(got - oracle.dot(xh, yh)) <= tol * max(1.0, abs(ref)) * np.sqrt(n)
+    assert abs(x.norm() - np.linalg.norm(xh.astype(np.complex128))) <= tol * np.sqrt(n)
+    alpha, beta = (0.7 - 0.2j, -1.3 + 0.4j) if kind in "cz" else (0.7, -1.3)
+    y.axpby(alpha, x, beta)
+    np.testing.assert_allclose(y.get(), (alpha * xh + beta * yh).astype(dt), rtol=1e-5 if kind in "sc" else 1e-14, atol=1e-6 if kind in "sc" else 1e-14)
+    # copy semantics: beta == 0 must overwrite even NaN garbage
+    z = lk.Vector(ctx, kind, n).put(np.full(n, np.nan, dtype=dt))
+    z.axpby(1, x, 0)
+    assert np.array_equal(z.get(), xh)
+    x.scal(alpha)
+    np.testing.assert_allclose(x.get(), (xh * dt(alpha)).astype(dt), rtol=1e-6 if kind in "sc" else 1e-15)
+    assert x.get_size() == n
+    x.zero(); assert not x.get().any()
+
+
+@pytest.mark.parametrize("kind", ["d", "z"])
+def test_rand_matches_oracle_generator(lk, ctx, oracle, kind):
+    n = 4099
+    v = lk.Vector(ctx, kind, n).fill_random("uniform", 42)
+    assert np.array_equal(v.get(), oracle.fill(n, kind, "uniform", 42))      # bit exact
+    g = lk.Vector(ctx, kind, n).fill_random("normal", 7).get()
+    np.testing.assert_allclose(g, oracle.fill(n, kind, "normal", 7), rtol=1e-12, atol=1e-13)
+    r = lk.Vector(ctx, kind, n).rand(ifnorm=True)
+    assert abs(r.norm() - 1.0) < 1e-13
+    # sharding independence: rows [row0, row0+m) of the same global vector
+    part = lk.Vector(ctx, kind, 1000, n_global=n, row0=2000).fill_random("uniform", 42)
+    assert np.array_equal(part.get(), oracle.fill(n, kind, "uniform", 42)[2000:3000])
+
+
+# ---------------------------------------------------------------------------------------------
+# Gram-Schmidt: innerprod / lincomb / DGS / QR
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("n,j", [(128, 5), (1000, 16), (100003, 17), (50001, 40), (4096, 129)])
+def test_dgs_step_vs_oracle(lk, ctx, oracle, kind, n, j):
+    dt = lk.DTYPES[kind]
+    rng = np.random.default_rng(100 * j + n % 97)
+    Q, _ = np.linalg.qr(randn(rng, (n, j), dt).astype(np.complex128 if kind in "cz" else np.float64))
+    Xh = np.asfortranarray(Q.astype(dt))
+    wh = randn(rng, n, dt)
+    X = lk.Basis(ctx, kind, n, j + 1).put(Xh)
+    X.put(wh, col0=j)
+    ip = X.innerprod(j, X, wcol0=j, p=1)[:, 0]
+    ref_ip = Xh.conj().T.astype(np.complex128) @ wh.astype(np.complex128)
+    assert rel_normwise(ip, ref_ip) < (1e-13 if kind in "dz" else 1e-5)
+    info, beta = lk.double_gram_schmidt_step(X, j, 1, X, j, if_chk_orthonormal=False)
+    wo = wh.copy()
+    oinfo, obeta = oracle.dgs_vec(wo, Xh, j)
+    assert info == oinfo == 0
+    assert rel_normwise(beta[:, 0], obeta) < tol_for(kind)
+    wg = X.get(j, 1)[:, 0]
+    assert rel_normwise(wg, wo) < tol_for(kind) * 10
+    assert np.abs(Xh.conj().T @ wg).max() < (1e-13 if kind in "dz" else 1e-5) * np.linalg.norm(wg)
+
+
+def test_dgs_zero_vector_info_and_orthonormal_check(lk, ctx):
+    n, j = 1000, 4
+    rng = np.random.default_rng(0)
+    Q, _ = np.linalg.qr(rng.standard_normal((n, j)))
+    X = lk.Basis(ctx, "d", n, j + 2).put(np.asfortranarray(Q))
+    info, _ = lk.double_gram_schmidt_step(X, j, 1, X, j, if_chk_orthonormal=True)   # zero vector
+    assert info == 1
+    X.put(rng.standard_normal(n), col0=j)
+    info, _ = lk.double_gram_schmidt_step(X, j, 2, X, j, if_chk_orthonormal=False)  # second column is zero
+    assert info == 2
+    bad = lk.Basis(ctx, "d", n, 3).put(np.asfortranarray(rng.standard_normal((n, 3))))
+    with pytest.raises(lk.LkbError, match="not orthonormal"):
+        lk.double_gram_schmidt_step(bad, 2, 1, bad, 2, if_chk_orthonormal=True)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_qr_no_pivoting(lk, ctx, oracle, kind):
+    """TestKrylov.fypp:52-110 on the device + entrywise vs oracle."""
+    dt = lk.DTYPES[kind]; n, p = 128, 20
+    Ah = randn(np.random.default_rng(5), (n, p), dt)
+    Q = lk.Basis(ctx, kind, n, p).put(Ah)
+    info, R = lk.qr(Q)
+    Qo = Ah.copy(order="F"); oinfo, Ro = oracle.qr(Qo)
+    assert info == oinfo == 0
+    Qg = Q.get()
+    assert np.abs(Ah - Qg @ R).max() < lk.RTOL[kind]
+    assert np.abs(Qg.conj().T @ Qg - np.eye(p)).max() < lk.RTOL[kind]
+    assert rel_normwise(R, Ro) < tol_for(kind)
+
+
+def test_qr_breakdown_refill(lk, ctx):
+    n = 128
+    Ah = randn(np.random.default_rng(6), (n, 6), np.float64)
+    Ah[:, 3] = 2.0 * Ah[:, 1] - Ah[:, 0]
+    Q = lk.Basis(ctx, "d", n, 6).put(Ah)
+    info, R = lk.qr(Q, tol=1e-10)
+    assert info == 0 and R[3, 3] == 0.0            # literal reference info semantics (see oracle pin test)
+    Qg = Q.get()
+    assert np.abs(Qg.T @ Qg - np.eye(6)).max() < 1e-12
+    Z = lk.Basis(ctx, "d", n, 1)
+    info, R = lk.qr(Z)
+    assert info == 1 and R[0, 0] == 0.0 and abs(np.linalg.norm(Z.get()) - 1) < 1e-13
+
+
+# ---------------------------------------------------------------------------------------------
+# operators
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("dims", [(64, 48), (33, 17), (16, 12, 10), (7, 5, 4)])
+def test_stencil_matvec_vs_oracle(lk, ctx, oracle, kind, dims):
+    dt = lk.DTYPES[kind]
+    coef = list(CONVDIFF7[: 5 if len(dims) == 2 else 7])
+    if kind in "cz":
+        coef = [c + 0.1j * (i + 1) for i, c in enumerate(coef)]
+    n = int(np.prod(dims))
+    A = (lk.LinOp.stencil5(ctx, kind, *dims, coef) if len(dims) == 2 else lk.LinOp.stencil7(ctx, kind, *dims, coef))
+    Ao = oracle.Op.stencil(kind, dims, coef)
+    xh = randn(np.random.default_rng(1), n, dt)
+    x = lk.Vector(ctx, kind, n).put(xh); y = lk.Vector(ctx, kind, n)
+    A.matvec(x, y)
+    np.testing.assert_allclose(y.get(), Ao.apply(xh), rtol=1e-5 if kind in "sc" else 1e-13, atol=1e-5 if kind in "sc" else 1e-13)
+    A.rmatvec(x, y)
+    np.testing.assert_allclose(y.get(), Ao.apply(xh, trans=True), rtol=1e-5 if kind in "sc" else 1e-13, atol=1e-5 if kind in "sc" else 1e-13)
+    assert A.counters() == (1, 1)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("per_row", [3, 12, 32, 70])
+def test_csr_matvec_rmatvec_vs_oracle(lk, ctx, oracle, kind, per_row):
+    dt = lk.DTYPES[kind]; m, n = 700, 500
+    rng = np.random.default_rng(per_row)
+    S = random_csr(rng, m, n, per_row, dt)
+    A = lk.LinOp.csr(ctx, m, n, S.indptr, S.indices, S.data.astype(dt))
+    Ao = oracle.Op.csr(m, n, S.indptr, S.indices, S.data.astype(dt))
+    xh, uh = randn(rng, n, dt), randn(rng, m, dt)
+    x = lk.Vector(ctx, kind, n).put(xh); u = lk.Vector(ctx, kind, m).put(uh)
+    y = lk.Vector(ctx, kind, m); v = lk.Vector(ctx, kind, n)
+    A.matvec(x, y); A.rmatvec(u, v)
+    tol = dict(rtol=1e-4, atol=1e-4) if kind in "sc" else dict(rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(y.get(), Ao.apply(xh), **tol)
+    np.testing.assert_allclose(v.get(), Ao.apply(uh, trans=True), **tol)
+
+
+# ---------------------------------------------------------------------------------------------
+# arnoldi
+# ---------------------------------------------------------------------------------------------
+def _arnoldi_pair(lk, ctx, oracle, kind, A, Ao, n, kdim, x0, **kw):
+    dt = lk.DTYPES[kind]
+    X = lk.Basis(ctx, kind, n, kdim + 1).put(x0, col0=0)
+    H = np.zeros((kdim + 1, kdim), dtype=dt, order="F")
+    info = lk.arnoldi(A, X, H, **kw)
+    Xo = np.zeros((n, kdim + 1), dtype=dt, order="F"); Xo[:, 0] = x0
+    Ho = np.zeros((kdim + 1, kdim), dtype=dt, order="F")
+    okw = {k: v for k, v in kw.items() if k in ("kstart", "kend")}
+    if "tol" in kw and kw["tol"] >= 0: okw["tol"] = kw["tol"]
+    if kw.get("transpose"): okw["trans"] = True
+    oinfo = oracle.arnoldi(Ao, Xo, Ho, **okw)
+    return info, X, H, oinfo, Xo, Ho
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_arnoldi_config1_dense_n128_kdim64(lk, ctx, oracle, kind):
+    """BASELINE config 1: TestKrylov-style arnoldi kdim=64 on a random dense linop, n=128."""
+    dt = lk.DTYPES[kind]; n, kdim = 128, 64
+    rng = np.random.default_rng(1)
+    Ah = randn(rng, (n, n), dt)                        # seed 1
+    x0 = randn(np.random.default_rng(2), n, dt); oracle.normalize(x0)
+    A = lk.LinOp.dense(ctx, Ah); Ao = oracle.Op.dense(Ah)
+    info, X, H, oinfo, Xo, Ho = _arnoldi_pair(lk, ctx, oracle, kind, A, Ao, n, kdim, x0)
+    assert info == oinfo == 0
+    assert rel_normwise(H, Ho) < tol_for(kind)
+    Xg = X.get()
+    assert rel_normwise(Xg, Xo) < tol_for(kind) * 100
+    # the reference's own assertions (TestKrylov.fypp:218-239)
+    assert np.abs(Ah @ Xg[:, :kdim] - Xg @ H).max() < lk.RTOL[kind] * np.abs(Ah).max() * 10
+    assert np.abs(Xg.conj().T @ Xg - np.eye(kdim + 1)).max() < orth_tol(kind)
+    ritz_g = np.sort_complex(np.linalg.eigvals(H[:kdim, :kdim].astype(np.complex128)))
+    ritz_o = np.sort_complex(np.linalg.eigvals(Ho[:kdim, :kdim].astype(np.complex128)))
+    assert np.abs(ritz_g - ritz_o).max() / np.abs(ritz_o).max() < tol_for(kind) * 100
+    assert A.counters()[0] == kdim
+
+
+@pytest.mark.parametrize("kind", ["d", "s", "z"])
+def test_arnoldi_poisson2d_vs_oracle(lk, ctx, oracle, kind):
+    """Config C2 operator at 256^2, full kdim=128: H, Ritz values, orthonormality."""
+    nx = ny = 256; n = nx * ny; kdim = 128 if kind != "s" else 48
+    A = lk.LinOp.stencil5(ctx, kind, nx, ny, POISSON5); Ao = oracle.Op.stencil(kind, (nx, ny), POISSON5)
+    x0 = oracle.fill(n, kind, "uniform", 42); oracle.normalize(x0)
+    info, X, H, oinfo, Xo, Ho = _arnoldi_pair(lk, ctx, oracle, kind, A, Ao, n, kdim, x0)
+    assert info == oinfo == 0
+    assert rel_normwise(H, Ho) < tol_for(kind)
+    Xg = X.get()
+    assert np.abs(Xg.conj().T @ Xg - np.eye(kdim + 1)).max() < orth_tol(kind)
+    ritz_g = np.sort(np.linalg.eigvals(H[:kdim, :kdim].astype(np.complex128)).real)
+    ritz_o = np.sort(np.linalg.eigvals(Ho[:kdim, :kdim].astype(np.complex128)).real)
+    assert np.abs(ritz_g - ritz_o).max() / np.abs(ritz_o).max() < tol_for(kind)
+
+
+def test_arnoldi_kstart_kend_resume_and_graph_equivalence(lk, ctx, oracle):
+    """Algorithmic resume (BaseKrylov.fypp:111-117): one step at a time == one shot; graphs on == off, bitwise."""
+    nx, ny, kdim = 128, 96, 24; n = nx * ny
+    A = lk.LinOp.stencil5(ctx, "d", nx, ny, CONVDIFF7[:5])
+    x0 = oracle.fill(n, "d", "uniform", 3); oracle.normalize(x0)
+    res = []
+    for mode in ("graph", "nograph", "stepwise"):
+        ctx.set_graphs(mode != "nograph")
+        X = lk.Basis(ctx, "d", n, kdim + 1).put(x0)
+        H = np.zeros((kdim + 1, kdim), order="F")
+        if mode == "stepwise":
+            for k in range(1, kdim + 1):
+                assert lk.arnoldi(A, X, H, kstart=k, kend=k) == 0
+        else:
+            assert lk.arnoldi(A, X, H) == 0
+        res.append((H.copy(), X.get()))
+    ctx.set_graphs(True)
+    for H, Xg in res[1:]:
+        assert np.array_equal(H, res[0][0]) and np.array_equal(Xg, res[0][1])
+    # run-to-run determinism of the two-stage reductions
+    X = lk.Basis(ctx, "d", n, kdim + 1).put(x0); H = np.zeros((kdim + 1, kdim), order="F")
+    lk.arnoldi(A, X, H)
+    assert np.array_equal(H, res[0][0])
+
+
+def test_arnoldi_transpose(lk, ctx, oracle):
+    nx, ny, kdim = 64, 64, 20; n = nx * ny
+    A = lk.LinOp.stencil5(ctx, "d", nx, ny, CONVDIFF7[:5]); Ao = oracle.Op.stencil("d", (nx, ny), CONVDIFF7[:5])
+    x0 = oracle.fill(n, "d", "uniform", 5); oracle.normalize(x0)
+    info, X, H, oinfo, Xo, Ho = _arnoldi_pair(lk, ctx, oracle, "d", A, Ao, n, kdim, x0, transpose=True)
+    assert info == oinfo == 0 and rel_normwise(H, Ho) < 1e-10
+    assert A.counters() == (0, kdim)
+
+
+@pytest.mark.parametrize("kind", ["d", "z"])
+def test_arnoldi_breakdown_invariant_subspace(lk, ctx, oracle, kind):
+    """arnoldi.fypp:59-71: info = dimension of the invariant subspace, later H columns untouched,
+    the breakdown vector is replaced by a normalised random one (qr.fypp:146-162)."""
+    dt = lk.DTYPES[kind]; n = 128
+    Ah = np.asfortranarray(np.diag(np.arange(1, n + 1)).astype(dt))
+    x0 = np.zeros(n, dtype=dt); x0[:3] = 1 / np.sqrt(3.0)
+    A = lk.LinOp.dense(ctx, Ah); Ao = oracle.Op.dense(Ah)
+    info, X, H, oinfo, Xo, Ho = _arnoldi_pair(lk, ctx, oracle, kind, A, Ao, n, 10, x0, tol=1e-12)
+    assert info == oinfo == 3
+    assert np.all(H[:, 3:] == 0) and rel_normwise(H, Ho) < 1e-10
+    Xg = X.get()
+    assert not Xg[:, 5:].any()
+    assert abs(np.linalg.norm(Xg[:, 3]) - 1.0) < 1e-12
+    assert A.counters()[0] == 3
+
+
+def test_arnoldi_block_p2(lk, ctx, oracle):
+    """TestKrylov.fypp:244-296: block Arnoldi p=2, kdim=64 on n=128, vs oracle."""
+    n, p, kdim = 128, 2, 64
+    rng = np.random.default_rng(2)
+    Ah = randn(rng, (n, n), np.float64) / np.sqrt(n)
+    X0 = randn(rng, (n, p), np.float64); oracle.qr(X0)
+    A = lk.LinOp.dense(ctx, Ah); Ao = oracle.Op.dense(Ah)
+    X = lk.Basis(ctx, "d", n, p * (kdim + 1)).put(X0)
+    H = np.zeros((p * (kdim + 1), p * kdim), order="F")
+    info = lk.arnoldi(A, X, H, blksize=p)
+    Xo = np.zeros((n, p * (kdim + 1)), order="F"); Xo[:, :p] = X0
+    Ho = np.zeros_like(H)
+    oinfo = oracle.arnoldi(Ao, Xo, Ho, blksize=p)
+    assert info == oinfo
+    k = p * kdim if info == 0 else info
+    Xg = X.get()
+    assert np.abs(Ah @ Xg[:, :k] - Xg[:, :k + p] @ H[:k + p, :k]).max() < lk.RTOL["d"]
+    assert np.abs(Xg[:, :k].T @ Xg[:, :k] - np.eye(k)).max() < 1e-12
+    assert rel_normwise(H[:, : k - p], Ho[:, : k - p]) < 1e-8
+
+
+# ---------------------------------------------------------------------------------------------
+# lanczos / bidiagonalization
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", KINDS)
+def test_lanczos_vs_oracle(lk, ctx, oracle, kind):
+    dt = lk.DTYPES[kind]; dims = (24, 20, 16); n = int(np.prod(dims)); kdim = 40
+    A = lk.LinOp.stencil7(ctx, kind, *dims, LAPLACE7); Ao = oracle.Op.stencil(kind, dims, LAPLACE7)
+    x0 = oracle.fill(n, kind, "uniform", 45); oracle.normalize(x0)
+    X = lk.Basis(ctx, kind, n, kdim + 1).put(x0)
+    T = np.zeros((kdim + 1, kdim), dtype=dt, order="F")
+    info = lk.lanczos(A, X, T)
+    Xo = np.zeros((n, kdim + 1), dtype=dt, order="F"); Xo[:, 0] = x0
+    To = np.zeros_like(T)
+    assert info == oracle.lanczos(Ao, Xo, To) == 0
+    assert rel_normwise(T, To) < tol_for(kind)
+    Xg = X.get()
+    assert np.abs(Xg.conj().T @ Xg - np.eye(kdim + 1)).max() < orth_tol(kind)
+    # only the three diagonals are written (lanczos.fypp:57-59, 29)
+    mask = np.ones_like(T, dtype=bool)
+    for k in range(kdim):
+        mask[max(0, k - 1):k + 2, k] = False
+    assert not T[mask].any()
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_bidiagonalization_vs_oracle(lk, ctx, oracle, kind):
+    dt = lk.DTYPES[kind]; m, n, kdim = 900, 700, 32
+    rng = np.random.default_rng(46)
+    S = random_csr(rng, m, n, 32, dt)
+    A = lk.LinOp.csr(ctx, m, n, S.indptr, S.indices, S.data.astype(dt))
+    Ao = oracle.Op.csr(m, n, S.indptr, S.indices, S.data.astype(dt))
+    u0 = oracle.fill(m, kind, "normal", 47); oracle.normalize(u0)
+    U = lk.Basis(ctx, kind, m, kdim + 1).put(u0); V = lk.Basis(ctx, kind, n, kdim + 1)
+    B = np.zeros((kdim + 1, kdim), dtype=dt, order="F")
+    info = lk.bidiagonalization(A, U, V, B)
+    Uo = np.zeros((m, kdim + 1), dtype=dt, order="F"); Uo[:, 0] = u0
+    Vo = np.zeros((n, kdim + 1), dtype=dt, order="F"); Bo = np.zeros_like(B)
+    assert info == oracle.bidiag(Ao, Uo, Vo, Bo) == 0
+    assert rel_normwise(B, Bo) < tol_for(kind)
+    Ug, Vg = U.get(), V.get()
+    Sd = S.toarray()
+    assert np.abs(Sd @ Vg[:, :kdim] - Ug @ B).max() < lk.RTOL[kind] * 10
+    assert np.abs(Ug.conj().T @ Ug - np.eye(kdim + 1)).max() < orth_tol(kind)
+    assert np.abs(Vg[:, :kdim].conj().T @ Vg[:, :kdim] - np.eye(kdim)).max() < orth_tol(kind)
+    assert A.counters() == (kdim, kdim)
+
+
+def test_lanczos_breakdown(lk, ctx, oracle):
+    n = 128
+    Ah = np.asfortranarray(np.diag(np.arange(1.0, n + 1)))
+    x0 = np.zeros(n); x0[:4] = 0.5
+    A = lk.LinOp.dense(ctx, Ah); Ao = oracle.Op.dense(Ah)
+    X = lk.Basis(ctx, "d", n, 11).put(x0); T = np.zeros((11, 10), order="F")
+    info = lk.lanczos(A, X, T, tol=1e-12)
+    Xo = np.zeros((n, 11), order="F"); Xo[:, 0] = x0; To = np.zeros_like(T)
+    assert info == oracle.lanczos(Ao, Xo, To, tol=1e-12) == 4
+    assert rel_normwise(T, To) < 1e-10 and not T[:, 4:].any()
+
+
+# ---------------------------------------------------------------------------------------------
+# solvers
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", KINDS)
+def test_gmres_vs_oracle(lk, ctx, oracle, kind):
+    dt = lk.DTYPES[kind]; nx, ny = 48, 40; n = nx * ny
+    coef = CONVDIFF7[:5]
+    A = lk.LinOp.stencil5(ctx, kind, nx, ny, coef); Ao = oracle.Op.stencil(kind, (nx, ny), coef)
+    bh = oracle.fill(n, kind, "uniform", 43)
+    b = lk.Vector(ctx, kind, n).put(bh); x = lk.Vector(ctx, kind, n)
+    info, meta = lk.gmres(A, b, x, kdim=30, maxiter=20)
+    xo = np.zeros(n, dtype=dt)
+    oinfo, ometa = oracle.gmres(Ao, bh, xo, kdim=30, maxiter=20)
+    assert info == oinfo and info > 0
+    assert meta["n_iter"] == ometa["n_iter"] and meta["n_outer"] == ometa["n_outer"]
+    r = np.array(meta["res"]); ro = np.array(ometa["res"])
+    assert r.shape == ro.shape
+    np.testing.assert_allclose(r, ro, rtol=1e-6 if kind in "dz" else 5e-2, atol=lk.ATOL[kind] * 100)
+    xg = x.get()
+    assert np.linalg.norm(Ao.apply(xg) - bh) < lk.RTOL[kind] * np.linalg.norm(bh) * 2
+    assert np.linalg.norm(xg - xo) / np.linalg.norm(xo) < (1e-7 if kind in "dz" else 1e-2)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_cg_vs_oracle(lk, ctx, oracle, kind):
+    dt = lk.DTYPES[kind]; dims = (20, 16, 12); n = int(np.prod(dims))
+    A = lk.LinOp.stencil7(ctx, kind, *dims, LAPLACE7); Ao = oracle.Op.stencil(kind, dims, LAPLACE7)
+    bh = oracle.fill(n, kind, "uniform", 45)
+    b = lk.Vector(ctx, kind, n).put(bh); x = lk.Vector(ctx, kind, n)
+    info, meta = lk.cg(A, b, x, maxiter=2000)
+    xo = np.zeros(n, dtype=dt)
+    oinfo, ometa = oracle.cg(Ao, bh, xo, maxiter=2000)
+    assert info > 0 and oinfo > 0 and abs(info - oinfo) <= (1 if kind in "dz" else 3)
+    k = min(len(meta["res"]), len(ometa["res"])) - 1
+    np.testing.assert_allclose(meta["res"][:k], ometa["res"][:k], rtol=1e-6 if kind in "dz" else 5e-2)
+    assert np.linalg.norm(Ao.apply(x.get()) - bh) < lk.RTOL[kind] * np.linalg.norm(bh) * 2
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json full size (config C2): size-independent properties + a short oracle comparison
+# ---------------------------------------------------------------------------------------------
+def test_arnoldi_full_size_c2(lk, ctx, oracle):
+    nx = ny = 4096; n = nx * ny; kdim = 128
+    A = lk.LinOp.stencil5(ctx, "d", nx, ny, POISSON5)
+    X = lk.Basis(ctx, "d", n, kdim + 1)
+    x0 = X.col(0).fill_random("uniform", 42)
+    x0.scal(1.0 / x0.norm())
+    H = np.zeros((kdim + 1, kdim), order="F")
+    assert lk.arnoldi(A, X, H) == 0
+    # orthonormality of the whole basis via the device Gram matrix (129 x 129)
+    G = X.innerprod(kdim + 1, X, wcol0=0, p=kdim + 1)
+    assert np.abs(G - np.eye(kdim + 1)).max() <= 1e-12
+    # Arnoldi relation A v_k = V_{k+1} H(:,k) for a few columns, evaluated on the device
+    y = lk.Vector(ctx, "d", n); r = lk.Vector(ctx, "d", n)
+    for k in (1, 64, 128):
+        A.matvec(X.col(k - 1), y)
+        X.linear_combination(k + 1, H[:k + 1, k - 1].copy(), r)
+        r.sub(y)
+        assert r.norm() < 1e-12 * 8
+    # H is symmetric tridiagonal up to rounding for the SPD Poisson operator, spectrum inside (0, 8)
+    Hs = H[:kdim, :kdim]
+    assert np.abs(Hs - Hs.T).max() < 1e-10
+    ev = np.linalg.eigvalsh((Hs + Hs.T) / 2)
+    assert ev.min() > 0 and ev.max() < 8
+    # first 6 steps against the oracle on the same bit-identical start vector
+    ko = 6
+    Xo = np.zeros((n, ko + 1), order="F"); Xo[:, 0] = oracle.fill(n, "d", "uniform", 42); oracle.normalize(Xo[:, 0])
+    Ho = np.zeros((ko + 1, ko), order="F")
+    oracle.set_threads(oracle.max_threads())
+    assert oracle.arnoldi(oracle.Op.stencil("d", (nx, ny), POISSON5), Xo, Ho) == 0
+    assert rel_normwise(H[:ko + 1, :ko], Ho) < 1e-10
