@@ -1,0 +1,89 @@
+"""Worker of tests/test_multi_gpu.py: run under torchrun with N ranks (one per GPU).
+Row-sharded arnoldi / lanczos / gmres / cg through the C ABI against the single-process CPU oracle."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import lightkrylov_b200 as lk
+    from oracle import lk_oracle as lo
+    from helpers import CONVDIFF7, POISSON5, rel_normwise
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = lk.Context.from_torch_distributed(local)
+    assert ctx.world == world and ctx.rank == rank
+
+    def gather_rows(local_arr):
+        parts = [None] * world
+        dist.all_gather_object(parts, local_arr)
+        return np.concatenate(parts, axis=0)
+
+    # ---- 2-D Poisson, ragged slabs (ny not divisible by world) ----
+    nx, ny, kdim = 128, 101, 40
+    n = nx * ny
+    for coef, trans in ((POISSON5, False), (CONVDIFF7[:5], True)):
+        A = lk.LinOp.stencil5(ctx, "d", nx, ny, coef)
+        X = lk.Basis(ctx, "d", A.n, kdim + 1, n_global=n, row0=A.row0)
+        x0 = X.col(0).fill_random("uniform", 42)
+        x0.scal(1.0 / x0.norm())
+        H = np.zeros((kdim + 1, kdim), order="F")
+        info = lk.arnoldi(A, X, H, transpose=trans)
+        Xg = gather_rows(X.get())
+        Hs = [None] * world
+        dist.all_gather_object(Hs, H)
+        assert all(np.array_equal(Hs[0], h) for h in Hs), "H must be identical on every rank"
+        if rank == 0:
+            Xo = np.zeros((n, kdim + 1), order="F"); Xo[:, 0] = lo.fill(n, "d", "uniform", 42); lo.normalize(Xo[:, 0])
+            Ho = np.zeros_like(H)
+            oinfo = lo.arnoldi(lo.Op.stencil("d", (nx, ny), coef), Xo, Ho, trans=trans)
+            assert info == oinfo == 0
+            assert rel_normwise(H, Ho) < 1e-10, rel_normwise(H, Ho)
+            assert np.abs(Xg.T @ Xg - np.eye(kdim + 1)).max() < 1e-12
+            assert rel_normwise(Xg, Xo) < 1e-8
+
+    # ---- 3-D 7-point, z-sharded: lanczos + cg + gmres ----
+    dims = (20, 16, 13); n3 = int(np.prod(dims)); kd = 24
+    L7 = (6.0, -1.0, -1.0, -1.0, -1.0, -1.0, -1.0)
+    A = lk.LinOp.stencil7(ctx, "d", *dims, L7)
+    X = lk.Basis(ctx, "d", A.n, kd + 1, n_global=n3, row0=A.row0)
+    x0 = X.col(0).fill_random("uniform", 45); x0.scal(1.0 / x0.norm())
+    T = np.zeros((kd + 1, kd), order="F")
+    info = lk.lanczos(A, X, T)
+    b = lk.Vector(ctx, "d", A.n, n_global=n3, row0=A.row0).fill_random("uniform", 43)
+    x = lk.Vector(ctx, "d", A.n, n_global=n3, row0=A.row0)
+    cinfo, cmeta = lk.cg(A, b, x, maxiter=500)
+    xg = gather_rows(x.get())
+    A2 = lk.LinOp.stencil7(ctx, "d", *dims, CONVDIFF7)
+    x2 = lk.Vector(ctx, "d", A.n, n_global=n3, row0=A.row0)
+    ginfo, gmeta = lk.gmres(A2, b, x2, kdim=20, maxiter=30)
+    x2g = gather_rows(x2.get())
+    if rank == 0:
+        Xo = np.zeros((n3, kd + 1), order="F"); Xo[:, 0] = lo.fill(n3, "d", "uniform", 45); lo.normalize(Xo[:, 0])
+        To = np.zeros_like(T)
+        assert info == lo.lanczos(lo.Op.stencil("d", dims, L7), Xo, To) == 0
+        assert rel_normwise(T, To) < 1e-10
+        bh = lo.fill(n3, "d", "uniform", 43)
+        xo = np.zeros(n3); oinfo, ometa = lo.cg(lo.Op.stencil("d", dims, L7), bh, xo, maxiter=500)
+        assert cinfo == oinfo > 0
+        assert np.linalg.norm(xg - xo) / np.linalg.norm(xo) < 1e-8
+        xo2 = np.zeros(n3); oinfo2, ometa2 = lo.gmres(lo.Op.stencil("d", dims, CONVDIFF7), bh, xo2, kdim=20, maxiter=30)
+        assert ginfo == oinfo2 > 0
+        assert np.linalg.norm(x2g - xo2) / np.linalg.norm(xo2) < 1e-7
+        print(f"MGPU_OK world={world}", flush=True)
+    ctx.sync()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

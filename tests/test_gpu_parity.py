@@ -211,9 +211,12 @@ def test_arnoldi_config1_dense_n128_kdim64(lk, ctx, oracle, kind):
     # the reference's own assertions (TestKrylov.fypp:218-239)
     assert np.abs(Ah @ Xg[:, :kdim] - Xg @ H).max() < lk.RTOL[kind] * np.abs(Ah).max() * 10
     assert np.abs(Xg.conj().T @ Xg - np.eye(kdim + 1)).max() < orth_tol(kind)
-    ritz_g = np.sort_complex(np.linalg.eigvals(H[:kdim, :kdim].astype(np.complex128)))
-    ritz_o = np.sort_complex(np.linalg.eigvals(Ho[:kdim, :kdim].astype(np.complex128)))
-    assert np.abs(ritz_g - ritz_o).max() / np.abs(ritz_o).max() < tol_for(kind) * 100
+    ritz_g = np.linalg.eigvals(H[:kdim, :kdim].astype(np.complex128))
+    ritz_o = np.linalg.eigvals(Ho[:kdim, :kdim].astype(np.complex128))
+    # nearest-neighbour matching (sorting conjugate pairs is order-unstable); interior Ritz values of a
+    # random non-normal matrix are ill-conditioned, hence the extra factor on top of the H tolerance
+    dist = np.abs(ritz_g[:, None] - ritz_o[None, :]).min(axis=1)
+    assert dist.max() / np.abs(ritz_o).max() < tol_for(kind) * 100
     assert A.counters()[0] == kdim
 
 
