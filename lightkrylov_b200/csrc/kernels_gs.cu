@@ -11,13 +11,42 @@
 namespace lkb {
 
 // ------------------------------------------------------------------------------------------
-// multi-dot:  grid = (nchunks, nrb).  blockIdx.x (fastest-scheduled) selects a chunk of MD_CB
-// basis columns, blockIdx.y a contiguous row range, so the CTAs that share a row range of w are
-// co-resident and w is served from L2 after its first read.  Every thread keeps MD_CB
-// accumulators and issues MD_CB independent 128-bit loads per iteration.
-// Stage 1: warp shuffle -> smem -> one partial row per (row block).  Stage 2: the last CTA to
-// retire (atomic ticket) folds the nrb partial rows in a fixed order => run-to-run deterministic.
+// multi-dot.  Persistent grid of 2 CTAs per SM; every CTA owns a contiguous row range and walks
+// it in tiles of MD_THREADS*PT packs.  Per tile the w packs are loaded ONCE into registers and
+// stay there while the CTA sweeps all j basis columns in chunks of MD_CB: V and w are each read
+// exactly once from HBM ((j+1)*n*s bytes per launch).  Every thread keeps MD_CB accumulators
+// and issues independent 128-bit loads; at the end of a (tile, chunk) the warp folds its
+// MD_CB x 32 partial sums with a transposing butterfly (16 shuffles instead of 80) and adds
+// them to its private row of shared-memory accumulators.
+// Stage 1: fixed-order sum over the CTA's warps -> one partial row per CTA.  Stage 2: the last
+// CTA to retire (atomic ticket) folds the partial rows in fixed order => run-to-run deterministic.
 // ------------------------------------------------------------------------------------------
+template <typename T> LKB_DI T shfl_xor_t(T v, int m);
+template <> LKB_DI float shfl_xor_t<float>(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+template <> LKB_DI double shfl_xor_t<double>(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+template <> LKB_DI float2 shfl_xor_t<float2>(float2 v, int m) {
+    return make_float2(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
+}
+template <> LKB_DI double2 shfl_xor_t<double2>(double2 v, int m) {
+    return make_double2(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
+}
+
+// Transposing warp reduction of 16 per-lane values: afterwards acc[0] of lane l holds the warp
+// total of value index ((l>>4)&1)*8 + ((l>>3)&1)*4 + ((l>>2)&1)*2 + ((l>>1)&1).  Fixed order.
+template <typename E> LKB_DI void warp_fold16(E (&acc)[16], int lane) {
+#pragma unroll
+    for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+        const bool up = (lane & bit) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const E send = up ? acc[i] : acc[i + half];
+            const E keep = up ? acc[i + half] : acc[i];
+            acc[i] = add_v(keep, shfl_xor_t<E>(send, bit));
+        }
+    }
+    acc[0] = add_v(acc[0], shfl_xor_t<E>(acc[0], 1));
+}
+
 template <int K>
 __global__ void __launch_bounds__(MD_THREADS, 2)
 k_multidot(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j,
@@ -29,101 +58,120 @@ k_multidot(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j,
     using W = typename Tr<K>::W;
     constexpr int EPP = Tr<K>::EPP;
     constexpr int CB = MD_CB;
+    constexpr int PT = 4;                       // packs of w held in registers per thread
+    constexpr int NW = MD_THREADS / 32;
     using P = Pack<E, EPP>;
+    static_assert(CB == 16, "warp_fold16 assumes 16 columns per chunk");
     if (flags && flags[F_STOP]) return;
 
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    W* sacc = reinterpret_cast<W*>(smem_raw);   // [NW][jp]
+    __shared__ bool is_last;
     const int jp = j + 1;
-    const int c0 = blockIdx.x * CB;
-    const int ncv = min(CB, j - c0) > 0 ? min(CB, j - c0) : 0;   // basis columns in this chunk
-    const bool do_ww = (blockIdx.x == 0);
-    const int64_t npk = n / EPP;
-    const int64_t per = (npk + gridDim.y - 1) / gridDim.y;
-    const int64_t p0 = (int64_t)blockIdx.y * per;
-    const int64_t p1 = min(npk, p0 + per);
-    const E* vb = V + (int64_t)c0 * ld;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < NW * jp; i += MD_THREADS) sacc[i] = zero_v(W());
+    __syncthreads();
+    W* myacc = sacc + wid * jp;
+    const int fold_idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 
-    E acc[CB];
-#pragma unroll
-    for (int i = 0; i < CB; ++i) acc[i] = zero_v(E());
+    const int64_t npk = n / EPP;
+    constexpr int64_t TILE = (int64_t)MD_THREADS * PT;
+    const int64_t ntiles = (npk + TILE - 1) / TILE;
+    const int64_t tper = (ntiles + gridDim.x - 1) / gridDim.x;
+    const int64_t t0 = (int64_t)blockIdx.x * tper;
+    const int64_t t1 = min(ntiles, t0 + tper);
+    const int nchunk = (j + CB - 1) / CB;
     E accw = zero_v(E());
 
-    if (ncv == CB) {
-        for (int64_t pk = p0 + threadIdx.x; pk < p1; pk += MD_THREADS) {
-            const int64_t off = pk * EPP;
-            const P wv = ld_pack_nc<P>(w + off);
-            P v[CB];
+    for (int64_t t = t0; t < t1; ++t) {
+        const int64_t base = t * TILE + threadIdx.x;
+        const bool full = (t + 1) * TILE <= npk;
+        P wv[PT];
 #pragma unroll
-            for (int i = 0; i < CB; ++i) v[i] = ld_pack_nc<P>(vb + (int64_t)i * ld + off);
+        for (int q = 0; q < PT; ++q) {
+            const int64_t pk = base + (int64_t)q * MD_THREADS;
+            if (full || pk < npk) wv[q] = ld_pack_nc<P>(w + pk * EPP);
+            else {
 #pragma unroll
-            for (int i = 0; i < CB; ++i)
+                for (int e = 0; e < EPP; ++e) wv[q].v[e] = zero_v(E());
+            }
 #pragma unroll
-                for (int e = 0; e < EPP; ++e) fma_conj(acc[i], v[i].v[e], wv.v[e]);
-            if (do_ww)
-#pragma unroll
-                for (int e = 0; e < EPP; ++e) fma_conj(accw, wv.v[e], wv.v[e]);
+            for (int e = 0; e < EPP; ++e) fma_conj(accw, wv[q].v[e], wv[q].v[e]);
         }
-    } else {
-        for (int64_t pk = p0 + threadIdx.x; pk < p1; pk += MD_THREADS) {
-            const int64_t off = pk * EPP;
-            const P wv = ld_pack_nc<P>(w + off);
+        for (int c = 0; c < nchunk; ++c) {
+            const int c0 = c * CB;
+            const int ncv = min(CB, j - c0);
+            const E* vb = V + (int64_t)c0 * ld;
+            E acc[CB];
 #pragma unroll
-            for (int i = 0; i < CB; ++i) {
-                if (i < ncv) {
-                    const P v = ld_pack_nc<P>(vb + (int64_t)i * ld + off);
+            for (int i = 0; i < CB; ++i) acc[i] = zero_v(E());
+            if (full && ncv == CB) {
 #pragma unroll
-                    for (int e = 0; e < EPP; ++e) fma_conj(acc[i], v.v[e], wv.v[e]);
+                for (int q = 0; q < PT; ++q) {
+                    const int64_t off = (base + (int64_t)q * MD_THREADS) * EPP;
+                    P v[CB];
+#pragma unroll
+                    for (int i = 0; i < CB; ++i) v[i] = ld_pack_nc<P>(vb + (int64_t)i * ld + off);
+#pragma unroll
+                    for (int i = 0; i < CB; ++i)
+#pragma unroll
+                        for (int e = 0; e < EPP; ++e) fma_conj(acc[i], v[i].v[e], wv[q].v[e]);
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < PT; ++q) {
+                    const int64_t pk = base + (int64_t)q * MD_THREADS;
+                    if (pk < npk) {
+                        const int64_t off = pk * EPP;
+#pragma unroll
+                        for (int i = 0; i < CB; ++i) {
+                            if (i < ncv) {
+                                const P v = ld_pack_nc<P>(vb + (int64_t)i * ld + off);
+#pragma unroll
+                                for (int e = 0; e < EPP; ++e) fma_conj(acc[i], v.v[e], wv[q].v[e]);
+                            }
+                        }
+                    }
                 }
             }
-            if (do_ww)
-#pragma unroll
-                for (int e = 0; e < EPP; ++e) fma_conj(accw, wv.v[e], wv.v[e]);
+            warp_fold16<E>(acc, lane);
+            if ((lane & 1) == 0 && fold_idx < ncv) wadd(myacc[c0 + fold_idx], widen(acc[0]));
         }
     }
-    // ragged tail (n not a multiple of the pack width): one thread of row block 0
-    if (blockIdx.y == 0 && threadIdx.x == 0) {
-        for (int64_t t = npk * EPP; t < n; ++t) {
-            const E wt = w[t];
-#pragma unroll
-            for (int i = 0; i < CB; ++i)
-                if (i < ncv) fma_conj(acc[i], vb[(int64_t)i * ld + t], wt);
-            if (do_ww) fma_conj(accw, wt, wt);
+    // ragged tail (n not a multiple of the pack width): one thread of CTA 0
+    __syncwarp();
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int64_t r = npk * EPP; r < n; ++r) {
+            const E wt = w[r];
+            for (int i = 0; i < j; ++i) {
+                E a = zero_v(E());
+                fma_conj(a, V[(int64_t)i * ld + r], wt);
+                wadd(myacc[i], widen(a));
+            }
+            fma_conj(accw, wt, wt);
         }
-    }
-
-    // ---- stage 1: CTA reduction in fixed order ----
-    __shared__ W sm[MD_THREADS / 32][CB + 1];
-    __shared__ bool is_last;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-    for (int i = 0; i < CB; ++i) {
-        W a = warp_sum(widen(acc[i]));
-        if (lane == 0) sm[wid][i] = a;
     }
     {
         W a = warp_sum(widen(accw));
-        if (lane == 0) sm[wid][CB] = a;
+        if (lane == 0) wadd(myacc[j], a);
     }
+    // ---- stage 1: fixed-order sum over the warps of this CTA ----
     __syncthreads();
-    if (threadIdx.x <= CB) {
-        const int i = threadIdx.x;
-        W a = sm[0][i];
+    for (int i = threadIdx.x; i < jp; i += MD_THREADS) {
+        W a = sacc[i];
 #pragma unroll
-        for (int q = 1; q < MD_THREADS / 32; ++q) wadd(a, sm[q][i]);
-        if (i < ncv) partial[(int64_t)blockIdx.y * jp + c0 + i] = a;
-        else if (i == CB && do_ww) partial[(int64_t)blockIdx.y * jp + j] = a;
+        for (int q = 1; q < NW; ++q) wadd(a, sacc[q * jp + i]);
+        partial[(int64_t)blockIdx.x * jp + i] = a;
     }
     // ---- stage 2: last CTA folds the partial rows ----
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned total = gridDim.x * gridDim.y;
-        is_last = (atomicAdd(counter, 1u) == total - 1u);
-    }
+    if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1u);
     __syncthreads();
     if (is_last) {
         __threadfence();
-        const int nrb = gridDim.y;
-        for (int col = wid; col < jp; col += MD_THREADS / 32) {
+        const int nrb = gridDim.x;
+        for (int col = wid; col < jp; col += NW) {
             W a = zero_v(W());
             for (int b = lane; b < nrb; b += 32) wadd(a, __ldcg(&partial[(int64_t)b * jp + col]));
             a = warp_sum(a);
@@ -226,25 +274,20 @@ k_multiaxpy(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j,
 }
 
 // ------------------------------------------------------------------------------------------
-static inline int grid_rowblocks(int64_t npk, int nchunks, int sms) {
-    // Fixed function of the problem (not of timing): 2 resident CTAs per SM, ~2 waves.
-    int target = (2 * sms * 2 + nchunks - 1) / nchunks;
-    if (target < 1) target = 1;
-    int64_t maxrb = (npk + MD_THREADS - 1) / MD_THREADS;   // at least one pack per thread
-    if (maxrb < 1) maxrb = 1;
-    if (target > maxrb) target = (int)maxrb;
-    if (target > MAX_ROWBLOCKS) target = MAX_ROWBLOCKS;
-    return target;
-}
-
 template <int K>
 static void multidot_t(cudaStream_t s, const void* V, int64_t ld, int j, const void* w, int64_t n,
                        void* partial, void* out, unsigned* counter, const int* flags, int sms) {
     using E = typename Tr<K>::E; using W = typename Tr<K>::W;
-    const int nchunks = j > 0 ? (j + MD_CB - 1) / MD_CB : 1;
-    const int nrb = grid_rowblocks(n / Tr<K>::EPP, nchunks, sms);
-    dim3 grid(nchunks, nrb);
-    k_multidot<K><<<grid, MD_THREADS, 0, s>>>((const E*)V, ld, j, (const E*)w, n, (W*)partial, (W*)out, counter, flags);
+    // grid: fixed function of the problem size (2 resident CTAs per SM), never of timing
+    const int64_t ntiles = (n / Tr<K>::EPP + (int64_t)MD_THREADS * 4 - 1) / ((int64_t)MD_THREADS * 4);
+    int64_t nb = 2 * (int64_t)sms;
+    if (nb > ntiles) nb = ntiles;
+    if (nb < 1) nb = 1;
+    if (nb > MAX_ROWBLOCKS) nb = MAX_ROWBLOCKS;
+    const size_t sh = (size_t)(MD_THREADS / 32) * (size_t)(j + 1) * sizeof(W);
+    static const bool attr_once = (cudaFuncSetAttribute(k_multidot<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024), true);
+    (void)attr_once;
+    k_multidot<K><<<(int)nb, MD_THREADS, sh, s>>>((const E*)V, ld, j, (const E*)w, n, (W*)partial, (W*)out, counter, flags);
 }
 void launch_multidot(int kind, cudaStream_t s, const void* V, int64_t ld, int j, const void* w, int64_t n,
                      void* partial, void* out, unsigned* counter, const int* flags, int sms) {
