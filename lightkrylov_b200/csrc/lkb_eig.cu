@@ -1,11 +1,451 @@
-// lkb_eig.cu -- eigs / eighs / svds / krylov_schur host shells (placeholder: filled in below)
+// lkb_eig.cu -- eigs / eighs / svds / krylov_schur: host shells around the device Krylov step.
+//
+//   eigs         src/IterativeSolvers/IterativeSolvers.fypp:972-1143
+//   krylov_schur src/Krylov/BaseKrylov.fypp:782-834
+//   eighs        src/IterativeSolvers/EIGHS/eighs.fypp:29-126
+//   svds         src/IterativeSolvers/SVDS/svd_solvers.fypp:28-121
+//   eig/ordschur src/Utilities/submodule_utility_functions.fypp:55-117
+//
+// The k x k algebra (k <= kdim) stays on the host as in the reference, which gets it from
+// stdlib_linalg_lapack (geev, gees, trsen, syev/heev, gesdd; fortran-lang/stdlib, version unpinned
+// in fpm.toml:25).  Here a Fortran-ABI LAPACK is resolved at run time with dlopen
+// (lkb_set_lapack); matrices of the single-precision kinds are promoted to double for these
+// O(k^3) host steps and rounded back.  All O(n) work (basis update X Z, Ritz-vector assembly) is
+// the tall-skinny device GEMM in kernels_gemm.cu.
+#include <dlfcn.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <complex>
+#include <numeric>
+#include <string>
+#include <vector>
 #include "../../include/lkb.h"
 #include "lkb_internal.h"
+
 using namespace lkb;
-extern "C" {
-int lkb_set_lapack(const char*, const char*, const char*) { set_error("lkb_set_lapack: not implemented yet"); return LKB_ERR_LAPACK; }
-int lkb_krylov_schur(lkb_basis_t, void*, int, int, int32_t*) { set_error("krylov_schur: not implemented yet"); return LKB_ERR_LAPACK; }
-int lkb_eigs(lkb_op_t, lkb_basis_t, int, double*, double*, int32_t*, lkb_vec_t, int32_t, double, int32_t) { set_error("eigs: not implemented yet"); return LKB_ERR_LAPACK; }
-int lkb_eighs(lkb_op_t, lkb_basis_t, int, double*, double*, int32_t*, lkb_vec_t, int32_t, double) { set_error("eighs: not implemented yet"); return LKB_ERR_LAPACK; }
-int lkb_svds(lkb_op_t, lkb_basis_t, double*, lkb_basis_t, int, double*, int32_t*, lkb_vec_t, int32_t, double) { set_error("svds: not implemented yet"); return LKB_ERR_LAPACK; }
+typedef std::complex<double> cd;
+typedef int lint;   // LP64 LAPACK
+
+namespace {
+
+struct Lapack {
+    void* h = nullptr;
+    void (*dgeev)(const char*, const char*, const lint*, double*, const lint*, double*, double*, double*, const lint*,
+                  double*, const lint*, double*, const lint*, lint*, size_t, size_t) = nullptr;
+    void (*zgeev)(const char*, const char*, const lint*, cd*, const lint*, cd*, cd*, const lint*, cd*, const lint*,
+                  cd*, const lint*, double*, lint*, size_t, size_t) = nullptr;
+    void (*dgees)(const char*, const char*, void*, const lint*, double*, const lint*, lint*, double*, double*, double*,
+                  const lint*, double*, const lint*, lint*, lint*, size_t, size_t) = nullptr;
+    void (*zgees)(const char*, const char*, void*, const lint*, cd*, const lint*, lint*, cd*, cd*, const lint*, cd*,
+                  const lint*, double*, lint*, lint*, size_t, size_t) = nullptr;
+    void (*dtrsen)(const char*, const char*, const lint*, const lint*, double*, const lint*, double*, const lint*,
+                   double*, double*, lint*, double*, double*, double*, const lint*, lint*, const lint*, lint*, size_t,
+                   size_t) = nullptr;
+    void (*ztrsen)(const char*, const char*, const lint*, const lint*, cd*, const lint*, cd*, const lint*, cd*, lint*,
+                   double*, double*, cd*, const lint*, lint*, size_t, size_t) = nullptr;
+    void (*dsyev)(const char*, const char*, const lint*, double*, const lint*, double*, double*, const lint*, lint*,
+                  size_t, size_t) = nullptr;
+    void (*zheev)(const char*, const char*, const lint*, cd*, const lint*, double*, cd*, const lint*, double*, lint*,
+                  size_t, size_t) = nullptr;
+    void (*dgesdd)(const char*, const lint*, const lint*, double*, const lint*, double*, double*, const lint*, double*,
+                   const lint*, double*, const lint*, lint*, lint*, size_t) = nullptr;
+    void (*zgesdd)(const char*, const lint*, const lint*, cd*, const lint*, double*, cd*, const lint*, cd*, const lint*,
+                   cd*, const lint*, double*, lint*, lint*, size_t) = nullptr;
+};
+Lapack g_la;
+
+int lapack_open(const char* path, const char* prefix, const char* suffix) {
+    void* h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+    if (!h) { set_error("cannot dlopen LAPACK provider %s: %s", path, dlerror()); return LKB_ERR_LAPACK; }
+    Lapack la; la.h = h;
+    auto sym = [&](const char* name) -> void* {
+        std::string s = std::string(prefix ? prefix : "") + name + (suffix ? suffix : "");
+        return dlsym(h, s.c_str());
+    };
+#define LA(f) *(void**)(&la.f) = sym(#f); if (!la.f) { set_error("LAPACK provider %s lacks %s%s%s", path, prefix ? prefix : "", #f, suffix ? suffix : ""); dlclose(h); return LKB_ERR_LAPACK; }
+    LA(dgeev) LA(zgeev) LA(dgees) LA(zgees) LA(dtrsen) LA(ztrsen) LA(dsyev) LA(zheev) LA(dgesdd) LA(zgesdd)
+#undef LA
+    g_la = la;
+    return 0;
 }
+int lapack_ready() {
+    if (g_la.h) return 0;
+    if (const char* env = getenv("LKB_LAPACK_LIB")) {
+        const char* pre = getenv("LKB_LAPACK_PREFIX"); const char* suf = getenv("LKB_LAPACK_SUFFIX");
+        if (lapack_open(env, pre ? pre : "", suf ? suf : "_") == 0) return 0;
+    }
+    for (const char* p : {"liblapack.so.3", "libopenblas.so.0", "libopenblas.so", "liblapack.so"})
+        if (lapack_open(p, "", "_") == 0) return 0;
+    set_error("no host LAPACK provider: call lkb_set_lapack(path, prefix, suffix) or set LKB_LAPACK_LIB");
+    return LKB_ERR_LAPACK;
+}
+
+cd load_kind(int kind, const void* H, size_t idx) {
+    switch (kind) {
+        case KS: return cd(((const float*)H)[idx], 0.0);
+        case KD: return cd(((const double*)H)[idx], 0.0);
+        case KC: return cd(((const float*)H)[2 * idx], ((const float*)H)[2 * idx + 1]);
+        default: return cd(((const double*)H)[2 * idx], ((const double*)H)[2 * idx + 1]);
+    }
+}
+void store_kind(int kind, void* H, size_t idx, cd v) {
+    switch (kind) {
+        case KS: ((float*)H)[idx] = (float)v.real(); break;
+        case KD: ((double*)H)[idx] = v.real(); break;
+        case KC: ((float*)H)[2 * idx] = (float)v.real(); ((float*)H)[2 * idx + 1] = (float)v.imag(); break;
+        default: ((double*)H)[2 * idx] = v.real(); ((double*)H)[2 * idx + 1] = v.imag(); break;
+    }
+}
+
+// eig(A(:k,:k)) -> vals (complex), vecs in LAPACK layout: for real kinds the REAL-pair convention
+// (column i = Re, i+1 = Im of the pair), stored in the real parts of `vecs`.
+int host_eig(bool cplx, int k, const std::vector<cd>& A, int lda, std::vector<cd>& vals, std::vector<cd>& vecs) {
+    LKB_TRY(lapack_ready());
+    vals.assign(k, cd(0)); vecs.assign((size_t)k * k, cd(0));
+    lint n = k, ldvl = 1, ldvr = k, info = 0;
+    if (cplx) {
+        std::vector<cd> a((size_t)k * k), work(std::max(1, 4 * k)); std::vector<double> rwork(2 * k);
+        for (int j = 0; j < k; ++j) for (int i = 0; i < k; ++i) a[i + (size_t)k * j] = A[i + (size_t)lda * j];
+        cd vl; lint lwork = (lint)work.size();
+        g_la.zgeev("N", "V", &n, a.data(), &n, vals.data(), &vl, &ldvl, vecs.data(), &ldvr, work.data(), &lwork, rwork.data(), &info, 1, 1);
+    } else {
+        std::vector<double> a((size_t)k * k), wr(k), wi(k), vr((size_t)k * k), work(std::max(1, 8 * k));
+        for (int j = 0; j < k; ++j) for (int i = 0; i < k; ++i) a[i + (size_t)k * j] = A[i + (size_t)lda * j].real();
+        double vl; lint lwork = (lint)work.size();
+        g_la.dgeev("N", "V", &n, a.data(), &n, wr.data(), wi.data(), &vl, &ldvl, vr.data(), &ldvr, work.data(), &lwork, &info, 1, 1);
+        for (int i = 0; i < k; ++i) vals[i] = cd(wr[i], wi[i]);
+        for (size_t t = 0; t < vr.size(); ++t) vecs[t] = cd(vr[t], 0.0);
+    }
+    if (info != 0) { set_error("GEEV failed, info = %d", (int)info); return LKB_ERR_LAPACK; }
+    return 0;
+}
+
+// stable ascending sort + reversal == stdlib sort_index(..., reverse=.true.)
+std::vector<int> sort_index_reverse(const std::vector<double>& key) {
+    std::vector<int> idx(key.size());
+    std::iota(idx.begin(), idx.end(), 0);
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return key[a] < key[b]; });
+    std::reverse(idx.begin(), idx.end());
+    return idx;
+}
+
+// Y(:, 0:p) = Xw(:, 0:k) Zc(0:k, 0:p) on the device; Zc given on the host as complex doubles
+int device_combine(lkb_basis_s* Xw, int k, const std::vector<cd>& Zc, int ldz, int p, void* Yd, int64_t ldy) {
+    lkb_ctx_s* c = Xw->ctx;
+    const int kind = Xw->kind;
+    const size_t es = kind_size(kind);
+    LKB_TRY(ensure_hstage(c, (size_t)k * p * es + 4096));
+    LKB_TRY(ensure_coefd(c, std::max((size_t)k * p * es, (size_t)4096)));
+    LKB_CUDA(cudaStreamSynchronize(c->stream));
+    for (int q = 0; q < p; ++q) for (int i = 0; i < k; ++i) store_kind(kind, c->hstage, (size_t)i + (size_t)k * q, Zc[i + (size_t)ldz * q]);
+    LKB_CUDA(cudaMemcpyAsync(c->coefd, c->hstage, (size_t)k * p * es, cudaMemcpyHostToDevice, c->stream));
+    prof_begin(c, PC_OTHER);
+    launch_basis_gemm(kind, c->stream, Xw->d, Xw->ld, k, c->coefd, k, p, Yd, ldy, Xw->n, c->sms);
+    prof_end(c, PC_OTHER, 1);
+    return check_launch(c, "basis_gemm");
+}
+
+int start_vector(lkb_basis_s* Xw, lkb_vec_t x0) {
+    lkb_ctx_s* c = Xw->ctx;
+    const int kind = Xw->kind;
+    LKB_TRY(lkb_basis_zero(Xw, 0, Xw->ncols));
+    if (x0) {
+        if (x0->n != Xw->n || x0->kind != kind) { set_error("x0: size/kind mismatch"); return LKB_ERR_ARG; }
+        launch_axpby(kind, c->stream, Scalar{1, 0}, x0->d, Scalar{0, 0}, Xw->d, Xw->n, c->sms);   // copy(Xwrk(1), x0)
+        c->launches++;
+    } else {
+        launch_fill(kind, c->stream, Xw->d, Xw->n, Xw->row0, LKB_DIST_NORMAL, next_seed(c), c->sms);   // rand(.true.)
+        c->launches++;
+    }
+    double nrm = 0;
+    LKB_TRY(vec_norm_sync(c, kind, Xw->d, Xw->n, &nrm));
+    launch_scal(kind, c->stream, Scalar{1.0 / nrm, 0}, Xw->d, Xw->n, c->sms);
+    c->launches++;
+    return check_launch(c, "start vector");
+}
+
+}  // namespace
+
+extern "C" {
+
+int lkb_set_lapack(const char* path, const char* prefix, const char* suffix) {
+    if (!path) return LKB_ERR_ARG;
+    return lapack_open(path, prefix ? prefix : "", suffix ? suffix : "_");
+}
+
+// krylov_schur(n, X, H, median_selector): BaseKrylov.fypp:782-834 + IterativeSolvers.fypp:1136-1141
+int lkb_krylov_schur(lkb_basis_t X, void* H, int ldh, int kdim, int32_t* nkeep) {
+    if (!X || !H || !nkeep || kdim < 1 || X->ncols < kdim + 1 || ldh < kdim + 1) { set_error("krylov_schur: bad arguments"); return LKB_ERR_ARG; }
+    LKB_TRY(lapack_ready());
+    lkb_ctx_s* c = X->ctx;
+    const int kind = X->kind;
+    const bool cplx = kind_cplx(kind);
+    const size_t es = kind_size(kind);
+    const int k = kdim;
+    lint n = k, sdim = 0, info = 0, m = 0;
+    std::vector<cd> ev(k), Zc((size_t)k * k), Tc((size_t)k * k);
+    std::vector<lint> sel(k, 0);
+    double s_ = 0, sep = 0;
+    if (cplx) {
+        std::vector<cd> T((size_t)k * k), Z((size_t)k * k), work(std::max(1, 4 * k)); std::vector<double> rwork(k);
+        for (int j = 0; j < k; ++j) for (int i = 0; i < k; ++i) T[i + (size_t)k * j] = load_kind(kind, H, (size_t)i + (size_t)ldh * j);
+        lint lwork = (lint)work.size(); lint bwork = 0;
+        g_la.zgees("V", "N", nullptr, &n, T.data(), &n, &sdim, ev.data(), Z.data(), &n, work.data(), &lwork, rwork.data(), &bwork, &info, 1, 1);
+        if (info != 0) { set_error("GEES failed, info = %d", (int)info); return LKB_ERR_LAPACK; }
+        std::vector<double> av(k); for (int i = 0; i < k; ++i) av[i] = std::abs(ev[i]);
+        std::vector<double> srt(av); std::sort(srt.begin(), srt.end());
+        const double med = (k % 2) ? srt[k / 2] : 0.5 * (srt[k / 2 - 1] + srt[k / 2]);
+        int cnt = 0; for (int i = 0; i < k; ++i) { sel[i] = av[i] > med; cnt += sel[i]; }
+        *nkeep = cnt;
+        std::vector<cd> w(k), wk(std::max(1, k)); lint lw = (lint)wk.size();
+        g_la.ztrsen("N", "V", sel.data(), &n, T.data(), &n, Z.data(), &n, w.data(), &m, &s_, &sep, wk.data(), &lw, &info, 1, 1);
+        if (info != 0) { set_error("TRSEN failed, info = %d", (int)info); return LKB_ERR_LAPACK; }
+        Tc = T; Zc = Z;
+    } else {
+        std::vector<double> T((size_t)k * k), Z((size_t)k * k), wr(k), wi(k), work(std::max(1, 8 * k));
+        for (int j = 0; j < k; ++j) for (int i = 0; i < k; ++i) T[i + (size_t)k * j] = load_kind(kind, H, (size_t)i + (size_t)ldh * j).real();
+        lint lwork = (lint)work.size(); lint bwork = 0;
+        g_la.dgees("V", "N", nullptr, &n, T.data(), &n, &sdim, wr.data(), wi.data(), Z.data(), &n, work.data(), &lwork, &bwork, &info, 1, 1);
+        if (info != 0) { set_error("GEES failed, info = %d", (int)info); return LKB_ERR_LAPACK; }
+        std::vector<double> av(k); for (int i = 0; i < k; ++i) av[i] = hypot(wr[i], wi[i]);
+        std::vector<double> srt(av); std::sort(srt.begin(), srt.end());
+        const double med = (k % 2) ? srt[k / 2] : 0.5 * (srt[k / 2 - 1] + srt[k / 2]);
+        int cnt = 0; for (int i = 0; i < k; ++i) { sel[i] = av[i] > med; cnt += sel[i]; }
+        *nkeep = cnt;
+        std::vector<double> wk(std::max(1, k)); lint lw = (lint)wk.size(); std::vector<lint> iwork(std::max(1, k)); lint liw = 1;
+        g_la.dtrsen("N", "V", sel.data(), &n, T.data(), &n, Z.data(), &n, wr.data(), wi.data(), &m, &s_, &sep, wk.data(), &lw, iwork.data(), &liw, &info, 1, 1);
+        if (info != 0) { set_error("TRSEN failed, info = %d", (int)info); return LKB_ERR_LAPACK; }
+        for (size_t t = 0; t < T.size(); ++t) { Tc[t] = T[t]; Zc[t] = Z[t]; }
+    }
+    const int nk = *nkeep;
+    // basis: X(:n) <- X(:kdim) Z(:, :n) ; X(n+1) <- X(kdim+1) ; X(n+2:) = 0
+    if (nk > 0) {
+        void* tmp = nullptr;
+        LKB_CUDA(cudaMalloc(&tmp, (size_t)X->ld * nk * es));
+        int r = device_combine(X, k, Zc, k, nk, tmp, X->ld);
+        if (r == 0 && cudaMemcpyAsync(X->d, tmp, (size_t)X->ld * nk * es, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess) r = LKB_ERR_CUDA;
+        cudaStreamSynchronize(c->stream);
+        cudaFree(tmp);
+        if (r) return r;
+    }
+    LKB_CUDA(cudaMemcpyAsync(col_ptr(X, nk), col_ptr(X, k), (size_t)X->n * es, cudaMemcpyDeviceToDevice, c->stream));
+    if (nk + 1 < X->ncols) LKB_TRY(lkb_basis_zero(X, nk + 1, X->ncols - nk - 1));
+    // Hessenberg: H(:k,:) = T ; b = H(k+1,:) Z ; H(n+1,:) = b ; H(n+2:,:) = 0 ; H(:, n+1:) = 0
+    std::vector<cd> b(k, cd(0));
+    for (int j = 0; j < k; ++j) for (int i = 0; i < k; ++i) b[j] += load_kind(kind, H, (size_t)k + (size_t)ldh * i) * Zc[i + (size_t)k * j];
+    for (int j = 0; j < k; ++j) for (int i = 0; i < k; ++i) store_kind(kind, H, (size_t)i + (size_t)ldh * j, Tc[i + (size_t)k * j]);
+    for (int j = 0; j < k; ++j) store_kind(kind, H, (size_t)nk + (size_t)ldh * j, b[j]);
+    for (int j = 0; j < k; ++j) for (int i = nk + 1; i < k + 1; ++i) store_kind(kind, H, (size_t)i + (size_t)ldh * j, cd(0));
+    for (int j = nk; j < k; ++j) for (int i = 0; i < k + 1; ++i) store_kind(kind, H, (size_t)i + (size_t)ldh * j, cd(0));
+    return 0;
+}
+
+int lkb_eigs(lkb_op_t A, lkb_basis_t X, int nev, double* eigvals, double* residuals, int32_t* info, lkb_vec_t x0,
+             int32_t kdim, double tolerance, int32_t transpose) {
+    if (!A || !X || !eigvals || !residuals || !info || nev < 1 || X->ncols < nev) { set_error("eigs: bad arguments"); return LKB_ERR_ARG; }
+    LKB_TRY(lapack_ready());
+    lkb_ctx_s* c = X->ctx;
+    const int kind = X->kind;
+    const bool cplx = kind_cplx(kind);
+    const size_t es = kind_size(kind);
+    const int kd = kdim > 0 ? kdim : 4 * nev;
+    const double tol = tolerance >= 0 ? tolerance : rtol_of(kind);
+    lkb_basis_t Xw = nullptr;
+    LKB_TRY(lkb_basis_create(c, kind, X->n, X->n_global, X->row0, kd + 1, &Xw));
+    int rc = 0;
+    auto cleanup = [&](int r) { lkb_basis_destroy(Xw); return r; };
+#define EG_TRY(call) do { rc = (call); if (rc) return cleanup(rc); } while (0)
+    EG_TRY(start_vector(Xw, x0));
+    const int ldh = kd + 1;
+    std::vector<char> H((size_t)ldh * kd * es, 0);
+    std::vector<cd> vals, vecs, Hc((size_t)kd * kd);
+    std::vector<double> res(kd, 0.0);
+    int kstart = 1, conv = 0, niter = 0, k = 1;
+    auto load_Hc = [&](int kk) {
+        for (int j = 0; j < kk; ++j) for (int i = 0; i < kk; ++i) Hc[i + (size_t)kd * j] = load_kind(kind, H.data(), (size_t)i + (size_t)ldh * j);
+    };
+    while (conv < nev) {
+        for (k = kstart; k <= kd; ++k) {
+            int32_t ainfo = 0;
+            EG_TRY(lkb_arnoldi(A, Xw, H.data(), ldh, &ainfo, k, k, -1.0, transpose, 1));
+            load_Hc(k);
+            EG_TRY(host_eig(cplx, k, Hc, kd, vals, vecs));
+            const cd beta = load_kind(kind, H.data(), (size_t)k + (size_t)ldh * (k - 1));
+            std::fill(res.begin(), res.end(), 0.0);
+            for (int i = 0; i < k; ++i) {
+                double alpha;
+                if (cplx) alpha = std::abs(vecs[(k - 1) + (size_t)k * i]);
+                else if (vals[i].imag() > 0) alpha = hypot(vecs[(k - 1) + (size_t)k * i].real(), vecs[(k - 1) + (size_t)k * (i + 1)].real());
+                else if (vals[i].imag() < 0) alpha = hypot(vecs[(k - 1) + (size_t)k * (i - 1)].real(), vecs[(k - 1) + (size_t)k * i].real());
+                else alpha = fabs(vecs[(k - 1) + (size_t)k * i].real());
+                res[i] = std::abs(beta) * alpha;
+            }
+            niter++;
+            conv = 0; for (int i = 0; i < k; ++i) conv += res[i] < tol;
+            if (conv >= nev) break;
+        }
+        if (conv >= nev) break;
+        // Krylov-Schur restart (IterativeSolvers.fypp:1096-1100); note the loop index is kd+1 here
+        int32_t nk = 0;
+        EG_TRY(lkb_krylov_schur(Xw, H.data(), ldh, kd, &nk));
+        kstart = nk + 1;
+        k = kd + 1;
+    }
+    // post-process (:1108-1132)
+    k = std::min(k, kd);
+    load_Hc(k);
+    EG_TRY(host_eig(cplx, k, Hc, kd, vals, vecs));
+    std::vector<double> av(kd, 0.0);
+    for (int i = 0; i < k; ++i) av[i] = std::abs(vals[i]);
+    std::vector<int> idx = sort_index_reverse(av);
+    std::vector<cd> Y((size_t)k * nev, cd(0));
+    for (int i = 0; i < nev; ++i) {
+        const int s = idx[i];
+        cd v = s < k ? vals[s] : cd(0);
+        eigvals[2 * i] = v.real(); eigvals[2 * i + 1] = v.imag();
+        residuals[i] = res[s];
+        if (s < k) for (int j = 0; j < k; ++j) Y[j + (size_t)k * i] = vecs[j + (size_t)k * s];
+    }
+    EG_TRY(device_combine(Xw, k, Y, k, nev, X->d, X->ld));
+    EG_TRY(lkb_sync(c));
+    *info = niter;
+#undef EG_TRY
+    return cleanup(0);
+}
+
+int lkb_eighs(lkb_op_t A, lkb_basis_t X, int nev, double* eigvals, double* residuals, int32_t* info, lkb_vec_t x0,
+              int32_t kdim, double tolerance) {
+    if (!A || !X || !eigvals || !residuals || !info || nev < 1 || X->ncols < nev) { set_error("eighs: bad arguments"); return LKB_ERR_ARG; }
+    LKB_TRY(lapack_ready());
+    lkb_ctx_s* c = X->ctx;
+    const int kind = X->kind;
+    const bool cplx = kind_cplx(kind);
+    const size_t es = kind_size(kind);
+    const int kd = kdim > 0 ? kdim : 4 * nev;
+    const double tol = tolerance >= 0 ? tolerance : rtol_of(kind);
+    lkb_basis_t Xw = nullptr;
+    LKB_TRY(lkb_basis_create(c, kind, X->n, X->n_global, X->row0, kd + 1, &Xw));
+    int rc = 0;
+    auto cleanup = [&](int r) { lkb_basis_destroy(Xw); return r; };
+#define EH_TRY(call) do { rc = (call); if (rc) return cleanup(rc); } while (0)
+    EH_TRY(start_vector(Xw, x0));
+    const int ldt = kd + 1;
+    std::vector<char> T((size_t)ldt * kd * es, 0);
+    std::vector<double> ev(kd, 0.0), res(kd, 0.0);
+    std::vector<cd> vecs((size_t)kd * kd, cd(0));
+    int k = 1, conv = 0;
+    for (k = 1; k <= kd; ++k) {
+        int32_t linfo = 0;
+        EH_TRY(lkb_lanczos(A, Xw, T.data(), ldt, &linfo, k, k, -1.0));
+        std::fill(ev.begin(), ev.end(), 0.0); std::fill(vecs.begin(), vecs.end(), cd(0));
+        lint n = k, linf = 0;
+        if (cplx) {
+            std::vector<cd> a((size_t)k * k), work(std::max(1, 4 * k)); std::vector<double> rwork(std::max(1, 3 * k));
+            for (int j = 0; j < k; ++j) for (int i = 0; i < k; ++i) a[i + (size_t)k * j] = load_kind(kind, T.data(), (size_t)i + (size_t)ldt * j);
+            lint lwork = (lint)work.size();
+            g_la.zheev("V", "L", &n, a.data(), &n, ev.data(), work.data(), &lwork, rwork.data(), &linf, 1, 1);
+            for (int j = 0; j < k; ++j) for (int i = 0; i < k; ++i) vecs[i + (size_t)kd * j] = a[i + (size_t)k * j];
+        } else {
+            std::vector<double> a((size_t)k * k), work(std::max(1, 8 * k));
+            for (int j = 0; j < k; ++j) for (int i = 0; i < k; ++i) a[i + (size_t)k * j] = load_kind(kind, T.data(), (size_t)i + (size_t)ldt * j).real();
+            lint lwork = (lint)work.size();
+            g_la.dsyev("V", "L", &n, a.data(), &n, ev.data(), work.data(), &lwork, &linf, 1, 1);
+            for (int j = 0; j < k; ++j) for (int i = 0; i < k; ++i) vecs[i + (size_t)kd * j] = a[i + (size_t)k * j];
+        }
+        if (linf != 0) { set_error("SYEV/HEEV failed, info = %d", (int)linf); return cleanup(LKB_ERR_LAPACK); }
+        const cd beta = load_kind(kind, T.data(), (size_t)k + (size_t)ldt * (k - 1));
+        std::fill(res.begin(), res.end(), 0.0);
+        for (int i = 0; i < k; ++i) res[i] = std::abs(beta * vecs[(k - 1) + (size_t)kd * i]);
+        conv = 0; for (int i = 0; i < k; ++i) conv += res[i] < tol;
+        if (conv >= nev) break;
+    }
+    std::vector<int> idx = sort_index_reverse(ev);        // over all kdim_ entries, zero padding included (eighs.fypp:106-107)
+    k = std::min(k, kd);
+    std::vector<cd> Y((size_t)k * nev, cd(0));
+    for (int i = 0; i < nev; ++i) {
+        const int s = idx[i];
+        eigvals[i] = ev[s]; residuals[i] = res[s];
+        for (int j = 0; j < k; ++j) Y[j + (size_t)k * i] = vecs[j + (size_t)kd * s];
+    }
+    EH_TRY(device_combine(Xw, k, Y, k, nev, X->d, X->ld));
+    EH_TRY(lkb_sync(c));
+    *info = k;
+#undef EH_TRY
+    return cleanup(0);
+}
+
+int lkb_svds(lkb_op_t A, lkb_basis_t U, double* S, lkb_basis_t V, int nsv, double* residuals, int32_t* info,
+             lkb_vec_t u0, int32_t kdim, double tolerance) {
+    if (!A || !U || !V || !S || !residuals || !info || nsv < 1 || U->ncols < nsv || V->ncols < nsv) { set_error("svds: bad arguments"); return LKB_ERR_ARG; }
+    LKB_TRY(lapack_ready());
+    lkb_ctx_s* c = U->ctx;
+    const int kind = U->kind;
+    const bool cplx = kind_cplx(kind);
+    const size_t es = kind_size(kind);
+    const int kd = kdim > 0 ? kdim : 4 * nsv;
+    const double tol = tolerance >= 0 ? tolerance : rtol_of(kind);
+    lkb_basis_t Uw = nullptr, Vw = nullptr;
+    LKB_TRY(lkb_basis_create(c, kind, U->n, U->n_global, U->row0, kd + 1, &Uw));
+    int rc = lkb_basis_create(c, kind, V->n, V->n_global, V->row0, kd + 1, &Vw);
+    if (rc) { lkb_basis_destroy(Uw); return rc; }
+    auto cleanup = [&](int r) { lkb_basis_destroy(Uw); lkb_basis_destroy(Vw); return r; };
+#define SV_TRY(call) do { rc = (call); if (rc) return cleanup(rc); } while (0)
+    SV_TRY(start_vector(Uw, u0));
+    const int ldb = kd + 1;
+    std::vector<char> B((size_t)ldb * kd * es, 0);
+    std::vector<double> sv(kd, 0.0), res(kd, 0.0);
+    std::vector<cd> umat((size_t)kd * kd), vmat((size_t)kd * kd);
+    *info = 0;
+    int k = 1, conv = 0;
+    for (k = 1; k <= kd; ++k) {
+        int32_t binfo = 0;
+        SV_TRY(lkb_bidiag(A, Uw, Vw, B.data(), ldb, &binfo, k, k, tol));      // tol = solver tolerance (svd_solvers.fypp:82)
+        std::fill(sv.begin(), sv.end(), 0.0);
+        std::fill(umat.begin(), umat.end(), cd(0)); std::fill(vmat.begin(), vmat.end(), cd(0));
+        lint n = k, linf = 0;
+        std::vector<lint> iwork(8 * k);
+        if (cplx) {
+            std::vector<cd> a((size_t)k * k), u((size_t)k * k), vt((size_t)k * k), work(std::max(1, 4 * k * k + 8 * k));
+            std::vector<double> rwork(std::max(1, 8 * k * k + 8 * k));
+            for (int j = 0; j < k; ++j) for (int i = 0; i < k; ++i) a[i + (size_t)k * j] = load_kind(kind, B.data(), (size_t)i + (size_t)ldb * j);
+            lint lwork = (lint)work.size();
+            g_la.zgesdd("A", &n, &n, a.data(), &n, sv.data(), u.data(), &n, vt.data(), &n, work.data(), &lwork, rwork.data(), iwork.data(), &linf, 1);
+            for (int j = 0; j < k; ++j) for (int i = 0; i < k; ++i) {
+                umat[i + (size_t)kd * j] = u[i + (size_t)k * j];
+                vmat[i + (size_t)kd * j] = std::conj(vt[j + (size_t)k * i]);      // vmat = hermitian(vt)
+            }
+        } else {
+            std::vector<double> a((size_t)k * k), u((size_t)k * k), vt((size_t)k * k), work(std::max(1, 8 * k * k + 16 * k));
+            for (int j = 0; j < k; ++j) for (int i = 0; i < k; ++i) a[i + (size_t)k * j] = load_kind(kind, B.data(), (size_t)i + (size_t)ldb * j).real();
+            lint lwork = (lint)work.size();
+            g_la.dgesdd("A", &n, &n, a.data(), &n, sv.data(), u.data(), &n, vt.data(), &n, work.data(), &lwork, iwork.data(), &linf, 1);
+            for (int j = 0; j < k; ++j) for (int i = 0; i < k; ++i) {
+                umat[i + (size_t)kd * j] = u[i + (size_t)k * j];
+                vmat[i + (size_t)kd * j] = vt[j + (size_t)k * i];
+            }
+        }
+        if (linf != 0) { set_error("GESDD failed, info = %d", (int)linf); return cleanup(LKB_ERR_LAPACK); }
+        const cd beta = load_kind(kind, B.data(), (size_t)k + (size_t)ldb * (k - 1));
+        std::fill(res.begin(), res.end(), 0.0);
+        for (int i = 0; i < k; ++i) res[i] = std::abs(beta * vmat[(k - 1) + (size_t)kd * i]);
+        conv = 0; for (int i = 0; i < k; ++i) conv += res[i] < tol;
+        if (conv >= nsv) break;
+    }
+    for (int i = 0; i < nsv; ++i) { S[i] = sv[i]; residuals[i] = res[i]; }
+    k = std::min(k, kd);
+    *info = k;
+    std::vector<cd> Yu((size_t)k * nsv), Yv((size_t)k * nsv);
+    for (int i = 0; i < nsv; ++i) for (int j = 0; j < k; ++j) {
+        Yu[j + (size_t)k * i] = umat[j + (size_t)kd * i];
+        Yv[j + (size_t)k * i] = vmat[j + (size_t)kd * i];
+    }
+    SV_TRY(device_combine(Uw, k, Yu, k, nsv, U->d, U->ld));
+    SV_TRY(device_combine(Vw, k, Yv, k, nsv, V->d, V->ld));
+    SV_TRY(lkb_sync(c));
+#undef SV_TRY
+    return cleanup(0);
+}
+
+}  // extern "C"

@@ -371,3 +371,162 @@ def cg(A: Op, b: np.ndarray, x: np.ndarray, rtol=None, atol=None, maxiter=100):
         rr_old = rr_new
     info = meta["n_iter"] if meta["converged"] else -meta["n_iter"]
     return info, meta
+
+
+# ------------------------------------------------------------------------------------------
+# eigs / krylov_schur / eighs / svds  (host LAPACK through scipy, double precision for the
+# k x k algebra exactly like the product's host shells)
+# ------------------------------------------------------------------------------------------
+
+def _host_eig(Hk: np.ndarray):
+    """eig = geev('N','V') (submodule_utility_functions.fypp:55-85); real kinds keep LAPACK's
+    real-pair eigenvector layout."""
+    from scipy.linalg import lapack
+    if np.iscomplexobj(Hk):
+        w, vl, vr, info = lapack.zgeev(Hk.astype(np.complex128), compute_vl=0, compute_vr=1)
+        return w, vr
+    wr, wi, vl, vr, info = lapack.dgeev(Hk.astype(np.float64), compute_vl=0, compute_vr=1)
+    return wr + 1j * wi, vr
+
+
+def _sort_index_reverse(key):
+    """stdlib sort_index(reverse=.true.): stable ascending sort, then reversal."""
+    return np.argsort(key, kind="stable")[::-1]
+
+
+def krylov_schur(X: np.ndarray, H: np.ndarray):
+    """BaseKrylov.fypp:782-834 with eigs' median selector; returns n. X, H updated in place."""
+    from scipy.linalg import lapack
+    kdim = X.shape[1] - 1
+    cplx = np.iscomplexobj(H)
+    Hk = np.asfortranarray(H[:kdim, :kdim]).astype(np.complex128 if cplx else np.float64)
+    if cplx:
+        T, sdim, w, Z, work, info = lapack.zgees(lambda x: False, Hk, sort_t=0)
+        ev = w
+    else:
+        T, sdim, wr, wi, Z, work, info = lapack.dgees(lambda x, y: False, Hk, sort_t=0)
+        ev = wr + 1j * wi
+    assert info == 0
+    sel = np.abs(ev) > np.median(np.abs(ev))
+    n = int(sel.sum())
+    trsen = lapack.ztrsen if cplx else lapack.dtrsen
+    out = trsen(sel.astype(np.int32), T, Z, job="N", wantq=1)
+    T2, Z2 = out[0], out[1]
+    assert out[-1] == 0
+    b = H[kdim, :].astype(Z2.dtype) @ Z2
+    X[:, :n] = (X[:, :kdim].astype(Z2.dtype) @ Z2[:, :n]).astype(X.dtype)
+    X[:, n] = X[:, kdim]
+    X[:, n + 1:] = 0
+    H[:kdim, :] = T2.astype(H.dtype)
+    H[n, :] = b.astype(H.dtype)
+    H[n + 1:, :] = 0
+    H[:, n:] = 0
+    return n
+
+
+def eigs(A: Op, n: int, nev: int, x0: np.ndarray, kdim=None, tolerance=None, trans=False, max_restarts=200):
+    """IterativeSolvers.fypp:972-1143.  Returns (eigvals[nev], residuals[nev], X[n, nev], info=niter)."""
+    kind = kind_of(x0.dtype)
+    dt = DTYPES[kind]
+    cplx = kind in "cz"
+    kdim = 4 * nev if kdim is None else kdim
+    tol = RTOL[kind] if tolerance is None else tolerance
+    Xw = np.zeros((n, kdim + 1), dtype=dt, order="F")
+    Xw[:, 0] = x0
+    normalize(Xw[:, 0])
+    H = np.zeros((kdim + 1, kdim), dtype=dt, order="F")
+    kstart, conv, niter, k = 1, 0, 0, 1
+    res = np.zeros(kdim)
+    restarts = 0
+    while conv < nev:
+        for k in range(kstart, kdim + 1):
+            arnoldi(A, Xw, H, kstart=k, kend=k, trans=trans)
+            vals, vecs = _host_eig(np.asfortranarray(H[:k, :k]))
+            beta = H[k, k - 1]
+            res[:] = 0
+            for i in range(k):
+                if cplx:
+                    alpha = abs(vecs[k - 1, i])
+                elif vals[i].imag > 0:
+                    alpha = abs(complex(vecs[k - 1, i], vecs[k - 1, i + 1]))
+                elif vals[i].imag < 0:
+                    alpha = abs(complex(vecs[k - 1, i - 1], vecs[k - 1, i]))
+                else:
+                    alpha = abs(vecs[k - 1, i])
+                res[i] = abs(beta) * alpha
+            niter += 1
+            conv = int((res[:k] < tol).sum())
+            if conv >= nev:
+                break
+        if conv >= nev:
+            break
+        kstart = krylov_schur(Xw, H) + 1
+        k = kdim + 1
+        restarts += 1
+        assert restarts < max_restarts, "eigs did not converge"
+    k = min(k, kdim)
+    vals, vecs = _host_eig(np.asfortranarray(H[:k, :k]))
+    av = np.zeros(kdim); av[:k] = np.abs(vals)
+    idx = _sort_index_reverse(av)
+    eigvals = np.zeros(nev, dtype=np.complex128); residuals = np.zeros(nev)
+    Xout = np.zeros((n, nev), dtype=dt, order="F")
+    for i in range(nev):
+        s = idx[i]
+        if s < k:
+            eigvals[i] = vals[s]
+            Xout[:, i] = (Xw[:, :k] @ vecs[:, s].astype(dt if cplx else REAL[kind])).astype(dt)
+        residuals[i] = res[s]
+    return eigvals, residuals, Xout, niter
+
+
+def eighs(A: Op, n: int, nev: int, x0: np.ndarray, kdim=None, tolerance=None):
+    """EIGHS/eighs.fypp:29-126.  eigh = syev/heev on the lower triangle."""
+    import scipy.linalg as sla
+    kind = kind_of(x0.dtype); dt = DTYPES[kind]
+    kdim = 4 * nev if kdim is None else kdim
+    tol = RTOL[kind] if tolerance is None else tolerance
+    Xw = np.zeros((n, kdim + 1), dtype=dt, order="F"); Xw[:, 0] = x0; normalize(Xw[:, 0])
+    T = np.zeros((kdim + 1, kdim), dtype=dt, order="F")
+    ev = np.zeros(kdim); res = np.zeros(kdim); vecs = np.zeros((kdim, kdim), dtype=np.complex128 if kind in "cz" else np.float64)
+    k = 1
+    for k in range(1, kdim + 1):
+        lanczos(A, Xw, T, kstart=k, kend=k)
+        ev[:] = 0; vecs[:] = 0; res[:] = 0
+        w, v = sla.eigh(T[:k, :k].astype(vecs.dtype), lower=True, driver="ev")
+        ev[:k] = w; vecs[:k, :k] = v
+        res[:k] = np.abs(T[k, k - 1] * vecs[k - 1, :k])
+        if int((res[:k] < tol).sum()) >= nev:
+            break
+    idx = _sort_index_reverse(ev)
+    k = min(k, kdim)
+    eigvals = ev[idx[:nev]].copy(); residuals = res[idx[:nev]].copy()
+    Xout = np.asfortranarray((Xw[:, :k].astype(vecs.dtype) @ vecs[:k, idx[:nev]]).astype(dt))
+    return eigvals, residuals, Xout, k
+
+
+def svds(A: Op, nsv: int, u0: np.ndarray, kdim=None, tolerance=None):
+    """SVDS/svd_solvers.fypp:28-121.  svd = gesdd."""
+    import scipy.linalg as sla
+    kind = kind_of(u0.dtype); dt = DTYPES[kind]
+    kdim = 4 * nsv if kdim is None else kdim
+    tol = RTOL[kind] if tolerance is None else tolerance
+    m, n = A.m, A.n
+    Uw = np.zeros((m, kdim + 1), dtype=dt, order="F"); Uw[:, 0] = u0; normalize(Uw[:, 0])
+    Vw = np.zeros((n, kdim + 1), dtype=dt, order="F")
+    B = np.zeros((kdim + 1, kdim), dtype=dt, order="F")
+    wd = np.complex128 if kind in "cz" else np.float64
+    sv = np.zeros(kdim); res = np.zeros(kdim)
+    k = 1
+    for k in range(1, kdim + 1):
+        bidiag(A, Uw, Vw, B, kstart=k, kend=k, tol=tol)
+        u, s, vt = sla.svd(B[:k, :k].astype(wd), lapack_driver="gesdd")
+        vm = vt.conj().T
+        sv[:] = 0; res[:] = 0
+        sv[:k] = s
+        res[:k] = np.abs(B[k, k - 1] * vm[k - 1, :k])
+        if int((res[:k] < tol).sum()) >= nsv:
+            break
+    k = min(k, kdim)
+    U = np.asfortranarray((Uw[:, :k].astype(wd) @ u[:k, :nsv]).astype(dt))
+    V = np.asfortranarray((Vw[:, :k].astype(wd) @ vm[:k, :nsv]).astype(dt))
+    return sv[:nsv].copy(), res[:nsv].copy(), U, V, k

@@ -214,3 +214,87 @@ def test_rng_uniform_is_sharding_independent(oracle):
     assert 0.0 < a.min() and a.max() < 1.0 and abs(a.mean() - 0.5) < 0.05
     g = oracle.fill(200000, "d", "normal", 7)
     assert abs(g.mean()) < 0.01 and abs(g.std() - 1.0) < 0.01
+
+
+# ---- known-answer pins of the solver shells (test/TestIterativeSolvers.fypp) -----------------
+def _toeplitz_tridiag(n, sub, diag, sup, dtype):
+    A = np.zeros((n, n), dtype=dtype)
+    i = np.arange(n)
+    A[i, i] = diag
+    A[i[1:], i[:-1]] = sub
+    A[i[:-1], i[1:]] = sup
+    return np.asfortranarray(A)
+
+
+def test_eigs_known_answer_full(oracle):
+    """TestIterativeSolvers.fypp:87-130: tridiagonal Toeplitz (-b, a, b): lambda = a +/- 2b cos(k pi/(n+1)) i."""
+    n, a, b = N, 1.0, 0.5
+    A = _toeplitz_tridiag(n, -b, a, b, np.float64)
+    rng = np.random.default_rng(20)
+    ev, res, X, info = oracle.eigs(oracle.Op.dense(A), n, n, rng.standard_normal(n), kdim=n)
+    true = a + 2j * b * np.cos(np.arange(1, n + 1) * np.pi / (n + 1))
+    got = np.sort_complex(ev); tr = np.sort_complex(true)
+    assert np.abs(np.sort(got.imag) - np.sort(tr.imag)).max() < oracle.RTOL["d"]
+    assert np.abs(got.real - a).max() < oracle.RTOL["d"]
+
+
+def test_eigs_known_answer_krylov_schur(oracle):
+    """TestIterativeSolvers.fypp:161-209: nev = 8 with Krylov-Schur restarts; leading |lambda|."""
+    n, a, b, nev = N, 1.0, 0.5, 8
+    A = _toeplitz_tridiag(n, -b, a, b, np.float64)
+    rng = np.random.default_rng(21)
+    ev, res, X, info = oracle.eigs(oracle.Op.dense(A), n, nev, rng.standard_normal(n), kdim=4 * nev)
+    true = a + 2j * b * np.cos(np.arange(1, n + 1) * np.pi / (n + 1))
+    lead = true[np.argsort(-np.abs(true))][:nev]
+    d = np.abs(ev[:, None] - lead[None, :]).min(axis=1)
+    assert d.max() < 1e-6 and info > 4 * nev          # restarted at least once
+    # conv counts ANY nev Ritz residuals below tol (IterativeSolvers.fypp:1087), not the leading ones
+    assert np.all(res < 1e-6)
+    # eigenvector residual for the converged pairs (real-pair convention)
+    i = 0
+    while i < nev - 1:
+        if ev[i].imag != 0:
+            v = X[:, i] + 1j * X[:, i + 1] if ev[i].imag > 0 else X[:, i + 1] + 1j * X[:, i]
+            lam = ev[i] if ev[i].imag > 0 else ev[i + 1]
+            assert np.linalg.norm(A @ v - lam * v) < 1e-6 * np.linalg.norm(v)
+            i += 2
+        else:
+            i += 1
+
+
+def test_krylov_schur_relation(oracle):
+    """TestKrylov.fypp:298-347: after the restart A X_n = X_{n+1} H_{n+1,n} and X stays orthonormal."""
+    rng = np.random.default_rng(22)
+    n, kdim = N, 32
+    A = _randn(rng, (n, n), np.float64) / np.sqrt(n)
+    X = _start(rng, n, kdim + 1, np.float64, oracle)
+    H = np.zeros((kdim + 1, kdim), order="F")
+    assert oracle.arnoldi(oracle.Op.dense(A), X, H) == 0
+    nk = oracle.krylov_schur(X, H)
+    assert 0 < nk < kdim
+    assert np.abs(A @ X[:, :nk] - X[:, :nk + 1] @ H[:nk + 1, :nk]).max() < oracle.RTOL["d"]
+    assert np.abs(X[:, :nk + 1].T @ X[:, :nk + 1] - np.eye(nk + 1)).max() < oracle.RTOL["d"]
+
+
+def test_eighs_known_answer(oracle):
+    """TestIterativeSolvers.fypp:254-307: symmetric Toeplitz, lambda_i = a + 2|b| cos(i pi/(n+1))."""
+    n, a, b, nev = N, 2.0, -1.0, 8
+    A = _toeplitz_tridiag(n, b, a, b, np.float64)
+    rng = np.random.default_rng(23)
+    ev, res, X, info = oracle.eighs(oracle.Op.dense(A), n, nev, rng.standard_normal(n), kdim=n)
+    true = a + 2 * abs(b) * np.cos(np.arange(1, n + 1) * np.pi / (n + 1))
+    assert np.abs(ev - true[:nev]).max() < oracle.RTOL["d"]
+    assert np.abs(A @ X - X * ev).max() < 1e-6
+    assert np.abs(X.T @ X - np.eye(nev)).max() < oracle.RTOL["d"]
+
+
+def test_svds_known_answer(oracle):
+    """TestIterativeSolvers.fypp:440-489: Strang matrix, sigma_i = 2 (1 + cos(i pi/(n+1)))."""
+    n, nsv = N, 8
+    A = _toeplitz_tridiag(n, -1.0, 2.0, -1.0, np.float64)
+    rng = np.random.default_rng(24)
+    S, res, U, V, info = oracle.svds(oracle.Op.dense(A), nsv, rng.standard_normal(n), kdim=n)
+    true = 2 * (1 + np.cos(np.arange(1, n + 1) * np.pi / (n + 1)))
+    assert np.abs(S - true[:nsv]).max() < oracle.RTOL["d"]
+    assert np.abs(A @ V - U * S).max() < 1e-6
+    assert np.abs(U.T @ U - np.eye(nsv)).max() < oracle.RTOL["d"]
