@@ -97,7 +97,10 @@ def test_krylov_schur_restart_relation(lk, ctx, oracle):
     assert np.abs(Ah @ Xg[:, :nk] - Xg[:, :nk + 1] @ H[:nk + 1, :nk]).max() < lk.RTOL["d"]
     assert np.abs(Xg[:, :nk + 1].T @ Xg[:, :nk + 1] - np.eye(nk + 1)).max() < 1e-12
     assert not Xg[:, nk + 1:].any() and not H[nk + 1:, :].any() and not H[:, nk:].any()
-    assert rel_normwise(H, Ho) < 1e-9
+    # the reordered real Schur form is not unique (2x2 block standardisation, swap order), so compare the
+    # invariants: the retained Ritz values and the residual row norm
+    assert _match(np.linalg.eigvals(H[:nk, :nk]), np.linalg.eigvals(Ho[:nk, :nk])) < 1e-10
+    assert abs(np.linalg.norm(H[nk, :nk]) - np.linalg.norm(Ho[nk, :nk])) < 1e-10
     # resume the factorisation from the restarted state (the way eigs does)
     assert lk.arnoldi(A, X, H, kstart=nk + 1, kend=kdim) == 0
     Xg = X.get()
