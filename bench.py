@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile-pass", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fused", action="store_true", help="disable the fused axpy+dot CGS2 kernel (A/B)")
     ap.add_argument("--cpu-sample-steps", type=int, default=12)
     return ap.parse_args()
 
@@ -190,6 +191,8 @@ def run_ours(args):
     else:
         ctx = lk.Context(local)
     assert world == args.gpus or world == 1, "--gpus must equal WORLD_SIZE"
+    if args.no_fused:
+        ctx.set_option("fused", 0)
 
     nx, ny, kdim = args.nx, args.ny, args.kdim
     n = nx * ny
@@ -275,16 +278,19 @@ def run_ours(args):
         prof = ctx.get_profile()
         ctx.set_profile(False)
         s = 8
+        fused_on = prof.get("fused_axpy_dot", (0.0, 0))[1] > 0
+        npass = 1 if fused_on else 2
         algb = {
             "matvec": kdim * 2 * nloc * s,
-            "multidot": sum(2 * (j + 1) * nloc * s for j in range(1, kdim + 1)),       # 2 passes x (V_j + w)
-            "multiaxpy": sum(2 * (j + 2) * nloc * s for j in range(1, kdim + 1)),      # 2 passes x (V_j + w r/w)
+            "multidot": sum(npass * (j + 1) * nloc * s for j in range(1, kdim + 1)),   # V_j + w per launch
+            "multiaxpy": sum(npass * (j + 2) * nloc * s for j in range(1, kdim + 1)),  # V_j + w read + w write
+            "fused_axpy_dot": sum((j + 2) * nloc * s for j in range(1, kdim + 1)) if fused_on else 0,
             "other": kdim * 2 * nloc * s,                                              # normalisation sweep
         }
         for name, (ms, nl) in prof.items():
             gbs = algb[name] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
             kernels[name] = {"ms_total": ms, "launches": nl, "alg_bytes": algb[name], "GBps": gbs, "frac": gbs / peak}
-        dom = max(("multidot", "multiaxpy"), key=lambda k: kernels[k]["ms_total"])
+        dom = max(("multidot", "multiaxpy", "fused_axpy_dot"), key=lambda k: kernels[k]["ms_total"])
         nl = max(kernels[dom]["launches"], 1)
         roof = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["GBps"] / peak, "traffic": None,
@@ -314,7 +320,7 @@ def run_ours(args):
                        "bench_step": f"one kstart=1..kend={kdim} factorisation = {kdim} Arnoldi steps",
                        "partition": f"grid rows over {world} rank(s), {nloc} rows/rank",
                        "l2": "working set 17.3 GB/GPU-share >> 126 MB L2 (inputs larger than L2, no flush needed)",
-                       "cuda_graph": True},
+                       "cuda_graph": True, "fused_cgs2": not args.no_fused},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps,
                     "what": "pinned host start vector -> H2D -> normalise -> lkb_arnoldi -> Hessenberg matrix on the host"},

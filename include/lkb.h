@@ -52,6 +52,7 @@ void* lkb_stream(lkb_ctx_t ctx);                           /* cudaStream_t of th
 const char* lkb_last_error(void);
 int lkb_set_seed(lkb_ctx_t ctx, uint64_t seed);            /* seed of the `rand` TBP stream */
 int lkb_set_graphs(lkb_ctx_t ctx, int enable);             /* CUDA-graph capture of step loops (default on) */
+int lkb_set_option(lkb_ctx_t ctx, const char* name, int value); /* "graphs", "fused" (fused CGS2 kernel, default on) */
 int lkb_rank(lkb_ctx_t ctx); int lkb_world(lkb_ctx_t ctx);
 
 /* ---- abstract_vector TBPs : src/AbstractTypes/AbstractVectors.fypp:295-381, 424-460 ------
@@ -172,10 +173,11 @@ int lkb_svds(lkb_op_t A, lkb_basis_t U, double* S, lkb_basis_t V, int nsv, doubl
 int lkb_set_lapack(const char* path, const char* prefix, const char* suffix);
 
 /* ---- measurement helpers ----------------------------------------------------------------- */
-/* per-kernel-class device time (ms) of the LAST process call, measured with CUDA events on the
- * context stream when profiling is enabled: [0] matvec, [1] multi-dot, [2] multi-axpy, [3] other */
+/* per-kernel-class device time (ms) accumulated since lkb_set_profile(ctx, 1), measured with CUDA
+ * events on the context stream (graphs are bypassed while profiling).  8 slots:
+ * [0] matvec, [1] multi-dot, [2] multi-axpy, [3] other, [4] fused axpy+dot, [5..7] reserved */
 int lkb_set_profile(lkb_ctx_t ctx, int enable);
-int lkb_get_profile(lkb_ctx_t ctx, double* ms4, int64_t* launches4);
+int lkb_get_profile(lkb_ctx_t ctx, double* ms8, int64_t* launches8);
 int64_t lkb_kernel_launches(lkb_ctx_t ctx);               /* kernels launched since context creation */
 
 #ifdef __cplusplus

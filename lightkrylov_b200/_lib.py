@@ -41,6 +41,7 @@ SIGNATURES = {
     "lkb_last_error": (C.c_char_p, []),
     "lkb_set_seed": (_i, [_vp, _u64]),
     "lkb_set_graphs": (_i, [_vp, _i]),
+    "lkb_set_option": (_i, [_vp, C.c_char_p, _i]),
     "lkb_rank": (_i, [_vp]),
     "lkb_world": (_i, [_vp]),
     "lkb_vec_create": (_i, [_vp, _i, _i64, _i64, _i64, _P(_vp)]),

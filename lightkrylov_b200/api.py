@@ -91,10 +91,13 @@ class Context:
     def set_profile(self, enable: bool):
         check(self.lib.lkb_set_profile(self.h, int(enable)))
 
+    def set_option(self, name: str, value: int):
+        check(self.lib.lkb_set_option(self.h, name.encode(), int(value)), "set_option")
+
     def get_profile(self):
-        ms = (C.c_double * 4)(); n = (C.c_int64 * 4)()
+        ms = (C.c_double * 8)(); n = (C.c_int64 * 8)()
         check(self.lib.lkb_get_profile(self.h, ms, n))
-        names = ["matvec", "multidot", "multiaxpy", "other"]
+        names = ["matvec", "multidot", "multiaxpy", "other", "fused_axpy_dot"]
         return {k: (ms[i], n[i]) for i, k in enumerate(names)}
 
     @property

@@ -14,7 +14,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "liblkb.so")
-SOURCES = ["kernels_gs.cu", "kernels_vec.cu", "kernels_ops.cu", "kernels_gemm.cu", "lkb_core.cu", "lkb_krylov.cu",
+SOURCES = ["kernels_gs.cu", "kernels_vec.cu", "kernels_ops.cu", "kernels_gemm.cu", "kernels_fused.cu", "lkb_core.cu", "lkb_krylov.cu",
            "lkb_solvers.cu", "lkb_eig.cu"]
 HEADERS = ["lkb_types.cuh", "lkb_kernels.h", "lkb_internal.h", "lkb_rng.h", os.path.join("..", "..", "include", "lkb.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -1,0 +1,307 @@
+// kernels_fused.cu -- pass-1 multi-axpy fused with the pass-2 multi-dot of one CGS2 step.
+//
+// CGS2 (gram_schmidt.fypp:12-57) is   c1 = V^H w ; w' = w - V c1 ; c2 = V^H w' ; w'' = w' - V c2.
+// The two middle operations touch the same rows of V: for a tile of rows, w'[tile] needs only
+// V[tile, :] and c1, and the tile's contribution to c2 needs only V[tile, :] and w'[tile].  Holding
+// the V tile in shared memory between the two phases removes one of the four sweeps over V per
+// step: 3*j*n*s bytes instead of 4*j*n*s.  The arithmetic is the reference's (same c1, w', c2),
+// only the summation order differs.
+//
+// Data movement: one TMA 2-D tensor map over V(:, 0:j) (column-major, box = TP packs of rows x 16
+// columns, out-of-range rows/columns zero-filled by the hardware, no HBM traffic for them); a
+// 3-stage ring of 64 KB shared-memory tiles filled by cp.async.bulk.tensor (one elected thread),
+// completion on mbarriers.  One CTA per SM (persistent, 192 KB of shared memory).
+//   phase A  warp q owns columns 16q..16q+15, lanes own row packs: partial row sums -> smem
+//   combine  w'[tile] = w[tile] - sum over warps (fixed order); stored to HBM and to smem; w'.w'
+//   phase B  per-lane accumulators acc[16] += conj(V[tile, col]) * w'[tile]  (persist over tiles)
+// End: one transposing warp fold per warp, one partial row per CTA, last CTA folds the rows in fixed
+// order (same deterministic two-stage scheme as k_multidot).
+#include <cuda.h>
+#include "lkb_kernels.h"
+
+namespace lkb {
+
+LKB_DI uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+LKB_DI void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+LKB_DI void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+LKB_DI void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+LKB_DI void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+LKB_DI void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+LKB_DI void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+
+template <typename T> LKB_DI T shfl_xor_f(T v, int m);
+template <> LKB_DI float shfl_xor_f<float>(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+template <> LKB_DI double shfl_xor_f<double>(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+template <> LKB_DI float2 shfl_xor_f<float2>(float2 v, int m) {
+    return make_float2(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
+}
+template <> LKB_DI double2 shfl_xor_f<double2>(double2 v, int m) {
+    return make_double2(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
+}
+template <typename E> LKB_DI void warp_fold16_f(E (&acc)[16], int lane) {
+#pragma unroll
+    for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+        const bool up = (lane & bit) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const E send = up ? acc[i] : acc[i + half];
+            const E keep = up ? acc[i + half] : acc[i];
+            acc[i] = add_v(keep, shfl_xor_f<E>(send, bit));
+        }
+    }
+    acc[0] = add_v(acc[0], shfl_xor_f<E>(acc[0], 1));
+}
+
+enum { FZ_THREADS = 256, FZ_NW = 8, FZ_STAGES = 3, FZ_CB = 16 };
+
+template <int K>
+__global__ void __launch_bounds__(FZ_THREADS, 1)
+k_axpy_dot(const __grid_constant__ CUtensorMap tmap, int j, int tp, int elt_per_pack,
+           const typename Tr<K>::W* __restrict__ c1, typename Tr<K>::E* __restrict__ w, int64_t n,
+           typename Tr<K>::W* __restrict__ partial, typename Tr<K>::W* __restrict__ out,
+           unsigned* __restrict__ counter, const int* __restrict__ flags)
+{
+    using E = typename Tr<K>::E;
+    using W = typename Tr<K>::W;
+    constexpr int EPP = Tr<K>::EPP;
+    using P = Pack<E, EPP>;
+    if (flags && flags[F_STOP]) return;
+
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int jp = j + 1;
+    const int jc = (j + FZ_CB - 1) & ~(FZ_CB - 1);
+    const int nchunk = jc / FZ_CB;
+    const uint32_t stage_bytes = (uint32_t)jc * (uint32_t)tp * 16u;
+    P* part = reinterpret_cast<P*>(smem + (size_t)FZ_STAGES * stage_bytes);   // [nchunk][tp]
+    P* wnew = part + (size_t)FZ_NW * tp;                                       // [tp]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wnew + tp);                   // [FZ_STAGES]
+    __shared__ double sww[FZ_NW];
+    __shared__ bool is_last;
+
+    const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
+    const int64_t npk = n / EPP;
+    const int64_t ntiles = (npk + tp - 1) / tp;
+    const int64_t tper = (ntiles + gridDim.x - 1) / gridDim.x;
+    const int64_t t0 = (int64_t)blockIdx.x * tper;
+    const int64_t t1 = min(ntiles, t0 + tper);
+    const int nmine = (int)max((int64_t)0, t1 - t0);
+
+    if (tid == 0) {
+        for (int s = 0; s < FZ_STAGES; ++s) mbar_init(smem_u32(&bars[s]), 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    // this warp's 16 coefficients of pass 1 and its 16 accumulators of pass 2
+    E c1r[FZ_CB], acc[FZ_CB];
+#pragma unroll
+    for (int i = 0; i < FZ_CB; ++i) {
+        const int col = wv * FZ_CB + i;
+        c1r[i] = zero_v(E());
+        if (col < j) narrow(c1[col], c1r[i]);
+        acc[i] = zero_v(E());
+    }
+    double wwacc = 0.0;
+
+    auto issue = [&](int it) {
+        const int s = it % FZ_STAGES;
+        const uint32_t bar = smem_u32(&bars[s]);
+        fence_proxy_async();
+        mbar_expect_tx(bar, stage_bytes);
+        const int row0 = (int)((t0 + it) * tp) * elt_per_pack;
+        for (int q = 0; q < nchunk; ++q)
+            tma_load_2d(smem_u32(smem + (size_t)s * stage_bytes + (size_t)q * FZ_CB * tp * 16), &tmap, row0, q * FZ_CB, bar);
+    };
+    if (tid == 0)
+        for (int it = 0; it < FZ_STAGES - 1 && it < nmine; ++it) issue(it);
+
+    const int msteps = tp / 32;
+    for (int it = 0; it < nmine; ++it) {
+        const int s = it % FZ_STAGES;
+        const uint32_t parity = (uint32_t)((it / FZ_STAGES) & 1);
+        const P* tile = reinterpret_cast<const P*>(smem + (size_t)s * stage_bytes);
+        // this tile's packs of w (threads 0..tp-1), issued before the wait to overlap their latency
+        const bool own = tid < tp;
+        const int64_t pk = (t0 + it) * tp + tid;
+        const bool inb = own && pk < npk;
+        P wp;
+#pragma unroll
+        for (int e = 0; e < EPP; ++e) wp.v[e] = zero_v(E());
+        if (inb) wp = ld_pack<P>(w + pk * EPP);
+
+        mbar_wait(smem_u32(&bars[s]), parity);
+
+        // ---- phase A: partial row sums over this warp's 16 columns ----
+        if (wv < nchunk) {
+            for (int m = 0; m < msteps; ++m) {
+                const int r = m * 32 + lane;
+                P ra;
+#pragma unroll
+                for (int e = 0; e < EPP; ++e) ra.v[e] = zero_v(E());
+#pragma unroll
+                for (int i = 0; i < FZ_CB; ++i) {
+                    const P v = tile[(size_t)(wv * FZ_CB + i) * tp + r];
+#pragma unroll
+                    for (int e = 0; e < EPP; ++e) fmacc(ra.v[e], v.v[e], c1r[i]);
+                }
+                part[(size_t)wv * tp + r] = ra;
+            }
+        }
+        __syncthreads();
+        // every warp is past phase B of the previous tile: its stage can be refilled
+        if (tid == 0 && it + FZ_STAGES - 1 < nmine) issue(it + FZ_STAGES - 1);
+
+        // ---- combine: w' = w - sum over warps (fixed order) ----
+        if (own) {
+            P sum = part[tid];
+            for (int q = 1; q < nchunk; ++q) {
+                const P t = part[(size_t)q * tp + tid];
+#pragma unroll
+                for (int e = 0; e < EPP; ++e) sum.v[e] = add_v(sum.v[e], t.v[e]);
+            }
+            if (inb) {
+#pragma unroll
+                for (int e = 0; e < EPP; ++e) {
+                    wp.v[e] = add_v(wp.v[e], rscale(sum.v[e], (typename Tr<K>::Rl)(-1)));
+                    wwacc += abs2_w(wp.v[e]);
+                }
+                st_pack(w + pk * EPP, wp);
+            }
+            wnew[tid] = wp;
+        }
+        __syncthreads();
+
+        // ---- phase B: c2 partials, accumulators persist across tiles ----
+        if (wv < nchunk) {
+            for (int m = 0; m < msteps; ++m) {
+                const int r = m * 32 + lane;
+                const P wn = wnew[r];
+#pragma unroll
+                for (int i = 0; i < FZ_CB; ++i) {
+                    const P v = tile[(size_t)(wv * FZ_CB + i) * tp + r];
+#pragma unroll
+                    for (int e = 0; e < EPP; ++e) fma_conj(acc[i], v.v[e], wn.v[e]);
+                }
+            }
+        }
+    }
+
+    // ---- stage 1: one partial row per CTA (each column is owned by exactly one warp) ----
+    const int fold_idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    if (wv < nchunk) {
+        warp_fold16_f<E>(acc, lane);
+        const int col = wv * FZ_CB + fold_idx;
+        if ((lane & 1) == 0 && col < j) partial[(int64_t)blockIdx.x * jp + col] = widen(acc[0]);
+    }
+    {
+        const double a = warp_sum(wwacc);
+        if (lane == 0) sww[wv] = a;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double t = sww[0];
+        for (int q = 1; q < FZ_NW; ++q) t += sww[q];
+        W o = zero_v(W());
+        *reinterpret_cast<double*>(&o) = t;
+        partial[(int64_t)blockIdx.x * jp + j] = o;
+    }
+    // ---- stage 2: last CTA folds the partial rows in fixed order ----
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1u);
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        const int nrb = gridDim.x;
+        for (int col = wv; col < jp; col += FZ_NW) {
+            W a = zero_v(W());
+            for (int b = lane; b < nrb; b += 32) wadd(a, __ldcg(&partial[(int64_t)b * jp + col]));
+            a = warp_sum(a);
+            if (lane == 0) out[col] = a;
+        }
+        if (tid == 0) *counter = 0u;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_tmapEncodeTiled get_encode() {
+    static PFN_tmapEncodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_tmapEncodeTiled)p;
+    }
+    return fn;
+}
+
+template <int K>
+static bool axpy_dot_t(cudaStream_t s, const void* V, int64_t ld, int j, const void* c1, void* w, int64_t n,
+                       void* partial, void* out, unsigned* counter, const int* flags, int sms) {
+    using E = typename Tr<K>::E; using W = typename Tr<K>::W;
+    constexpr int EPP = Tr<K>::EPP;
+    const size_t es = sizeof(E);
+    if (j < 1 || j > FZ_NW * FZ_CB) return false;                 // one 16-column chunk per warp
+    if (n % EPP != 0 || n < 32 * EPP) return false;
+    if (((uintptr_t)V & 15) || ((uintptr_t)w & 15) || ((size_t)ld * es) % 16) return false;
+    PFN_tmapEncodeTiled enc = get_encode();
+    if (!enc) return false;
+    const int jc = (j + FZ_CB - 1) & ~(FZ_CB - 1);
+    const int tp = jc > 64 ? 32 : 64;                              // stage = jc * tp * 16 B <= 64 KB
+    const int eltsz = (K == KS) ? 4 : 8;                           // tensor described in 4- or 8-byte words
+    const int elt_per_pack = 16 / eltsz;
+    if ((int64_t)n * (int64_t)es / eltsz >= ((int64_t)1 << 31)) return false;
+    CUtensorMap tmap;
+    cuuint64_t gdim[2] = {(cuuint64_t)((size_t)n * es / eltsz), (cuuint64_t)j};
+    cuuint64_t gstr[1] = {(cuuint64_t)((size_t)ld * es)};
+    cuuint32_t box[2] = {(cuuint32_t)(tp * elt_per_pack), (cuuint32_t)FZ_CB};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&tmap, eltsz == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT64, 2,
+                     const_cast<void*>(V), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    const size_t sh = (size_t)FZ_STAGES * jc * tp * 16 + (size_t)(FZ_NW + 1) * tp * 16 + 64;
+    static const bool attr_once = (cudaFuncSetAttribute(k_axpy_dot<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024), true);
+    (void)attr_once;
+    const int64_t ntiles = (n / EPP + tp - 1) / tp;
+    int64_t nb = sms;
+    if (nb > ntiles) nb = ntiles;
+    if (nb > MAX_ROWBLOCKS) nb = MAX_ROWBLOCKS;
+    k_axpy_dot<K><<<(int)nb, FZ_THREADS, sh, s>>>(tmap, j, tp, elt_per_pack, (const W*)c1, (E*)w, n, (W*)partial, (W*)out, counter, flags);
+    return true;
+}
+
+bool launch_axpy_dot(int kind, cudaStream_t s, const void* V, int64_t ld, int j, const void* c1, void* w, int64_t n,
+                     void* partial, void* out, unsigned* counter, const int* flags, int sms) {
+    switch (kind) {
+        case KS: return axpy_dot_t<KS>(s, V, ld, j, c1, w, n, partial, out, counter, flags, sms);
+        case KD: return axpy_dot_t<KD>(s, V, ld, j, c1, w, n, partial, out, counter, flags, sms);
+        case KC: return axpy_dot_t<KC>(s, V, ld, j, c1, w, n, partial, out, counter, flags, sms);
+        default: return axpy_dot_t<KZ>(s, V, ld, j, c1, w, n, partial, out, counter, flags, sms);
+    }
+}
+
+}  // namespace lkb

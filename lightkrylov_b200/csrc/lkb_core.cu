@@ -245,6 +245,13 @@ int lkb_sync(lkb_ctx_t c) { LKB_CUDA(cudaStreamSynchronize(c->stream)); return 0
 void* lkb_stream(lkb_ctx_t c) { return (void*)c->stream; }
 int lkb_set_seed(lkb_ctx_t c, uint64_t seed) { c->seed = seed; c->seed_calls = 0; return 0; }
 int lkb_set_graphs(lkb_ctx_t c, int enable) { c->graphs = enable != 0; return 0; }
+int lkb_set_option(lkb_ctx_t c, const char* name, int value) {
+    if (!c || !name) return LKB_ERR_ARG;
+    if (!strcmp(name, "graphs")) c->graphs = value != 0;
+    else if (!strcmp(name, "fused")) c->fused = value != 0;
+    else { set_error("unknown option %s", name); return LKB_ERR_ARG; }
+    return 0;
+}
 int lkb_rank(lkb_ctx_t c) { return c->rank; }
 int lkb_world(lkb_ctx_t c) { return c->world; }
 int lkb_set_profile(lkb_ctx_t c, int enable) {
@@ -252,9 +259,9 @@ int lkb_set_profile(lkb_ctx_t c, int enable) {
     for (int i = 0; i < PC_COUNT; ++i) { c->prof_ms[i] = 0; c->prof_n[i] = 0; }
     return 0;
 }
-int lkb_get_profile(lkb_ctx_t c, double* ms4, int64_t* launches4) {
+int lkb_get_profile(lkb_ctx_t c, double* ms8, int64_t* launches8) {
     LKB_TRY(prof_collect(c));
-    for (int i = 0; i < PC_COUNT; ++i) { if (ms4) ms4[i] = c->prof_ms[i]; if (launches4) launches4[i] = c->prof_n[i]; }
+    for (int i = 0; i < PC_COUNT; ++i) { if (ms8) ms8[i] = c->prof_ms[i]; if (launches8) launches8[i] = c->prof_n[i]; }
     return 0;
 }
 int64_t lkb_kernel_launches(lkb_ctx_t c) { return c->launches; }

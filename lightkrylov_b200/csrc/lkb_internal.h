@@ -28,7 +28,7 @@ struct NcclApi {
 };
 NcclApi* nccl_api();   // nullptr (+ error set) when libnccl cannot be loaded
 
-enum ProfClass { PC_MATVEC = 0, PC_DOT = 1, PC_AXPY = 2, PC_OTHER = 3, PC_COUNT = 4 };
+enum ProfClass { PC_MATVEC = 0, PC_DOT = 1, PC_AXPY = 2, PC_OTHER = 3, PC_FUSED = 4, PC_COUNT = 8 };
 
 }  // namespace lkb
 
@@ -50,11 +50,12 @@ struct lkb_ctx_s {
     void* hstage = nullptr; size_t hstage_bytes = 0;
     uint64_t seed = 0x1234abcdULL, seed_calls = 0;
     bool graphs = true;
+    bool fused = true;
     bool capturing = false;
     bool profile = false;
     int64_t launches = 0;
-    double prof_ms[lkb::PC_COUNT] = {0, 0, 0, 0};
-    int64_t prof_n[lkb::PC_COUNT] = {0, 0, 0, 0};
+    double prof_ms[lkb::PC_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int64_t prof_n[lkb::PC_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
     struct ProfEv { int cls; cudaEvent_t a, b; };
     std::vector<ProfEv> prof_evs;
     struct GraphEntry { cudaGraphExec_t exec; int64_t launches; };

@@ -33,6 +33,11 @@ void launch_multidot(int kind, cudaStream_t s, const void* V, int64_t ld, int j,
 // w -= V(:, 0:j) c ; optionally nrm2_out[0] = ||w_new||^2 (same two-stage scheme).
 void launch_multiaxpy(int kind, cudaStream_t s, const void* V, int64_t ld, int j, const void* c, void* w, int64_t n,
                       bool want_norm, void* partial, void* nrm2_out, unsigned* counter, const int* flags, int sms);
+// Fused pass-1 multi-axpy + pass-2 multi-dot (TMA + mbarrier pipeline, kernels_fused.cu):
+//   w -= V c1 ; out[0..j) = V^H w_new ; out[j] = w_new^H w_new.   Returns false when the shape is not
+//   supported (j > 128, ragged n, unaligned) -- the caller then runs the two separate kernels.
+bool launch_axpy_dot(int kind, cudaStream_t s, const void* V, int64_t ld, int j, const void* c1, void* w, int64_t n,
+                     void* partial, void* out, unsigned* counter, const int* flags, int sms);
 // y = alpha*x + beta*y  (beta == 0: y is overwritten without being read)
 void launch_axpby(int kind, cudaStream_t s, Scalar alpha, const void* x, Scalar beta, void* y, int64_t n, int sms);
 // y = sgn * (*alpha_dev) * x + y   with alpha on the device (W type)

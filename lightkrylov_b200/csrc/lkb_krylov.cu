@@ -27,24 +27,40 @@ int dgs_enqueue(lkb_ctx_s* c, int kind, const void* V, int64_t ld, int j, void* 
     LKB_TRY(ensure_ws(c, j + 1));
     const size_t nd = (size_t)(j + 1) * (kind_cplx(kind) ? 2 : 1);
     const size_t wsz = kind_cplx(kind) ? 16 : 8;
-    for (int pass = 0; pass < 2; ++pass) {
-        void* cbuf = pass == 0 ? c->c1 : c->c2;
+    // pass 1 coefficients
+    prof_begin(c, PC_DOT);
+    launch_multidot(kind, c->stream, V, ld, j, w, n, c->partial, c->c1, c->counter, flags, c->sms);
+    prof_end(c, PC_DOT, 1);
+    LKB_TRY(check_launch(c, "multidot"));
+    LKB_TRY(allreduce_w(c, c->c1, nd));
+    // pass-1 update fused with the pass-2 coefficients (V read once for both) when the shape allows
+    bool fused = false;
+    if (c->fused) {
+        prof_begin(c, PC_FUSED);
+        fused = launch_axpy_dot(kind, c->stream, V, ld, j, c->c1, w, n, c->partial, c->c2, c->counter, flags, c->sms);
+        prof_end(c, PC_FUSED, fused ? 1 : 0);
+        if (!fused && c->profile && !c->capturing) { cudaEventDestroy(c->prof_evs.back().a); cudaEventDestroy(c->prof_evs.back().b); c->prof_evs.pop_back(); }
+        LKB_TRY(check_launch(c, "axpy_dot"));
+    }
+    if (!fused) {
+        prof_begin(c, PC_AXPY);
+        launch_multiaxpy(kind, c->stream, V, ld, j, c->c1, w, n, false, c->partial, c->nrm2, c->counter, flags, c->sms);
+        prof_end(c, PC_AXPY, 1);
         prof_begin(c, PC_DOT);
-        launch_multidot(kind, c->stream, V, ld, j, w, n, c->partial, cbuf, c->counter, flags, c->sms);
+        launch_multidot(kind, c->stream, V, ld, j, w, n, c->partial, c->c2, c->counter, flags, c->sms);
         prof_end(c, PC_DOT, 1);
         LKB_TRY(check_launch(c, "multidot"));
-        LKB_TRY(allreduce_w(c, cbuf, nd));
-        if (pass == 1 && want_gsinfo) {
-            launch_gsinfo(c->stream, (char*)cbuf + (size_t)j * wsz, kind_cplx(kind), atol_of(kind), c->flags);
-            c->launches++;
-        }
-        const bool nrm = (pass == 1) && want_norm;
-        prof_begin(c, PC_AXPY);
-        launch_multiaxpy(kind, c->stream, V, ld, j, cbuf, w, n, nrm, c->partial, c->nrm2, c->counter, flags, c->sms);
-        prof_end(c, PC_AXPY, 1);
-        LKB_TRY(check_launch(c, "multiaxpy"));
-        if (nrm) LKB_TRY(allreduce_w(c, c->nrm2, 1));
     }
+    LKB_TRY(allreduce_w(c, c->c2, nd));
+    if (want_gsinfo) {
+        launch_gsinfo(c->stream, (char*)c->c2 + (size_t)j * wsz, kind_cplx(kind), atol_of(kind), c->flags);
+        c->launches++;
+    }
+    prof_begin(c, PC_AXPY);
+    launch_multiaxpy(kind, c->stream, V, ld, j, c->c2, w, n, want_norm, c->partial, c->nrm2, c->counter, flags, c->sms);
+    prof_end(c, PC_AXPY, 1);
+    LKB_TRY(check_launch(c, "multiaxpy"));
+    if (want_norm) LKB_TRY(allreduce_w(c, c->nrm2, 1));
     return 0;
 }
 

@@ -438,3 +438,33 @@ def test_arnoldi_full_size_c2(lk, ctx, oracle):
     oracle.set_threads(oracle.max_threads())
     assert oracle.arnoldi(oracle.Op.stencil("d", (nx, ny), POISSON5), Xo, Ho) == 0
     assert rel_normwise(H[:ko + 1, :ko], Ho) < 1e-10
+
+
+# ---------------------------------------------------------------------------------------------
+# fused pass-1-axpy + pass-2-dot kernel (TMA pipeline) against the two separate kernels
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("n,j", [(4096, 1), (4096, 16), (100000, 17), (65536, 64), (200000, 65), (30000, 128), (262144, 100)])
+def test_fused_cgs2_matches_unfused(lk, ctx, oracle, kind, n, j):
+    dt = lk.DTYPES[kind]
+    rng = np.random.default_rng(7 * j + 1)
+    Q, _ = np.linalg.qr(randn(rng, (n, j), dt).astype(np.complex128 if kind in "cz" else np.float64))
+    Xh = np.asfortranarray(Q.astype(dt)); wh = randn(rng, n, dt)
+    out = {}
+    for fused in (1, 0):
+        ctx.set_option("fused", fused)
+        X = lk.Basis(ctx, kind, n, j + 1).put(Xh); X.put(wh, col0=j)
+        info, beta = lk.double_gram_schmidt_step(X, j, 1, X, j, if_chk_orthonormal=False)
+        out[fused] = (info, beta.copy(), X.get(j, 1)[:, 0])
+    ctx.set_option("fused", 1)
+    wo = wh.copy(); oinfo, obeta = oracle.dgs_vec(wo, Xh, j)
+    for fused in (1, 0):
+        info, beta, wg = out[fused]
+        assert info == oinfo == 0
+        assert rel_normwise(beta[:, 0], obeta) < tol_for(kind)
+        assert rel_normwise(wg, wo) < tol_for(kind) * 10
+        assert np.abs(Xh.conj().T @ wg).max() < (1e-13 if kind in "dz" else 1e-5) * np.linalg.norm(wg)
+    # run-to-run determinism of the fused path
+    X = lk.Basis(ctx, kind, n, j + 1).put(Xh); X.put(wh, col0=j)
+    info, beta2 = lk.double_gram_schmidt_step(X, j, 1, X, j, if_chk_orthonormal=False)
+    assert np.array_equal(beta2, out[1][1]) and np.array_equal(X.get(j, 1)[:, 0], out[1][2])
