@@ -9,8 +9,8 @@
 //
 // Data movement: one TMA 2-D tensor map over V(:, 0:j) (column-major, box = TP packs of rows x 16
 // columns, out-of-range rows/columns zero-filled by the hardware, no HBM traffic for them); a
-// 3-stage ring of 64 KB shared-memory tiles filled by cp.async.bulk.tensor (one elected thread),
-// completion on mbarriers.  One CTA per SM (persistent, 192 KB of shared memory).
+// ring of 3..8 shared-memory stages (as many <= 64 KB tiles as fit in ~220 KB) filled by
+// cp.async.bulk.tensor (one elected thread), completion on mbarriers.  One CTA per SM (persistent).
 //   phase A  warp q owns columns 16q..16q+15, lanes own row packs: partial row sums -> smem
 //   combine  w'[tile] = w[tile] - sum over warps (fixed order); stored to HBM and to smem; w'.w'
 //   phase B  per-lane accumulators acc[16] += conj(V[tile, col]) * w'[tile]  (persist over tiles)
@@ -39,6 +39,14 @@ LKB_DI void mbar_wait(uint32_t bar, uint32_t parity) {
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     } while (!done);
+}
+LKB_DI void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+LKB_DI void consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 consumer warps only
+LKB_DI void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 LKB_DI void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
     asm volatile(
@@ -69,11 +77,11 @@ template <typename E> LKB_DI void warp_fold16_f(E (&acc)[16], int lane) {
     acc[0] = add_v(acc[0], shfl_xor_f<E>(acc[0], 1));
 }
 
-enum { FZ_THREADS = 256, FZ_NW = 8, FZ_STAGES = 3, FZ_CB = 16 };
+enum { FZ_THREADS = 288, FZ_NW = 8, FZ_MAXSTAGES = 8, FZ_CB = 16 };   // 8 consumer warps + 1 TMA producer warp
 
 template <int K>
 __global__ void __launch_bounds__(FZ_THREADS, 1)
-k_axpy_dot(const __grid_constant__ CUtensorMap tmap, int j, int tp, int elt_per_pack,
+k_axpy_dot(const __grid_constant__ CUtensorMap tmap, int j, int tp, int nst, int elt_per_pack,
            const typename Tr<K>::W* __restrict__ c1, typename Tr<K>::E* __restrict__ w, int64_t n,
            typename Tr<K>::W* __restrict__ partial, typename Tr<K>::W* __restrict__ out,
            unsigned* __restrict__ counter, const int* __restrict__ flags)
@@ -89,10 +97,12 @@ k_axpy_dot(const __grid_constant__ CUtensorMap tmap, int j, int tp, int elt_per_
     const int jc = (j + FZ_CB - 1) & ~(FZ_CB - 1);
     const int nchunk = jc / FZ_CB;
     const uint32_t stage_bytes = (uint32_t)jc * (uint32_t)tp * 16u;
-    P* part = reinterpret_cast<P*>(smem + (size_t)FZ_STAGES * stage_bytes);   // [nchunk][tp]
+    P* part = reinterpret_cast<P*>(smem + (size_t)nst * stage_bytes);         // [nchunk][tp]
     P* wnew = part + (size_t)FZ_NW * tp;                                       // [tp]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(wnew + tp);                   // [FZ_STAGES]
-    __shared__ double sww[FZ_NW];
+    P* wst = wnew + tp;                                                        // [nst][tp]  w tiles (bulk copies)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wst + (size_t)nst * tp);      // full[nst], empty[nst]
+    uint64_t* ebars = bars + nst;
+    __shared__ double sww[FZ_NW + 1];
     __shared__ bool is_last;
 
     const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
@@ -104,7 +114,7 @@ k_axpy_dot(const __grid_constant__ CUtensorMap tmap, int j, int tp, int elt_per_
     const int nmine = (int)max((int64_t)0, t1 - t0);
 
     if (tid == 0) {
-        for (int s = 0; s < FZ_STAGES; ++s) mbar_init(smem_u32(&bars[s]), 1);
+        for (int s = 0; s < nst; ++s) { mbar_init(smem_u32(&bars[s]), 1); mbar_init(smem_u32(&ebars[s]), FZ_NW); }
         fence_barrier_init();
     }
     __syncthreads();
@@ -120,31 +130,32 @@ k_axpy_dot(const __grid_constant__ CUtensorMap tmap, int j, int tp, int elt_per_
     }
     double wwacc = 0.0;
 
-    auto issue = [&](int it) {
-        const int s = it % FZ_STAGES;
-        const uint32_t bar = smem_u32(&bars[s]);
-        fence_proxy_async();
-        mbar_expect_tx(bar, stage_bytes);
-        const int row0 = (int)((t0 + it) * tp) * elt_per_pack;
-        for (int q = 0; q < nchunk; ++q)
-            tma_load_2d(smem_u32(smem + (size_t)s * stage_bytes + (size_t)q * FZ_CB * tp * 16), &tmap, row0, q * FZ_CB, bar);
-    };
-    if (tid == 0)
-        for (int it = 0; it < FZ_STAGES - 1 && it < nmine; ++it) issue(it);
-
     const int msteps = tp / 32;
+    if (wv == FZ_NW) {
+        // ---- producer warp: one elected lane streams tiles through the ring (one 2-D TMA box of
+        // tp packs x jc columns plus one 1-D bulk copy of the w packs per tile) ----
+        if (lane == 0) {
+            for (int it = 0; it < nmine; ++it) {
+                const int s = it % nst;
+                const int use = it / nst;
+                if (use > 0) mbar_wait(smem_u32(&ebars[s]), (uint32_t)((use - 1) & 1));
+                const uint32_t bar = smem_u32(&bars[s]);
+                const int64_t pk0 = (t0 + it) * tp;
+                const uint32_t wbytes = (uint32_t)min((int64_t)tp, npk - pk0) * 16u;
+                mbar_expect_tx(bar, stage_bytes + wbytes);
+                tma_load_2d(smem_u32(smem + (size_t)s * stage_bytes), &tmap, (int)pk0 * elt_per_pack, 0, bar);
+                bulk_load_1d(smem_u32(wst + (size_t)s * tp), w + pk0 * EPP, wbytes, bar);
+            }
+        }
+    } else
     for (int it = 0; it < nmine; ++it) {
-        const int s = it % FZ_STAGES;
-        const uint32_t parity = (uint32_t)((it / FZ_STAGES) & 1);
+        const int s = it % nst;
+        const uint32_t parity = (uint32_t)((it / nst) & 1);
         const P* tile = reinterpret_cast<const P*>(smem + (size_t)s * stage_bytes);
-        // this tile's packs of w (threads 0..tp-1), issued before the wait to overlap their latency
+        // this tile's packs of w arrive with the V tile (1-D bulk copy on the same mbarrier)
         const bool own = tid < tp;
         const int64_t pk = (t0 + it) * tp + tid;
         const bool inb = own && pk < npk;
-        P wp;
-#pragma unroll
-        for (int e = 0; e < EPP; ++e) wp.v[e] = zero_v(E());
-        if (inb) wp = ld_pack<P>(w + pk * EPP);
 
         mbar_wait(smem_u32(&bars[s]), parity);
 
@@ -164,12 +175,14 @@ k_axpy_dot(const __grid_constant__ CUtensorMap tmap, int j, int tp, int elt_per_
                 part[(size_t)wv * tp + r] = ra;
             }
         }
-        __syncthreads();
-        // every warp is past phase B of the previous tile: its stage can be refilled
-        if (tid == 0 && it + FZ_STAGES - 1 < nmine) issue(it + FZ_STAGES - 1);
+        consumer_sync();
 
         // ---- combine: w' = w - sum over warps (fixed order) ----
         if (own) {
+            P wp;
+#pragma unroll
+            for (int e = 0; e < EPP; ++e) wp.v[e] = zero_v(E());
+            if (inb) wp = wst[(size_t)s * tp + tid];
             P sum = part[tid];
             for (int q = 1; q < nchunk; ++q) {
                 const P t = part[(size_t)q * tp + tid];
@@ -186,7 +199,7 @@ k_axpy_dot(const __grid_constant__ CUtensorMap tmap, int j, int tp, int elt_per_
             }
             wnew[tid] = wp;
         }
-        __syncthreads();
+        consumer_sync();
 
         // ---- phase B: c2 partials, accumulators persist across tiles ----
         if (wv < nchunk) {
@@ -201,6 +214,9 @@ k_axpy_dot(const __grid_constant__ CUtensorMap tmap, int j, int tp, int elt_per_
                 }
             }
         }
+        // this warp is done with the stage: release it to the producer
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&ebars[s]));
     }
 
     // ---- stage 1: one partial row per CTA (each column is owned by exactly one warp) ----
@@ -217,7 +233,7 @@ k_axpy_dot(const __grid_constant__ CUtensorMap tmap, int j, int tp, int elt_per_
     __syncthreads();
     if (tid == 0) {
         double t = sww[0];
-        for (int q = 1; q < FZ_NW; ++q) t += sww[q];
+        for (int q = 1; q < FZ_NW; ++q) t += sww[q];     // the producer warp's slot is always zero
         W o = zero_v(W());
         *reinterpret_cast<double*>(&o) = t;
         partial[(int64_t)blockIdx.x * jp + j] = o;
@@ -230,7 +246,7 @@ k_axpy_dot(const __grid_constant__ CUtensorMap tmap, int j, int tp, int elt_per_
     if (is_last) {
         __threadfence();
         const int nrb = gridDim.x;
-        for (int col = wv; col < jp; col += FZ_NW) {
+        for (int col = wv; col < jp; col += FZ_NW + 1) {
             W a = zero_v(W());
             for (int b = lane; b < nrb; b += 32) wadd(a, __ldcg(&partial[(int64_t)b * jp + col]));
             a = warp_sum(a);
@@ -277,20 +293,27 @@ static bool axpy_dot_t(cudaStream_t s, const void* V, int64_t ld, int j, const v
     CUtensorMap tmap;
     cuuint64_t gdim[2] = {(cuuint64_t)((size_t)n * es / eltsz), (cuuint64_t)j};
     cuuint64_t gstr[1] = {(cuuint64_t)((size_t)ld * es)};
-    cuuint32_t box[2] = {(cuuint32_t)(tp * elt_per_pack), (cuuint32_t)FZ_CB};
+    cuuint32_t box[2] = {(cuuint32_t)(tp * elt_per_pack), (cuuint32_t)jc};   // one box = the whole tile
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&tmap, eltsz == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT64, 2,
                      const_cast<void*>(V), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return false;
-    const size_t sh = (size_t)FZ_STAGES * jc * tp * 16 + (size_t)(FZ_NW + 1) * tp * 16 + 64;
-    static const bool attr_once = (cudaFuncSetAttribute(k_axpy_dot<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024), true);
+    // as many stages as fit: the ring must keep >= ~100 KB in flight per SM to cover the ~2 us loaded
+    // TMA latency at 23 B/clk/SM (measured: 3 x 40 KB stages ran latency-bound at 5.0 TB/s)
+    const size_t budget = 222 * 1024;
+    const size_t fixed = (size_t)(FZ_NW + 1) * tp * 16 + 128;
+    int nst = (int)((budget - fixed) / ((size_t)jc * tp * 16 + (size_t)tp * 16 + 16));
+    if (nst > FZ_MAXSTAGES) nst = FZ_MAXSTAGES;
+    if (nst < 2) return false;
+    const size_t sh = (size_t)nst * jc * tp * 16 + (size_t)(FZ_NW + 1 + nst) * tp * 16 + 16 * nst + 64;
+    static const bool attr_once = (cudaFuncSetAttribute(k_axpy_dot<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024), true);
     (void)attr_once;
     const int64_t ntiles = (n / EPP + tp - 1) / tp;
     int64_t nb = sms;
     if (nb > ntiles) nb = ntiles;
     if (nb > MAX_ROWBLOCKS) nb = MAX_ROWBLOCKS;
-    k_axpy_dot<K><<<(int)nb, FZ_THREADS, sh, s>>>(tmap, j, tp, elt_per_pack, (const W*)c1, (E*)w, n, (W*)partial, (W*)out, counter, flags);
+    k_axpy_dot<K><<<(int)nb, FZ_THREADS, sh, s>>>(tmap, j, tp, nst, elt_per_pack, (const W*)c1, (E*)w, n, (W*)partial, (W*)out, counter, flags);
     return true;
 }
 
