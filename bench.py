@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--no-profile-pass", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fused", action="store_true", help="disable the fused axpy+dot CGS2 kernel (A/B)")
+    ap.add_argument("--no-p2p", action="store_true", help="use ncclAllReduce instead of the in-kernel NVLink allreduce (A/B)")
     ap.add_argument("--cpu-sample-steps", type=int, default=12)
     return ap.parse_args()
 
@@ -170,7 +171,7 @@ def run_reference(args):
         "note": "reference = CPU oracle (C restatement of LightKrylov's per-vector algorithm, OpenMP); the Fortran "
                 "reference cannot be built in this image (no Fortran compiler / fpm / stdlib)",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -185,6 +186,8 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
+    if args.no_p2p:
+        os.environ["LKB_P2P"] = "0"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         ctx = lk.Context.from_torch_distributed(local)
@@ -320,7 +323,8 @@ def run_ours(args):
                        "bench_step": f"one kstart=1..kend={kdim} factorisation = {kdim} Arnoldi steps",
                        "partition": f"grid rows over {world} rank(s), {nloc} rows/rank",
                        "l2": "working set 17.3 GB/GPU-share >> 126 MB L2 (inputs larger than L2, no flush needed)",
-                       "cuda_graph": True, "fused_cgs2": not args.no_fused},
+                       "cuda_graph": True, "fused_cgs2": not args.no_fused,
+                       "allreduce": ("in-kernel NVLink p2p" if ctx.p2p else "ncclAllReduce") if world > 1 else "none"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps,
                     "what": "pinned host start vector -> H2D -> normalise -> lkb_arnoldi -> Hessenberg matrix on the host"},
@@ -332,7 +336,7 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.sync()
     del X, A, x0
     if world > 1:
@@ -340,8 +344,27 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Route fd 1 to stderr while the benchmark runs (NCCL / torchrun banners are printed to stdout by
+    native code); the single JSON line is written to the saved descriptor at the end."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     args = parse()
+    _quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

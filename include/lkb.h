@@ -52,7 +52,14 @@ void* lkb_stream(lkb_ctx_t ctx);                           /* cudaStream_t of th
 const char* lkb_last_error(void);
 int lkb_set_seed(lkb_ctx_t ctx, uint64_t seed);            /* seed of the `rand` TBP stream */
 int lkb_set_graphs(lkb_ctx_t ctx, int enable);             /* CUDA-graph capture of step loops (default on) */
-int lkb_set_option(lkb_ctx_t ctx, const char* name, int value); /* "graphs", "fused" (fused CGS2 kernel, default on) */
+int lkb_set_option(lkb_ctx_t ctx, const char* name, int value); /* "graphs", "fused" (fused CGS2 kernel), "p2p" */
+/* In-kernel NVLink allreduce (all ranks on one NVSwitch box): each rank exports a CUDA-IPC handle
+ * (64 bytes) of its exchange buffer, the caller all-gathers the handles (rank order) and attaches.
+ * Afterwards the (j+1)-coefficient reductions happen inside the multi-dot / fused / multi-axpy
+ * kernels over peer memory instead of separate ncclAllReduce launches.  Optional: without it the
+ * NCCL path is used.  lkb_set_option(ctx, "p2p", 0/1) toggles it. */
+int lkb_p2p_export(lkb_ctx_t ctx, void* handle64);
+int lkb_p2p_attach(lkb_ctx_t ctx, const void* handles_world_x_64);
 int lkb_rank(lkb_ctx_t ctx); int lkb_world(lkb_ctx_t ctx);
 
 /* ---- abstract_vector TBPs : src/AbstractTypes/AbstractVectors.fypp:295-381, 424-460 ------

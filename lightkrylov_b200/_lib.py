@@ -42,6 +42,8 @@ SIGNATURES = {
     "lkb_set_seed": (_i, [_vp, _u64]),
     "lkb_set_graphs": (_i, [_vp, _i]),
     "lkb_set_option": (_i, [_vp, C.c_char_p, _i]),
+    "lkb_p2p_export": (_i, [_vp, _vp]),
+    "lkb_p2p_attach": (_i, [_vp, _vp]),
     "lkb_rank": (_i, [_vp]),
     "lkb_world": (_i, [_vp]),
     "lkb_vec_create": (_i, [_vp, _i, _i64, _i64, _i64, _P(_vp)]),

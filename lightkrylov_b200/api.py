@@ -15,6 +15,7 @@ happens inside liblkb.so on the GPU; numpy is only used to marshal host arrays.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence
 
 import numpy as np
@@ -60,6 +61,7 @@ class Context:
         else:
             check(self.lib.lkb_init(device, C.byref(h)), "lkb_init")
         self.h, self.rank, self.world, self.device = h, rank, world, device
+        self.p2p = False
 
     @staticmethod
     def nccl_unique_id() -> bytes:
@@ -77,7 +79,29 @@ class Context:
             return cls(device)
         obj = [cls.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(obj, src=0)
-        return cls(device, rank, world, obj[0])
+        ctx = cls(device, rank, world, obj[0])
+        if world <= 8 and os.environ.get("LKB_P2P", "1") != "0":
+            # in-kernel NVLink allreduce: exchange CUDA-IPC handles of the per-rank exchange buffers
+            try:
+                mine = ctx.p2p_export()
+                handles = [None] * world
+                dist.all_gather_object(handles, mine)
+                ctx.p2p_attach(b"".join(handles))
+                ctx.p2p = True
+            except LkbError as e:          # no peer access: stay on the NCCL path
+                import warnings
+                warnings.warn(f"p2p allreduce unavailable, using NCCL: {e}")
+            dist.barrier()
+        return ctx
+
+    def p2p_export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        check(self.lib.lkb_p2p_export(self.h, buf), "lkb_p2p_export")
+        return buf.raw
+
+    def p2p_attach(self, handles: bytes):
+        buf = C.create_string_buffer(handles, len(handles))
+        check(self.lib.lkb_p2p_attach(self.h, buf), "lkb_p2p_attach")
 
     def sync(self):
         check(self.lib.lkb_sync(self.h), "lkb_sync")

@@ -18,6 +18,7 @@
 // order (same deterministic two-stage scheme as k_multidot).
 #include <cuda.h>
 #include "lkb_kernels.h"
+#include "lkb_p2p.cuh"
 
 namespace lkb {
 
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1)
 k_axpy_dot(const __grid_constant__ CUtensorMap tmap, int j, int tp, int nst, int elt_per_pack,
            const typename Tr<K>::W* __restrict__ c1, typename Tr<K>::E* __restrict__ w, int64_t n,
            typename Tr<K>::W* __restrict__ partial, typename Tr<K>::W* __restrict__ out,
-           unsigned* __restrict__ counter, const int* __restrict__ flags)
+           unsigned* __restrict__ counter, const int* __restrict__ flags, const P2P p2p)
 {
     using E = typename Tr<K>::E;
     using W = typename Tr<K>::W;
@@ -253,6 +254,7 @@ k_axpy_dot(const __grid_constant__ CUtensorMap tmap, int j, int tp, int nst, int
             if (lane == 0) out[col] = a;
         }
         if (tid == 0) *counter = 0u;
+        if (p2p.world > 1) p2p_allreduce_cta<W>(p2p, out, jp);
     }
 }
 
@@ -276,7 +278,7 @@ static PFN_tmapEncodeTiled get_encode() {
 
 template <int K>
 static bool axpy_dot_t(cudaStream_t s, const void* V, int64_t ld, int j, const void* c1, void* w, int64_t n,
-                       void* partial, void* out, unsigned* counter, const int* flags, int sms) {
+                       void* partial, void* out, unsigned* counter, const int* flags, int sms, const P2P* p2p) {
     using E = typename Tr<K>::E; using W = typename Tr<K>::W;
     constexpr int EPP = Tr<K>::EPP;
     const size_t es = sizeof(E);
@@ -313,17 +315,17 @@ static bool axpy_dot_t(cudaStream_t s, const void* V, int64_t ld, int j, const v
     int64_t nb = sms;
     if (nb > ntiles) nb = ntiles;
     if (nb > MAX_ROWBLOCKS) nb = MAX_ROWBLOCKS;
-    k_axpy_dot<K><<<(int)nb, FZ_THREADS, sh, s>>>(tmap, j, tp, nst, elt_per_pack, (const W*)c1, (E*)w, n, (W*)partial, (W*)out, counter, flags);
+    k_axpy_dot<K><<<(int)nb, FZ_THREADS, sh, s>>>(tmap, j, tp, nst, elt_per_pack, (const W*)c1, (E*)w, n, (W*)partial, (W*)out, counter, flags, p2p ? *p2p : P2P());
     return true;
 }
 
 bool launch_axpy_dot(int kind, cudaStream_t s, const void* V, int64_t ld, int j, const void* c1, void* w, int64_t n,
-                     void* partial, void* out, unsigned* counter, const int* flags, int sms) {
+                     void* partial, void* out, unsigned* counter, const int* flags, int sms, const P2P* p2p) {
     switch (kind) {
-        case KS: return axpy_dot_t<KS>(s, V, ld, j, c1, w, n, partial, out, counter, flags, sms);
-        case KD: return axpy_dot_t<KD>(s, V, ld, j, c1, w, n, partial, out, counter, flags, sms);
-        case KC: return axpy_dot_t<KC>(s, V, ld, j, c1, w, n, partial, out, counter, flags, sms);
-        default: return axpy_dot_t<KZ>(s, V, ld, j, c1, w, n, partial, out, counter, flags, sms);
+        case KS: return axpy_dot_t<KS>(s, V, ld, j, c1, w, n, partial, out, counter, flags, sms, p2p);
+        case KD: return axpy_dot_t<KD>(s, V, ld, j, c1, w, n, partial, out, counter, flags, sms, p2p);
+        case KC: return axpy_dot_t<KC>(s, V, ld, j, c1, w, n, partial, out, counter, flags, sms, p2p);
+        default: return axpy_dot_t<KZ>(s, V, ld, j, c1, w, n, partial, out, counter, flags, sms, p2p);
     }
 }
 

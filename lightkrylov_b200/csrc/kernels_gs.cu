@@ -7,6 +7,7 @@
 // by ONE multi-dot (reads V once, w once) and ONE multi-axpy (reads V once, w once, writes w once).
 // Algorithmic bytes per pass: 2*j*n*s (+3*n*s for w).  No tensor cores: AI ~ 0.25 flop/B.
 #include "lkb_kernels.h"
+#include "lkb_p2p.cuh"
 
 namespace lkb {
 
@@ -52,7 +53,7 @@ __global__ void __launch_bounds__(MD_THREADS, 2)
 k_multidot(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j,
            const typename Tr<K>::E* __restrict__ w, int64_t n,
            typename Tr<K>::W* __restrict__ partial, typename Tr<K>::W* __restrict__ out,
-           unsigned* __restrict__ counter, const int* __restrict__ flags)
+           unsigned* __restrict__ counter, const int* __restrict__ flags, const P2P p2p)
 {
     using E = typename Tr<K>::E;
     using W = typename Tr<K>::W;
@@ -178,6 +179,7 @@ k_multidot(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j,
             if (lane == 0) out[col] = a;
         }
         if (threadIdx.x == 0) *counter = 0u;
+        if (p2p.world > 1) p2p_allreduce_cta<W>(p2p, out, jp);
     }
 }
 
@@ -192,7 +194,7 @@ __global__ void __launch_bounds__(256, 2)
 k_multiaxpy(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j,
             const typename Tr<K>::W* __restrict__ c, typename Tr<K>::E* __restrict__ w, int64_t n,
             double* __restrict__ partial, typename Tr<K>::W* __restrict__ nrm2_out,
-            unsigned* __restrict__ counter, const int* __restrict__ flags)
+            unsigned* __restrict__ counter, const int* __restrict__ flags, const P2P p2p)
 {
     using E = typename Tr<K>::E;
     using W = typename Tr<K>::W;
@@ -258,17 +260,20 @@ k_multiaxpy(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j,
             is_last = (atomicAdd(counter, 1u) == gridDim.x - 1u);
         }
         __syncthreads();
-        if (is_last && wid == 0) {
-            __threadfence();
-            double t = 0.0;
-            for (int b = lane; b < (int)gridDim.x; b += 32) t += __ldcg(&partial[b]);
-            t = warp_sum(t);
-            if (lane == 0) {
-                W o = zero_v(W());
-                *reinterpret_cast<double*>(&o) = t;   // real part
-                nrm2_out[0] = o;
-                *counter = 0u;
+        if (is_last) {
+            if (wid == 0) {
+                __threadfence();
+                double t = 0.0;
+                for (int b = lane; b < (int)gridDim.x; b += 32) t += __ldcg(&partial[b]);
+                t = warp_sum(t);
+                if (lane == 0) {
+                    W o = zero_v(W());
+                    *reinterpret_cast<double*>(&o) = t;   // real part
+                    nrm2_out[0] = o;
+                    *counter = 0u;
+                }
             }
+            if (p2p.world > 1) p2p_allreduce_cta<W>(p2p, nrm2_out, 1);
         }
     }
 }
@@ -276,7 +281,7 @@ k_multiaxpy(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j,
 // ------------------------------------------------------------------------------------------
 template <int K>
 static void multidot_t(cudaStream_t s, const void* V, int64_t ld, int j, const void* w, int64_t n,
-                       void* partial, void* out, unsigned* counter, const int* flags, int sms) {
+                       void* partial, void* out, unsigned* counter, const int* flags, int sms, const P2P* p2p) {
     using E = typename Tr<K>::E; using W = typename Tr<K>::W;
     // grid: fixed function of the problem size (2 resident CTAs per SM), never of timing
     const int64_t ntiles = (n / Tr<K>::EPP + (int64_t)MD_THREADS * 4 - 1) / ((int64_t)MD_THREADS * 4);
@@ -287,22 +292,24 @@ static void multidot_t(cudaStream_t s, const void* V, int64_t ld, int j, const v
     const size_t sh = (size_t)(MD_THREADS / 32) * (size_t)(j + 1) * sizeof(W);
     static const bool attr_once = (cudaFuncSetAttribute(k_multidot<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024), true);
     (void)attr_once;
-    k_multidot<K><<<(int)nb, MD_THREADS, sh, s>>>((const E*)V, ld, j, (const E*)w, n, (W*)partial, (W*)out, counter, flags);
+    k_multidot<K><<<(int)nb, MD_THREADS, sh, s>>>((const E*)V, ld, j, (const E*)w, n, (W*)partial, (W*)out, counter, flags, p2p ? *p2p : P2P());
 }
 void launch_multidot(int kind, cudaStream_t s, const void* V, int64_t ld, int j, const void* w, int64_t n,
-                     void* partial, void* out, unsigned* counter, const int* flags, int sms) {
+                     void* partial, void* out, unsigned* counter, const int* flags, int sms, const P2P* p2p) {
     switch (kind) {
-        case KS: multidot_t<KS>(s, V, ld, j, w, n, partial, out, counter, flags, sms); break;
-        case KD: multidot_t<KD>(s, V, ld, j, w, n, partial, out, counter, flags, sms); break;
-        case KC: multidot_t<KC>(s, V, ld, j, w, n, partial, out, counter, flags, sms); break;
-        default: multidot_t<KZ>(s, V, ld, j, w, n, partial, out, counter, flags, sms); break;
+        case KS: multidot_t<KS>(s, V, ld, j, w, n, partial, out, counter, flags, sms, p2p); break;
+        case KD: multidot_t<KD>(s, V, ld, j, w, n, partial, out, counter, flags, sms, p2p); break;
+        case KC: multidot_t<KC>(s, V, ld, j, w, n, partial, out, counter, flags, sms, p2p); break;
+        default: multidot_t<KZ>(s, V, ld, j, w, n, partial, out, counter, flags, sms, p2p); break;
     }
 }
 
 template <int K>
 static void multiaxpy_t(cudaStream_t s, const void* V, int64_t ld, int j, const void* c, void* w, int64_t n,
-                        bool want_norm, void* partial, void* nrm2_out, unsigned* counter, const int* flags, int sms) {
+                        bool want_norm, void* partial, void* nrm2_out, unsigned* counter, const int* flags, int sms,
+                        const P2P* p2p) {
     using E = typename Tr<K>::E; using W = typename Tr<K>::W;
+    const P2P pp = p2p ? *p2p : P2P();
     const int64_t npk = n / Tr<K>::EPP;
     int64_t nb = (npk + 255) / 256;
     if (nb < 1) nb = 1;
@@ -310,17 +317,18 @@ static void multiaxpy_t(cudaStream_t s, const void* V, int64_t ld, int j, const 
     if (nb > MAX_ROWBLOCKS) nb = MAX_ROWBLOCKS;
     const size_t sh = (size_t)(j > 0 ? j : 1) * sizeof(E);
     if (want_norm)
-        k_multiaxpy<K, true><<<(int)nb, 256, sh, s>>>((const E*)V, ld, j, (const W*)c, (E*)w, n, (double*)partial, (W*)nrm2_out, counter, flags);
+        k_multiaxpy<K, true><<<(int)nb, 256, sh, s>>>((const E*)V, ld, j, (const W*)c, (E*)w, n, (double*)partial, (W*)nrm2_out, counter, flags, pp);
     else
-        k_multiaxpy<K, false><<<(int)nb, 256, sh, s>>>((const E*)V, ld, j, (const W*)c, (E*)w, n, (double*)partial, (W*)nrm2_out, counter, flags);
+        k_multiaxpy<K, false><<<(int)nb, 256, sh, s>>>((const E*)V, ld, j, (const W*)c, (E*)w, n, (double*)partial, (W*)nrm2_out, counter, flags, pp);
 }
 void launch_multiaxpy(int kind, cudaStream_t s, const void* V, int64_t ld, int j, const void* c, void* w, int64_t n,
-                      bool want_norm, void* partial, void* nrm2_out, unsigned* counter, const int* flags, int sms) {
+                      bool want_norm, void* partial, void* nrm2_out, unsigned* counter, const int* flags, int sms,
+                      const P2P* p2p) {
     switch (kind) {
-        case KS: multiaxpy_t<KS>(s, V, ld, j, c, w, n, want_norm, partial, nrm2_out, counter, flags, sms); break;
-        case KD: multiaxpy_t<KD>(s, V, ld, j, c, w, n, want_norm, partial, nrm2_out, counter, flags, sms); break;
-        case KC: multiaxpy_t<KC>(s, V, ld, j, c, w, n, want_norm, partial, nrm2_out, counter, flags, sms); break;
-        default: multiaxpy_t<KZ>(s, V, ld, j, c, w, n, want_norm, partial, nrm2_out, counter, flags, sms); break;
+        case KS: multiaxpy_t<KS>(s, V, ld, j, c, w, n, want_norm, partial, nrm2_out, counter, flags, sms, p2p); break;
+        case KD: multiaxpy_t<KD>(s, V, ld, j, c, w, n, want_norm, partial, nrm2_out, counter, flags, sms, p2p); break;
+        case KC: multiaxpy_t<KC>(s, V, ld, j, c, w, n, want_norm, partial, nrm2_out, counter, flags, sms, p2p); break;
+        default: multiaxpy_t<KZ>(s, V, ld, j, c, w, n, want_norm, partial, nrm2_out, counter, flags, sms, p2p); break;
     }
 }
 

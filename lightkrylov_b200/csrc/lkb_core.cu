@@ -103,7 +103,7 @@ int ensure_Hd(lkb_ctx_s* c, size_t bytes) { return grow(&c->Hd, &c->Hd_bytes, by
 int ensure_coefd(lkb_ctx_s* c, size_t bytes) { return grow(&c->coefd, &c->coefd_bytes, bytes); }
 
 int allreduce_w(lkb_ctx_s* c, void* buf, size_t ndoubles) {
-    if (c->world == 1) return 0;
+    if (c->world == 1 || c->p2p_active) return 0;      // p2p: already reduced inside the producing kernel
     NcclApi* api = nccl_api();
     if (!api) return LKB_ERR_NCCL;
     LKB_NCCL(api->AllReduce(buf, buf, ndoubles, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->comm, c->stream));
@@ -124,7 +124,7 @@ int fetch_flags(lkb_ctx_s* c, int* host_flags) {
 int norm2_enqueue(lkb_ctx_s* c, int kind, const void* w, int64_t n, const int* flags) {
     LKB_TRY(ensure_ws(c, 1));
     prof_begin(c, PC_DOT);
-    launch_multidot(kind, c->stream, w, n, 0, w, n, c->partial, c->nrm2, c->counter, flags, c->sms);
+    launch_multidot(kind, c->stream, w, n, 0, w, n, c->partial, c->nrm2, c->counter, flags, c->sms, c->p2p_arg());
     prof_end(c, PC_DOT, 1);
     LKB_TRY(check_launch(c, "norm2"));
     return allreduce_w(c, c->nrm2, 1);
@@ -140,7 +140,7 @@ int vec_norm_sync(lkb_ctx_s* c, int kind, const void* w, int64_t n, double* out)
 int vec_dot_sync(lkb_ctx_s* c, int kind, const void* x, const void* y, int64_t n, Scalar* out) {
     LKB_TRY(ensure_ws(c, 2));
     prof_begin(c, PC_DOT);
-    launch_multidot(kind, c->stream, x, n, 1, y, n, c->partial, c->tmpw, c->counter, nullptr, c->sms);
+    launch_multidot(kind, c->stream, x, n, 1, y, n, c->partial, c->tmpw, c->counter, nullptr, c->sms, c->p2p_arg());
     prof_end(c, PC_DOT, 1);
     LKB_TRY(check_launch(c, "dot"));
     LKB_TRY(allreduce_w(c, c->tmpw, kind_cplx(kind) ? 2 : 1));
@@ -234,6 +234,9 @@ int lkb_finalize(lkb_ctx_t c) {
     cudaStreamSynchronize(c->stream);
     for (auto& kv : c->graph_cache) cudaGraphExecDestroy(kv.second.exec);
     if (c->comm && nccl_api()) nccl_api()->CommDestroy(c->comm);
+    for (int r = 0; r < c->p2p.world; ++r) if (r != c->rank && c->p2p.peer[r]) cudaIpcCloseMemHandle(c->p2p.peer[r]);
+    if (c->p2p_region) cudaFree(c->p2p_region);
+    if (c->p2p.epoch) cudaFree(c->p2p.epoch);
     void* bufs[] = { c->partial, c->c1, c->c2, c->tmpw, c->nrm2, c->inv, c->flags, c->counter, c->Hd, c->coefd };
     for (void* b : bufs) if (b) cudaFree(b);
     if (c->hstage) cudaFreeHost(c->hstage);
@@ -249,7 +252,40 @@ int lkb_set_option(lkb_ctx_t c, const char* name, int value) {
     if (!c || !name) return LKB_ERR_ARG;
     if (!strcmp(name, "graphs")) c->graphs = value != 0;
     else if (!strcmp(name, "fused")) c->fused = value != 0;
+    else if (!strcmp(name, "p2p")) c->p2p_active = (value != 0) && c->p2p.world > 1;
     else { set_error("unknown option %s", name); return LKB_ERR_ARG; }
+    return 0;
+}
+int lkb_p2p_export(lkb_ctx_t c, void* handle64) {
+    if (!c || !handle64) return LKB_ERR_ARG;
+    cudaSetDevice(c->dev);
+    if (!c->p2p_region) {
+        LKB_CUDA(cudaMalloc(&c->p2p_region, p2p_region_bytes()));
+        LKB_CUDA(cudaMemset(c->p2p_region, 0, p2p_region_bytes()));
+        LKB_CUDA(cudaMalloc((void**)&c->p2p.epoch, 64));
+        LKB_CUDA(cudaMemset(c->p2p.epoch, 0, 64));
+        LKB_CUDA(cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t h;
+    LKB_CUDA(cudaIpcGetMemHandle(&h, c->p2p_region));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+int lkb_p2p_attach(lkb_ctx_t c, const void* handles) {
+    if (!c || !handles || !c->p2p_region) { set_error("p2p_attach: call lkb_p2p_export first"); return LKB_ERR_ARG; }
+    if (c->world < 2 || c->world > P2P_MAXW) { set_error("p2p_attach: world size %d not supported (2..%d)", c->world, (int)P2P_MAXW); return LKB_ERR_ARG; }
+    cudaSetDevice(c->dev);
+    c->p2p.world = c->world; c->p2p.rank = c->rank;
+    for (int r = 0; r < c->world; ++r) {
+        if (r == c->rank) { c->p2p.peer[r] = (char*)c->p2p_region; continue; }
+        cudaIpcMemHandle_t h; memcpy(&h, (const char*)handles + 64 * (size_t)r, 64);
+        void* ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { set_error("cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e)); cudaGetLastError(); return LKB_ERR_CUDA; }
+        c->p2p.peer[r] = (char*)ptr;
+    }
+    c->p2p_active = true;
     return 0;
 }
 int lkb_rank(lkb_ctx_t c) { return c->rank; }

@@ -51,6 +51,11 @@ struct lkb_ctx_s {
     uint64_t seed = 0x1234abcdULL, seed_calls = 0;
     bool graphs = true;
     bool fused = true;
+    // in-kernel NVLink allreduce (CUDA IPC peer buffers); falls back to NCCL when not attached
+    bool p2p_active = false;
+    lkb::P2P p2p;
+    void* p2p_region = nullptr;
+    const lkb::P2P* p2p_arg() const { return p2p_active ? &p2p : nullptr; }
     bool capturing = false;
     bool profile = false;
     int64_t launches = 0;

@@ -18,6 +18,16 @@ enum { MD_CB = 16 };           // basis columns per multi-dot CTA
 enum { MD_THREADS = 256 };
 enum { MAX_ROWBLOCKS = 1024 }; // upper bound on stage-1 partial rows
 
+// In-kernel allreduce over NVLink peer memory (one process per GPU, buffers mapped with CUDA IPC).
+// Region layout per rank: flags[world] (one per 128 B line) | data[2][world][P2P_SLOT] (16-byte words).
+enum { P2P_MAXW = 8, P2P_SLOT = 1040, P2P_FLAG_BYTES = 128 * P2P_MAXW };
+struct P2P {
+    int world = 1, rank = 0;
+    unsigned* epoch = nullptr;          // device-side collective counter (identical on all ranks)
+    char* peer[P2P_MAXW] = {nullptr};   // peer[r] = rank r's region as mapped in this process
+};
+static inline size_t p2p_region_bytes() { return (size_t)P2P_FLAG_BYTES + 2 * (size_t)P2P_MAXW * P2P_SLOT * 16; }
+
 struct StencilArgs {
     int64_t nx, ny, nz;        // local slab: nx fastest; the slowest axis is the sharded one
     Scalar coef[7];            // center, -x, +x, -y, +y, -z, +z
@@ -29,15 +39,16 @@ struct StencilArgs {
 // c[0..j) = V(:, 0:j)^H w, c[j] = w^H w.  Two-stage deterministic reduction; the last CTA to
 // finish folds the stage-1 partials in fixed order into out[0..j].
 void launch_multidot(int kind, cudaStream_t s, const void* V, int64_t ld, int j, const void* w, int64_t n,
-                     void* partial, void* out, unsigned* counter, const int* flags, int sms);
+                     void* partial, void* out, unsigned* counter, const int* flags, int sms, const P2P* p2p = nullptr);
 // w -= V(:, 0:j) c ; optionally nrm2_out[0] = ||w_new||^2 (same two-stage scheme).
 void launch_multiaxpy(int kind, cudaStream_t s, const void* V, int64_t ld, int j, const void* c, void* w, int64_t n,
-                      bool want_norm, void* partial, void* nrm2_out, unsigned* counter, const int* flags, int sms);
+                      bool want_norm, void* partial, void* nrm2_out, unsigned* counter, const int* flags, int sms,
+                      const P2P* p2p = nullptr);
 // Fused pass-1 multi-axpy + pass-2 multi-dot (TMA + mbarrier pipeline, kernels_fused.cu):
 //   w -= V c1 ; out[0..j) = V^H w_new ; out[j] = w_new^H w_new.   Returns false when the shape is not
 //   supported (j > 128, ragged n, unaligned) -- the caller then runs the two separate kernels.
 bool launch_axpy_dot(int kind, cudaStream_t s, const void* V, int64_t ld, int j, const void* c1, void* w, int64_t n,
-                     void* partial, void* out, unsigned* counter, const int* flags, int sms);
+                     void* partial, void* out, unsigned* counter, const int* flags, int sms, const P2P* p2p = nullptr);
 // y = alpha*x + beta*y  (beta == 0: y is overwritten without being read)
 void launch_axpby(int kind, cudaStream_t s, Scalar alpha, const void* x, Scalar beta, void* y, int64_t n, int sms);
 // y = sgn * (*alpha_dev) * x + y   with alpha on the device (W type)

@@ -29,7 +29,7 @@ int dgs_enqueue(lkb_ctx_s* c, int kind, const void* V, int64_t ld, int j, void* 
     const size_t wsz = kind_cplx(kind) ? 16 : 8;
     // pass 1 coefficients
     prof_begin(c, PC_DOT);
-    launch_multidot(kind, c->stream, V, ld, j, w, n, c->partial, c->c1, c->counter, flags, c->sms);
+    launch_multidot(kind, c->stream, V, ld, j, w, n, c->partial, c->c1, c->counter, flags, c->sms, c->p2p_arg());
     prof_end(c, PC_DOT, 1);
     LKB_TRY(check_launch(c, "multidot"));
     LKB_TRY(allreduce_w(c, c->c1, nd));
@@ -37,17 +37,17 @@ int dgs_enqueue(lkb_ctx_s* c, int kind, const void* V, int64_t ld, int j, void* 
     bool fused = false;
     if (c->fused) {
         prof_begin(c, PC_FUSED);
-        fused = launch_axpy_dot(kind, c->stream, V, ld, j, c->c1, w, n, c->partial, c->c2, c->counter, flags, c->sms);
+        fused = launch_axpy_dot(kind, c->stream, V, ld, j, c->c1, w, n, c->partial, c->c2, c->counter, flags, c->sms, c->p2p_arg());
         prof_end(c, PC_FUSED, fused ? 1 : 0);
         if (!fused && c->profile && !c->capturing) { cudaEventDestroy(c->prof_evs.back().a); cudaEventDestroy(c->prof_evs.back().b); c->prof_evs.pop_back(); }
         LKB_TRY(check_launch(c, "axpy_dot"));
     }
     if (!fused) {
         prof_begin(c, PC_AXPY);
-        launch_multiaxpy(kind, c->stream, V, ld, j, c->c1, w, n, false, c->partial, c->nrm2, c->counter, flags, c->sms);
+        launch_multiaxpy(kind, c->stream, V, ld, j, c->c1, w, n, false, c->partial, c->nrm2, c->counter, flags, c->sms, c->p2p_arg());
         prof_end(c, PC_AXPY, 1);
         prof_begin(c, PC_DOT);
-        launch_multidot(kind, c->stream, V, ld, j, w, n, c->partial, c->c2, c->counter, flags, c->sms);
+        launch_multidot(kind, c->stream, V, ld, j, w, n, c->partial, c->c2, c->counter, flags, c->sms, c->p2p_arg());
         prof_end(c, PC_DOT, 1);
         LKB_TRY(check_launch(c, "multidot"));
     }
@@ -57,7 +57,7 @@ int dgs_enqueue(lkb_ctx_s* c, int kind, const void* V, int64_t ld, int j, void* 
         c->launches++;
     }
     prof_begin(c, PC_AXPY);
-    launch_multiaxpy(kind, c->stream, V, ld, j, c->c2, w, n, want_norm, c->partial, c->nrm2, c->counter, flags, c->sms);
+    launch_multiaxpy(kind, c->stream, V, ld, j, c->c2, w, n, want_norm, c->partial, c->nrm2, c->counter, flags, c->sms, c->p2p_arg());
     prof_end(c, PC_AXPY, 1);
     LKB_TRY(check_launch(c, "multiaxpy"));
     if (want_norm) LKB_TRY(allreduce_w(c, c->nrm2, 1));
@@ -188,7 +188,7 @@ static int check_orthonormal(lkb_basis_s* X, int j, bool* ok) {
     std::vector<Scalar> col;
     for (int q = 0; q < j && *ok; ++q) {
         LKB_TRY(ensure_ws(c, j + 1));
-        launch_multidot(X->kind, c->stream, X->d, X->ld, j, col_ptr(X, q), X->n, c->partial, c->c1, c->counter, nullptr, c->sms);
+        launch_multidot(X->kind, c->stream, X->d, X->ld, j, col_ptr(X, q), X->n, c->partial, c->c1, c->counter, nullptr, c->sms, c->p2p_arg());
         c->launches++;
         LKB_TRY(check_launch(c, "gram"));
         LKB_TRY(allreduce_w(c, c->c1, (size_t)(j + 1) * (kind_cplx(X->kind) ? 2 : 1)));
@@ -213,7 +213,7 @@ int lkb_basis_innerprod(lkb_basis_t X, int j, lkb_basis_t W, int wcol0, int p, v
     for (int q = 0; q < p; ++q) {
         LKB_TRY(ensure_ws(c, j + 1));
         prof_begin(c, PC_DOT);
-        launch_multidot(X->kind, c->stream, X->d, X->ld, j, col_ptr(W, wcol0 + q), X->n, c->partial, c->c1, c->counter, nullptr, c->sms);
+        launch_multidot(X->kind, c->stream, X->d, X->ld, j, col_ptr(W, wcol0 + q), X->n, c->partial, c->c1, c->counter, nullptr, c->sms, c->p2p_arg());
         prof_end(c, PC_DOT, 1);
         LKB_TRY(check_launch(c, "innerprod"));
         LKB_TRY(allreduce_w(c, c->c1, (size_t)(j + 1) * (kind_cplx(X->kind) ? 2 : 1)));
@@ -231,7 +231,7 @@ int lkb_basis_lincomb_sub(lkb_basis_t X, int j, const void* coef, int ldcoef, lk
     for (int q = 0; q < p; ++q) {
         LKB_TRY(upload_coef(c, X->kind, (const char*)coef + (size_t)ldcoef * q * kind_size(X->kind), j, 1.0));
         prof_begin(c, PC_AXPY);
-        launch_multiaxpy(X->kind, c->stream, X->d, X->ld, j, c->coefd, col_ptr(W, wcol0 + q), X->n, false, c->partial, c->nrm2, c->counter, nullptr, c->sms);
+        launch_multiaxpy(X->kind, c->stream, X->d, X->ld, j, c->coefd, col_ptr(W, wcol0 + q), X->n, false, c->partial, c->nrm2, c->counter, nullptr, c->sms, c->p2p_arg());
         prof_end(c, PC_AXPY, 1);
         LKB_TRY(check_launch(c, "lincomb_sub"));
     }
@@ -245,7 +245,7 @@ int lkb_basis_lincomb(lkb_basis_t X, int j, const void* coef, lkb_vec_t y) {
     LKB_TRY(upload_coef(c, X->kind, coef, j, -1.0));
     LKB_TRY(lkb_vec_zero(y));
     prof_begin(c, PC_AXPY);
-    launch_multiaxpy(X->kind, c->stream, X->d, X->ld, j, c->coefd, y->d, X->n, false, c->partial, c->nrm2, c->counter, nullptr, c->sms);
+    launch_multiaxpy(X->kind, c->stream, X->d, X->ld, j, c->coefd, y->d, X->n, false, c->partial, c->nrm2, c->counter, nullptr, c->sms, c->p2p_arg());
     prof_end(c, PC_AXPY, 1);
     return check_launch(c, "lincomb");
 }
@@ -272,12 +272,12 @@ static int gs_common(lkb_basis_t X, int j, lkb_basis_t W, int wcol0, int p, int3
         } else {
             LKB_TRY(ensure_ws(c, j + 1));
             prof_begin(c, PC_DOT);
-            launch_multidot(X->kind, c->stream, X->d, X->ld, j, w, X->n, c->partial, c->c1, c->counter, nullptr, c->sms);
+            launch_multidot(X->kind, c->stream, X->d, X->ld, j, w, X->n, c->partial, c->c1, c->counter, nullptr, c->sms, c->p2p_arg());
             prof_end(c, PC_DOT, 1);
             LKB_TRY(allreduce_w(c, c->c1, (size_t)(j + 1) * (kind_cplx(X->kind) ? 2 : 1)));
             launch_gsinfo(c->stream, (char*)c->c1 + (size_t)j * (kind_cplx(X->kind) ? 16 : 8), 0, atol_of(X->kind), c->flags);
             prof_begin(c, PC_AXPY);
-            launch_multiaxpy(X->kind, c->stream, X->d, X->ld, j, c->c1, w, X->n, false, c->partial, c->nrm2, c->counter, nullptr, c->sms);
+            launch_multiaxpy(X->kind, c->stream, X->d, X->ld, j, c->c1, w, X->n, false, c->partial, c->nrm2, c->counter, nullptr, c->sms, c->p2p_arg());
             prof_end(c, PC_AXPY, 1);
             LKB_TRY(check_launch(c, "orthogonalize"));
         }
@@ -480,7 +480,7 @@ int lkb_lanczos(lkb_op_t A, lkb_basis_t X, void* T, int ldt, int32_t* info, int3
             for (int i = (k - 1 > 1 ? k - 1 : 1); i <= k; ++i) {        // update_tridiag_matrix :57-59
                 void* xi = col_ptr(X, i - 1);
                 prof_begin(c, PC_DOT);
-                launch_multidot(kind, c->stream, xi, X->ld, 1, w, X->n, c->partial, c->tmpw, c->counter, c->flags, c->sms);
+                launch_multidot(kind, c->stream, xi, X->ld, 1, w, X->n, c->partial, c->tmpw, c->counter, c->flags, c->sms, c->p2p_arg());
                 prof_end(c, PC_DOT, 1);
                 LKB_TRY(allreduce_w(c, c->tmpw, ndw));
                 prof_begin(c, PC_OTHER);

@@ -22,6 +22,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = lk.Context.from_torch_distributed(local)
     assert ctx.world == world and ctx.rank == rank
+    assert ctx.p2p, "in-kernel NVLink allreduce should be active on a single NVSwitch box"
 
     def gather_rows(local_arr):
         parts = [None] * world
@@ -50,6 +51,21 @@ def main():
             assert rel_normwise(H, Ho) < 1e-10, rel_normwise(H, Ho)
             assert np.abs(Xg.T @ Xg - np.eye(kdim + 1)).max() < 1e-12
             assert rel_normwise(Xg, Xo) < 1e-8
+
+    # ---- in-kernel p2p allreduce vs ncclAllReduce: same factorisation to rounding, both deterministic ----
+    A = lk.LinOp.stencil5(ctx, "d", nx, ny, POISSON5)
+    Hs = {}
+    for mode in (1, 0, 1):
+        ctx.set_option("p2p", mode)
+        X = lk.Basis(ctx, "d", A.n, kdim + 1, n_global=n, row0=A.row0)
+        x0 = X.col(0).fill_random("uniform", 42); x0.scal(1.0 / x0.norm())
+        H = np.zeros((kdim + 1, kdim), order="F")
+        assert lk.arnoldi(A, X, H) == 0
+        if mode in Hs:
+            assert np.array_equal(Hs[mode], H), "p2p allreduce must be run-to-run deterministic"
+        Hs[mode] = H
+    assert rel_normwise(Hs[1], Hs[0]) < 1e-12
+    ctx.set_option("p2p", 1)
 
     # ---- 3-D 7-point, z-sharded: lanczos + cg + gmres ----
     dims = (20, 16, 13); n3 = int(np.prod(dims)); kd = 24
