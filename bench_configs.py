@@ -1,0 +1,167 @@
+#!/usr/bin/env python
+"""bench_configs.py -- the other BASELINE.json configs (C2 gmres, C3 eigs, C4 lanczos/eighs/cg,
+C5 bidiagonalization/svds) run through the public API on one GPU, with property checks.
+
+These are NOT the headline bench lines (bench.py measures configs[1]); they show the callers of
+the hot path working at (or near) the named sizes and report steps/s plus achieved GB/s against
+the official per-step algorithmic bytes.  One JSON line per config.
+
+    python bench_configs.py [--full] [--only c2,c3,c4,c5]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import lightkrylov_b200 as lk  # noqa: E402
+
+POISSON5 = (4.0, -1.0, -1.0, -1.0, -1.0)
+CONVDIFF7 = (6.0, -1.3, -0.7, -1.2, -0.8, -1.1, -0.9)
+LAPLACE7 = (6.0, -1.0, -1.0, -1.0, -1.0, -1.0, -1.0)
+PEAK = 6553.6
+if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+
+
+def timed(ctx, fn):
+    ctx.sync(); t0 = time.perf_counter(); r = fn(); ctx.sync()
+    return r, time.perf_counter() - t0
+
+
+def emit(**kw):
+    print(json.dumps(kw), flush=True)
+
+
+def c2_gmres(ctx, full):
+    nx = ny = 4096 if full else 2048
+    n = nx * ny
+    A = lk.LinOp.stencil5(ctx, "d", nx, ny, POISSON5)
+    b = lk.Vector(ctx, "d", n).fill_random("uniform", 43)
+    x = lk.Vector(ctx, "d", n)
+    (info, meta), dt = timed(ctx, lambda: lk.gmres(A, b, x, kdim=50, maxiter=10))
+    r = lk.Vector(ctx, "d", n); A.matvec(x, r); r.sub(b)
+    steps = meta["n_inner"]
+    # per inner step j: matvec + 4*j*n*s (official); j cycles 1..50
+    byts = sum(2 * n * 8 + 4 * ((i % 50) + 1) * n * 8 for i in range(steps))
+    emit(config="C2 gmres(kdim=50, maxiter=10) 5-pt Poisson %dx%d fp64" % (nx, ny), n=n, info=info,
+         n_inner=steps, n_outer=meta["n_outer"], converged=meta["converged"], seconds=dt,
+         inner_steps_per_s=steps / dt, alg_GBps=byts / dt / 1e9, frac_of_measured_hbm=byts / dt / 1e9 / PEAK,
+         final_residual=r.norm(), res_first=meta["res"][0], res_last=meta["res"][-1])
+
+
+def c3_eigs(ctx, full):
+    m = 512 if full else 256
+    n = m ** 3
+    lk.set_lapack_from_scipy()
+    A = lk.LinOp.stencil7(ctx, "d", m, m, m, CONVDIFF7)
+    nev, kdim = 8, 128
+    X = lk.Basis(ctx, "d", n, nev)
+    x0 = lk.Vector(ctx, "d", n).fill_random("uniform", 44)
+    (res, dt) = timed(ctx, lambda: lk.eigs(A, X, nev, x0=x0, kdim=kdim, tolerance=1e-6))
+    ev, resid, info = res
+    # residual check of the leading real-pair / real eigenpair on the device
+    y = lk.Vector(ctx, "d", n)
+    chk = None
+    if abs(ev[0].imag) == 0:
+        A.matvec(X.col(0), y); y.axpby(-ev[0].real, X.col(0), 1.0); chk = y.norm() / X.col(0).norm()
+    emit(config="C3 eigs(nev=8, kdim=128) 7-pt convection-diffusion %d^3 fp64, 1 GPU" % m, n=n, info_niter=int(info),
+         seconds=dt, arnoldi_steps_per_s=info / dt, eigvals=[[float(z.real), float(z.imag)] for z in ev],
+         residuals=[float(r) for r in resid], leading_pair_residual=chk, matvecs=A.counters()[0])
+
+
+def c4_sym(ctx, full):
+    m = 384 if full else 256
+    n = m ** 3
+    lk.set_lapack_from_scipy()
+    for kind in ("d", "s"):
+        es = 8 if kind == "d" else 4
+        A = lk.LinOp.stencil7(ctx, kind, m, m, m, LAPLACE7)
+        kdim = 128
+        X = lk.Basis(ctx, kind, n, kdim + 1)
+        x0 = X.col(0).fill_random("uniform", 45); x0.scal(1.0 / x0.norm())
+        T = np.zeros((kdim + 1, kdim), dtype=lk.DTYPES[kind], order="F")
+        lk.lanczos(A, X, T)                                             # warm-up (graph capture)
+        (info, dt) = timed(ctx, lambda: lk.lanczos(A, X, T))
+        G = X.innerprod(kdim + 1, X, wcol0=0, p=8)                      # first 8 columns of the Gram matrix
+        orth = float(np.abs(G - np.eye(kdim + 1)[:, :8]).max())
+        byts = sum(2 * n * es + 4 * j * n * es + 4 * n * es for j in range(1, kdim + 1))
+        emit(config="C4 lanczos(kdim=128) 7-pt Laplacian %d^3 %s" % (m, "fp64" if kind == "d" else "fp32"), n=n,
+             info=info, seconds=dt, steps_per_s=kdim / dt, alg_GBps=byts / dt / 1e9,
+             frac_of_measured_hbm=byts / dt / 1e9 / PEAK, orth_err_first8=orth,
+             T_sym_err=float(np.abs(np.diag(T, 1)[:kdim - 1] - np.diag(T, -1)[:kdim - 1]).max()))
+        del X
+        Xe = lk.Basis(ctx, kind, n, 8)
+        x0 = lk.Vector(ctx, kind, n).fill_random("uniform", 45)
+        (res, dt) = timed(ctx, lambda: lk.eighs(A, Xe, 8, x0=x0, kdim=128, tolerance=1e-6 if kind == "d" else 1e-3))
+        ev, resid, info = res
+        emit(config="C4 eighs(nev=8, kdim=128) %d^3 %s" % (m, "fp64" if kind == "d" else "fp32"), info_k=int(info),
+             seconds=dt, eigvals=[float(v) for v in ev], residuals=[float(r) for r in resid])
+        del Xe
+        b = lk.Vector(ctx, kind, n).fill_random("uniform", 45); x = lk.Vector(ctx, kind, n)
+        ((info, meta), dt) = timed(ctx, lambda: lk.cg(A, b, x, maxiter=2000))
+        byts = meta["n_iter"] * (2 + 2 + 3 + 3 + 2 + 3) * n * es     # matvec, dot, 2 axpby(3), dot, axpby per iteration
+        emit(config="C4 cg(maxiter=2000) %d^3 %s" % (m, "fp64" if kind == "d" else "fp32"), info=int(info),
+             n_iter=meta["n_iter"], converged=meta["converged"], seconds=dt, iters_per_s=meta["n_iter"] / dt,
+             alg_GBps=byts / dt / 1e9, res_last=meta["res"][-1])
+
+
+def c5_svds(ctx, full):
+    # 50M x 40M with 32 nnz/row needs ~110 GB (values + transpose copy): run a 1/10-scale replica by default
+    m, n = (50_000_000, 40_000_000) if full else (5_000_000, 4_000_000)
+    per_row = 32
+    lk.set_lapack_from_scipy()
+    rng = np.random.default_rng(46)
+    t0 = time.perf_counter()
+    col = np.sort(rng.integers(0, n, size=(m, per_row), dtype=np.int32), axis=1).ravel()
+    val = (rng.standard_normal(m * per_row) + 1j * rng.standard_normal(m * per_row)).astype(np.complex128)
+    rowptr = np.arange(0, (m + 1) * per_row, per_row, dtype=np.int64)
+    tgen = time.perf_counter() - t0
+    A = lk.LinOp.csr(ctx, m, n, rowptr, col, val)
+    del col, val
+    kdim, nsv = 32, 8
+    U = lk.Basis(ctx, "z", m, kdim + 1); V = lk.Basis(ctx, "z", n, kdim + 1)
+    u0 = U.col(0).fill_random("normal", 47); u0.scal(1.0 / u0.norm())
+    B = np.zeros((kdim + 1, kdim), dtype=np.complex128, order="F")
+    lk.bidiagonalization(A, U, V, B)
+    (info, dt) = timed(ctx, lambda: lk.bidiagonalization(A, U, V, B))
+    nnz = m * per_row
+    es = 16
+    spmv = nnz * (es + 4) + 8 * (m + 1) + (n + m) * es
+    byts = sum(2 * spmv + 4 * (k - 1) * n * es + 4 * k * m * es for k in range(1, kdim + 1))
+    emit(config="C5 bidiagonalization(kdim=32) random CSR %dx%d, 32 nnz/row, cdp" % (m, n), info=int(info), seconds=dt,
+         steps_per_s=kdim / dt, alg_GBps=byts / dt / 1e9, frac_of_measured_hbm=byts / dt / 1e9 / PEAK,
+         host_generation_s=tgen, B_diag_first=[float(abs(B[i, i])) for i in range(4)])
+    Us = lk.Basis(ctx, "z", m, nsv); Vs = lk.Basis(ctx, "z", n, nsv)
+    u0 = lk.Vector(ctx, "z", m).fill_random("normal", 47)
+    (res, dt) = timed(ctx, lambda: lk.svds(A, Us, Vs, nsv, u0=u0, kdim=32, tolerance=1e-6))
+    S, resid, info = res
+    y = lk.Vector(ctx, "z", m); A.matvec(Vs.col(0), y); y.axpby(-S[0], Us.col(0), 1.0)
+    emit(config="C5 svds(nsv=8, kdim=32)", info_k=int(info), seconds=dt, S=[float(s) for s in S],
+         residuals=[float(r) for r in resid], triplet0_residual=y.norm())
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--full", action="store_true", help="BASELINE.json sizes (C3 512^3, C4 384^3, C5 50Mx40M)")
+    ap.add_argument("--only", default="c2,c3,c4,c5")
+    args = ap.parse_args()
+    ctx = lk.Context(0)
+    for name, fn in (("c2", c2_gmres), ("c3", c3_eigs), ("c4", c4_sym), ("c5", c5_svds)):
+        if name in args.only.split(","):
+            try:
+                fn(ctx, args.full)
+            except Exception as e:                       # keep going: one JSON line per config either way
+                emit(config=name, error=repr(e))
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -222,10 +222,28 @@ int lkb_krylov_schur(lkb_basis_t X, void* H, int ldh, int kdim, int32_t* nkeep) 
     const int nk = *nkeep;
     // basis: X(:n) <- X(:kdim) Z(:, :n) ; X(n+1) <- X(kdim+1) ; X(n+2:) = 0
     if (nk > 0) {
+        // The update is row-local, so it is done in place one row chunk at a time through a bounded
+        // staging buffer (<= 1 GB) instead of a second n x nk basis (C3: 64 GB at n = 134M).
+        LKB_TRY(ensure_hstage(c, (size_t)k * nk * es + 4096));
+        LKB_TRY(ensure_coefd(c, std::max((size_t)k * nk * es, (size_t)4096)));
+        LKB_CUDA(cudaStreamSynchronize(c->stream));
+        for (int q = 0; q < nk; ++q) for (int i = 0; i < k; ++i) store_kind(kind, c->hstage, (size_t)i + (size_t)k * q, Zc[i + (size_t)k * q]);
+        LKB_CUDA(cudaMemcpyAsync(c->coefd, c->hstage, (size_t)k * nk * es, cudaMemcpyHostToDevice, c->stream));
+        int64_t chunk = (int64_t)(((size_t)1 << 30) / ((size_t)nk * es));
+        chunk = std::max<int64_t>(4096, (chunk / 4096) * 4096);
+        chunk = std::min<int64_t>(chunk, ((X->n + 4095) / 4096) * 4096);
         void* tmp = nullptr;
-        LKB_CUDA(cudaMalloc(&tmp, (size_t)X->ld * nk * es));
-        int r = device_combine(X, k, Zc, k, nk, tmp, X->ld);
-        if (r == 0 && cudaMemcpyAsync(X->d, tmp, (size_t)X->ld * nk * es, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess) r = LKB_ERR_CUDA;
+        LKB_CUDA(cudaMalloc(&tmp, (size_t)chunk * nk * es));
+        int r = 0;
+        for (int64_t r0 = 0; r0 < X->n && r == 0; r0 += chunk) {
+            const int64_t rows = std::min<int64_t>(chunk, X->n - r0);
+            prof_begin(c, PC_OTHER);
+            launch_basis_gemm(kind, c->stream, (char*)X->d + (size_t)r0 * es, X->ld, k, c->coefd, k, nk, tmp, chunk, rows, c->sms);
+            prof_end(c, PC_OTHER, 1);
+            r = check_launch(c, "basis_gemm");
+            if (r == 0 && cudaMemcpy2DAsync((char*)X->d + (size_t)r0 * es, (size_t)X->ld * es, tmp, (size_t)chunk * es,
+                                            (size_t)rows * es, nk, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess) r = LKB_ERR_CUDA;
+        }
         cudaStreamSynchronize(c->stream);
         cudaFree(tmp);
         if (r) return r;
