@@ -48,7 +48,7 @@ template <typename E> LKB_DI void warp_fold16(E (&acc)[16], int lane) {
     acc[0] = add_v(acc[0], shfl_xor_t<E>(acc[0], 1));
 }
 
-template <int K>
+template <int K, int PT>
 __global__ void __launch_bounds__(MD_THREADS, 2)
 k_multidot(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j,
            const typename Tr<K>::E* __restrict__ w, int64_t n,
@@ -59,7 +59,8 @@ k_multidot(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j,
     using W = typename Tr<K>::W;
     constexpr int EPP = Tr<K>::EPP;
     constexpr int CB = MD_CB;
-    constexpr int PT = 4;                       // packs of w held in registers per thread
+    // PT = packs of w held in registers per thread (tile = MD_THREADS*PT packs); smaller tiles are
+    // chosen for small n so that the tiles still spread evenly over the 2*SM CTAs
     constexpr int NW = MD_THREADS / 32;
     using P = Pack<E, EPP>;
     static_assert(CB == 16, "warp_fold16 assumes 16 columns per chunk");
@@ -283,16 +284,26 @@ template <int K>
 static void multidot_t(cudaStream_t s, const void* V, int64_t ld, int j, const void* w, int64_t n,
                        void* partial, void* out, unsigned* counter, const int* flags, int sms, const P2P* p2p) {
     using E = typename Tr<K>::E; using W = typename Tr<K>::W;
-    // grid: fixed function of the problem size (2 resident CTAs per SM), never of timing
-    const int64_t ntiles = (n / Tr<K>::EPP + (int64_t)MD_THREADS * 4 - 1) / ((int64_t)MD_THREADS * 4);
+    // grid: fixed function of the problem size (2 resident CTAs per SM), never of timing.  Tile size:
+    // the largest of 4/2/1 packs per thread that still leaves >= 12 tiles per CTA, so the ceil() in the
+    // tile split costs < 8 % (at 1/8 of C2 per GPU, 4-pack tiles gave 3.46 tiles per CTA = 86 % balance).
+    const int64_t npk = n / Tr<K>::EPP;
     int64_t nb = 2 * (int64_t)sms;
+    int pt = 4;
+    while (pt > 1 && (npk + (int64_t)MD_THREADS * pt - 1) / ((int64_t)MD_THREADS * pt) < 12 * nb) pt >>= 1;
+    const int64_t ntiles = (npk + (int64_t)MD_THREADS * pt - 1) / ((int64_t)MD_THREADS * pt);
     if (nb > ntiles) nb = ntiles;
     if (nb < 1) nb = 1;
     if (nb > MAX_ROWBLOCKS) nb = MAX_ROWBLOCKS;
     const size_t sh = (size_t)(MD_THREADS / 32) * (size_t)(j + 1) * sizeof(W);
-    static const bool attr_once = (cudaFuncSetAttribute(k_multidot<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024), true);
+    static const bool attr_once = (cudaFuncSetAttribute(k_multidot<K, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024),
+                                   cudaFuncSetAttribute(k_multidot<K, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024),
+                                   cudaFuncSetAttribute(k_multidot<K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024), true);
     (void)attr_once;
-    k_multidot<K><<<(int)nb, MD_THREADS, sh, s>>>((const E*)V, ld, j, (const E*)w, n, (W*)partial, (W*)out, counter, flags, p2p ? *p2p : P2P());
+    const P2P pp = p2p ? *p2p : P2P();
+    if (pt == 4) k_multidot<K, 4><<<(int)nb, MD_THREADS, sh, s>>>((const E*)V, ld, j, (const E*)w, n, (W*)partial, (W*)out, counter, flags, pp);
+    else if (pt == 2) k_multidot<K, 2><<<(int)nb, MD_THREADS, sh, s>>>((const E*)V, ld, j, (const E*)w, n, (W*)partial, (W*)out, counter, flags, pp);
+    else k_multidot<K, 1><<<(int)nb, MD_THREADS, sh, s>>>((const E*)V, ld, j, (const E*)w, n, (W*)partial, (W*)out, counter, flags, pp);
 }
 void launch_multidot(int kind, cudaStream_t s, const void* V, int64_t ld, int j, const void* w, int64_t n,
                      void* partial, void* out, unsigned* counter, const int* flags, int sms, const P2P* p2p) {
