@@ -152,9 +152,16 @@ typedef struct {            /* gmres_dp_opts / gmres_dp_metadata : IterativeSolv
     double* res; int32_t res_cap, res_len;               /* optional residual history (caller-owned) */
 } lkb_gmres_io;
 /* gmres(A, b, x, info, rtol, atol, preconditioner, options, transpose, meta)  gmres.fypp:65-255
- * rtol/atol < 0 = absent.  No preconditioner hook in this round. */
+ * rtol/atol < 0 = absent.  lkb_gmres_precond adds the optional right preconditioner. */
 int lkb_gmres(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, double rtol, double atol,
               int32_t transpose, lkb_gmres_io* io);
+/* abstract_precond_*: `apply(vec, iter, current_residual, target_residual)` (IterativeSolvers.fypp:73-107).
+ * The callback transforms vec_dev in place with work launched on `stream`; iter / residuals are -1 when the
+ * reference passes them as absent (`preconditioner%apply(dx)`, `preconditioner%apply(z)`). */
+typedef int (*lkb_precond_fn)(void* user, void* vec_dev, int64_t n_local, int32_t iter, double current_residual,
+                              double target_residual, void* stream);
+int lkb_gmres_precond(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, double rtol, double atol,
+                      int32_t transpose, lkb_gmres_io* io, lkb_precond_fn precond, void* user);
 typedef struct {            /* cg_dp_opts / cg_dp_metadata : IterativeSolvers.fypp:467-507 */
     int32_t maxiter;        /* default 100 */
     int32_t n_iter, converged, info;
@@ -162,6 +169,8 @@ typedef struct {            /* cg_dp_opts / cg_dp_metadata : IterativeSolvers.fy
 } lkb_cg_io;
 /* cg(A, b, x, info, rtol, atol, preconditioner, options, meta)  CG/CG.fypp:61-196 */
 int lkb_cg(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, double rtol, double atol, lkb_cg_io* io);
+int lkb_cg_precond(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, double rtol, double atol, lkb_cg_io* io,
+                   lkb_precond_fn precond, void* user);
 /* eigs(A, X, eigvals, residuals, info, x0, kdim, tolerance, transpose)  IterativeSolvers.fypp:972-1143
  *   X: nev columns (out); eigvals: nev complex (double[2] each); residuals: nev doubles.
  *   x0 may be NULL (random start); kdim <= 0 = 4*nev; tolerance < 0 = rtol_kind. */

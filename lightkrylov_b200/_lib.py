@@ -26,6 +26,7 @@ class CgIO(C.Structure):
 
 
 MATVEC_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p)
+PRECOND_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_void_p)
 
 _vp, _i, _i32, _i64, _u64, _d = C.c_void_p, C.c_int, C.c_int32, C.c_int64, C.c_uint64, C.c_double
 _P = C.POINTER
@@ -92,6 +93,8 @@ SIGNATURES = {
     "lkb_krylov_schur": (_i, [_vp, _vp, _i, _i, _P(_i32)]),
     "lkb_gmres": (_i, [_vp, _vp, _vp, _P(_i32), _d, _d, _i32, _P(GmresIO)]),
     "lkb_cg": (_i, [_vp, _vp, _vp, _P(_i32), _d, _d, _P(CgIO)]),
+    "lkb_gmres_precond": (_i, [_vp, _vp, _vp, _P(_i32), _d, _d, _i32, _P(GmresIO), PRECOND_FN, _vp]),
+    "lkb_cg_precond": (_i, [_vp, _vp, _vp, _P(_i32), _d, _d, _P(CgIO), PRECOND_FN, _vp]),
     "lkb_eigs": (_i, [_vp, _vp, _i, _P(_d), _P(_d), _P(_i32), _vp, _i32, _d, _i32]),
     "lkb_eighs": (_i, [_vp, _vp, _i, _P(_d), _P(_d), _P(_i32), _vp, _i32, _d]),
     "lkb_svds": (_i, [_vp, _vp, _P(_d), _vp, _i, _P(_d), _P(_i32), _vp, _i32, _d]),

@@ -406,24 +406,39 @@ def qr(Q: Basis, col0: int = 0, p: Optional[int] = None, tol: float = -1.0):
     return info.value, R
 
 
+def _wrap_precond(preconditioner):
+    """preconditioner(vec_ptr, n_local, iter, current_residual, target_residual, stream) -> None/int"""
+    return _lib.PRECOND_FN(lambda user, v, n, it, cur, tgt, stream: int(preconditioner(v, n, it, cur, tgt, stream) or 0))
+
+
 def gmres(A: LinOp, b: Vector, x: Vector, rtol: float = -1.0, atol: float = -1.0, kdim: int = 30,
-          maxiter: int = 10, transpose: bool = False):
+          maxiter: int = 10, transpose: bool = False, preconditioner=None):
     cap = (kdim + 2) * (maxiter + 2) + 8
     res = (C.c_double * cap)()
     io = _lib.GmresIO(kdim=kdim, maxiter=maxiter, res=res, res_cap=cap)
     info = C.c_int32()
-    check(A.ctx.lib.lkb_gmres(A.h, b.h, x.h, C.byref(info), rtol, atol, int(transpose), C.byref(io)), "gmres")
+    if preconditioner is None:
+        check(A.ctx.lib.lkb_gmres(A.h, b.h, x.h, C.byref(info), rtol, atol, int(transpose), C.byref(io)), "gmres")
+    else:
+        cb = _wrap_precond(preconditioner)
+        check(A.ctx.lib.lkb_gmres_precond(A.h, b.h, x.h, C.byref(info), rtol, atol, int(transpose), C.byref(io),
+                                          cb, None), "gmres")
     meta = dict(n_iter=io.n_iter, n_inner=io.n_inner, n_outer=io.n_outer, converged=bool(io.converged),
                 info=io.info, res=[res[i] for i in range(min(io.res_len, cap))])
     return info.value, meta
 
 
-def cg(A: LinOp, b: Vector, x: Vector, rtol: float = -1.0, atol: float = -1.0, maxiter: int = 100):
+def cg(A: LinOp, b: Vector, x: Vector, rtol: float = -1.0, atol: float = -1.0, maxiter: int = 100,
+       preconditioner=None):
     cap = maxiter + 8
     res = (C.c_double * cap)()
     io = _lib.CgIO(maxiter=maxiter, res=res, res_cap=cap)
     info = C.c_int32()
-    check(A.ctx.lib.lkb_cg(A.h, b.h, x.h, C.byref(info), rtol, atol, C.byref(io)), "cg")
+    if preconditioner is None:
+        check(A.ctx.lib.lkb_cg(A.h, b.h, x.h, C.byref(info), rtol, atol, C.byref(io)), "cg")
+    else:
+        cb = _wrap_precond(preconditioner)
+        check(A.ctx.lib.lkb_cg_precond(A.h, b.h, x.h, C.byref(info), rtol, atol, C.byref(io), cb, None), "cg")
     meta = dict(n_iter=io.n_iter, converged=bool(io.converged), info=io.info,
                 res=[res[i] for i in range(min(io.res_len, cap))])
     return info.value, meta

@@ -32,9 +32,14 @@ template <typename E, int PW> struct PackOps {
         return r; }
 };
 
-// One CTA = 256 threads side by side along x (256*PW points of one grid row), marching RY rows
-// in y with the south/centre/north packs held in registers: every x element is loaded once per
-// CTA (+2 halo rows per RY rows, +2 scalars per pack that hit L1).  HBM traffic ~ 2*n*s.
+// One CTA = 256 threads side by side along x (256*PW points of one grid row), marching RY rows in y
+// (2.5-D blocking): the south / centre / north packs of a column live in registers, so every x
+// element is loaded from HBM once per CTA (+2 halo rows per RY rows, served by L2 because the
+// neighbouring CTA streams them at the same time).  The x-halo (west / east neighbour of a pack) is
+// staged through warp shuffles; only the two edge lanes of a warp issue an extra (L1-resident)
+// scalar load.  The march is unrolled by 4 with the four north loads issued up front, so each
+// thread keeps 4 x 16 B in flight.  Inter-GPU halos arrive in halo_lo / halo_hi (slab edges).
+// HBM traffic ~ (2 + 2/RY) * n * s.
 template <int K, int PW, int DIM>
 __global__ void __launch_bounds__(256)
 k_stencil(const typename Tr<K>::E* __restrict__ x, typename Tr<K>::E* __restrict__ y,
@@ -45,18 +50,19 @@ k_stencil(const typename Tr<K>::E* __restrict__ x, typename Tr<K>::E* __restrict
     using E = typename Tr<K>::E;
     using PO = PackOps<E, PW>;
     using P = typename PO::P;
-    constexpr int RY = 16;
+    constexpr int RY = 32, UN = 4;
     if (flags && flags[F_STOP]) return;
     const int64_t npk_row = nx / PW;
     const int64_t ip = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (ip >= npk_row) return;
-    const int64_t i0 = ip * PW;
+    const bool active = ip < npk_row;                 // inactive lanes still take part in the shuffles
+    const int64_t i0 = (active ? ip : npk_row - 1) * PW;
     const int64_t nyb = (ny + RY - 1) / RY;
     const int64_t k = (DIM == 3) ? (int64_t)blockIdx.y / nyb : 0;
     const int64_t j0 = ((int64_t)blockIdx.y % nyb) * RY;
     const int64_t j1 = min(ny, j0 + RY);
     const int64_t plane = nx * ny;
     const E* xk = x + k * plane;
+    const int lane = threadIdx.x & 31;
 
     auto getrow = [&](int64_t j) -> P {
         if (DIM == 2) {
@@ -67,12 +73,19 @@ k_stencil(const typename Tr<K>::E* __restrict__ x, typename Tr<K>::E* __restrict
         }
         return PO::ld(xk + j * nx + i0);
     };
-    P south = getrow(j0 - 1), center = getrow(j0);
-    for (int64_t j = j0; j < j1; ++j) {
-        const P north = getrow(j + 1);
+    auto shfl_e = [&](E v, int src) -> E {
+        if constexpr (sizeof(E) == 4) return __shfl_sync(0xffffffffu, v, src);
+        else if constexpr (sizeof(E) == 8 && !Tr<K>::cplx) return __shfl_sync(0xffffffffu, v, src);
+        else if constexpr (sizeof(E) == 8) { E r; r.x = __shfl_sync(0xffffffffu, v.x, src); r.y = __shfl_sync(0xffffffffu, v.y, src); return r; }
+        else { E r; r.x = __shfl_sync(0xffffffffu, v.x, src); r.y = __shfl_sync(0xffffffffu, v.y, src); return r; }
+    };
+    auto do_row = [&](int64_t j, const P& south, const P& center, const P& north) {
         const int64_t p = j * nx + i0;
-        const E west = i0 > 0 ? __ldg(xk + p - 1) : zero_v(E());
-        const E east = (i0 + PW < nx) ? __ldg(xk + p + PW) : zero_v(E());
+        // x-halo through warp shuffles; edge lanes of the warp (and of the row) load / zero-fill
+        E west = shfl_e(center.v[PW - 1], (lane + 31) & 31);
+        E east = shfl_e(center.v[0], (lane + 1) & 31);
+        if (lane == 0) west = i0 > 0 ? __ldg(xk + p - 1) : zero_v(E());
+        if (lane == 31 || ip + 1 >= npk_row) east = (i0 + PW < nx) ? __ldg(xk + p + PW) : zero_v(E());
         P down, up;
         if (DIM == 3) {
             down = (k > 0) ? PO::ld(xk + p - plane) : (halo_lo ? PO::ld(halo_lo + p) : PO::zero());
@@ -89,7 +102,24 @@ k_stencil(const typename Tr<K>::E* __restrict__ x, typename Tr<K>::E* __restrict
             if (DIM == 3) { fmacc(s, down.v[e], cf.c[5]); fmacc(s, up.v[e], cf.c[6]); }
             out.v[e] = s;
         }
-        PO::st(y + k * plane + p, out);
+        if (active) PO::st(y + k * plane + p, out);
+    };
+
+    P south = getrow(j0 - 1), center = getrow(j0);
+    int64_t j = j0;
+    for (; j + UN <= j1; j += UN) {
+        P nb[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) nb[u] = getrow(j + 1 + u);
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            do_row(j + u, south, center, nb[u]);
+            south = center; center = nb[u];
+        }
+    }
+    for (; j < j1; ++j) {
+        const P north = getrow(j + 1);
+        do_row(j, south, center, north);
         south = center; center = north;
     }
 }
@@ -107,7 +137,7 @@ static void stencil_launch(cudaStream_t s, const StencilArgs& a, const void* x, 
     }
     for (int q = 0; q < 7; ++q) from_scalar(c[q], cf.c[q]);
     const int64_t npk_row = a.nx / PW;
-    const int64_t nyb = (a.ny + 15) / 16;
+    const int64_t nyb = (a.ny + 31) / 32;
     dim3 grid((unsigned)((npk_row + 255) / 256), (unsigned)(nyb * (DIM == 3 ? a.nz : 1)));
     k_stencil<K, PW, DIM><<<grid, 256, 0, s>>>((const E*)x, (E*)y, a.nx, a.ny, a.nz, cf,
                                                (const E*)a.halo_lo, (const E*)a.halo_hi, flags);

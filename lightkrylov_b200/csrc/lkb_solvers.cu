@@ -68,8 +68,8 @@ void push_res(double* res, int32_t cap, int32_t* len, double v) {
 
 extern "C" {
 
-int lkb_gmres(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, double rtol, double atol, int32_t transpose,
-              lkb_gmres_io* io) {
+static int gmres_impl(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, double rtol, double atol, int32_t transpose,
+                      lkb_gmres_io* io, lkb_precond_fn precond, void* puser) {
     if (!A || !b || !x || !info) { set_error("gmres: null argument"); return LKB_ERR_ARG; }
     if (b->n != x->n || b->kind != A->kind || x->kind != A->kind || A->m != b->n || A->n != b->n)
         { set_error("gmres: size/kind mismatch"); return LKB_ERR_ARG; }
@@ -91,14 +91,20 @@ int lkb_gmres(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, double rtol, 
 
     lkb_basis_t V = nullptr;
     LKB_TRY(lkb_basis_create(c, kind, b->n, b->n_global, b->row0, kdim + 1, &V));
-    lkb_vec_t dx = nullptr;
+    lkb_vec_t dx = nullptr, wrk = nullptr;
     LKB_TRY(lkb_vec_create(c, kind, b->n, b->n_global, b->row0, &dx));
+    if (precond) LKB_TRY(lkb_vec_create(c, kind, b->n, b->n_global, b->row0, &wrk));
     std::vector<cd> H((size_t)(kdim + 1) * kdim), e(kdim + 1), cs(kdim), sn(kdim), y(kdim);
     std::vector<Scalar> col;
     const Scalar one{1, 0}, mone{-1, 0};
     int hf[F_COUNT];
     int rc = 0;
-    auto cleanup = [&](int r) { lkb_basis_destroy(V); lkb_vec_destroy(dx); return r; };
+    auto cleanup = [&](int r) { lkb_basis_destroy(V); lkb_vec_destroy(dx); if (wrk) lkb_vec_destroy(wrk); return r; };
+    auto apply_precond = [&](void* v, int iter, double cur, double target) -> int {
+        int r = precond(puser, v, b->n, iter, cur, target, (void*)c->stream);
+        if (r != 0) { set_error("preconditioner callback returned %d", r); return LKB_ERR_ARG; }
+        return 0;
+    };
 #define GM_TRY(call) do { rc = (call); if (rc) return cleanup(rc); } while (0)
 
     auto residual_into_v1 = [&](bool skip_if_zero) -> int {
@@ -129,7 +135,13 @@ int lkb_gmres(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, double rtol, 
         for (k = 1; k <= kdim; ++k) {
             void* w = col_ptr(V, k);
             if (trans) A->n_rmatvec++; else A->n_matvec++;
-            GM_TRY(op_apply_enqueue(A, col_ptr(V, k - 1), w, trans, nullptr));
+            const void* src = col_ptr(V, k - 1);
+            if (precond) {      // wrk = V(k) ; preconditioner%apply(wrk, k, beta, tol)   (gmres.fypp:155)
+                launch_axpby(kind, c->stream, one, col_ptr(V, k - 1), Scalar{0, 0}, wrk->d, b->n, c->sms); c->launches++;
+                GM_TRY(apply_precond(wrk->d, k, beta, tol));
+                src = wrk->d;
+            }
+            GM_TRY(op_apply_enqueue(A, src, w, trans, nullptr));
             GM_TRY(cudaMemsetAsync(c->flags, 0, F_COUNT * sizeof(int), c->stream) == cudaSuccess ? 0 : LKB_ERR_CUDA);
             GM_TRY(dgs_enqueue(c, kind, V->d, V->ld, k, w, b->n, c->flags, true, false));
             // H(:k, k) = c1 + c2 ; H(k+1, k) = ||V(k+1)||
@@ -171,6 +183,7 @@ int lkb_gmres(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, double rtol, 
             std::vector<char> yk((size_t)k * kind_size(kind));
             for (int i = 0; i < k; ++i) store_kind(kind, y[i], &yk[(size_t)i * kind_size(kind)]);
             GM_TRY(lkb_basis_lincomb(V, k, yk.data(), dx));
+            if (precond) GM_TRY(apply_precond(dx->d, -1, -1.0, -1.0));          // preconditioner%apply(dx)  (:202)
             launch_axpby(kind, c->stream, one, dx->d, one, x->d, x->n, c->sms); c->launches++;
         }
         GM_TRY(residual_into_v1(false));
@@ -187,7 +200,17 @@ int lkb_gmres(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, double rtol, 
     return cleanup(0);
 }
 
-int lkb_cg(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, double rtol, double atol, lkb_cg_io* io) {
+int lkb_gmres(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, double rtol, double atol, int32_t transpose,
+              lkb_gmres_io* io) {
+    return gmres_impl(A, b, x, info, rtol, atol, transpose, io, nullptr, nullptr);
+}
+int lkb_gmres_precond(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, double rtol, double atol, int32_t transpose,
+                      lkb_gmres_io* io, lkb_precond_fn precond, void* user) {
+    return gmres_impl(A, b, x, info, rtol, atol, transpose, io, precond, user);
+}
+
+static int cg_impl(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, double rtol, double atol, lkb_cg_io* io,
+                   lkb_precond_fn precond, void* puser) {
     if (!A || !b || !x || !info) { set_error("cg: null argument"); return LKB_ERR_ARG; }
     if (b->n != x->n || b->kind != A->kind || x->kind != A->kind || A->m != b->n || A->n != b->n)
         { set_error("cg: size/kind mismatch"); return LKB_ERR_ARG; }
@@ -202,21 +225,35 @@ int lkb_cg(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, double rtol, dou
     double bnorm = 0;
     LKB_TRY(vec_norm_sync(c, kind, b->d, b->n, &bnorm));
     const double tol = atol + rtol * bnorm;
-    lkb_vec_t r = nullptr, p = nullptr, Ap = nullptr;
+    lkb_vec_t r = nullptr, p = nullptr, Ap = nullptr, z = nullptr;
     LKB_TRY(lkb_vec_create(c, kind, b->n, b->n_global, b->row0, &r));
     LKB_TRY(lkb_vec_create(c, kind, b->n, b->n_global, b->row0, &p));
     LKB_TRY(lkb_vec_create(c, kind, b->n, b->n_global, b->row0, &Ap));
+    if (precond) LKB_TRY(lkb_vec_create(c, kind, b->n, b->n_global, b->row0, &z));
     int rc = 0;
-    auto cleanup = [&](int rr) { lkb_vec_destroy(r); lkb_vec_destroy(p); lkb_vec_destroy(Ap); return rr; };
+    auto cleanup = [&](int rr) { lkb_vec_destroy(r); lkb_vec_destroy(p); lkb_vec_destroy(Ap); if (z) lkb_vec_destroy(z); return rr; };
+    // z = r ; preconditioner%apply(z)   (CG.fypp:113-114, 137)
+    auto make_z = [&]() -> int {
+        launch_axpby(kind, c->stream, Scalar{1, 0}, r->d, Scalar{0, 0}, z->d, b->n, c->sms); c->launches++;
+        int pr = precond(puser, z->d, b->n, -1, -1.0, -1.0, (void*)c->stream);
+        if (pr != 0) { set_error("preconditioner callback returned %d", pr); return LKB_ERR_ARG; }
+        return 0;
+    };
 #define CG_TRY(call) do { rc = (call); if (rc) return cleanup(rc); } while (0)
     const Scalar one{1, 0}, mone{-1, 0}, zero{0, 0};
     double xn = 0;
     CG_TRY(vec_norm_sync(c, kind, x->d, x->n, &xn));
     if (xn > 0) { A->n_matvec++; CG_TRY(op_apply_enqueue(A, x->d, r->d, false, nullptr)); }
     launch_axpby(kind, c->stream, one, b->d, mone, r->d, b->n, c->sms); c->launches++;      // r = b - A x
-    launch_axpby(kind, c->stream, one, r->d, zero, p->d, b->n, c->sms); c->launches++;      // p = r
     Scalar rr_old;
-    CG_TRY(vec_dot_sync(c, kind, r->d, r->d, b->n, &rr_old));
+    if (precond) {
+        CG_TRY(make_z());
+        launch_axpby(kind, c->stream, one, z->d, zero, p->d, b->n, c->sms); c->launches++;  // p = z
+        CG_TRY(vec_dot_sync(c, kind, r->d, z->d, b->n, &rr_old));
+    } else {
+        launch_axpby(kind, c->stream, one, r->d, zero, p->d, b->n, c->sms); c->launches++;  // p = r
+        CG_TRY(vec_dot_sync(c, kind, r->d, r->d, b->n, &rr_old));
+    }
     push_res(io->res, io->res_cap, &io->res_len, sqrt(hypot(rr_old.re, rr_old.im)));
     for (int it = 1; it <= maxiter; ++it) {
         A->n_matvec++;
@@ -228,13 +265,14 @@ int lkb_cg(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, double rtol, dou
         launch_axpby(kind, c->stream, to_scalar(-alpha), Ap->d, one, r->d, b->n, c->sms);    // r -= alpha Ap
         c->launches += 2;
         Scalar rr_new;
-        CG_TRY(vec_dot_sync(c, kind, r->d, r->d, b->n, &rr_new));
+        if (precond) { CG_TRY(make_z()); CG_TRY(vec_dot_sync(c, kind, r->d, z->d, b->n, &rr_new)); }
+        else CG_TRY(vec_dot_sync(c, kind, r->d, r->d, b->n, &rr_new));
         const double residual = sqrt(hypot(rr_new.re, rr_new.im));
         io->n_iter++;
         push_res(io->res, io->res_cap, &io->res_len, residual);
         if (residual < tol) { io->converged = 1; break; }
         const cd beta = round_kind(kind, cd(rr_new.re, rr_new.im) / cd(rr_old.re, rr_old.im));
-        launch_axpby(kind, c->stream, one, r->d, to_scalar(beta), p->d, b->n, c->sms);       // p = r + beta p
+        launch_axpby(kind, c->stream, one, precond ? z->d : r->d, to_scalar(beta), p->d, b->n, c->sms);  // p = z + beta p
         c->launches++;
         rr_old = rr_new;
     }
@@ -242,6 +280,14 @@ int lkb_cg(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, double rtol, dou
     *info = io->converged ? io->n_iter : -io->n_iter;
     io->info = *info;
     return cleanup(check_launch(c, "cg"));
+}
+
+int lkb_cg(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, double rtol, double atol, lkb_cg_io* io) {
+    return cg_impl(A, b, x, info, rtol, atol, io, nullptr, nullptr);
+}
+int lkb_cg_precond(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, double rtol, double atol, lkb_cg_io* io,
+                   lkb_precond_fn precond, void* user) {
+    return cg_impl(A, b, x, info, rtol, atol, io, precond, user);
 }
 
 }  // extern "C"

@@ -286,7 +286,7 @@ def apply_givens_rotation(h, c, s):
         h[k] = 0
 
 
-def gmres(A: Op, b: np.ndarray, x: np.ndarray, rtol=None, atol=None, kdim=30, maxiter=10, trans=False):
+def gmres(A: Op, b: np.ndarray, x: np.ndarray, rtol=None, atol=None, kdim=30, maxiter=10, trans=False, precond=None):
     """gmres.fypp:65-255 (no preconditioner).  Returns (info, meta dict); x updated in place."""
     import scipy.linalg as sla
     kind = kind_of(b.dtype)
@@ -310,7 +310,10 @@ def gmres(A: Op, b: np.ndarray, x: np.ndarray, rtol=None, atol=None, kdim=30, ma
             meta["res"].append(abs(beta))
         kk = kdim
         for k in range(1, kdim + 1):
-            V[:, k] = A.apply(V[:, k - 1].copy(), trans)
+            wrk = V[:, k - 1].copy()
+            if precond is not None:
+                precond(wrk)                                   # preconditioner%apply(wrk, k, beta, tol)
+            V[:, k] = A.apply(wrk, trans)
             _, hcol = dgs_vec(V[:, k], V, k)
             H[:k, k - 1] = hcol
             H[k, k - 1] = norm(V[:, k])
@@ -329,6 +332,8 @@ def gmres(A: Op, b: np.ndarray, x: np.ndarray, rtol=None, atol=None, kdim=30, ma
         k = kk
         y = sla.solve_triangular(H[:k, :k], e[:k], lower=False)
         dx = V[:, :k] @ y
+        if precond is not None:
+            precond(dx)
         x += dx
         V[:, 0] = A.apply(x, trans)
         axpby(-1, b, 1, V[:, 0]); V[:, 0] *= -1
@@ -342,7 +347,7 @@ def gmres(A: Op, b: np.ndarray, x: np.ndarray, rtol=None, atol=None, kdim=30, ma
     return info, meta
 
 
-def cg(A: Op, b: np.ndarray, x: np.ndarray, rtol=None, atol=None, maxiter=100):
+def cg(A: Op, b: np.ndarray, x: np.ndarray, rtol=None, atol=None, maxiter=100, precond=None):
     """CG.fypp:61-196 (no preconditioner)."""
     kind = kind_of(b.dtype)
     rtol = RTOL[kind] if rtol is None else rtol
@@ -352,22 +357,28 @@ def cg(A: Op, b: np.ndarray, x: np.ndarray, rtol=None, atol=None, maxiter=100):
     if norm(x) > 0:
         r = A.apply(x)
     axpby(-1, b, 1, r); r *= -1
-    p = r.copy()
-    rr_old = dot(r, r)
+    if precond is not None:
+        z = r.copy(); precond(z); p = z.copy(); rr_old = dot(r, z)
+    else:
+        p = r.copy()
+        rr_old = dot(r, r)
     meta = dict(n_iter=0, res=[float(np.sqrt(abs(rr_old)))], converged=False)
     for _ in range(maxiter):
         Ap = A.apply(p)
         alpha = rr_old / dot(p, Ap)
         axpby(alpha, p, 1, x)
         axpby(-alpha, Ap, 1, r)
-        rr_new = dot(r, r)
+        if precond is not None:
+            z = r.copy(); precond(z); rr_new = dot(r, z)
+        else:
+            rr_new = dot(r, r)
         residual = float(np.sqrt(abs(rr_new)))
         meta["n_iter"] += 1; meta["res"].append(residual)
         if residual < tol:
             meta["converged"] = True
             break
         beta = rr_new / rr_old
-        axpby(1, r, beta, p)
+        axpby(1, z if precond is not None else r, beta, p)
         rr_old = rr_new
     info = meta["n_iter"] if meta["converged"] else -meta["n_iter"]
     return info, meta

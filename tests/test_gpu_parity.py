@@ -468,3 +468,50 @@ def test_fused_cgs2_matches_unfused(lk, ctx, oracle, kind, n, j):
     X = lk.Basis(ctx, kind, n, j + 1).put(Xh); X.put(wh, col0=j)
     info, beta2 = lk.double_gram_schmidt_step(X, j, 1, X, j, if_chk_orthonormal=False)
     assert np.array_equal(beta2, out[1][1]) and np.array_equal(X.get(j, 1)[:, 0], out[1][2])
+
+
+# ---------------------------------------------------------------------------------------------
+# preconditioned gmres / cg (the `preconditioner` optional argument of the reference signatures;
+# PCG as in test/TestSpecialMatrices.f90:122-157, here with a diagonal preconditioner)
+# ---------------------------------------------------------------------------------------------
+class _DevArray:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}
+
+
+def test_preconditioned_cg_and_gmres_vs_oracle(lk, ctx, oracle):
+    import torch
+    dims = (20, 16, 12); n = int(np.prod(dims))
+    dh = 0.2 + oracle.fill(n, "d", "uniform", 99)            # SPD diagonal preconditioner M^-1 = diag(dh)
+    dd = torch.from_numpy(dh).cuda()
+    ext = torch.cuda.ExternalStream(ctx.stream)
+    calls = []
+
+    def precond_dev(ptr, nloc, it, cur, tgt, stream):
+        calls.append(it)
+        with torch.cuda.stream(ext):
+            v = torch.as_tensor(_DevArray(ptr, nloc, "<f8"), device="cuda")
+            v.mul_(dd)
+        return 0
+
+    def precond_host(v):
+        v *= dh
+
+    bh = oracle.fill(n, "d", "uniform", 45)
+    A = lk.LinOp.stencil7(ctx, "d", *dims, LAPLACE7); Ao = oracle.Op.stencil("d", dims, LAPLACE7)
+    b = lk.Vector(ctx, "d", n).put(bh); x = lk.Vector(ctx, "d", n)
+    info, meta = lk.cg(A, b, x, maxiter=2000, preconditioner=precond_dev)
+    xo = np.zeros(n); oinfo, ometa = oracle.cg(Ao, bh, xo, maxiter=2000, precond=precond_host)
+    assert info == oinfo > 0
+    np.testing.assert_allclose(meta["res"], ometa["res"], rtol=1e-6)
+    assert np.linalg.norm(x.get() - xo) < 1e-8 * np.linalg.norm(xo)
+    assert len(calls) == info + 1 and all(c == -1 for c in calls)
+    calls.clear()
+    A2 = lk.LinOp.stencil7(ctx, "d", *dims, CONVDIFF7); A2o = oracle.Op.stencil("d", dims, CONVDIFF7)
+    x2 = lk.Vector(ctx, "d", n)
+    ginfo, gmeta = lk.gmres(A2, b, x2, kdim=20, maxiter=30, preconditioner=precond_dev)
+    xo2 = np.zeros(n); oinfo2, ometa2 = oracle.gmres(A2o, bh, xo2, kdim=20, maxiter=30, precond=precond_host)
+    assert ginfo == oinfo2 > 0 and gmeta["n_outer"] == ometa2["n_outer"]
+    np.testing.assert_allclose(gmeta["res"], ometa2["res"], rtol=1e-5, atol=1e-13)
+    assert np.linalg.norm(x2.get() - xo2) < 1e-7 * np.linalg.norm(xo2)
+    assert calls[0] == 1 and -1 in calls                     # (wrk, k, beta, tol) form and the plain apply(dx) form
