@@ -4,6 +4,7 @@
 // intent(out)).  Stencil index convention: p = i + nx*(j + ny*k); coef = (center,-x,+x,-y,+y,-z,+z),
 // homogeneous Dirichlet outside the global grid.  The slowest axis (y in 2-D, z in 3-D) is the
 // row-sharded one: the neighbouring slab's boundary row / plane arrives in halo_lo / halo_hi.
+#include <stdlib.h>
 #include "lkb_kernels.h"
 
 namespace lkb {
@@ -35,12 +36,11 @@ template <typename E, int PW> struct PackOps {
 // One CTA = 256 threads side by side along x (256*PW points of one grid row), marching RY rows in y
 // (2.5-D blocking): the south / centre / north packs of a column live in registers, so every x
 // element is loaded from HBM once per CTA (+2 halo rows per RY rows, served by L2 because the
-// neighbouring CTA streams them at the same time).  The x-halo (west / east neighbour of a pack) is
-// staged through warp shuffles; only the two edge lanes of a warp issue an extra (L1-resident)
-// scalar load.  The march is unrolled by 4 with the four north loads issued up front, so each
-// thread keeps 4 x 16 B in flight.  Inter-GPU halos arrive in halo_lo / halo_hi (slab edges).
-// HBM traffic ~ (2 + 2/RY) * n * s.
-template <int K, int PW, int DIM>
+// neighbouring CTA streams them at the same time).  The x-halo (west / east neighbour of a pack)
+// comes from L1 (the neighbouring thread loaded that line) or, with SHFL, through warp shuffles.
+// UN > 1 prefetches UN north rows up front.  Inter-GPU halos arrive in halo_lo / halo_hi (slab
+// edges, filled by ncclSend/Recv).  HBM traffic ~ (2 + 2/RY) * n * s.
+template <int K, int PW, int DIM, int RY, int UN, bool SHFL>
 __global__ void __launch_bounds__(256)
 k_stencil(const typename Tr<K>::E* __restrict__ x, typename Tr<K>::E* __restrict__ y,
           int64_t nx, int64_t ny, int64_t nz, Coef7<typename Tr<K>::E> cf,
@@ -50,15 +50,14 @@ k_stencil(const typename Tr<K>::E* __restrict__ x, typename Tr<K>::E* __restrict
     using E = typename Tr<K>::E;
     using PO = PackOps<E, PW>;
     using P = typename PO::P;
-    constexpr int RY = 32, UN = 4;
     if (flags && flags[F_STOP]) return;
     const int64_t npk_row = nx / PW;
-    const int64_t ip = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t ip = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
     const bool active = ip < npk_row;                 // inactive lanes still take part in the shuffles
     const int64_t i0 = (active ? ip : npk_row - 1) * PW;
     const int64_t nyb = (ny + RY - 1) / RY;
-    const int64_t k = (DIM == 3) ? (int64_t)blockIdx.y / nyb : 0;
-    const int64_t j0 = ((int64_t)blockIdx.y % nyb) * RY;
+    const int64_t k = (DIM == 3) ? (int64_t)blockIdx.x / nyb : 0;
+    const int64_t j0 = ((int64_t)blockIdx.x % nyb) * RY;
     const int64_t j1 = min(ny, j0 + RY);
     const int64_t plane = nx * ny;
     const E* xk = x + k * plane;
@@ -82,10 +81,16 @@ k_stencil(const typename Tr<K>::E* __restrict__ x, typename Tr<K>::E* __restrict
     auto do_row = [&](int64_t j, const P& south, const P& center, const P& north) {
         const int64_t p = j * nx + i0;
         // x-halo through warp shuffles; edge lanes of the warp (and of the row) load / zero-fill
-        E west = shfl_e(center.v[PW - 1], (lane + 31) & 31);
-        E east = shfl_e(center.v[0], (lane + 1) & 31);
-        if (lane == 0) west = i0 > 0 ? __ldg(xk + p - 1) : zero_v(E());
-        if (lane == 31 || ip + 1 >= npk_row) east = (i0 + PW < nx) ? __ldg(xk + p + PW) : zero_v(E());
+        E west, east;
+        if (SHFL) {
+            west = shfl_e(center.v[PW - 1], (lane + 31) & 31);
+            east = shfl_e(center.v[0], (lane + 1) & 31);
+            if (lane == 0) west = i0 > 0 ? __ldg(xk + p - 1) : zero_v(E());
+            if (lane == 31 || ip + 1 >= npk_row) east = (i0 + PW < nx) ? __ldg(xk + p + PW) : zero_v(E());
+        } else {
+            west = i0 > 0 ? __ldg(xk + p - 1) : zero_v(E());
+            east = (i0 + PW < nx) ? __ldg(xk + p + PW) : zero_v(E());
+        }
         P down, up;
         if (DIM == 3) {
             down = (k > 0) ? PO::ld(xk + p - plane) : (halo_lo ? PO::ld(halo_lo + p) : PO::zero());
@@ -137,10 +142,14 @@ static void stencil_launch(cudaStream_t s, const StencilArgs& a, const void* x, 
     }
     for (int q = 0; q < 7; ++q) from_scalar(c[q], cf.c[q]);
     const int64_t npk_row = a.nx / PW;
-    const int64_t nyb = (a.ny + 31) / 32;
-    dim3 grid((unsigned)((npk_row + 255) / 256), (unsigned)(nyb * (DIM == 3 ? a.nz : 1)));
-    k_stencil<K, PW, DIM><<<grid, 256, 0, s>>>((const E*)x, (E*)y, a.nx, a.ny, a.nz, cf,
-                                               (const E*)a.halo_lo, (const E*)a.halo_hi, flags);
+    // RY = 8 rows per CTA, no unrolling, L1-served x-halo: chosen by measurement (profiles/stencil_ab.py,
+    // B200): 5.2 TB/s (2-D 4096^2) / 4.6 TB/s (3-D 384^3); longer marches or 4x-unrolled prefetch were
+    // slower (fewer CTAs in flight), warp-shuffle x-halo made no difference.
+    constexpr int RY = 8;
+    const int64_t nyb = (a.ny + RY - 1) / RY;
+    dim3 grid((unsigned)(nyb * (DIM == 3 ? a.nz : 1)), (unsigned)((npk_row + 255) / 256));
+    k_stencil<K, PW, DIM, RY, 1, false><<<grid, 256, 0, s>>>((const E*)x, (E*)y, a.nx, a.ny, a.nz, cf,
+                                                             (const E*)a.halo_lo, (const E*)a.halo_hi, flags);
 }
 
 template <int K>

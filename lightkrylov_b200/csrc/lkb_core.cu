@@ -465,8 +465,8 @@ static int stencil_create(lkb_ctx_t c, int kind, int dim, int64_t nx, int64_t ny
         if (slow0 > 0) op->st.halo_lo = op->halo_lo;
         if (slow0 + nslow_local < nslow) op->st.halo_hi = op->halo_hi;
     }
-    const int64_t gy = ((op->st.ny + 31) / 32) * op->st.nz;
-    if (gy > 65535) { delete op; set_error("stencil: grid too large for this kernel (%lld row groups)", (long long)gy); return LKB_ERR_ARG; }
+    const int64_t gy = op->st.ny * op->st.nz;
+    if (gy > 2147483647LL) { delete op; set_error("stencil: grid too large for this kernel (%lld row groups)", (long long)gy); return LKB_ERR_ARG; }
     *A = op;
     return 0;
 }
