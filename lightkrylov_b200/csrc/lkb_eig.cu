@@ -284,10 +284,39 @@ int lkb_eigs(lkb_op_t A, lkb_basis_t X, int nev, double* eigvals, double* residu
     auto load_Hc = [&](int kk) {
         for (int j = 0; j < kk; ++j) for (int i = 0; i < kk; ++i) Hc[i + (size_t)kd * j] = load_kind(kind, H.data(), (size_t)i + (size_t)ldh * j);
     };
+    // Host/device overlap: the per-step geev of the reference
+    // (IterativeSolvers.fypp:1062-1066) costs up to ~14 ms at k = 128, longer than a device step at C2
+    // size.  Step k+1 is therefore enqueued speculatively BEFORE the host decomposes H_k; Xwrk and H
+    // are internal work arrays and the post-processing only reads their first k columns, so a
+    // speculative step that turns out to be unnecessary (convergence at k) is simply discarded.
+    const bool tr = transpose != 0;
+    const double atolk = atol_of(kind);
+    void* slots[2] = {nullptr, nullptr};
+    cudaEvent_t evs[2] = {nullptr, nullptr};
+    const size_t slot_bytes = (size_t)ldh * es + 256;
+    auto free_slots = [&]() { for (int q = 0; q < 2; ++q) { if (slots[q]) cudaFreeHost(slots[q]); if (evs[q]) cudaEventDestroy(evs[q]); } };
+    for (int q = 0; q < 2; ++q) {
+        if (cudaMallocHost(&slots[q], slot_bytes) != cudaSuccess || cudaEventCreateWithFlags(&evs[q], cudaEventDisableTiming) != cudaSuccess) {
+            free_slots(); set_error("eigs: pinned staging allocation failed"); return cleanup(LKB_ERR_ALLOC);
+        }
+    }
+#undef EG_TRY
+#define EG_TRY(call) do { rc = (call); if (rc) { cudaStreamSynchronize(c->stream); free_slots(); return cleanup(rc); } } while (0)
+    auto enqueue_step = [&](int kk) -> int {
+        LKB_TRY(arnoldi_enqueue(A, Xw, kk, kk, atolk, tr));
+        LKB_TRY(arnoldi_fetch_async(Xw, kk, kk, slots[kk & 1]));
+        LKB_CUDA(cudaEventRecord(evs[kk & 1], c->stream));
+        return 0;
+    };
+    int restarts = 0;
     while (conv < nev) {
+        int inflight = 0;                              // highest step already enqueued
         for (k = kstart; k <= kd; ++k) {
             int32_t ainfo = 0;
-            EG_TRY(lkb_arnoldi(A, Xw, H.data(), ldh, &ainfo, k, k, -1.0, transpose, 1));
+            if (inflight < k) { EG_TRY(enqueue_step(k)); inflight = k; }
+            EG_TRY(cudaEventSynchronize(evs[k & 1]) == cudaSuccess ? 0 : LKB_ERR_CUDA);
+            EG_TRY(arnoldi_collect(A, Xw, H.data(), ldh, &ainfo, k, k, tr, slots[k & 1]));
+            if (ainfo == 0 && k < kd) { EG_TRY(enqueue_step(k + 1)); inflight = k + 1; }   // speculative
             load_Hc(k);
             EG_TRY(host_eig(cplx, k, Hc, kd, vals, vecs));
             const cd beta = load_kind(kind, H.data(), (size_t)k + (size_t)ldh * (k - 1));
@@ -302,7 +331,11 @@ int lkb_eigs(lkb_op_t A, lkb_basis_t X, int nev, double* eigvals, double* residu
             }
             niter++;
             conv = 0; for (int i = 0; i < k; ++i) conv += res[i] < tol;
-            if (conv >= nev) break;
+            if (conv >= nev) {
+                // a speculative step k+1 may still be running: it is discarded (never collected, so the
+                // operator's matvec counter does not include it); the sync below waits for it
+                break;
+            }
         }
         if (conv >= nev) break;
         // Krylov-Schur restart (IterativeSolvers.fypp:1096-1100); note the loop index is kd+1 here
@@ -310,7 +343,12 @@ int lkb_eigs(lkb_op_t A, lkb_basis_t X, int nev, double* eigvals, double* residu
         EG_TRY(lkb_krylov_schur(Xw, H.data(), ldh, kd, &nk));
         kstart = nk + 1;
         k = kd + 1;
+        if (++restarts > 2000) { set_error("eigs: no convergence after 2000 Krylov-Schur restarts"); EG_TRY(LKB_ERR_ARG); }
     }
+    EG_TRY(cudaStreamSynchronize(c->stream) == cudaSuccess ? 0 : LKB_ERR_CUDA);
+    free_slots();
+#undef EG_TRY
+#define EG_TRY(call) do { rc = (call); if (rc) return cleanup(rc); } while (0)
     // post-process (:1108-1132)
     k = std::min(k, kd);
     load_Hc(k);

@@ -363,11 +363,27 @@ int lkb_arnoldi(lkb_op_t A, lkb_basis_t X, void* H, int ldh, int32_t* info, int3
     *info = 0;
     if (p > 1) return arnoldi_block(A, X, H, ldh, info, kstart, kend, tol, transpose != 0, p);
 
+    const bool tr = transpose != 0;
+    LKB_TRY(ensure_hstage(c, (size_t)(kdim + 1) * (kend - kstart + 1) * es + 4096));
+    LKB_TRY(arnoldi_enqueue(A, X, kstart, kend, tol, tr));
+    LKB_TRY(arnoldi_fetch_async(X, kstart, kend, c->hstage));
+    LKB_CUDA(cudaStreamSynchronize(c->stream));
+    return arnoldi_collect(A, X, H, ldh, info, kstart, kend, tr, c->hstage);
+}
+
+}  // extern "C"
+
+namespace lkb {
+// The three phases of a p = 1 arnoldi call, exposed so that eigs can overlap the host geev of
+// step k with the device work of step k+1.
+int arnoldi_enqueue(lkb_op_s* A, lkb_basis_s* X, int kstart, int kend, double tol, bool tr) {
+    lkb_ctx_s* c = X->ctx;
+    const int kind = X->kind;
+    const size_t es = kind_size(kind);
+    const int kdim = X->ncols - 1;
     const int ldhd = kdim + 1;
     LKB_TRY(ensure_Hd(c, (size_t)ldhd * kdim * es));
     LKB_TRY(ensure_ws(c, kend + 1));
-    LKB_TRY(ensure_hstage(c, (size_t)ldhd * (kend - kstart + 1) * es + 4096));
-    const bool tr = transpose != 0;
     auto body = [&]() -> int {
         LKB_TRY(reset_flags(c));
         for (int k = kstart; k <= kend; ++k) {
@@ -383,14 +399,29 @@ int lkb_arnoldi(lkb_op_t A, lkb_basis_t X, void* H, int ldh, int32_t* info, int3
         }
         return 0;
     };
-    LKB_TRY(run_maybe_graph(c, op_capturable(A), make_key("arn", A, X, nullptr, kstart, kend, tol, tr), body));
-    // one sync: flags + the freshly written Hessenberg columns
+    return run_maybe_graph(c, op_capturable(A), make_key("arn", A, X, nullptr, kstart, kend, tol, tr), body);
+}
+// D2H of the freshly written Hessenberg columns + flags into `host` (pinned), no sync
+int arnoldi_fetch_async(lkb_basis_s* X, int kstart, int kend, void* host) {
+    lkb_ctx_s* c = X->ctx;
+    const size_t es = kind_size(X->kind);
+    const int ldhd = X->ncols;
     const int ncol = kend - kstart + 1;
-    char* hs = (char*)c->hstage;
+    char* hs = (char*)host;
     LKB_CUDA(cudaMemcpyAsync(hs, (char*)c->Hd + (size_t)ldhd * (kstart - 1) * es, (size_t)ldhd * ncol * es, cudaMemcpyDeviceToHost, c->stream));
-    int hf[F_COUNT];
     LKB_CUDA(cudaMemcpyAsync(hs + (size_t)ldhd * ncol * es, c->flags, F_COUNT * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    LKB_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+// after the stream reached the fetch: scatter the columns into the caller's H, set info, refill on breakdown
+int arnoldi_collect(lkb_op_s* A, lkb_basis_s* X, void* H, int ldh, int32_t* info, int kstart, int kend, bool tr,
+                    const void* host) {
+    lkb_ctx_s* c = X->ctx;
+    const int kind = X->kind;
+    const size_t es = kind_size(kind);
+    const int ldhd = X->ncols;
+    const int ncol = kend - kstart + 1;
+    const char* hs = (const char*)host;
+    int hf[F_COUNT];
     memcpy(hf, hs + (size_t)ldhd * ncol * es, sizeof(hf));
     if (hf[F_NAN]) { set_error("|beta| = NaN detected! Abort"); return LKB_ERR_NAN; }
     const int kdone = hf[F_STOP] ? hf[F_INFO] : kend;
@@ -398,6 +429,7 @@ int lkb_arnoldi(lkb_op_t A, lkb_basis_t X, void* H, int ldh, int32_t* info, int3
         for (int i = 0; i <= k; ++i)
             host_store(kind, H, (int64_t)i + (int64_t)ldh * (k - 1), hs, (int64_t)i + (int64_t)ldhd * (k - kstart));
     if (tr) A->n_rmatvec += kdone - kstart + 1; else A->n_matvec += kdone - kstart + 1;
+    *info = 0;
     if (hf[F_STOP]) {
         *info = hf[F_INFO];
         if (hf[F_REFILL]) {
@@ -414,6 +446,9 @@ int lkb_arnoldi(lkb_op_t A, lkb_basis_t X, void* H, int ldh, int32_t* info, int3
     }
     return 0;
 }
+}  // namespace lkb
+
+extern "C" {
 
 // Block Arnoldi (blksize > 1), host-driven: arnoldi.fypp:36-71 with the per-column passes of
 // DGS_basis_against_basis (columns of Y are independent within a pass) and qr_no_pivoting.
