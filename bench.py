@@ -295,8 +295,22 @@ def run_ours(args):
             kernels[name] = {"ms_total": ms, "launches": nl, "alg_bytes": algb[name], "GBps": gbs, "frac": gbs / peak}
         dom = max(("multidot", "multiaxpy", "fused_axpy_dot"), key=lambda k: kernels[k]["ms_total"])
         nl = max(kernels[dom]["launches"], 1)
+        traffic_ncu = None
+        try:   # DRAM bytes of ONE captured launch (j = 101) from the committed ncu capture, with its algorithmic bytes
+            import glob
+            tf = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))[-1]
+            t = json.load(open(tf)).get({"multidot": "multidot", "multiaxpy": "multiaxpy", "fused_axpy_dot": "axpy_dot"}[dom])
+            if t and world == 1 and (nx, ny) == (4096, 4096):
+                jcap = 101
+                alg = {"multidot": jcap + 1, "multiaxpy": jcap + 2, "fused_axpy_dot": jcap + 2}[dom] * nloc * 8
+                traffic_ncu = {"file": os.path.basename(tf), "j": jcap, "dram_bytes": t["dram_bytes_read"] + t["dram_bytes_write"],
+                               "alg_bytes": alg, "ratio": (t["dram_bytes_read"] + t["dram_bytes_write"]) / alg}
+        except Exception:
+            traffic_ncu = None
         roof = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
-                "frac": kernels[dom]["GBps"] / peak, "traffic": None,
+                "frac": kernels[dom]["GBps"] / peak,
+                "traffic": (traffic_ncu["ratio"] * algb[dom] / max(kernels[dom]["launches"], 1)) if traffic_ncu else None,
+                "traffic_ncu": traffic_ncu,
                 "alg_bytes_per_launch_avg": algb[dom] / nl, "avg_launch_ms": kernels[dom]["ms_total"] / nl,
                 "peak_source": peak_src,
                 "how": "separate profiled factorisation in the same process: CUDA events on the context stream around "

@@ -65,4 +65,20 @@ for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", f"prof_*_{tag}.ncu-
     if "Kernel Name" in hdr:
         out_md.append(f"\nkernel: `{rows[2][hdr.index('Kernel Name')]}`\n")
 open(os.path.join(ROOT, "profiles", f"{tag}_ncu_summary.md"), "w").write("\n".join(out_md) + "\n")
+# machine-readable DRAM traffic per captured launch (bench.py copies it into roofline.traffic_ncu)
+import json
+traffic = {}
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}
+for rep in sorted(glob.glob(os.path.join(ROOT, "profiles", f"{tag}_*_raw.csv"))):
+    kname = os.path.basename(rep)[len(tag) + 1:-len("_raw.csv")]
+    rows = list(csv.reader(open(rep)))
+    if len(rows) < 3:
+        continue
+    hdr, units, r = rows[0], rows[1], rows[2]
+    def val(m):
+        i = hdr.index(m); return float(r[i].replace(",", "")) * UNIT.get(units[i], 1.0)
+    traffic[kname] = {"dram_bytes_read": val("dram__bytes_read.sum"), "dram_bytes_write": val("dram__bytes_write.sum"),
+                      "duration_s": val("gpu__time_duration.sum"), "grid": r[hdr.index("launch__grid_size")],
+                      "capture": "ncu --set full --clock-control none, launch #100 of the class in bench.py (j = 101)"}
+json.dump(traffic, open(os.path.join(ROOT, "profiles", f"{tag}_traffic.json"), "w"), indent=1)
 print("\n".join(out_md))
