@@ -120,18 +120,24 @@ k_axpy_dot(const __grid_constant__ CUtensorMap tmap, int j, int tp, int nst, int
     }
     __syncthreads();
 
+    // Work split of the 8 consumer warps: chunk q = 16 columns, row slice = every rs-th group of 32 packs.
+    // With few columns (nchunk < 8) the warps share a chunk and split the tile's rows instead of idling.
+    const int msteps = tp / 32;
+    const int rs = min(msteps, FZ_NW / nchunk);
+    const bool worker = wv < nchunk * rs;
+    const int q = worker ? wv % nchunk : 0;
+    const int slice = worker ? wv / nchunk : 0;
     // this warp's 16 coefficients of pass 1 and its 16 accumulators of pass 2
     E c1r[FZ_CB], acc[FZ_CB];
 #pragma unroll
     for (int i = 0; i < FZ_CB; ++i) {
-        const int col = wv * FZ_CB + i;
+        const int col = q * FZ_CB + i;
         c1r[i] = zero_v(E());
         if (col < j) narrow(c1[col], c1r[i]);
         acc[i] = zero_v(E());
     }
     double wwacc = 0.0;
 
-    const int msteps = tp / 32;
     if (wv == FZ_NW) {
         // ---- producer warp: one elected lane streams tiles through the ring (one 2-D TMA box of
         // tp packs x jc columns plus one 1-D bulk copy of the w packs per tile) ----
@@ -161,19 +167,19 @@ k_axpy_dot(const __grid_constant__ CUtensorMap tmap, int j, int tp, int nst, int
         mbar_wait(smem_u32(&bars[s]), parity);
 
         // ---- phase A: partial row sums over this warp's 16 columns ----
-        if (wv < nchunk) {
-            for (int m = 0; m < msteps; ++m) {
+        if (worker) {
+            for (int m = slice; m < msteps; m += rs) {
                 const int r = m * 32 + lane;
                 P ra;
 #pragma unroll
                 for (int e = 0; e < EPP; ++e) ra.v[e] = zero_v(E());
 #pragma unroll
                 for (int i = 0; i < FZ_CB; ++i) {
-                    const P v = tile[(size_t)(wv * FZ_CB + i) * tp + r];
+                    const P v = tile[(size_t)(q * FZ_CB + i) * tp + r];
 #pragma unroll
                     for (int e = 0; e < EPP; ++e) fmacc(ra.v[e], v.v[e], c1r[i]);
                 }
-                part[(size_t)wv * tp + r] = ra;
+                part[(size_t)q * tp + r] = ra;
             }
         }
         consumer_sync();
@@ -185,8 +191,8 @@ k_axpy_dot(const __grid_constant__ CUtensorMap tmap, int j, int tp, int nst, int
             for (int e = 0; e < EPP; ++e) wp.v[e] = zero_v(E());
             if (inb) wp = wst[(size_t)s * tp + tid];
             P sum = part[tid];
-            for (int q = 1; q < nchunk; ++q) {
-                const P t = part[(size_t)q * tp + tid];
+            for (int qq = 1; qq < nchunk; ++qq) {
+                const P t = part[(size_t)qq * tp + tid];
 #pragma unroll
                 for (int e = 0; e < EPP; ++e) sum.v[e] = add_v(sum.v[e], t.v[e]);
             }
@@ -203,13 +209,13 @@ k_axpy_dot(const __grid_constant__ CUtensorMap tmap, int j, int tp, int nst, int
         consumer_sync();
 
         // ---- phase B: c2 partials, accumulators persist across tiles ----
-        if (wv < nchunk) {
-            for (int m = 0; m < msteps; ++m) {
+        if (worker) {
+            for (int m = slice; m < msteps; m += rs) {
                 const int r = m * 32 + lane;
                 const P wn = wnew[r];
 #pragma unroll
                 for (int i = 0; i < FZ_CB; ++i) {
-                    const P v = tile[(size_t)(wv * FZ_CB + i) * tp + r];
+                    const P v = tile[(size_t)(q * FZ_CB + i) * tp + r];
 #pragma unroll
                     for (int e = 0; e < EPP; ++e) fma_conj(acc[i], v.v[e], wn.v[e]);
                 }
@@ -220,18 +226,24 @@ k_axpy_dot(const __grid_constant__ CUtensorMap tmap, int j, int tp, int nst, int
         if (lane == 0) mbar_arrive(smem_u32(&ebars[s]));
     }
 
-    // ---- stage 1: one partial row per CTA (each column is owned by exactly one warp) ----
+    // ---- stage 1: one partial row per CTA; the rs row-slice warps of a chunk are summed in fixed order ----
     const int fold_idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-    if (wv < nchunk) {
+    __syncthreads();                                   // the ring is drained: reuse `part` as [rs][jc] W scratch
+    W* fold = reinterpret_cast<W*>(part);
+    if (worker) {
         warp_fold16_f<E>(acc, lane);
-        const int col = wv * FZ_CB + fold_idx;
-        if ((lane & 1) == 0 && col < j) partial[(int64_t)blockIdx.x * jp + col] = widen(acc[0]);
+        if ((lane & 1) == 0) fold[(size_t)slice * jc + q * FZ_CB + fold_idx] = widen(acc[0]);
     }
     {
         const double a = warp_sum(wwacc);
         if (lane == 0) sww[wv] = a;
     }
     __syncthreads();
+    for (int col = tid; col < j; col += FZ_THREADS) {
+        W a = fold[col];
+        for (int sl = 1; sl < rs; ++sl) wadd(a, fold[(size_t)sl * jc + col]);
+        partial[(int64_t)blockIdx.x * jp + col] = a;
+    }
     if (tid == 0) {
         double t = sww[0];
         for (int q = 1; q < FZ_NW; ++q) t += sww[q];     // the producer warp's slot is always zero
@@ -288,7 +300,9 @@ static bool axpy_dot_t(cudaStream_t s, const void* V, int64_t ld, int j, const v
     PFN_tmapEncodeTiled enc = get_encode();
     if (!enc) return false;
     const int jc = (j + FZ_CB - 1) & ~(FZ_CB - 1);
-    const int tp = jc > 64 ? 32 : 64;                              // stage = jc * tp * 16 B <= 64 KB
+    // rows per tile: stage = jc * tp * 16 B <= 64 KB; few columns -> taller tiles, so the per-tile
+    // synchronisation cost (~1500 clk) stays small against the tile's HBM time (TMA box rows <= 256 words)
+    const int tp = jc > 64 ? 32 : ((jc > 32 || K == KS) ? 64 : 128);
     const int eltsz = (K == KS) ? 4 : 8;                           // tensor described in 4- or 8-byte words
     const int elt_per_pack = 16 / eltsz;
     if ((int64_t)n * (int64_t)es / eltsz >= ((int64_t)1 << 31)) return false;
