@@ -30,7 +30,7 @@ NcclApi* nccl_api() {
     if (!h) { set_error("cannot dlopen libnccl (set LKB_NCCL_LIB): %s", dlerror()); return nullptr; }
 #define LKB_SYM(field, name) *(void**)(&g_nccl.field) = dlsym(h, name); if (!g_nccl.field) { set_error("missing %s", name); return nullptr; }
     LKB_SYM(GetUniqueId, "ncclGetUniqueId") LKB_SYM(CommInitRank, "ncclCommInitRank") LKB_SYM(CommDestroy, "ncclCommDestroy")
-    LKB_SYM(AllReduce, "ncclAllReduce") LKB_SYM(Send, "ncclSend") LKB_SYM(Recv, "ncclRecv")
+    LKB_SYM(AllReduce, "ncclAllReduce") LKB_SYM(Broadcast, "ncclBroadcast") LKB_SYM(Send, "ncclSend") LKB_SYM(Recv, "ncclRecv")
     LKB_SYM(GroupStart, "ncclGroupStart") LKB_SYM(GroupEnd, "ncclGroupEnd") LKB_SYM(GetErrorString, "ncclGetErrorString")
 #undef LKB_SYM
     g_nccl.handle = h;
@@ -111,6 +111,25 @@ int allreduce_w(lkb_ctx_s* c, void* buf, size_t ndoubles) {
 }
 static uint64_t g_uid = 0;
 uint64_t next_uid() { return ++g_uid; }
+// The k x k host algebra (geev / gees+trsen / syev / gesdd) runs redundantly on every rank; a threaded
+// LAPACK need not be bitwise reproducible across processes, and a rank that decides "converged" one
+// step earlier than its peers would deadlock the collectives.  Rank 0's results are broadcast.
+int bcast_host(lkb_ctx_s* c, void* host_buf, size_t bytes) {
+    if (c->world == 1 || bytes == 0) return 0;
+    NcclApi* api = nccl_api();
+    if (!api) return LKB_ERR_NCCL;
+    const size_t padded = (bytes + 15) & ~(size_t)15;
+    LKB_TRY(ensure_hstage(c, padded + 4096));
+    LKB_TRY(ensure_coefd(c, std::max(padded, (size_t)4096)));
+    LKB_CUDA(cudaStreamSynchronize(c->stream));
+    memcpy(c->hstage, host_buf, bytes);
+    LKB_CUDA(cudaMemcpyAsync(c->coefd, c->hstage, padded, cudaMemcpyHostToDevice, c->stream));
+    LKB_NCCL(api->Broadcast(c->coefd, c->coefd, padded, /*ncclInt8*/ 0, 0, c->comm, c->stream));
+    LKB_CUDA(cudaMemcpyAsync(c->hstage, c->coefd, padded, cudaMemcpyDeviceToHost, c->stream));
+    LKB_CUDA(cudaStreamSynchronize(c->stream));
+    memcpy(host_buf, c->hstage, bytes);
+    return 0;
+}
 uint64_t next_seed(lkb_ctx_s* c) { return c->seed + 0x9E3779B97F4A7C15ULL * (++c->seed_calls); }
 
 int fetch_flags(lkb_ctx_s* c, int* host_flags) {

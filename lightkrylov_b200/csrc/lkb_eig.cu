@@ -219,6 +219,13 @@ int lkb_krylov_schur(lkb_basis_t X, void* H, int ldh, int kdim, int32_t* nkeep) 
         if (info != 0) { set_error("TRSEN failed, info = %d", (int)info); return LKB_ERR_LAPACK; }
         for (size_t t = 0; t < T.size(); ++t) { Tc[t] = T[t]; Zc[t] = Z[t]; }
     }
+    {   // rank 0's Schur data is authoritative (see bcast_host)
+        LKB_TRY(bcast_host(c, Zc.data(), Zc.size() * sizeof(cd)));
+        LKB_TRY(bcast_host(c, Tc.data(), Tc.size() * sizeof(cd)));
+        int32_t nk0 = *nkeep;
+        LKB_TRY(bcast_host(c, &nk0, sizeof(nk0)));
+        *nkeep = nk0;
+    }
     const int nk = *nkeep;
     // basis: X(:n) <- X(:kdim) Z(:, :n) ; X(n+1) <- X(kdim+1) ; X(n+2:) = 0
     if (nk > 0) {
@@ -330,6 +337,7 @@ int lkb_eigs(lkb_op_t A, lkb_basis_t X, int nev, double* eigvals, double* residu
                 res[i] = std::abs(beta) * alpha;
             }
             niter++;
+            EG_TRY(bcast_host(c, res.data(), (size_t)k * sizeof(double)));
             conv = 0; for (int i = 0; i < k; ++i) conv += res[i] < tol;
             if (conv >= nev) {
                 // a speculative step k+1 may still be running: it is discarded (never collected, so the
@@ -353,6 +361,8 @@ int lkb_eigs(lkb_op_t A, lkb_basis_t X, int nev, double* eigvals, double* residu
     k = std::min(k, kd);
     load_Hc(k);
     EG_TRY(host_eig(cplx, k, Hc, kd, vals, vecs));
+    EG_TRY(bcast_host(c, vals.data(), vals.size() * sizeof(cd)));
+    EG_TRY(bcast_host(c, vecs.data(), vecs.size() * sizeof(cd)));
     std::vector<double> av(kd, 0.0);
     for (int i = 0; i < k; ++i) av[i] = std::abs(vals[i]);
     std::vector<int> idx = sort_index_reverse(av);
@@ -414,9 +424,12 @@ int lkb_eighs(lkb_op_t A, lkb_basis_t X, int nev, double* eigvals, double* resid
         const cd beta = load_kind(kind, T.data(), (size_t)k + (size_t)ldt * (k - 1));
         std::fill(res.begin(), res.end(), 0.0);
         for (int i = 0; i < k; ++i) res[i] = std::abs(beta * vecs[(k - 1) + (size_t)kd * i]);
+        EH_TRY(bcast_host(c, res.data(), (size_t)k * sizeof(double)));
         conv = 0; for (int i = 0; i < k; ++i) conv += res[i] < tol;
         if (conv >= nev) break;
     }
+    EH_TRY(bcast_host(c, ev.data(), ev.size() * sizeof(double)));
+    EH_TRY(bcast_host(c, vecs.data(), vecs.size() * sizeof(cd)));
     std::vector<int> idx = sort_index_reverse(ev);        // over all kdim_ entries, zero padding included (eighs.fypp:106-107)
     k = std::min(k, kd);
     std::vector<cd> Y((size_t)k * nev, cd(0));
@@ -486,9 +499,13 @@ int lkb_svds(lkb_op_t A, lkb_basis_t U, double* S, lkb_basis_t V, int nsv, doubl
         const cd beta = load_kind(kind, B.data(), (size_t)k + (size_t)ldb * (k - 1));
         std::fill(res.begin(), res.end(), 0.0);
         for (int i = 0; i < k; ++i) res[i] = std::abs(beta * vmat[(k - 1) + (size_t)kd * i]);
+        SV_TRY(bcast_host(c, res.data(), (size_t)k * sizeof(double)));
         conv = 0; for (int i = 0; i < k; ++i) conv += res[i] < tol;
         if (conv >= nsv) break;
     }
+    SV_TRY(bcast_host(c, sv.data(), sv.size() * sizeof(double)));
+    SV_TRY(bcast_host(c, umat.data(), umat.size() * sizeof(cd)));
+    SV_TRY(bcast_host(c, vmat.data(), vmat.size() * sizeof(cd)));
     for (int i = 0; i < nsv; ++i) { S[i] = sv[i]; residuals[i] = res[i]; }
     k = std::min(k, kd);
     *info = k;

@@ -20,6 +20,7 @@ struct NcclApi {
     int (*CommInitRank)(void**, int, /*ncclUniqueId by value*/ NcclId, int) = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
@@ -100,7 +101,9 @@ int ensure_ws(lkb_ctx_s* c, int jp);                 // grow partial / c1 / c2 f
 int ensure_hstage(lkb_ctx_s* c, size_t bytes);
 int ensure_Hd(lkb_ctx_s* c, size_t bytes);
 int ensure_coefd(lkb_ctx_s* c, size_t bytes);
-int allreduce_w(lkb_ctx_s* c, void* buf, size_t ndoubles);   // in-place sum over ranks (no-op when world == 1)
+int allreduce_w(lkb_ctx_s* c, void* buf, size_t ndoubles);
+// make rank 0's copy of a small HOST array authoritative on every rank (k x k host-LAPACK results)
+int bcast_host(lkb_ctx_s* c, void* host_buf, size_t bytes);   // in-place sum over ranks (no-op when world == 1)
 int check_launch(lkb_ctx_s* c, const char* what);
 void prof_begin(lkb_ctx_s* c, int cls);
 void prof_end(lkb_ctx_s* c, int cls, int nlaunch);

@@ -83,6 +83,23 @@ def main():
     x2 = lk.Vector(ctx, "d", A.n, n_global=n3, row0=A.row0)
     ginfo, gmeta = lk.gmres(A2, b, x2, kdim=20, maxiter=30)
     x2g = gather_rows(x2.get())
+    # ---- eigs (Krylov-Schur restarts) and eighs on the sharded operator: config-3 shaped ----
+    lk.set_lapack_from_scipy()
+    nev = 4
+    Xe = lk.Basis(ctx, "d", A.n, nev, n_global=n3, row0=A.row0)
+    x0e = lk.Vector(ctx, "d", A.n, n_global=n3, row0=A.row0).fill_random("uniform", 44)
+    ev, eres, einfo = lk.eigs(A2, Xe, nev, x0=x0e, kdim=24, tolerance=1e-8)
+    evs = [None] * world
+    dist.all_gather_object(evs, (ev, einfo))
+    assert all(np.array_equal(evs[0][0], e[0]) and evs[0][1] == e[1] for e in evs), "eigs must agree on all ranks"
+    Xh = lk.Basis(ctx, "d", A.n, nev, n_global=n3, row0=A.row0)
+    evh, hres, hinfo = lk.eighs(A, Xh, nev, x0=x0e, kdim=40, tolerance=1e-8)
+    if rank == 0:
+        evo, reso, Xo_, infoo = lo.eigs(lo.Op.stencil("d", dims, CONVDIFF7), n3, nev, lo.fill(n3, "d", "uniform", 44), kdim=24, tolerance=1e-8)
+        assert einfo == infoo, (einfo, infoo)
+        assert np.abs(ev[:, None] - evo[None, :]).min(axis=1).max() < 1e-10 * np.abs(evo).max()
+        evho, _, _, kho = lo.eighs(lo.Op.stencil("d", dims, L7), n3, nev, lo.fill(n3, "d", "uniform", 44), kdim=40, tolerance=1e-8)
+        assert hinfo == kho and np.abs(evh - evho).max() < 1e-10 * np.abs(evho).max()
     if rank == 0:
         Xo = np.zeros((n3, kd + 1), order="F"); Xo[:, 0] = lo.fill(n3, "d", "uniform", 45); lo.normalize(Xo[:, 0])
         To = np.zeros_like(T)
