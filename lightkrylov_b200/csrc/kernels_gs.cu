@@ -185,6 +185,71 @@ k_multidot(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j,
 }
 
 // ------------------------------------------------------------------------------------------
+// dot of two vectors (the `dot` TBP, CG's p^H Ap, Lanczos' 3-term coefficients): the j = 1 case of the
+// multi-dot contract -- out[0] = x^H y, out[1] = y^H y -- as a plain grid-stride kernel with 4 + 4
+// independent 128-bit loads in flight per thread (the chunked multi-dot keeps only 1 of its 16 column
+// slots busy for j = 1 and ran at 2.4 TB/s).  Same deterministic two-stage reduction + p2p allreduce.
+template <int K>
+__global__ void __launch_bounds__(256, 4)
+k_dot2(const typename Tr<K>::E* __restrict__ x, const typename Tr<K>::E* __restrict__ y, int64_t n,
+       typename Tr<K>::W* __restrict__ partial, typename Tr<K>::W* __restrict__ out,
+       unsigned* __restrict__ counter, const int* __restrict__ flags, const P2P p2p)
+{
+    using E = typename Tr<K>::E;
+    using W = typename Tr<K>::W;
+    constexpr int EPP = Tr<K>::EPP;
+    constexpr int U = 4;
+    using P = Pack<E, EPP>;
+    if (flags && flags[F_STOP]) return;
+    const int64_t npk = n / EPP;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    E axy = zero_v(E()), ayy = zero_v(E());
+    int64_t pk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; pk + (U - 1) * stride < npk; pk += U * stride) {
+        P xv[U], yv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { xv[u] = ld_pack_nc<P>(x + (pk + u * stride) * EPP); yv[u] = ld_pack_nc<P>(y + (pk + u * stride) * EPP); }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int e = 0; e < EPP; ++e) { fma_conj(axy, xv[u].v[e], yv[u].v[e]); fma_conj(ayy, yv[u].v[e], yv[u].v[e]); }
+    }
+    for (; pk < npk; pk += stride) {
+        const P xv = ld_pack_nc<P>(x + pk * EPP), yv = ld_pack_nc<P>(y + pk * EPP);
+#pragma unroll
+        for (int e = 0; e < EPP; ++e) { fma_conj(axy, xv.v[e], yv.v[e]); fma_conj(ayy, yv.v[e], yv.v[e]); }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int64_t t = npk * EPP; t < n; ++t) { fma_conj(axy, x[t], y[t]); fma_conj(ayy, y[t], y[t]); }
+    __shared__ W sm[8][2];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const W a = warp_sum(widen(axy)), b = warp_sum(widen(ayy));
+    if (lane == 0) { sm[wid][0] = a; sm[wid][1] = b; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        W t = sm[0][threadIdx.x];
+        for (int q = 1; q < 8; ++q) wadd(t, sm[q][threadIdx.x]);
+        partial[(int64_t)blockIdx.x * 2 + threadIdx.x] = t;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1u);
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        if (wid < 2) {
+            W t = zero_v(W());
+            for (int bq = lane; bq < (int)gridDim.x; bq += 32) wadd(t, __ldcg(&partial[(int64_t)bq * 2 + wid]));
+            t = warp_sum(t);
+            if (lane == 0) out[wid] = t;
+        }
+        if (threadIdx.x == 0) *counter = 0u;
+        if (p2p.world > 1) p2p_allreduce_cta<W>(p2p, out, 2);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // multi-axpy:  w -= V(:, 0:j) c.  One 16-byte pack of w per thread per iteration, the j basis
 // packs streamed with UA independent 128-bit loads in flight; c broadcast from shared memory.
 // Optional epilogue: ||w_new||^2 with the same two-stage deterministic reduction (this is the
@@ -284,6 +349,15 @@ template <int K>
 static void multidot_t(cudaStream_t s, const void* V, int64_t ld, int j, const void* w, int64_t n,
                        void* partial, void* out, unsigned* counter, const int* flags, int sms, const P2P* p2p) {
     using E = typename Tr<K>::E; using W = typename Tr<K>::W;
+    if (j == 1) {      // two-vector dot: dedicated streaming kernel
+        const int64_t npk1 = n / Tr<K>::EPP;
+        int64_t nb1 = (npk1 + 256 * 4 - 1) / (256 * 4);
+        if (nb1 < 1) nb1 = 1;
+        if (nb1 > 4 * (int64_t)sms) nb1 = 4 * (int64_t)sms;
+        if (nb1 > MAX_ROWBLOCKS) nb1 = MAX_ROWBLOCKS;
+        k_dot2<K><<<(int)nb1, 256, 0, s>>>((const E*)V, (const E*)w, n, (W*)partial, (W*)out, counter, flags, p2p ? *p2p : P2P());
+        return;
+    }
     // grid: fixed function of the problem size (2 resident CTAs per SM), never of timing.  Tile size:
     // the largest of 4/2/1 packs per thread that still leaves >= 12 tiles per CTA, so the ceil() in the
     // tile split costs < 8 % (at 1/8 of C2 per GPU, 4-pack tiles gave 3.46 tiles per CTA = 86 % balance).

@@ -7,6 +7,7 @@
 // lanczos.fypp:29-40, golub_kahan.fypp:37-59.
 #include "lkb_kernels.h"
 #include "lkb_rng.h"
+#include "lkb_p2p.cuh"
 
 namespace lkb {
 
@@ -197,6 +198,131 @@ __global__ void k_narrow(const typename Tr<K>::W* src, typename Tr<K>::E* dst, i
 }
 
 // ------------------------------------------------------------------------------------------
+// Conjugate gradient on the device (CG/CG.fypp:123-171).  One iteration =
+//   matvec ; pAp = p^H Ap (multi-dot) ; k_cg_update ; k_cg_check ; k_cg_direction
+// with alpha / beta / the residual test kept in device scalars, so a chunk of iterations is one CUDA
+// graph and the host only looks at the flags between chunks.  Iterations enqueued after the one that
+// converged are no-ops (every kernel returns on flags[F_STOP]) => n_iter, x and the residual history
+// are exactly those of the reference's sequential loop.
+//   scal[0] = r_dot_r_old, scal[1] = beta ; flags[5] = iteration counter, flags[6] = converged
+LKB_DI double2 wdiv(double2 a, double2 b) {
+    const double d = b.x * b.x + b.y * b.y;
+    return make_double2((a.x * b.x + a.y * b.y) / d, (a.y * b.x - a.x * b.y) / d);
+}
+LKB_DI double2 as_w2(double a) { return make_double2(a, 0.0); }
+LKB_DI double2 as_w2(double2 a) { return a; }
+LKB_DI void from_w2(double2 a, double& o) { o = a.x; }
+LKB_DI void from_w2(double2 a, double2& o) { o = a; }
+
+// x += alpha p ; r -= alpha Ap ; nrm2 = r_new^H r_new   with alpha = rr_old / pAp  (device scalars)
+template <int K>
+__global__ void __launch_bounds__(256, 2)
+k_cg_update(const typename Tr<K>::W* __restrict__ scal, const typename Tr<K>::W* __restrict__ pAp,
+            const typename Tr<K>::E* __restrict__ p, const typename Tr<K>::E* __restrict__ Ap,
+            typename Tr<K>::E* __restrict__ x, typename Tr<K>::E* __restrict__ r, int64_t n,
+            double* __restrict__ partial, typename Tr<K>::W* __restrict__ nrm2_out,
+            unsigned* __restrict__ counter, const int* __restrict__ flags, const P2P p2p)
+{
+    using E = typename Tr<K>::E;
+    using W = typename Tr<K>::W;
+    constexpr int EPP = Tr<K>::EPP;
+    using P = Pack<E, EPP>;
+    if (flags[F_STOP]) return;
+    W aw; from_w2(wdiv(as_w2(scal[0]), as_w2(pAp[0])), aw);
+    E alpha; narrow(aw, alpha);
+    const int64_t npk = n / EPP;
+    double nrm = 0.0;
+    for (int64_t pk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pk < npk; pk += (int64_t)gridDim.x * blockDim.x) {
+        const P pv = ld_pack_nc<P>(p + pk * EPP), av = ld_pack_nc<P>(Ap + pk * EPP);
+        P xv = ld_pack<P>(x + pk * EPP), rv = ld_pack<P>(r + pk * EPP);
+#pragma unroll
+        for (int e = 0; e < EPP; ++e) {
+            fmacc(xv.v[e], pv.v[e], alpha);
+            fnma(rv.v[e], av.v[e], alpha);
+            nrm += abs2_w(rv.v[e]);
+        }
+        st_pack(x + pk * EPP, xv);
+        st_pack(r + pk * EPP, rv);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int64_t t = npk * EPP; t < n; ++t) {
+            E xv = x[t], rv = r[t];
+            fmacc(xv, p[t], alpha); fnma(rv, Ap[t], alpha);
+            x[t] = xv; r[t] = rv; nrm += abs2_w(rv);
+        }
+    __shared__ double sm[8];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const double a = warp_sum(nrm);
+    if (lane == 0) sm[wid] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = sm[0];
+        for (int q = 1; q < (int)(blockDim.x >> 5); ++q) t += sm[q];
+        partial[blockIdx.x] = t;
+        __threadfence();
+        is_last = (atomicAdd(counter, 1u) == gridDim.x - 1u);
+    }
+    __syncthreads();
+    if (is_last) {
+        if (wid == 0) {
+            __threadfence();
+            double t = 0.0;
+            for (int b = lane; b < (int)gridDim.x; b += 32) t += __ldcg(&partial[b]);
+            t = warp_sum(t);
+            if (lane == 0) {
+                W o = zero_v(W());
+                *reinterpret_cast<double*>(&o) = t;
+                nrm2_out[0] = o;
+                *counter = 0u;
+            }
+        }
+        if (p2p.world > 1) p2p_allreduce_cta<W>(p2p, nrm2_out, 1);
+    }
+}
+
+// residual = sqrt(|rr_new|) ; history ; convergence / maxiter stop ; beta = rr_new / rr_old ; rr_old <- rr_new
+template <int K>
+__global__ void k_cg_check(typename Tr<K>::W* __restrict__ scal, const typename Tr<K>::W* __restrict__ rr_new,
+                           double tol, int maxiter, double* __restrict__ res_hist, int* __restrict__ flags)
+{
+    using W = typename Tr<K>::W;
+    if (flags[F_STOP]) return;
+    const double2 rn = as_w2(rr_new[0]), ro = as_w2(scal[0]);
+    const double residual = sqrt(sqrt(rn.x * rn.x + rn.y * rn.y));
+    const int it = ++flags[5];
+    res_hist[it] = residual;
+    if (residual < tol) { flags[F_STOP] = 1; flags[F_INFO] = it; flags[6] = 1; return; }
+    W b; from_w2(wdiv(rn, ro), b);
+    scal[1] = b;
+    scal[0] = rr_new[0];
+    if (it >= maxiter) { flags[F_STOP] = 1; flags[F_INFO] = it; }
+}
+
+// p = r + beta p  (beta = scal[1] on the device)
+template <int K>
+__global__ void __launch_bounds__(256)
+k_cg_direction(const typename Tr<K>::W* __restrict__ scal, const typename Tr<K>::E* __restrict__ r,
+               typename Tr<K>::E* __restrict__ p, int64_t n, const int* __restrict__ flags)
+{
+    using E = typename Tr<K>::E;
+    constexpr int EPP = Tr<K>::EPP;
+    using P = Pack<E, EPP>;
+    if (flags[F_STOP]) return;
+    E beta; narrow(scal[1], beta);
+    const int64_t npk = n / EPP;
+    for (int64_t pk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pk < npk; pk += (int64_t)gridDim.x * blockDim.x) {
+        const P rv = ld_pack_nc<P>(r + pk * EPP);
+        P pv = ld_pack<P>(p + pk * EPP);
+#pragma unroll
+        for (int e = 0; e < EPP; ++e) pv.v[e] = add_v(rv.v[e], mul_v(beta, pv.v[e]));
+        st_pack(p + pk * EPP, pv);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int64_t t = npk * EPP; t < n; ++t) p[t] = add_v(r[t], mul_v(beta, p[t]));
+}
+
+// ------------------------------------------------------------------------------------------
 #define LKB_DISPATCH(kind, ...)                                \
     switch (kind) {                                            \
         case KS: { constexpr int K = KS; __VA_ARGS__; } break; \
@@ -247,6 +373,27 @@ void launch_update(int kind, cudaStream_t s, const void* c1, const void* c2, int
         using E = typename Tr<K>::E; using W = typename Tr<K>::W;
         k_update<K><<<1, 128, 0, s>>>((const W*)c1, (const W*)c2, j, (const W*)nrm2, (E*)hcol, tol, atol,
                                       (double*)inv_dev, flags, kstep, mode);
+    });
+}
+void launch_cg_update(int kind, cudaStream_t s, const void* scal, const void* pAp, const void* p, const void* Ap, void* x,
+                      void* r, int64_t n, void* partial, void* nrm2_out, unsigned* counter, const int* flags, int sms,
+                      const P2P* p2p) {
+    const P2P pp = p2p ? *p2p : P2P();
+    LKB_DISPATCH(kind, {
+        using E = typename Tr<K>::E; using W = typename Tr<K>::W;
+        int64_t nb = (n / Tr<K>::EPP + 255) / 256; if (nb < 1) nb = 1; if (nb > 4 * (int64_t)sms) nb = 4 * (int64_t)sms;
+        if (nb > MAX_ROWBLOCKS) nb = MAX_ROWBLOCKS;
+        k_cg_update<K><<<(int)nb, 256, 0, s>>>((const W*)scal, (const W*)pAp, (const E*)p, (const E*)Ap, (E*)x, (E*)r, n,
+                                              (double*)partial, (W*)nrm2_out, counter, flags, pp);
+    });
+}
+void launch_cg_check(int kind, cudaStream_t s, void* scal, const void* rr_new, double tol, int maxiter, double* res_hist, int* flags) {
+    LKB_DISPATCH(kind, { using W = typename Tr<K>::W; k_cg_check<K><<<1, 1, 0, s>>>((W*)scal, (const W*)rr_new, tol, maxiter, res_hist, flags); });
+}
+void launch_cg_direction(int kind, cudaStream_t s, const void* scal, const void* r, void* p, int64_t n, const int* flags, int sms) {
+    LKB_DISPATCH(kind, {
+        using E = typename Tr<K>::E; using W = typename Tr<K>::W;
+        k_cg_direction<K><<<ew_grid(n / Tr<K>::EPP, sms), 256, 0, s>>>((const W*)scal, (const E*)r, (E*)p, n, flags);
     });
 }
 void launch_gsinfo(cudaStream_t s, const void* ww, int, double atol, int* flags) {

@@ -70,8 +70,24 @@ int prof_collect(lkb_ctx_s* c) {
     return 0;
 }
 
-static int grow(void** p, size_t* cur, size_t need) {
+// Captured graphs hold raw pointers into the context workspaces and into bases / operators: whenever
+// one of those allocations goes away the cached executables that may reference it are dropped.
+void invalidate_graphs(lkb_ctx_s* c, uint64_t uid) {
+    if (uid == 0) {
+        for (auto& kv : c->graph_cache) cudaGraphExecDestroy(kv.second.exec);
+        c->graph_cache.clear();
+        return;
+    }
+    char tag[40]; snprintf(tag, sizeof(tag), ":%llu:", (unsigned long long)uid);
+    for (auto it = c->graph_cache.begin(); it != c->graph_cache.end();) {
+        if (it->first.find(tag) != std::string::npos) { cudaGraphExecDestroy(it->second.exec); it = c->graph_cache.erase(it); }
+        else ++it;
+    }
+}
+static int grow(lkb_ctx_s* c, void** p, size_t* cur, size_t need) {
     if (*cur >= need) return 0;
+    cudaStreamSynchronize(c->stream);
+    invalidate_graphs(c, 0);
     if (*p) cudaFree(*p);
     *p = nullptr; *cur = 0;
     LKB_CUDA(cudaMalloc(p, need));
@@ -81,9 +97,11 @@ static int grow(void** p, size_t* cur, size_t need) {
 int ensure_ws(lkb_ctx_s* c, int jp) {
     if (c->capturing) return 0;   // sized before capture begins
     const size_t need = (size_t)MAX_ROWBLOCKS * (size_t)jp * 16;
-    LKB_TRY(grow(&c->partial, &c->partial_bytes, std::max(need, (size_t)MAX_ROWBLOCKS * 16 * 8)));
+    LKB_TRY(grow(c, &c->partial, &c->partial_bytes, std::max(need, (size_t)MAX_ROWBLOCKS * 16 * 8)));
     if (c->cbuf_len < (size_t)jp) {
         size_t len = std::max((size_t)jp, (size_t)272);
+        cudaStreamSynchronize(c->stream);
+        invalidate_graphs(c, 0);
         if (c->c1) cudaFree(c->c1); if (c->c2) cudaFree(c->c2); if (c->tmpw) cudaFree(c->tmpw);
         c->c1 = c->c2 = c->tmpw = nullptr; c->cbuf_len = 0;
         LKB_CUDA(cudaMalloc(&c->c1, len * 16)); LKB_CUDA(cudaMalloc(&c->c2, len * 16)); LKB_CUDA(cudaMalloc(&c->tmpw, len * 16));
@@ -99,8 +117,8 @@ int ensure_hstage(lkb_ctx_s* c, size_t bytes) {
     c->hstage_bytes = bytes;
     return 0;
 }
-int ensure_Hd(lkb_ctx_s* c, size_t bytes) { return grow(&c->Hd, &c->Hd_bytes, bytes); }
-int ensure_coefd(lkb_ctx_s* c, size_t bytes) { return grow(&c->coefd, &c->coefd_bytes, bytes); }
+int ensure_Hd(lkb_ctx_s* c, size_t bytes) { return grow(c, &c->Hd, &c->Hd_bytes, bytes); }
+int ensure_coefd(lkb_ctx_s* c, size_t bytes) { return grow(c, &c->coefd, &c->coefd_bytes, bytes); }
 
 int allreduce_w(lkb_ctx_s* c, void* buf, size_t ndoubles) {
     if (c->world == 1 || c->p2p_active) return 0;      // p2p: already reduced inside the producing kernel
@@ -426,6 +444,7 @@ int lkb_basis_create(lkb_ctx_t c, int kind, int64_t n_local, int64_t n_global, i
 int lkb_basis_destroy(lkb_basis_t b) {
     if (!b) return LKB_ERR_ARG;
     cudaStreamSynchronize(b->ctx->stream);
+    invalidate_graphs(b->ctx, b->uid);
     cudaFree(b->d);
     delete b;
     return 0;
@@ -565,6 +584,7 @@ int lkb_op_callback_create(lkb_ctx_t c, int kind, int64_t m_local, int64_t n_loc
 int lkb_op_destroy(lkb_op_t A) {
     if (!A) return LKB_ERR_ARG;
     cudaStreamSynchronize(A->ctx->stream);
+    invalidate_graphs(A->ctx, A->uid);
     void* bufs[] = { A->halo_lo, A->halo_hi, A->rowptr, A->col, A->val, A->t_rowptr, A->t_col, A->t_val, A->a };
     for (void* b : bufs) if (b) cudaFree(b);
     delete A;

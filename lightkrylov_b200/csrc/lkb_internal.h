@@ -122,6 +122,7 @@ int vec_dot_sync(lkb_ctx_s* c, int kind, const void* x, const void* y, int64_t n
 int fetch_flags(lkb_ctx_s* c, int* host_flags);
 uint64_t next_seed(lkb_ctx_s* c);
 uint64_t next_uid();
+void invalidate_graphs(lkb_ctx_s* c, uint64_t uid);   // uid == 0: all
 int arnoldi_enqueue(lkb_op_s* A, lkb_basis_s* X, int kstart, int kend, double tol, bool tr);
 int arnoldi_fetch_async(lkb_basis_s* X, int kstart, int kend, void* pinned_host);
 int arnoldi_collect(lkb_op_s* A, lkb_basis_s* X, void* H, int ldh, int32_t* info, int kstart, int kend, bool tr,

@@ -59,6 +59,13 @@ void launch_scal(int kind, cudaStream_t s, Scalar alpha, void* x, int64_t n, int
 void launch_scale_dev(int kind, cudaStream_t s, void* x, int64_t n, const void* inv_dev, const int* flags, int kstep, int sms);
 void launch_fill(int kind, cudaStream_t s, void* x, int64_t n, int64_t row0, int dist, uint64_t seed, int sms);
 
+// device-resident CG iteration (kernels_vec.cu): see k_cg_update / k_cg_check / k_cg_direction
+void launch_cg_update(int kind, cudaStream_t s, const void* scal, const void* pAp, const void* p, const void* Ap, void* x,
+                      void* r, int64_t n, void* partial, void* nrm2_out, unsigned* counter, const int* flags, int sms,
+                      const P2P* p2p);
+void launch_cg_check(int kind, cudaStream_t s, void* scal, const void* rr_new, double tol, int maxiter, double* res_hist, int* flags);
+void launch_cg_direction(int kind, cudaStream_t s, const void* scal, const void* r, void* p, int64_t n, const int* flags, int sms);
+
 // Hessenberg / tridiagonal / bidiagonal column update (one tiny CTA).
 //   mode 0 arnoldi (qr_no_pivoting p=1 + breakdown test), 1 lanczos (< tol), 2 bidiag (<= tol), 3 plain norm
 void launch_update(int kind, cudaStream_t s, const void* c1, const void* c2, int j, const void* nrm2, void* hcol,

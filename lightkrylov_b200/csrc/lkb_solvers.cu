@@ -255,6 +255,76 @@ static int cg_impl(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, double r
         CG_TRY(vec_dot_sync(c, kind, r->d, r->d, b->n, &rr_old));
     }
     push_res(io->res, io->res_cap, &io->res_len, sqrt(hypot(rr_old.re, rr_old.im)));
+    if (!precond) {
+        // ---- device-resident iteration: alpha, beta and the convergence test stay on the GPU; chunks of
+        // CH iterations run as one CUDA graph, the host reads the flags between chunks (kernels_vec.cu) ----
+        const int CH = 16;
+        const size_t wsz = kind_cplx(kind) ? 16 : 8;
+        void* scal = nullptr; double* res_hist = nullptr;
+        auto cleanup2 = [&](int rr) { cudaStreamSynchronize(c->stream); if (scal) cudaFree(scal); if (res_hist) cudaFree(res_hist); return cleanup(rr); };
+        if (cudaMalloc(&scal, 64) != cudaSuccess || cudaMalloc((void**)&res_hist, (size_t)(maxiter + 2) * sizeof(double)) != cudaSuccess)
+            { set_error("cg: workspace allocation failed"); return cleanup2(LKB_ERR_ALLOC); }
+#undef CG_TRY
+#define CG_TRY(call) do { rc = (call); if (rc) return cleanup2(rc); } while (0)
+        CG_TRY(ensure_ws(c, 2));
+        cudaMemsetAsync(scal, 0, 64, c->stream);
+        cudaMemcpyAsync(scal, c->tmpw, wsz, cudaMemcpyDeviceToDevice, c->stream);     // r_dot_r_old (just reduced)
+        cudaMemsetAsync(c->flags, 0, F_COUNT * sizeof(int), c->stream);
+        const size_t ndw = 2 * (size_t)(kind_cplx(kind) ? 2 : 1);
+        auto one_iteration = [&]() -> int {
+            LKB_TRY(op_apply_enqueue(A, p->d, Ap->d, false, c->flags));
+            prof_begin(c, PC_DOT);
+            launch_multidot(kind, c->stream, p->d, b->n, 1, Ap->d, b->n, c->partial, c->tmpw, c->counter, c->flags, c->sms, c->p2p_arg());
+            prof_end(c, PC_DOT, 1);
+            LKB_TRY(allreduce_w(c, c->tmpw, ndw));
+            prof_begin(c, PC_OTHER);
+            launch_cg_update(kind, c->stream, scal, c->tmpw, p->d, Ap->d, x->d, r->d, b->n, c->partial, c->nrm2, c->counter,
+                             c->flags, c->sms, c->p2p_arg());
+            prof_end(c, PC_OTHER, 1);
+            LKB_TRY(allreduce_w(c, c->nrm2, 1));
+            prof_begin(c, PC_OTHER);
+            launch_cg_check(kind, c->stream, scal, c->nrm2, tol, maxiter, res_hist, c->flags);
+            launch_cg_direction(kind, c->stream, scal, r->d, p->d, b->n, c->flags, c->sms);
+            prof_end(c, PC_OTHER, 2);
+            return check_launch(c, "cg iteration");
+        };
+        cudaGraphExec_t exec = nullptr;
+        int64_t graph_launches = 0;
+        const bool use_graph = c->graphs && !c->profile && (A->type != 9 || A->capturable);
+        if (use_graph) {
+            const int64_t l0 = c->launches;
+            CG_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess ? 0 : LKB_ERR_CUDA);
+            c->capturing = true;
+            int r2 = 0;
+            for (int q = 0; q < CH && r2 == 0; ++q) r2 = one_iteration();
+            c->capturing = false;
+            cudaGraph_t g = nullptr;
+            cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+            if (r2 == 0 && e != cudaSuccess) { set_error("cg: graph capture failed: %s", cudaGetErrorString(e)); r2 = LKB_ERR_CUDA; }
+            if (r2 == 0 && cudaGraphInstantiate(&exec, g, 0) != cudaSuccess) { set_error("cg: graph instantiate failed"); r2 = LKB_ERR_CUDA; }
+            if (g) cudaGraphDestroy(g);
+            graph_launches = c->launches - l0; c->launches = l0;
+            CG_TRY(r2);
+        }
+        int hf[F_COUNT] = {0};
+        while (true) {
+            if (exec) { CG_TRY(cudaGraphLaunch(exec, c->stream) == cudaSuccess ? 0 : LKB_ERR_CUDA); c->launches += graph_launches; }
+            else for (int q = 0; q < CH; ++q) CG_TRY(one_iteration());
+            CG_TRY(fetch_flags(c, hf));
+            if (hf[F_STOP]) break;
+        }
+        if (exec) cudaGraphExecDestroy(exec);
+        io->n_iter = hf[5]; io->converged = hf[6];
+        A->n_matvec += io->n_iter;
+        std::vector<double> hist((size_t)io->n_iter + 1);
+        CG_TRY(cudaMemcpy(hist.data(), res_hist, hist.size() * sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : LKB_ERR_CUDA);
+        for (int i = 1; i <= io->n_iter; ++i) push_res(io->res, io->res_cap, &io->res_len, hist[i]);
+        *info = io->converged ? io->n_iter : -io->n_iter;
+        io->info = *info;
+        return cleanup2(check_launch(c, "cg"));
+    }
+#undef CG_TRY
+#define CG_TRY(call) do { rc = (call); if (rc) return cleanup(rc); } while (0)
     for (int it = 1; it <= maxiter; ++it) {
         A->n_matvec++;
         CG_TRY(op_apply_enqueue(A, p->d, Ap->d, false, nullptr));
@@ -265,14 +335,13 @@ static int cg_impl(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, double r
         launch_axpby(kind, c->stream, to_scalar(-alpha), Ap->d, one, r->d, b->n, c->sms);    // r -= alpha Ap
         c->launches += 2;
         Scalar rr_new;
-        if (precond) { CG_TRY(make_z()); CG_TRY(vec_dot_sync(c, kind, r->d, z->d, b->n, &rr_new)); }
-        else CG_TRY(vec_dot_sync(c, kind, r->d, r->d, b->n, &rr_new));
+        CG_TRY(make_z()); CG_TRY(vec_dot_sync(c, kind, r->d, z->d, b->n, &rr_new));
         const double residual = sqrt(hypot(rr_new.re, rr_new.im));
         io->n_iter++;
         push_res(io->res, io->res_cap, &io->res_len, residual);
         if (residual < tol) { io->converged = 1; break; }
         const cd beta = round_kind(kind, cd(rr_new.re, rr_new.im) / cd(rr_old.re, rr_old.im));
-        launch_axpby(kind, c->stream, one, precond ? z->d : r->d, to_scalar(beta), p->d, b->n, c->sms);  // p = z + beta p
+        launch_axpby(kind, c->stream, one, z->d, to_scalar(beta), p->d, b->n, c->sms);       // p = z + beta p
         c->launches++;
         rr_old = rr_new;
     }

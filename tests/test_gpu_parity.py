@@ -515,3 +515,19 @@ def test_preconditioned_cg_and_gmres_vs_oracle(lk, ctx, oracle):
     np.testing.assert_allclose(gmeta["res"], ometa2["res"], rtol=1e-5, atol=1e-13)
     assert np.linalg.norm(x2.get() - xo2) < 1e-7 * np.linalg.norm(xo2)
     assert calls[0] == 1 and -1 in calls                     # (wrk, k, beta, tol) form and the plain apply(dx) form
+
+
+def test_arnoldi_large_kdim_workspace_growth(lk, ctx, oracle):
+    """kdim > 271 grows the coefficient workspaces (cached graphs must be dropped) and j > 128 takes the
+    unfused CGS2 path; a second, smaller factorisation afterwards must still be correct."""
+    nx, ny, kdim = 96, 64, 300; n = nx * ny
+    A = lk.LinOp.stencil5(ctx, "d", nx, ny, CONVDIFF7[:5]); Ao = oracle.Op.stencil("d", (nx, ny), CONVDIFF7[:5])
+    x0 = oracle.fill(n, "d", "uniform", 11); oracle.normalize(x0)
+    small = lk.Basis(ctx, "d", n, 17).put(x0); Hs = np.zeros((17, 16), order="F")
+    assert lk.arnoldi(A, small, Hs) == 0                       # cached 16-step graph using the small workspaces
+    info, X, H, oinfo, Xo, Ho = _arnoldi_pair(lk, ctx, oracle, "d", A, Ao, n, kdim, x0)
+    assert info == oinfo == 0 and rel_normwise(H, Ho) < 1e-10
+    Xg = X.get()
+    assert np.abs(Xg.T @ Xg - np.eye(kdim + 1)).max() < 1e-12
+    small.zero(); small.put(x0); Hs2 = np.zeros_like(Hs)
+    assert lk.arnoldi(A, small, Hs2) == 0 and np.array_equal(Hs, Hs2)
