@@ -526,8 +526,12 @@ def test_arnoldi_large_kdim_workspace_growth(lk, ctx, oracle):
     small = lk.Basis(ctx, "d", n, 17).put(x0); Hs = np.zeros((17, 16), order="F")
     assert lk.arnoldi(A, small, Hs) == 0                       # cached 16-step graph using the small workspaces
     info, X, H, oinfo, Xo, Ho = _arnoldi_pair(lk, ctx, oracle, "d", A, Ao, n, kdim, x0)
-    assert info == oinfo == 0 and rel_normwise(H, Ho) < 1e-10
+    # a 300-step Krylov sequence is not entrywise reproducible between two summation orders once Ritz
+    # values have converged (tiny differences are amplified), so: early columns entrywise, then invariants
+    assert info == oinfo == 0 and rel_normwise(H[:41, :40], Ho[:41, :40]) < 1e-9
     Xg = X.get()
     assert np.abs(Xg.T @ Xg - np.eye(kdim + 1)).max() < 1e-12
+    AX = np.stack([Ao.apply(Xg[:, k].copy()) for k in range(kdim)], axis=1)
+    assert np.abs(AX - Xg @ H).max() < 1e-12 * 10
     small.zero(); small.put(x0); Hs2 = np.zeros_like(Hs)
     assert lk.arnoldi(A, small, Hs2) == 0 and np.array_equal(Hs, Hs2)
