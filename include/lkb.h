@@ -162,6 +162,10 @@ typedef int (*lkb_precond_fn)(void* user, void* vec_dev, int64_t n_local, int32_
                               double target_residual, void* stream);
 int lkb_gmres_precond(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, double rtol, double atol,
                       int32_t transpose, lkb_gmres_io* io, lkb_precond_fn precond, void* user);
+/* fgmres(A, b, x, info, rtol, atol, preconditioner, options, transpose, meta)  GMRES/fgmres.fypp:65-260:
+ * flexible GMRES, the preconditioned vectors Z(k) are stored; options / metadata as gmres. */
+int lkb_fgmres(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, double rtol, double atol,
+               int32_t transpose, lkb_gmres_io* io, lkb_precond_fn precond, void* user);
 typedef struct {            /* cg_dp_opts / cg_dp_metadata : IterativeSolvers.fypp:467-507 */
     int32_t maxiter;        /* default 100 */
     int32_t n_iter, converged, info;

@@ -94,6 +94,7 @@ SIGNATURES = {
     "lkb_gmres": (_i, [_vp, _vp, _vp, _P(_i32), _d, _d, _i32, _P(GmresIO)]),
     "lkb_cg": (_i, [_vp, _vp, _vp, _P(_i32), _d, _d, _P(CgIO)]),
     "lkb_gmres_precond": (_i, [_vp, _vp, _vp, _P(_i32), _d, _d, _i32, _P(GmresIO), PRECOND_FN, _vp]),
+    "lkb_fgmres": (_i, [_vp, _vp, _vp, _P(_i32), _d, _d, _i32, _P(GmresIO), PRECOND_FN, _vp]),
     "lkb_cg_precond": (_i, [_vp, _vp, _vp, _P(_i32), _d, _d, _P(CgIO), PRECOND_FN, _vp]),
     "lkb_eigs": (_i, [_vp, _vp, _i, _P(_d), _P(_d), _P(_i32), _vp, _i32, _d, _i32]),
     "lkb_eighs": (_i, [_vp, _vp, _i, _P(_d), _P(_d), _P(_i32), _vp, _i32, _d]),

@@ -428,6 +428,20 @@ def gmres(A: LinOp, b: Vector, x: Vector, rtol: float = -1.0, atol: float = -1.0
     return info.value, meta
 
 
+def fgmres(A: LinOp, b: Vector, x: Vector, rtol: float = -1.0, atol: float = -1.0, kdim: int = 30,
+           maxiter: int = 10, transpose: bool = False, preconditioner=None):
+    """Flexible GMRES (GMRES/fgmres.fypp): same options / metadata as gmres."""
+    cap = (kdim + 2) * (maxiter + 2) + 8
+    res = (C.c_double * cap)()
+    io = _lib.GmresIO(kdim=kdim, maxiter=maxiter, res=res, res_cap=cap)
+    info = C.c_int32()
+    cb = _wrap_precond(preconditioner) if preconditioner is not None else C.cast(None, _lib.PRECOND_FN)
+    check(A.ctx.lib.lkb_fgmres(A.h, b.h, x.h, C.byref(info), rtol, atol, int(transpose), C.byref(io), cb, None), "fgmres")
+    meta = dict(n_iter=io.n_iter, n_inner=io.n_inner, n_outer=io.n_outer, converged=bool(io.converged),
+                info=io.info, res=[res[i] for i in range(min(io.res_len, cap))])
+    return info.value, meta
+
+
 def cg(A: LinOp, b: Vector, x: Vector, rtol: float = -1.0, atol: float = -1.0, maxiter: int = 100,
        preconditioner=None):
     cap = maxiter + 8

@@ -68,8 +68,10 @@ void push_res(double* res, int32_t cap, int32_t* len, double v) {
 
 extern "C" {
 
+// flexible = fgmres (GMRES/fgmres.fypp:65-260): the preconditioned vectors Z(k) are stored and the update is
+// dx = Z(:k) y, so the preconditioner may change from one inner step to the next.
 static int gmres_impl(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, double rtol, double atol, int32_t transpose,
-                      lkb_gmres_io* io, lkb_precond_fn precond, void* puser) {
+                      lkb_gmres_io* io, lkb_precond_fn precond, void* puser, bool flexible = false) {
     if (!A || !b || !x || !info) { set_error("gmres: null argument"); return LKB_ERR_ARG; }
     if (b->n != x->n || b->kind != A->kind || x->kind != A->kind || A->m != b->n || A->n != b->n)
         { set_error("gmres: size/kind mismatch"); return LKB_ERR_ARG; }
@@ -92,14 +94,16 @@ static int gmres_impl(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, doubl
     lkb_basis_t V = nullptr;
     LKB_TRY(lkb_basis_create(c, kind, b->n, b->n_global, b->row0, kdim + 1, &V));
     lkb_vec_t dx = nullptr, wrk = nullptr;
+    lkb_basis_t Z = nullptr;
     LKB_TRY(lkb_vec_create(c, kind, b->n, b->n_global, b->row0, &dx));
-    if (precond) LKB_TRY(lkb_vec_create(c, kind, b->n, b->n_global, b->row0, &wrk));
+    if (precond && !flexible) LKB_TRY(lkb_vec_create(c, kind, b->n, b->n_global, b->row0, &wrk));
+    if (flexible) LKB_TRY(lkb_basis_create(c, kind, b->n, b->n_global, b->row0, kdim, &Z));
     std::vector<cd> H((size_t)(kdim + 1) * kdim), e(kdim + 1), cs(kdim), sn(kdim), y(kdim);
     std::vector<Scalar> col;
     const Scalar one{1, 0}, mone{-1, 0};
     int hf[F_COUNT];
     int rc = 0;
-    auto cleanup = [&](int r) { lkb_basis_destroy(V); lkb_vec_destroy(dx); if (wrk) lkb_vec_destroy(wrk); return r; };
+    auto cleanup = [&](int r) { lkb_basis_destroy(V); lkb_vec_destroy(dx); if (wrk) lkb_vec_destroy(wrk); if (Z) lkb_basis_destroy(Z); return r; };
     auto apply_precond = [&](void* v, int iter, double cur, double target) -> int {
         int r = precond(puser, v, b->n, iter, cur, target, (void*)c->stream);
         if (r != 0) { set_error("preconditioner callback returned %d", r); return LKB_ERR_ARG; }
@@ -136,7 +140,11 @@ static int gmres_impl(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, doubl
             void* w = col_ptr(V, k);
             if (trans) A->n_rmatvec++; else A->n_matvec++;
             const void* src = col_ptr(V, k - 1);
-            if (precond) {      // wrk = V(k) ; preconditioner%apply(wrk, k, beta, tol)   (gmres.fypp:155)
+            if (flexible) {     // copy(Z(k), V(k)) ; preconditioner%apply(Z(k), k, beta, tol)   (fgmres.fypp:160-161)
+                launch_axpby(kind, c->stream, one, col_ptr(V, k - 1), Scalar{0, 0}, col_ptr(Z, k - 1), b->n, c->sms); c->launches++;
+                if (precond) GM_TRY(apply_precond(col_ptr(Z, k - 1), k, beta, tol));
+                src = col_ptr(Z, k - 1);
+            } else if (precond) {      // wrk = V(k) ; preconditioner%apply(wrk, k, beta, tol)   (gmres.fypp:155)
                 launch_axpby(kind, c->stream, one, col_ptr(V, k - 1), Scalar{0, 0}, wrk->d, b->n, c->sms); c->launches++;
                 GM_TRY(apply_precond(wrk->d, k, beta, tol));
                 src = wrk->d;
@@ -182,8 +190,8 @@ static int gmres_impl(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, doubl
         {   // dx = V(:k) y ; x += dx
             std::vector<char> yk((size_t)k * kind_size(kind));
             for (int i = 0; i < k; ++i) store_kind(kind, y[i], &yk[(size_t)i * kind_size(kind)]);
-            GM_TRY(lkb_basis_lincomb(V, k, yk.data(), dx));
-            if (precond) GM_TRY(apply_precond(dx->d, -1, -1.0, -1.0));          // preconditioner%apply(dx)  (:202)
+            GM_TRY(lkb_basis_lincomb(flexible ? Z : V, k, yk.data(), dx));         // fgmres: dx = Z(:k) y (fgmres.fypp:207)
+            if (precond && !flexible) GM_TRY(apply_precond(dx->d, -1, -1.0, -1.0)); // preconditioner%apply(dx)  (gmres.fypp:202)
             launch_axpby(kind, c->stream, one, dx->d, one, x->d, x->n, c->sms); c->launches++;
         }
         GM_TRY(residual_into_v1(false));
@@ -207,6 +215,10 @@ int lkb_gmres(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, double rtol, 
 int lkb_gmres_precond(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, double rtol, double atol, int32_t transpose,
                       lkb_gmres_io* io, lkb_precond_fn precond, void* user) {
     return gmres_impl(A, b, x, info, rtol, atol, transpose, io, precond, user);
+}
+int lkb_fgmres(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, double rtol, double atol, int32_t transpose,
+               lkb_gmres_io* io, lkb_precond_fn precond, void* user) {
+    return gmres_impl(A, b, x, info, rtol, atol, transpose, io, precond, user, true);
 }
 
 static int cg_impl(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, double rtol, double atol, lkb_cg_io* io,

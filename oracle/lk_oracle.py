@@ -286,8 +286,10 @@ def apply_givens_rotation(h, c, s):
         h[k] = 0
 
 
-def gmres(A: Op, b: np.ndarray, x: np.ndarray, rtol=None, atol=None, kdim=30, maxiter=10, trans=False, precond=None):
-    """gmres.fypp:65-255 (no preconditioner).  Returns (info, meta dict); x updated in place."""
+def gmres(A: Op, b: np.ndarray, x: np.ndarray, rtol=None, atol=None, kdim=30, maxiter=10, trans=False, precond=None,
+          flexible=False):
+    """gmres.fypp:65-255; flexible=True restates fgmres.fypp:65-260 (Z(k) stored, dx = Z(:k) y).
+    precond(vec) or, for fgmres, precond(vec, k).  Returns (info, meta dict); x updated in place."""
     import scipy.linalg as sla
     kind = kind_of(b.dtype)
     n = b.size
@@ -295,6 +297,7 @@ def gmres(A: Op, b: np.ndarray, x: np.ndarray, rtol=None, atol=None, kdim=30, ma
     atol = ATOL[kind] if atol is None else atol
     tol = atol + rtol * norm(b)
     V = np.zeros((n, kdim + 1), dtype=b.dtype, order="F")
+    Zb = np.zeros((n, kdim), dtype=b.dtype, order="F") if flexible else None
     meta = dict(n_iter=0, n_inner=0, n_outer=0, res=[], converged=False)
     while (not meta["converged"]) and meta["n_outer"] <= maxiter:
         H = np.zeros((kdim + 1, kdim), dtype=b.dtype, order="F")
@@ -312,7 +315,12 @@ def gmres(A: Op, b: np.ndarray, x: np.ndarray, rtol=None, atol=None, kdim=30, ma
         for k in range(1, kdim + 1):
             wrk = V[:, k - 1].copy()
             if precond is not None:
-                precond(wrk)                                   # preconditioner%apply(wrk, k, beta, tol)
+                if flexible:
+                    precond(wrk, k)                            # preconditioner%apply(Z(k), k, beta, tol)
+                else:
+                    precond(wrk)                               # preconditioner%apply(wrk, k, beta, tol)
+            if flexible:
+                Zb[:, k - 1] = wrk
             V[:, k] = A.apply(wrk, trans)
             _, hcol = dgs_vec(V[:, k], V, k)
             H[:k, k - 1] = hcol
@@ -331,8 +339,8 @@ def gmres(A: Op, b: np.ndarray, x: np.ndarray, rtol=None, atol=None, kdim=30, ma
                 break
         k = kk
         y = sla.solve_triangular(H[:k, :k], e[:k], lower=False)
-        dx = V[:, :k] @ y
-        if precond is not None:
+        dx = (Zb if flexible else V)[:, :k] @ y
+        if precond is not None and not flexible:
             precond(dx)
         x += dx
         V[:, 0] = A.apply(x, trans)

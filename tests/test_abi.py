@@ -70,3 +70,32 @@ def test_sass_has_128bit_loads(so_path):
         chunks = [c for c in out.split("Function : ")[1:] if fn in c.split("\n", 1)[0]]
         assert chunks, fn
         assert all("LDG.E.128" in c for c in chunks), fn
+
+
+def _build_c_demo(so_path, tmp_path):
+    import subprocess
+    exe = str(tmp_path / "c_abi_demo")
+    libdir = os.path.dirname(so_path)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "c_abi_demo.c"), "-L" + libdir, "-llkb",
+                           "-Wl,-rpath," + libdir, "-lm", "-o", exe])
+    return exe
+
+
+def test_header_is_plain_c_and_links(so_path, tmp_path):
+    """include/lkb.h must compile as C99 and a C client must link against liblkb.so (no C++/torch types)."""
+    import subprocess
+    exe = _build_c_demo(so_path, tmp_path)
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, "64"], capture_output=True, text=True)
+        assert r.returncode == 2 and "no CUDA device" in r.stderr      # loud failure, no CPU fallback
+
+
+@pytest.mark.gpu
+def test_c_client_runs_on_gpu(so_path, tmp_path):
+    import subprocess
+    exe = _build_c_demo(so_path, tmp_path)
+    r = subprocess.run([exe, "1024"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "info=0" in r.stdout

@@ -535,3 +535,35 @@ def test_arnoldi_large_kdim_workspace_growth(lk, ctx, oracle):
     assert np.abs(AX - Xg @ H).max() < 1e-12 * 10
     small.zero(); small.put(x0); Hs2 = np.zeros_like(Hs)
     assert lk.arnoldi(A, small, Hs2) == 0 and np.array_equal(Hs, Hs2)
+
+
+def test_fgmres_vs_oracle(lk, ctx, oracle):
+    """Flexible GMRES with a preconditioner that CHANGES with the inner iteration (what fgmres is for)."""
+    import torch
+    dims = (20, 16, 12); n = int(np.prod(dims))
+    dh = 0.2 + oracle.fill(n, "d", "uniform", 99)
+    dd = torch.from_numpy(dh).cuda()
+    ext = torch.cuda.ExternalStream(ctx.stream)
+
+    def precond_dev(ptr, nloc, it, cur, tgt, stream):
+        with torch.cuda.stream(ext):
+            v = torch.as_tensor(_DevArray(ptr, nloc, "<f8"), device="cuda")
+            v.mul_(dd).mul_(1.0 + 0.05 * it)
+        return 0
+
+    def precond_host(v, k):
+        v *= dh * (1.0 + 0.05 * k)
+
+    bh = oracle.fill(n, "d", "uniform", 45)
+    A = lk.LinOp.stencil7(ctx, "d", *dims, CONVDIFF7); Ao = oracle.Op.stencil("d", dims, CONVDIFF7)
+    b = lk.Vector(ctx, "d", n).put(bh); x = lk.Vector(ctx, "d", n)
+    info, meta = lk.fgmres(A, b, x, kdim=20, maxiter=30, preconditioner=precond_dev)
+    xo = np.zeros(n); oinfo, ometa = oracle.gmres(Ao, bh, xo, kdim=20, maxiter=30, precond=precond_host, flexible=True)
+    assert info == oinfo > 0 and meta["n_outer"] == ometa["n_outer"]
+    np.testing.assert_allclose(meta["res"], ometa["res"], rtol=1e-5, atol=1e-13)
+    assert np.linalg.norm(x.get() - xo) < 1e-7 * np.linalg.norm(xo)
+    assert np.linalg.norm(Ao.apply(x.get()) - bh) < lk.RTOL["d"] * np.linalg.norm(bh) * 2
+    # without a preconditioner fgmres == gmres
+    x1 = lk.Vector(ctx, "d", n); x2 = lk.Vector(ctx, "d", n)
+    i1, m1 = lk.fgmres(A, b, x1, kdim=20, maxiter=30); i2, m2 = lk.gmres(A, b, x2, kdim=20, maxiter=30)
+    assert i1 == i2 and np.array_equal(x1.get(), x2.get())
