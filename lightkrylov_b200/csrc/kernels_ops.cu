@@ -6,6 +6,7 @@
 // row-sharded one: the neighbouring slab's boundary row / plane arrives in halo_lo / halo_hi.
 #include <stdlib.h>
 #include "lkb_kernels.h"
+#include "lkb_p2p.cuh"
 
 namespace lkb {
 
@@ -45,10 +46,15 @@ __global__ void __launch_bounds__(256)
 k_stencil(const typename Tr<K>::E* __restrict__ x, typename Tr<K>::E* __restrict__ y,
           int64_t nx, int64_t ny, int64_t nz, Coef7<typename Tr<K>::E> cf,
           const typename Tr<K>::E* __restrict__ halo_lo, const typename Tr<K>::E* __restrict__ halo_hi,
-          const int* __restrict__ flags)
+          const unsigned* __restrict__ halo_epoch, int64_t halo_parity_stride, const int* __restrict__ flags)
 {
     using E = typename Tr<K>::E;
     using PO = PackOps<E, PW>;
+    if (halo_epoch) {      // double-buffered p2p halos: pick the parity the preceding push kernel filled
+        const int64_t off = (int64_t)(*halo_epoch & 1u) * halo_parity_stride;
+        if (halo_lo) halo_lo += off;
+        if (halo_hi) halo_hi += off;
+    }
     using P = typename PO::P;
     if (flags && flags[F_STOP]) return;
     const int64_t npk_row = nx / PW;
@@ -149,7 +155,8 @@ static void stencil_launch(cudaStream_t s, const StencilArgs& a, const void* x, 
     const int64_t nyb = (a.ny + RY - 1) / RY;
     dim3 grid((unsigned)(nyb * (DIM == 3 ? a.nz : 1)), (unsigned)((npk_row + 255) / 256));
     k_stencil<K, PW, DIM, RY, 1, false><<<grid, 256, 0, s>>>((const E*)x, (E*)y, a.nx, a.ny, a.nz, cf,
-                                                             (const E*)a.halo_lo, (const E*)a.halo_hi, flags);
+                                                             (const E*)a.halo_lo, (const E*)a.halo_hi, a.halo_epoch,
+                                                             a.halo_parity_stride, flags);
 }
 
 template <int K>
@@ -171,6 +178,61 @@ void launch_stencil(int kind, cudaStream_t s, const StencilArgs& a, const void* 
         case KD: stencil_t<KD>(s, a, x, y, trans, flags); break;
         case KC: stencil_t<KC>(s, a, x, y, trans, flags); break;
         default: stencil_t<KZ>(s, a, x, y, trans, flags); break;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Halo exchange over NVLink peer memory, fused with its synchronisation: replaces the
+// ncclSend/ncclRecv group in front of the stencil.  Every CTA copies a slice of the boundary rows
+// straight into the neighbours' (CUDA-IPC mapped) halo buffers; the last CTA to finish raises this
+// rank's epoch flag in both neighbours and waits for theirs, so when the kernel retires the local
+// halo buffers of the current parity are complete.  Buffers alternate by epoch parity: a neighbour
+// can push for matvec m+1 only after it saw my push for matvec m, i.e. after I finished matvec m-1,
+// the last reader of that parity.
+template <int K>
+__global__ void __launch_bounds__(256)
+k_halo_push(HaloP2P h, const typename Tr<K>::E* __restrict__ x, int64_t n_loc, const int* __restrict__ flags)
+{
+    using E = typename Tr<K>::E;
+    if (flags && flags[F_STOP]) return;
+    __shared__ bool is_last;
+    const unsigned ep = *h.epoch + 1u;
+    const size_t par = (size_t)(ep & 1u) * 2 * h.side_bytes;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h.lo_region) {      // my first row/plane -> lower neighbour's halo_hi (side 1)
+        E* dst = reinterpret_cast<E*>(h.lo_region + h.data_off + par + h.side_bytes);
+        for (int64_t i = t0; i < h.he; i += stride) dst[i] = x[i];
+    }
+    if (h.hi_region) {      // my last row/plane -> upper neighbour's halo_lo (side 0)
+        E* dst = reinterpret_cast<E*>(h.hi_region + h.data_off + par);
+        const E* src = x + (n_loc - h.he);
+        for (int64_t i = t0; i < h.he; i += stride) dst[i] = src[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(h.ticket, 1u) == gridDim.x - 1u);
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+        __threadfence_system();
+        if (h.lo_region) st_volatile_u32(reinterpret_cast<unsigned*>(h.lo_region + 128), ep);   // "upper neighbour pushed"
+        if (h.hi_region) st_volatile_u32(reinterpret_cast<unsigned*>(h.hi_region), ep);         // "lower neighbour pushed"
+        if (h.lo_region) while ((int)(ld_volatile_u32(reinterpret_cast<const unsigned*>(h.my_region)) - ep) < 0) { }
+        if (h.hi_region) while ((int)(ld_volatile_u32(reinterpret_cast<const unsigned*>(h.my_region + 128)) - ep) < 0) { }
+        __threadfence_system();
+        *h.ticket = 0u;
+        *h.epoch = ep;
+    }
+}
+void launch_halo_push(int kind, cudaStream_t s, const HaloP2P& h, const void* x, int64_t n_loc, const int* flags) {
+    int nb = (int)((h.he + 2047) / 2048);
+    if (nb < 1) nb = 1;
+    if (nb > 64) nb = 64;
+    switch (kind) {
+        case KS: k_halo_push<KS><<<nb, 256, 0, s>>>(h, (const float*)x, n_loc, flags); break;
+        case KD: k_halo_push<KD><<<nb, 256, 0, s>>>(h, (const double*)x, n_loc, flags); break;
+        case KC: k_halo_push<KC><<<nb, 256, 0, s>>>(h, (const float2*)x, n_loc, flags); break;
+        default: k_halo_push<KZ><<<nb, 256, 0, s>>>(h, (const double2*)x, n_loc, flags); break;
     }
 }
 

@@ -30,7 +30,7 @@ NcclApi* nccl_api() {
     if (!h) { set_error("cannot dlopen libnccl (set LKB_NCCL_LIB): %s", dlerror()); return nullptr; }
 #define LKB_SYM(field, name) *(void**)(&g_nccl.field) = dlsym(h, name); if (!g_nccl.field) { set_error("missing %s", name); return nullptr; }
     LKB_SYM(GetUniqueId, "ncclGetUniqueId") LKB_SYM(CommInitRank, "ncclCommInitRank") LKB_SYM(CommDestroy, "ncclCommDestroy")
-    LKB_SYM(AllReduce, "ncclAllReduce") LKB_SYM(Broadcast, "ncclBroadcast") LKB_SYM(Send, "ncclSend") LKB_SYM(Recv, "ncclRecv")
+    LKB_SYM(AllReduce, "ncclAllReduce") LKB_SYM(Broadcast, "ncclBroadcast") LKB_SYM(AllGather, "ncclAllGather") LKB_SYM(Send, "ncclSend") LKB_SYM(Recv, "ncclRecv")
     LKB_SYM(GroupStart, "ncclGroupStart") LKB_SYM(GroupEnd, "ncclGroupEnd") LKB_SYM(GetErrorString, "ncclGetErrorString")
 #undef LKB_SYM
     g_nccl.handle = h;
@@ -502,6 +502,66 @@ static int stencil_create(lkb_ctx_t c, int kind, int dim, int64_t nx, int64_t ny
         LKB_CUDA(cudaMalloc(&op->halo_hi, op->halo_elems * es));
         if (slow0 > 0) op->st.halo_lo = op->halo_lo;
         if (slow0 + nslow_local < nslow) op->st.halo_hi = op->halo_hi;
+        if (c->p2p_active) {
+            // P2P halo exchange: a double-buffered halo region per rank, mapped into both neighbours with
+            // CUDA IPC (handles all-gathered over the context's NCCL communicator: creation is collective)
+            NcclApi* api = nccl_api();
+            const size_t side = (((size_t)op->halo_elems * es) + 255) & ~(size_t)255;
+            const size_t region = 256 + 4 * side;
+            void* reg = nullptr; void* hbuf = nullptr; unsigned* ctr = nullptr;
+            bool ok = api && cudaMalloc(&reg, region) == cudaSuccess && cudaMemset(reg, 0, region) == cudaSuccess &&
+                      cudaMalloc(&hbuf, 64 * (size_t)(c->world + 1)) == cudaSuccess &&
+                      cudaMalloc((void**)&ctr, 128) == cudaSuccess && cudaMemset(ctr, 0, 128) == cudaSuccess;
+            std::vector<char> all(64 * (size_t)c->world);
+            if (ok) {
+                cudaIpcMemHandle_t hnd;
+                ok = cudaIpcGetMemHandle(&hnd, reg) == cudaSuccess &&
+                     cudaMemcpy((char*)hbuf + 64 * (size_t)c->world, &hnd, 64, cudaMemcpyHostToDevice) == cudaSuccess;
+            }
+            // the all-gather is issued unconditionally so that the ranks stay in step even if one failed locally
+            int okflag = ok ? 1 : 0;
+            if (api && hbuf) {
+                if (api->AllGather((char*)hbuf + 64 * (size_t)c->world, hbuf, 64, /*ncclInt8*/ 0, c->comm, c->stream) != 0) okflag = 0;
+                if (cudaMemcpyAsync(all.data(), hbuf, all.size(), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) okflag = 0;
+                if (cudaStreamSynchronize(c->stream) != cudaSuccess) okflag = 0;
+            } else okflag = 0;
+            const bool has_lo = slow0 > 0, has_hi = slow0 + nslow_local < nslow;
+            if (okflag && has_lo) {
+                cudaIpcMemHandle_t hnd; memcpy(&hnd, &all[64 * (size_t)(c->rank - 1)], 64);
+                if (cudaIpcOpenMemHandle(&op->hp_lo_map, hnd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { okflag = 0; cudaGetLastError(); }
+            }
+            if (okflag && has_hi) {
+                cudaIpcMemHandle_t hnd; memcpy(&hnd, &all[64 * (size_t)(c->rank + 1)], 64);
+                if (cudaIpcOpenMemHandle(&op->hp_hi_map, hnd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { okflag = 0; cudaGetLastError(); }
+            }
+            if (hbuf) cudaFree(hbuf);
+            // every rank must take the same path: agree through one more (tiny) all-reduce-like exchange
+            LKB_TRY(ensure_ws(c, 2));
+            {
+                double v = okflag ? 0.0 : 1.0;
+                cudaMemcpyAsync(c->tmpw, &v, sizeof(double), cudaMemcpyHostToDevice, c->stream);
+                if (api) api->AllReduce(c->tmpw, c->tmpw, 1, 8, 0, c->comm, c->stream);
+                cudaMemcpyAsync(&v, c->tmpw, sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+                cudaStreamSynchronize(c->stream);
+                if (v != 0.0) okflag = 0;
+            }
+            if (okflag) {
+                op->hp.my_region = (char*)reg; op->hp.lo_region = (char*)op->hp_lo_map; op->hp.hi_region = (char*)op->hp_hi_map;
+                op->hp.epoch = ctr; op->hp.ticket = ctr + 16; op->hp.he = op->halo_elems;
+                op->hp.data_off = 256; op->hp.side_bytes = side;
+                op->hp_active = true;
+                if (has_lo) op->st.halo_lo = (char*)reg + 256;              // parity 0, side 0
+                if (has_hi) op->st.halo_hi = (char*)reg + 256 + side;       // parity 0, side 1
+                op->st.halo_epoch = ctr;
+                op->st.halo_parity_stride = (int64_t)(2 * side / es);
+            } else {
+                if (op->hp_lo_map) cudaIpcCloseMemHandle(op->hp_lo_map);
+                if (op->hp_hi_map) cudaIpcCloseMemHandle(op->hp_hi_map);
+                op->hp_lo_map = op->hp_hi_map = nullptr;
+                if (reg) cudaFree(reg);
+                if (ctr) cudaFree(ctr);
+            }
+        }
     }
     const int64_t gy = op->st.ny * op->st.nz;
     if (gy > 2147483647LL) { delete op; set_error("stencil: grid too large for this kernel (%lld row groups)", (long long)gy); return LKB_ERR_ARG; }
@@ -585,6 +645,9 @@ int lkb_op_destroy(lkb_op_t A) {
     if (!A) return LKB_ERR_ARG;
     cudaStreamSynchronize(A->ctx->stream);
     invalidate_graphs(A->ctx, A->uid);
+    if (A->hp_lo_map) cudaIpcCloseMemHandle(A->hp_lo_map);
+    if (A->hp_hi_map) cudaIpcCloseMemHandle(A->hp_hi_map);
+    if (A->hp_active) { cudaFree(A->hp.my_region); cudaFree(A->hp.epoch); }
     void* bufs[] = { A->halo_lo, A->halo_hi, A->rowptr, A->col, A->val, A->t_rowptr, A->t_col, A->t_val, A->a };
     for (void* b : bufs) if (b) cudaFree(b);
     delete A;
@@ -606,7 +669,11 @@ int op_apply_enqueue(lkb_op_s* A, const void* x, void* y, bool trans, const int*
     int nl = 1;
     prof_begin(c, PC_MATVEC);
     if (A->type == 1) {
-        if (c->world > 1) {
+        if (c->world > 1 && A->hp_active) {
+            // halo exchange fused with its synchronisation over NVLink peer memory (k_halo_push)
+            launch_halo_push(A->kind, c->stream, A->hp, x, A->m, flags);
+            nl = 2;
+        } else if (c->world > 1) {
             // halo exchange over NCCL send/recv: my first row/plane -> rank-1's halo_hi, my last -> rank+1's halo_lo
             NcclApi* api = nccl_api();
             if (!api) return LKB_ERR_NCCL;

@@ -21,6 +21,7 @@ struct NcclApi {
     int (*CommDestroy)(void*) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
     int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
@@ -81,6 +82,7 @@ struct lkb_op_s {
     // stencil
     lkb::StencilArgs st; int64_t slow0 = 0, nslow_global = 0;
     void* halo_lo = nullptr; void* halo_hi = nullptr; int64_t halo_elems = 0;
+    lkb::HaloP2P hp; bool hp_active = false; void* hp_lo_map = nullptr; void* hp_hi_map = nullptr;
     // csr (+ explicit transpose for rmatvec)
     int64_t* rowptr = nullptr; int32_t* col = nullptr; void* val = nullptr; int lpr = 8;
     int64_t* t_rowptr = nullptr; int32_t* t_col = nullptr; void* t_val = nullptr; int t_lpr = 8;

@@ -34,7 +34,23 @@ struct StencilArgs {
     const void* halo_lo;       // previous slab's last row/plane (nullptr = Dirichlet boundary)
     const void* halo_hi;       // next slab's first row/plane
     int dim;                   // 2 or 3
+    // p2p halo exchange: halo_lo / halo_hi point at parity 0 of double-buffered regions; the kernel adds
+    // (epoch & 1) * halo_parity_stride elements, epoch being the device counter of the push kernel
+    const unsigned* halo_epoch = nullptr;
+    int64_t halo_parity_stride = 0;
 };
+// P2P halo push (kernels_ops.cu): my first / last `he` elements of x go straight into the neighbours' halo
+// buffers over NVLink; the last CTA signals the neighbours and waits for their pushes.
+struct HaloP2P {
+    char* my_region = nullptr;      // flags[2] (128 B apart) then data[parity][side][he]
+    char* lo_region = nullptr;      // rank-1's region (mapped), nullptr at the domain boundary
+    char* hi_region = nullptr;      // rank+1's region
+    unsigned* epoch = nullptr;      // device counter of pushes (same sequence on every rank)
+    unsigned* ticket = nullptr;
+    int64_t he = 0;                 // halo elements
+    size_t data_off = 256, side_bytes = 0;   // layout
+};
+void launch_halo_push(int kind, cudaStream_t s, const HaloP2P& h, const void* x, int64_t n_loc, const int* flags);
 
 // c[0..j) = V(:, 0:j)^H w, c[j] = w^H w.  Two-stage deterministic reduction; the last CTA to
 // finish folds the stage-1 partials in fixed order into out[0..j].
