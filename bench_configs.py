@@ -58,21 +58,25 @@ def c2_gmres(ctx, full):
 
 
 def c3_eigs(ctx, full):
+    """Config 3: eigs (Krylov-Schur, kdim=128) on the 7-point convection-diffusion operator, z-slabs over the ranks."""
     m = 512 if full else 256
     n = m ** 3
     lk.set_lapack_from_scipy()
-    A = lk.LinOp.stencil7(ctx, "d", m, m, m, CONVDIFF7)
+    A = lk.LinOp.stencil7(ctx, "d", m, m, m, CONVDIFF7)          # slab of this rank (partition over ctx.world)
+    nloc, row0 = A.n, A.row0
     nev, kdim = 8, 128
-    X = lk.Basis(ctx, "d", n, nev)
-    x0 = lk.Vector(ctx, "d", n).fill_random("uniform", 44)
+    X = lk.Basis(ctx, "d", nloc, nev, n_global=n, row0=row0)
+    x0 = lk.Vector(ctx, "d", nloc, n_global=n, row0=row0).fill_random("uniform", 44)
     (res, dt) = timed(ctx, lambda: lk.eigs(A, X, nev, x0=x0, kdim=kdim, tolerance=1e-6))
     ev, resid, info = res
     # residual check of the leading real-pair / real eigenpair on the device
-    y = lk.Vector(ctx, "d", n)
+    y = lk.Vector(ctx, "d", nloc, n_global=n, row0=row0)
     chk = None
     if abs(ev[0].imag) == 0:
         A.matvec(X.col(0), y); y.axpby(-ev[0].real, X.col(0), 1.0); chk = y.norm() / X.col(0).norm()
-    emit(config="C3 eigs(nev=8, kdim=128) 7-pt convection-diffusion %d^3 fp64, 1 GPU" % m, n=n, info_niter=int(info),
+    if ctx.rank != 0:
+        return
+    emit(config="C3 eigs(nev=8, kdim=128) 7-pt convection-diffusion %d^3 fp64, %d GPU(s)" % (m, ctx.world), n=n, info_niter=int(info),
          seconds=dt, arnoldi_steps_per_s=info / dt, eigvals=[[float(z.real), float(z.imag)] for z in ev],
          residuals=[float(r) for r in resid], leading_pair_residual=chk, matvecs=A.counters()[0])
 
@@ -153,14 +157,29 @@ def main():
     ap.add_argument("--full", action="store_true", help="BASELINE.json sizes (C3 512^3, C4 384^3, C5 50Mx40M)")
     ap.add_argument("--only", default="c2,c3,c4,c5")
     args = ap.parse_args()
-    ctx = lk.Context(0)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:                                   # torchrun: only the sharded config (C3) is meaningful
+        import torch
+        import torch.distributed as dist
+        local = int(os.environ["LOCAL_RANK"])
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        ctx = lk.Context.from_torch_distributed(local)
+        args.only = "c3"
+    else:
+        ctx = lk.Context(0)
     for name, fn in (("c2", c2_gmres), ("c3", c3_eigs), ("c4", c4_sym), ("c5", c5_svds)):
         if name in args.only.split(","):
             try:
                 fn(ctx, args.full)
             except Exception as e:                       # keep going: one JSON line per config either way
                 emit(config=name, error=repr(e))
-    ctx.close()
+    ctx.sync()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier(); dist.destroy_process_group()
+    else:
+        ctx.close()
 
 
 if __name__ == "__main__":

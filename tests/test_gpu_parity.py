@@ -567,3 +567,25 @@ def test_fgmres_vs_oracle(lk, ctx, oracle):
     x1 = lk.Vector(ctx, "d", n); x2 = lk.Vector(ctx, "d", n)
     i1, m1 = lk.fgmres(A, b, x1, kdim=20, maxiter=30); i2, m2 = lk.gmres(A, b, x2, kdim=20, maxiter=30)
     assert i1 == i2 and np.array_equal(x1.get(), x2.get())
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_empty_and_wrapped_vectors(lk, ctx, kind):
+    """Edge cases: zero-length vectors (an idle rank of a ragged partition) and lkb_vec_wrap of user memory."""
+    import ctypes as C
+    import torch
+    dt = lk.DTYPES[kind]
+    e1 = lk.Vector(ctx, kind, 0); e2 = lk.Vector(ctx, kind, 0)
+    assert e1.norm() == 0.0 and e1.dot(e2) == 0 and e1.get_size() == 0
+    e1.axpby(2, e2, 3); e1.scal(2); e1.zero()
+    n = 1001
+    tdt = {np.float32: torch.float32, np.float64: torch.float64, np.complex64: torch.complex64, np.complex128: torch.complex128}[dt]
+    t = torch.arange(n, device="cuda").to(tdt) + 1
+    h = C.c_void_p()
+    lk._lib.check(ctx.lib.lkb_vec_wrap(ctx.h, lk.KINDS[kind], n, n, 0, C.c_void_p(t.data_ptr()), C.byref(h)), "wrap")
+    w = lk.Vector(ctx, kind, n, _handle=h)
+    torch.cuda.synchronize()
+    ref = np.sqrt(np.sum(np.arange(1, n + 1, dtype=np.float64) ** 2))
+    assert abs(w.norm() - ref) < (1e-9 if kind in "dz" else 1e-3) * ref
+    w.scal(2); ctx.sync()
+    assert abs(float(t[10].real) - 22.0) < 1e-6                # the user's memory was updated in place
