@@ -81,16 +81,29 @@ class Context:
         dist.broadcast_object_list(obj, src=0)
         ctx = cls(device, rank, world, obj[0])
         if world <= 8 and os.environ.get("LKB_P2P", "1") != "0":
-            # in-kernel NVLink allreduce: exchange CUDA-IPC handles of the per-rank exchange buffers
+            # in-kernel NVLink allreduce: exchange CUDA-IPC handles of the per-rank exchange buffers.
+            # Every step is collective and the ranks agree on the outcome, so a local failure (no peer
+            # access, IPC disabled) downgrades ALL ranks to the NCCL path instead of desynchronising them.
+            ok = 1
             try:
                 mine = ctx.p2p_export()
-                handles = [None] * world
-                dist.all_gather_object(handles, mine)
-                ctx.p2p_attach(b"".join(handles))
+            except LkbError:
+                mine, ok = b"\0" * 64, 0
+            handles = [None] * world
+            dist.all_gather_object(handles, mine)
+            if ok:
+                try:
+                    ctx.p2p_attach(b"".join(handles))
+                except LkbError as e:
+                    ok = 0
+                    import warnings
+                    warnings.warn(f"p2p allreduce unavailable, using NCCL: {e}")
+            flags = [None] * world
+            dist.all_gather_object(flags, ok)
+            if all(flags):
                 ctx.p2p = True
-            except LkbError as e:          # no peer access: stay on the NCCL path
-                import warnings
-                warnings.warn(f"p2p allreduce unavailable, using NCCL: {e}")
+            else:
+                ctx.set_option("p2p", 0)
             dist.barrier()
         return ctx
 
