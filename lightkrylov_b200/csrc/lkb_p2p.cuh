@@ -28,7 +28,18 @@ LKB_DI double2 ld_cv_w(const double2* p) {
 // Called by ALL threads of one CTA.  vals[0..count) (global, W type) holds this rank's sums on
 // entry and the world total on exit.  count <= P2P_SLOT.
 template <typename W>
+LKB_DI void p2p_allreduce_chunk(const P2P& c, W* vals, int count);
+
+// count may exceed the slot size (j + 1 > P2P_SLOT coefficients): processed in slot-sized rounds, one
+// epoch each, identically on every rank.
+template <typename W>
 LKB_DI void p2p_allreduce_cta(const P2P& c, W* vals, int count) {
+    for (int base = 0; base < count; base += P2P_SLOT)
+        p2p_allreduce_chunk<W>(c, vals + base, min((int)P2P_SLOT, count - base));
+}
+
+template <typename W>
+LKB_DI void p2p_allreduce_chunk(const P2P& c, W* vals, int count) {
     __shared__ unsigned s_epoch;
     const int tid = threadIdx.x, nth = blockDim.x;
     if (tid == 0) s_epoch = *c.epoch + 1u;
@@ -68,6 +79,7 @@ LKB_DI void p2p_allreduce_cta(const P2P& c, W* vals, int count) {
         else *reinterpret_cast<double*>(&vals[i]) = a.x;
     }
     if (tid == 0) *c.epoch = ep;
+    __syncthreads();                     // s_epoch may be rewritten by the next round
 }
 
 }  // namespace lkb
