@@ -135,6 +135,119 @@ k_stencil(const typename Tr<K>::E* __restrict__ x, typename Tr<K>::E* __restrict
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Shared-memory halo-staged stencil (default).  One CTA = ST_TX packs in x by RY rows in y.  The CTA
+// first issues ALL its loads -- the (RY+2) x ST_TX tile of plane k including the y-halo rows (from
+// the neighbouring rows, from the inter-GPU halo buffers at slab edges, or zero at the Dirichlet
+// boundary) and, in 3-D, the RY x ST_TX centre rows of planes k-1 / k+1 -- as 16-byte cp.async
+// copies straight into shared memory (RY+2 .. 3RY+2 requests in flight per thread, no register
+// staging), waits once, and then computes the RY output rows from shared memory: north / south /
+// west / east neighbours are shared-memory reads, only the west/east scalar of the tile's edge
+// columns comes from global memory.  Every x element is fetched from L2/HBM once per CTA.
+// ------------------------------------------------------------------------------------------
+enum { ST_TX = 128 };
+
+template <int BYTES> LKB_DI void cp_async(void* smem_dst, const void* gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    if constexpr (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+    else if constexpr (BYTES == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+LKB_DI void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+
+template <int K, int PW, int DIM, int RY>
+__global__ void __launch_bounds__(ST_TX)
+k_stencil_smem(const typename Tr<K>::E* __restrict__ x, typename Tr<K>::E* __restrict__ y,
+               int64_t nx, int64_t ny, int64_t nz, Coef7<typename Tr<K>::E> cf,
+               const typename Tr<K>::E* __restrict__ halo_lo, const typename Tr<K>::E* __restrict__ halo_hi,
+               const unsigned* __restrict__ halo_epoch, int64_t halo_parity_stride, const int* __restrict__ flags)
+{
+    using E = typename Tr<K>::E;
+    using P = Pack<E, PW>;
+    constexpr int PB = PW * (int)sizeof(E);       // payload bytes (Pack is padded to 16 B)
+    if (flags && flags[F_STOP]) return;
+    if (halo_epoch) {
+        const int64_t off = (int64_t)(*halo_epoch & 1u) * halo_parity_stride;
+        if (halo_lo) halo_lo += off;
+        if (halo_hi) halo_hi += off;
+    }
+    extern __shared__ __align__(16) unsigned char st_smem[];
+    P* tile = reinterpret_cast<P*>(st_smem);                       // [(RY+2)][ST_TX]
+    P* dn = tile + (RY + 2) * ST_TX;                               // [RY][ST_TX]  (3-D only)
+    P* up = dn + RY * ST_TX;                                       // [RY][ST_TX]
+    const int tx = threadIdx.x;
+    const int64_t npk_row = nx / PW;
+    const int64_t ip = (int64_t)blockIdx.y * ST_TX + tx;
+    const bool active = ip < npk_row;
+    const int64_t i0 = ip * PW;
+    const int64_t nyb = (ny + RY - 1) / RY;
+    const int64_t k = (DIM == 3) ? (int64_t)blockIdx.x / nyb : 0;
+    const int64_t j0 = ((int64_t)blockIdx.x % nyb) * RY;
+    const int64_t plane = nx * ny;
+    const E* xk = x + k * plane;
+    P zero;
+#pragma unroll
+    for (int e = 0; e < PW; ++e) zero.v[e] = zero_v(E());
+
+    if (active) {
+        // ---- issue every load of the tile ----
+#pragma unroll
+        for (int r = 0; r < RY + 2; ++r) {
+            const int64_t j = j0 - 1 + r;
+            const E* src = nullptr;
+            if (j >= 0 && j < ny) src = xk + j * nx + i0;
+            else if (DIM == 2 && j < 0 && halo_lo) src = halo_lo + i0;
+            else if (DIM == 2 && j >= ny && j == ny && halo_hi) src = halo_hi + i0;
+            if (src && j <= ny) cp_async<PB>(&tile[r * ST_TX + tx], src);
+            else tile[r * ST_TX + tx] = zero;
+        }
+        if (DIM == 3) {
+#pragma unroll
+            for (int r = 0; r < RY; ++r) {
+                const int64_t j = j0 + r;
+                if (j < ny) {
+                    const int64_t p = j * nx + i0;
+                    const E* sd = (k > 0) ? xk + p - plane : (halo_lo ? halo_lo + p : nullptr);
+                    const E* su = (k < nz - 1) ? xk + p + plane : (halo_hi ? halo_hi + p : nullptr);
+                    if (sd) cp_async<PB>(&dn[r * ST_TX + tx], sd); else dn[r * ST_TX + tx] = zero;
+                    if (su) cp_async<PB>(&up[r * ST_TX + tx], su); else up[r * ST_TX + tx] = zero;
+                }
+            }
+        }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    if (!active) return;
+    // ---- compute RY rows out of shared memory ----
+#pragma unroll
+    for (int r = 0; r < RY; ++r) {
+        const int64_t j = j0 + r;
+        if (j >= ny) break;
+        const int64_t p = j * nx + i0;
+        const P center = tile[(r + 1) * ST_TX + tx], south = tile[r * ST_TX + tx], north = tile[(r + 2) * ST_TX + tx];
+        E west, east;
+        if (tx > 0) west = tile[(r + 1) * ST_TX + tx - 1].v[PW - 1];
+        else west = i0 > 0 ? __ldg(xk + p - 1) : zero_v(E());
+        if (tx < ST_TX - 1 && ip + 1 < npk_row) east = tile[(r + 1) * ST_TX + tx + 1].v[0];
+        else east = (i0 + PW < nx) ? __ldg(xk + p + PW) : zero_v(E());
+        P out;
+#pragma unroll
+        for (int e = 0; e < PW; ++e) {
+            E sacc = mul_v(cf.c[0], center.v[e]);
+            fmacc(sacc, (e > 0 ? center.v[e > 0 ? e - 1 : 0] : west), cf.c[1]);
+            fmacc(sacc, (e < PW - 1 ? center.v[e < PW - 1 ? e + 1 : 0] : east), cf.c[2]);
+            fmacc(sacc, south.v[e], cf.c[3]);
+            fmacc(sacc, north.v[e], cf.c[4]);
+            if (DIM == 3) {
+                fmacc(sacc, dn[r * ST_TX + tx].v[e], cf.c[5]);
+                fmacc(sacc, up[r * ST_TX + tx].v[e], cf.c[6]);
+            }
+            out.v[e] = sacc;
+        }
+        PackOps<E, PW>::st(y + k * plane + p, out);
+    }
+}
+
 template <int K, int PW, int DIM>
 static void stencil_launch(cudaStream_t s, const StencilArgs& a, const void* x, void* y, bool trans, const int* flags) {
     using E = typename Tr<K>::E;
@@ -148,9 +261,25 @@ static void stencil_launch(cudaStream_t s, const StencilArgs& a, const void* x, 
     }
     for (int q = 0; q < 7; ++q) from_scalar(c[q], cf.c[q]);
     const int64_t npk_row = a.nx / PW;
-    // RY = 8 rows per CTA, no unrolling, L1-served x-halo: chosen by measurement (profiles/stencil_ab.py,
-    // B200): 5.2 TB/s (2-D 4096^2) / 4.6 TB/s (3-D 384^3); longer marches or 4x-unrolled prefetch were
-    // slower (fewer CTAs in flight), warp-shuffle x-halo made no difference.
+    // Measured on B200 (profiles/stencil_ab.py, fp64): 2-D 4096^2 -- shared-memory kernel RY=8 5.64 TB/s vs
+    // register march 5.24 TB/s; 3-D 384^3 -- shared-memory kernel 2.1-3.0 TB/s (3RY+2 staged rows per CTA cut
+    // the occupancy) vs register march 4.62 TB/s.  Default: shared-memory staging in 2-D, register march in 3-D.
+    static const int variant = getenv("LKB_STENCIL_VARIANT") ? atoi(getenv("LKB_STENCIL_VARIANT")) : (DIM == 2 ? 1 : 0);
+    if (variant >= 1) {
+        // shared-memory halo-staged kernel
+#define LKB_STS(RY_) { const int64_t nyb_ = (a.ny + RY_ - 1) / RY_; \
+            dim3 grid_((unsigned)(nyb_ * (DIM == 3 ? a.nz : 1)), (unsigned)((npk_row + ST_TX - 1) / ST_TX)); \
+            const size_t sh_ = (size_t)((RY_ + 2) + (DIM == 3 ? 2 * RY_ : 0)) * ST_TX * sizeof(Pack<E, PW>); \
+            static const bool once_ = (cudaFuncSetAttribute(k_stencil_smem<K, PW, DIM, RY_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024), true); (void)once_; \
+            k_stencil_smem<K, PW, DIM, RY_><<<grid_, ST_TX, sh_, s>>>((const E*)x, (E*)y, a.nx, a.ny, a.nz, cf, \
+                (const E*)a.halo_lo, (const E*)a.halo_hi, a.halo_epoch, a.halo_parity_stride, flags); }
+        if (variant == 3) LKB_STS(4) else LKB_STS(8)
+#undef LKB_STS
+        return;
+    }
+    // variant 0: register-marching kernel.  RY = 8 rows per CTA, no unrolling, L1-served x-halo
+    // (profiles/stencil_ab.py, B200: 5.2 TB/s 2-D 4096^2 / 4.6 TB/s 3-D 384^3; longer marches or 4x-unrolled
+    // prefetch were slower, warp-shuffle x-halo made no difference).
     constexpr int RY = 8;
     const int64_t nyb = (a.ny + RY - 1) / RY;
     dim3 grid((unsigned)(nyb * (DIM == 3 ? a.nz : 1)), (unsigned)((npk_row + 255) / 256));
