@@ -185,6 +185,170 @@ k_multidot(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j,
 }
 
 // ------------------------------------------------------------------------------------------
+// Block (blksize > 1) Gram-Schmidt: two right-hand sides per sweep of V.
+//   innerprod_matrix / linear_combination_matrix (AbstractVectors.fypp:605-643, 677-695) loop over the p
+//   columns of Y, re-reading X for each; here a pair of columns shares one read of every V pack, so a
+//   block step with p = 2 moves the same bytes as a single-vector step.  Same tile walk, transposing fold
+//   and deterministic two-stage reduction as k_multidot; out / partial are laid out [2][j+1].
+template <int K>
+__global__ void __launch_bounds__(MD_THREADS, 1)
+k_multidot2(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j,
+            const typename Tr<K>::E* __restrict__ w0, const typename Tr<K>::E* __restrict__ w1, int64_t n,
+            typename Tr<K>::W* __restrict__ partial, typename Tr<K>::W* __restrict__ out,
+            unsigned* __restrict__ counter, const int* __restrict__ flags, const P2P p2p)
+{
+    using E = typename Tr<K>::E;
+    using W = typename Tr<K>::W;
+    constexpr int EPP = Tr<K>::EPP;
+    constexpr int CB = MD_CB, PT = 2, NW = MD_THREADS / 32;
+    using P = Pack<E, EPP>;
+    if (flags && flags[F_STOP]) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    W* sacc = reinterpret_cast<W*>(smem_raw);   // [NW][2][jp]
+    __shared__ bool is_last;
+    const int jp = j + 1;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < NW * 2 * jp; i += MD_THREADS) sacc[i] = zero_v(W());
+    __syncthreads();
+    W* myacc = sacc + (size_t)wid * 2 * jp;
+    const int fold_idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    const int64_t npk = n / EPP;
+    constexpr int64_t TILE = (int64_t)MD_THREADS * PT;
+    const int64_t ntiles = (npk + TILE - 1) / TILE;
+    const int64_t tper = (ntiles + gridDim.x - 1) / gridDim.x;
+    const int64_t t0 = (int64_t)blockIdx.x * tper, t1 = min(ntiles, t0 + tper);
+    const int nchunk = (j + CB - 1) / CB;
+    E aw0 = zero_v(E()), aw1 = zero_v(E());
+    for (int64_t t = t0; t < t1; ++t) {
+        const int64_t base = t * TILE + threadIdx.x;
+        P u0[PT], u1[PT];
+#pragma unroll
+        for (int q = 0; q < PT; ++q) {
+            const int64_t pk = base + (int64_t)q * MD_THREADS;
+            if (pk < npk) { u0[q] = ld_pack_nc<P>(w0 + pk * EPP); u1[q] = ld_pack_nc<P>(w1 + pk * EPP); }
+            else {
+#pragma unroll
+                for (int e = 0; e < EPP; ++e) { u0[q].v[e] = zero_v(E()); u1[q].v[e] = zero_v(E()); }
+            }
+#pragma unroll
+            for (int e = 0; e < EPP; ++e) { fma_conj(aw0, u0[q].v[e], u0[q].v[e]); fma_conj(aw1, u1[q].v[e], u1[q].v[e]); }
+        }
+        for (int c = 0; c < nchunk; ++c) {
+            const int c0 = c * CB;
+            const int ncv = min(CB, j - c0);
+            const E* vb = V + (int64_t)c0 * ld;
+            E a0[CB], a1[CB];
+#pragma unroll
+            for (int i = 0; i < CB; ++i) { a0[i] = zero_v(E()); a1[i] = zero_v(E()); }
+#pragma unroll
+            for (int q = 0; q < PT; ++q) {
+                const int64_t pk = base + (int64_t)q * MD_THREADS;
+                if (pk < npk) {
+                    const int64_t off = pk * EPP;
+#pragma unroll
+                    for (int i = 0; i < CB; ++i) {
+                        if (i < ncv) {
+                            const P v = ld_pack_nc<P>(vb + (int64_t)i * ld + off);
+#pragma unroll
+                            for (int e = 0; e < EPP; ++e) { fma_conj(a0[i], v.v[e], u0[q].v[e]); fma_conj(a1[i], v.v[e], u1[q].v[e]); }
+                        }
+                    }
+                }
+            }
+            warp_fold16<E>(a0, lane);
+            warp_fold16<E>(a1, lane);
+            if ((lane & 1) == 0 && fold_idx < ncv) {
+                wadd(myacc[c0 + fold_idx], widen(a0[0]));
+                wadd(myacc[jp + c0 + fold_idx], widen(a1[0]));
+            }
+        }
+    }
+    __syncwarp();
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int64_t r = npk * EPP; r < n; ++r) {
+            const E x0 = w0[r], x1 = w1[r];
+            for (int i = 0; i < j; ++i) {
+                E b0 = zero_v(E()), b1 = zero_v(E());
+                fma_conj(b0, V[(int64_t)i * ld + r], x0); fma_conj(b1, V[(int64_t)i * ld + r], x1);
+                wadd(myacc[i], widen(b0)); wadd(myacc[jp + i], widen(b1));
+            }
+            fma_conj(aw0, x0, x0); fma_conj(aw1, x1, x1);
+        }
+    }
+    {
+        const W b0 = warp_sum(widen(aw0)), b1 = warp_sum(widen(aw1));
+        if (lane == 0) { wadd(myacc[j], b0); wadd(myacc[jp + j], b1); }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * jp; i += MD_THREADS) {
+        W a = sacc[i];
+#pragma unroll
+        for (int q = 1; q < NW; ++q) wadd(a, sacc[(size_t)q * 2 * jp + i]);
+        partial[(int64_t)blockIdx.x * 2 * jp + i] = a;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1u);
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        const int nrb = gridDim.x;
+        for (int col = wid; col < 2 * jp; col += NW) {
+            W a = zero_v(W());
+            for (int b = lane; b < nrb; b += 32) wadd(a, __ldcg(&partial[(int64_t)b * 2 * jp + col]));
+            a = warp_sum(a);
+            if (lane == 0) out[col] = a;
+        }
+        if (threadIdx.x == 0) *counter = 0u;
+        if (p2p.world > 1) p2p_allreduce_cta<W>(p2p, out, 2 * jp);
+    }
+}
+
+// W_q -= V c_q for q = 0, 1 with one read of every V pack; c laid out [2][j+1] (W type).
+template <int K>
+__global__ void __launch_bounds__(256, 2)
+k_multiaxpy2(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j, const typename Tr<K>::W* __restrict__ c,
+             typename Tr<K>::E* __restrict__ w0, typename Tr<K>::E* __restrict__ w1, int64_t n, const int* __restrict__ flags)
+{
+    using E = typename Tr<K>::E;
+    constexpr int EPP = Tr<K>::EPP;
+    using P = Pack<E, EPP>;
+    if (flags && flags[F_STOP]) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    E* cs = reinterpret_cast<E*>(smem_raw);      // [2][j]
+    for (int i = threadIdx.x; i < j; i += blockDim.x) { narrow(c[i], cs[i]); narrow(c[(j + 1) + i], cs[j + i]); }
+    __syncthreads();
+    const int64_t npk = n / EPP;
+    for (int64_t pk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pk < npk; pk += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t off = pk * EPP;
+        P a0 = ld_pack<P>(w0 + off), a1 = ld_pack<P>(w1 + off);
+        const E* vp = V + off;
+        int i = 0;
+        for (; i + 4 <= j; i += 4) {
+            P v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = ld_pack_nc<P>(vp + (int64_t)(i + u) * ld);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int e = 0; e < EPP; ++e) { fnma(a0.v[e], v[u].v[e], cs[i + u]); fnma(a1.v[e], v[u].v[e], cs[j + i + u]); }
+        }
+        for (; i < j; ++i) {
+            const P v = ld_pack_nc<P>(vp + (int64_t)i * ld);
+#pragma unroll
+            for (int e = 0; e < EPP; ++e) { fnma(a0.v[e], v.v[e], cs[i]); fnma(a1.v[e], v.v[e], cs[j + i]); }
+        }
+        st_pack(w0 + off, a0); st_pack(w1 + off, a1);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int64_t t = npk * EPP; t < n; ++t) {
+            E a0 = w0[t], a1 = w1[t];
+            for (int i = 0; i < j; ++i) { fnma(a0, V[(int64_t)i * ld + t], cs[i]); fnma(a1, V[(int64_t)i * ld + t], cs[j + i]); }
+            w0[t] = a0; w1[t] = a1;
+        }
+}
+
+// ------------------------------------------------------------------------------------------
 // dot of two vectors (the `dot` TBP, CG's p^H Ap, Lanczos' 3-term coefficients): the j = 1 case of the
 // multi-dot contract -- out[0] = x^H y, out[1] = y^H y -- as a plain grid-stride kernel with 4 + 4
 // independent 128-bit loads in flight per thread (the chunked multi-dot keeps only 1 of its 16 column
@@ -414,6 +578,52 @@ void launch_multiaxpy(int kind, cudaStream_t s, const void* V, int64_t ld, int j
         case KD: multiaxpy_t<KD>(s, V, ld, j, c, w, n, want_norm, partial, nrm2_out, counter, flags, sms, p2p); break;
         case KC: multiaxpy_t<KC>(s, V, ld, j, c, w, n, want_norm, partial, nrm2_out, counter, flags, sms, p2p); break;
         default: multiaxpy_t<KZ>(s, V, ld, j, c, w, n, want_norm, partial, nrm2_out, counter, flags, sms, p2p); break;
+    }
+}
+
+template <int K>
+static void multidot2_t(cudaStream_t s, const void* V, int64_t ld, int j, const void* w0, const void* w1, int64_t n,
+                        void* partial, void* out, unsigned* counter, const int* flags, int sms, const P2P* p2p) {
+    using E = typename Tr<K>::E; using W = typename Tr<K>::W;
+    const int64_t npk = n / Tr<K>::EPP;
+    const int64_t ntiles = (npk + (int64_t)MD_THREADS * 2 - 1) / ((int64_t)MD_THREADS * 2);
+    int64_t nb = sms;
+    if (nb > ntiles) nb = ntiles;
+    if (nb < 1) nb = 1;
+    const size_t sh = (size_t)(MD_THREADS / 32) * 2 * (size_t)(j + 1) * sizeof(W);
+    static const bool attr_once = (cudaFuncSetAttribute(k_multidot2<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), true);
+    (void)attr_once;
+    k_multidot2<K><<<(int)nb, MD_THREADS, sh, s>>>((const E*)V, ld, j, (const E*)w0, (const E*)w1, n, (W*)partial, (W*)out,
+                                                   counter, flags, p2p ? *p2p : P2P());
+}
+void launch_multidot2(int kind, cudaStream_t s, const void* V, int64_t ld, int j, const void* w0, const void* w1, int64_t n,
+                      void* partial, void* out, unsigned* counter, const int* flags, int sms, const P2P* p2p) {
+    switch (kind) {
+        case KS: multidot2_t<KS>(s, V, ld, j, w0, w1, n, partial, out, counter, flags, sms, p2p); break;
+        case KD: multidot2_t<KD>(s, V, ld, j, w0, w1, n, partial, out, counter, flags, sms, p2p); break;
+        case KC: multidot2_t<KC>(s, V, ld, j, w0, w1, n, partial, out, counter, flags, sms, p2p); break;
+        default: multidot2_t<KZ>(s, V, ld, j, w0, w1, n, partial, out, counter, flags, sms, p2p); break;
+    }
+}
+template <int K>
+static void multiaxpy2_t(cudaStream_t s, const void* V, int64_t ld, int j, const void* c, void* w0, void* w1, int64_t n,
+                         const int* flags, int sms) {
+    using E = typename Tr<K>::E; using W = typename Tr<K>::W;
+    int64_t nb = (n / Tr<K>::EPP + 255) / 256;
+    if (nb < 1) nb = 1;
+    if (nb > 4 * (int64_t)sms) nb = 4 * (int64_t)sms;
+    const size_t sh = (size_t)2 * (j > 0 ? j : 1) * sizeof(E);
+    static const bool attr_once = (cudaFuncSetAttribute(k_multiaxpy2<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024), true);
+    (void)attr_once;
+    k_multiaxpy2<K><<<(int)nb, 256, sh, s>>>((const E*)V, ld, j, (const W*)c, (E*)w0, (E*)w1, n, flags);
+}
+void launch_multiaxpy2(int kind, cudaStream_t s, const void* V, int64_t ld, int j, const void* c, void* w0, void* w1,
+                       int64_t n, const int* flags, int sms) {
+    switch (kind) {
+        case KS: multiaxpy2_t<KS>(s, V, ld, j, c, w0, w1, n, flags, sms); break;
+        case KD: multiaxpy2_t<KD>(s, V, ld, j, c, w0, w1, n, flags, sms); break;
+        case KC: multiaxpy2_t<KC>(s, V, ld, j, c, w0, w1, n, flags, sms); break;
+        default: multiaxpy2_t<KZ>(s, V, ld, j, c, w0, w1, n, flags, sms); break;
     }
 }
 

@@ -60,6 +60,11 @@ void launch_multidot(int kind, cudaStream_t s, const void* V, int64_t ld, int j,
 void launch_multiaxpy(int kind, cudaStream_t s, const void* V, int64_t ld, int j, const void* c, void* w, int64_t n,
                       bool want_norm, void* partial, void* nrm2_out, unsigned* counter, const int* flags, int sms,
                       const P2P* p2p = nullptr);
+// Block Gram-Schmidt, two right-hand sides per sweep of V: out / c are laid out [2][j+1] (W type)
+void launch_multidot2(int kind, cudaStream_t s, const void* V, int64_t ld, int j, const void* w0, const void* w1, int64_t n,
+                      void* partial, void* out, unsigned* counter, const int* flags, int sms, const P2P* p2p = nullptr);
+void launch_multiaxpy2(int kind, cudaStream_t s, const void* V, int64_t ld, int j, const void* c, void* w0, void* w1,
+                       int64_t n, const int* flags, int sms);
 // Fused pass-1 multi-axpy + pass-2 multi-dot (TMA + mbarrier pipeline, kernels_fused.cu):
 //   w -= V c1 ; out[0..j) = V^H w_new ; out[j] = w_new^H w_new.   Returns false when the shape is not
 //   supported (j > 128, ragged n, unaligned) -- the caller then runs the two separate kernels.

@@ -466,8 +466,40 @@ static int arnoldi_block(lkb_op_t A, lkb_basis_t X, void* H, int ldh, int32_t* i
             LKB_TRY(op_apply_enqueue(A, col_ptr(X, kpm + i), col_ptr(X, kp + i), trans, nullptr));
             if (trans) A->n_rmatvec++; else A->n_matvec++;
         }
-        for (int i = 0; i < p; ++i) {
+        for (int i = 0; i < p; i += 2) {
             LKB_TRY(reset_flags(c));
+            if (i + 1 < p) {
+                // two block columns per sweep of the basis (k_multidot2 / k_multiaxpy2): c laid out [2][kp+1]
+                const int jp = kp + 1;
+                const size_t wsz = kind_cplx(kind) ? 16 : 8;
+                const size_t nd = (size_t)2 * jp * (kind_cplx(kind) ? 2 : 1);
+                LKB_TRY(ensure_ws(c, 2 * jp));
+                void* w0 = col_ptr(X, kp + i); void* w1 = col_ptr(X, kp + i + 1);
+                for (int pass = 0; pass < 2; ++pass) {
+                    void* cb = pass == 0 ? c->c1 : c->c2;
+                    prof_begin(c, PC_DOT);
+                    launch_multidot2(kind, c->stream, X->d, X->ld, kp, w0, w1, X->n, c->partial, cb, c->counter, nullptr, c->sms, c->p2p_arg());
+                    prof_end(c, PC_DOT, 1);
+                    LKB_TRY(allreduce_w(c, cb, nd));
+                    prof_begin(c, PC_AXPY);
+                    launch_multiaxpy2(kind, c->stream, X->d, X->ld, kp, cb, w0, w1, X->n, nullptr, c->sms);
+                    prof_end(c, PC_AXPY, 1);
+                    LKB_TRY(check_launch(c, "block gram-schmidt"));
+                }
+                LKB_TRY(ensure_hstage(c, 4 * (size_t)jp * 16 + 4096));
+                char* hs = (char*)c->hstage;
+                LKB_CUDA(cudaMemcpyAsync(hs, c->c1, 2 * (size_t)jp * wsz, cudaMemcpyDeviceToHost, c->stream));
+                LKB_CUDA(cudaMemcpyAsync(hs + 2 * (size_t)jp * wsz, c->c2, 2 * (size_t)jp * wsz, cudaMemcpyDeviceToHost, c->stream));
+                LKB_CUDA(cudaStreamSynchronize(c->stream));
+                for (int q = 0; q < 2; ++q)
+                    for (int r = 0; r < kp; ++r) {
+                        const double* a = (const double*)(hs + ((size_t)q * jp + r) * wsz);
+                        const double* b = (const double*)(hs + (2 * (size_t)jp + (size_t)q * jp + r) * wsz);
+                        Scalar v{a[0] + b[0], kind_cplx(kind) ? a[1] + b[1] : 0.0};
+                        scalar_store(kind, v, (char*)H + ((size_t)r + (size_t)ldh * (kpm + i + q)) * es);
+                    }
+                continue;
+            }
             LKB_TRY(dgs_enqueue(c, kind, X->d, X->ld, kp, col_ptr(X, kp + i), X->n, c->flags, false, true));
             LKB_TRY(fetch_coeffs(c, kind, kp, true, col, nullptr, hf));
             for (int r = 0; r < kp; ++r)

@@ -287,9 +287,11 @@ def test_arnoldi_breakdown_invariant_subspace(lk, ctx, oracle, kind):
     assert A.counters()[0] == 3
 
 
-def test_arnoldi_block_p2(lk, ctx, oracle):
-    """TestKrylov.fypp:244-296: block Arnoldi p=2, kdim=64 on n=128, vs oracle."""
-    n, p, kdim = 128, 2, 64
+@pytest.mark.parametrize("p,kdim", [(2, 64), (3, 40), (4, 30)])
+def test_arnoldi_block(lk, ctx, oracle, p, kdim):
+    """TestKrylov.fypp:244-296: block Arnoldi on n=128 vs oracle (p = 2 is the reference's case; pairs of
+    block columns share one sweep of the basis, an odd column falls back to the single-vector kernels)."""
+    n = 128
     rng = np.random.default_rng(2)
     Ah = randn(rng, (n, n), np.float64) / np.sqrt(n)
     X0 = randn(rng, (n, p), np.float64); oracle.qr(X0)
