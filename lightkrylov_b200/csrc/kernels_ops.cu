@@ -346,8 +346,8 @@ k_halo_push(HaloP2P h, const typename Tr<K>::E* __restrict__ x, int64_t n_loc, c
         __threadfence_system();
         if (h.lo_region) st_volatile_u32(reinterpret_cast<unsigned*>(h.lo_region + 128), ep);   // "upper neighbour pushed"
         if (h.hi_region) st_volatile_u32(reinterpret_cast<unsigned*>(h.hi_region), ep);         // "lower neighbour pushed"
-        if (h.lo_region) while ((int)(ld_volatile_u32(reinterpret_cast<const unsigned*>(h.my_region)) - ep) < 0) { }
-        if (h.hi_region) while ((int)(ld_volatile_u32(reinterpret_cast<const unsigned*>(h.my_region + 128)) - ep) < 0) { }
+        if (h.lo_region) spin_until(reinterpret_cast<const unsigned*>(h.my_region), ep);
+        if (h.hi_region) spin_until(reinterpret_cast<const unsigned*>(h.my_region + 128), ep);
         __threadfence_system();
         *h.ticket = 0u;
         *h.epoch = ep;

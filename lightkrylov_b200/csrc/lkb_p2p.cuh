@@ -19,6 +19,14 @@ LKB_DI unsigned ld_volatile_u32(const unsigned* p) {
 LKB_DI void st_volatile_u32(unsigned* p, unsigned v) {
     asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// Spin until *f reaches epoch ep.  A peer that died (or a collective entered by only some ranks) must not
+// hang the GPU: after ~30 s of spinning the kernel traps, which surfaces as a CUDA launch failure on the host.
+LKB_DI void spin_until(const unsigned* f, unsigned ep) {
+    const long long t0 = clock64();
+    while ((int)(ld_volatile_u32(f) - ep) < 0) {
+        if (clock64() - t0 > 60000000000LL) { asm volatile("trap;"); }
+    }
+}
 LKB_DI double2 ld_cv_w(const double2* p) {
     double2 v;
     asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
@@ -62,8 +70,7 @@ LKB_DI void p2p_allreduce_chunk(const P2P& c, W* vals, int count) {
     // 2. raise my flag in every rank, 3. wait for every rank's flag in my region
     if (tid < c.world) st_volatile_u32(reinterpret_cast<unsigned*>(c.peer[tid] + (size_t)c.rank * 128), ep);
     if (tid < c.world) {
-        const unsigned* f = reinterpret_cast<const unsigned*>(c.peer[c.rank] + (size_t)tid * 128);
-        while ((int)(ld_volatile_u32(f) - ep) < 0) { }
+        spin_until(reinterpret_cast<const unsigned*>(c.peer[c.rank] + (size_t)tid * 128), ep);
     }
     __syncthreads();
     __threadfence_system();
