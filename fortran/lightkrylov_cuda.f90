@@ -88,6 +88,23 @@ module lightkrylov_cuda
             integer(c_int), value :: ldh; integer(c_int32_t), intent(out) :: info
             integer(c_int32_t), value :: kstart, kend, transpose, blksize; real(c_double), value :: tol
         end function
+        integer(c_int) function lkb_bidiag(A, U, V, B, ldb, info, kstart, kend, tol) bind(C, name='lkb_bidiag')
+            import; type(c_ptr), value :: A, U, V; real(c_double), intent(inout) :: B(ldb, *)
+            integer(c_int), value :: ldb; integer(c_int32_t), intent(out) :: info
+            integer(c_int32_t), value :: kstart, kend; real(c_double), value :: tol
+        end function
+        integer(c_int) function lkb_dgs_step(X, j, W, wcol0, p, chk, beta, ldbeta, info) bind(C, name='lkb_dgs_step')
+            import; type(c_ptr), value :: X, W, beta; integer(c_int), value :: j, wcol0, p, ldbeta
+            integer(c_int32_t), value :: chk; integer(c_int32_t), intent(out) :: info
+        end function
+        integer(c_int) function lkb_gmres(A, b, x, info, rtol, atol, transpose, io) bind(C, name='lkb_gmres')
+            import; type(c_ptr), value :: A, b, x, io; integer(c_int32_t), intent(out) :: info
+            real(c_double), value :: rtol, atol; integer(c_int32_t), value :: transpose
+        end function
+        integer(c_int) function lkb_cg(A, b, x, info, rtol, atol, io) bind(C, name='lkb_cg')
+            import; type(c_ptr), value :: A, b, x, io; integer(c_int32_t), intent(out) :: info
+            real(c_double), value :: rtol, atol
+        end function
         integer(c_int) function lkb_lanczos(A, X, T, ldt, info, kstart, kend, tol) bind(C, name='lkb_lanczos')
             import; type(c_ptr), value :: A, X; real(c_double), intent(inout) :: T(ldt, *)
             integer(c_int), value :: ldt; integer(c_int32_t), intent(out) :: info
@@ -126,7 +143,22 @@ module lightkrylov_cuda
         procedure, pass(self), public :: rmatvec => stencil_rmatvec_rdp
     end type
 
-    public :: cuda_basis_create_rdp, arnoldi_cuda_rdp, lanczos_cuda_rdp
+    !> C mirrors of gmres_dp_opts + gmres_dp_metadata / cg_dp_opts + cg_dp_metadata (lkb_gmres_io, lkb_cg_io)
+    type, bind(C), public :: lkb_gmres_io
+        integer(c_int32_t) :: kdim = 30, maxiter = 10
+        integer(c_int32_t) :: n_iter = 0, n_inner = 0, n_outer = 0, converged = 0, info = 0
+        type(c_ptr) :: res = c_null_ptr
+        integer(c_int32_t) :: res_cap = 0, res_len = 0
+    end type
+    type, bind(C), public :: lkb_cg_io
+        integer(c_int32_t) :: maxiter = 100
+        integer(c_int32_t) :: n_iter = 0, converged = 0, info = 0
+        type(c_ptr) :: res = c_null_ptr
+        integer(c_int32_t) :: res_cap = 0, res_len = 0
+    end type
+
+    public :: cuda_basis_create_rdp, arnoldi_cuda_rdp, lanczos_cuda_rdp, bidiagonalization_cuda_rdp
+    public :: dgs_cuda_rdp, gmres_cuda_rdp, cg_cuda_rdp
 
 contains
 
@@ -288,6 +320,92 @@ contains
         Tc = T
         call chk(lkb_lanczos(A%h, X%h, Tc, int(size(Tc, 1), c_int), cinfo, ks, ke, ctol), 'lkb_lanczos')
         T = Tc; info = cinfo
+    end subroutine
+
+    !> bidiagonalization(A, U, V, B, info, kstart, kend, tol)   BaseKrylov.fypp:311-330
+    subroutine bidiagonalization_cuda_rdp(A, U, V, B, info, kstart, kend, tol)
+        class(cuda_stencil5_rdp), intent(inout) :: A
+        type(cuda_basis_rdp), intent(inout) :: U, V
+        real(dp), intent(inout) :: B(:, :)
+        integer, intent(out) :: info
+        integer, optional, intent(in) :: kstart, kend
+        real(dp), optional, intent(in) :: tol
+        integer(c_int32_t) :: ks, ke, cinfo
+        real(c_double) :: ctol
+        real(dp), allocatable :: Bc(:, :)
+        ks = 0; ke = 0; ctol = -1.0_c_double
+        if (present(kstart)) ks = kstart
+        if (present(kend)) ke = kend
+        if (present(tol)) ctol = tol
+        Bc = B
+        call chk(lkb_bidiag(A%h, U%h, V%h, Bc, int(size(Bc, 1), c_int), cinfo, ks, ke, ctol), 'lkb_bidiag')
+        B = Bc; info = cinfo
+    end subroutine
+
+    !> double_gram_schmidt_step(y, X(:j), info, if_chk_orthonormal, beta) with y = W%X(iw)   BaseKrylov.fypp:679-709
+    subroutine dgs_cuda_rdp(W, iw, X, j, info, if_chk_orthonormal, beta)
+        type(cuda_basis_rdp), intent(inout) :: W
+        type(cuda_basis_rdp), intent(in) :: X
+        integer, intent(in) :: iw, j
+        integer, intent(out) :: info
+        logical, optional, intent(in) :: if_chk_orthonormal
+        real(dp), optional, target, intent(out) :: beta(:)
+        integer(c_int32_t) :: cinfo, chkflag
+        type(c_ptr) :: pbeta
+        chkflag = 1; if (present(if_chk_orthonormal)) chkflag = merge(1, 0, if_chk_orthonormal)   ! default .true.
+        pbeta = c_null_ptr
+        if (present(beta)) then
+            if (size(beta) /= j) call stop_error('beta has the wrong shape', this_module, 'dgs_cuda_rdp')  ! assert_shape
+            pbeta = c_loc(beta)
+        end if
+        call chk(lkb_dgs_step(X%h, int(j, c_int), W%h, int(iw - 1, c_int), 1_c_int, chkflag, pbeta, int(max(j, 1), c_int), cinfo), &
+                 'lkb_dgs_step')
+        info = cinfo
+    end subroutine
+
+    !> gmres(A, b, x, info, rtol, atol, options) -- options%kdim / %maxiter as in gmres_dp_opts
+    subroutine gmres_cuda_rdp(A, b, x, info, rtol, atol, kdim, maxiter, transpose, n_iter, converged)
+        class(cuda_stencil5_rdp), intent(inout) :: A
+        type(cuda_vector_rdp), intent(in) :: b
+        type(cuda_vector_rdp), intent(inout) :: x
+        integer, intent(out) :: info
+        real(dp), optional, intent(in) :: rtol, atol
+        integer, optional, intent(in) :: kdim, maxiter
+        logical, optional, intent(in) :: transpose
+        integer, optional, intent(out) :: n_iter
+        logical, optional, intent(out) :: converged
+        type(lkb_gmres_io), target :: io
+        real(c_double) :: r, a
+        integer(c_int32_t) :: tr, cinfo
+        r = -1.0_c_double; a = -1.0_c_double; tr = 0
+        if (present(rtol)) r = rtol
+        if (present(atol)) a = atol
+        if (present(kdim)) io%kdim = kdim
+        if (present(maxiter)) io%maxiter = maxiter
+        if (present(transpose)) tr = merge(1, 0, transpose)
+        call chk(lkb_gmres(A%h, b%h, x%h, cinfo, r, a, tr, c_loc(io)), 'lkb_gmres')
+        info = cinfo                                  ! +n_iter converged / -n_iter not (gmres.fypp:234-238)
+        if (present(n_iter)) n_iter = io%n_iter
+        if (present(converged)) converged = io%converged /= 0
+    end subroutine
+
+    !> cg(A, b, x, info, rtol, atol, options)
+    subroutine cg_cuda_rdp(A, b, x, info, rtol, atol, maxiter)
+        class(cuda_stencil5_rdp), intent(inout) :: A
+        type(cuda_vector_rdp), intent(in) :: b
+        type(cuda_vector_rdp), intent(inout) :: x
+        integer, intent(out) :: info
+        real(dp), optional, intent(in) :: rtol, atol
+        integer, optional, intent(in) :: maxiter
+        type(lkb_cg_io), target :: io
+        real(c_double) :: r, a
+        integer(c_int32_t) :: cinfo
+        r = -1.0_c_double; a = -1.0_c_double
+        if (present(rtol)) r = rtol
+        if (present(atol)) a = atol
+        if (present(maxiter)) io%maxiter = maxiter
+        call chk(lkb_cg(A%h, b%h, x%h, cinfo, r, a, c_loc(io)), 'lkb_cg')
+        info = cinfo
     end subroutine
 
 end module lightkrylov_cuda

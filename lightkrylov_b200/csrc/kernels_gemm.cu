@@ -6,7 +6,7 @@
 // svd_solvers.fypp:113-119), which the reference performs as k*p separate axpby sweeps.
 // Row-local (no collective).  Each thread owns one 16-byte pack of rows and PB output columns in
 // registers; X is streamed once per group of PB outputs with 128-bit loads, Z is broadcast from
-// shared memory.  fp64 FMA rate needed at PB = 8 is ~13 TFLOP/s at full HBM speed, below the
+// shared memory.  PB = 16 (real) / 8 (complex) keeps the fp64 FMA rate needed at full HBM speed below the
 // B200 fp64 pipe, so this stays HBM-bound without tensor cores (a DMMA variant is a later row).
 #include "lkb_kernels.h"
 
@@ -78,7 +78,9 @@ template <int K>
 static void gemm_t(cudaStream_t s, const void* X, int64_t ldx, int k, const void* Z, int ldz, int p, void* Y,
                    int64_t ldy, int64_t n, int sms) {
     using E = typename Tr<K>::E;
-    constexpr int PB = 8;
+    // output columns per sweep of X: 16 for the real kinds (2 * 16 FMA per 16-byte pack = 26 TFLOP/s fp64 at
+    // full HBM speed, ~70 % of the B200 fp64 pipe), 8 for the complex kinds (4 FMA per complex multiply-add)
+    constexpr int PB = Tr<K>::cplx ? 8 : 16;
     const int64_t npk = n / Tr<K>::EPP;
     int64_t nb = (npk + 255) / 256;
     if (nb < 1) nb = 1;
