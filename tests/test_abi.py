@@ -99,3 +99,15 @@ def test_c_client_runs_on_gpu(so_path, tmp_path):
     r = subprocess.run([exe, "1024"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "info=0" in r.stdout
+
+
+def test_fortran_shim_binds_only_exported_symbols(so_path):
+    """The ISO_C_BINDING shim cannot be compiled here (no Fortran compiler): at least every bind(C) name it
+    uses must be an entry point of include/lkb.h that liblkb.so exports."""
+    src = open(os.path.join(ROOT, "fortran", "lightkrylov_cuda.f90")).read()
+    names = set(re.findall(r"bind\(C,\s*name='(lkb_[a-z0-9_]+)'\)", src))
+    assert len(names) >= 20
+    lib = ctypes.CDLL(so_path)
+    declared = set(_declared_symbols())
+    assert names <= declared, names - declared
+    assert all(hasattr(lib, n) for n in names)
