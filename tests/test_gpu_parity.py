@@ -591,3 +591,69 @@ def test_empty_and_wrapped_vectors(lk, ctx, kind):
     assert abs(w.norm() - ref) < (1e-9 if kind in "dz" else 1e-3) * ref
     w.scal(2); ctx.sync()
     assert abs(float(t[10].real) - 22.0) < 1e-6                # the user's memory was updated in place
+
+
+# ---------------------------------------------------------------------------------------------
+# remaining entry points of the boundary: user-callback operator, one-pass orthogonalisation,
+# lincomb_sub, clone, seeded rand
+# ---------------------------------------------------------------------------------------------
+def test_callback_operator_in_arnoldi(lk, ctx, oracle):
+    """A user-written device matvec (abstract_linop extension) plugged in through lkb_op_callback_create."""
+    import torch
+    n, kdim = 4096, 24
+    dh = 1.0 + oracle.fill(n, "d", "uniform", 5)                       # A = diag(d) + shift-by-one coupling
+    dd = torch.from_numpy(dh).cuda()
+    ext = torch.cuda.ExternalStream(ctx.stream)
+    calls = []
+
+    def matvec(xp, yp, trans, stream):
+        calls.append(trans)
+        with torch.cuda.stream(ext):
+            x = torch.as_tensor(_DevArray(xp, n, "<f8"), device="cuda")
+            y = torch.as_tensor(_DevArray(yp, n, "<f8"), device="cuda")
+            torch.mul(x, dd, out=y)
+            if trans:
+                y[:-1] += 0.5 * x[1:]
+            else:
+                y[1:] += 0.5 * x[:-1]
+        return 0
+
+    Ad = np.diag(dh) + 0.5 * np.diag(np.ones(n - 1), -1)
+    x0 = oracle.fill(n, "d", "uniform", 6); oracle.normalize(x0)
+    for trans in (False, True):
+        A = lk.LinOp.callback(ctx, "d", n, n, matvec, capturable=False)
+        X = lk.Basis(ctx, "d", n, kdim + 1).put(x0)
+        H = np.zeros((kdim + 1, kdim), order="F")
+        assert lk.arnoldi(A, X, H, transpose=trans) == 0
+        Xo = np.zeros((n, kdim + 1), order="F"); Xo[:, 0] = x0; Ho = np.zeros_like(H)
+        assert oracle.arnoldi(oracle.Op.dense(np.asfortranarray(Ad)), Xo, Ho, trans=trans) == 0
+        assert rel_normwise(H, Ho) < 1e-10
+        assert A.counters() == ((0, kdim) if trans else (kdim, 0))
+    assert calls.count(0) == kdim and calls.count(1) == kdim
+
+
+@pytest.mark.parametrize("kind", ["d", "z"])
+def test_orthogonalize_one_pass_lincomb_sub_clone(lk, ctx, oracle, kind):
+    dt = lk.DTYPES[kind]; n, j, p = 5003, 9, 3
+    rng = np.random.default_rng(3)
+    Q, _ = np.linalg.qr(randn(rng, (n, j), dt).astype(np.complex128 if kind == "z" else np.float64))
+    Xh = np.asfortranarray(Q.astype(dt)); Wh = randn(rng, (n, p), dt)
+    X = lk.Basis(ctx, kind, n, j).put(Xh); W = lk.Basis(ctx, kind, n, p).put(Wh)
+    info, beta = lk.orthogonalize_against_basis(W, 0, p, X, j, if_chk_orthonormal=True)
+    ref_beta = Xh.conj().T @ Wh
+    assert info == 0 and rel_normwise(beta, ref_beta) < 1e-12
+    assert rel_normwise(W.get(), Wh - Xh @ ref_beta) < 1e-12                  # one CGS pass (gram_schmidt.fypp:156-200)
+    W.put(Wh)
+    X.lincomb_sub(j, ref_beta, W, 0)                                           # linear_combination + sub
+    assert rel_normwise(W.get(), Wh - Xh @ ref_beta) < 1e-12
+    v = X.col(2); c = v.clone(); c.scal(3.0)
+    assert np.array_equal(v.get(), Xh[:, 2]) and np.allclose(c.get(), 3.0 * Xh[:, 2])   # deep copy
+
+
+def test_rand_is_seeded_and_reproducible(lk, ctx):
+    ctx.set_seed(123)
+    a = lk.Vector(ctx, "d", 1000).rand().get(); b = lk.Vector(ctx, "d", 1000).rand().get()
+    ctx.set_seed(123)
+    a2 = lk.Vector(ctx, "d", 1000).rand().get()
+    assert np.array_equal(a, a2) and not np.array_equal(a, b)
+    assert abs(a.mean()) < 0.15 and abs(a.std() - 1.0) < 0.1
