@@ -287,6 +287,8 @@ int lkb_set_seed(lkb_ctx_t c, uint64_t seed) { c->seed = seed; c->seed_calls = 0
 int lkb_set_graphs(lkb_ctx_t c, int enable) { c->graphs = enable != 0; return 0; }
 int lkb_set_option(lkb_ctx_t c, const char* name, int value) {
     if (!c || !name) return LKB_ERR_ARG;
+    cudaStreamSynchronize(c->stream);
+    invalidate_graphs(c, 0);          // cached step graphs were captured with the previous settings
     if (!strcmp(name, "graphs")) c->graphs = value != 0;
     else if (!strcmp(name, "fused")) c->fused = value != 0;
     else if (!strcmp(name, "p2p")) c->p2p_active = (value != 0) && c->p2p.world > 1;
