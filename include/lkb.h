@@ -116,6 +116,12 @@ int lkb_op_stencil7_create(lkb_ctx_t ctx, int kind, int64_t nx, int64_t ny, int6
                            int64_t slow0, int64_t nslow_local, lkb_op_t* A);
 int lkb_op_csr_create(lkb_ctx_t ctx, int kind, int64_t m, int64_t n, const int64_t* rowptr, const int32_t* col,
                       const void* val, lkb_op_t* A);
+/* Row-sharded CSR (collective): this rank owns rows [row0, row0+m_local) with GLOBAL column indices; vectors of
+ * the column space are sharded as [col0, col0+n_local).  matvec gathers x over the ranks, rmatvec reduces the
+ * partial A_loc^H u_loc onto the owners (NCCL over NVLink). */
+int lkb_op_csr_create_dist(lkb_ctx_t ctx, int kind, int64_t m_global, int64_t n_global, int64_t row0, int64_t m_local,
+                           int64_t col0, int64_t n_local, const int64_t* rowptr_local, const int32_t* col_global,
+                           const void* val, lkb_op_t* A);
 int lkb_op_dense_create(lkb_ctx_t ctx, int kind, int64_t m, int64_t n, const void* a_colmajor, lkb_op_t* A);
 /* user-supplied device matvec (a Fortran/C extension of abstract_linop): fn launches on `stream` */
 typedef int (*lkb_matvec_fn)(void* user, const void* x_dev, void* y_dev, int32_t trans, void* stream);

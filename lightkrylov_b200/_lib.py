@@ -80,6 +80,7 @@ SIGNATURES = {
     "lkb_op_stencil5_create": (_i, [_vp, _i, _i64, _i64, _vp, _i64, _i64, _P(_vp)]),
     "lkb_op_stencil7_create": (_i, [_vp, _i, _i64, _i64, _i64, _vp, _i64, _i64, _P(_vp)]),
     "lkb_op_csr_create": (_i, [_vp, _i, _i64, _i64, _vp, _vp, _vp, _P(_vp)]),
+    "lkb_op_csr_create_dist": (_i, [_vp, _i, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _P(_vp)]),
     "lkb_op_dense_create": (_i, [_vp, _i, _i64, _i64, _vp, _P(_vp)]),
     "lkb_op_callback_create": (_i, [_vp, _i, _i64, _i64, MATVEC_FN, _vp, _i32, _P(_vp)]),
     "lkb_op_destroy": (_i, [_vp]),

@@ -322,6 +322,23 @@ class LinOp:
         return op
 
     @classmethod
+    def csr_dist(cls, ctx: Context, m: int, n: int, rowptr_local, col_global, val, row_slab=None, col_slab=None) -> "LinOp":
+        """Row-sharded CSR: this rank passes ITS rows (local rowptr, global column indices).  Collective."""
+        kind = kind_of(val.dtype)
+        r0, ml = row_slab if row_slab is not None else partition(m, ctx.world, ctx.rank)
+        c0, nl = col_slab if col_slab is not None else partition(n, ctx.world, ctx.rank)
+        rp = np.ascontiguousarray(rowptr_local, dtype=np.int64); ci = np.ascontiguousarray(col_global, dtype=np.int32)
+        va = np.ascontiguousarray(val)
+        assert rp.size == ml + 1
+        h = C.c_void_p()
+        check(ctx.lib.lkb_op_csr_create_dist(ctx.h, KINDS[kind], m, n, r0, ml, c0, nl, rp.ctypes.data, ci.ctypes.data,
+                                             va.ctypes.data, C.byref(h)), "csr_dist")
+        op = cls(ctx, kind, h, ml, nl)
+        op.row0, op.n_global = c0, n            # layout of the column-space vectors
+        op.out_row0, op.m_global = r0, m        # layout of the row-space vectors
+        return op
+
+    @classmethod
     def dense(cls, ctx: Context, A: np.ndarray) -> "LinOp":
         kind = kind_of(A.dtype)
         Af = np.asfortranarray(A)

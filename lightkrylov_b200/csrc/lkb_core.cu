@@ -30,7 +30,7 @@ NcclApi* nccl_api() {
     if (!h) { set_error("cannot dlopen libnccl (set LKB_NCCL_LIB): %s", dlerror()); return nullptr; }
 #define LKB_SYM(field, name) *(void**)(&g_nccl.field) = dlsym(h, name); if (!g_nccl.field) { set_error("missing %s", name); return nullptr; }
     LKB_SYM(GetUniqueId, "ncclGetUniqueId") LKB_SYM(CommInitRank, "ncclCommInitRank") LKB_SYM(CommDestroy, "ncclCommDestroy")
-    LKB_SYM(AllReduce, "ncclAllReduce") LKB_SYM(Broadcast, "ncclBroadcast") LKB_SYM(AllGather, "ncclAllGather") LKB_SYM(Send, "ncclSend") LKB_SYM(Recv, "ncclRecv")
+    LKB_SYM(AllReduce, "ncclAllReduce") LKB_SYM(Broadcast, "ncclBroadcast") LKB_SYM(AllGather, "ncclAllGather") LKB_SYM(Reduce, "ncclReduce") LKB_SYM(Send, "ncclSend") LKB_SYM(Recv, "ncclRecv")
     LKB_SYM(GroupStart, "ncclGroupStart") LKB_SYM(GroupEnd, "ncclGroupEnd") LKB_SYM(GetErrorString, "ncclGetErrorString")
 #undef LKB_SYM
     g_nccl.handle = h;
@@ -583,43 +583,90 @@ static int pick_lpr(int64_t nnz, int64_t rows) {
     const double avg = rows > 0 ? (double)nnz / (double)rows : 0.0;
     return avg >= 48 ? 32 : (avg >= 24 ? 16 : (avg >= 10 ? 8 : 4));
 }
-int lkb_op_csr_create(lkb_ctx_t c, int kind, int64_t m, int64_t n, const int64_t* rowptr, const int32_t* col,
-                      const void* val, lkb_op_t* A) {
-    if (!c || !A || !rowptr || m < 1 || n < 1) return LKB_ERR_ARG;
-    if (c->world > 1) { set_error("csr operators are single-rank in this round (SURVEY 8e: allgather/reduce-scatter path is next)"); return LKB_ERR_ARG; }
-    cudaSetDevice(c->dev);
-    const int64_t nnz = rowptr[m];
+// rows = local rows of A, ncols_index = size of the column index space (global n for a sharded operator)
+static int csr_build(lkb_ctx_t c, lkb_op_s* op, int kind, int64_t rows, int64_t ncols_index, const int64_t* rowptr,
+                     const int32_t* col, const void* val) {
+    const int64_t nnz = rowptr[rows];
     const size_t es = kind_size(kind);
-    lkb_op_s* op = new lkb_op_s();
-    op->ctx = c; op->type = 3; op->kind = kind; op->m = m; op->n = n; op->uid = next_uid();
-    op->lpr = pick_lpr(nnz, m); op->t_lpr = pick_lpr(nnz, n);
-    LKB_CUDA(cudaMalloc((void**)&op->rowptr, (m + 1) * sizeof(int64_t)));
+    op->lpr = pick_lpr(nnz, rows); op->t_lpr = pick_lpr(nnz, ncols_index);
+    LKB_CUDA(cudaMalloc((void**)&op->rowptr, (rows + 1) * sizeof(int64_t)));
     LKB_CUDA(cudaMalloc((void**)&op->col, std::max<int64_t>(nnz, 1) * sizeof(int32_t)));
     LKB_CUDA(cudaMalloc(&op->val, std::max<int64_t>(nnz, 1) * es));
-    LKB_CUDA(cudaMemcpy(op->rowptr, rowptr, (m + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
+    LKB_CUDA(cudaMemcpy(op->rowptr, rowptr, (rows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
     LKB_CUDA(cudaMemcpy(op->col, col, nnz * sizeof(int32_t), cudaMemcpyHostToDevice));
     LKB_CUDA(cudaMemcpy(op->val, val, nnz * es, cudaMemcpyHostToDevice));
     // explicit transpose (counting sort, host) so that rmatvec is a gather, not an atomic scatter
-    std::vector<int64_t> trp(n + 1, 0);
+    std::vector<int64_t> trp(ncols_index + 1, 0);
     for (int64_t q = 0; q < nnz; ++q) trp[col[q] + 1]++;
-    for (int64_t j = 0; j < n; ++j) trp[j + 1] += trp[j];
+    for (int64_t j = 0; j < ncols_index; ++j) trp[j + 1] += trp[j];
     std::vector<int32_t> tcol(std::max<int64_t>(nnz, 1));
     std::vector<char> tval((size_t)std::max<int64_t>(nnz, 1) * es);
     {
         std::vector<int64_t> pos(trp.begin(), trp.end() - 1);
-        for (int64_t i = 0; i < m; ++i)
+        for (int64_t i = 0; i < rows; ++i)
             for (int64_t q = rowptr[i]; q < rowptr[i + 1]; ++q) {
                 const int64_t d = pos[col[q]]++;
                 tcol[d] = (int32_t)i;
                 memcpy(&tval[(size_t)d * es], (const char*)val + (size_t)q * es, es);
             }
     }
-    LKB_CUDA(cudaMalloc((void**)&op->t_rowptr, (n + 1) * sizeof(int64_t)));
+    LKB_CUDA(cudaMalloc((void**)&op->t_rowptr, (ncols_index + 1) * sizeof(int64_t)));
     LKB_CUDA(cudaMalloc((void**)&op->t_col, std::max<int64_t>(nnz, 1) * sizeof(int32_t)));
     LKB_CUDA(cudaMalloc(&op->t_val, std::max<int64_t>(nnz, 1) * es));
-    LKB_CUDA(cudaMemcpy(op->t_rowptr, trp.data(), (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
+    LKB_CUDA(cudaMemcpy(op->t_rowptr, trp.data(), (ncols_index + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
     LKB_CUDA(cudaMemcpy(op->t_col, tcol.data(), nnz * sizeof(int32_t), cudaMemcpyHostToDevice));
     LKB_CUDA(cudaMemcpy(op->t_val, tval.data(), nnz * es, cudaMemcpyHostToDevice));
+    return 0;
+}
+int lkb_op_csr_create(lkb_ctx_t c, int kind, int64_t m, int64_t n, const int64_t* rowptr, const int32_t* col,
+                      const void* val, lkb_op_t* A) {
+    if (!c || !A || !rowptr || m < 1 || n < 1) return LKB_ERR_ARG;
+    if (c->world > 1) { set_error("lkb_op_csr_create is single-rank; use lkb_op_csr_create_dist for a row-sharded matrix"); return LKB_ERR_ARG; }
+    cudaSetDevice(c->dev);
+    lkb_op_s* op = new lkb_op_s();
+    op->ctx = c; op->type = 3; op->kind = kind; op->m = m; op->n = n; op->uid = next_uid();
+    int r = csr_build(c, op, kind, m, n, rowptr, col, val);
+    if (r) { lkb_op_destroy(op); return r; }
+    *A = op;
+    return 0;
+}
+// Row-sharded CSR: this rank owns rows [row0, row0+m_local) of the m_global x n_global matrix with
+// GLOBAL column indices; input vectors of matvec are sharded over the column space as [col0, col0+n_local).
+//   matvec : all ranks' slabs of x are gathered into a full-length buffer (grouped ncclBroadcast, ragged slabs
+//            allowed), then the local SpMV runs;   rmatvec: the local A_loc^H u_loc contributes to all n_global
+//            entries, each slab is summed onto its owner (grouped ncclReduce).  Creation is collective.
+int lkb_op_csr_create_dist(lkb_ctx_t c, int kind, int64_t m_global, int64_t n_global, int64_t row0, int64_t m_local,
+                           int64_t col0, int64_t n_local, const int64_t* rowptr_local, const int32_t* col_global,
+                           const void* val, lkb_op_t* A) {
+    if (!c || !A || !rowptr_local || m_local < 0 || n_local < 0 || m_global < 1 || n_global < 1) return LKB_ERR_ARG;
+    cudaSetDevice(c->dev);
+    const size_t es = kind_size(kind);
+    lkb_op_s* op = new lkb_op_s();
+    op->ctx = c; op->type = 3; op->kind = kind; op->m = m_local; op->n = n_local; op->uid = next_uid();
+    op->dist = true; op->m_global = m_global; op->n_global = n_global;
+    int r = csr_build(c, op, kind, m_local, n_global, rowptr_local, col_global, val);
+    if (r) { lkb_op_destroy(op); return r; }
+    // every rank's slab of the column and row spaces
+    const int W = c->world;
+    op->col_off.assign(W, 0); op->col_cnt.assign(W, 0); op->row_off.assign(W, 0); op->row_cnt.assign(W, 0);
+    if (W == 1) {
+        op->col_off[0] = col0; op->col_cnt[0] = n_local; op->row_off[0] = row0; op->row_cnt[0] = m_local;
+    } else {
+        NcclApi* api = nccl_api();
+        if (!api) { lkb_op_destroy(op); return LKB_ERR_NCCL; }
+        void* dbuf = nullptr;
+        LKB_CUDA(cudaMalloc(&dbuf, 32 * (size_t)(W + 1)));
+        const int64_t mine[4] = {col0, n_local, row0, m_local};
+        LKB_CUDA(cudaMemcpy((char*)dbuf + 32 * (size_t)W, mine, 32, cudaMemcpyHostToDevice));
+        LKB_NCCL(api->AllGather((char*)dbuf + 32 * (size_t)W, dbuf, 32, /*ncclInt8*/ 0, c->comm, c->stream));
+        std::vector<int64_t> all(4 * (size_t)W);
+        LKB_CUDA(cudaMemcpyAsync(all.data(), dbuf, 32 * (size_t)W, cudaMemcpyDeviceToHost, c->stream));
+        LKB_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(dbuf);
+        for (int q = 0; q < W; ++q) { op->col_off[q] = all[4 * q]; op->col_cnt[q] = all[4 * q + 1]; op->row_off[q] = all[4 * q + 2]; op->row_cnt[q] = all[4 * q + 3]; }
+    }
+    LKB_CUDA(cudaMalloc(&op->x_full, std::max<size_t>((size_t)n_global * es, 16)));
+    LKB_CUDA(cudaMalloc(&op->y_full, std::max<size_t>((size_t)n_global * es, 16)));
     *A = op;
     return 0;
 }
@@ -650,7 +697,7 @@ int lkb_op_destroy(lkb_op_t A) {
     if (A->hp_lo_map) cudaIpcCloseMemHandle(A->hp_lo_map);
     if (A->hp_hi_map) cudaIpcCloseMemHandle(A->hp_hi_map);
     if (A->hp_active) { cudaFree(A->hp.my_region); cudaFree(A->hp.epoch); }
-    void* bufs[] = { A->halo_lo, A->halo_hi, A->rowptr, A->col, A->val, A->t_rowptr, A->t_col, A->t_val, A->a };
+    void* bufs[] = { A->halo_lo, A->halo_hi, A->rowptr, A->col, A->val, A->t_rowptr, A->t_col, A->t_val, A->a, A->x_full, A->y_full };
     for (void* b : bufs) if (b) cudaFree(b);
     delete A;
     return 0;
@@ -696,6 +743,36 @@ int op_apply_enqueue(lkb_op_s* A, const void* x, void* y, bool trans, const int*
             LKB_NCCL(api->GroupEnd());
         }
         launch_stencil(A->kind, c->stream, A->st, x, y, trans, flags, c->sms);
+    } else if (A->type == 3 && A->dist) {
+        const int dt = (A->kind == KS || A->kind == KC) ? 7 : 8;            // ncclFloat32 / ncclFloat64
+        const size_t per = kind_cplx(A->kind) ? 2 : 1;
+        NcclApi* api = c->world > 1 ? nccl_api() : nullptr;
+        if (c->world > 1 && !api) return LKB_ERR_NCCL;
+        if (!trans) {
+            // gather every rank's slab of x at its true offset (ragged slabs), then the local SpMV
+            if (c->world > 1) {
+                LKB_NCCL(api->GroupStart());
+                for (int q = 0; q < c->world; ++q) {
+                    void* dst = (char*)A->x_full + (size_t)A->col_off[q] * es;
+                    LKB_NCCL(api->Broadcast(q == c->rank ? x : dst, dst, (size_t)A->col_cnt[q] * per, dt, q, c->comm, c->stream));
+                }
+                LKB_NCCL(api->GroupEnd());
+            } else {
+                LKB_CUDA(cudaMemcpyAsync((char*)A->x_full + (size_t)A->col_off[0] * es, x, (size_t)A->n * es, cudaMemcpyDeviceToDevice, c->stream));
+            }
+            launch_csr(A->kind, c->stream, A->m, A->rowptr, A->col, A->val, A->x_full, y, false, flags, c->sms | (A->lpr << 16));
+        } else {
+            // local A_loc^H u_loc over the whole column space, then every slab is summed onto its owner
+            launch_csr(A->kind, c->stream, A->n_global, A->t_rowptr, A->t_col, A->t_val, x, A->y_full, true, flags, c->sms | (A->t_lpr << 16));
+            if (c->world > 1) {
+                LKB_NCCL(api->GroupStart());
+                for (int q = 0; q < c->world; ++q)
+                    LKB_NCCL(api->Reduce((char*)A->y_full + (size_t)A->col_off[q] * es, y, (size_t)A->col_cnt[q] * per, dt, /*ncclSum*/ 0, q, c->comm, c->stream));
+                LKB_NCCL(api->GroupEnd());
+            } else {
+                LKB_CUDA(cudaMemcpyAsync(y, (char*)A->y_full + (size_t)A->col_off[0] * es, (size_t)A->n * es, cudaMemcpyDeviceToDevice, c->stream));
+            }
+        }
     } else if (A->type == 3) {
         if (!trans) launch_csr(A->kind, c->stream, A->m, A->rowptr, A->col, A->val, x, y, false, flags, c->sms | (A->lpr << 16));
         else launch_csr(A->kind, c->stream, A->n, A->t_rowptr, A->t_col, A->t_val, x, y, true, flags, c->sms | (A->t_lpr << 16));

@@ -22,6 +22,7 @@ struct NcclApi {
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*Reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t) = nullptr;
     int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
@@ -86,6 +87,10 @@ struct lkb_op_s {
     // csr (+ explicit transpose for rmatvec)
     int64_t* rowptr = nullptr; int32_t* col = nullptr; void* val = nullptr; int lpr = 8;
     int64_t* t_rowptr = nullptr; int32_t* t_col = nullptr; void* t_val = nullptr; int t_lpr = 8;
+    // row-sharded csr: full-length gather / scatter buffers and every rank's (offset, count) of the column and row spaces
+    bool dist = false; int64_t m_global = 0, n_global = 0;
+    void* x_full = nullptr; void* y_full = nullptr;
+    std::vector<int64_t> col_off, col_cnt, row_off, row_cnt;
     // dense
     void* a = nullptr;
     // callback

@@ -100,6 +100,32 @@ def main():
         assert np.abs(ev[:, None] - evo[None, :]).min(axis=1).max() < 1e-10 * np.abs(evo).max()
         evho, _, _, kho = lo.eighs(lo.Op.stencil("d", dims, L7), n3, nev, lo.fill(n3, "d", "uniform", 44), kdim=40, tolerance=1e-8)
         assert hinfo == kho and np.abs(evh - evho).max() < 1e-10 * np.abs(evho).max()
+    # ---- row-sharded random CSR (config-5 shaped): matvec gathers x, rmatvec reduces onto the owners ----
+    from helpers import random_csr
+    for kind in ("d", "z"):
+        dt = lk.DTYPES[kind]
+        m5, n5, kd5 = 903, 701, 16                   # ragged slabs on purpose
+        S = random_csr(np.random.default_rng(46), m5, n5, 12, dt)
+        r0, ml = lk.partition(m5, world, rank); c0, nl = lk.partition(n5, world, rank)
+        ip = S.indptr
+        Ac = lk.LinOp.csr_dist(ctx, m5, n5, ip[r0:r0 + ml + 1] - ip[r0], S.indices[ip[r0]:ip[r0 + ml]],
+                               S.data[ip[r0]:ip[r0 + ml]].astype(dt))
+        xg = lo.fill(n5, kind, "normal", 3); ug = lo.fill(m5, kind, "normal", 4)
+        xv = lk.Vector(ctx, kind, nl, n_global=n5, row0=c0).put(xg[c0:c0 + nl])
+        uv = lk.Vector(ctx, kind, ml, n_global=m5, row0=r0).put(ug[r0:r0 + ml])
+        yv = lk.Vector(ctx, kind, ml, n_global=m5, row0=r0); vv = lk.Vector(ctx, kind, nl, n_global=n5, row0=c0)
+        Ac.matvec(xv, yv); Ac.rmatvec(uv, vv)
+        assert np.allclose(yv.get(), (S @ xg)[r0:r0 + ml], rtol=1e-12, atol=1e-12)
+        assert np.allclose(vv.get(), (S.conj().T @ ug)[c0:c0 + nl], rtol=1e-12, atol=1e-12)
+        U5 = lk.Basis(ctx, kind, ml, kd5 + 1, n_global=m5, row0=r0); V5 = lk.Basis(ctx, kind, nl, kd5 + 1, n_global=n5, row0=c0)
+        u0 = U5.col(0).fill_random("normal", 47); u0.scal(1.0 / u0.norm())
+        B5 = np.zeros((kd5 + 1, kd5), dtype=dt, order="F")
+        binfo = lk.bidiagonalization(Ac, U5, V5, B5)
+        if rank == 0:
+            Uo = np.zeros((m5, kd5 + 1), dtype=dt, order="F"); Uo[:, 0] = lo.fill(m5, kind, "normal", 47); lo.normalize(Uo[:, 0])
+            Vo = np.zeros((n5, kd5 + 1), dtype=dt, order="F"); Bo = np.zeros_like(B5)
+            assert binfo == lo.bidiag(lo.Op.csr(m5, n5, S.indptr, S.indices, S.data.astype(dt)), Uo, Vo, Bo) == 0
+            assert rel_normwise(B5, Bo) < 1e-10
     if rank == 0:
         Xo = np.zeros((n3, kd + 1), order="F"); Xo[:, 0] = lo.fill(n3, "d", "uniform", 45); lo.normalize(Xo[:, 0])
         To = np.zeros_like(T)
