@@ -110,13 +110,13 @@ def main():
         ip = S.indptr
         Ac = lk.LinOp.csr_dist(ctx, m5, n5, ip[r0:r0 + ml + 1] - ip[r0], S.indices[ip[r0]:ip[r0 + ml]],
                                S.data[ip[r0]:ip[r0 + ml]].astype(dt))
-        xg = lo.fill(n5, kind, "normal", 3); ug = lo.fill(m5, kind, "normal", 4)
-        xv = lk.Vector(ctx, kind, nl, n_global=n5, row0=c0).put(xg[c0:c0 + nl])
-        uv = lk.Vector(ctx, kind, ml, n_global=m5, row0=r0).put(ug[r0:r0 + ml])
-        yv = lk.Vector(ctx, kind, ml, n_global=m5, row0=r0); vv = lk.Vector(ctx, kind, nl, n_global=n5, row0=c0)
-        Ac.matvec(xv, yv); Ac.rmatvec(uv, vv)
-        assert np.allclose(yv.get(), (S @ xg)[r0:r0 + ml], rtol=1e-12, atol=1e-12)
-        assert np.allclose(vv.get(), (S.conj().T @ ug)[c0:c0 + nl], rtol=1e-12, atol=1e-12)
+        x5g = lo.fill(n5, kind, "normal", 3); u5g = lo.fill(m5, kind, "normal", 4)
+        x5v = lk.Vector(ctx, kind, nl, n_global=n5, row0=c0).put(x5g[c0:c0 + nl])
+        u5v = lk.Vector(ctx, kind, ml, n_global=m5, row0=r0).put(u5g[r0:r0 + ml])
+        y5v = lk.Vector(ctx, kind, ml, n_global=m5, row0=r0); v5v = lk.Vector(ctx, kind, nl, n_global=n5, row0=c0)
+        Ac.matvec(x5v, y5v); Ac.rmatvec(u5v, v5v)
+        assert np.allclose(y5v.get(), (S @ x5g)[r0:r0 + ml], rtol=1e-12, atol=1e-12)
+        assert np.allclose(v5v.get(), (S.conj().T @ u5g)[c0:c0 + nl], rtol=1e-12, atol=1e-12)
         U5 = lk.Basis(ctx, kind, ml, kd5 + 1, n_global=m5, row0=r0); V5 = lk.Basis(ctx, kind, nl, kd5 + 1, n_global=n5, row0=c0)
         u0 = U5.col(0).fill_random("normal", 47); u0.scal(1.0 / u0.norm())
         B5 = np.zeros((kd5 + 1, kd5), dtype=dt, order="F")
