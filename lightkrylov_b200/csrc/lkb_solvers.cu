@@ -91,13 +91,18 @@ static int gmres_impl(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, doubl
     LKB_TRY(vec_norm_sync(c, kind, b->d, b->n, &bnorm));
     const double tol = atol + rtol * bnorm;
 
-    lkb_basis_t V = nullptr;
-    LKB_TRY(lkb_basis_create(c, kind, b->n, b->n_global, b->row0, kdim + 1, &V));
+    lkb_basis_t V = nullptr, Z = nullptr;
     lkb_vec_t dx = nullptr, wrk = nullptr;
-    lkb_basis_t Z = nullptr;
-    LKB_TRY(lkb_vec_create(c, kind, b->n, b->n_global, b->row0, &dx));
-    if (precond && !flexible) LKB_TRY(lkb_vec_create(c, kind, b->n, b->n_global, b->row0, &wrk));
-    if (flexible) LKB_TRY(lkb_basis_create(c, kind, b->n, b->n_global, b->row0, kdim, &Z));
+    {
+        int ra = lkb_basis_create(c, kind, b->n, b->n_global, b->row0, kdim + 1, &V);
+        if (!ra) ra = lkb_vec_create(c, kind, b->n, b->n_global, b->row0, &dx);
+        if (!ra && precond && !flexible) ra = lkb_vec_create(c, kind, b->n, b->n_global, b->row0, &wrk);
+        if (!ra && flexible) ra = lkb_basis_create(c, kind, b->n, b->n_global, b->row0, kdim, &Z);
+        if (ra) {      // release whatever was allocated before the failure
+            if (V) lkb_basis_destroy(V); if (dx) lkb_vec_destroy(dx); if (wrk) lkb_vec_destroy(wrk); if (Z) lkb_basis_destroy(Z);
+            return ra;
+        }
+    }
     std::vector<cd> H((size_t)(kdim + 1) * kdim), e(kdim + 1), cs(kdim), sn(kdim), y(kdim);
     std::vector<Scalar> col;
     const Scalar one{1, 0}, mone{-1, 0};
@@ -238,10 +243,16 @@ static int cg_impl(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, double r
     LKB_TRY(vec_norm_sync(c, kind, b->d, b->n, &bnorm));
     const double tol = atol + rtol * bnorm;
     lkb_vec_t r = nullptr, p = nullptr, Ap = nullptr, z = nullptr;
-    LKB_TRY(lkb_vec_create(c, kind, b->n, b->n_global, b->row0, &r));
-    LKB_TRY(lkb_vec_create(c, kind, b->n, b->n_global, b->row0, &p));
-    LKB_TRY(lkb_vec_create(c, kind, b->n, b->n_global, b->row0, &Ap));
-    if (precond) LKB_TRY(lkb_vec_create(c, kind, b->n, b->n_global, b->row0, &z));
+    {
+        int ra = lkb_vec_create(c, kind, b->n, b->n_global, b->row0, &r);
+        if (!ra) ra = lkb_vec_create(c, kind, b->n, b->n_global, b->row0, &p);
+        if (!ra) ra = lkb_vec_create(c, kind, b->n, b->n_global, b->row0, &Ap);
+        if (!ra && precond) ra = lkb_vec_create(c, kind, b->n, b->n_global, b->row0, &z);
+        if (ra) {
+            if (r) lkb_vec_destroy(r); if (p) lkb_vec_destroy(p); if (Ap) lkb_vec_destroy(Ap); if (z) lkb_vec_destroy(z);
+            return ra;
+        }
+    }
     int rc = 0;
     auto cleanup = [&](int rr) { lkb_vec_destroy(r); lkb_vec_destroy(p); lkb_vec_destroy(Ap); if (z) lkb_vec_destroy(z); return rr; };
     // z = r ; preconditioner%apply(z)   (CG.fypp:113-114, 137)
