@@ -144,12 +144,20 @@ def cpu_arnoldi_sample(nx, ny, kdim, nsteps, threads):
     return kdim / total, spent, desc
 
 
+def host_threads() -> int:
+    """All the host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which must not shrink the CPU arm)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import lk_oracle as lo
-    threads = lo.max_threads()
+    threads = host_threads()
     vals = []
     desc = ""
     nsample = max(3, min(args.cpu_sample_steps, 8))
@@ -321,8 +329,7 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import lk_oracle as lo
-        thr = lo.max_threads()
+        thr = host_threads()
         v_all, _, desc = cpu_arnoldi_sample(nx, ny, kdim, args.cpu_sample_steps, thr)
         v_one, _, desc1 = cpu_arnoldi_sample(nx, ny, kdim, 4, 1)
         cpu = {"value": v_all, "unit": UNIT, "cores": thr, "kind": "port", "sample": desc,
