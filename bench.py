@@ -276,8 +276,9 @@ def run_ours(args):
         step_e2e()
         ms_e2e = timed(step_e2e, args.steps)
     e2e_value = args.steps * kdim / (ms_e2e * 1e-3)
-    h2d = nloc * 8
-    d2h = (kdim + 1) * kdim * 8 + 32 + 2 * 16      # H columns + flags + norm scalars
+    # whole-job bytes per bench step: every rank uploads its slab of the start vector and reads back H + flags
+    h2d = n * 8
+    d2h = world * ((kdim + 1) * kdim * 8 + 32 + 2 * 16)
 
     # ---- per-kernel-class device time: separate profiled pass (events on the launching stream) ---
     peak, peak_src = load_peaks()
