@@ -323,7 +323,7 @@ def run_ours(args):
                 "alg_bytes_per_launch_avg": algb[dom] / nl, "avg_launch_ms": kernels[dom]["ms_total"] / nl,
                 "peak_source": peak_src,
                 "how": "separate profiled factorisation in the same process: CUDA events on the context stream around "
-                       "every launch of the class (graphs off), algorithmic bytes summed over the 2*kdim launches"}
+                       "every launch of the class (graphs off), algorithmic bytes summed over the launches of the class (kdim with the fused CGS2 kernel, 2*kdim without)"}
     # whole-step roofline with the official per-step bytes (matvec + 4*j*n*s), per GPU
     total_alg = sum(alg_bytes_step(j, nloc) for j in range(1, kdim + 1))
     step_gbs = total_alg * args.steps / (ms_total * 1e-3) / 1e9
