@@ -263,7 +263,9 @@ static void stencil_launch(cudaStream_t s, const StencilArgs& a, const void* x, 
     const int64_t npk_row = a.nx / PW;
     // Measured on B200 (profiles/stencil_ab.py, fp64): 2-D 4096^2 -- shared-memory kernel RY=8 5.64 TB/s vs
     // register march 5.24 TB/s; 3-D 384^3 -- shared-memory kernel 2.1-3.0 TB/s (3RY+2 staged rows per CTA cut
-    // the occupancy) vs register march 4.62 TB/s.  Default: shared-memory staging in 2-D, register march in 3-D.
+    // the occupancy) vs register march 4.62 TB/s; a z-march with the plane staged in shared memory (two block
+    // barriers per plane) reached only 2.8 TB/s and was dropped.  Default: shared-memory staging in 2-D,
+    // register march in 3-D.
     static const int variant = getenv("LKB_STENCIL_VARIANT") ? atoi(getenv("LKB_STENCIL_VARIANT")) : (DIM == 2 ? 1 : 0);
     if (variant >= 1) {
         // shared-memory halo-staged kernel
