@@ -323,6 +323,78 @@ k_cg_direction(const typename Tr<K>::W* __restrict__ scal, const typename Tr<K>:
 }
 
 // ------------------------------------------------------------------------------------------
+// GMRES column update on the device (gmres.fypp:167-194 + submodule_utility_functions.fypp:169-204): after the
+// CGS2 kernels of inner step k this single CTA forms H(:k,k) = c1 + c2 and H(k+1,k) = ||w||, decides the
+// scaling (`abs(H(k+1,k)) > tol`), applies the stored Givens rotations to the new column, generates the new
+// rotation, updates the right-hand side e, appends |e(k+1)| to the residual history and raises the stop flag
+// when it drops below tol.  With it a whole restart cycle is one CUDA graph; inner steps enqueued after the
+// converged one are no-ops.  H / e / c / s live on the device as double2 (real kinds use .x), rounded through
+// the kind's precision at the same points as the host shell.
+LKB_DI double2 rnd_kind(double2 v, bool single) {
+    return single ? make_double2((double)(float)v.x, (double)(float)v.y) : v;
+}
+LKB_DI double2 cmul2(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+template <int K>
+__global__ void k_gmres_update(const typename Tr<K>::W* __restrict__ c1, const typename Tr<K>::W* __restrict__ c2, int k,
+                               const typename Tr<K>::W* __restrict__ nrm2, double2* __restrict__ H, int ldh,
+                               double2* __restrict__ e, double2* __restrict__ cs, double2* __restrict__ sn, double tol,
+                               double* __restrict__ inv_dev, int* __restrict__ flags, double* __restrict__ res_hist)
+{
+    constexpr bool cplx = Tr<K>::cplx;
+    constexpr bool single = (K == KS || K == KC);
+    if (flags[F_STOP]) return;
+    extern __shared__ double2 gh[];                       // h(0..k)
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        double2 a = as_w2(c1[i]); const double2 b = as_w2(c2[i]);
+        a.x += b.x; a.y += b.y;
+        if (!cplx) a.y = 0.0;
+        gh[i] = rnd_kind(a, single);
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const double beta = sqrt(fabs(wreal(nrm2[0])));
+    gh[k] = rnd_kind(make_double2(beta, 0.0), single);
+    *inv_dev = beta > tol ? 1.0 / beta : 1.0;
+    if (!cplx) {
+        for (int j = 0; j < k - 1; ++j) {                  // lasr('L','V','F')
+            const double t = gh[j + 1].x;
+            gh[j + 1].x = cs[j].x * t - sn[j].x * gh[j].x;
+            gh[j].x = sn[j].x * t + cs[j].x * gh[j].x;
+        }
+        const double f = gh[k - 1].x, g = gh[k].x;         // LAPACK 3.10 lartg
+        double cc, ss, r;
+        if (g == 0.0) { cc = 1.0; ss = 0.0; r = f; }
+        else if (f == 0.0) { cc = 0.0; ss = g > 0 ? 1.0 : -1.0; r = fabs(g); }
+        else { const double d = hypot(f, g); cc = fabs(f) / d; r = copysign(d, f); ss = g / r; }
+        cs[k - 1] = make_double2(cc, 0.0); sn[k - 1] = make_double2(ss, 0.0);
+        gh[k - 1] = make_double2(r, 0.0); gh[k] = make_double2(0.0, 0.0);
+    } else {
+        for (int i = 0; i < k - 1; ++i) {
+            const double2 a = cmul2(cs[i], gh[i]), b = cmul2(sn[i], gh[i + 1]);
+            const double2 t = make_double2(a.x + b.x, a.y + b.y);
+            const double2 p = cmul2(sn[i], gh[i]), q = cmul2(cs[i], gh[i + 1]);
+            gh[i + 1] = make_double2(q.x - p.x, q.y - p.y);
+            gh[i] = t;
+        }
+        const double nrm = sqrt(gh[k - 1].x * gh[k - 1].x + gh[k - 1].y * gh[k - 1].y + gh[k].x * gh[k].x + gh[k].y * gh[k].y);
+        cs[k - 1] = make_double2(gh[k - 1].x / nrm, gh[k - 1].y / nrm);
+        sn[k - 1] = make_double2(gh[k].x / nrm, gh[k].y / nrm);
+        const double2 a = cmul2(cs[k - 1], gh[k - 1]), b = cmul2(sn[k - 1], gh[k]);
+        gh[k - 1] = make_double2(a.x + b.x, a.y + b.y);
+        gh[k] = make_double2(0.0, 0.0);
+    }
+    for (int i = 0; i <= k; ++i) H[i + (size_t)ldh * (k - 1)] = rnd_kind(gh[i], single);
+    const double2 ek = e[k - 1];
+    const double2 m = cmul2(sn[k - 1], ek);
+    e[k] = rnd_kind(make_double2(-m.x, -m.y), single);
+    e[k - 1] = rnd_kind(cmul2(cs[k - 1], ek), single);
+    const double res = sqrt(e[k].x * e[k].x + e[k].y * e[k].y);
+    res_hist[k] = res;
+    flags[5] = k;
+    if (res < tol) { flags[F_STOP] = 1; flags[F_INFO] = k; }
+}
+
+// ------------------------------------------------------------------------------------------
 #define LKB_DISPATCH(kind, ...)                                \
     switch (kind) {                                            \
         case KS: { constexpr int K = KS; __VA_ARGS__; } break; \
@@ -394,6 +466,14 @@ void launch_cg_direction(int kind, cudaStream_t s, const void* scal, const void*
     LKB_DISPATCH(kind, {
         using E = typename Tr<K>::E; using W = typename Tr<K>::W;
         k_cg_direction<K><<<ew_grid(n / Tr<K>::EPP, sms), 256, 0, s>>>((const W*)scal, (const E*)r, (E*)p, n, flags);
+    });
+}
+void launch_gmres_update(int kind, cudaStream_t s, const void* c1, const void* c2, int k, const void* nrm2, void* H, int ldh,
+                         void* e, void* cs, void* sn, double tol, void* inv_dev, int* flags, double* res_hist) {
+    LKB_DISPATCH(kind, {
+        using W = typename Tr<K>::W;
+        k_gmres_update<K><<<1, 128, (size_t)(k + 1) * sizeof(double2), s>>>((const W*)c1, (const W*)c2, k, (const W*)nrm2, (double2*)H, ldh,
+                                                                             (double2*)e, (double2*)cs, (double2*)sn, tol, (double*)inv_dev, flags, res_hist);
     });
 }
 void launch_gsinfo(cudaStream_t s, const void* ww, int, double atol, int* flags) {

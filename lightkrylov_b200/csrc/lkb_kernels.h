@@ -87,6 +87,10 @@ void launch_cg_update(int kind, cudaStream_t s, const void* scal, const void* pA
 void launch_cg_check(int kind, cudaStream_t s, void* scal, const void* rr_new, double tol, int maxiter, double* res_hist, int* flags);
 void launch_cg_direction(int kind, cudaStream_t s, const void* scal, const void* r, void* p, int64_t n, const int* flags, int sms);
 
+// GMRES column update + Givens + convergence flag on the device (H / e / cs / sn are double2 arrays)
+void launch_gmres_update(int kind, cudaStream_t s, const void* c1, const void* c2, int k, const void* nrm2, void* H, int ldh,
+                         void* e, void* cs, void* sn, double tol, void* inv_dev, int* flags, double* res_hist);
+
 // Hessenberg / tridiagonal / bidiagonal column update (one tiny CTA).
 //   mode 0 arnoldi (qr_no_pivoting p=1 + breakdown test), 1 lanczos (< tol), 2 bidiag (<= tol), 3 plain norm
 void launch_update(int kind, cudaStream_t s, const void* c1, const void* c2, int j, const void* nrm2, void* hcol,

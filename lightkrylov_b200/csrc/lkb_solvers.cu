@@ -129,6 +129,47 @@ static int gmres_impl(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, doubl
         return check_launch(c, "gmres residual");
     };
 
+    // Without a preconditioner the whole inner cycle runs on the device (graph-captured once per call)
+    const bool device_cycle = !precond && !flexible;
+    void* gH = nullptr; void* ge = nullptr; double* gres = nullptr;
+    cudaGraphExec_t cycle_exec = nullptr; int64_t cycle_launches = 0;
+    auto cleanup_dev = [&]() { cudaStreamSynchronize(c->stream); if (cycle_exec) cudaGraphExecDestroy(cycle_exec); if (gH) cudaFree(gH); if (ge) cudaFree(ge); if (gres) cudaFree(gres); };
+    auto enqueue_cycle = [&]() -> int {
+        char* gcs = (char*)ge + (size_t)(kdim + 1) * 16; char* gsn = gcs + (size_t)kdim * 16;
+        for (int kk = 1; kk <= kdim; ++kk) {
+            void* w = col_ptr(V, kk);
+            LKB_TRY(op_apply_enqueue(A, col_ptr(V, kk - 1), w, trans, c->flags));
+            LKB_TRY(dgs_enqueue(c, kind, V->d, V->ld, kk, w, b->n, c->flags, true, false));
+            prof_begin(c, PC_OTHER);
+            launch_gmres_update(kind, c->stream, c->c1, c->c2, kk, c->nrm2, gH, kdim + 1, ge, gcs, gsn, tol, c->inv, c->flags, gres);
+            launch_scale_dev(kind, c->stream, w, b->n, c->inv, c->flags, kk, c->sms);
+            prof_end(c, PC_OTHER, 2);
+            LKB_TRY(check_launch(c, "gmres update"));
+        }
+        return 0;
+    };
+    if (device_cycle) {
+        if (cudaMalloc(&gH, (size_t)(kdim + 1) * kdim * 16) != cudaSuccess || cudaMalloc(&ge, (size_t)(3 * kdim + 2) * 16) != cudaSuccess ||
+            cudaMalloc((void**)&gres, (size_t)(kdim + 2) * 8) != cudaSuccess) { cleanup_dev(); set_error("gmres: workspace allocation failed"); return cleanup(LKB_ERR_ALLOC); }
+        rc = ensure_ws(c, kdim + 1);
+        if (rc) { cleanup_dev(); return cleanup(rc); }
+        if (c->graphs && !c->profile && (A->type != 9 || A->capturable)) {
+            const int64_t l0 = c->launches;
+            int r2 = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess ? 0 : LKB_ERR_CUDA;
+            if (r2 == 0) {
+                c->capturing = true; r2 = enqueue_cycle(); c->capturing = false;
+                cudaGraph_t g = nullptr;
+                cudaError_t ce = cudaStreamEndCapture(c->stream, &g);
+                if (r2 == 0 && ce != cudaSuccess) { set_error("gmres: graph capture failed: %s", cudaGetErrorString(ce)); r2 = LKB_ERR_CUDA; }
+                if (r2 == 0 && cudaGraphInstantiate(&cycle_exec, g, 0) != cudaSuccess) { set_error("gmres: graph instantiate failed"); r2 = LKB_ERR_CUDA; }
+                if (g) cudaGraphDestroy(g);
+            }
+            cycle_launches = c->launches - l0; c->launches = l0;
+            if (r2) { cleanup_dev(); return cleanup(r2); }
+        }
+    }
+#undef GM_TRY
+#define GM_TRY(call) do { rc = (call); if (rc) { cleanup_dev(); return cleanup(rc); } } while (0)
     while (!io->converged && io->n_outer <= maxiter) {
         std::fill(H.begin(), H.end(), cd(0));
         GM_TRY(lkb_basis_zero(V, 0, kdim + 1));
@@ -141,6 +182,35 @@ static int gmres_impl(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, doubl
         std::fill(cs.begin(), cs.end(), cd(0)); std::fill(sn.begin(), sn.end(), cd(0));
         if (io->n_outer == 0) push_res(io->res, io->res_cap, &io->res_len, fabs(beta));
         int k = 1;
+        if (device_cycle) {
+            // ---- whole restart cycle on the device: one CUDA graph, one host sync (k_gmres_update) ----
+            const size_t hbytes = (size_t)(kdim + 1) * kdim * 16;
+            GM_TRY(cudaMemsetAsync(gH, 0, hbytes, c->stream) == cudaSuccess ? 0 : LKB_ERR_CUDA);
+            GM_TRY(cudaMemsetAsync(ge, 0, (size_t)(3 * kdim + 2) * 16, c->stream) == cudaSuccess ? 0 : LKB_ERR_CUDA);   // e, cs, sn
+            const double e0[2] = {e[0].real(), 0.0};
+            GM_TRY(cudaMemcpyAsync(ge, e0, 16, cudaMemcpyHostToDevice, c->stream) == cudaSuccess ? 0 : LKB_ERR_CUDA);
+            GM_TRY(cudaMemsetAsync(c->flags, 0, F_COUNT * sizeof(int), c->stream) == cudaSuccess ? 0 : LKB_ERR_CUDA);
+            if (cycle_exec) { GM_TRY(cudaGraphLaunch(cycle_exec, c->stream) == cudaSuccess ? 0 : LKB_ERR_CUDA); c->launches += cycle_launches; }
+            else GM_TRY(enqueue_cycle());
+            GM_TRY(ensure_hstage(c, hbytes + (size_t)(kdim + 2) * 24 + 64 + 4096));
+            char* hs = (char*)c->hstage;
+            cudaMemcpyAsync(hs, gH, hbytes, cudaMemcpyDeviceToHost, c->stream);
+            cudaMemcpyAsync(hs + hbytes, ge, (size_t)(kdim + 1) * 16, cudaMemcpyDeviceToHost, c->stream);
+            cudaMemcpyAsync(hs + hbytes + (size_t)(kdim + 1) * 16, gres, (size_t)(kdim + 1) * 8, cudaMemcpyDeviceToHost, c->stream);
+            char* hflags = hs + hbytes + (size_t)(kdim + 1) * 24;      // (fetch_flags would stage at offset 0 and clobber H)
+            cudaMemcpyAsync(hflags, c->flags, F_COUNT * sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+            GM_TRY(cudaStreamSynchronize(c->stream) == cudaSuccess ? 0 : LKB_ERR_CUDA);
+            memcpy(hf, hflags, sizeof(hf));
+            const int kdone = hf[F_STOP] ? hf[F_INFO] : kdim;
+            const double* Hh = (const double*)hs; const double* eh = (const double*)(hs + hbytes);
+            const double* rh = (const double*)(hs + hbytes + (size_t)(kdim + 1) * 16);
+            for (size_t t = 0; t < (size_t)(kdim + 1) * kdim; ++t) H[t] = cd(Hh[2 * t], Hh[2 * t + 1]);
+            for (int i = 0; i <= kdim; ++i) e[i] = cd(eh[2 * i], eh[2 * i + 1]);
+            for (int i = 1; i <= kdone; ++i) { io->n_iter++; io->n_inner++; push_res(io->res, io->res_cap, &io->res_len, rh[i]); }
+            if (trans) A->n_rmatvec += kdone; else A->n_matvec += kdone;
+            if (hf[F_STOP]) io->converged = 1;
+            k = hf[F_STOP] ? kdone : kdim + 1;
+        } else
         for (k = 1; k <= kdim; ++k) {
             void* w = col_ptr(V, k);
             if (trans) A->n_rmatvec++; else A->n_matvec++;
@@ -207,7 +277,8 @@ static int gmres_impl(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, doubl
         if (fabs(beta) < tol) { io->converged = 1; break; }
     }
 #undef GM_TRY
-    (void)hf; (void)col;
+    (void)col;
+    cleanup_dev();
     *info = io->converged ? io->n_iter : -io->n_iter;
     io->info = *info;
     return cleanup(0);

@@ -568,7 +568,8 @@ def test_fgmres_vs_oracle(lk, ctx, oracle):
     # without a preconditioner fgmres == gmres
     x1 = lk.Vector(ctx, "d", n); x2 = lk.Vector(ctx, "d", n)
     i1, m1 = lk.fgmres(A, b, x1, kdim=20, maxiter=30); i2, m2 = lk.gmres(A, b, x2, kdim=20, maxiter=30)
-    assert i1 == i2 and np.array_equal(x1.get(), x2.get())
+    # (gmres without a preconditioner runs its Givens update on the device, fgmres on the host: same iterates to rounding)
+    assert i1 == i2 and np.allclose(x1.get(), x2.get(), rtol=1e-10, atol=1e-13)
 
 
 @pytest.mark.parametrize("kind", KINDS)
