@@ -47,7 +47,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
     if force or _stale(OUT, objs):
-        cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-cudart", "static", "-ldl", "-lpthread", "-ccbin", "/usr/bin/g++"]
+        cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] + objs + \
+              ["-cudart", "static", "-ldl", "-lpthread", "-ccbin", "/usr/bin/g++"]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)
