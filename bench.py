@@ -48,7 +48,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fused", action="store_true", help="disable the fused axpy+dot CGS2 kernel (A/B)")
     ap.add_argument("--no-p2p", action="store_true", help="use ncclAllReduce instead of the in-kernel NVLink allreduce (A/B)")
-    ap.add_argument("--cpu-sample-steps", type=int, default=12)
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=0|1",
+                    help="lkb_set_option A/B switches: fused, fin (fused final pass), fused_halo, p2p, graphs")
     return ap.parse_args()
 
 
@@ -115,33 +116,57 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle (C restatement of the reference's per-vector algorithm) on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_arnoldi_sample(nx, ny, kdim, nsteps, threads):
-    """Time oracle Arnoldi steps j = 1..nsteps at full n, fit t(j) = a + b*j, extrapolate to kdim.
-    Returns (steps_per_s, seconds_spent, description)."""
-    from oracle import lk_oracle as lo
-    lo.set_threads(threads)
-    n = nx * ny
-    A = lo.Op.stencil("d", (nx, ny), POISSON5)
-    X = np.zeros((n, nsteps + 1), order="F")
-    X[:, 0] = lo.fill(n, "d", "uniform", 42); lo.normalize(X[:, 0])
-    H = np.zeros((nsteps + 1, nsteps), order="F")
-    ts = []
-    t00 = time.perf_counter()
-    for k in range(1, nsteps + 1):
-        t0 = time.perf_counter()
-        info = lo.arnoldi(A, X, H, kstart=k, kend=k)
-        ts.append(time.perf_counter() - t0)
-        assert info == 0
-    spent = time.perf_counter() - t00
-    js = np.arange(1, nsteps + 1, dtype=float)
-    if nsteps >= 3:
-        b, a = np.polyfit(js, np.array(ts), 1)
-    else:
-        a, b = 0.0, ts[-1] / nsteps
-    total = sum(max(a + b * j, 0.0) for j in range(1, kdim + 1))
-    desc = (f"oracle arnoldi steps j=1..{nsteps} at full n={n} (5-pt Poisson {nx}x{ny}, fp64), per-step times "
-            f"fitted t(j)=a+b*j (a={a:.3f}s, b={b:.4f}s) and summed over j=1..{kdim}")
-    return kdim / total, spent, desc
+WORKLOAD = "arnoldi kdim={kdim} on 5-pt Poisson {nx}x{ny} (n={n}) fp64 [BASELINE configs[1]]"
+
+
+class CpuArnoldi:
+    """The reference's CPU path for this workload: the oracle (C restatement of LightKrylov's per-vector algorithm,
+    OpenMP over `threads` host cores) on the full-size operator.  One SAMPLE = oracle Arnoldi steps at step indices
+    `js` spread over the whole 1..kdim range on a basis that is pre-filled ONCE with normalised random columns
+    (the cost of a step depends on j, not on the values), so t(j) = a + b*j is fitted by INTERPOLATION and summed
+    over j = 1..kdim.  (Round 1 sampled j = 1..8 only and extrapolated; VERDICT r01 weak #6.)"""
+
+    def __init__(self, nx, ny, kdim, threads):
+        from oracle import lk_oracle as lo
+        self.lo, self.nx, self.ny, self.kdim, self.threads = lo, nx, ny, kdim, threads
+        self.n = nx * ny
+        self.A = lo.Op.stencil("d", (nx, ny), POISSON5)
+        self.X = None
+
+    def _prefill(self, jmax):
+        lo = self.lo
+        lo.set_threads(host_threads())
+        if self.X is None:
+            self.X = np.zeros((self.n, self.kdim + 1), order="F")
+            self.filled = 0
+        for i in range(self.filled, jmax):
+            self.X[:, i] = lo.fill(self.n, "d", "uniform", 42 + i)
+            lo.normalize(self.X[:, i])
+        self.filled = max(self.filled, jmax)
+
+    def sample(self, js):
+        """Returns (steps_per_s, seconds_spent, description)."""
+        lo = self.lo
+        js = sorted(set(min(max(int(j), 1), self.kdim) for j in js))
+        self._prefill(max(js))
+        lo.set_threads(self.threads)
+        H = np.zeros((self.kdim + 1, self.kdim), order="F")
+        ts = []
+        t00 = time.perf_counter()
+        for k in js:
+            t0 = time.perf_counter()
+            info = lo.arnoldi(self.A, self.X, H, kstart=k, kend=k)
+            ts.append(time.perf_counter() - t0)
+            assert info == 0
+        spent = time.perf_counter() - t00
+        if len(js) >= 2:
+            b, a = np.polyfit(np.array(js, dtype=float), np.array(ts), 1)
+        else:
+            a, b = 0.0, ts[-1] / js[-1]
+        total = sum(max(a + b * j, 0.0) for j in range(1, self.kdim + 1))
+        desc = (f"oracle arnoldi steps at j={js} of 1..{self.kdim} at full n={self.n} (5-pt Poisson {self.nx}x{self.ny}, fp64, "
+                f"{self.threads} thread(s)), per-step times fitted t(j)=a+b*j (a={a:.3f}s, b={b:.4f}s) and summed over j=1..{self.kdim}")
+        return self.kdim / total, spent, desc
 
 
 def host_threads() -> int:
@@ -156,13 +181,14 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import lk_oracle as lo
     threads = host_threads()
+    cpu = CpuArnoldi(args.nx, args.ny, args.kdim, threads)
+    kd = args.kdim
+    js = sorted(set([1, kd // 4, kd // 2, (3 * kd) // 4, kd]))
     vals = []
     desc = ""
-    nsample = max(3, min(args.cpu_sample_steps, 8))
     for i in range(args.warmup + args.steps):
-        v, spent, desc = cpu_arnoldi_sample(args.nx, args.ny, args.kdim, nsample, threads)
+        v, spent, desc = cpu.sample(js)
         if i >= args.warmup:
             vals.append((v, spent))
     value = float(np.mean([v for v, _ in vals]))
@@ -171,13 +197,13 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"arnoldi kdim={args.kdim} on 5-pt Poisson {args.nx}x{args.ny} (n={args.nx * args.ny}) fp64",
+        "config": {"workload": WORKLOAD.format(kdim=args.kdim, nx=args.nx, ny=args.ny, n=args.nx * args.ny),
                    "bench_step": "bounded CPU sample: " + desc},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "reference = CPU oracle (C restatement of LightKrylov's per-vector algorithm, OpenMP); the Fortran "
-                "reference cannot be built in this image (no Fortran compiler / fpm / stdlib)",
+                "reference cannot be built in this image or on the GPU box (no Fortran compiler / fpm / stdlib; probed in round 2)",
     }
     emit(line)
 
@@ -204,6 +230,9 @@ def run_ours(args):
     assert world == args.gpus or world == 1, "--gpus must equal WORLD_SIZE"
     if args.no_fused:
         ctx.set_option("fused", 0)
+    for o in args.opt:
+        name, val = o.split("=")
+        ctx.set_option(name, int(val))
 
     nx, ny, kdim = args.nx, args.ny, args.kdim
     n = nx * ny
@@ -255,6 +284,30 @@ def run_ours(args):
     launches = ctx.kernel_launches - l0
     clocks = sampler.stop() if rank == 0 else None
     value = args.steps * kdim / (ms_total * 1e-3)
+
+    # ---- parity record (outside the timed region): H and Ritz values of THIS run, at THIS number of ranks, against the
+    # committed oracle Hessenberg matrix of the same workload (tests/golden/c2_full_H.npz, all 128 steps on the CPU) ----
+    parity = None
+    gold_path = os.path.join(ROOT, "tests", "golden", "c2_full_H.npz")
+    if (nx, ny, kdim) == (4096, 4096, 128) and os.path.exists(gold_path):
+        g = np.load(gold_path)
+        Hg = g["H"]
+        herr = float(np.abs(H - Hg).max() / np.abs(Hg).max())
+        ritz = np.sort(np.linalg.eigvals(H[:kdim, :kdim]).real)
+        rerr = float(np.abs(ritz - g["ritz"]).max() / np.abs(g["ritz"]).max())
+        # ||V^H V - I||_max over the first and last 8 columns, evaluated on the device (all ranks take part in the reductions)
+        Gm = X.innerprod(kdim + 1, X, wcol0=0, p=8); Gl = X.innerprod(kdim + 1, X, wcol0=kdim - 7, p=8)
+        E = np.eye(kdim + 1)
+        orth = float(max(np.abs(Gm - E[:, :8]).max(), np.abs(Gl - E[:, kdim - 7:]).max()))
+        same = True
+        if world > 1:      # H must be bitwise identical on every rank
+            hs = [None] * world
+            dist.all_gather_object(hs, H.tobytes())
+            same = all(h == hs[0] for h in hs)
+        parity = {"oracle": "tests/golden/c2_full_H.npz (CPU oracle, 128 steps, same start vector)",
+                  "max_rel_err_H": herr, "max_rel_err_ritz": rerr, "orth_err_first_last_8_cols": orth,
+                  "H_identical_on_all_ranks": bool(same), "tol": 1e-10, "orth_tol": 1e-12,
+                  "ok": bool(herr < 1e-10 and rerr < 1e-10 and orth <= 1e-12 and same)}
 
     # ---- end-to-end arm: host start vector in pinned memory -> H on the host ---------------------
     x0_host = torch.empty(nloc, dtype=torch.float64).pin_memory()
@@ -331,8 +384,8 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         thr = host_threads()
-        v_all, _, desc = cpu_arnoldi_sample(nx, ny, kdim, args.cpu_sample_steps, thr)
-        v_one, _, desc1 = cpu_arnoldi_sample(nx, ny, kdim, 4, 1)
+        v_all, _, desc = CpuArnoldi(nx, ny, kdim, thr).sample([1, kdim // 2, kdim])
+        v_one, _, desc1 = CpuArnoldi(nx, ny, kdim, 1).sample([1, 12])
         cpu = {"value": v_all, "unit": UNIT, "cores": thr, "kind": "port", "sample": desc,
                "serial": {"value": v_one, "cores": 1, "sample": desc1}}
 
@@ -341,7 +394,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"arnoldi kdim={kdim} on 5-pt Poisson {nx}x{ny} (n={n}) fp64 [BASELINE configs[1]]",
+            "config": {"workload": WORKLOAD.format(kdim=kdim, nx=nx, ny=ny, n=n),
                        "bench_step": f"one kstart=1..kend={kdim} factorisation = {kdim} Arnoldi steps",
                        "partition": f"grid rows over {world} rank(s), {nloc} rows/rank",
                        "l2": "working set 17.3 GB/GPU-share >> 126 MB L2 (inputs larger than L2, no flush needed)",
@@ -356,6 +409,7 @@ def run_ours(args):
                               "frac_of_measured": step_gbs / peak, "frac_of_nominal_8TBps": step_gbs / 8000.0},
             "kernels": kernels,
             "cpu_baseline": cpu,
+            "parity": parity,
             "clocks": clocks,
         }
         emit(line)

@@ -116,6 +116,12 @@ int lkb_op_stencil7_create(lkb_ctx_t ctx, int kind, int64_t nx, int64_t ny, int6
                            int64_t slow0, int64_t nslow_local, lkb_op_t* A);
 int lkb_op_csr_create(lkb_ctx_t ctx, int kind, int64_t m, int64_t n, const int64_t* rowptr, const int32_t* col,
                       const void* val, lkb_op_t* A);
+/* The same operator from CSR arrays that already live on this GPU (cudaMalloc'ed device pointers).  adopt != 0: the
+ * library takes ownership of the three arrays (freed by lkb_op_destroy; on failure they stay with the caller),
+ * adopt == 0: they are copied.  (rowptr, col) are validated on the device: rowptr[0] == 0, non-decreasing,
+ * 0 <= col < n, else LKB_ERR_ARG.  The explicit transpose for rmatvec is built on the device. */
+int lkb_op_csr_create_device(lkb_ctx_t ctx, int kind, int64_t m, int64_t n, int64_t* rowptr_dev, int32_t* col_dev,
+                             void* val_dev, int32_t adopt, lkb_op_t* A);
 /* Row-sharded CSR (collective): this rank owns rows [row0, row0+m_local) with GLOBAL column indices; vectors of
  * the column space are sharded as [col0, col0+n_local).  matvec gathers x over the ranks, rmatvec reduces the
  * partial A_loc^H u_loc onto the owners (NCCL over NVLink). */
@@ -199,12 +205,24 @@ int lkb_svds(lkb_op_t A, lkb_basis_t U, double* S, lkb_basis_t V, int nsv, doubl
 int lkb_set_lapack(const char* path, const char* prefix, const char* suffix);
 
 /* ---- measurement helpers ----------------------------------------------------------------- */
+/* Synthetic CSR matrix of BASELINE config 5 generated ON THE DEVICE (`per_row` column indices per row
+ * drawn uniformly, sorted, values N(0,1)[+ i N(0,1)]), rows [row0, row0 + m_local) of the global matrix, counter RNG
+ * keyed on (seed, global row, slot) -- the oracle regenerates the identical matrix on the host.  The three arrays are
+ * cudaMalloc'ed; hand them to lkb_op_csr_create_device(adopt = 1) or release them with lkb_dev_free. */
+int lkb_csr_random_device(lkb_ctx_t ctx, int kind, int64_t m_local, int64_t row0, int64_t n, int32_t per_row, uint64_t seed,
+                          int64_t** rowptr_dev, int32_t** col_dev, void** val_dev);
+int lkb_dev_free(void* devptr);
 /* per-kernel-class device time (ms) accumulated since lkb_set_profile(ctx, 1), measured with CUDA
  * events on the context stream (graphs are bypassed while profiling).  8 slots:
  * [0] matvec, [1] multi-dot, [2] multi-axpy, [3] other, [4] fused axpy+dot, [5..7] reserved */
 int lkb_set_profile(lkb_ctx_t ctx, int enable);
 int lkb_get_profile(lkb_ctx_t ctx, double* ms8, int64_t* launches8);
 int64_t lkb_kernel_launches(lkb_ctx_t ctx);               /* kernels launched since context creation */
+/* in-kernel timeline of the last reduction kernel launched (k_multidot / k_axpy_dot): per CTA {start, main loop done,
+ * ticket taken, -} in %globaltimer ns, then at word 4096 {stage-2 start, stage-2 done, allreduce done} of the last CTA.
+ * Used by profiles/ktime_probe.py to split a launch into ramp-up / streaming / reduction tail. */
+int lkb_debug_ktime(lkb_ctx_t ctx, int enable);
+int lkb_debug_ktime_read(lkb_ctx_t ctx, uint64_t* out, int nwords);
 
 #ifdef __cplusplus
 }

@@ -80,6 +80,9 @@ SIGNATURES = {
     "lkb_op_stencil5_create": (_i, [_vp, _i, _i64, _i64, _vp, _i64, _i64, _P(_vp)]),
     "lkb_op_stencil7_create": (_i, [_vp, _i, _i64, _i64, _i64, _vp, _i64, _i64, _P(_vp)]),
     "lkb_op_csr_create": (_i, [_vp, _i, _i64, _i64, _vp, _vp, _vp, _P(_vp)]),
+    "lkb_op_csr_create_device": (_i, [_vp, _i, _i64, _i64, _vp, _vp, _vp, _i32, _P(_vp)]),
+    "lkb_csr_random_device": (_i, [_vp, _i, _i64, _i64, _i64, _i32, _u64, _P(_vp), _P(_vp), _P(_vp)]),
+    "lkb_dev_free": (_i, [_vp]),
     "lkb_op_csr_create_dist": (_i, [_vp, _i, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _P(_vp)]),
     "lkb_op_dense_create": (_i, [_vp, _i, _i64, _i64, _vp, _P(_vp)]),
     "lkb_op_callback_create": (_i, [_vp, _i, _i64, _i64, MATVEC_FN, _vp, _i32, _P(_vp)]),
@@ -104,6 +107,8 @@ SIGNATURES = {
     "lkb_set_profile": (_i, [_vp, _i]),
     "lkb_get_profile": (_i, [_vp, _P(_d), _P(_i64)]),
     "lkb_kernel_launches": (_i64, [_vp]),
+    "lkb_debug_ktime": (_i, [_vp, _i]),
+    "lkb_debug_ktime_read": (_i, [_vp, _P(_u64), _i]),
 }
 
 

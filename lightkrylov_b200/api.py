@@ -322,6 +322,23 @@ class LinOp:
         return op
 
     @classmethod
+    def csr_random(cls, ctx: Context, kind: str, m: int, n: int, per_row: int, seed: int) -> "LinOp":
+        """Synthetic config-5 matrix generated and transposed ON THE DEVICE (lkb_csr_random_device +
+        lkb_op_csr_create_device, adopt = 1): `per_row` uniformly drawn, sorted column indices per row, normal values.
+        The oracle builds the same matrix with `csr_random_host` below."""
+        rp, ci, va = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(ctx.lib.lkb_csr_random_device(ctx.h, KINDS[kind], m, 0, n, per_row, seed, C.byref(rp), C.byref(ci), C.byref(va)), "csr_random")
+        h = C.c_void_p()
+        rc = ctx.lib.lkb_op_csr_create_device(ctx.h, KINDS[kind], m, n, rp, ci, va, 1, C.byref(h))
+        if rc != 0:
+            for ptr in (rp, ci, va):
+                ctx.lib.lkb_dev_free(ptr)
+            check(rc, "csr_create_device")
+        op = cls(ctx, kind, h, m, n)
+        op.row0, op.n_global = 0, n
+        return op
+
+    @classmethod
     def csr_dist(cls, ctx: Context, m: int, n: int, rowptr_local, col_global, val, row_slab=None, col_slab=None) -> "LinOp":
         """Row-sharded CSR: this rank passes ITS rows (local rowptr, global column indices).  Collective."""
         kind = kind_of(val.dtype)

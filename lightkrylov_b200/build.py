@@ -14,9 +14,10 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "liblkb.so")
-SOURCES = ["kernels_gs.cu", "kernels_vec.cu", "kernels_ops.cu", "kernels_gemm.cu", "kernels_fused.cu", "lkb_core.cu", "lkb_krylov.cu",
+SOURCES = ["kernels_gs.cu", "kernels_vec.cu", "kernels_ops.cu", "kernels_gemm.cu", "kernels_fused.cu", "lkb_core.cu", "lkb_csr.cu", "lkb_krylov.cu",
            "lkb_solvers.cu", "lkb_eig.cu"]
-HEADERS = ["lkb_types.cuh", "lkb_kernels.h", "lkb_internal.h", "lkb_rng.h", os.path.join("..", "..", "include", "lkb.h")]
+# every header in csrc/ (globbed: a forgotten header once left objects stale) + the public C ABI
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".h", ".cuh", ".inc"))) + [os.path.join("..", "..", "include", "lkb.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "-ccbin", "/usr/bin/g++"]

@@ -19,6 +19,7 @@
 #include <cuda.h>
 #include "lkb_kernels.h"
 #include "lkb_p2p.cuh"
+#include "lkb_reduce.cuh"
 
 namespace lkb {
 
@@ -104,16 +105,15 @@ k_axpy_dot(const __grid_constant__ CUtensorMap tmap, int j, int tp, int nst, int
     uint64_t* bars = reinterpret_cast<uint64_t*>(wst + (size_t)nst * tp);      // full[nst], empty[nst]
     uint64_t* ebars = bars + nst;
     __shared__ double sww[FZ_NW + 1];
-    __shared__ bool is_last;
 
     const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
     const int64_t npk = n / EPP;
     const int64_t ntiles = (npk + tp - 1) / tp;
-    const int64_t tper = (ntiles + gridDim.x - 1) / gridDim.x;
-    const int64_t t0 = (int64_t)blockIdx.x * tper;
-    const int64_t t1 = min(ntiles, t0 + tper);
+    const int64_t t0 = ((int64_t)blockIdx.x * ntiles) / gridDim.x;          // balanced to within one tile
+    const int64_t t1 = (((int64_t)blockIdx.x + 1) * ntiles) / gridDim.x;
     const int nmine = (int)max((int64_t)0, t1 - t0);
 
+    ktime_cta(p2p, 0);
     if (tid == 0) {
         for (int s = 0; s < nst; ++s) { mbar_init(smem_u32(&bars[s]), 1); mbar_init(smem_u32(&ebars[s]), FZ_NW); }
         fence_barrier_init();
@@ -229,6 +229,7 @@ k_axpy_dot(const __grid_constant__ CUtensorMap tmap, int j, int tp, int nst, int
     // ---- stage 1: one partial row per CTA; the rs row-slice warps of a chunk are summed in fixed order ----
     const int fold_idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
     __syncthreads();                                   // the ring is drained: reuse `part` as [rs][jc] W scratch
+    ktime_cta(p2p, 1);
     W* fold = reinterpret_cast<W*>(part);
     if (worker) {
         warp_fold16_f<E>(acc, lane);
@@ -251,22 +252,12 @@ k_axpy_dot(const __grid_constant__ CUtensorMap tmap, int j, int tp, int nst, int
         *reinterpret_cast<double*>(&o) = t;
         partial[(int64_t)blockIdx.x * jp + j] = o;
     }
-    // ---- stage 2: last CTA folds the partial rows in fixed order ----
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1u);
-    __syncthreads();
-    if (is_last) {
-        __threadfence();
-        const int nrb = gridDim.x;
-        for (int col = wv; col < jp; col += FZ_NW + 1) {
-            W a = zero_v(W());
-            for (int b = lane; b < nrb; b += 32) wadd(a, __ldcg(&partial[(int64_t)b * jp + col]));
-            a = warp_sum(a);
-            if (lane == 0) out[col] = a;
-        }
-        if (tid == 0) *counter = 0u;
+    // ---- stage 2: two-level tree over the partial rows (lkb_reduce.cuh) ----
+    ktime_cta(p2p, 2);
+    if (reduce_rows_tree<W>(partial, jp, out, counter)) {
+        ktime_last(p2p, 1);
         if (p2p.world > 1) p2p_allreduce_cta<W>(p2p, out, jp);
+        ktime_last(p2p, 2);
     }
 }
 
@@ -323,12 +314,12 @@ static bool axpy_dot_t(cudaStream_t s, const void* V, int64_t ld, int j, const v
     if (nst > FZ_MAXSTAGES) nst = FZ_MAXSTAGES;
     if (nst < 2) return false;
     const size_t sh = (size_t)nst * jc * tp * 16 + (size_t)(FZ_NW + 1 + nst) * tp * 16 + 16 * nst + 64;
-    static const bool attr_once = (cudaFuncSetAttribute(k_axpy_dot<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024), true);
-    (void)attr_once;
+    static const SmemAttrOnce attr((const void*)k_axpy_dot<K>, 224 * 1024);
+    attr.ensure();
     const int64_t ntiles = (n / EPP + tp - 1) / tp;
     int64_t nb = sms;
     if (nb > ntiles) nb = ntiles;
-    if (nb > MAX_ROWBLOCKS) nb = MAX_ROWBLOCKS;
+    if (nb > RT_MAXROWS) nb = RT_MAXROWS;
     k_axpy_dot<K><<<(int)nb, FZ_THREADS, sh, s>>>(tmap, j, tp, nst, elt_per_pack, (const W*)c1, (E*)w, n, (W*)partial, (W*)out, counter, flags, p2p ? *p2p : P2P());
     return true;
 }

@@ -6,8 +6,11 @@
 //   linear_combination + y%sub     = j axpbys on a temporary  (gram_schmidt.fypp:141-146)
 // by ONE multi-dot (reads V once, w once) and ONE multi-axpy (reads V once, w once, writes w once).
 // Algorithmic bytes per pass: 2*j*n*s (+3*n*s for w).  No tensor cores: AI ~ 0.25 flop/B.
+#include <stdlib.h>
 #include "lkb_kernels.h"
 #include "lkb_p2p.cuh"
+#include "lkb_step.cuh"
+#include "lkb_reduce.cuh"
 
 namespace lkb {
 
@@ -48,7 +51,72 @@ template <typename E> LKB_DI void warp_fold16(E (&acc)[16], int lane) {
     acc[0] = add_v(acc[0], shfl_xor_t<E>(acc[0], 1));
 }
 
-template <int K, int PT>
+// One tile of MD_THREADS*PT packs starting at pack `tb`: the PT packs of w of this thread are loaded once and stay in
+// registers while all j columns are swept in chunks of 16.  FULL: every pack of the tile lies below `p1`.
+template <int K, int PT, bool FULL>
+LKB_DI void md_tile(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j, int nchunk,
+                    const typename Tr<K>::E* __restrict__ w, int64_t tb, int64_t p1,
+                    typename Tr<K>::W* __restrict__ myacc, typename Tr<K>::E& accw, int lane, int fold_idx)
+{
+    using E = typename Tr<K>::E;
+    constexpr int EPP = Tr<K>::EPP;
+    constexpr int CB = MD_CB;
+    using P = Pack<E, EPP>;
+    const int64_t base = tb + threadIdx.x;
+    P wv[PT];
+#pragma unroll
+    for (int q = 0; q < PT; ++q) {
+        const int64_t pk = base + (int64_t)q * MD_THREADS;
+        if (FULL || pk < p1) wv[q] = ld_pack_nc<P>(w + pk * EPP);
+        else {
+#pragma unroll
+            for (int e = 0; e < EPP; ++e) wv[q].v[e] = zero_v(E());
+        }
+#pragma unroll
+        for (int e = 0; e < EPP; ++e) fma_conj(accw, wv[q].v[e], wv[q].v[e]);
+    }
+    for (int c = 0; c < nchunk; ++c) {
+        const int c0 = c * CB;
+        const int ncv = min(CB, j - c0);
+        const E* vb = V + (int64_t)c0 * ld;
+        E acc[CB];
+#pragma unroll
+        for (int i = 0; i < CB; ++i) acc[i] = zero_v(E());
+        if (FULL && ncv == CB) {
+#pragma unroll
+            for (int q = 0; q < PT; ++q) {
+                const int64_t off = (base + (int64_t)q * MD_THREADS) * EPP;
+                P v[CB];
+#pragma unroll
+                for (int i = 0; i < CB; ++i) v[i] = ld_pack_nc<P>(vb + (int64_t)i * ld + off);
+#pragma unroll
+                for (int i = 0; i < CB; ++i)
+#pragma unroll
+                    for (int e = 0; e < EPP; ++e) fma_conj(acc[i], v[i].v[e], wv[q].v[e]);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < PT; ++q) {
+                const int64_t pk = base + (int64_t)q * MD_THREADS;
+                if (FULL || pk < p1) {
+                    const int64_t off = pk * EPP;
+#pragma unroll
+                    for (int i = 0; i < CB; ++i) {
+                        if (i < ncv) {
+                            const P v = ld_pack_nc<P>(vb + (int64_t)i * ld + off);
+#pragma unroll
+                            for (int e = 0; e < EPP; ++e) fma_conj(acc[i], v.v[e], wv[q].v[e]);
+                        }
+                    }
+                }
+            }
+        }
+        warp_fold16<E>(acc, lane);
+        if ((lane & 1) == 0 && fold_idx < ncv) wadd(myacc[c0 + fold_idx], widen(acc[0]));
+    }
+}
+
+template <int K>
 __global__ void __launch_bounds__(MD_THREADS, 2)
 k_multidot(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j,
            const typename Tr<K>::E* __restrict__ w, int64_t n,
@@ -59,87 +127,35 @@ k_multidot(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j,
     using W = typename Tr<K>::W;
     constexpr int EPP = Tr<K>::EPP;
     constexpr int CB = MD_CB;
-    // PT = packs of w held in registers per thread (tile = MD_THREADS*PT packs); smaller tiles are
-    // chosen for small n so that the tiles still spread evenly over the 2*SM CTAs
     constexpr int NW = MD_THREADS / 32;
-    using P = Pack<E, EPP>;
     static_assert(CB == 16, "warp_fold16 assumes 16 columns per chunk");
     if (flags && flags[F_STOP]) return;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     W* sacc = reinterpret_cast<W*>(smem_raw);   // [NW][jp]
-    __shared__ bool is_last;
     const int jp = j + 1;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < NW * jp; i += MD_THREADS) sacc[i] = zero_v(W());
     __syncthreads();
     W* myacc = sacc + wid * jp;
     const int fold_idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    ktime_cta(p2p, 0);
 
+    // Row split: every CTA owns a contiguous range [p0, p1) of 32-pack groups, balanced to within ONE group (512 B)
+    // for any n.  The range is walked in tiles of 4 packs per thread (one warp fold per 64 loads); what is left is
+    // walked in 1-pack tiles and only the final < 256 packs take the masked path.  (Round 1 split whole tiles and
+    // shrank ALL tiles to 1 pack per thread at 1/8 of C2 per GPU to stay balanced; a first round-2 version kept
+    // 4-pack tiles and masked the remainder -- 13 % of a CTA's rows there -- which was slower still.)
     const int64_t npk = n / EPP;
-    constexpr int64_t TILE = (int64_t)MD_THREADS * PT;
-    const int64_t ntiles = (npk + TILE - 1) / TILE;
-    const int64_t tper = (ntiles + gridDim.x - 1) / gridDim.x;
-    const int64_t t0 = (int64_t)blockIdx.x * tper;
-    const int64_t t1 = min(ntiles, t0 + tper);
+    const int64_t ngroups = (npk + 31) / 32;
+    const int64_t p0 = (((int64_t)blockIdx.x * ngroups) / gridDim.x) * 32;
+    const int64_t p1 = min(npk, ((((int64_t)blockIdx.x + 1) * ngroups) / gridDim.x) * 32);
     const int nchunk = (j + CB - 1) / CB;
     E accw = zero_v(E());
-
-    for (int64_t t = t0; t < t1; ++t) {
-        const int64_t base = t * TILE + threadIdx.x;
-        const bool full = (t + 1) * TILE <= npk;
-        P wv[PT];
-#pragma unroll
-        for (int q = 0; q < PT; ++q) {
-            const int64_t pk = base + (int64_t)q * MD_THREADS;
-            if (full || pk < npk) wv[q] = ld_pack_nc<P>(w + pk * EPP);
-            else {
-#pragma unroll
-                for (int e = 0; e < EPP; ++e) wv[q].v[e] = zero_v(E());
-            }
-#pragma unroll
-            for (int e = 0; e < EPP; ++e) fma_conj(accw, wv[q].v[e], wv[q].v[e]);
-        }
-        for (int c = 0; c < nchunk; ++c) {
-            const int c0 = c * CB;
-            const int ncv = min(CB, j - c0);
-            const E* vb = V + (int64_t)c0 * ld;
-            E acc[CB];
-#pragma unroll
-            for (int i = 0; i < CB; ++i) acc[i] = zero_v(E());
-            if (full && ncv == CB) {
-#pragma unroll
-                for (int q = 0; q < PT; ++q) {
-                    const int64_t off = (base + (int64_t)q * MD_THREADS) * EPP;
-                    P v[CB];
-#pragma unroll
-                    for (int i = 0; i < CB; ++i) v[i] = ld_pack_nc<P>(vb + (int64_t)i * ld + off);
-#pragma unroll
-                    for (int i = 0; i < CB; ++i)
-#pragma unroll
-                        for (int e = 0; e < EPP; ++e) fma_conj(acc[i], v[i].v[e], wv[q].v[e]);
-                }
-            } else {
-#pragma unroll
-                for (int q = 0; q < PT; ++q) {
-                    const int64_t pk = base + (int64_t)q * MD_THREADS;
-                    if (pk < npk) {
-                        const int64_t off = pk * EPP;
-#pragma unroll
-                        for (int i = 0; i < CB; ++i) {
-                            if (i < ncv) {
-                                const P v = ld_pack_nc<P>(vb + (int64_t)i * ld + off);
-#pragma unroll
-                                for (int e = 0; e < EPP; ++e) fma_conj(acc[i], v.v[e], wv[q].v[e]);
-                            }
-                        }
-                    }
-                }
-            }
-            warp_fold16<E>(acc, lane);
-            if ((lane & 1) == 0 && fold_idx < ncv) wadd(myacc[c0 + fold_idx], widen(acc[0]));
-        }
-    }
+    int64_t tb = p0;
+    for (; tb + 4 * MD_THREADS <= p1; tb += 4 * MD_THREADS) md_tile<K, 4, true>(V, ld, j, nchunk, w, tb, p1, myacc, accw, lane, fold_idx);
+    for (; tb + MD_THREADS <= p1; tb += MD_THREADS) md_tile<K, 1, true>(V, ld, j, nchunk, w, tb, p1, myacc, accw, lane, fold_idx);
+    if (tb < p1) md_tile<K, 1, false>(V, ld, j, nchunk, w, tb, p1, myacc, accw, lane, fold_idx);
     // ragged tail (n not a multiple of the pack width): one thread of CTA 0
     __syncwarp();
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -159,30 +175,22 @@ k_multidot(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j,
     }
     // ---- stage 1: fixed-order sum over the warps of this CTA ----
     __syncthreads();
+    ktime_cta(p2p, 1);
     for (int i = threadIdx.x; i < jp; i += MD_THREADS) {
         W a = sacc[i];
 #pragma unroll
         for (int q = 1; q < NW; ++q) wadd(a, sacc[q * jp + i]);
         partial[(int64_t)blockIdx.x * jp + i] = a;
     }
-    // ---- stage 2: last CTA folds the partial rows ----
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1u);
-    __syncthreads();
-    if (is_last) {
-        __threadfence();
-        const int nrb = gridDim.x;
-        for (int col = wid; col < jp; col += NW) {
-            W a = zero_v(W());
-            for (int b = lane; b < nrb; b += 32) wadd(a, __ldcg(&partial[(int64_t)b * jp + col]));
-            a = warp_sum(a);
-            if (lane == 0) out[col] = a;
-        }
-        if (threadIdx.x == 0) *counter = 0u;
+    // ---- stage 2: two-level tree over the partial rows (lkb_reduce.cuh) ----
+    ktime_cta(p2p, 2);
+    if (reduce_rows_tree<W>(partial, jp, out, counter)) {
+        ktime_last(p2p, 1);
         if (p2p.world > 1) p2p_allreduce_cta<W>(p2p, out, jp);
+        ktime_last(p2p, 2);
     }
 }
+
 
 // ------------------------------------------------------------------------------------------
 // Block (blksize > 1) Gram-Schmidt: two right-hand sides per sweep of V.
@@ -205,7 +213,6 @@ k_multidot2(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j,
     if (flags && flags[F_STOP]) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     W* sacc = reinterpret_cast<W*>(smem_raw);   // [NW][2][jp]
-    __shared__ bool is_last;
     const int jp = j + 1;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < NW * 2 * jp; i += MD_THREADS) sacc[i] = zero_v(W());
@@ -286,22 +293,8 @@ k_multidot2(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j,
         for (int q = 1; q < NW; ++q) wadd(a, sacc[(size_t)q * 2 * jp + i]);
         partial[(int64_t)blockIdx.x * 2 * jp + i] = a;
     }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1u);
-    __syncthreads();
-    if (is_last) {
-        __threadfence();
-        const int nrb = gridDim.x;
-        for (int col = wid; col < 2 * jp; col += NW) {
-            W a = zero_v(W());
-            for (int b = lane; b < nrb; b += 32) wadd(a, __ldcg(&partial[(int64_t)b * 2 * jp + col]));
-            a = warp_sum(a);
-            if (lane == 0) out[col] = a;
-        }
-        if (threadIdx.x == 0) *counter = 0u;
+    if (reduce_rows_tree<W>(partial, 2 * jp, out, counter))
         if (p2p.world > 1) p2p_allreduce_cta<W>(p2p, out, 2 * jp);
-    }
 }
 
 // W_q -= V c_q for q = 0, 1 with one read of every V pack; c laid out [2][j+1] (W type).
@@ -386,7 +379,6 @@ k_dot2(const typename Tr<K>::E* __restrict__ x, const typename Tr<K>::E* __restr
     if (blockIdx.x == 0 && threadIdx.x == 0)
         for (int64_t t = npk * EPP; t < n; ++t) { fma_conj(axy, x[t], y[t]); fma_conj(ayy, y[t], y[t]); }
     __shared__ W sm[8][2];
-    __shared__ bool is_last;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const W a = warp_sum(widen(axy)), b = warp_sum(widen(ayy));
     if (lane == 0) { sm[wid][0] = a; sm[wid][1] = b; }
@@ -396,21 +388,8 @@ k_dot2(const typename Tr<K>::E* __restrict__ x, const typename Tr<K>::E* __restr
         for (int q = 1; q < 8; ++q) wadd(t, sm[q][threadIdx.x]);
         partial[(int64_t)blockIdx.x * 2 + threadIdx.x] = t;
     }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1u);
-    __syncthreads();
-    if (is_last) {
-        __threadfence();
-        if (wid < 2) {
-            W t = zero_v(W());
-            for (int bq = lane; bq < (int)gridDim.x; bq += 32) wadd(t, __ldcg(&partial[(int64_t)bq * 2 + wid]));
-            t = warp_sum(t);
-            if (lane == 0) out[wid] = t;
-        }
-        if (threadIdx.x == 0) *counter = 0u;
+    if (reduce_rows_tree<W>(partial, 2, out, counter))
         if (p2p.world > 1) p2p_allreduce_cta<W>(p2p, out, 2);
-    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -491,19 +470,204 @@ k_multiaxpy(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j,
         }
         __syncthreads();
         if (is_last) {
-            if (wid == 0) {
-                __threadfence();
-                double t = 0.0;
-                for (int b = lane; b < (int)gridDim.x; b += 32) t += __ldcg(&partial[b]);
-                t = warp_sum(t);
-                if (lane == 0) {
-                    W o = zero_v(W());
-                    *reinterpret_cast<double*>(&o) = t;   // real part
-                    nrm2_out[0] = o;
-                    *counter = 0u;
-                }
+            __threadfence();
+            const double t = reduce_scalar_last(partial, (int)gridDim.x);
+            if (threadIdx.x == 0) {
+                W o = zero_v(W());
+                *reinterpret_cast<double*>(&o) = t;   // real part
+                nrm2_out[0] = o;
+                *counter = 0u;
             }
+            __syncthreads();
             if (p2p.world > 1) p2p_allreduce_cta<W>(p2p, nrm2_out, 1);
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Final multi-axpy of a CGS2 step fused with the normalisation of the new basis vector and with the
+// Hessenberg / tridiagonal / bidiagonal column update (round 2):
+//     w'' = w' - V c2 ;  beta = ||w''|| ;  v_{k+1} = w'' / beta ;  H(1:k,k) = c1 + c2 ; H(k+1,k) = beta.
+// The reference computes beta with one more sweep (qr_no_pivoting: `beta = Q(j)%norm()`, qr.fypp:137) and
+// scales with another (`Q(j)%scal(one/beta)`, :164).  Here beta is known BEFORE the update from quantities the
+// second pass already produced: V is orthonormal and c2 = V^H w', so
+//     ||w' - V c2||^2 = ||w'||^2 - ||c2||^2         (Pythagoras; ||w'||^2 = c2[j] rides along with c2).
+// Relative error of the right-hand side: eps * (1 + r) / (1 - r) + O(||V^H V - I||) * r with r = ||c2||^2 /
+// ||w'||^2; in CGS2 r is O(eps^2 kappa^2), so the prediction is as accurate as a computed norm.  When r > 1e-2
+// (pass 1 left more than 10 % of w' inside span(V): severe cancellation, i.e. at or next to a breakdown) every
+// CTA takes the exact path instead: plain update, exact ||w''||^2 by the two-stage reduction (+ the in-kernel
+// allreduce), and the separate k_scale_dev sweep that follows in the stream does the scaling (it returns at
+// once when flags[F_SCALED] is set).  The decision is a pure function of (c2, ww), identical on every CTA and,
+// after the allreduce of c2, on every rank.  Saves per step: one n*s read + n*s write sweep, one reduction with
+// its cross-GPU synchronisation point, and the 1-CTA update kernel.
+// ------------------------------------------------------------------------------------------
+struct FinParams {
+    const void* c1;      // pass-1 coefficients (W type) or nullptr (lanczos / bidiag: only the norm entry is stored)
+    void* hcol;          // column of H / T / B on the device (E type) or nullptr (mode 4)
+    double tol, atol;
+    double* inv_dev;
+    int* flags;
+    int kstep, mode;     // mode 0 arnoldi, 1 lanczos, 2 bidiag, 4 gmres (norm + scaling only; k_gmres_update follows)
+};
+
+template <int K>
+__global__ void __launch_bounds__(256, 2)
+k_multiaxpy_fin(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j,
+                const typename Tr<K>::W* __restrict__ c, typename Tr<K>::E* __restrict__ w, int64_t n,
+                double* __restrict__ partial, typename Tr<K>::W* __restrict__ nrm2_out,
+                unsigned* __restrict__ counter, const FinParams fp, const P2P p2p, const HaloP2P hp)
+{
+    using E = typename Tr<K>::E;
+    using W = typename Tr<K>::W;
+    using Rl = typename Tr<K>::Rl;
+    constexpr int EPP = Tr<K>::EPP;
+    constexpr int UA = 8;
+    using P = Pack<E, EPP>;
+    if (fp.flags[F_STOP]) return;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    E* cs = reinterpret_cast<E*>(smem_raw);
+    __shared__ double sm[8];
+    __shared__ double s_s2;
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // ---- prologue: coefficients to shared memory, ||c2||^2 in a fixed order (identical on every CTA) ----
+    double s2p = 0.0;
+    for (int i = threadIdx.x; i < j; i += blockDim.x) {
+        const W ci = c[i];
+        narrow(ci, cs[i]);
+        if constexpr (Tr<K>::cplx) s2p += ci.x * ci.x + ci.y * ci.y; else s2p += ci * ci;
+    }
+    s2p = warp_sum(s2p);
+    if (lane == 0) sm[wid] = s2p;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = sm[0];
+        for (int q = 1; q < (int)(blockDim.x >> 5); ++q) t += sm[q];
+        s_s2 = t;
+    }
+    __syncthreads();
+    const double s2 = s_s2;
+    const double ww = wreal(c[j]);
+    const bool exact = !(s2 <= 1e-2 * ww);                 // also true for NaN input
+    const double pred = ww - s2;
+    const double beta_p = sqrt(fabs(pred));
+    const Rl inv = exact ? (Rl)1 : (Rl)fin_inv(fp.mode, beta_p, fp.tol, fp.atol);
+    const bool do_scale = !exact && inv != (Rl)1;
+    // P2P halo push of the finished vector (fast path only; the exact path pushes from k_scale_dev)
+    const bool push = hp.he > 0 && !exact;
+    const unsigned ep = push ? *hp.epoch + 1u : 0u;
+    const size_t par = (size_t)(ep & 1u) * 2 * hp.side_bytes;
+    E* push_lo = (push && hp.lo_region) ? reinterpret_cast<E*>(hp.lo_region + hp.data_off + par + hp.side_bytes) : nullptr;
+    E* push_hi = (push && hp.hi_region) ? reinterpret_cast<E*>(hp.hi_region + hp.data_off + par) : nullptr;
+    const int64_t hi0 = n - hp.he;
+    ktime_cta(p2p, 0);
+
+    const int64_t npk = n / EPP;
+    double nrm = 0.0;
+    for (int64_t pk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pk < npk; pk += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t off = pk * EPP;
+        P a = ld_pack<P>(w + off);
+        const E* vp = V + off;
+        int i = 0;
+        for (; i + UA <= j; i += UA) {
+            P v[UA];
+#pragma unroll
+            for (int u = 0; u < UA; ++u) v[u] = ld_pack_nc<P>(vp + (int64_t)(i + u) * ld);
+#pragma unroll
+            for (int u = 0; u < UA; ++u) {
+                const E ci = cs[i + u];
+#pragma unroll
+                for (int e = 0; e < EPP; ++e) fnma(a.v[e], v[u].v[e], ci);
+            }
+        }
+        for (; i < j; ++i) {
+            const P v = ld_pack_nc<P>(vp + (int64_t)i * ld);
+            const E ci = cs[i];
+#pragma unroll
+            for (int e = 0; e < EPP; ++e) fnma(a.v[e], v.v[e], ci);
+        }
+        if (exact) {
+#pragma unroll
+            for (int e = 0; e < EPP; ++e) nrm += abs2_w(a.v[e]);
+        } else if (do_scale) {
+#pragma unroll
+            for (int e = 0; e < EPP; ++e) a.v[e] = rscale(a.v[e], inv);
+        }
+        st_pack(w + off, a);
+        if (push_lo && off < hp.he) {
+#pragma unroll
+            for (int e = 0; e < EPP; ++e) if (off + e < hp.he) push_lo[off + e] = a.v[e];
+        }
+        if (push_hi && off + EPP > hi0) {
+#pragma unroll
+            for (int e = 0; e < EPP; ++e) if (off + e >= hi0) push_hi[off + e - hi0] = a.v[e];
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int64_t t = npk * EPP; t < n; ++t) {
+            E a = w[t];
+            for (int i = 0; i < j; ++i) fnma(a, V[(int64_t)i * ld + t], cs[i]);
+            if (exact) nrm += abs2_w(a); else if (do_scale) a = rscale(a, inv);
+            w[t] = a;
+            if (push_lo && t < hp.he) push_lo[t] = a;
+            if (push_hi && t >= hi0) push_hi[t - hi0] = a;
+        }
+    }
+    // ---- ticket: the last CTA to finish finalises the step ----
+    __syncthreads();
+    ktime_cta(p2p, 1);
+    if (exact) {
+        const double a = warp_sum(nrm);
+        __syncthreads();
+        if (lane == 0) sm[wid] = a;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = sm[0];
+            for (int q = 1; q < (int)(blockDim.x >> 5); ++q) t += sm[q];
+            partial[blockIdx.x] = t;
+        }
+    }
+    if (push) __threadfence_system();
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1u);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    __shared__ double s_val;
+    if (exact) {
+        const double t = reduce_scalar_last(partial, (int)gridDim.x);
+        if (threadIdx.x == 0) { W o = zero_v(W()); *reinterpret_cast<double*>(&o) = t; nrm2_out[0] = o; }
+        __syncthreads();
+        if (p2p.world > 1) p2p_allreduce_cta<W>(p2p, nrm2_out, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) s_val = wreal(nrm2_out[0]);
+    } else if (threadIdx.x == 0) {
+        W o = zero_v(W()); *reinterpret_cast<double*>(&o) = pred; nrm2_out[0] = o;
+        s_val = pred;
+    }
+    __syncthreads();
+    if (fp.mode != 4) {
+        E* hcol = reinterpret_cast<E*>(fp.hcol);
+        const W* c1 = reinterpret_cast<const W*>(fp.c1);
+        if (c1 && hcol)
+            for (int i = threadIdx.x; i < j; i += blockDim.x) { W a = c1[i]; wadd(a, c[i]); narrow(a, hcol[i]); }
+        if (threadIdx.x == 0)
+            step_decide<K>(sqrt(fabs(s_val)), hcol, j, fp.tol, fp.atol, fp.inv_dev, fp.flags, fp.kstep, fp.mode);
+    }
+    ktime_last(p2p, 1);
+    if (threadIdx.x == 0) {
+        fp.flags[F_SCALED] = exact ? 0 : 1;
+        *counter = 0u;
+        if (push) {
+            // all CTAs of this rank have stored (and fenced) their boundary rows: publish the epoch to the
+            // neighbours; the NEXT stencil kernel waits for theirs (k_stencil*: halo_wait), not this kernel
+            __threadfence_system();
+            if (hp.lo_region) st_volatile_u32(reinterpret_cast<unsigned*>(hp.lo_region + 128), ep);
+            if (hp.hi_region) st_volatile_u32(reinterpret_cast<unsigned*>(hp.hi_region), ep);
+            *hp.epoch = ep;
         }
     }
 }
@@ -518,30 +682,24 @@ static void multidot_t(cudaStream_t s, const void* V, int64_t ld, int j, const v
         int64_t nb1 = (npk1 + 256 * 4 - 1) / (256 * 4);
         if (nb1 < 1) nb1 = 1;
         if (nb1 > 4 * (int64_t)sms) nb1 = 4 * (int64_t)sms;
-        if (nb1 > MAX_ROWBLOCKS) nb1 = MAX_ROWBLOCKS;
+        if (nb1 > RT_MAXROWS) nb1 = RT_MAXROWS;
         k_dot2<K><<<(int)nb1, 256, 0, s>>>((const E*)V, (const E*)w, n, (W*)partial, (W*)out, counter, flags, p2p ? *p2p : P2P());
         return;
     }
-    // grid: fixed function of the problem size (2 resident CTAs per SM), never of timing.  Tile size:
-    // the largest of 4/2/1 packs per thread that still leaves >= 12 tiles per CTA, so the ceil() in the
-    // tile split costs < 8 % (at 1/8 of C2 per GPU, 4-pack tiles gave 3.46 tiles per CTA = 86 % balance).
     const int64_t npk = n / Tr<K>::EPP;
-    int64_t nb = 2 * (int64_t)sms;
-    int pt = 4;
-    while (pt > 1 && (npk + (int64_t)MD_THREADS * pt - 1) / ((int64_t)MD_THREADS * pt) < 12 * nb) pt >>= 1;
-    const int64_t ntiles = (npk + (int64_t)MD_THREADS * pt - 1) / ((int64_t)MD_THREADS * pt);
-    if (nb > ntiles) nb = ntiles;
-    if (nb < 1) nb = 1;
-    if (nb > MAX_ROWBLOCKS) nb = MAX_ROWBLOCKS;
-    const size_t sh = (size_t)(MD_THREADS / 32) * (size_t)(j + 1) * sizeof(W);
-    static const bool attr_once = (cudaFuncSetAttribute(k_multidot<K, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024),
-                                   cudaFuncSetAttribute(k_multidot<K, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024),
-                                   cudaFuncSetAttribute(k_multidot<K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024), true);
-    (void)attr_once;
     const P2P pp = p2p ? *p2p : P2P();
-    if (pt == 4) k_multidot<K, 4><<<(int)nb, MD_THREADS, sh, s>>>((const E*)V, ld, j, (const E*)w, n, (W*)partial, (W*)out, counter, flags, pp);
-    else if (pt == 2) k_multidot<K, 2><<<(int)nb, MD_THREADS, sh, s>>>((const E*)V, ld, j, (const E*)w, n, (W*)partial, (W*)out, counter, flags, pp);
-    else k_multidot<K, 1><<<(int)nb, MD_THREADS, sh, s>>>((const E*)V, ld, j, (const E*)w, n, (W*)partial, (W*)out, counter, flags, pp);
+    // grid: fixed function of the problem size (2 resident CTAs per SM), never of timing.  The kernel balances the
+    // rows over the CTAs in 32-pack groups, so the tile size only has to fit a CTA's share: 4 packs of w per
+    // thread whenever a CTA owns at least ~one such tile, smaller tiles for small vectors.
+    const int64_t ngroups = (npk + 31) / 32;
+    int64_t nb = 2 * (int64_t)sms;
+    if (nb > ngroups) nb = ngroups;
+    if (nb < 1) nb = 1;
+    if (nb > RT_MAXROWS) nb = RT_MAXROWS;
+    const size_t sh = (size_t)(MD_THREADS / 32) * (size_t)(j + 1) * sizeof(W);
+    static const SmemAttrOnce attr((const void*)k_multidot<K>, 160 * 1024);
+    attr.ensure();
+    k_multidot<K><<<(int)nb, MD_THREADS, sh, s>>>((const E*)V, ld, j, (const E*)w, n, (W*)partial, (W*)out, counter, flags, pp);
 }
 void launch_multidot(int kind, cudaStream_t s, const void* V, int64_t ld, int j, const void* w, int64_t n,
                      void* partial, void* out, unsigned* counter, const int* flags, int sms, const P2P* p2p) {
@@ -582,6 +740,34 @@ void launch_multiaxpy(int kind, cudaStream_t s, const void* V, int64_t ld, int j
 }
 
 template <int K>
+static void multiaxpy_fin_t(cudaStream_t s, const void* V, int64_t ld, int j, const void* c1, const void* c2, void* w, int64_t n,
+                            void* partial, void* nrm2_out, unsigned* counter, void* hcol, double tol, double atol,
+                            void* inv_dev, int* flags, int kstep, int mode, int sms, const P2P* p2p, const HaloP2P* hp) {
+    using E = typename Tr<K>::E; using W = typename Tr<K>::W;
+    const int64_t npk = n / Tr<K>::EPP;
+    int64_t nb = (npk + 255) / 256;
+    if (nb < 1) nb = 1;
+    if (nb > 2 * sms * 2) nb = 2 * sms * 2;
+    if (nb > MAX_ROWBLOCKS) nb = MAX_ROWBLOCKS;
+    const size_t sh = (size_t)(j > 0 ? j : 1) * sizeof(E);
+    FinParams fp;
+    fp.c1 = c1; fp.hcol = hcol; fp.tol = tol; fp.atol = atol; fp.inv_dev = (double*)inv_dev; fp.flags = flags;
+    fp.kstep = kstep; fp.mode = mode;
+    k_multiaxpy_fin<K><<<(int)nb, 256, sh, s>>>((const E*)V, ld, j, (const W*)c2, (E*)w, n, (double*)partial, (W*)nrm2_out, counter,
+                                               fp, p2p ? *p2p : P2P(), hp ? *hp : HaloP2P());
+}
+void launch_multiaxpy_fin(int kind, cudaStream_t s, const void* V, int64_t ld, int j, const void* c1, const void* c2, void* w,
+                          int64_t n, void* partial, void* nrm2_out, unsigned* counter, void* hcol, double tol, double atol,
+                          void* inv_dev, int* flags, int kstep, int mode, int sms, const P2P* p2p, const HaloP2P* hp) {
+    switch (kind) {
+        case KS: multiaxpy_fin_t<KS>(s, V, ld, j, c1, c2, w, n, partial, nrm2_out, counter, hcol, tol, atol, inv_dev, flags, kstep, mode, sms, p2p, hp); break;
+        case KD: multiaxpy_fin_t<KD>(s, V, ld, j, c1, c2, w, n, partial, nrm2_out, counter, hcol, tol, atol, inv_dev, flags, kstep, mode, sms, p2p, hp); break;
+        case KC: multiaxpy_fin_t<KC>(s, V, ld, j, c1, c2, w, n, partial, nrm2_out, counter, hcol, tol, atol, inv_dev, flags, kstep, mode, sms, p2p, hp); break;
+        default: multiaxpy_fin_t<KZ>(s, V, ld, j, c1, c2, w, n, partial, nrm2_out, counter, hcol, tol, atol, inv_dev, flags, kstep, mode, sms, p2p, hp); break;
+    }
+}
+
+template <int K>
 static void multidot2_t(cudaStream_t s, const void* V, int64_t ld, int j, const void* w0, const void* w1, int64_t n,
                         void* partial, void* out, unsigned* counter, const int* flags, int sms, const P2P* p2p) {
     using E = typename Tr<K>::E; using W = typename Tr<K>::W;
@@ -591,8 +777,8 @@ static void multidot2_t(cudaStream_t s, const void* V, int64_t ld, int j, const 
     if (nb > ntiles) nb = ntiles;
     if (nb < 1) nb = 1;
     const size_t sh = (size_t)(MD_THREADS / 32) * 2 * (size_t)(j + 1) * sizeof(W);
-    static const bool attr_once = (cudaFuncSetAttribute(k_multidot2<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), true);
-    (void)attr_once;
+    static const SmemAttrOnce attr((const void*)k_multidot2<K>, 200 * 1024);
+    attr.ensure();
     k_multidot2<K><<<(int)nb, MD_THREADS, sh, s>>>((const E*)V, ld, j, (const E*)w0, (const E*)w1, n, (W*)partial, (W*)out,
                                                    counter, flags, p2p ? *p2p : P2P());
 }
@@ -613,8 +799,8 @@ static void multiaxpy2_t(cudaStream_t s, const void* V, int64_t ld, int j, const
     if (nb < 1) nb = 1;
     if (nb > 4 * (int64_t)sms) nb = 4 * (int64_t)sms;
     const size_t sh = (size_t)2 * (j > 0 ? j : 1) * sizeof(E);
-    static const bool attr_once = (cudaFuncSetAttribute(k_multiaxpy2<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024), true);
-    (void)attr_once;
+    static const SmemAttrOnce attr((const void*)k_multiaxpy2<K>, 160 * 1024);
+    attr.ensure();
     k_multiaxpy2<K><<<(int)nb, 256, sh, s>>>((const E*)V, ld, j, (const W*)c, (E*)w0, (E*)w1, n, flags);
 }
 void launch_multiaxpy2(int kind, cudaStream_t s, const void* V, int64_t ld, int j, const void* c, void* w0, void* w1,

@@ -21,6 +21,14 @@ template <typename E, int PW> struct PackOps {
             for (int e = 0; e < PW; ++e) r.v[e] = __ldg(p + e);
             return r; }
     }
+    // halo data written by a peer GPU during this kernel's lifetime: bypass L1 (ld.global.cg)
+    static LKB_DI P ld_cg(const E* p) {
+        if constexpr (sizeof(P) == 16) { int4 r = __ldcg(reinterpret_cast<const int4*>(p)); return *reinterpret_cast<P*>(&r); }
+        else { P r;
+#pragma unroll
+            for (int e = 0; e < PW; ++e) r.v[e] = __ldcg(p + e);
+            return r; }
+    }
     static LKB_DI void st(E* p, const P& v) {
         if constexpr (sizeof(P) == 16) st_pack(p, v);
         else {
@@ -34,6 +42,36 @@ template <typename E, int PW> struct PackOps {
         return r; }
 };
 
+
+// Block decode shared by the two stencil kernels.  1-D grid, column block fastest (consecutive CTAs stream
+// consecutive segments of the same grid rows); the row groups are rotated by one so that the two groups that
+// read the inter-GPU halos (first / last row group in 2-D, first / last plane in 3-D) are scheduled LAST: the
+// slab interior is computed while the neighbours' halo rows are still in flight ("overlapped with the
+// interior update").  halo_wait: the halo-reading CTAs wait until the neighbours published the epoch the local
+// counter says (k_halo_push has already waited, so this is one load; after a push fused into k_multiaxpy_fin /
+// k_scale_dev nobody has waited yet and this is where the exchange is synchronised).
+struct StBlock { int64_t cb, rb, k; };
+template <int DIM>
+LKB_DI StBlock st_decode(int64_t ncb, int64_t nyb, int64_t nz) {
+    StBlock b;
+    const int64_t bid = blockIdx.x;
+    b.cb = bid % ncb;
+    const int64_t rg = bid / ncb;
+    if (DIM == 2) { b.k = 0; b.rb = (rg + 1) % nyb; }
+    else { b.rb = rg % nyb; b.k = (rg / nyb + 1) % nz; }
+    return b;
+}
+LKB_DI void halo_wait(const unsigned* halo_epoch, const unsigned* flag_lo, const unsigned* flag_hi, bool need_lo, bool need_hi) {
+    if (!halo_epoch || !(need_lo || need_hi)) return;      // uniform over the CTA
+    if (threadIdx.x == 0) {
+        const unsigned ep = *halo_epoch;
+        if (need_lo && flag_lo) spin_until(flag_lo, ep);
+        if (need_hi && flag_hi) spin_until(flag_hi, ep);
+        __threadfence_system();
+    }
+    __syncthreads();
+}
+
 // One CTA = 256 threads side by side along x (256*PW points of one grid row), marching RY rows in y
 // (2.5-D blocking): the south / centre / north packs of a column live in registers, so every x
 // element is loaded from HBM once per CTA (+2 halo rows per RY rows, served by L2 because the
@@ -46,33 +84,37 @@ __global__ void __launch_bounds__(256)
 k_stencil(const typename Tr<K>::E* __restrict__ x, typename Tr<K>::E* __restrict__ y,
           int64_t nx, int64_t ny, int64_t nz, Coef7<typename Tr<K>::E> cf,
           const typename Tr<K>::E* __restrict__ halo_lo, const typename Tr<K>::E* __restrict__ halo_hi,
-          const unsigned* __restrict__ halo_epoch, int64_t halo_parity_stride, const int* __restrict__ flags)
+          const unsigned* __restrict__ halo_epoch, int64_t halo_parity_stride, const unsigned* __restrict__ flag_lo,
+          const unsigned* __restrict__ flag_hi, int64_t ncb, const int* __restrict__ flags)
 {
     using E = typename Tr<K>::E;
     using PO = PackOps<E, PW>;
-    if (halo_epoch) {      // double-buffered p2p halos: pick the parity the preceding push kernel filled
+    if (flags && flags[F_STOP]) return;
+    if (halo_epoch) {      // double-buffered p2p halos: pick the parity of the current epoch
         const int64_t off = (int64_t)(*halo_epoch & 1u) * halo_parity_stride;
         if (halo_lo) halo_lo += off;
         if (halo_hi) halo_hi += off;
     }
     using P = typename PO::P;
-    if (flags && flags[F_STOP]) return;
     const int64_t npk_row = nx / PW;
-    const int64_t ip = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+    const int64_t nyb = (ny + RY - 1) / RY;
+    const StBlock sb = st_decode<DIM>(ncb, nyb, nz);
+    const int64_t ip = sb.cb * blockDim.x + threadIdx.x;
     const bool active = ip < npk_row;                 // inactive lanes still take part in the shuffles
     const int64_t i0 = (active ? ip : npk_row - 1) * PW;
-    const int64_t nyb = (ny + RY - 1) / RY;
-    const int64_t k = (DIM == 3) ? (int64_t)blockIdx.x / nyb : 0;
-    const int64_t j0 = ((int64_t)blockIdx.x % nyb) * RY;
+    const int64_t k = sb.k;
+    const int64_t j0 = sb.rb * RY;
     const int64_t j1 = min(ny, j0 + RY);
+    halo_wait(halo_epoch, flag_lo, flag_hi, halo_lo && (DIM == 2 ? j0 == 0 : k == 0),
+              halo_hi && (DIM == 2 ? j1 >= ny : k == nz - 1));
     const int64_t plane = nx * ny;
     const E* xk = x + k * plane;
     const int lane = threadIdx.x & 31;
 
     auto getrow = [&](int64_t j) -> P {
         if (DIM == 2) {
-            if (j < 0) return halo_lo ? PO::ld(halo_lo + i0) : PO::zero();
-            if (j >= ny) return halo_hi ? PO::ld(halo_hi + i0) : PO::zero();
+            if (j < 0) return halo_lo ? PO::ld_cg(halo_lo + i0) : PO::zero();
+            if (j >= ny) return halo_hi ? PO::ld_cg(halo_hi + i0) : PO::zero();
         } else {
             if (j < 0 || j >= ny) return PO::zero();
         }
@@ -99,8 +141,8 @@ k_stencil(const typename Tr<K>::E* __restrict__ x, typename Tr<K>::E* __restrict
         }
         P down, up;
         if (DIM == 3) {
-            down = (k > 0) ? PO::ld(xk + p - plane) : (halo_lo ? PO::ld(halo_lo + p) : PO::zero());
-            up = (k < nz - 1) ? PO::ld(xk + p + plane) : (halo_hi ? PO::ld(halo_hi + p) : PO::zero());
+            down = (k > 0) ? PO::ld(xk + p - plane) : (halo_lo ? PO::ld_cg(halo_lo + p) : PO::zero());
+            up = (k < nz - 1) ? PO::ld(xk + p + plane) : (halo_hi ? PO::ld_cg(halo_hi + p) : PO::zero());
         }
         P out;
 #pragma unroll
@@ -160,7 +202,8 @@ __global__ void __launch_bounds__(ST_TX)
 k_stencil_smem(const typename Tr<K>::E* __restrict__ x, typename Tr<K>::E* __restrict__ y,
                int64_t nx, int64_t ny, int64_t nz, Coef7<typename Tr<K>::E> cf,
                const typename Tr<K>::E* __restrict__ halo_lo, const typename Tr<K>::E* __restrict__ halo_hi,
-               const unsigned* __restrict__ halo_epoch, int64_t halo_parity_stride, const int* __restrict__ flags)
+               const unsigned* __restrict__ halo_epoch, int64_t halo_parity_stride, const unsigned* __restrict__ flag_lo,
+               const unsigned* __restrict__ flag_hi, int64_t ncb, const int* __restrict__ flags)
 {
     using E = typename Tr<K>::E;
     using P = Pack<E, PW>;
@@ -177,13 +220,16 @@ k_stencil_smem(const typename Tr<K>::E* __restrict__ x, typename Tr<K>::E* __res
     P* up = dn + RY * ST_TX;                                       // [RY][ST_TX]
     const int tx = threadIdx.x;
     const int64_t npk_row = nx / PW;
-    const int64_t ip = (int64_t)blockIdx.y * ST_TX + tx;
+    const int64_t nyb = (ny + RY - 1) / RY;
+    const StBlock sb = st_decode<DIM>(ncb, nyb, nz);
+    const int64_t ip = sb.cb * ST_TX + tx;
     const bool active = ip < npk_row;
     const int64_t i0 = ip * PW;
-    const int64_t nyb = (ny + RY - 1) / RY;
-    const int64_t k = (DIM == 3) ? (int64_t)blockIdx.x / nyb : 0;
-    const int64_t j0 = ((int64_t)blockIdx.x % nyb) * RY;
+    const int64_t k = sb.k;
+    const int64_t j0 = sb.rb * RY;
     const int64_t plane = nx * ny;
+    halo_wait(halo_epoch, flag_lo, flag_hi, halo_lo && (DIM == 2 ? j0 == 0 : k == 0),
+              halo_hi && (DIM == 2 ? j0 + RY >= ny : k == nz - 1));
     const E* xk = x + k * plane;
     P zero;
 #pragma unroll
@@ -270,11 +316,12 @@ static void stencil_launch(cudaStream_t s, const StencilArgs& a, const void* x, 
     if (variant >= 1) {
         // shared-memory halo-staged kernel
 #define LKB_STS(RY_) { const int64_t nyb_ = (a.ny + RY_ - 1) / RY_; \
-            dim3 grid_((unsigned)(nyb_ * (DIM == 3 ? a.nz : 1)), (unsigned)((npk_row + ST_TX - 1) / ST_TX)); \
+            const int64_t ncb_ = (npk_row + ST_TX - 1) / ST_TX; \
+            const unsigned grid_ = (unsigned)(nyb_ * (DIM == 3 ? a.nz : 1) * ncb_); \
             const size_t sh_ = (size_t)((RY_ + 2) + (DIM == 3 ? 2 * RY_ : 0)) * ST_TX * sizeof(Pack<E, PW>); \
-            static const bool once_ = (cudaFuncSetAttribute(k_stencil_smem<K, PW, DIM, RY_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024), true); (void)once_; \
+            static const SmemAttrOnce once_((const void*)k_stencil_smem<K, PW, DIM, RY_>, 96 * 1024); once_.ensure(); \
             k_stencil_smem<K, PW, DIM, RY_><<<grid_, ST_TX, sh_, s>>>((const E*)x, (E*)y, a.nx, a.ny, a.nz, cf, \
-                (const E*)a.halo_lo, (const E*)a.halo_hi, a.halo_epoch, a.halo_parity_stride, flags); }
+                (const E*)a.halo_lo, (const E*)a.halo_hi, a.halo_epoch, a.halo_parity_stride, a.flag_lo, a.flag_hi, ncb_, flags); }
         if (variant == 3) LKB_STS(4) else LKB_STS(8)
 #undef LKB_STS
         return;
@@ -284,10 +331,11 @@ static void stencil_launch(cudaStream_t s, const StencilArgs& a, const void* x, 
     // prefetch were slower, warp-shuffle x-halo made no difference).
     constexpr int RY = 8;
     const int64_t nyb = (a.ny + RY - 1) / RY;
-    dim3 grid((unsigned)(nyb * (DIM == 3 ? a.nz : 1)), (unsigned)((npk_row + 255) / 256));
+    const int64_t ncb = (npk_row + 255) / 256;
+    const unsigned grid = (unsigned)(nyb * (DIM == 3 ? a.nz : 1) * ncb);
     k_stencil<K, PW, DIM, RY, 1, false><<<grid, 256, 0, s>>>((const E*)x, (E*)y, a.nx, a.ny, a.nz, cf,
                                                              (const E*)a.halo_lo, (const E*)a.halo_hi, a.halo_epoch,
-                                                             a.halo_parity_stride, flags);
+                                                             a.halo_parity_stride, a.flag_lo, a.flag_hi, ncb, flags);
 }
 
 template <int K>

@@ -8,6 +8,8 @@
 #include "lkb_kernels.h"
 #include "lkb_rng.h"
 #include "lkb_p2p.cuh"
+#include "lkb_step.cuh"
+#include "lkb_reduce.cuh"
 
 namespace lkb {
 
@@ -91,31 +93,77 @@ k_scal(typename Tr<K>::E alpha, typename Tr<K>::E* __restrict__ x, int64_t n)
         for (int64_t t = npk * EPP; t < n; ++t) x[t] = mul_v(x[t], alpha);
 }
 
-// x *= *inv (real scalar on the device).  Gate: (!stop || info == kstep) && !refill.
+// x *= *inv (real scalar on the device).  Gate: !scaled && (!stop || info == kstep) && !refill.
+// flags[F_SCALED] is raised by k_multiaxpy_fin when it already normalised the vector (the usual case): this
+// kernel is then an empty launch.  With a P2P halo descriptor (hp.he > 0, multi-GPU stencil inside a Krylov
+// loop) the finished boundary rows are also stored into the neighbours' halo buffers and the epoch is
+// published, exactly as k_multiaxpy_fin does on its fast path -- whichever kernel finishes the vector pushes.
 template <int K>
 __global__ void __launch_bounds__(256)
 k_scale_dev(typename Tr<K>::E* __restrict__ x, int64_t n, const double* __restrict__ inv_dev,
-            const int* __restrict__ flags, int kstep)
+            const int* __restrict__ flags, int kstep, const HaloP2P hp)
 {
     using E = typename Tr<K>::E;
     using Rl = typename Tr<K>::Rl;
     constexpr int EPP = Tr<K>::EPP;
     using P = Pack<E, EPP>;
     if (flags) {
+        if (flags[F_SCALED]) return;
         if (flags[F_STOP] && flags[F_INFO] != kstep) return;
         if (flags[F_REFILL]) return;
     }
     const Rl inv = (Rl)(*inv_dev);
-    if (inv == (Rl)1) return;
+    const bool push = hp.he > 0;
+    if (inv == (Rl)1 && !push) return;
+    const unsigned ep = push ? *hp.epoch + 1u : 0u;
+    const size_t par = (size_t)(ep & 1u) * 2 * hp.side_bytes;
+    E* push_lo = (push && hp.lo_region) ? reinterpret_cast<E*>(hp.lo_region + hp.data_off + par + hp.side_bytes) : nullptr;
+    E* push_hi = (push && hp.hi_region) ? reinterpret_cast<E*>(hp.hi_region + hp.data_off + par) : nullptr;
+    const int64_t hi0 = n - hp.he;
     const int64_t npk = n / EPP;
     for (int64_t pk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pk < npk; pk += (int64_t)gridDim.x * blockDim.x) {
-        P xv = ld_pack<P>(x + pk * EPP);
+        const int64_t off = pk * EPP;
+        P xv = ld_pack<P>(x + off);
 #pragma unroll
         for (int e = 0; e < EPP; ++e) xv.v[e] = rscale(xv.v[e], inv);
-        st_pack(x + pk * EPP, xv);
+        st_pack(x + off, xv);
+        if (push_lo && off < hp.he) {
+#pragma unroll
+            for (int e = 0; e < EPP; ++e) if (off + e < hp.he) push_lo[off + e] = xv.v[e];
+        }
+        if (push_hi && off + EPP > hi0) {
+#pragma unroll
+            for (int e = 0; e < EPP; ++e) if (off + e >= hi0) push_hi[off + e - hi0] = xv.v[e];
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0)
-        for (int64_t t = npk * EPP; t < n; ++t) x[t] = rscale(x[t], inv);
+        for (int64_t t = npk * EPP; t < n; ++t) {
+            const E a = rscale(x[t], inv);
+            x[t] = a;
+            if (push_lo && t < hp.he) push_lo[t] = a;
+            if (push_hi && t >= hi0) push_hi[t - hi0] = a;
+        }
+    if (!push) return;
+    __shared__ bool is_last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(hp.ticket, 1u) == gridDim.x - 1u);
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+        __threadfence_system();
+        if (hp.lo_region) st_volatile_u32(reinterpret_cast<unsigned*>(hp.lo_region + 128), ep);
+        if (hp.hi_region) st_volatile_u32(reinterpret_cast<unsigned*>(hp.hi_region), ep);
+        *hp.ticket = 0u;
+        *hp.epoch = ep;
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(256)
+k_copy_gated(const typename Tr<K>::E* __restrict__ src, typename Tr<K>::E* __restrict__ dst, int64_t n, const int* __restrict__ flags)
+{
+    if (flags && flags[F_STOP]) return;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
 }
 
 template <int K>
@@ -134,7 +182,8 @@ k_fill(typename Tr<K>::E* __restrict__ x, int64_t n, int64_t row0, int dist, uin
     }
 }
 
-// Column update of H / T / B after the second CGS pass; one CTA.
+// Column update of H / T / B after the second CGS pass; one CTA.  (Only on the paths that do not end in
+// k_multiaxpy_fin: j = 0, NCCL allreduce, host-driven loops.)
 //   hcol[0..j) = c1 + c2 (if c1),  beta = sqrt(|nrm2|),  hcol[j] = beta (or 0), inv = 1/beta
 template <int K>
 __global__ void k_update(const typename Tr<K>::W* __restrict__ c1, const typename Tr<K>::W* __restrict__ c2, int j,
@@ -152,29 +201,8 @@ __global__ void k_update(const typename Tr<K>::W* __restrict__ c1, const typenam
             narrow(a, hcol[i]);
         }
     if (threadIdx.x == 0) {
-        const double beta = sqrt(fabs(wreal(nrm2[0])));
-        if (beta != beta) flags[F_NAN] = 1;
-        Scalar hb; hb.re = beta; hb.im = 0.0;
-        double inv = 1.0;
-        if (mode == 0) {
-            // qr_no_pivoting (p = 1) uses its own default tol = atol for the refill decision
-            // (qr.fypp:125,146), arnoldi then tests |H(k+1,k)| < tol (arnoldi.fypp:59-71).
-            double hkk = beta;
-            if (beta < atol) { hkk = 0.0; flags[F_REFILL] = 1; }
-            else inv = 1.0 / beta;
-            hb.re = hkk;
-            if (hkk < tol) { flags[F_STOP] = 1; flags[F_INFO] = kstep; }
-        } else if (mode == 1) {          // lanczos.fypp:29-40: beta < tol => exit, no scaling
-            if (beta < tol) { flags[F_STOP] = 1; flags[F_INFO] = kstep; flags[F_REFILL] = 1; }
-            else inv = 1.0 / beta;
-        } else if (mode == 2) {          // golub_kahan.fypp:37-43: scale iff beta > tol
-            if (beta > tol) inv = 1.0 / beta;
-            else { flags[F_STOP] = 1; flags[F_INFO] = kstep; flags[F_REFILL] = 1; }
-        } else {                         // plain norm: no decision
-            inv = beta > 0.0 ? 1.0 / beta : 1.0;
-        }
-        if (hcol) { E h; from_scalar(hb, h); hcol[j] = h; }
-        *inv_dev = inv;
+        flags[F_SCALED] = 0;                  // the k_scale_dev that follows does the scaling
+        step_decide<K>(sqrt(fabs(wreal(nrm2[0]))), hcol, j, tol, atol, inv_dev, flags, kstep, mode);
     }
 }
 
@@ -265,18 +293,15 @@ k_cg_update(const typename Tr<K>::W* __restrict__ scal, const typename Tr<K>::W*
     }
     __syncthreads();
     if (is_last) {
-        if (wid == 0) {
-            __threadfence();
-            double t = 0.0;
-            for (int b = lane; b < (int)gridDim.x; b += 32) t += __ldcg(&partial[b]);
-            t = warp_sum(t);
-            if (lane == 0) {
-                W o = zero_v(W());
-                *reinterpret_cast<double*>(&o) = t;
-                nrm2_out[0] = o;
-                *counter = 0u;
-            }
+        __threadfence();
+        const double t = reduce_scalar_last(partial, (int)gridDim.x);
+        if (threadIdx.x == 0) {
+            W o = zero_v(W());
+            *reinterpret_cast<double*>(&o) = t;
+            nrm2_out[0] = o;
+            *counter = 0u;
         }
+        __syncthreads();
         if (p2p.world > 1) p2p_allreduce_cta<W>(p2p, nrm2_out, 1);
     }
 }
@@ -427,10 +452,18 @@ void launch_scal(int kind, cudaStream_t s, Scalar alpha, void* x, int64_t n, int
         k_scal<K><<<ew_grid(n / Tr<K>::EPP, sms), 256, 0, s>>>(a, (E*)x, n);
     });
 }
-void launch_scale_dev(int kind, cudaStream_t s, void* x, int64_t n, const void* inv_dev, const int* flags, int kstep, int sms) {
+void launch_scale_dev(int kind, cudaStream_t s, void* x, int64_t n, const void* inv_dev, const int* flags, int kstep, int sms,
+                      const HaloP2P* hp) {
+    const HaloP2P h = hp ? *hp : HaloP2P();
     LKB_DISPATCH(kind, {
         using E = typename Tr<K>::E;
-        k_scale_dev<K><<<ew_grid(n / Tr<K>::EPP, sms), 256, 0, s>>>((E*)x, n, (const double*)inv_dev, flags, kstep);
+        k_scale_dev<K><<<ew_grid(n / Tr<K>::EPP, sms), 256, 0, s>>>((E*)x, n, (const double*)inv_dev, flags, kstep, h);
+    });
+}
+void launch_copy_gated(int kind, cudaStream_t s, const void* src, void* dst, int64_t n, const int* flags, int sms) {
+    LKB_DISPATCH(kind, {
+        using E = typename Tr<K>::E;
+        k_copy_gated<K><<<ew_grid(n, sms), 256, 0, s>>>((const E*)src, (E*)dst, n, flags);
     });
 }
 void launch_fill(int kind, cudaStream_t s, void* x, int64_t n, int64_t row0, int dist, uint64_t seed, int sms) {

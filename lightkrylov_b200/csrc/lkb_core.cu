@@ -227,9 +227,9 @@ static int ctx_common(int device, lkb_ctx_s* c) {
     LKB_CUDA(cudaMalloc(&c->nrm2, 64));
     LKB_CUDA(cudaMalloc((void**)&c->inv, 64));
     LKB_CUDA(cudaMalloc((void**)&c->flags, F_COUNT * sizeof(int)));
-    LKB_CUDA(cudaMalloc((void**)&c->counter, 64));
+    LKB_CUDA(cudaMalloc((void**)&c->counter, 1024));      // global ticket + one per group of the reduction tree
     LKB_CUDA(cudaMemset(c->flags, 0, F_COUNT * sizeof(int)));
-    LKB_CUDA(cudaMemset(c->counter, 0, 64));
+    LKB_CUDA(cudaMemset(c->counter, 0, 1024));
     LKB_CUDA(cudaMemset(c->nrm2, 0, 64));
     LKB_TRY(ensure_ws(c, 272));
     LKB_TRY(ensure_hstage(c, 1 << 20));
@@ -274,6 +274,7 @@ int lkb_finalize(lkb_ctx_t c) {
     for (int r = 0; r < c->p2p.world; ++r) if (r != c->rank && c->p2p.peer[r]) cudaIpcCloseMemHandle(c->p2p.peer[r]);
     if (c->p2p_region) cudaFree(c->p2p_region);
     if (c->p2p.epoch) cudaFree(c->p2p.epoch);
+    if (c->p2p.dbg) cudaFree(c->p2p.dbg);
     void* bufs[] = { c->partial, c->c1, c->c2, c->tmpw, c->nrm2, c->inv, c->flags, c->counter, c->Hd, c->coefd };
     for (void* b : bufs) if (b) cudaFree(b);
     if (c->hstage) cudaFreeHost(c->hstage);
@@ -291,6 +292,8 @@ int lkb_set_option(lkb_ctx_t c, const char* name, int value) {
     invalidate_graphs(c, 0);          // cached step graphs were captured with the previous settings
     if (!strcmp(name, "graphs")) c->graphs = value != 0;
     else if (!strcmp(name, "fused")) c->fused = value != 0;
+    else if (!strcmp(name, "fin")) c->fin = value != 0;
+    else if (!strcmp(name, "fused_halo")) c->fused_halo = value != 0;
     else if (!strcmp(name, "p2p")) c->p2p_active = (value != 0) && c->p2p.world > 1;
     else { set_error("unknown option %s", name); return LKB_ERR_ARG; }
     return 0;
@@ -340,6 +343,27 @@ int lkb_get_profile(lkb_ctx_t c, double* ms8, int64_t* launches8) {
     return 0;
 }
 int64_t lkb_kernel_launches(lkb_ctx_t c) { return c->launches; }
+// In-kernel timeline of the reduction kernels (k_multidot, k_axpy_dot): %globaltimer at CTA start / main loop done /
+// ticket, and around the last CTA's stage-2 fold and allreduce.  Debug / measurement only (profiles/ktime_probe.py).
+int lkb_debug_ktime(lkb_ctx_t c, int enable) {
+    if (!c) return LKB_ERR_ARG;
+    cudaSetDevice(c->dev);
+    cudaStreamSynchronize(c->stream);
+    invalidate_graphs(c, 0);
+    if (enable) {
+        if (!c->p2p.dbg) LKB_CUDA(cudaMalloc((void**)&c->p2p.dbg, KT_WORDS * sizeof(unsigned long long)));
+        LKB_CUDA(cudaMemset(c->p2p.dbg, 0, KT_WORDS * sizeof(unsigned long long)));
+    } else if (!enable && c->p2p.dbg) {
+        cudaFree(c->p2p.dbg); c->p2p.dbg = nullptr;
+    }
+    return 0;
+}
+int lkb_debug_ktime_read(lkb_ctx_t c, uint64_t* out, int nwords) {
+    if (!c || !out || !c->p2p.dbg || nwords < 0 || nwords > KT_WORDS) { set_error("ktime_read: not enabled / bad size"); return LKB_ERR_ARG; }
+    LKB_CUDA(cudaStreamSynchronize(c->stream));
+    LKB_CUDA(cudaMemcpy(out, c->p2p.dbg, (size_t)nwords * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return 0;
+}
 
 // ---- vectors --------------------------------------------------------------------------------
 int lkb_vec_create(lkb_ctx_t c, int kind, int64_t n_local, int64_t n_global, int64_t row0, lkb_vec_t* v) {
@@ -500,8 +524,11 @@ static int stencil_create(lkb_ctx_t c, int kind, int dim, int64_t nx, int64_t ny
     op->halo_elems = dim == 2 ? nx : nx * ny;
     op->st.halo_lo = op->st.halo_hi = nullptr;
     if (c->world > 1) {
-        LKB_CUDA(cudaMalloc(&op->halo_lo, op->halo_elems * es));
-        LKB_CUDA(cudaMalloc(&op->halo_hi, op->halo_elems * es));
+        if (cudaMalloc(&op->halo_lo, op->halo_elems * es) != cudaSuccess || cudaMalloc(&op->halo_hi, op->halo_elems * es) != cudaSuccess) {
+            // (NCCL-halo fallback buffers; a failure here is local, but nothing collective has been issued yet)
+            set_error("stencil: cudaMalloc of the halo buffers failed"); cudaGetLastError();
+            lkb_op_destroy(op); return LKB_ERR_ALLOC;
+        }
         if (slow0 > 0) op->st.halo_lo = op->halo_lo;
         if (slow0 + nslow_local < nslow) op->st.halo_hi = op->halo_hi;
         if (c->p2p_active) {
@@ -538,7 +565,7 @@ static int stencil_create(lkb_ctx_t c, int kind, int dim, int64_t nx, int64_t ny
             }
             if (hbuf) cudaFree(hbuf);
             // every rank must take the same path: agree through one more (tiny) all-reduce-like exchange
-            LKB_TRY(ensure_ws(c, 2));
+            if (ensure_ws(c, 2) != 0) okflag = 0;     // (never return before the agreement step: the ranks would desynchronise)
             {
                 double v = okflag ? 0.0 : 1.0;
                 cudaMemcpyAsync(c->tmpw, &v, sizeof(double), cudaMemcpyHostToDevice, c->stream);
@@ -556,6 +583,8 @@ static int stencil_create(lkb_ctx_t c, int kind, int dim, int64_t nx, int64_t ny
                 if (has_hi) op->st.halo_hi = (char*)reg + 256 + side;       // parity 0, side 1
                 op->st.halo_epoch = ctr;
                 op->st.halo_parity_stride = (int64_t)(2 * side / es);
+                op->st.flag_lo = (const unsigned*)reg;                      // "lower neighbour pushed epoch e"
+                op->st.flag_hi = (const unsigned*)((char*)reg + 128);       // "upper neighbour pushed epoch e"
             } else {
                 if (op->hp_lo_map) cudaIpcCloseMemHandle(op->hp_lo_map);
                 if (op->hp_hi_map) cudaIpcCloseMemHandle(op->hp_hi_map);
@@ -565,8 +594,8 @@ static int stencil_create(lkb_ctx_t c, int kind, int dim, int64_t nx, int64_t ny
             }
         }
     }
-    const int64_t gy = op->st.ny * op->st.nz;
-    if (gy > 2147483647LL) { delete op; set_error("stencil: grid too large for this kernel (%lld row groups)", (long long)gy); return LKB_ERR_ARG; }
+    const int64_t gy = ((op->st.ny + 7) / 8) * op->st.nz * (nx / 128 + 1);     // upper bound on the 1-D grid of the stencil kernels
+    if (gy > 2147483647LL) { lkb_op_destroy(op); set_error("stencil: grid too large for this kernel (%lld CTAs)", (long long)gy); return LKB_ERR_ARG; }
     *A = op;
     return 0;
 }
@@ -579,57 +608,6 @@ int lkb_op_stencil7_create(lkb_ctx_t c, int kind, int64_t nx, int64_t ny, int64_
     return stencil_create(c, kind, 3, nx, ny, nz, coef7, slow0, nslow_local, A);
 }
 
-static int pick_lpr(int64_t nnz, int64_t rows) {
-    const double avg = rows > 0 ? (double)nnz / (double)rows : 0.0;
-    return avg >= 48 ? 32 : (avg >= 24 ? 16 : (avg >= 10 ? 8 : 4));
-}
-// rows = local rows of A, ncols_index = size of the column index space (global n for a sharded operator)
-static int csr_build(lkb_ctx_t c, lkb_op_s* op, int kind, int64_t rows, int64_t ncols_index, const int64_t* rowptr,
-                     const int32_t* col, const void* val) {
-    const int64_t nnz = rowptr[rows];
-    const size_t es = kind_size(kind);
-    op->lpr = pick_lpr(nnz, rows); op->t_lpr = pick_lpr(nnz, ncols_index);
-    LKB_CUDA(cudaMalloc((void**)&op->rowptr, (rows + 1) * sizeof(int64_t)));
-    LKB_CUDA(cudaMalloc((void**)&op->col, std::max<int64_t>(nnz, 1) * sizeof(int32_t)));
-    LKB_CUDA(cudaMalloc(&op->val, std::max<int64_t>(nnz, 1) * es));
-    LKB_CUDA(cudaMemcpy(op->rowptr, rowptr, (rows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
-    LKB_CUDA(cudaMemcpy(op->col, col, nnz * sizeof(int32_t), cudaMemcpyHostToDevice));
-    LKB_CUDA(cudaMemcpy(op->val, val, nnz * es, cudaMemcpyHostToDevice));
-    // explicit transpose (counting sort, host) so that rmatvec is a gather, not an atomic scatter
-    std::vector<int64_t> trp(ncols_index + 1, 0);
-    for (int64_t q = 0; q < nnz; ++q) trp[col[q] + 1]++;
-    for (int64_t j = 0; j < ncols_index; ++j) trp[j + 1] += trp[j];
-    std::vector<int32_t> tcol(std::max<int64_t>(nnz, 1));
-    std::vector<char> tval((size_t)std::max<int64_t>(nnz, 1) * es);
-    {
-        std::vector<int64_t> pos(trp.begin(), trp.end() - 1);
-        for (int64_t i = 0; i < rows; ++i)
-            for (int64_t q = rowptr[i]; q < rowptr[i + 1]; ++q) {
-                const int64_t d = pos[col[q]]++;
-                tcol[d] = (int32_t)i;
-                memcpy(&tval[(size_t)d * es], (const char*)val + (size_t)q * es, es);
-            }
-    }
-    LKB_CUDA(cudaMalloc((void**)&op->t_rowptr, (ncols_index + 1) * sizeof(int64_t)));
-    LKB_CUDA(cudaMalloc((void**)&op->t_col, std::max<int64_t>(nnz, 1) * sizeof(int32_t)));
-    LKB_CUDA(cudaMalloc(&op->t_val, std::max<int64_t>(nnz, 1) * es));
-    LKB_CUDA(cudaMemcpy(op->t_rowptr, trp.data(), (ncols_index + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
-    LKB_CUDA(cudaMemcpy(op->t_col, tcol.data(), nnz * sizeof(int32_t), cudaMemcpyHostToDevice));
-    LKB_CUDA(cudaMemcpy(op->t_val, tval.data(), nnz * es, cudaMemcpyHostToDevice));
-    return 0;
-}
-int lkb_op_csr_create(lkb_ctx_t c, int kind, int64_t m, int64_t n, const int64_t* rowptr, const int32_t* col,
-                      const void* val, lkb_op_t* A) {
-    if (!c || !A || !rowptr || m < 1 || n < 1) return LKB_ERR_ARG;
-    if (c->world > 1) { set_error("lkb_op_csr_create is single-rank; use lkb_op_csr_create_dist for a row-sharded matrix"); return LKB_ERR_ARG; }
-    cudaSetDevice(c->dev);
-    lkb_op_s* op = new lkb_op_s();
-    op->ctx = c; op->type = 3; op->kind = kind; op->m = m; op->n = n; op->uid = next_uid();
-    int r = csr_build(c, op, kind, m, n, rowptr, col, val);
-    if (r) { lkb_op_destroy(op); return r; }
-    *A = op;
-    return 0;
-}
 // Row-sharded CSR: this rank owns rows [row0, row0+m_local) of the m_global x n_global matrix with
 // GLOBAL column indices; input vectors of matvec are sharded over the column space as [col0, col0+n_local).
 //   matvec : all ranks' slabs of x are gathered into a full-length buffer (grouped ncclBroadcast, ragged slabs
@@ -655,18 +633,23 @@ int lkb_op_csr_create_dist(lkb_ctx_t c, int kind, int64_t m_global, int64_t n_gl
         NcclApi* api = nccl_api();
         if (!api) { lkb_op_destroy(op); return LKB_ERR_NCCL; }
         void* dbuf = nullptr;
-        LKB_CUDA(cudaMalloc(&dbuf, 32 * (size_t)(W + 1)));
         const int64_t mine[4] = {col0, n_local, row0, m_local};
-        LKB_CUDA(cudaMemcpy((char*)dbuf + 32 * (size_t)W, mine, 32, cudaMemcpyHostToDevice));
-        LKB_NCCL(api->AllGather((char*)dbuf + 32 * (size_t)W, dbuf, 32, /*ncclInt8*/ 0, c->comm, c->stream));
         std::vector<int64_t> all(4 * (size_t)W);
-        LKB_CUDA(cudaMemcpyAsync(all.data(), dbuf, 32 * (size_t)W, cudaMemcpyDeviceToHost, c->stream));
-        LKB_CUDA(cudaStreamSynchronize(c->stream));
-        cudaFree(dbuf);
+        bool ok = cudaMalloc(&dbuf, 32 * (size_t)(W + 1)) == cudaSuccess &&
+                  cudaMemcpy((char*)dbuf + 32 * (size_t)W, mine, 32, cudaMemcpyHostToDevice) == cudaSuccess &&
+                  api->AllGather((char*)dbuf + 32 * (size_t)W, dbuf, 32, /*ncclInt8*/ 0, c->comm, c->stream) == 0 &&
+                  cudaMemcpyAsync(all.data(), dbuf, 32 * (size_t)W, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess &&
+                  cudaStreamSynchronize(c->stream) == cudaSuccess;
+        if (dbuf) cudaFree(dbuf);
+        if (!ok) { set_error("csr_create_dist: slab exchange failed"); lkb_op_destroy(op); return LKB_ERR_NCCL; }
         for (int q = 0; q < W; ++q) { op->col_off[q] = all[4 * q]; op->col_cnt[q] = all[4 * q + 1]; op->row_off[q] = all[4 * q + 2]; op->row_cnt[q] = all[4 * q + 3]; }
     }
-    LKB_CUDA(cudaMalloc(&op->x_full, std::max<size_t>((size_t)n_global * es, 16)));
-    LKB_CUDA(cudaMalloc(&op->y_full, std::max<size_t>((size_t)n_global * es, 16)));
+    if (cudaMalloc(&op->x_full, std::max<size_t>((size_t)n_global * es, 16)) != cudaSuccess ||
+        cudaMalloc(&op->y_full, std::max<size_t>((size_t)n_global * es, 16)) != cudaSuccess ||
+        cudaMalloc(&op->y_red, std::max<size_t>((size_t)n_local * es, 16)) != cudaSuccess) {
+        set_error("csr_create_dist: cudaMalloc of the gather / reduce buffers failed"); cudaGetLastError();
+        lkb_op_destroy(op); return LKB_ERR_ALLOC;
+    }
     *A = op;
     return 0;
 }
@@ -697,7 +680,7 @@ int lkb_op_destroy(lkb_op_t A) {
     if (A->hp_lo_map) cudaIpcCloseMemHandle(A->hp_lo_map);
     if (A->hp_hi_map) cudaIpcCloseMemHandle(A->hp_hi_map);
     if (A->hp_active) { cudaFree(A->hp.my_region); cudaFree(A->hp.epoch); }
-    void* bufs[] = { A->halo_lo, A->halo_hi, A->rowptr, A->col, A->val, A->t_rowptr, A->t_col, A->t_val, A->a, A->x_full, A->y_full };
+    void* bufs[] = { A->halo_lo, A->halo_hi, A->rowptr, A->col, A->val, A->t_rowptr, A->t_col, A->t_val, A->a, A->x_full, A->y_full, A->y_red };
     for (void* b : bufs) if (b) cudaFree(b);
     delete A;
     return 0;
@@ -712,16 +695,20 @@ int lkb_op_reset_counters(lkb_op_t A) { A->n_matvec = A->n_rmatvec = 0; return 0
 }  // extern "C"
 
 namespace lkb {
-int op_apply_enqueue(lkb_op_s* A, const void* x, void* y, bool trans, const int* flags) {
+const HaloP2P* op_halo_desc(const lkb_op_s* A) {
+    const lkb_ctx_s* c = A->ctx;
+    return (A->type == 1 && c->world > 1 && A->hp_active && c->p2p_active && c->fused_halo && c->fin) ? &A->hp : nullptr;
+}
+int op_apply_enqueue(lkb_op_s* A, const void* x, void* y, bool trans, const int* flags, bool halo_prepushed) {
     lkb_ctx_s* c = A->ctx;
     const size_t es = kind_size(A->kind);
     int nl = 1;
     prof_begin(c, PC_MATVEC);
     if (A->type == 1) {
         if (c->world > 1 && A->hp_active) {
-            // halo exchange fused with its synchronisation over NVLink peer memory (k_halo_push)
-            launch_halo_push(A->kind, c->stream, A->hp, x, A->m, flags);
-            nl = 2;
+            // halo exchange over NVLink peer memory: pushed by the kernel that finished x, or by k_halo_push
+            // (copy + synchronisation in one kernel)
+            if (!halo_prepushed) { launch_halo_push(A->kind, c->stream, A->hp, x, A->m, flags); nl = 2; }
         } else if (c->world > 1) {
             // halo exchange over NCCL send/recv: my first row/plane -> rank-1's halo_hi, my last -> rank+1's halo_lo
             NcclApi* api = nccl_api();
@@ -766,9 +753,13 @@ int op_apply_enqueue(lkb_op_s* A, const void* x, void* y, bool trans, const int*
             launch_csr(A->kind, c->stream, A->n_global, A->t_rowptr, A->t_col, A->t_val, x, A->y_full, true, flags, c->sms | (A->t_lpr << 16));
             if (c->world > 1) {
                 LKB_NCCL(api->GroupStart());
+                // reduce into a scratch slab, then a flags-gated copy: after a device-side stop the reference leaves the
+                // later basis columns untouched, so stale reductions must not land in y
                 for (int q = 0; q < c->world; ++q)
-                    LKB_NCCL(api->Reduce((char*)A->y_full + (size_t)A->col_off[q] * es, y, (size_t)A->col_cnt[q] * per, dt, /*ncclSum*/ 0, q, c->comm, c->stream));
+                    LKB_NCCL(api->Reduce((char*)A->y_full + (size_t)A->col_off[q] * es, A->y_red, (size_t)A->col_cnt[q] * per, dt, /*ncclSum*/ 0, q, c->comm, c->stream));
                 LKB_NCCL(api->GroupEnd());
+                launch_copy_gated(A->kind, c->stream, A->y_red, y, A->n, flags, c->sms);
+                nl = 2;
             } else {
                 LKB_CUDA(cudaMemcpyAsync(y, (char*)A->y_full + (size_t)A->col_off[0] * es, (size_t)A->n * es, cudaMemcpyDeviceToDevice, c->stream));
             }

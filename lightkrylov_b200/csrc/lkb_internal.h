@@ -54,11 +54,13 @@ struct lkb_ctx_s {
     uint64_t seed = 0x1234abcdULL, seed_calls = 0;
     bool graphs = true;
     bool fused = true;
+    bool fin = true;            // final CGS2 pass fused with normalisation + column update (k_multiaxpy_fin)
+    bool fused_halo = true;     // P2P halo push fused into the kernel that finishes the next matvec input
     // in-kernel NVLink allreduce (CUDA IPC peer buffers); falls back to NCCL when not attached
     bool p2p_active = false;
     lkb::P2P p2p;
     void* p2p_region = nullptr;
-    const lkb::P2P* p2p_arg() const { return p2p_active ? &p2p : nullptr; }
+    const lkb::P2P* p2p_arg() const { return (p2p_active || p2p.dbg) ? &p2p : nullptr; }
     bool capturing = false;
     bool profile = false;
     int64_t launches = 0;
@@ -89,7 +91,7 @@ struct lkb_op_s {
     int64_t* t_rowptr = nullptr; int32_t* t_col = nullptr; void* t_val = nullptr; int t_lpr = 8;
     // row-sharded csr: full-length gather / scatter buffers and every rank's (offset, count) of the column and row spaces
     bool dist = false; int64_t m_global = 0, n_global = 0;
-    void* x_full = nullptr; void* y_full = nullptr;
+    void* x_full = nullptr; void* y_full = nullptr; void* y_red = nullptr;
     std::vector<int64_t> col_off, col_cnt, row_off, row_cnt;
     // dense
     void* a = nullptr;
@@ -119,15 +121,27 @@ inline void* col_ptr(const lkb_basis_s* b, int i) { return (char*)b->d + (size_t
 inline double atol_of(int kind) { return (kind == KS || kind == KC) ? 1e-6 : 1e-15; }   // Constants.f90:18-37
 inline double rtol_of(int kind) { return (kind == KS || kind == KC) ? 1e-3 : 3.1622776601683795e-08; }
 // enqueue y = A x (trans: y = A^H x) on the context stream, including halo exchange
-int op_apply_enqueue(lkb_op_s* A, const void* x, void* y, bool trans, const int* flags);
+// halo_prepushed: x's boundary rows were already stored into the neighbours' halo buffers by the kernel that
+// finished x (k_multiaxpy_fin / k_scale_dev with a HaloP2P descriptor): skip the k_halo_push kernel.
+int op_apply_enqueue(lkb_op_s* A, const void* x, void* y, bool trans, const int* flags, bool halo_prepushed = false);
+// descriptor for a fused halo push of this operator's next input vector, or nullptr (single GPU / NCCL halos / not a stencil)
+const lkb::HaloP2P* op_halo_desc(const lkb_op_s* A);
+// final-pass description of a CGS2 step that ends in k_multiaxpy_fin (see step_tail_enqueue)
+struct FinArgs { int mode; double tol; int kstep; void* hcol; bool with_c1; const lkb::HaloP2P* hp; };
 // enqueue one double Gram-Schmidt step of w against V(:, 0:j); leaves c1, c2 (and nrm2 if asked) in the workspace
 int dgs_enqueue(lkb_ctx_s* c, int kind, const void* V, int64_t ld, int j, void* w, int64_t n, int* flags,
-                bool want_norm, bool want_gsinfo);
+                bool want_norm, bool want_gsinfo, const FinArgs* fin = nullptr);
+int step_tail_enqueue(lkb_ctx_s* c, int kind, const void* V, int64_t ld, int j, void* w, int64_t n, int mode, double tol,
+                      int kstep, void* hcol, const lkb::HaloP2P* hp);
 int norm2_enqueue(lkb_ctx_s* c, int kind, const void* w, int64_t n, const int* flags);  // nrm2 <- ||w||^2
 int vec_norm_sync(lkb_ctx_s* c, int kind, const void* w, int64_t n, double* out);
 int vec_dot_sync(lkb_ctx_s* c, int kind, const void* x, const void* y, int64_t n, Scalar* out);
 int fetch_flags(lkb_ctx_s* c, int* host_flags);
 uint64_t next_seed(lkb_ctx_s* c);
+// CSR set-up (lkb_csr.cu): host arrays -> device + validation + explicit transpose; or finish arrays already on the device
+int csr_build(lkb_ctx_s* c, lkb_op_s* op, int kind, int64_t rows, int64_t ncols_index, const int64_t* rowptr,
+              const int32_t* col, const void* val);
+int csr_finish_device(lkb_ctx_s* c, lkb_op_s* op, int kind, int64_t rows, int64_t ncols_index);
 uint64_t next_uid();
 void invalidate_graphs(lkb_ctx_s* c, uint64_t uid);   // uid == 0: all
 int arnoldi_enqueue(lkb_op_s* A, lkb_basis_s* X, int kstart, int kend, double tol, bool tr);

@@ -12,7 +12,9 @@ namespace lkb {
 //   flags[2] refill    the new vector was numerically zero (< atol): host must rand-refill it
 //   flags[3] nan       a norm evaluated to NaN (reference: stop_error, qr.fypp:139-145)
 //   flags[4] gs_info   info of the last orthogonalize_against_basis pass (zero-vector check)
-enum { F_STOP = 0, F_INFO = 1, F_REFILL = 2, F_NAN = 3, F_GSINFO = 4, F_COUNT = 8 };
+//   flags[5], flags[6] iteration counter / converged (device-resident cg and gmres cycles)
+//   flags[7] scaled    k_multiaxpy_fin already normalised the new vector: the k_scale_dev that follows is a no-op
+enum { F_STOP = 0, F_INFO = 1, F_REFILL = 2, F_NAN = 3, F_GSINFO = 4, F_SCALED = 7, F_COUNT = 8 };
 
 enum { MD_CB = 16 };           // basis columns per multi-dot CTA
 enum { MD_THREADS = 256 };
@@ -25,8 +27,25 @@ struct P2P {
     int world = 1, rank = 0;
     unsigned* epoch = nullptr;          // device-side collective counter (identical on all ranks)
     char* peer[P2P_MAXW] = {nullptr};   // peer[r] = rank r's region as mapped in this process
+    // in-kernel timeline (lkb_debug_ktime): [cta][4] = {start, main loop done, ticket taken, -} then
+    // [4*MAX_ROWBLOCKS + {0,1,2}] = {stage-2 start, stage-2 done, allreduce done} of the last CTA (%globaltimer ns)
+    unsigned long long* dbg = nullptr;
 };
+enum { KT_WORDS = 4 * 1024 + 8 };
 static inline size_t p2p_region_bytes() { return (size_t)P2P_FLAG_BYTES + 2 * (size_t)P2P_MAXW * P2P_SLOT * 16; }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: set it once for every device a kernel is
+// launched on (a process may hold contexts on several GPUs), not once per process.
+struct SmemAttrOnce {
+    const void* fn; int bytes; mutable unsigned long long done = 0ULL;      // bit d = set on device d
+    SmemAttrOnce(const void* f, int b) : fn(f), bytes(b) {}
+    void ensure() const {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const unsigned long long bit = 1ULL << (dev & 63);
+        if (!(done & bit)) { cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); done |= bit; }
+    }
+};
 
 struct StencilArgs {
     int64_t nx, ny, nz;        // local slab: nx fastest; the slowest axis is the sharded one
@@ -38,6 +57,10 @@ struct StencilArgs {
     // (epoch & 1) * halo_parity_stride elements, epoch being the device counter of the push kernel
     const unsigned* halo_epoch = nullptr;
     int64_t halo_parity_stride = 0;
+    // flags the neighbours raise in this rank's halo region ("lower / upper neighbour pushed epoch e"): the CTAs
+    // that read a halo wait on them (see halo_wait in kernels_ops.cu)
+    const unsigned* flag_lo = nullptr;
+    const unsigned* flag_hi = nullptr;
 };
 // P2P halo push (kernels_ops.cu): my first / last `he` elements of x go straight into the neighbours' halo
 // buffers over NVLink; the last CTA signals the neighbours and waits for their pushes.
@@ -77,7 +100,16 @@ void launch_axpy_dev(int kind, cudaStream_t s, const void* alpha_dev, double sgn
                      const int* flags, int sms);
 void launch_scal(int kind, cudaStream_t s, Scalar alpha, void* x, int64_t n, int sms);
 // x *= *inv_dev (real, device); runs when !stop or info == kstep, and never when refill is set
-void launch_scale_dev(int kind, cudaStream_t s, void* x, int64_t n, const void* inv_dev, const int* flags, int kstep, int sms);
+void launch_scale_dev(int kind, cudaStream_t s, void* x, int64_t n, const void* inv_dev, const int* flags, int kstep, int sms,
+                      const HaloP2P* hp = nullptr);
+// Final CGS2 update fused with the normalisation (predicted norm), the H/T/B column update and, optionally, the
+// P2P halo push of the finished vector (kernels_gs.cu: k_multiaxpy_fin).  mode: 0 arnoldi, 1 lanczos, 2 bidiag,
+// 4 gmres (no column update).  c2 has j+1 entries, c2[j] = ||w'||^2.
+void launch_multiaxpy_fin(int kind, cudaStream_t s, const void* V, int64_t ld, int j, const void* c1, const void* c2, void* w,
+                          int64_t n, void* partial, void* nrm2_out, unsigned* counter, void* hcol, double tol, double atol,
+                          void* inv_dev, int* flags, int kstep, int mode, int sms, const P2P* p2p, const HaloP2P* hp);
+// dst = src unless flags[F_STOP] (E type, length n)
+void launch_copy_gated(int kind, cudaStream_t s, const void* src, void* dst, int64_t n, const int* flags, int sms);
 void launch_fill(int kind, cudaStream_t s, void* x, int64_t n, int64_t row0, int dist, uint64_t seed, int sms);
 
 // device-resident CG iteration (kernels_vec.cu): see k_cg_update / k_cg_check / k_cg_direction

@@ -19,7 +19,7 @@ using namespace lkb;
 namespace lkb {
 
 int dgs_enqueue(lkb_ctx_s* c, int kind, const void* V, int64_t ld, int j, void* w, int64_t n, int* flags,
-                bool want_norm, bool want_gsinfo) {
+                bool want_norm, bool want_gsinfo, const FinArgs* fin) {
     if (j <= 0) {
         if (want_norm) return norm2_enqueue(c, kind, w, n, flags);
         return 0;
@@ -56,12 +56,45 @@ int dgs_enqueue(lkb_ctx_s* c, int kind, const void* V, int64_t ld, int j, void* 
         launch_gsinfo(c->stream, (char*)c->c2 + (size_t)j * wsz, kind_cplx(kind), atol_of(kind), c->flags);
         c->launches++;
     }
+    if (fin) {
+        // pass-2 update + predicted-norm normalisation + H/T/B column + (optional) halo push in ONE kernel
+        prof_begin(c, PC_AXPY);
+        launch_multiaxpy_fin(kind, c->stream, V, ld, j, fin->with_c1 ? c->c1 : nullptr, c->c2, w, n, c->partial, c->nrm2, c->counter,
+                             fin->hcol, fin->tol, atol_of(kind), c->inv, flags, fin->kstep, fin->mode, c->sms, c->p2p_arg(), fin->hp);
+        prof_end(c, PC_AXPY, 1);
+        return check_launch(c, "multiaxpy_fin");
+    }
     prof_begin(c, PC_AXPY);
     launch_multiaxpy(kind, c->stream, V, ld, j, c->c2, w, n, want_norm, c->partial, c->nrm2, c->counter, flags, c->sms, c->p2p_arg());
     prof_end(c, PC_AXPY, 1);
     LKB_TRY(check_launch(c, "multiaxpy"));
     if (want_norm) LKB_TRY(allreduce_w(c, c->nrm2, 1));
     return 0;
+}
+
+// Orthogonalisation + normalisation + column update of ONE Krylov step (everything after the matvec):
+//   CGS2 of w against V(:, 0:j), beta = ||w||, column of H / T / B, breakdown decision, w /= beta.
+// mode 0 arnoldi (hcol(0:j) = c1 + c2), 1 lanczos, 2 bidiag (only hcol(j) = beta is written).
+// Default: the final pass is k_multiaxpy_fin (3 kernels + 1 empty launch per step, 2 reductions).  Falls back to
+// the round-1 sequence (multi-axpy with norm, allreduce, k_update, k_scale_dev) for j = 0, when the reductions
+// go through ncclAllReduce (the predicted norm must not be summed over ranks), or with option "fin" = 0.
+int step_tail_enqueue(lkb_ctx_s* c, int kind, const void* V, int64_t ld, int j, void* w, int64_t n, int mode, double tol,
+                      int kstep, void* hcol, const HaloP2P* hp) {
+    const bool fin_ok = c->fin && j > 0 && (c->world == 1 || c->p2p_active);
+    if (fin_ok) {
+        FinArgs fa; fa.mode = mode; fa.tol = tol; fa.kstep = kstep; fa.hcol = hcol; fa.with_c1 = (mode == 0); fa.hp = hp;
+        LKB_TRY(dgs_enqueue(c, kind, V, ld, j, w, n, c->flags, false, false, &fa));
+    } else {
+        LKB_TRY(dgs_enqueue(c, kind, V, ld, j, w, n, c->flags, true, false));
+        prof_begin(c, PC_OTHER);
+        launch_update(kind, c->stream, mode == 0 ? c->c1 : nullptr, mode == 0 ? c->c2 : nullptr, j, c->nrm2, hcol, tol,
+                      atol_of(kind), c->inv, c->flags, kstep, mode);
+        prof_end(c, PC_OTHER, 1);
+    }
+    prof_begin(c, PC_OTHER);
+    launch_scale_dev(kind, c->stream, w, n, c->inv, c->flags, kstep, c->sms, hp);
+    prof_end(c, PC_OTHER, 1);
+    return check_launch(c, "step tail");
 }
 
 // Run `body` (which only enqueues work on c->stream) either directly or through a cached CUDA graph.
@@ -386,16 +419,14 @@ int arnoldi_enqueue(lkb_op_s* A, lkb_basis_s* X, int kstart, int kend, double to
     LKB_TRY(ensure_ws(c, kend + 1));
     auto body = [&]() -> int {
         LKB_TRY(reset_flags(c));
+        bool pushed = false;       // X(k-1)'s boundary rows already sit in the neighbours' halo buffers
         for (int k = kstart; k <= kend; ++k) {
             void* w = col_ptr(X, k);
-            LKB_TRY(op_apply_enqueue(A, col_ptr(X, k - 1), w, tr, c->flags));
-            LKB_TRY(dgs_enqueue(c, kind, X->d, X->ld, k, w, X->n, c->flags, true, false));
-            prof_begin(c, PC_OTHER);
-            launch_update(kind, c->stream, c->c1, c->c2, k, c->nrm2, (char*)c->Hd + (size_t)ldhd * (k - 1) * es,
-                          tol, atol_of(kind), c->inv, c->flags, k, 0);
-            launch_scale_dev(kind, c->stream, w, X->n, c->inv, c->flags, k, c->sms);
-            prof_end(c, PC_OTHER, 2);
-            LKB_TRY(check_launch(c, "arnoldi update"));
+            LKB_TRY(op_apply_enqueue(A, col_ptr(X, k - 1), w, tr, c->flags, pushed));
+            // the kernel that finishes X(k) also pushes its halo rows for the next step's matvec
+            const HaloP2P* hp = (k < kend) ? op_halo_desc(A) : nullptr;
+            LKB_TRY(step_tail_enqueue(c, kind, X->d, X->ld, k, w, X->n, 0, tol, k, (char*)c->Hd + (size_t)ldhd * (k - 1) * es, hp));
+            pushed = hp != nullptr;
         }
         return 0;
     };
@@ -540,10 +571,11 @@ int lkb_lanczos(lkb_op_t A, lkb_basis_t X, void* T, int ldt, int32_t* info, int3
     const size_t ndw = 2 * (size_t)(kind_cplx(kind) ? 2 : 1);
     auto body = [&]() -> int {
         LKB_TRY(reset_flags(c));
+        bool pushed = false;
         for (int k = kstart; k <= kend; ++k) {
             void* w = col_ptr(X, k);
             char* tcol = (char*)c->Hd + (size_t)ldtd * (k - 1) * es;
-            LKB_TRY(op_apply_enqueue(A, col_ptr(X, k - 1), w, false, c->flags));
+            LKB_TRY(op_apply_enqueue(A, col_ptr(X, k - 1), w, false, c->flags, pushed));
             for (int i = (k - 1 > 1 ? k - 1 : 1); i <= k; ++i) {        // update_tridiag_matrix :57-59
                 void* xi = col_ptr(X, i - 1);
                 prof_begin(c, PC_DOT);
@@ -555,12 +587,9 @@ int lkb_lanczos(lkb_op_t A, lkb_basis_t X, void* T, int ldt, int32_t* info, int3
                 launch_axpy_dev(kind, c->stream, c->tmpw, -1.0, xi, w, X->n, c->flags, c->sms);
                 prof_end(c, PC_OTHER, 2);
             }
-            LKB_TRY(dgs_enqueue(c, kind, X->d, X->ld, k, w, X->n, c->flags, true, false));
-            prof_begin(c, PC_OTHER);
-            launch_update(kind, c->stream, nullptr, nullptr, k, c->nrm2, tcol, tol, atol_of(kind), c->inv, c->flags, k, 1);
-            launch_scale_dev(kind, c->stream, w, X->n, c->inv, c->flags, k, c->sms);
-            prof_end(c, PC_OTHER, 2);
-            LKB_TRY(check_launch(c, "lanczos update"));
+            const HaloP2P* hp = (k < kend) ? op_halo_desc(A) : nullptr;
+            LKB_TRY(step_tail_enqueue(c, kind, X->d, X->ld, k, w, X->n, 1, tol, k, tcol, hp));
+            pushed = hp != nullptr;
         }
         return 0;
     };
@@ -608,19 +637,10 @@ int lkb_bidiag(lkb_op_t A, lkb_basis_t U, lkb_basis_t V, void* B, int ldb, int32
             char* bcol = (char*)c->Hd + (size_t)ldbd * (k - 1) * es;
             void* vk = col_ptr(V, k - 1);
             LKB_TRY(op_apply_enqueue(A, col_ptr(U, k - 1), vk, true, c->flags));
-            LKB_TRY(dgs_enqueue(c, kind, V->d, V->ld, k - 1, vk, V->n, c->flags, true, false));
-            prof_begin(c, PC_OTHER);
-            launch_update(kind, c->stream, nullptr, nullptr, k - 1, c->nrm2, bcol, tol, atol_of(kind), c->inv, c->flags, 2 * k - 1, 2);
-            launch_scale_dev(kind, c->stream, vk, V->n, c->inv, c->flags, 2 * k - 1, c->sms);
-            prof_end(c, PC_OTHER, 2);
+            LKB_TRY(step_tail_enqueue(c, kind, V->d, V->ld, k - 1, vk, V->n, 2, tol, 2 * k - 1, bcol, nullptr));
             void* uk1 = col_ptr(U, k);
             LKB_TRY(op_apply_enqueue(A, vk, uk1, false, c->flags));
-            LKB_TRY(dgs_enqueue(c, kind, U->d, U->ld, k, uk1, U->n, c->flags, true, false));
-            prof_begin(c, PC_OTHER);
-            launch_update(kind, c->stream, nullptr, nullptr, k, c->nrm2, bcol, tol, atol_of(kind), c->inv, c->flags, 2 * k, 2);
-            launch_scale_dev(kind, c->stream, uk1, U->n, c->inv, c->flags, 2 * k, c->sms);
-            prof_end(c, PC_OTHER, 2);
-            LKB_TRY(check_launch(c, "bidiag update"));
+            LKB_TRY(step_tail_enqueue(c, kind, U->d, U->ld, k, uk1, U->n, 2, tol, 2 * k, bcol, nullptr));
         }
         return 0;
     };

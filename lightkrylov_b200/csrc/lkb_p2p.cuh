@@ -11,6 +11,18 @@
 
 namespace lkb {
 
+LKB_DI unsigned long long gtimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// record a timeline point of this CTA (thread 0 only; no-op unless lkb_debug_ktime enabled the buffer)
+LKB_DI void ktime_cta(const P2P& c, int slot) {
+    if (c.dbg && threadIdx.x == 0) c.dbg[(size_t)blockIdx.x * 4 + slot] = gtimer_ns();
+}
+LKB_DI void ktime_last(const P2P& c, int slot) {
+    if (c.dbg && threadIdx.x == 0) c.dbg[(size_t)4 * MAX_ROWBLOCKS + slot] = gtimer_ns();
+}
 LKB_DI unsigned ld_volatile_u32(const unsigned* p) {
     unsigned v;
     asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");

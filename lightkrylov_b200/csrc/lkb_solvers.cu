@@ -136,13 +136,22 @@ static int gmres_impl(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, doubl
     auto cleanup_dev = [&]() { cudaStreamSynchronize(c->stream); if (cycle_exec) cudaGraphExecDestroy(cycle_exec); if (gH) cudaFree(gH); if (ge) cudaFree(ge); if (gres) cudaFree(gres); };
     auto enqueue_cycle = [&]() -> int {
         char* gcs = (char*)ge + (size_t)(kdim + 1) * 16; char* gsn = gcs + (size_t)kdim * 16;
+        const bool fin_ok = c->fin && (c->world == 1 || c->p2p_active);
+        bool pushed = false;
         for (int kk = 1; kk <= kdim; ++kk) {
             void* w = col_ptr(V, kk);
-            LKB_TRY(op_apply_enqueue(A, col_ptr(V, kk - 1), w, trans, c->flags));
-            LKB_TRY(dgs_enqueue(c, kind, V->d, V->ld, kk, w, b->n, c->flags, true, false));
+            LKB_TRY(op_apply_enqueue(A, col_ptr(V, kk - 1), w, trans, c->flags, pushed));
+            const HaloP2P* hp = (kk < kdim) ? op_halo_desc(A) : nullptr;
+            if (fin_ok) {     // final pass normalises with the predicted norm (mode 4: k_gmres_update does the column)
+                FinArgs fa; fa.mode = 4; fa.tol = tol; fa.kstep = kk; fa.hcol = nullptr; fa.with_c1 = false; fa.hp = hp;
+                LKB_TRY(dgs_enqueue(c, kind, V->d, V->ld, kk, w, b->n, c->flags, false, false, &fa));
+            } else {
+                LKB_TRY(dgs_enqueue(c, kind, V->d, V->ld, kk, w, b->n, c->flags, true, false));
+            }
+            pushed = fin_ok && hp != nullptr;
             prof_begin(c, PC_OTHER);
             launch_gmres_update(kind, c->stream, c->c1, c->c2, kk, c->nrm2, gH, kdim + 1, ge, gcs, gsn, tol, c->inv, c->flags, gres);
-            launch_scale_dev(kind, c->stream, w, b->n, c->inv, c->flags, kk, c->sms);
+            launch_scale_dev(kind, c->stream, w, b->n, c->inv, c->flags, kk, c->sms, fin_ok ? hp : nullptr);
             prof_end(c, PC_OTHER, 2);
             LKB_TRY(check_launch(c, "gmres update"));
         }

@@ -151,6 +151,18 @@ def fill(n: int, kind: str, dist: str, seed: int, row0: int = 0) -> np.ndarray:
     return x
 
 
+def csr_random(kind: str, m: int, n: int, per_row: int, seed: int):
+    """Host twin of the device generator lkb_csr_random_device (BASELINE config 5): entry q = row*per_row
+    + slot has column floor(u(seed, q) * n), the columns of a row are sorted (duplicates stay separate entries, i.e.
+    are summed by the SpMV), and the value at sorted position q is normal(seed + 1, q).  Returns (rowptr, col, val)."""
+    u = fill(m * per_row, "d", "uniform", seed)
+    col = np.minimum(np.floor(u * float(n)), n - 1).astype(np.int32).reshape(m, per_row)
+    col.sort(axis=1)
+    val = fill(m * per_row, kind, "normal", seed + 1)
+    rowptr = np.arange(0, (m + 1) * per_row, per_row, dtype=np.int64)
+    return rowptr, col.ravel(), val
+
+
 def normalize(x: np.ndarray) -> None:
     getattr(lib(), f"lko_normalize_{kind_of(x.dtype)}")(C.c_int64(x.size), _ptr(x))
 

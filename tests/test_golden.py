@@ -56,7 +56,7 @@ def test_gpu_matches_golden_config1(kind):
     H = np.zeros((kdim + 1, kdim), dtype=lk.DTYPES[kind], order="F")
     assert lk.arnoldi(A, X, H) == int(g["info"])
     assert _rel(H, g["H"]) < _tol(kind)
-    assert _rel(X.get(kdim, 1)[:, 0], g["X_last"]) < _tol(kind) * 1e3
+    assert _rel(X.get(kdim, 1)[:, 0], g["X_last"]) < _tol(kind)
     del X, A
     ctx.close()
 
@@ -81,7 +81,7 @@ def test_gpu_matches_golden_poisson(kind):
     A2 = lk.LinOp.stencil5(ctx, kind, nx, ny, (6.0, -1.3, -0.7, -1.2, -0.8))
     b = lk.Vector(ctx, kind, n).fill_random("uniform", 43); x = lk.Vector(ctx, kind, n)
     info, meta = lk.gmres(A2, b, x, kdim=20, maxiter=20)
-    assert info == int(g["gmres_info"]) and _rel(x.get(), g["gmres_x"]) < 1e-8
-    np.testing.assert_allclose(meta["res"], g["gmres_res"], rtol=1e-6, atol=1e-14)
+    assert info == int(g["gmres_info"]) and _rel(x.get(), g["gmres_x"]) < 1e-10
+    assert _rel(np.array(meta["res"]), g["gmres_res"]) < 1e-10
     del X, Xl, A, A2, b, x, x0, xl
     ctx.close()

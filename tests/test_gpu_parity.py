@@ -2,7 +2,12 @@
 inputs, plus size-independent properties at the BASELINE.json sizes.
 
 Tolerances (BASELINE.json north_star): Hessenberg entries (normwise) and Ritz values 1e-10 in
-fp64 (1e-4 fp32); ||V^H V - I||_max <= 1e-12 (fp64).
+fp64 (1e-4 fp32); ||V^H V - I||_max <= 1e-12 (fp64).  Every comparison with the oracle in this file uses these
+two numbers (helpers.tol_for); residual histories and solution vectors are compared normwise with the same
+tolerance.  How much two CORRECT evaluations of the reference algorithm differ was measured by running the
+oracle with 1 and with 8 threads (different summation orders): fp64 H 3e-15, basis 1e-14, Ritz values 1e-14,
+gmres / cg residual histories 1e-14 of the initial residual, iteration counts identical; fp32 H 4e-6, basis
+1.4e-5, Ritz 1e-6, histories 8e-6 -- all far inside 1e-10 / 1e-4, so no tolerance here is loosened.
 """
 import numpy as np
 import pytest
@@ -207,16 +212,16 @@ def test_arnoldi_config1_dense_n128_kdim64(lk, ctx, oracle, kind):
     assert info == oinfo == 0
     assert rel_normwise(H, Ho) < tol_for(kind)
     Xg = X.get()
-    assert rel_normwise(Xg, Xo) < tol_for(kind) * 100
+    assert rel_normwise(Xg, Xo) < tol_for(kind)
     # the reference's own assertions (TestKrylov.fypp:218-239)
     assert np.abs(Ah @ Xg[:, :kdim] - Xg @ H).max() < lk.RTOL[kind] * np.abs(Ah).max() * 10
     assert np.abs(Xg.conj().T @ Xg - np.eye(kdim + 1)).max() < orth_tol(kind)
     ritz_g = np.linalg.eigvals(H[:kdim, :kdim].astype(np.complex128))
     ritz_o = np.linalg.eigvals(Ho[:kdim, :kdim].astype(np.complex128))
-    # nearest-neighbour matching (sorting conjugate pairs is order-unstable); interior Ritz values of a
-    # random non-normal matrix are ill-conditioned, hence the extra factor on top of the H tolerance
+    # nearest-neighbour matching (sorting conjugate pairs is order-unstable).  The Ritz values of this H are well
+    # conditioned (max eigenvalue condition number 8.6), so they meet the same tolerance as H itself.
     dist = np.abs(ritz_g[:, None] - ritz_o[None, :]).min(axis=1)
-    assert dist.max() / np.abs(ritz_o).max() < tol_for(kind) * 100
+    assert dist.max() / np.abs(ritz_o).max() < tol_for(kind)
     assert A.counters()[0] == kdim
 
 
@@ -307,7 +312,7 @@ def test_arnoldi_block(lk, ctx, oracle, p, kdim):
     Xg = X.get()
     assert np.abs(Ah @ Xg[:, :k] - Xg[:, :k + p] @ H[:k + p, :k]).max() < lk.RTOL["d"]
     assert np.abs(Xg[:, :k].T @ Xg[:, :k] - np.eye(k)).max() < 1e-12
-    assert rel_normwise(H[:, : k - p], Ho[:, : k - p]) < 1e-8
+    assert rel_normwise(H[:, : k - p], Ho[:, : k - p]) < 1e-10
 
 
 # ---------------------------------------------------------------------------------------------
@@ -386,10 +391,10 @@ def test_gmres_vs_oracle(lk, ctx, oracle, kind):
     assert meta["n_iter"] == ometa["n_iter"] and meta["n_outer"] == ometa["n_outer"]
     r = np.array(meta["res"]); ro = np.array(ometa["res"])
     assert r.shape == ro.shape
-    np.testing.assert_allclose(r, ro, rtol=1e-6 if kind in "dz" else 5e-2, atol=lk.ATOL[kind] * 100)
+    assert rel_normwise(r, ro) < tol_for(kind)                 # residual history, normwise like H
     xg = x.get()
     assert np.linalg.norm(Ao.apply(xg) - bh) < lk.RTOL[kind] * np.linalg.norm(bh) * 2
-    assert np.linalg.norm(xg - xo) / np.linalg.norm(xo) < (1e-7 if kind in "dz" else 1e-2)
+    assert np.linalg.norm(xg - xo) / np.linalg.norm(xo) < tol_for(kind)
 
 
 @pytest.mark.parametrize("kind", KINDS)
@@ -401,9 +406,9 @@ def test_cg_vs_oracle(lk, ctx, oracle, kind):
     info, meta = lk.cg(A, b, x, maxiter=2000)
     xo = np.zeros(n, dtype=dt)
     oinfo, ometa = oracle.cg(Ao, bh, xo, maxiter=2000)
-    assert info > 0 and oinfo > 0 and abs(info - oinfo) <= (1 if kind in "dz" else 3)
-    k = min(len(meta["res"]), len(ometa["res"])) - 1
-    np.testing.assert_allclose(meta["res"][:k], ometa["res"][:k], rtol=1e-6 if kind in "dz" else 5e-2)
+    assert info == oinfo > 0                                   # same iteration count (the last residual clears tol by > 10 %)
+    assert rel_normwise(np.array(meta["res"]), np.array(ometa["res"])) < tol_for(kind)
+    assert np.linalg.norm(x.get() - xo) / np.linalg.norm(xo) < tol_for(kind)
     assert np.linalg.norm(Ao.apply(x.get()) - bh) < lk.RTOL[kind] * np.linalg.norm(bh) * 2
 
 
@@ -411,6 +416,12 @@ def test_cg_vs_oracle(lk, ctx, oracle, kind):
 # BASELINE.json full size (config C2): size-independent properties + a short oracle comparison
 # ---------------------------------------------------------------------------------------------
 def test_arnoldi_full_size_c2(lk, ctx, oracle):
+    """BASELINE configs[1] at the NAMED size (n = 16.8M, kdim = 128): every Hessenberg entry and every Ritz value
+    against (a) the committed golden matrix tests/golden/c2_full_H.npz (oracle, all 128 steps) and (b) a LIVE run of the
+    oracle for all 128 steps on this box's host cores (~1-2 min), both at 1e-10 -- the north-star sentence
+    "matching the reference's Ritz values within 1e-10" at the size it is stated for.  Columns 17..128 are where
+    j > 16, the full TMA ring, 32-row tiles and all 8 chunk warps of the fused kernel are live."""
+    import os
     nx = ny = 4096; n = nx * ny; kdim = 128
     A = lk.LinOp.stencil5(ctx, "d", nx, ny, POISSON5)
     X = lk.Basis(ctx, "d", n, kdim + 1)
@@ -433,13 +444,23 @@ def test_arnoldi_full_size_c2(lk, ctx, oracle):
     assert np.abs(Hs - Hs.T).max() < 1e-10
     ev = np.linalg.eigvalsh((Hs + Hs.T) / 2)
     assert ev.min() > 0 and ev.max() < 8
-    # first 6 steps against the oracle on the same bit-identical start vector
-    ko = 6
-    Xo = np.zeros((n, ko + 1), order="F"); Xo[:, 0] = oracle.fill(n, "d", "uniform", 42); oracle.normalize(Xo[:, 0])
-    Ho = np.zeros((ko + 1, ko), order="F")
+    ritz = np.sort(np.linalg.eigvals(Hs).real)
+    # (a) committed golden matrix: all 129 x 128 entries and all 128 Ritz values
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c2_full_H.npz"))
+    np.testing.assert_allclose(X.get(0, 1)[:8, 0], g["x0_head"], rtol=1e-14)             # same start vector
+    assert rel_normwise(H, g["H"]) < 1e-10
+    assert np.abs(ritz - g["ritz"]).max() / np.abs(g["ritz"]).max() < 1e-10
+    np.testing.assert_allclose(X.get(kdim, 1)[:8, 0], g["xlast_head"], rtol=0, atol=1e-10 * np.abs(g["xlast_head"]).max())
+    # (b) live oracle, all 128 steps, on the bit-identical start vector
+    del y, r
+    Xo = np.zeros((n, kdim + 1), order="F"); Xo[:, 0] = oracle.fill(n, "d", "uniform", 42); oracle.normalize(Xo[:, 0])
+    Ho = np.zeros((kdim + 1, kdim), order="F")
     oracle.set_threads(oracle.max_threads())
     assert oracle.arnoldi(oracle.Op.stencil("d", (nx, ny), POISSON5), Xo, Ho) == 0
-    assert rel_normwise(H[:ko + 1, :ko], Ho) < 1e-10
+    assert rel_normwise(H, Ho) < 1e-10
+    ritz_o = np.sort(np.linalg.eigvals(Ho[:kdim, :kdim]).real)
+    assert np.abs(ritz - ritz_o).max() / np.abs(ritz_o).max() < 1e-10
+    assert rel_normwise(Ho, g["H"]) < 1e-12                                               # the golden file is this oracle's output
 
 
 # ---------------------------------------------------------------------------------------------
@@ -505,8 +526,8 @@ def test_preconditioned_cg_and_gmres_vs_oracle(lk, ctx, oracle):
     info, meta = lk.cg(A, b, x, maxiter=2000, preconditioner=precond_dev)
     xo = np.zeros(n); oinfo, ometa = oracle.cg(Ao, bh, xo, maxiter=2000, precond=precond_host)
     assert info == oinfo > 0
-    np.testing.assert_allclose(meta["res"], ometa["res"], rtol=1e-6)
-    assert np.linalg.norm(x.get() - xo) < 1e-8 * np.linalg.norm(xo)
+    assert rel_normwise(np.array(meta["res"]), np.array(ometa["res"])) < 1e-10
+    assert np.linalg.norm(x.get() - xo) < 1e-10 * np.linalg.norm(xo)
     assert len(calls) == info + 1 and all(c == -1 for c in calls)
     calls.clear()
     A2 = lk.LinOp.stencil7(ctx, "d", *dims, CONVDIFF7); A2o = oracle.Op.stencil("d", dims, CONVDIFF7)
@@ -514,8 +535,8 @@ def test_preconditioned_cg_and_gmres_vs_oracle(lk, ctx, oracle):
     ginfo, gmeta = lk.gmres(A2, b, x2, kdim=20, maxiter=30, preconditioner=precond_dev)
     xo2 = np.zeros(n); oinfo2, ometa2 = oracle.gmres(A2o, bh, xo2, kdim=20, maxiter=30, precond=precond_host)
     assert ginfo == oinfo2 > 0 and gmeta["n_outer"] == ometa2["n_outer"]
-    np.testing.assert_allclose(gmeta["res"], ometa2["res"], rtol=1e-5, atol=1e-13)
-    assert np.linalg.norm(x2.get() - xo2) < 1e-7 * np.linalg.norm(xo2)
+    assert rel_normwise(np.array(gmeta["res"]), np.array(ometa2["res"])) < 1e-10
+    assert np.linalg.norm(x2.get() - xo2) < 1e-10 * np.linalg.norm(xo2)
     assert calls[0] == 1 and -1 in calls                     # (wrk, k, beta, tol) form and the plain apply(dx) form
 
 
@@ -530,7 +551,7 @@ def test_arnoldi_large_kdim_workspace_growth(lk, ctx, oracle):
     info, X, H, oinfo, Xo, Ho = _arnoldi_pair(lk, ctx, oracle, "d", A, Ao, n, kdim, x0)
     # a 300-step Krylov sequence is not entrywise reproducible between two summation orders once Ritz
     # values have converged (tiny differences are amplified), so: early columns entrywise, then invariants
-    assert info == oinfo == 0 and rel_normwise(H[:41, :40], Ho[:41, :40]) < 1e-9
+    assert info == oinfo == 0 and rel_normwise(H[:41, :40], Ho[:41, :40]) < 1e-10
     Xg = X.get()
     assert np.abs(Xg.T @ Xg - np.eye(kdim + 1)).max() < 1e-12
     AX = np.stack([Ao.apply(Xg[:, k].copy()) for k in range(kdim)], axis=1)
@@ -562,8 +583,8 @@ def test_fgmres_vs_oracle(lk, ctx, oracle):
     info, meta = lk.fgmres(A, b, x, kdim=20, maxiter=30, preconditioner=precond_dev)
     xo = np.zeros(n); oinfo, ometa = oracle.gmres(Ao, bh, xo, kdim=20, maxiter=30, precond=precond_host, flexible=True)
     assert info == oinfo > 0 and meta["n_outer"] == ometa["n_outer"]
-    np.testing.assert_allclose(meta["res"], ometa["res"], rtol=1e-5, atol=1e-13)
-    assert np.linalg.norm(x.get() - xo) < 1e-7 * np.linalg.norm(xo)
+    assert rel_normwise(np.array(meta["res"]), np.array(ometa["res"])) < 1e-10
+    assert np.linalg.norm(x.get() - xo) < 1e-10 * np.linalg.norm(xo)
     assert np.linalg.norm(Ao.apply(x.get()) - bh) < lk.RTOL["d"] * np.linalg.norm(bh) * 2
     # without a preconditioner fgmres == gmres
     x1 = lk.Vector(ctx, "d", n); x2 = lk.Vector(ctx, "d", n)
@@ -658,3 +679,103 @@ def test_rand_is_seeded_and_reproducible(lk, ctx):
     a2 = lk.Vector(ctx, "d", 1000).rand().get()
     assert np.array_equal(a, a2) and not np.array_equal(a, b)
     assert abs(a.mean()) < 0.15 and abs(a.std() - 1.0) < 0.1
+
+
+# ---------------------------------------------------------------------------------------------
+# round 2: final CGS2 pass fused with the normalisation (predicted norm ||w'||^2 - ||c2||^2) against the
+# round-1 tail (exact norm sweep + k_update + k_scale_dev), including the exact-norm fallback near breakdown
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", KINDS)
+def test_fused_final_pass_matches_separate_tail(lk, ctx, oracle, kind):
+    dt = lk.DTYPES[kind]; nx, ny, kdim = 96, 80, 40; n = nx * ny
+    coef = CONVDIFF7[:5]
+    A = lk.LinOp.stencil5(ctx, kind, nx, ny, coef); Ao = oracle.Op.stencil(kind, (nx, ny), coef)
+    x0 = oracle.fill(n, kind, "uniform", 9); oracle.normalize(x0)
+    res = {}
+    for fin in (1, 0):
+        ctx.set_option("fin", fin)
+        X = lk.Basis(ctx, kind, n, kdim + 1).put(x0)
+        H = np.zeros((kdim + 1, kdim), dtype=dt, order="F")
+        assert lk.arnoldi(A, X, H) == 0
+        res[fin] = (H.copy(), X.get())
+    ctx.set_option("fin", 1)
+    Xo = np.zeros((n, kdim + 1), dtype=dt, order="F"); Xo[:, 0] = x0; Ho = np.zeros((kdim + 1, kdim), dtype=dt, order="F")
+    assert oracle.arnoldi(Ao, Xo, Ho) == 0
+    for fin in (1, 0):
+        H, Xg = res[fin]
+        assert rel_normwise(H, Ho) < tol_for(kind)
+        assert np.abs(Xg.conj().T @ Xg - np.eye(kdim + 1)).max() < orth_tol(kind)
+    # the two tails agree far below the parity tolerance: the predicted norm is as accurate as a computed one
+    assert rel_normwise(res[1][0], res[0][0]) < (1e-13 if kind in "dz" else 1e-5)
+    # the new vector leaves the fused kernel normalised to working precision
+    nrm = np.linalg.norm(res[1][1].astype(np.complex128 if kind in "cz" else np.float64), axis=0)
+    assert np.abs(nrm - 1).max() < (1e-14 if kind in "dz" else 1e-6)
+
+
+@pytest.mark.parametrize("kind", ["d", "z"])
+def test_fused_final_pass_exact_fallback_near_breakdown(lk, ctx, oracle, kind):
+    """A start vector that is 1e-9 away from a 3-dimensional invariant subspace: at step 3 the first pass cancels
+    nine digits, ||c2||^2 is no longer negligible against ||w'||^2 in later steps' noise, and on a true breakdown
+    (second operator) w' is pure rounding noise -- the kernel must switch to the exact norm and agree with the oracle."""
+    dt = lk.DTYPES[kind]; n = 128
+    Ah = np.asfortranarray(np.diag(np.arange(1, n + 1)).astype(dt))
+    rng = np.random.default_rng(4)
+    x0 = np.zeros(n, dtype=dt); x0[:3] = 1 / np.sqrt(3.0)
+    x0 += (1e-9 * rng.standard_normal(n)).astype(dt); oracle.normalize(x0)
+    A = lk.LinOp.dense(ctx, Ah); Ao = oracle.Op.dense(Ah)
+    info, X, H, oinfo, Xo, Ho = _arnoldi_pair(lk, ctx, oracle, kind, A, Ao, n, 6, x0)
+    assert info == oinfo == 0
+    # columns 1..3 are well conditioned; afterwards the process restarts from 1e-9-sized noise (amplification 1e9)
+    assert rel_normwise(H[:4, :3], Ho[:4, :3]) < 1e-10
+    assert abs(H[3, 2] - Ho[3, 2]) < 1e-10 * abs(Ho[3, 2]) + 1e-22
+    Xg = X.get()
+    assert np.abs(Xg.conj().T @ Xg - np.eye(7)).max() < 1e-12
+    # exact invariant subspace built from non-representable weights: w' is rounding noise, c2 is of the same size
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    Bh = np.asfortranarray((Q @ np.diag(np.arange(1, n + 1)) @ Q.T).astype(dt))
+    y0 = (Q[:, :3] @ np.array([0.3, 0.5, 0.7])).astype(dt); oracle.normalize(y0)
+    B = lk.LinOp.dense(ctx, Bh); Bo = oracle.Op.dense(Bh)
+    # (the invariant subspace of the rounded Q diag Q^T is exact to ~1e-13; two multiplications by B, ||B|| = 128,
+    # leave a residual of order 1e-9: a breakdown for tol = 1e-8, and H(4,3) itself is rounding noise)
+    info, X, H, oinfo, Xo, Ho = _arnoldi_pair(lk, ctx, oracle, kind, B, Bo, n, 8, y0, tol=1e-8)
+    assert info == oinfo == 3
+    assert rel_normwise(H[:3, :3], Ho[:3, :3]) < 1e-10 and abs(H[3, 2]) < 1e-8 and not H[:, 3:].any()
+    Xg = X.get()
+    assert abs(np.linalg.norm(Xg[:, 3]) - 1.0) < 1e-12                          # atol <= beta < tol: still scaled (qr.fypp:164)
+
+
+def test_csr_random_device_matches_oracle_twin(lk, ctx, oracle):
+    """Config-5 generator on the device (lkb_csr_random_device + device-side transpose) against the host twin."""
+    for kind in ("z", "d", "c"):
+        dt = lk.DTYPES[kind]; m, n, pr = 3001, 2003, 32
+        A = lk.LinOp.csr_random(ctx, kind, m, n, pr, 46)
+        rp, ci, va = oracle.csr_random(kind, m, n, pr, 46)
+        Ao = oracle.Op.csr(m, n, rp, ci, va)
+        xh = oracle.fill(n, kind, "normal", 3); uh = oracle.fill(m, kind, "normal", 4)
+        x = lk.Vector(ctx, kind, n).put(xh); u = lk.Vector(ctx, kind, m).put(uh)
+        y = lk.Vector(ctx, kind, m); v = lk.Vector(ctx, kind, n)
+        A.matvec(x, y); A.rmatvec(u, v)
+        tol = dict(rtol=1e-4, atol=1e-4) if kind == "c" else dict(rtol=1e-11, atol=1e-11)
+        np.testing.assert_allclose(y.get(), Ao.apply(xh), **tol)
+        np.testing.assert_allclose(v.get(), Ao.apply(uh, trans=True), **tol)
+
+
+def test_csr_create_validates_indices(lk, ctx):
+    """1-based / out-of-range column indices or a non-monotone rowptr must be LKB_ERR_ARG, not heap corruption."""
+    m, n = 5, 4
+    rowptr = np.array([0, 2, 4, 6, 8, 10], dtype=np.int64)
+    col = np.array([0, 1, 1, 2, 2, 3, 0, 3, 1, 4], dtype=np.int32)          # 4 is out of range (1-based habit)
+    val = np.ones(10)
+    with pytest.raises(lk.LkbError, match="column index out of range"):
+        lk.LinOp.csr(ctx, m, n, rowptr, col, val)
+    col[-1] = 3
+    bad = rowptr.copy(); bad[2] = 1
+    with pytest.raises(lk.LkbError, match="non-decreasing"):
+        lk.LinOp.csr(ctx, m, n, bad, col, val)
+    bad = rowptr.copy(); bad[0] = 1
+    with pytest.raises(lk.LkbError, match="rowptr"):
+        lk.LinOp.csr(ctx, m, n, bad, col, val)
+    A = lk.LinOp.csr(ctx, m, n, rowptr, col, val)                              # the corrected matrix is accepted
+    x = lk.Vector(ctx, "d", n).put(np.arange(1.0, n + 1)); y = lk.Vector(ctx, "d", m)
+    A.matvec(x, y)
+    assert np.array_equal(y.get(), np.array([3.0, 5.0, 7.0, 5.0, 6.0]))
