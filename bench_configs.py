@@ -41,20 +41,30 @@ def emit(**kw):
 
 
 def c2_gmres(ctx, full):
+    """Config 2, second half: gmres(kdim=50, maxiter=10) on the 4096^2 Poisson operator, grid rows over the ranks."""
     nx = ny = 4096 if full else 2048
     n = nx * ny
-    A = lk.LinOp.stencil5(ctx, "d", nx, ny, POISSON5)
-    b = lk.Vector(ctx, "d", n).fill_random("uniform", 43)
-    x = lk.Vector(ctx, "d", n)
+    A = lk.LinOp.stencil5(ctx, "d", nx, ny, POISSON5)             # slab of this rank
+    nloc, row0 = A.n, A.row0
+    b = lk.Vector(ctx, "d", nloc, n_global=n, row0=row0).fill_random("uniform", 43)
+    x = lk.Vector(ctx, "d", nloc, n_global=n, row0=row0)
+    lk.gmres(A, b, x, kdim=50, maxiter=10)                        # warm-up (allocation pool, graph capture)
+    x.zero()
     (info, meta), dt = timed(ctx, lambda: lk.gmres(A, b, x, kdim=50, maxiter=10))
-    r = lk.Vector(ctx, "d", n); A.matvec(x, r); r.sub(b)
+    r = lk.Vector(ctx, "d", nloc, n_global=n, row0=row0); A.matvec(x, r); r.sub(b)
+    rn = r.norm()
+    if ctx.rank != 0:
+        return
     steps = meta["n_inner"]
     # per inner step j: matvec + 4*j*n*s (official); j cycles 1..50
     byts = sum(2 * n * 8 + 4 * ((i % 50) + 1) * n * 8 for i in range(steps))
-    emit(config="C2 gmres(kdim=50, maxiter=10) 5-pt Poisson %dx%d fp64" % (nx, ny), n=n, info=info,
+    emit(config="C2 gmres(kdim=50, maxiter=10) 5-pt Poisson %dx%d fp64, %d GPU(s)" % (nx, ny, ctx.world), n=n, info=info,
          n_inner=steps, n_outer=meta["n_outer"], converged=meta["converged"], seconds=dt,
-         inner_steps_per_s=steps / dt, alg_GBps=byts / dt / 1e9, frac_of_measured_hbm=byts / dt / 1e9 / PEAK,
-         final_residual=r.norm(), res_first=meta["res"][0], res_last=meta["res"][-1])
+         inner_steps_per_s=steps / dt, alg_GBps_per_gpu=byts / dt / 1e9 / ctx.world,
+         frac_of_measured_hbm=byts / dt / 1e9 / PEAK / ctx.world,
+         final_residual=rn, res_first=meta["res"][0], res_last=meta["res"][-1],
+         res_history_sha=__import__("hashlib").sha1(np.asarray(meta["res"]).tobytes()).hexdigest()[:12],
+         res_every_50=[float(v) for v in meta["res"][::50]])
 
 
 def c3_eigs(ctx, full):
@@ -118,38 +128,67 @@ def c4_sym(ctx, full):
 
 
 def c5_svds(ctx, full):
-    # 50M x 40M with 32 nnz/row needs ~110 GB (values + transpose copy): run a 1/10-scale replica by default
+    """Config 5: random rectangular CSR (50M x 40M, 32 nnz/row, cdp): bidiagonalization(kdim=32) + svds(nsv=8).
+    The matrix is generated AND transposed on the device (lkb_csr_random_device / lkb_op_csr_create_device): at BASELINE
+    size it holds 1.6e9 non-zeros = 64.7 GB with its explicit transpose, the two bases take 47.5 GB more."""
     m, n = (50_000_000, 40_000_000) if full else (5_000_000, 4_000_000)
     per_row = 32
     lk.set_lapack_from_scipy()
-    rng = np.random.default_rng(46)
     t0 = time.perf_counter()
-    col = np.sort(rng.integers(0, n, size=(m, per_row), dtype=np.int32), axis=1).ravel()
-    val = (rng.standard_normal(m * per_row) + 1j * rng.standard_normal(m * per_row)).astype(np.complex128)
-    rowptr = np.arange(0, (m + 1) * per_row, per_row, dtype=np.int64)
+    A = lk.LinOp.csr_random(ctx, "z", m, n, per_row, 46)
+    ctx.sync()
     tgen = time.perf_counter() - t0
-    A = lk.LinOp.csr(ctx, m, n, rowptr, col, val)
-    del col, val
+    nnz = m * per_row
+    es = 16
+    spmv = nnz * (es + 4) + 8 * (m + 1) + (n + m) * es
+    # stand-alone SpMV rates (CUDA-event-free: wall clock around 10 back-to-back launches + sync)
+    x = lk.Vector(ctx, "z", n).fill_random("normal", 1); y = lk.Vector(ctx, "z", m).fill_random("normal", 2)
+    rates = {}
+    for name, fn in (("matvec", lambda: A.matvec(x, y)), ("rmatvec", lambda: A.rmatvec(y, x))):
+        fn(); ctx.sync()
+        t1 = time.perf_counter()
+        for _ in range(10):
+            fn()
+        ctx.sync()
+        rates[name] = spmv / ((time.perf_counter() - t1) / 10) / 1e9
+    del x, y
     kdim, nsv = 32, 8
     U = lk.Basis(ctx, "z", m, kdim + 1); V = lk.Basis(ctx, "z", n, kdim + 1)
     u0 = U.col(0).fill_random("normal", 47); u0.scal(1.0 / u0.norm())
     B = np.zeros((kdim + 1, kdim), dtype=np.complex128, order="F")
     lk.bidiagonalization(A, U, V, B)
     (info, dt) = timed(ctx, lambda: lk.bidiagonalization(A, U, V, B))
-    nnz = m * per_row
-    es = 16
-    spmv = nnz * (es + 4) + 8 * (m + 1) + (n + m) * es
     byts = sum(2 * spmv + 4 * (k - 1) * n * es + 4 * k * m * es for k in range(1, kdim + 1))
+    # parity-style properties at full size: orthonormality of both bases (device Gram blocks), the Golub-Kahan relation
+    # A v_k = alpha_k u_k + beta_k u_{k+1} evaluated on the device for k = 1, 16, 32, bidiagonal structure of B
+    Gu = U.innerprod(kdim + 1, U, wcol0=0, p=4); Gv = V.innerprod(kdim, V, wcol0=0, p=4)
+    orth = float(max(np.abs(Gu - np.eye(kdim + 1)[:, :4]).max(), np.abs(Gv - np.eye(kdim)[:, :4]).max()))
+    rel = 0.0
+    r = lk.Vector(ctx, "z", m)
+    for k in (1, 16, 32):
+        A.matvec(V.col(k - 1), r)
+        r.axpby(-B[k - 1, k - 1], U.col(k - 1), 1.0)
+        r.axpby(-B[k, k - 1], U.col(k), 1.0)
+        rel = max(rel, r.norm() / abs(B[k - 1, k - 1]))
+    del r
+    offband = float(np.abs(np.triu(B, 1)).max() + np.abs(np.tril(B, -2)).max())
     emit(config="C5 bidiagonalization(kdim=32) random CSR %dx%d, 32 nnz/row, cdp" % (m, n), info=int(info), seconds=dt,
          steps_per_s=kdim / dt, alg_GBps=byts / dt / 1e9, frac_of_measured_hbm=byts / dt / 1e9 / PEAK,
-         host_generation_s=tgen, B_diag_first=[float(abs(B[i, i])) for i in range(4)])
+         device_generation_and_transpose_s=tgen, spmv_alg_GBps=rates, nnz=nnz,
+         B_diag_first=[float(abs(B[i, i])) for i in range(4)], orth_err_first4=orth, golub_kahan_relation_rel_err=rel,
+         B_off_band_max=offband)
+    del U, V
     Us = lk.Basis(ctx, "z", m, nsv); Vs = lk.Basis(ctx, "z", n, nsv)
     u0 = lk.Vector(ctx, "z", m).fill_random("normal", 47)
     (res, dt) = timed(ctx, lambda: lk.svds(A, Us, Vs, nsv, u0=u0, kdim=32, tolerance=1e-6))
     S, resid, info = res
     y = lk.Vector(ctx, "z", m); A.matvec(Vs.col(0), y); y.axpby(-S[0], Us.col(0), 1.0)
+    # known answer for this random ensemble: the largest singular value of an m x n matrix with `per_row` i.i.d. complex
+    # N(0, 2) entries per row concentrates at sqrt(2 per_row) (1 + sqrt(m / n))  (Marchenko-Pastur edge)
+    mp_edge = float(np.sqrt(2.0 * per_row) * (1.0 + np.sqrt(m / n)))
     emit(config="C5 svds(nsv=8, kdim=32)", info_k=int(info), seconds=dt, S=[float(s) for s in S],
-         residuals=[float(r) for r in resid], triplet0_residual=y.norm())
+         residuals=[float(r) for r in resid], triplet0_residual=y.norm(), marchenko_pastur_edge=mp_edge,
+         S0_over_edge=float(S[0] / mp_edge))
 
 
 def main():
@@ -165,7 +204,7 @@ def main():
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         ctx = lk.Context.from_torch_distributed(local)
-        args.only = "c3"
+        args.only = ",".join(c for c in args.only.split(",") if c in ("c2", "c3"))      # the row-sharded configs
     else:
         ctx = lk.Context(0)
     for name, fn in (("c2", c2_gmres), ("c3", c3_eigs), ("c4", c4_sym), ("c5", c5_svds)):

@@ -87,6 +87,15 @@ int lkb_basis_create(lkb_ctx_t ctx, int kind, int64_t n_local, int64_t n_global,
 int lkb_basis_destroy(lkb_basis_t b);
 int lkb_basis_col(lkb_basis_t b, int i0, lkb_vec_t* view); /* non-owning view of column i0 (0-based) */
 int lkb_basis_zero(lkb_basis_t b, int col0, int ncols);    /* zero_basis :711-715 */
+/* non-owning view of columns [col0, col0+ncols): the array section X(k1:k2); release with lkb_basis_destroy */
+int lkb_basis_view(lkb_basis_t b, int col0, int ncols, lkb_basis_t* view);
+/* axpby_basis :697-709  Y(:, ycol0+q) = alpha X(:, xcol0+q) + beta Y(:, ycol0+q), q < ncols; beta == 0 is `copy` :717-723 */
+int lkb_basis_axpby(const void* alpha, lkb_basis_t X, int xcol0, const void* beta, lkb_basis_t Y, int ycol0, int ncols);
+int lkb_basis_rand(lkb_basis_t b, int col0, int ncols, int32_t ifnorm);   /* rand_basis :725-730 */
+/* src/Krylov/utilities.fypp:32-81 (interfaces BaseKrylov.fypp:490-600): block-Arnoldi start helpers */
+int lkb_orthonormalize_basis(lkb_basis_t X, int col0, int p, int32_t* info);
+int lkb_initialize_krylov_subspace(lkb_basis_t X, lkb_basis_t X0 /* may be NULL */, int x0col0, int p0);
+int lkb_initialize_random_orthonormal_basis(lkb_basis_t X, int col0, int p);
 int lkb_basis_put(lkb_basis_t b, int col0, int ncols, const void* host, int64_t ldhost);
 int lkb_basis_get(lkb_basis_t b, int col0, int ncols, void* host, int64_t ldhost);
 int lkb_basis_ncols(lkb_basis_t b);

@@ -67,6 +67,12 @@ SIGNATURES = {
     "lkb_basis_destroy": (_i, [_vp]),
     "lkb_basis_col": (_i, [_vp, _i, _P(_vp)]),
     "lkb_basis_zero": (_i, [_vp, _i, _i]),
+    "lkb_basis_view": (_i, [_vp, _i, _i, _P(_vp)]),
+    "lkb_basis_axpby": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i]),
+    "lkb_basis_rand": (_i, [_vp, _i, _i, _i32]),
+    "lkb_orthonormalize_basis": (_i, [_vp, _i, _i, _P(_i32)]),
+    "lkb_initialize_krylov_subspace": (_i, [_vp, _vp, _i, _i]),
+    "lkb_initialize_random_orthonormal_basis": (_i, [_vp, _i, _i]),
     "lkb_basis_put": (_i, [_vp, _i, _i, _vp, _i64]),
     "lkb_basis_get": (_i, [_vp, _i, _i, _vp, _i64]),
     "lkb_basis_ncols": (_i, [_vp]),

@@ -247,6 +247,38 @@ class Basis:
     def __getitem__(self, i): return self.col(i)
     def __len__(self): return self.ncols
 
+    @classmethod
+    def _from_handle(cls, parent: "Basis", h, ncols: int) -> "Basis":
+        b = cls.__new__(cls)
+        b.ctx, b.kind, b.n, b.ncols, b.n_global, b.row0, b.h, b._parent = parent.ctx, parent.kind, parent.n, ncols, parent.n_global, parent.row0, h, parent
+        return b
+
+    def view(self, col0: int, ncols: int) -> "Basis":
+        """Non-owning view of columns [col0, col0+ncols): the array section X(col0+1 : col0+ncols) of the reference."""
+        h = C.c_void_p()
+        check(self.ctx.lib.lkb_basis_view(self.h, col0, ncols, C.byref(h)), "basis_view")
+        return Basis._from_handle(self, h, ncols)
+
+    def axpby(self, alpha, X: "Basis", beta, xcol0: int = 0, ycol0: int = 0, ncols: Optional[int] = None):
+        """axpby_basis: self(:, ycol0+q) = alpha X(:, xcol0+q) + beta self(:, ycol0+q)  (AbstractVectors.fypp:697-709)"""
+        a, b = _scalar(self.kind, alpha), _scalar(self.kind, beta)
+        ncols = min(self.ncols - ycol0, X.ncols - xcol0) if ncols is None else ncols
+        check(self.ctx.lib.lkb_basis_axpby(a.ctypes.data, X.h, xcol0, b.ctypes.data, self.h, ycol0, ncols), "basis_axpby"); return self
+
+    def copy_from(self, X: "Basis", xcol0: int = 0, ycol0: int = 0, ncols: Optional[int] = None):
+        """copy(out, from) = out%axpby(1, from, 0)  (AbstractVectors.fypp:717-723)"""
+        return self.axpby(1, X, 0, xcol0, ycol0, ncols)
+
+    def rand(self, col0: int = 0, ncols: Optional[int] = None, ifnorm: bool = False):
+        """rand_basis (AbstractVectors.fypp:725-730)"""
+        check(self.ctx.lib.lkb_basis_rand(self.h, col0, self.ncols - col0 if ncols is None else ncols, int(ifnorm)), "basis_rand"); return self
+
+    def orthonormalize(self, col0: int = 0, p: Optional[int] = None) -> int:
+        """orthonormalize_basis (src/Krylov/utilities.fypp:70-81)"""
+        info = C.c_int32()
+        check(self.ctx.lib.lkb_orthonormalize_basis(self.h, col0, self.ncols - col0 if p is None else p, C.byref(info)), "orthonormalize_basis")
+        return info.value
+
     def zero(self, col0: int = 0, ncols: Optional[int] = None):
         check(self.ctx.lib.lkb_basis_zero(self.h, col0, self.ncols - col0 if ncols is None else ncols)); return self
 
@@ -541,6 +573,20 @@ def svds(A: LinOp, U: Basis, V: Basis, nsv: int, u0: Optional[Vector] = None, kd
                              residuals.ctypes.data_as(C.POINTER(C.c_double)), C.byref(info),
                              u0.h if u0 is not None else None, kdim, tolerance), "svds")
     return S, residuals, info.value
+
+
+def initialize_krylov_subspace(X: Basis, X0: Optional[Basis] = None, p0: Optional[int] = None) -> None:
+    """initialize_krylov_subspace(X [, X0]) (src/Krylov/utilities.fypp:32-46, BaseKrylov.fypp:490-517): zero X, copy the
+    p0 starting vectors into X(:p0) and orthonormalise them."""
+    if X0 is None:
+        check(X.ctx.lib.lkb_initialize_krylov_subspace(X.h, None, 0, 0), "initialize_krylov_subspace")
+    else:
+        check(X.ctx.lib.lkb_initialize_krylov_subspace(X.h, X0.h, 0, X0.ncols if p0 is None else p0), "initialize_krylov_subspace")
+
+
+def initialize_random_orthonormal_basis(X: Basis, col0: int = 0, p: Optional[int] = None) -> None:
+    """utilities.fypp:52-62"""
+    check(X.ctx.lib.lkb_initialize_random_orthonormal_basis(X.h, col0, X.ncols - col0 if p is None else p), "initialize_random_orthonormal_basis")
 
 
 def krylov_schur(X: Basis, H: np.ndarray, kdim: int) -> int:

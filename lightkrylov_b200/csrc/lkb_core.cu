@@ -127,6 +127,24 @@ int allreduce_w(lkb_ctx_s* c, void* buf, size_t ndoubles) {
     LKB_NCCL(api->AllReduce(buf, buf, ndoubles, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->comm, c->stream));
     return 0;
 }
+// Stream-ordered allocation of vectors / bases / solver work space from the device's default memory pool with an
+// unlimited release threshold: freed blocks stay cached in the pool, so the GB-sized work bases that gmres / cg /
+// eigs allocate per call (`allocate(V(kdim+1), source=b)` in the reference) cost a pool lookup instead of a
+// cudaMalloc / cudaFree pair (measured in round 1: 0.3-1 s of call-to-call variance).  P2P / IPC regions stay on
+// cudaMalloc (CUDA IPC handles cannot be taken of pool memory).
+int dev_alloc(lkb_ctx_s* c, void** p, size_t bytes) {
+    cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 16, c->stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cudaMallocAsync(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        *p = nullptr;
+        return LKB_ERR_ALLOC;
+    }
+    return 0;
+}
+void dev_free(lkb_ctx_s* c, void* p) {
+    if (p) cudaFreeAsync(p, c->stream);      // stream-ordered: no host synchronisation needed
+}
 static uint64_t g_uid = 0;
 uint64_t next_uid() { return ++g_uid; }
 // The k x k host algebra (geev / gees+trsen / syev / gesdd) runs redundantly on every rank; a threaded
@@ -224,6 +242,14 @@ static int ctx_common(int device, lkb_ctx_s* c) {
     c->dev = device;
     LKB_CUDA(cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, device));
     LKB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {   // keep freed blocks in the default pool (see dev_alloc)
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+            unsigned long long thr = ~0ULL;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        cudaGetLastError();
+    }
     LKB_CUDA(cudaMalloc(&c->nrm2, 64));
     LKB_CUDA(cudaMalloc((void**)&c->inv, 64));
     LKB_CUDA(cudaMalloc((void**)&c->flags, F_COUNT * sizeof(int)));
@@ -278,6 +304,12 @@ int lkb_finalize(lkb_ctx_t c) {
     void* bufs[] = { c->partial, c->c1, c->c2, c->tmpw, c->nrm2, c->inv, c->flags, c->counter, c->Hd, c->coefd };
     for (void* b : bufs) if (b) cudaFree(b);
     if (c->hstage) cudaFreeHost(c->hstage);
+    cudaStreamSynchronize(c->stream);
+    {
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, c->dev) == cudaSuccess && pool) cudaMemPoolTrimTo(pool, 0);
+        cudaGetLastError();
+    }
     cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -371,8 +403,7 @@ int lkb_vec_create(lkb_ctx_t c, int kind, int64_t n_local, int64_t n_global, int
     cudaSetDevice(c->dev);
     lkb_vec_s* h = new lkb_vec_s{c, kind, n_local, n_global, row0, nullptr, true};
     size_t bytes = std::max((size_t)n_local * kind_size(kind), (size_t)16);
-    cudaError_t e = cudaMalloc(&h->d, bytes);
-    if (e != cudaSuccess) { delete h; set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return LKB_ERR_ALLOC; }
+    if (dev_alloc(c, &h->d, bytes) != 0) { delete h; return LKB_ERR_ALLOC; }
     cudaMemsetAsync(h->d, 0, bytes, c->stream);
     *v = h;
     return 0;
@@ -390,7 +421,7 @@ int lkb_vec_clone(lkb_vec_t src, lkb_vec_t* dst) {
 }
 int lkb_vec_destroy(lkb_vec_t v) {
     if (!v) return LKB_ERR_ARG;
-    if (v->owns && v->d) { cudaStreamSynchronize(v->ctx->stream); cudaFree(v->d); }
+    if (v->owns && v->d) dev_free(v->ctx, v->d);
     delete v;
     return 0;
 }
@@ -461,17 +492,15 @@ int lkb_basis_create(lkb_ctx_t c, int kind, int64_t n_local, int64_t n_global, i
     const int64_t ld = ((std::max<int64_t>(n_local, 1) + epl - 1) / epl) * epl;
     lkb_basis_s* h = new lkb_basis_s{c, kind, n_local, n_global, row0, ld, ncols, nullptr, next_uid()};
     const size_t bytes = (size_t)ld * (size_t)ncols * kind_size(kind);
-    cudaError_t e = cudaMalloc(&h->d, bytes);
-    if (e != cudaSuccess) { delete h; set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return LKB_ERR_ALLOC; }
+    if (dev_alloc(c, &h->d, bytes) != 0) { delete h; return LKB_ERR_ALLOC; }
     cudaMemsetAsync(h->d, 0, bytes, c->stream);
     *b = h;
     return 0;
 }
 int lkb_basis_destroy(lkb_basis_t b) {
     if (!b) return LKB_ERR_ARG;
-    cudaStreamSynchronize(b->ctx->stream);
     invalidate_graphs(b->ctx, b->uid);
-    cudaFree(b->d);
+    if (b->owns) dev_free(b->ctx, b->d);
     delete b;
     return 0;
 }
@@ -479,6 +508,46 @@ int lkb_basis_col(lkb_basis_t b, int i0, lkb_vec_t* view) {
     if (!b || i0 < 0 || i0 >= b->ncols) { set_error("basis_col: column %d out of range", i0); return LKB_ERR_ARG; }
     *view = new lkb_vec_s{b->ctx, b->kind, b->n, b->n_global, b->row0, col_ptr(b, i0), false};
     return 0;
+}
+// Non-owning view of columns [col0, col0 + ncols) of a basis: what a Fortran array section X(k1:k2) of device
+// vectors maps to.  The view's identity is a fixed function of (parent, col0, ncols), so step graphs captured
+// through a view are found again when the same section is passed the next time.
+int lkb_basis_view(lkb_basis_t b, int col0, int ncols, lkb_basis_t* view) {
+    if (!b || !view || col0 < 0 || ncols < 1 || col0 + ncols > b->ncols) { set_error("basis_view: columns [%d, %d) out of range", col0, col0 + ncols); return LKB_ERR_ARG; }
+    lkb_basis_s* h = new lkb_basis_s{b->ctx, b->kind, b->n, b->n_global, b->row0, b->ld, ncols, col_ptr(b, col0),
+                                     (b->uid * 1000003ULL + (uint64_t)col0 * 4099ULL + (uint64_t)ncols) | (1ULL << 62)};
+    h->owns = false;
+    *view = h;
+    return 0;
+}
+// axpby_basis (AbstractVectors.fypp:697-709): Y(:, ycol0 + q) = alpha X(:, xcol0 + q) + beta Y(:, ycol0 + q); beta == 0 = copy
+int lkb_basis_axpby(const void* alpha, lkb_basis_t X, int xcol0, const void* beta, lkb_basis_t Y, int ycol0, int ncols) {
+    if (!X || !Y || !alpha || !beta || xcol0 < 0 || ycol0 < 0 || ncols < 0 || xcol0 + ncols > X->ncols || ycol0 + ncols > Y->ncols ||
+        X->n != Y->n || X->kind != Y->kind) { set_error("basis_axpby: bad arguments"); return LKB_ERR_ARG; }
+    lkb_ctx_s* c = Y->ctx;
+    const Scalar a = scalar_from(Y->kind, alpha), bb = scalar_from(Y->kind, beta);
+    for (int q = 0; q < ncols; ++q) {
+        launch_axpby(Y->kind, c->stream, a, col_ptr(X, xcol0 + q), bb, col_ptr(Y, ycol0 + q), Y->n, c->sms);
+        c->launches++;
+    }
+    return check_launch(c, "basis_axpby");
+}
+// rand_basis (AbstractVectors.fypp:725-730)
+int lkb_basis_rand(lkb_basis_t b, int col0, int ncols, int32_t ifnorm) {
+    if (!b || col0 < 0 || ncols < 0 || col0 + ncols > b->ncols) { set_error("basis_rand: bad arguments"); return LKB_ERR_ARG; }
+    lkb_ctx_s* c = b->ctx;
+    for (int q = 0; q < ncols; ++q) {
+        void* w = col_ptr(b, col0 + q);
+        launch_fill(b->kind, c->stream, w, b->n, b->row0, LKB_DIST_NORMAL, next_seed(c), c->sms);
+        c->launches++;
+        if (ifnorm) {
+            double nrm = 0;
+            LKB_TRY(vec_norm_sync(c, b->kind, w, b->n, &nrm));
+            launch_scal(b->kind, c->stream, Scalar{1.0 / nrm, 0.0}, w, b->n, c->sms);
+            c->launches++;
+        }
+    }
+    return check_launch(c, "basis_rand");
 }
 int lkb_basis_zero(lkb_basis_t b, int col0, int ncols) {
     if (col0 < 0 || col0 + ncols > b->ncols) return LKB_ERR_ARG;

@@ -240,7 +240,7 @@ int lkb_krylov_schur(lkb_basis_t X, void* H, int ldh, int kdim, int32_t* nkeep) 
         chunk = std::max<int64_t>(4096, (chunk / 4096) * 4096);
         chunk = std::min<int64_t>(chunk, ((X->n + 4095) / 4096) * 4096);
         void* tmp = nullptr;
-        LKB_CUDA(cudaMalloc(&tmp, (size_t)chunk * nk * es));
+        LKB_TRY(dev_alloc(c, &tmp, (size_t)chunk * nk * es));
         int r = 0;
         for (int64_t r0 = 0; r0 < X->n && r == 0; r0 += chunk) {
             const int64_t rows = std::min<int64_t>(chunk, X->n - r0);
@@ -252,7 +252,7 @@ int lkb_krylov_schur(lkb_basis_t X, void* H, int ldh, int kdim, int32_t* nkeep) 
                                             (size_t)rows * es, nk, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess) r = LKB_ERR_CUDA;
         }
         cudaStreamSynchronize(c->stream);
-        cudaFree(tmp);
+        dev_free(c, tmp);
         if (r) return r;
     }
     LKB_CUDA(cudaMemcpyAsync(col_ptr(X, nk), col_ptr(X, k), (size_t)X->n * es, cudaMemcpyDeviceToDevice, c->stream));

@@ -77,6 +77,7 @@ struct lkb_vec_s {
 };
 struct lkb_basis_s {
     lkb_ctx_s* ctx; int kind; int64_t n, n_global, row0, ld; int ncols; void* d; uint64_t uid;
+    bool owns = true;          // false: lkb_basis_view of a column range of another basis
 };
 struct lkb_op_s {
     lkb_ctx_s* ctx; int type; int kind;           // type: 0 dense, 1 stencil, 3 csr, 9 callback
@@ -106,6 +107,8 @@ namespace lkb {
     lkb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); return LKB_ERR_CUDA; } } while (0)
 #define LKB_TRY(call) do { int r_ = (call); if (r_ != 0) return r_; } while (0)
 
+int dev_alloc(lkb_ctx_s* c, void** p, size_t bytes);   // stream-ordered, pooled (vectors, bases, solver work space)
+void dev_free(lkb_ctx_s* c, void* p);
 int ensure_ws(lkb_ctx_s* c, int jp);                 // grow partial / c1 / c2 for jp = j+1 coefficients
 int ensure_hstage(lkb_ctx_s* c, size_t bytes);
 int ensure_Hd(lkb_ctx_s* c, size_t bytes);

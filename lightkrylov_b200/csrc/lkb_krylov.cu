@@ -374,6 +374,34 @@ int lkb_qr(lkb_basis_t Q, int col0, int p, void* R, int ldr, double tol, int32_t
     return 0;
 }
 
+// orthonormalize_basis (src/Krylov/utilities.fypp:70-81): in-place QR of X(:, col0 : col0 + p), R discarded
+int lkb_orthonormalize_basis(lkb_basis_t X, int col0, int p, int32_t* info) {
+    if (!X || !info || p < 1) { set_error("orthonormalize_basis: bad arguments"); return LKB_ERR_ARG; }
+    std::vector<char> R((size_t)p * p * kind_size(X->kind));
+    return lkb_qr(X, col0, p, R.data(), p, -1.0, info);
+}
+// initialize_krylov_subspace(X [, X0]) (src/Krylov/utilities.fypp:32-46): zero X; X(:p) = X0; orthonormalise X(:p)
+int lkb_initialize_krylov_subspace(lkb_basis_t X, lkb_basis_t X0, int x0col0, int p0) {
+    if (!X) { set_error("initialize_krylov_subspace: null basis"); return LKB_ERR_ARG; }
+    LKB_TRY(lkb_basis_zero(X, 0, X->ncols));
+    if (X0) {
+        if (p0 < 1 || p0 > X->ncols) { set_error("initialize_krylov_subspace: size(X0) = %d does not fit", p0); return LKB_ERR_ARG; }
+        const double one[2] = {1.0, 0.0}, zero[2] = {0.0, 0.0};
+        const float onef[2] = {1.f, 0.f}, zerof[2] = {0.f, 0.f};
+        const bool sp = (X->kind == KS || X->kind == KC);
+        LKB_TRY(lkb_basis_axpby(sp ? (const void*)onef : (const void*)one, X0, x0col0, sp ? (const void*)zerof : (const void*)zero, X, 0, p0));
+        int32_t info = 0;
+        LKB_TRY(lkb_orthonormalize_basis(X, 0, p0, &info));
+    }
+    return 0;
+}
+// initialize_random_orthonormal_basis (utilities.fypp:52-62)
+int lkb_initialize_random_orthonormal_basis(lkb_basis_t X, int col0, int p) {
+    LKB_TRY(lkb_basis_rand(X, col0, p, 0));
+    int32_t info = 0;
+    return lkb_orthonormalize_basis(X, col0, p, &info);
+}
+
 // ------------------------------------------------------------------------------------------
 // arnoldi
 // ------------------------------------------------------------------------------------------

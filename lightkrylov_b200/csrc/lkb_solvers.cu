@@ -133,7 +133,7 @@ static int gmres_impl(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, doubl
     const bool device_cycle = !precond && !flexible;
     void* gH = nullptr; void* ge = nullptr; double* gres = nullptr;
     cudaGraphExec_t cycle_exec = nullptr; int64_t cycle_launches = 0;
-    auto cleanup_dev = [&]() { cudaStreamSynchronize(c->stream); if (cycle_exec) cudaGraphExecDestroy(cycle_exec); if (gH) cudaFree(gH); if (ge) cudaFree(ge); if (gres) cudaFree(gres); };
+    auto cleanup_dev = [&]() { cudaStreamSynchronize(c->stream); if (cycle_exec) cudaGraphExecDestroy(cycle_exec); dev_free(c, gH); dev_free(c, ge); dev_free(c, gres); };
     auto enqueue_cycle = [&]() -> int {
         char* gcs = (char*)ge + (size_t)(kdim + 1) * 16; char* gsn = gcs + (size_t)kdim * 16;
         const bool fin_ok = c->fin && (c->world == 1 || c->p2p_active);
@@ -158,8 +158,8 @@ static int gmres_impl(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, doubl
         return 0;
     };
     if (device_cycle) {
-        if (cudaMalloc(&gH, (size_t)(kdim + 1) * kdim * 16) != cudaSuccess || cudaMalloc(&ge, (size_t)(3 * kdim + 2) * 16) != cudaSuccess ||
-            cudaMalloc((void**)&gres, (size_t)(kdim + 2) * 8) != cudaSuccess) { cleanup_dev(); set_error("gmres: workspace allocation failed"); return cleanup(LKB_ERR_ALLOC); }
+        if (dev_alloc(c, &gH, (size_t)(kdim + 1) * kdim * 16) != 0 || dev_alloc(c, &ge, (size_t)(3 * kdim + 2) * 16) != 0 ||
+            dev_alloc(c, (void**)&gres, (size_t)(kdim + 2) * 8) != 0) { cleanup_dev(); return cleanup(LKB_ERR_ALLOC); }
         rc = ensure_ws(c, kdim + 1);
         if (rc) { cleanup_dev(); return cleanup(rc); }
         if (c->graphs && !c->profile && (A->type != 9 || A->capturable)) {
@@ -364,9 +364,9 @@ static int cg_impl(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, double r
         const int CH = 16;
         const size_t wsz = kind_cplx(kind) ? 16 : 8;
         void* scal = nullptr; double* res_hist = nullptr;
-        auto cleanup2 = [&](int rr) { cudaStreamSynchronize(c->stream); if (scal) cudaFree(scal); if (res_hist) cudaFree(res_hist); return cleanup(rr); };
-        if (cudaMalloc(&scal, 64) != cudaSuccess || cudaMalloc((void**)&res_hist, (size_t)(maxiter + 2) * sizeof(double)) != cudaSuccess)
-            { set_error("cg: workspace allocation failed"); return cleanup2(LKB_ERR_ALLOC); }
+        auto cleanup2 = [&](int rr) { cudaStreamSynchronize(c->stream); dev_free(c, scal); dev_free(c, res_hist); return cleanup(rr); };
+        if (dev_alloc(c, &scal, 64) != 0 || dev_alloc(c, (void**)&res_hist, (size_t)(maxiter + 2) * sizeof(double)) != 0)
+            return cleanup2(LKB_ERR_ALLOC);
 #undef CG_TRY
 #define CG_TRY(call) do { rc = (call); if (rc) return cleanup2(rc); } while (0)
         CG_TRY(ensure_ws(c, 2));

@@ -101,13 +101,87 @@ def test_c_client_runs_on_gpu(so_path, tmp_path):
     assert "info=0" in r.stdout
 
 
-def test_fortran_shim_binds_only_exported_symbols(so_path):
-    """The ISO_C_BINDING shim cannot be compiled here (no Fortran compiler): at least every bind(C) name it
-    uses must be an entry point of include/lkb.h that liblkb.so exports."""
+def _c_prototypes():
+    """name -> list of (is_pointer, base type) for every function declared in include/lkb.h."""
+    src = open(os.path.join(ROOT, "include", "lkb.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(lkb_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        name, args = m.group(1), " ".join(m.group(2).split())
+        if name in ("lkb_matvec_fn", "lkb_precond_fn"):
+            continue
+        params = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = a.strip()
+                is_ptr = "*" in a
+                base = re.sub(r"\bconst\b", "", a).replace("*", " ")
+                base = " ".join(base.split()[:-1]) if len(base.split()) > 1 else base.strip()
+                params.append((is_ptr, base))
+        protos[name] = params
+    return protos
+
+
+HANDLES = {"lkb_ctx_t", "lkb_vec_t", "lkb_basis_t", "lkb_op_t"}
+FWIDTH = {"int": "c_int", "int32_t": "c_int32_t", "int64_t": "c_int64_t", "uint64_t": "c_int64_t", "double": "c_double"}
+
+
+def test_fortran_shim_interfaces_match_header(so_path):
+    """The ISO_C_BINDING shim cannot be compiled here (no Fortran compiler, also not on the GPU box), so every bind(C)
+    interface of the generated module is checked against the C prototypes of include/lkb.h: the symbol is exported, the
+    argument COUNT agrees, and every argument agrees in by-value-ness and width: a C scalar / handle / function pointer
+    must be `value` with the matching c_* kind; a C pointer is either `type(c_ptr), value` or a by-reference dummy."""
+    import subprocess, sys
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "fortran", "gen_shim.py")], stdout=subprocess.DEVNULL)
     src = open(os.path.join(ROOT, "fortran", "lightkrylov_cuda.f90")).read()
-    names = set(re.findall(r"bind\(C,\s*name='(lkb_[a-z0-9_]+)'\)", src))
-    assert len(names) >= 20
+    protos = _c_prototypes()
     lib = ctypes.CDLL(so_path)
-    declared = set(_declared_symbols())
-    assert names <= declared, names - declared
-    assert all(hasattr(lib, n) for n in names)
+    blocks = re.findall(r"function (lkb_[a-z0-9_]+)\(([^)]*)\) bind\(C, name='(lkb_[a-z0-9_]+)'\)(.*?)end function", src, flags=re.S)
+    assert len(blocks) >= 40
+    for fname, dummies, cname, body in blocks:
+        assert fname == cname and hasattr(lib, cname), cname
+        cparams = protos[cname]
+        names = [d.strip() for d in dummies.split(",") if d.strip()]
+        assert len(names) == len(cparams), f"{cname}: {len(names)} Fortran arguments vs {len(cparams)} in lkb.h"
+        decl = {}
+        for line in body.splitlines():
+            if "::" in line:
+                left, right = line.split("::")
+                for nm in right.split(","):
+                    decl[nm.strip()] = left.strip()
+        for nm, (is_ptr, base) in zip(names, cparams):
+            d = decl[nm]
+            by_value = "value" in d
+            if base in ("lkb_matvec_fn", "lkb_precond_fn"):
+                assert d.startswith("type(c_funptr)") and by_value, (cname, nm, d)
+            elif base in HANDLES and not is_ptr:
+                assert d.startswith("type(c_ptr)") and by_value, (cname, nm, d)
+            elif not is_ptr:
+                assert by_value and FWIDTH[base] in d, (cname, nm, d, base)
+            else:
+                # pointer in C: address passed by value, or a by-reference dummy of the pointee's width
+                if d.startswith("type(c_ptr)"):
+                    assert by_value or "intent(out)" in d, (cname, nm, d)
+                    if "intent(out)" in d:
+                        assert base in HANDLES, (cname, nm, d, base)          # handle out-argument (T* where T is a handle)
+                else:
+                    assert not by_value and FWIDTH.get(base, "?") in d, (cname, nm, d, base)
+    # the try-functions exist for all four kinds with the reference's argument lists
+    for sfx in ("rsp", "rdp", "csp", "cdp"):
+        for fn, args in (("arnoldi", "A, X, H, info, kstart, kend, tol, transpose, blksize"), ("lanczos", "A, X, T, info, kstart, kend, tol"),
+                         ("bidiagonalization", "A, U, V, B, info, kstart, kend, tol"), ("qr", "Q, R, info, tol"),
+                         ("gmres", "A, b, x, info, rtol, atol, preconditioner, options, transpose, meta"),
+                         ("fgmres", "A, b, x, info, rtol, atol, preconditioner, options, transpose, meta"),
+                         ("cg", "A, b, x, info, rtol, atol, preconditioner, options, meta"),
+                         ("eigs", "A, X, eigvals, residuals, info, x0, kdim, tolerance, transpose, write_intermediate"),
+                         ("eighs", "A, X, eigvals, residuals, info, x0, kdim, tolerance, write_intermediate"),
+                         ("svds", "A, U, S, V, residuals, info, u0, kdim, tolerance, write_intermediate"),
+                         ("dgs_vector", "y, X, info, if_chk_orthonormal, beta"), ("dgs_basis", "Y, X, info, if_chk_orthonormal, beta"),
+                         ("orthogonalize_vector", "y, X, info, if_chk_orthonormal, beta"),
+                         ("orthogonalize_basis", "Y, X, info, if_chk_orthonormal, beta")):
+            assert f"function lkb_try_{fn}_{sfx}({args}) result(done)" in src, (fn, sfx)
+    # no component of the device vector is default-initialised (intent(out) dummies must not reset the handle)
+    for sfx in ("rsp", "rdp", "csp", "cdp"):
+        tdef = src[src.index(f":: cuda_vector_{sfx}\n"):]
+        tdef = tdef[:tdef.index("contains")]
+        assert "=" not in tdef.replace("=>", ""), tdef

@@ -779,3 +779,40 @@ def test_csr_create_validates_indices(lk, ctx):
     x = lk.Vector(ctx, "d", n).put(np.arange(1.0, n + 1)); y = lk.Vector(ctx, "d", m)
     A.matvec(x, y)
     assert np.array_equal(y.get(), np.array([3.0, 5.0, 7.0, 5.0, 6.0]))
+
+
+# ---------------------------------------------------------------------------------------------
+# basis-level helpers: axpby_basis / copy / rand_basis / views / initialize_krylov_subspace
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["d", "z", "s"])
+def test_basis_level_helpers(lk, ctx, oracle, kind):
+    dt = lk.DTYPES[kind]; n, p = 3001, 5
+    rng = np.random.default_rng(11)
+    Xh, Yh = randn(rng, (n, p), dt), randn(rng, (n, p + 2), dt)
+    X = lk.Basis(ctx, kind, n, p).put(Xh); Y = lk.Basis(ctx, kind, n, p + 2).put(Yh)
+    alpha, beta = (0.5 - 0.25j, 2.0 + 1.0j) if kind == "z" else (0.5, 2.0)
+    Y.axpby(alpha, X, beta, xcol0=1, ycol0=2, ncols=3)                 # axpby_basis on array sections X(2:4), Y(3:5)
+    ref = Yh.copy(); ref[:, 2:5] = (alpha * Xh[:, 1:4] + beta * Yh[:, 2:5]).astype(dt)
+    np.testing.assert_allclose(Y.get(), ref, rtol=1e-6 if kind == "s" else 1e-14, atol=1e-6 if kind == "s" else 1e-14)
+    Y.put(np.full((n, 2), np.nan, dtype=dt), col0=0)
+    Y.copy_from(X, xcol0=3, ycol0=0, ncols=2)                           # copy overwrites NaN garbage (beta = 0)
+    assert np.array_equal(Y.get(0, 2), Xh[:, 3:5])
+    # a view is the same memory: operations through it land in the parent
+    V = Y.view(2, 3)
+    V.zero()
+    assert not Y.get(2, 3).any() and np.array_equal(Y.get(0, 2), Xh[:, 3:5])
+    # rand_basis + orthonormalize_basis == initialize_random_orthonormal_basis
+    ctx.set_seed(5)
+    R = lk.Basis(ctx, kind, n, 4); R.rand(ifnorm=True)
+    Rg = R.get()
+    assert np.abs(np.linalg.norm(Rg.astype(np.complex128), axis=0) - 1).max() < (1e-6 if kind == "s" else 1e-13)
+    assert R.orthonormalize() == 0
+    Rg = R.get()
+    assert np.abs(Rg.conj().T @ Rg - np.eye(4)).max() < orth_tol(kind)
+    # initialize_krylov_subspace(X, X0): zero, copy, orthonormalise (utilities.fypp:32-46) vs the oracle's qr
+    K = lk.Basis(ctx, kind, n, 9).put(randn(rng, (n, 9), dt))
+    X0h = randn(rng, (n, 2), dt)
+    lk.initialize_krylov_subspace(K, lk.Basis(ctx, kind, n, 2).put(X0h))
+    Q0 = X0h.copy(order="F"); oracle.qr(Q0)
+    Kg = K.get()
+    assert rel_normwise(Kg[:, :2], Q0) < tol_for(kind) and not Kg[:, 2:].any()
