@@ -207,6 +207,18 @@ int lkb_eighs(lkb_op_t A, lkb_basis_t X, int nev, double* eigvals, double* resid
 /* svds(A, U, S, V, residuals, info, u0, kdim, tolerance)  SVDS/svd_solvers.fypp:28-121 */
 int lkb_svds(lkb_op_t A, lkb_basis_t U, double* S, lkb_basis_t V, int nsv, double* residuals, int32_t* info,
              lkb_vec_t u0, int32_t kdim, double tolerance);
+/* kexpm_vec(c, A, b, tau, tol, info, trans, kdim)  src/Expm/ExpmLib.fypp:128-232: c = exp(tau A) b by Arnoldi + dense expm of
+ * the (k+1) x (k+1) extended Hessenberg matrix (stdlib_linalg `expm`: Pade 10 + scaling and squaring, restated on the host).
+ * info = dimension used when |E(kp,1) beta| <= tol, -1 when not converged within kdim (<= 0: 100) steps. */
+int lkb_kexpm_vec(lkb_vec_t c, lkb_op_t A, lkb_vec_t b, double tau, double tol, int32_t* info, int32_t trans, int32_t kdim);
+/* on-disk formats of the spectral solvers (IterativeSolvers.fypp:882-963).  write_results: the text table the reference
+ * rewrites every step as eigs_output.txt / eighs_output.txt / svds_output.txt ('(I6,4(2X,E16.9),2X,L4)'); vals = k reals or
+ * k (re, im) pairs, res is sorted ascending in place as the reference does.  save_eigenspectrum: NPY 1.0, Fortran order,
+ * k x 3 (Re, Im, residual) or k x 2 (value, residual), '<f8' or '<f4'.  lkb_set_option(ctx, "write_intermediate", 1) makes
+ * eigs / eighs / svds write their table every step (rank 0 only); default off (the reference: on for eigs only). */
+int lkb_write_results(const char* filename, int32_t is_complex, const double* vals, double* res, int32_t k, double tol);
+int lkb_save_eigenspectrum(const char* fname, int32_t is_complex, int32_t single_precision, const double* lambda,
+                           const double* residuals, int32_t k);
 /* host LAPACK provider for the k x k algebra of eigs/eighs/svds/krylov_schur (geev, gees, trsen,
  * syev/heev, gesvd): a shared library exporting Fortran-ABI LAPACK, symbol = prefix + name + suffix
  * (e.g. scipy's bundled OpenBLAS: prefix "scipy_", suffix "_").  The reference gets these from

@@ -589,6 +589,35 @@ def initialize_random_orthonormal_basis(X: Basis, col0: int = 0, p: Optional[int
     check(X.ctx.lib.lkb_initialize_random_orthonormal_basis(X.h, col0, X.ncols - col0 if p is None else p), "initialize_random_orthonormal_basis")
 
 
+def kexpm(c: Vector, A: LinOp, b: Vector, tau: float, tol: float, trans: bool = False, kdim: int = 0) -> int:
+    """kexpm_vec(c, A, b, tau, tol, info, trans, kdim)  (src/Expm/ExpmLib.fypp:128-232): c = exp(tau A) b; returns info."""
+    info = C.c_int32()
+    check(A.ctx.lib.lkb_kexpm_vec(c.h, A.h, b.h, float(tau), float(tol), C.byref(info), int(trans), int(kdim)), "kexpm_vec")
+    return info.value
+
+
+def write_results(filename: str, vals: np.ndarray, res: np.ndarray, tol: float) -> np.ndarray:
+    """write_results (IterativeSolvers.fypp:882-924); returns the residuals in the sorted order the reference leaves them in."""
+    v = np.ascontiguousarray(vals)
+    cplx = np.iscomplexobj(v)
+    vv = np.ascontiguousarray(v.astype(np.complex128).view(np.float64) if cplx else v.astype(np.float64))
+    rr = np.ascontiguousarray(res, dtype=np.float64).copy()
+    check(_lib.load().lkb_write_results(filename.encode(), int(cplx), vv.ctypes.data_as(C.POINTER(C.c_double)),
+                                   rr.ctypes.data_as(C.POINTER(C.c_double)), int(rr.size), float(tol)), "write_results")
+    return rr
+
+
+def save_eigenspectrum(lam: np.ndarray, residuals: np.ndarray, fname: str) -> None:
+    """save_eigenspectrum (IterativeSolvers.fypp:941-960): .npy, k x 3 (Re, Im, residual) or k x 2 (value, residual)."""
+    v = np.ascontiguousarray(lam)
+    cplx = np.iscomplexobj(v)
+    single = v.dtype in (np.float32, np.complex64)
+    vv = np.ascontiguousarray(v.astype(np.complex128).view(np.float64) if cplx else v.astype(np.float64))
+    rr = np.ascontiguousarray(residuals, dtype=np.float64)
+    check(_lib.load().lkb_save_eigenspectrum(fname.encode(), int(cplx), int(single), vv.ctypes.data_as(C.POINTER(C.c_double)),
+                                        rr.ctypes.data_as(C.POINTER(C.c_double)), int(rr.size)), "save_eigenspectrum")
+
+
 def krylov_schur(X: Basis, H: np.ndarray, kdim: int) -> int:
     _hostmat(H, X.kind)
     n = C.c_int32()

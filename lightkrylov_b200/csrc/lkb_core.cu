@@ -325,6 +325,7 @@ int lkb_set_option(lkb_ctx_t c, const char* name, int value) {
     if (!strcmp(name, "graphs")) c->graphs = value != 0;
     else if (!strcmp(name, "fused")) c->fused = value != 0;
     else if (!strcmp(name, "fin")) c->fin = value != 0;
+    else if (!strcmp(name, "write_intermediate")) c->write_intermediate = value != 0;
     else if (!strcmp(name, "fused_halo")) c->fused_halo = value != 0;
     else if (!strcmp(name, "p2p")) c->p2p_active = (value != 0) && c->p2p.world > 1;
     else { set_error("unknown option %s", name); return LKB_ERR_ARG; }

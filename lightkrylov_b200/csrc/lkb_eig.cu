@@ -147,6 +147,23 @@ int device_combine(lkb_basis_s* Xw, int k, const std::vector<cd>& Zc, int ldz, i
     return check_launch(c, "basis_gemm");
 }
 
+// Two pinned host slots + events for the "collect step k, enqueue step k+1 speculatively, then run the host LAPACK
+// of step k" pipeline shared by eigs / eighs / svds.
+struct StepSlots {
+    void* slot[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    int init(size_t bytes) {
+        for (int q = 0; q < 2; ++q)
+            if (cudaMallocHost(&slot[q], bytes) != cudaSuccess || cudaEventCreateWithFlags(&ev[q], cudaEventDisableTiming) != cudaSuccess) {
+                release(); set_error("pinned staging allocation failed"); return LKB_ERR_ALLOC;
+            }
+        return 0;
+    }
+    void release() {
+        for (int q = 0; q < 2; ++q) { if (slot[q]) cudaFreeHost(slot[q]); if (ev[q]) cudaEventDestroy(ev[q]); slot[q] = nullptr; ev[q] = nullptr; }
+    }
+};
+
 int start_vector(lkb_basis_s* Xw, lkb_vec_t x0) {
     lkb_ctx_s* c = Xw->ctx;
     const int kind = Xw->kind;
@@ -338,6 +355,11 @@ int lkb_eigs(lkb_op_t A, lkb_basis_t X, int nev, double* eigvals, double* residu
             }
             niter++;
             EG_TRY(bcast_host(c, res.data(), (size_t)k * sizeof(double)));
+            if (c->write_intermediate && c->rank == 0) {          // write_results_c(eigs_output, ...)  (:1091)
+                std::vector<double> vv(2 * (size_t)k), rr(res.begin(), res.begin() + k);
+                for (int i = 0; i < k; ++i) { vv[2 * i] = vals[i].real(); vv[2 * i + 1] = vals[i].imag(); }
+                lkb_write_results("eigs_output.txt", 1, vv.data(), rr.data(), k, tol);
+            }
             conv = 0; for (int i = 0; i < k; ++i) conv += res[i] < tol;
             if (conv >= nev) {
                 // a speculative step k+1 may still be running: it is discarded (never collected, so the
@@ -402,9 +424,26 @@ int lkb_eighs(lkb_op_t A, lkb_basis_t X, int nev, double* eigvals, double* resid
     std::vector<double> ev(kd, 0.0), res(kd, 0.0);
     std::vector<cd> vecs((size_t)kd * kd, cd(0));
     int k = 1, conv = 0;
+    // Host/device overlap as in eigs: step k+1 is enqueued speculatively before the host runs syev / heev on T_k
+    // (eighs.fypp:84-100); Xwrk and T are internal work arrays, a speculative step past convergence is discarded.
+    StepSlots ss;
+    EH_TRY(ss.init((size_t)ldt * es + 256));
+#undef EH_TRY
+#define EH_TRY(call) do { rc = (call); if (rc) { cudaStreamSynchronize(c->stream); ss.release(); return cleanup(rc); } } while (0)
+    const double atolk = atol_of(kind);
+    auto enqueue_step = [&](int kk) -> int {
+        LKB_TRY(lanczos_enqueue(A, Xw, kk, kk, atolk));
+        LKB_TRY(krylov_fetch_async(c, kind, ldt, kk, kk, ss.slot[kk & 1]));
+        LKB_CUDA(cudaEventRecord(ss.ev[kk & 1], c->stream));
+        return 0;
+    };
+    int inflight = 0;
     for (k = 1; k <= kd; ++k) {
         int32_t linfo = 0;
-        EH_TRY(lkb_lanczos(A, Xw, T.data(), ldt, &linfo, k, k, -1.0));
+        if (inflight < k) { EH_TRY(enqueue_step(k)); inflight = k; }
+        EH_TRY(cudaEventSynchronize(ss.ev[k & 1]) == cudaSuccess ? 0 : LKB_ERR_CUDA);
+        EH_TRY(lanczos_collect(A, Xw, T.data(), ldt, &linfo, k, k, ss.slot[k & 1]));
+        if (linfo == 0 && k < kd) { EH_TRY(enqueue_step(k + 1)); inflight = k + 1; }      // speculative
         std::fill(ev.begin(), ev.end(), 0.0); std::fill(vecs.begin(), vecs.end(), cd(0));
         lint n = k, linf = 0;
         if (cplx) {
@@ -420,14 +459,22 @@ int lkb_eighs(lkb_op_t A, lkb_basis_t X, int nev, double* eigvals, double* resid
             g_la.dsyev("V", "L", &n, a.data(), &n, ev.data(), work.data(), &lwork, &linf, 1, 1);
             for (int j = 0; j < k; ++j) for (int i = 0; i < k; ++i) vecs[i + (size_t)kd * j] = a[i + (size_t)k * j];
         }
-        if (linf != 0) { set_error("SYEV/HEEV failed, info = %d", (int)linf); return cleanup(LKB_ERR_LAPACK); }
+        if (linf != 0) { set_error("SYEV/HEEV failed, info = %d", (int)linf); EH_TRY(LKB_ERR_LAPACK); }
         const cd beta = load_kind(kind, T.data(), (size_t)k + (size_t)ldt * (k - 1));
         std::fill(res.begin(), res.end(), 0.0);
         for (int i = 0; i < k; ++i) res[i] = std::abs(beta * vecs[(k - 1) + (size_t)kd * i]);
         EH_TRY(bcast_host(c, res.data(), (size_t)k * sizeof(double)));
+        if (c->write_intermediate && c->rank == 0) {              // write_results_r(eighs_output, ...)  (eighs.fypp:99)
+            std::vector<double> rr(res.begin(), res.begin() + k);
+            lkb_write_results("eighs_output.txt", 0, ev.data(), rr.data(), k, tol);
+        }
         conv = 0; for (int i = 0; i < k; ++i) conv += res[i] < tol;
         if (conv >= nev) break;
     }
+    EH_TRY(cudaStreamSynchronize(c->stream) == cudaSuccess ? 0 : LKB_ERR_CUDA);     // a discarded speculative step may still run
+    ss.release();
+#undef EH_TRY
+#define EH_TRY(call) do { rc = (call); if (rc) return cleanup(rc); } while (0)
     EH_TRY(bcast_host(c, ev.data(), ev.size() * sizeof(double)));
     EH_TRY(bcast_host(c, vecs.data(), vecs.size() * sizeof(cd)));
     std::vector<int> idx = sort_index_reverse(ev);        // over all kdim_ entries, zero padding included (eighs.fypp:106-107)
@@ -468,9 +515,24 @@ int lkb_svds(lkb_op_t A, lkb_basis_t U, double* S, lkb_basis_t V, int nsv, doubl
     std::vector<cd> umat((size_t)kd * kd), vmat((size_t)kd * kd);
     *info = 0;
     int k = 1, conv = 0;
+    // speculative step k+1 overlapped with the host gesdd of B_k (svd_solvers.fypp:85-101), as in eigs / eighs
+    StepSlots ss;
+    SV_TRY(ss.init((size_t)ldb * es + 256));
+#undef SV_TRY
+#define SV_TRY(call) do { rc = (call); if (rc) { cudaStreamSynchronize(c->stream); ss.release(); return cleanup(rc); } } while (0)
+    auto enqueue_step = [&](int kk) -> int {
+        LKB_TRY(bidiag_enqueue(A, Uw, Vw, kk, kk, tol));                    // tol = solver tolerance (svd_solvers.fypp:82)
+        LKB_TRY(krylov_fetch_async(c, kind, ldb, kk, kk, ss.slot[kk & 1]));
+        LKB_CUDA(cudaEventRecord(ss.ev[kk & 1], c->stream));
+        return 0;
+    };
+    int inflight = 0;
     for (k = 1; k <= kd; ++k) {
         int32_t binfo = 0;
-        SV_TRY(lkb_bidiag(A, Uw, Vw, B.data(), ldb, &binfo, k, k, tol));      // tol = solver tolerance (svd_solvers.fypp:82)
+        if (inflight < k) { SV_TRY(enqueue_step(k)); inflight = k; }
+        SV_TRY(cudaEventSynchronize(ss.ev[k & 1]) == cudaSuccess ? 0 : LKB_ERR_CUDA);
+        SV_TRY(bidiag_collect(A, Uw, B.data(), ldb, &binfo, k, k, ss.slot[k & 1]));
+        if (binfo == 0 && k < kd) { SV_TRY(enqueue_step(k + 1)); inflight = k + 1; }      // speculative
         std::fill(sv.begin(), sv.end(), 0.0);
         std::fill(umat.begin(), umat.end(), cd(0)); std::fill(vmat.begin(), vmat.end(), cd(0));
         lint n = k, linf = 0;
@@ -495,14 +557,22 @@ int lkb_svds(lkb_op_t A, lkb_basis_t U, double* S, lkb_basis_t V, int nsv, doubl
                 vmat[i + (size_t)kd * j] = vt[j + (size_t)k * i];
             }
         }
-        if (linf != 0) { set_error("GESDD failed, info = %d", (int)linf); return cleanup(LKB_ERR_LAPACK); }
+        if (linf != 0) { set_error("GESDD failed, info = %d", (int)linf); SV_TRY(LKB_ERR_LAPACK); }
         const cd beta = load_kind(kind, B.data(), (size_t)k + (size_t)ldb * (k - 1));
         std::fill(res.begin(), res.end(), 0.0);
         for (int i = 0; i < k; ++i) res[i] = std::abs(beta * vmat[(k - 1) + (size_t)kd * i]);
         SV_TRY(bcast_host(c, res.data(), (size_t)k * sizeof(double)));
+        if (c->write_intermediate && c->rank == 0) {              // write_results_r(svds_output, ...)  (svd_solvers.fypp:100)
+            std::vector<double> rr(res.begin(), res.begin() + k);
+            lkb_write_results("svds_output.txt", 0, sv.data(), rr.data(), k, tol);
+        }
         conv = 0; for (int i = 0; i < k; ++i) conv += res[i] < tol;
         if (conv >= nsv) break;
     }
+    SV_TRY(cudaStreamSynchronize(c->stream) == cudaSuccess ? 0 : LKB_ERR_CUDA);
+    ss.release();
+#undef SV_TRY
+#define SV_TRY(call) do { rc = (call); if (rc) return cleanup(rc); } while (0)
     SV_TRY(bcast_host(c, sv.data(), sv.size() * sizeof(double)));
     SV_TRY(bcast_host(c, umat.data(), umat.size() * sizeof(cd)));
     SV_TRY(bcast_host(c, vmat.data(), vmat.size() * sizeof(cd)));

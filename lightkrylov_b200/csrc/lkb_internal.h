@@ -55,6 +55,7 @@ struct lkb_ctx_s {
     bool graphs = true;
     bool fused = true;
     bool fin = true;            // final CGS2 pass fused with normalisation + column update (k_multiaxpy_fin)
+    bool write_intermediate = false;   // eigs / eighs / svds rewrite <solver>_output.txt every step (rank 0)
     bool fused_halo = true;     // P2P halo push fused into the kernel that finishes the next matvec input
     // in-kernel NVLink allreduce (CUDA IPC peer buffers); falls back to NCCL when not attached
     bool p2p_active = false;
@@ -151,4 +152,9 @@ int arnoldi_enqueue(lkb_op_s* A, lkb_basis_s* X, int kstart, int kend, double to
 int arnoldi_fetch_async(lkb_basis_s* X, int kstart, int kend, void* pinned_host);
 int arnoldi_collect(lkb_op_s* A, lkb_basis_s* X, void* H, int ldh, int32_t* info, int kstart, int kend, bool tr,
                     const void* pinned_host);
+int krylov_fetch_async(lkb_ctx_s* c, int kind, int ldd, int kstart, int kend, void* pinned_host);
+int lanczos_enqueue(lkb_op_s* A, lkb_basis_s* X, int kstart, int kend, double tol);
+int lanczos_collect(lkb_op_s* A, lkb_basis_s* X, void* T, int ldt, int32_t* info, int kstart, int kend, const void* pinned_host);
+int bidiag_enqueue(lkb_op_s* A, lkb_basis_s* U, lkb_basis_s* V, int kstart, int kend, double tol);
+int bidiag_collect(lkb_op_s* A, lkb_basis_s* U, void* B, int ldb, int32_t* info, int kstart, int kend, const void* pinned_host);
 }  // namespace lkb

@@ -462,14 +462,7 @@ int arnoldi_enqueue(lkb_op_s* A, lkb_basis_s* X, int kstart, int kend, double to
 }
 // D2H of the freshly written Hessenberg columns + flags into `host` (pinned), no sync
 int arnoldi_fetch_async(lkb_basis_s* X, int kstart, int kend, void* host) {
-    lkb_ctx_s* c = X->ctx;
-    const size_t es = kind_size(X->kind);
-    const int ldhd = X->ncols;
-    const int ncol = kend - kstart + 1;
-    char* hs = (char*)host;
-    LKB_CUDA(cudaMemcpyAsync(hs, (char*)c->Hd + (size_t)ldhd * (kstart - 1) * es, (size_t)ldhd * ncol * es, cudaMemcpyDeviceToHost, c->stream));
-    LKB_CUDA(cudaMemcpyAsync(hs + (size_t)ldhd * ncol * es, c->flags, F_COUNT * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    return 0;
+    return krylov_fetch_async(X->ctx, X->kind, X->ncols, kstart, kend, host);
 }
 // after the stream reached the fetch: scatter the columns into the caller's H, set info, refill on breakdown
 int arnoldi_collect(lkb_op_s* A, lkb_basis_s* X, void* H, int ldh, int32_t* info, int kstart, int kend, bool tr,
@@ -588,14 +581,28 @@ int lkb_lanczos(lkb_op_t A, lkb_basis_t X, void* T, int ldt, int32_t* info, int3
     if (kstart > kend || kend > kdim || ldt < kend + 1 || A->kind != X->kind || A->m != X->n || A->n != X->n)
         { set_error("lanczos: inconsistent sizes"); return LKB_ERR_ARG; }
     lkb_ctx_s* c = X->ctx;
+    if (tol < 0) tol = atol_of(X->kind);
+    *info = 0;
+    LKB_TRY(ensure_hstage(c, (size_t)(kdim + 1) * (kend - kstart + 1) * kind_size(X->kind) + 4096));
+    LKB_TRY(lanczos_enqueue(A, X, kstart, kend, tol));
+    LKB_TRY(krylov_fetch_async(X->ctx, X->kind, kdim + 1, kstart, kend, c->hstage));
+    LKB_CUDA(cudaStreamSynchronize(c->stream));
+    return lanczos_collect(A, X, T, ldt, info, kstart, kend, c->hstage);
+}
+
+}  // extern "C"
+
+namespace lkb {
+// The three phases of lanczos / bidiagonalization (as for arnoldi): eighs and svds overlap the host syev / gesdd of
+// step k with the device work of a speculative step k+1.
+int lanczos_enqueue(lkb_op_s* A, lkb_basis_s* X, int kstart, int kend, double tol) {
+    lkb_ctx_s* c = X->ctx;
     const int kind = X->kind;
     const size_t es = kind_size(kind);
-    if (tol < 0) tol = atol_of(kind);
-    *info = 0;
+    const int kdim = X->ncols - 1;
     const int ldtd = kdim + 1;
     LKB_TRY(ensure_Hd(c, (size_t)ldtd * kdim * es));
     LKB_TRY(ensure_ws(c, kend + 1));
-    LKB_TRY(ensure_hstage(c, (size_t)ldtd * (kend - kstart + 1) * es + 4096));
     const size_t ndw = 2 * (size_t)(kind_cplx(kind) ? 2 : 1);
     auto body = [&]() -> int {
         LKB_TRY(reset_flags(c));
@@ -621,13 +628,24 @@ int lkb_lanczos(lkb_op_t A, lkb_basis_t X, void* T, int ldt, int32_t* info, int3
         }
         return 0;
     };
-    LKB_TRY(run_maybe_graph(c, op_capturable(A), make_key("lan", A, X, nullptr, kstart, kend, tol, 0), body));
+    return run_maybe_graph(c, op_capturable(A), make_key("lan", A, X, nullptr, kstart, kend, tol, 0), body);
+}
+// D2H of the freshly written columns of the device-side H / T / B (leading dimension ldd) + flags, no sync
+int krylov_fetch_async(lkb_ctx_s* c, int kind, int ldd, int kstart, int kend, void* host) {
+    const size_t es = kind_size(kind);
     const int ncol = kend - kstart + 1;
-    char* hs = (char*)c->hstage;
-    LKB_CUDA(cudaMemcpyAsync(hs, (char*)c->Hd + (size_t)ldtd * (kstart - 1) * es, (size_t)ldtd * ncol * es, cudaMemcpyDeviceToHost, c->stream));
+    char* hs = (char*)host;
+    LKB_CUDA(cudaMemcpyAsync(hs, (char*)c->Hd + (size_t)ldd * (kstart - 1) * es, (size_t)ldd * ncol * es, cudaMemcpyDeviceToHost, c->stream));
+    LKB_CUDA(cudaMemcpyAsync(hs + (size_t)ldd * ncol * es, c->flags, F_COUNT * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    return 0;
+}
+int lanczos_collect(lkb_op_s* A, lkb_basis_s* X, void* T, int ldt, int32_t* info, int kstart, int kend, const void* host) {
+    const int kind = X->kind;
+    const size_t es = kind_size(kind);
+    const int ldtd = X->ncols;
+    const int ncol = kend - kstart + 1;
+    const char* hs = (const char*)host;
     int hf[F_COUNT];
-    LKB_CUDA(cudaMemcpyAsync(hs + (size_t)ldtd * ncol * es, c->flags, F_COUNT * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    LKB_CUDA(cudaStreamSynchronize(c->stream));
     memcpy(hf, hs + (size_t)ldtd * ncol * es, sizeof(hf));
     if (hf[F_NAN]) { set_error("lanczos: NaN norm"); return LKB_ERR_NAN; }
     const int kdone = hf[F_STOP] ? hf[F_INFO] : kend;
@@ -635,9 +653,12 @@ int lkb_lanczos(lkb_op_t A, lkb_basis_t X, void* T, int ldt, int32_t* info, int3
         for (int i = (k - 1 > 1 ? k - 1 : 1); i <= k + 1; ++i)
             host_store(kind, T, (int64_t)(i - 1) + (int64_t)ldt * (k - 1), hs, (int64_t)(i - 1) + (int64_t)ldtd * (k - kstart));
     A->n_matvec += kdone - kstart + 1;
-    if (hf[F_STOP]) *info = hf[F_INFO];
+    *info = hf[F_STOP] ? hf[F_INFO] : 0;
     return 0;
 }
+}  // namespace lkb
+
+extern "C" {
 
 // ------------------------------------------------------------------------------------------
 // bidiagonalization : src/Krylov/golub_kahan.fypp:7-64.   A is m x n; U has m rows, V has n rows.
@@ -651,14 +672,26 @@ int lkb_bidiag(lkb_op_t A, lkb_basis_t U, lkb_basis_t V, void* B, int ldb, int32
     if (kstart > kend || kend > kdim || V->ncols < kend || ldb < kend + 1 || A->kind != U->kind || A->kind != V->kind ||
         A->m != U->n || A->n != V->n) { set_error("bidiag: inconsistent sizes"); return LKB_ERR_ARG; }
     lkb_ctx_s* c = U->ctx;
+    if (tol < 0) tol = atol_of(U->kind);
+    *info = 0;
+    LKB_TRY(ensure_hstage(c, (size_t)(kdim + 1) * (kend - kstart + 1) * kind_size(U->kind) + 4096));
+    LKB_TRY(bidiag_enqueue(A, U, V, kstart, kend, tol));
+    LKB_TRY(krylov_fetch_async(c, U->kind, kdim + 1, kstart, kend, c->hstage));
+    LKB_CUDA(cudaStreamSynchronize(c->stream));
+    return bidiag_collect(A, U, B, ldb, info, kstart, kend, c->hstage);
+}
+
+}  // extern "C"
+
+namespace lkb {
+int bidiag_enqueue(lkb_op_s* A, lkb_basis_s* U, lkb_basis_s* V, int kstart, int kend, double tol) {
+    lkb_ctx_s* c = U->ctx;
     const int kind = U->kind;
     const size_t es = kind_size(kind);
-    if (tol < 0) tol = atol_of(kind);
-    *info = 0;
+    const int kdim = U->ncols - 1;
     const int ldbd = kdim + 1;
     LKB_TRY(ensure_Hd(c, (size_t)ldbd * kdim * es));
     LKB_TRY(ensure_ws(c, kend + 1));
-    LKB_TRY(ensure_hstage(c, (size_t)ldbd * (kend - kstart + 1) * es + 4096));
     auto body = [&]() -> int {
         LKB_TRY(reset_flags(c));
         for (int k = kstart; k <= kend; ++k) {
@@ -672,13 +705,15 @@ int lkb_bidiag(lkb_op_t A, lkb_basis_t U, lkb_basis_t V, void* B, int ldb, int32
         }
         return 0;
     };
-    LKB_TRY(run_maybe_graph(c, op_capturable(A), make_key("bid", A, U, V, kstart, kend, tol, 0), body));
+    return run_maybe_graph(c, op_capturable(A), make_key("bid", A, U, V, kstart, kend, tol, 0), body);
+}
+int bidiag_collect(lkb_op_s* A, lkb_basis_s* U, void* B, int ldb, int32_t* info, int kstart, int kend, const void* host) {
+    const int kind = U->kind;
+    const size_t es = kind_size(kind);
+    const int ldbd = U->ncols;
     const int ncol = kend - kstart + 1;
-    char* hs = (char*)c->hstage;
-    LKB_CUDA(cudaMemcpyAsync(hs, (char*)c->Hd + (size_t)ldbd * (kstart - 1) * es, (size_t)ldbd * ncol * es, cudaMemcpyDeviceToHost, c->stream));
+    const char* hs = (const char*)host;
     int hf[F_COUNT];
-    LKB_CUDA(cudaMemcpyAsync(hs + (size_t)ldbd * ncol * es, c->flags, F_COUNT * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    LKB_CUDA(cudaStreamSynchronize(c->stream));
     memcpy(hf, hs + (size_t)ldbd * ncol * es, sizeof(hf));
     if (hf[F_NAN]) { set_error("bidiag: NaN norm"); return LKB_ERR_NAN; }
     const int stage = hf[F_STOP] ? hf[F_INFO] : 2 * kend;
@@ -690,8 +725,7 @@ int lkb_bidiag(lkb_op_t A, lkb_basis_t U, lkb_basis_t V, void* B, int ldb, int32
     }
     A->n_rmatvec += kdone - kstart + 1;
     A->n_matvec += (stage / 2) - kstart + 1;
-    if (hf[F_STOP]) *info = kdone;
+    *info = hf[F_STOP] ? kdone : 0;
     return 0;
 }
-
-}  // extern "C"
+}  // namespace lkb

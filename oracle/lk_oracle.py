@@ -561,3 +561,59 @@ def svds(A: Op, nsv: int, u0: np.ndarray, kdim=None, tolerance=None):
     U = np.asfortranarray((Uw[:, :k].astype(wd) @ u[:k, :nsv]).astype(dt))
     V = np.asfortranarray((Vw[:, :k].astype(wd) @ vm[:k, :nsv]).astype(dt))
     return sv[:nsv].copy(), res[:nsv].copy(), U, V, k
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# kexpm_vec (src/Expm/ExpmLib.fypp:128-232).  The dense `expm` is stdlib_linalg's (third-party, unpinned, not in the
+# tree): Pade approximant of order 10 with scaling and squaring -- restated here from the published algorithm
+# (Golub & Van Loan Alg. 11.3.1 / Moler & Van Loan method 3) and pinned against scipy.linalg.expm in tests/test_oracle_pins.py.
+# ---------------------------------------------------------------------------------------------------------------
+def expm_pade10(A: np.ndarray) -> np.ndarray:
+    A = np.asarray(A, dtype=np.complex128 if np.iscomplexobj(A) else np.float64)
+    n = A.shape[0]
+    q = 10
+    nrm = np.abs(A).sum(axis=1).max() if n else 0.0
+    ee = max(0, int(np.frexp(nrm)[1]) + 1) if nrm > 0 else 0
+    A2 = A * 2.0 ** (-ee)
+    X = A2.copy()
+    c = 0.5
+    E = np.eye(n, dtype=A.dtype) + c * A2
+    D = np.eye(n, dtype=A.dtype) - c * A2
+    pos = True
+    for k in range(2, q + 1):
+        c = c * (q - k + 1) / (k * (2 * q - k + 1))
+        X = A2 @ X
+        E = E + c * X
+        D = D + (c if pos else -c) * X
+        pos = not pos
+    E = np.linalg.solve(D, E)
+    for _ in range(ee):
+        E = E @ E
+    return E
+
+
+def kexpm_vec(A: Op, b: np.ndarray, tau: float, tol: float, trans: bool = False, kdim: int = 100):
+    """Returns (c, info): c = exp(tau A) b, info = kp when converged, -1 otherwise (ExpmLib.fypp:128-232)."""
+    dt = b.dtype
+    n = b.size
+    nk = kdim
+    beta = norm(b)
+    if beta == 0.0:
+        return np.zeros_like(b), 1
+    X = np.zeros((n, nk + 1), dtype=dt, order="F")
+    X[:, 0] = b / dt.type(beta)
+    H = np.zeros((nk + 1, nk + 1), dtype=dt, order="F")
+    c = np.zeros_like(b)
+    err_est, kp = 0.0, 1
+    for k in range(1, nk + 1):
+        kp = k + 1
+        info = arnoldi(A, X, H, kstart=k, kend=k, trans=trans)
+        breakdown = info == k
+        if breakdown:
+            kp = k
+        E = expm_pade10(tau * H[:kp, :kp])
+        c = (beta * (X[:, :kp] @ E[:kp, 0])).astype(dt)
+        err_est = 0.0 if breakdown else abs(E[kp - 1, 0] * beta)
+        if err_est <= tol:
+            break
+    return c, (kp if err_est <= tol else -1)

@@ -167,3 +167,26 @@ def test_eigs_convdiff_stencil_vs_oracle(lk, ctx, oracle):
     evo, reso, Xo, infoo = oracle.eigs(Ao, n, nev, x0h, kdim=24, tolerance=1e-8)
     assert info == infoo
     assert _match(ev, evo) < 1e-10 * np.abs(evo).max()
+
+
+@pytest.mark.parametrize("kind", ["d", "z", "s"])
+def test_kexpm_vec_vs_oracle(lk, ctx, oracle, kind):
+    """kexpm_vec (src/Expm/ExpmLib.fypp:128-232): c = exp(tau A) b on the device vs the oracle restatement:
+    same `info` (Krylov dimension used) and the same vector."""
+    dims = (24, 20); n = 480
+    coef = (-4.0, 1.0, 1.0, 1.0, 1.0)
+    A = lk.LinOp.stencil5(ctx, kind, *dims, coef); Ao = oracle.Op.stencil(kind, dims, coef)
+    bh = oracle.fill(n, kind, "uniform", 3)
+    b = lk.Vector(ctx, kind, n).put(bh); c = lk.Vector(ctx, kind, n)
+    tol = 1e-10 if kind in "dz" else 1e-5
+    info = lk.kexpm(c, A, b, 0.1, tol)
+    co, oinfo = oracle.kexpm_vec(Ao, bh, 0.1, tol)
+    assert info == oinfo and info > 1
+    assert np.linalg.norm(c.get() - co) < (1e-10 if kind in "dz" else 1e-4) * np.linalg.norm(co)
+    # zero input => zero output (ExpmLib.fypp:180-184); transpose of the symmetric operator gives the same vector
+    z = lk.Vector(ctx, kind, n); c2 = lk.Vector(ctx, kind, n).put(bh)
+    lk.kexpm(c2, A, z, 0.1, tol)
+    assert not c2.get().any()
+    ct = lk.Vector(ctx, kind, n)
+    assert lk.kexpm(ct, A, b, 0.1, tol, trans=True) == info
+    assert np.linalg.norm(ct.get() - co) < (1e-10 if kind in "dz" else 1e-4) * np.linalg.norm(co)
