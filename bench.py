@@ -372,14 +372,37 @@ def run_ours(args):
         roof = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["GBps"] / peak,
                 "traffic": (traffic_ncu["ratio"] * algb[dom] / max(kernels[dom]["launches"], 1)) if traffic_ncu else None,
-                "traffic_ncu": traffic_ncu,
+                "traffic_source": "NOT measured in this run: DRAM bytes / algorithmic bytes of ONE launch (j = 101) in the committed "
+                                  "ncu --set full capture, scaled to this run's average launch",
+                "traffic_from_committed_ncu": traffic_ncu,
                 "alg_bytes_per_launch_avg": algb[dom] / nl, "avg_launch_ms": kernels[dom]["ms_total"] / nl,
                 "peak_source": peak_src,
                 "how": "separate profiled factorisation in the same process: CUDA events on the context stream around "
                        "every launch of the class (graphs off), algorithmic bytes summed over the launches of the class (kdim with the fused CGS2 kernel, 2*kdim without)"}
+    # ---- cross-GPU exchange cost (N > 1): in-kernel %globaltimer totals of the time the last CTA of k_multidot / k_axpy_dot
+    # spends in the NVLink allreduce (latency + waiting for the slowest rank), one extra factorisation, per rank ----
+    sync_profile = None
+    if world > 1 and ctx.p2p:
+        import ctypes as C
+        NW = 4 * 1024 + 16
+        lk._lib.check(lib.lkb_debug_ktime(ctx.h, 1), "ktime")
+        step_resident()
+        buf = (C.c_uint64 * NW)()
+        lk._lib.check(lib.lkb_debug_ktime_read(ctx.h, buf, NW), "ktime_read")
+        lk._lib.check(lib.lkb_debug_ktime(ctx.h, 0), "ktime")
+        t = np.frombuffer(buf, dtype=np.uint64).astype(np.float64)[4096:]
+        mine = [t[8] / max(t[9], 1) / 1e3, t[10] / max(t[11], 1) / 1e3, int(t[9]), int(t[11])]
+        allr = [None] * world
+        dist.all_gather_object(allr, mine)
+        sync_profile = {"what": "average time (us) per launch that the last CTA spends inside the in-kernel NVLink allreduce "
+                                "(LL protocol: one-way latency + wait for the slowest rank), per rank, over one factorisation",
+                        "multidot_allreduce_us": [round(a[0], 2) for a in allr], "fused_allreduce_us": [round(a[1], 2) for a in allr],
+                        "launches": [allr[0][2], allr[0][3]]}
     # whole-step roofline with the official per-step bytes (matvec + 4*j*n*s), per GPU
     total_alg = sum(alg_bytes_step(j, nloc) for j in range(1, kdim + 1))
     step_gbs = total_alg * args.steps / (ms_total * 1e-3) / 1e9
+    actual_b = sum((3 * j + 7) * nloc * 8 for j in range(1, kdim + 1))
+    actual_gbs = actual_b * args.steps / (ms_total * 1e-3) / 1e9
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -406,10 +429,16 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": roof,
             "step_roofline": {"alg_bytes_per_factorisation_per_gpu": total_alg, "achieved_GBps_per_gpu": step_gbs,
-                              "frac_of_measured": step_gbs / peak, "frac_of_nominal_8TBps": step_gbs / 8000.0},
+                              "frac_of_measured": step_gbs / peak, "frac_of_nominal_8TBps": step_gbs / 8000.0,
+                              # what the fused step really moves: 3 sweeps of V (multi-dot, fused axpy+dot, final axpy) and
+                              # 7 vector passes (matvec 2, w in pass 1, w r/w in the fused kernel, w r/w in the final pass);
+                              # round 1 moved (3j+9) n s, the normalisation sweep is gone since round 2
+                              "actual_bytes_per_factorisation_per_gpu": actual_b, "actual_GBps_per_gpu": actual_gbs,
+                              "actual_frac_of_measured": actual_gbs / peak},
             "kernels": kernels,
             "cpu_baseline": cpu,
             "parity": parity,
+            "sync_profile": sync_profile,
             "clocks": clocks,
         }
         emit(line)

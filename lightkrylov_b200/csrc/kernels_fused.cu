@@ -258,6 +258,7 @@ k_axpy_dot(const __grid_constant__ CUtensorMap tmap, int j, int tp, int nst, int
         ktime_last(p2p, 1);
         if (p2p.world > 1) p2p_allreduce_cta<W>(p2p, out, jp);
         ktime_last(p2p, 2);
+        ktime_accumulate_wait(p2p, 1);
     }
 }
 

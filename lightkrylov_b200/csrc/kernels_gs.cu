@@ -188,6 +188,7 @@ k_multidot(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j,
         ktime_last(p2p, 1);
         if (p2p.world > 1) p2p_allreduce_cta<W>(p2p, out, jp);
         ktime_last(p2p, 2);
+        ktime_accumulate_wait(p2p, 0);
     }
 }
 

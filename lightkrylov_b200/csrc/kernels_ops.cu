@@ -294,6 +294,80 @@ k_stencil_smem(const typename Tr<K>::E* __restrict__ x, typename Tr<K>::E* __res
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// 3-D z-march (round 2; "3.5-D blocking").  One CTA = ZT_TX packs in x by ZT_TY rows in y, marching LZ planes in z
+// with the below / centre / above packs of its column in REGISTERS and the next plane prefetched one iteration
+// ahead.  The y-neighbours (rows j-1 / j+1 of the centre plane) are re-read through L1: the neighbouring threads
+// of the same CTA loaded exactly those lines one iteration earlier as their "above" pack.  Per point and plane the
+// kernel issues ONE load that can miss L1 -- against three in the y-marching kernel, whose z-neighbours belong to
+// other CTAs and are always served by L2 (ncu, 384^3 fp64: DRAM traffic already equal to the algorithmic 2 n s, but
+// 3.4 n s of L2->L1 traffic and 4.6 TB/s).  No shared memory, no block barrier (the shared-memory z-march of round 1
+// paid two barriers per plane: 2.8 TB/s).  Inter-GPU halo planes (k = -1, k = nz) come from halo_lo / halo_hi.
+// ------------------------------------------------------------------------------------------
+enum { ZT_TX = 32, ZT_TY = 8 };
+
+template <int K, int PW, int LZ>
+__global__ void __launch_bounds__(ZT_TX * ZT_TY)
+k_stencil3d_zmarch(const typename Tr<K>::E* __restrict__ x, typename Tr<K>::E* __restrict__ y,
+                   int64_t nx, int64_t ny, int64_t nz, Coef7<typename Tr<K>::E> cf,
+                   const typename Tr<K>::E* __restrict__ halo_lo, const typename Tr<K>::E* __restrict__ halo_hi,
+                   const unsigned* __restrict__ halo_epoch, int64_t halo_parity_stride, const unsigned* __restrict__ flag_lo,
+                   const unsigned* __restrict__ flag_hi, int64_t ncbx, int64_t ncby, const int* __restrict__ flags)
+{
+    using E = typename Tr<K>::E;
+    using PO = PackOps<E, PW>;
+    using P = typename PO::P;
+    if (flags && flags[F_STOP]) return;
+    if (halo_epoch) {
+        const int64_t off = (int64_t)(*halo_epoch & 1u) * halo_parity_stride;
+        if (halo_lo) halo_lo += off;
+        if (halo_hi) halo_hi += off;
+    }
+    const int64_t nzc = (nz + LZ - 1) / LZ;
+    const int64_t bid = blockIdx.x;
+    const int64_t cbx = bid % ncbx, cby = (bid / ncbx) % ncby;
+    const int64_t zc = ((bid / (ncbx * ncby)) + 1) % nzc;            // the chunks touching the inter-GPU halos run last
+    const int64_t k0 = zc * LZ, k1 = min(nz, k0 + LZ);
+    halo_wait(halo_epoch, flag_lo, flag_hi, halo_lo && k0 == 0, halo_hi && k1 == nz);
+    const int tx = threadIdx.x % ZT_TX, ty = threadIdx.x / ZT_TX;
+    const int64_t npk_row = nx / PW;
+    const int64_t ip = cbx * ZT_TX + tx;
+    const int64_t j = cby * ZT_TY + ty;
+    if (ip >= npk_row || j >= ny) return;
+    const int64_t i0 = ip * PW;
+    const int64_t plane = nx * ny;
+    const int64_t q = j * nx + i0;                                   // offset inside a plane
+    auto load_plane = [&](int64_t k) -> P {
+        if (k < 0) return halo_lo ? PO::ld_cg(halo_lo + q) : PO::zero();
+        if (k >= nz) return halo_hi ? PO::ld_cg(halo_hi + q) : PO::zero();
+        return PO::ld(x + k * plane + q);
+    };
+    P down = load_plane(k0 - 1), center = load_plane(k0), up = load_plane(k0 + 1);
+    for (int64_t k = k0; k < k1; ++k) {
+        const P nxt = (k + 2 <= k1) ? load_plane(k + 2) : PO::zero();          // prefetch: used two iterations later as `up`
+        const E* xc = x + k * plane + q;
+        const P north = (j + 1 < ny) ? PO::ld(xc + nx) : PO::zero();
+        const P south = (j > 0) ? PO::ld(xc - nx) : PO::zero();
+        const E west = i0 > 0 ? __ldg(xc - 1) : zero_v(E());
+        const E east = (i0 + PW < nx) ? __ldg(xc + PW) : zero_v(E());
+        P out;
+#pragma unroll
+        for (int e = 0; e < PW; ++e) {
+            E s = mul_v(cf.c[0], center.v[e]);
+            fmacc(s, (e > 0 ? center.v[e > 0 ? e - 1 : 0] : west), cf.c[1]);
+            fmacc(s, (e < PW - 1 ? center.v[e < PW - 1 ? e + 1 : 0] : east), cf.c[2]);
+            fmacc(s, south.v[e], cf.c[3]);
+            fmacc(s, north.v[e], cf.c[4]);
+            fmacc(s, down.v[e], cf.c[5]);
+            fmacc(s, up.v[e], cf.c[6]);
+            out.v[e] = s;
+        }
+        PO::st(y + k * plane + q, out);
+        down = center; center = up; up = nxt;
+    }
+}
+
 template <int K, int PW, int DIM>
 static void stencil_launch(cudaStream_t s, const StencilArgs& a, const void* x, void* y, bool trans, const int* flags) {
     using E = typename Tr<K>::E;
@@ -312,8 +386,18 @@ static void stencil_launch(cudaStream_t s, const StencilArgs& a, const void* x, 
     // the occupancy) vs register march 4.62 TB/s; a z-march with the plane staged in shared memory (two block
     // barriers per plane) reached only 2.8 TB/s and was dropped.  Default: shared-memory staging in 2-D,
     // register march in 3-D.
-    static const int variant = getenv("LKB_STENCIL_VARIANT") ? atoi(getenv("LKB_STENCIL_VARIANT")) : (DIM == 2 ? 1 : 0);
-    if (variant >= 1) {
+    static const int variant = getenv("LKB_STENCIL_VARIANT") ? atoi(getenv("LKB_STENCIL_VARIANT")) : (DIM == 2 ? 1 : 4);
+    if constexpr (DIM == 3) {
+        if (variant == 4) {      // z-march with register planes (default in 3-D since round 2)
+            constexpr int LZ = 32;
+            const int64_t ncbx = (npk_row + ZT_TX - 1) / ZT_TX, ncby = (a.ny + ZT_TY - 1) / ZT_TY, nzc = (a.nz + LZ - 1) / LZ;
+            const unsigned grid = (unsigned)(ncbx * ncby * nzc);
+            k_stencil3d_zmarch<K, PW, LZ><<<grid, ZT_TX * ZT_TY, 0, s>>>((const E*)x, (E*)y, a.nx, a.ny, a.nz, cf,
+                (const E*)a.halo_lo, (const E*)a.halo_hi, a.halo_epoch, a.halo_parity_stride, a.flag_lo, a.flag_hi, ncbx, ncby, flags);
+            return;
+        }
+    }
+    if (variant >= 1 && variant <= 3) {
         // shared-memory halo-staged kernel
 #define LKB_STS(RY_) { const int64_t nyb_ = (a.ny + RY_ - 1) / RY_; \
             const int64_t ncb_ = (npk_row + ST_TX - 1) / ST_TX; \

@@ -31,7 +31,7 @@ struct P2P {
     // [4*MAX_ROWBLOCKS + {0,1,2}] = {stage-2 start, stage-2 done, allreduce done} of the last CTA (%globaltimer ns)
     unsigned long long* dbg = nullptr;
 };
-enum { KT_WORDS = 4 * 1024 + 8 };
+enum { KT_WORDS = 4 * 1024 + 16 };
 static inline size_t p2p_region_bytes() { return (size_t)P2P_FLAG_BYTES + 2 * (size_t)P2P_MAXW * P2P_SLOT * 16; }
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: set it once for every device a kernel is

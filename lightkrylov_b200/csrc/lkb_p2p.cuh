@@ -5,7 +5,8 @@
 // a separate ncclAllReduce launch (~20 us) by a few NVLink round trips inside the same kernel.
 // Result is bitwise identical on every rank (fixed rank order) and run-to-run deterministic.
 // Two data buffers alternate by epoch parity: a rank can run at most one collective ahead of the
-// slowest peer, because completing epoch e+1 requires every peer's contribution to e+1.
+// slowest peer, because completing epoch e+1 requires every peer's contribution to e+1 (which that peer sends
+// only after it has finished reading epoch e).
 #pragma once
 #include "lkb_kernels.h"
 
@@ -22,6 +23,16 @@ LKB_DI void ktime_cta(const P2P& c, int slot) {
 }
 LKB_DI void ktime_last(const P2P& c, int slot) {
     if (c.dbg && threadIdx.x == 0) c.dbg[(size_t)4 * MAX_ROWBLOCKS + slot] = gtimer_ns();
+}
+// running totals over all launches since lkb_debug_ktime(enable): words [4096 + 8 + 2*cls] += allreduce time (ns),
+// [.. + 1] += 1, cls 0 = k_multidot, 1 = k_axpy_dot (how long the last CTA spent in the cross-GPU exchange, i.e.
+// NVLink latency + waiting for the slowest rank)
+LKB_DI void ktime_accumulate_wait(const P2P& c, int cls) {
+    if (c.dbg && threadIdx.x == 0) {
+        unsigned long long* t = c.dbg + (size_t)4 * MAX_ROWBLOCKS;
+        t[8 + 2 * cls] += t[2] - t[1];
+        t[9 + 2 * cls] += 1ULL;
+    }
 }
 LKB_DI unsigned ld_volatile_u32(const unsigned* p) {
     unsigned v;
@@ -45,60 +56,72 @@ LKB_DI double2 ld_cv_w(const double2* p) {
     return v;
 }
 
-// Called by ALL threads of one CTA.  vals[0..count) (global, W type) holds this rank's sums on
-// entry and the world total on exit.  count <= P2P_SLOT.
-template <typename W>
-LKB_DI void p2p_allreduce_chunk(const P2P& c, W* vals, int count);
-
-// count may exceed the slot size (j + 1 > P2P_SLOT coefficients): processed in slot-sized rounds, one
-// epoch each, identically on every rank.
-template <typename W>
-LKB_DI void p2p_allreduce_cta(const P2P& c, W* vals, int count) {
-    for (int base = 0; base < count; base += P2P_SLOT)
-        p2p_allreduce_chunk<W>(c, vals + base, min((int)P2P_SLOT, count - base));
+// p2p_allreduce_cta: called by ALL threads of one CTA.  vals[0..count) (global, W type) holds this rank's sums on entry
+// and the world total on exit (bitwise identical on every rank: fixed rank order).
+// Low-latency protocol (round 2): every 16-byte word carries its own arrival tags, so a receiver spins on the words
+// themselves.  No __threadfence_system + separate flag store: one one-way NVLink latency per collective instead of a
+// fence round trip plus a flag hop.  This is NCCL's "LL" layout: each 8-byte half of the word is {32 bits of the
+// double, 32-bit epoch tag} and is valid on its own, so nothing depends on the two halves of the 128-bit store
+// becoming visible together (8-byte accesses are single-copy atomic).  Complex coefficients take two words.
+// Slots alternate by epoch parity; a stale word of the same parity carries tag epoch - 2.
+LKB_DI void st_ll(double2* p, double v, unsigned ep) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    const unsigned long long tag = (unsigned long long)ep << 32;
+    const unsigned long long lo = (bits & 0xffffffffULL) | tag, hi = (bits >> 32) | tag;
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(lo), "l"(hi) : "memory");
+}
+LKB_DI double ld_ll(const double2* p, unsigned ep) {
+    unsigned long long lo, hi;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(p) : "memory");
+        if ((unsigned)(lo >> 32) == ep && (unsigned)(hi >> 32) == ep) break;
+        if (clock64() - t0 > 60000000000LL) { asm volatile("trap;"); }       // a peer died: fail instead of hanging the GPU
+    }
+    return __longlong_as_double((long long)((lo & 0xffffffffULL) | (hi << 32)));
 }
 
 template <typename W>
 LKB_DI void p2p_allreduce_chunk(const P2P& c, W* vals, int count) {
     __shared__ unsigned s_epoch;
+    constexpr int WPV = sizeof(W) / 8;                  // 16-byte words per value: 1 (real) or 2 (re, im)
     const int tid = threadIdx.x, nth = blockDim.x;
     if (tid == 0) s_epoch = *c.epoch + 1u;
     __syncthreads();
     const unsigned ep = s_epoch;
     const int buf = (int)(ep & 1u);
     const size_t slot_bytes = (size_t)P2P_SLOT * 16;
-    // 1. push my values into slot [buf][my rank] of every rank (16-byte words; real kinds use .x)
-    for (int i = tid; i < count; i += nth) {
-        double2 v = make_double2(0.0, 0.0);
-        if constexpr (sizeof(W) == 16) v = *reinterpret_cast<const double2*>(&vals[i]);
-        else v.x = *reinterpret_cast<const double*>(&vals[i]);
+    const int nwords = count * WPV;
+    const double* src = reinterpret_cast<const double*>(vals);
+    // 1. push {value, epoch} words into slot [buf][my rank] of every rank
+    for (int i = tid; i < nwords; i += nth) {
+        const double v = src[i];
         for (int r = 0; r < c.world; ++r) {
             double2* dst = reinterpret_cast<double2*>(c.peer[r] + P2P_FLAG_BYTES + ((size_t)buf * P2P_MAXW + c.rank) * slot_bytes);
-            dst[i] = v;
+            st_ll(dst + i, v, ep);
         }
     }
-    __threadfence_system();
-    __syncthreads();
-    // 2. raise my flag in every rank, 3. wait for every rank's flag in my region
-    if (tid < c.world) st_volatile_u32(reinterpret_cast<unsigned*>(c.peer[tid] + (size_t)c.rank * 128), ep);
-    if (tid < c.world) {
-        spin_until(reinterpret_cast<const unsigned*>(c.peer[c.rank] + (size_t)tid * 128), ep);
-    }
-    __syncthreads();
-    __threadfence_system();
-    // 4. fixed rank-order sum of the world slots
-    for (int i = tid; i < count; i += nth) {
-        double2 a = make_double2(0.0, 0.0);
+    // 2. every word of every rank's slot in MY region: spin until its tag is this epoch, sum in rank order
+    double* out = reinterpret_cast<double*>(vals);
+    for (int i = tid; i < nwords; i += nth) {
+        double a = 0.0;
         for (int r = 0; r < c.world; ++r) {
-            const double2* src = reinterpret_cast<const double2*>(c.peer[c.rank] + P2P_FLAG_BYTES + ((size_t)buf * P2P_MAXW + r) * slot_bytes);
-            const double2 v = ld_cv_w(src + i);
-            a.x += v.x; a.y += v.y;
+            const double2* s = reinterpret_cast<const double2*>(c.peer[c.rank] + P2P_FLAG_BYTES + ((size_t)buf * P2P_MAXW + r) * slot_bytes);
+            a += ld_ll(s + i, ep);
         }
-        if constexpr (sizeof(W) == 16) *reinterpret_cast<double2*>(&vals[i]) = a;
-        else *reinterpret_cast<double*>(&vals[i]) = a.x;
+        out[i] = a;
     }
+    __syncthreads();
     if (tid == 0) *c.epoch = ep;
     __syncthreads();                     // s_epoch may be rewritten by the next round
+}
+
+// count may exceed the slot size: processed in slot-sized rounds, one epoch each, identically on every rank.
+template <typename W>
+LKB_DI void p2p_allreduce_cta(const P2P& c, W* vals, int count) {
+    constexpr int PER = P2P_SLOT / (int)(sizeof(W) / 8);
+    for (int base = 0; base < count; base += PER)
+        p2p_allreduce_chunk<W>(c, vals + base, min(PER, count - base));
 }
 
 }  // namespace lkb

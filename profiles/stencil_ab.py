@@ -22,6 +22,6 @@ if len(sys.argv) > 1:
         out[name] = (round(us, 1), round(2 * n * 8 / us / 1e3))
     print(sys.argv[1], out)
 else:
-    for v in range(4):
+    for v in range(5):
         env = dict(os.environ, LKB_STENCIL_VARIANT=str(v))
         subprocess.run([sys.executable, __file__, str(v)], env=env)
