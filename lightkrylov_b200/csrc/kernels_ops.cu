@@ -560,6 +560,63 @@ void launch_csr(int kind, cudaStream_t s, int64_t m, const int64_t* rowptr, cons
 }
 
 // ------------------------------------------------------------------------------------------
+// L2-blocked CSR SpMV (layout: lkb_csr.cu).  One launch per column block; thread-per-row (a row has ~nnz/nb entries
+// in a block: 1-3 for C5), consecutive threads read consecutive table entries and nearly consecutive values.
+// The x gathers of a block all fall into one L2-resident slice; they carry an L2 evict_last policy while the
+// streamed operands (table, col, val, y) are marked evict_first so that they do not push the slice out.
+LKB_DI uint64_t l2_policy_evict_last() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
+LKB_DI uint64_t l2_policy_evict_first() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+template <typename T> LKB_DI T ld_hint(const T* p, uint64_t pol);
+template <> LKB_DI float ld_hint<float>(const float* p, uint64_t pol) {
+    float v; asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol)); return v; }
+template <> LKB_DI double ld_hint<double>(const double* p, uint64_t pol) {
+    double v; asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol)); return v; }
+template <> LKB_DI float2 ld_hint<float2>(const float2* p, uint64_t pol) {
+    float2 v; asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol)); return v; }
+template <> LKB_DI double2 ld_hint<double2>(const double2* p, uint64_t pol) {
+    double2 v; asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol)); return v; }
+template <> LKB_DI int32_t ld_hint<int32_t>(const int32_t* p, uint64_t pol) {
+    int32_t v; asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol)); return v; }
+template <> LKB_DI uint32_t ld_hint<uint32_t>(const uint32_t* p, uint64_t pol) {
+    uint32_t v; asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol)); return v; }
+
+template <int K>
+__global__ void __launch_bounds__(256)
+k_csr_blocked(int64_t rows, const uint32_t* __restrict__ tab, const int32_t* __restrict__ col,
+              const typename Tr<K>::E* __restrict__ val, const typename Tr<K>::E* __restrict__ x,
+              typename Tr<K>::E* __restrict__ y, bool conj_vals, bool first, const int* __restrict__ flags)
+{
+    using E = typename Tr<K>::E;
+    if (flags && flags[F_STOP]) return;
+    const uint64_t keep = l2_policy_evict_last(), stream = l2_policy_evict_first();
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t q0 = ld_hint<uint32_t>(tab + r, stream), q1 = ld_hint<uint32_t>(tab + r + 1, stream);
+        if (q0 == q1 && !first) continue;                       // nothing in this block for row r
+        E acc = first ? zero_v(E()) : y[r];
+        for (uint32_t q = q0; q < q1; ++q) {
+            E a = ld_hint<E>(val + q, stream);
+            if (conj_vals) a = conj_v(a);
+            fmacc(acc, a, ld_hint<E>(x + ld_hint<int32_t>(col + q, stream), keep));
+        }
+        y[r] = acc;
+    }
+}
+void launch_csr_blocked(int kind, cudaStream_t s, const CsrBlocked& b, const void* x, void* y, bool conj_vals, const int* flags, int sms) {
+    int64_t nb = (b.rows + 255) / 256;
+    if (nb < 1) nb = 1;
+    if (nb > (int64_t)sms * 16) nb = (int64_t)sms * 16;
+    for (int blk = 0; blk < b.nb; ++blk) {
+        const uint32_t* tab = b.tab + (size_t)blk * (b.rows + 1);
+        switch (kind) {
+            case KS: k_csr_blocked<KS><<<(int)nb, 256, 0, s>>>(b.rows, tab, b.col, (const float*)b.val, (const float*)x, (float*)y, conj_vals, blk == 0, flags); break;
+            case KD: k_csr_blocked<KD><<<(int)nb, 256, 0, s>>>(b.rows, tab, b.col, (const double*)b.val, (const double*)x, (double*)y, conj_vals, blk == 0, flags); break;
+            case KC: k_csr_blocked<KC><<<(int)nb, 256, 0, s>>>(b.rows, tab, b.col, (const float2*)b.val, (const float2*)x, (float2*)y, conj_vals, blk == 0, flags); break;
+            default: k_csr_blocked<KZ><<<(int)nb, 256, 0, s>>>(b.rows, tab, b.col, (const double2*)b.val, (const double2*)x, (double2*)y, conj_vals, blk == 0, flags); break;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // dense_linop (AbstractLinops.fypp:608-671, gemv): only the n = 128 plumbing config uses it.
 template <int K>
 __global__ void k_dense(int64_t m, int64_t n, const typename Tr<K>::E* __restrict__ a,

@@ -326,6 +326,8 @@ int lkb_set_option(lkb_ctx_t c, const char* name, int value) {
     else if (!strcmp(name, "fused")) c->fused = value != 0;
     else if (!strcmp(name, "fin")) c->fin = value != 0;
     else if (!strcmp(name, "write_intermediate")) c->write_intermediate = value != 0;
+    else if (!strcmp(name, "csr_slice_kb")) c->csr_slice_kb = value;            // 0 disables the L2 blocking
+    else if (!strcmp(name, "csr_block_min_kb")) c->csr_block_min_kb = value;
     else if (!strcmp(name, "fused_halo")) c->fused_halo = value != 0;
     else if (!strcmp(name, "p2p")) c->p2p_active = (value != 0) && c->p2p.world > 1;
     else { set_error("unknown option %s", name); return LKB_ERR_ARG; }
@@ -750,7 +752,8 @@ int lkb_op_destroy(lkb_op_t A) {
     if (A->hp_lo_map) cudaIpcCloseMemHandle(A->hp_lo_map);
     if (A->hp_hi_map) cudaIpcCloseMemHandle(A->hp_hi_map);
     if (A->hp_active) { cudaFree(A->hp.my_region); cudaFree(A->hp.epoch); }
-    void* bufs[] = { A->halo_lo, A->halo_hi, A->rowptr, A->col, A->val, A->t_rowptr, A->t_col, A->t_val, A->a, A->x_full, A->y_full, A->y_red };
+    void* bufs[] = { A->halo_lo, A->halo_hi, A->rowptr, A->col, A->val, A->t_rowptr, A->t_col, A->t_val, A->a, A->x_full, A->y_full, A->y_red,
+                     A->blk.tab, A->blk.col, A->blk.val, A->t_blk.tab, A->t_blk.col, A->t_blk.val };
     for (void* b : bufs) if (b) cudaFree(b);
     delete A;
     return 0;
@@ -835,8 +838,13 @@ int op_apply_enqueue(lkb_op_s* A, const void* x, void* y, bool trans, const int*
             }
         }
     } else if (A->type == 3) {
-        if (!trans) launch_csr(A->kind, c->stream, A->m, A->rowptr, A->col, A->val, x, y, false, flags, c->sms | (A->lpr << 16));
-        else launch_csr(A->kind, c->stream, A->n, A->t_rowptr, A->t_col, A->t_val, x, y, true, flags, c->sms | (A->t_lpr << 16));
+        if (!trans) {
+            if (A->blk.nb > 0) { launch_csr_blocked(A->kind, c->stream, A->blk, x, y, false, flags, c->sms); nl = A->blk.nb; }
+            else launch_csr(A->kind, c->stream, A->m, A->rowptr, A->col, A->val, x, y, false, flags, c->sms | (A->lpr << 16));
+        } else {
+            if (A->t_blk.nb > 0) { launch_csr_blocked(A->kind, c->stream, A->t_blk, x, y, true, flags, c->sms); nl = A->t_blk.nb; }
+            else launch_csr(A->kind, c->stream, A->n, A->t_rowptr, A->t_col, A->t_val, x, y, true, flags, c->sms | (A->t_lpr << 16));
+        }
     } else if (A->type == 0) {
         launch_dense(A->kind, c->stream, A->m, A->n, A->a, x, y, trans, flags);
     } else {

@@ -10,6 +10,7 @@
 // summation order of A^H u -- and hence the result -- is a fixed function of the matrix, identical to the host
 // counting sort of round 1.  1.6e9 nnz (C5 at BASELINE size) transpose in well under a second; the round-1 host
 // build needed minutes and ~70 GB of host memory.
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <cub/device/device_radix_sort.cuh>
@@ -101,6 +102,49 @@ __global__ void k_csr_random(int64_t m_local, int64_t row0, int64_t n, int per_r
     }
 }
 
+// ---- L2-blocked layout (column blocks) ---------------------------------------------------------------------
+// A random sparse matrix gathers x with no locality: once x no longer fits in L2 every gather is a DRAM sector
+// (and a TLB miss).  Measured on C5 at BASELINE size (x = 640 MB): 0.97 TB/s algorithmic for matvec, against
+// 2.85 TB/s at 1/10 scale where x (64 MB) still half-fits.  The remedy is the classic one: cut the COLUMN space
+// into blocks whose slice of x stays L2 resident (default 48 MB, LKB_CSR_SLICE_MB) and sweep the matrix block by
+// block; y is accumulated across the blocks (read-modify-write per block, the price of the blocking).
+// Layout: the non-zeros stably sorted by column block (one 1-pass CUB radix sort on a <= 8-bit key), so inside a
+// block they are still ordered by row and by their original position in the row; tab[b * (rows + 1) + r] is the
+// position of the first entry of (block b, row r) -- a per-block CSR row pointer into the blocked arrays.
+// The summation order of every row is a fixed function of the matrix => deterministic, no atomics.
+__global__ void k_blk_keys(int64_t nnz, int64_t cw, const int32_t* __restrict__ col, uint8_t* __restrict__ keys, uint32_t* __restrict__ iota) {
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nnz; q += (int64_t)gridDim.x * blockDim.x) {
+        keys[q] = (uint8_t)((int64_t)col[q] / cw);
+        iota[q] = (uint32_t)q;
+    }
+}
+template <typename E>
+__global__ void k_blk_gather(int64_t nnz, int64_t rows, const int64_t* __restrict__ rowptr, const uint32_t* __restrict__ perm,
+                             const int32_t* __restrict__ col, const E* __restrict__ val, int32_t* __restrict__ bcol,
+                             E* __restrict__ bval, uint32_t* __restrict__ brow) {
+    for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < nnz; d += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t q = (int64_t)perm[d];
+        int64_t lo = 0, hi = rows;                    // largest i with rowptr[i] <= q
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (rowptr[mid] <= q) lo = mid; else hi = mid;
+        }
+        brow[d] = (uint32_t)lo;
+        bcol[d] = col[q];
+        bval[d] = val[q];
+    }
+}
+// tab[key] = first position whose (block, row) key is >= key, key = block * (rows + 1) + row
+__global__ void k_blk_table(int64_t nnz, int64_t rows, int nb, const uint8_t* __restrict__ bkey, const uint32_t* __restrict__ brow,
+                            uint32_t* __restrict__ tab) {
+    const int64_t nkeys = (int64_t)nb * (rows + 1);
+    for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d <= nnz; d += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t prev = d == 0 ? -1 : (int64_t)bkey[d - 1] * (rows + 1) + (int64_t)brow[d - 1];
+        const int64_t cur = d == nnz ? nkeys - 1 : (int64_t)bkey[d] * (rows + 1) + (int64_t)brow[d];
+        for (int64_t key = prev + 1; key <= cur; ++key) tab[key] = (uint32_t)d;
+    }
+}
+
 int grid_for(int64_t n, int sms) {
     int64_t nb = (n + 255) / 256;
     if (nb < 1) nb = 1;
@@ -116,6 +160,8 @@ int pick_lpr(int64_t nnz, int64_t rows) {
 }  // namespace
 
 namespace lkb {
+
+int csr_block_device(lkb_ctx_s* c, int kind, int64_t rows, int64_t ncols, int64_t** rowptr, int32_t** col, void** val, CsrBlocked* blk);
 
 // Validate (rowptr, col) ON THE DEVICE and build the explicit transpose.  `rows` = local rows, `ncols_index` =
 // size of the column index space (global n for a row-sharded operator).  op->rowptr / col / val must already
@@ -174,6 +220,74 @@ int csr_finish_device(lkb_ctx_s* c, lkb_op_s* op, int kind, int64_t rows, int64_
     CSR_CUDA(cudaStreamSynchronize(c->stream));
 #undef CSR_CUDA
     free_tmp();
+    if (!op->dist) {
+        // L2 blocking of both orientations when the gathered vector exceeds L2 (no-op otherwise)
+        LKB_TRY(csr_block_device(c, kind, rows, ncols_index, &op->rowptr, &op->col, &op->val, &op->blk));
+        LKB_TRY(csr_block_device(c, kind, ncols_index, rows, &op->t_rowptr, &op->t_col, &op->t_val, &op->t_blk));
+    }
+    return 0;
+}
+
+// Build the L2-blocked copy of a CSR matrix (rows x ncols) when the gathered vector is too large for L2; the plain
+// arrays are released afterwards (`*rowptr / *col / *val` become null).  blk.nb == 0 afterwards: not blocked.
+int csr_block_device(lkb_ctx_s* c, int kind, int64_t rows, int64_t ncols, int64_t** rowptr, int32_t** col, void** val, CsrBlocked* blk) {
+    blk->nb = 0;
+    const size_t es = kind_size(kind);
+    // slice / threshold: lkb_set_option(ctx, "csr_slice_kb" | "csr_block_min_kb", v); defaults 48 MB / 96 MB
+    const int64_t slice_b = (int64_t)c->csr_slice_kb * 1024, min_b = (int64_t)c->csr_block_min_kb * 1024;
+    if (slice_b <= 0 || (int64_t)ncols * (int64_t)es < min_b) return 0;                 // x (nearly) fits in L2: plain CSR
+    int64_t nnz = 0;
+    LKB_CUDA(cudaMemcpy(&nnz, *rowptr + rows, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    if (nnz < 1) return 0;
+    int64_t cw = (slice_b / (int64_t)es + 1023) / 1024 * 1024;
+    int nb = (int)((ncols + cw - 1) / cw);
+    if (nb > 255) { nb = 255; cw = ((ncols + nb - 1) / nb + 1023) / 1024 * 1024; nb = (int)((ncols + cw - 1) / cw); }
+    if (nb < 2) return 0;
+    if ((int64_t)nb * (rows + 1) >= (int64_t)1 << 40) return 0;
+    uint8_t *keys = nullptr, *keys_out = nullptr; uint32_t *iota = nullptr, *perm = nullptr, *brow = nullptr; void* tmp = nullptr;
+    int32_t* bcol = nullptr; void* bval = nullptr; uint32_t* tab = nullptr;
+    auto free_tmp = [&]() { for (void* p : {(void*)keys, (void*)keys_out, (void*)iota, (void*)perm, (void*)brow, tmp}) if (p) cudaFree(p); };
+    // a failure here (in practice: not enough memory for the second copy) is not fatal: the plain CSR arrays are only
+    // released after everything else succeeded, so the operator simply stays unblocked
+    auto fail = [&](const char*, cudaError_t) {
+        free_tmp(); if (bcol) cudaFree(bcol); if (bval) cudaFree(bval); if (tab) cudaFree(tab);
+        cudaGetLastError();
+        return 0;
+    };
+#define BLK_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(#call, e_); } while (0)
+    BLK_CUDA(cudaMalloc((void**)&keys, nnz)); BLK_CUDA(cudaMalloc((void**)&keys_out, nnz));
+    BLK_CUDA(cudaMalloc((void**)&iota, nnz * sizeof(uint32_t))); BLK_CUDA(cudaMalloc((void**)&perm, nnz * sizeof(uint32_t)));
+    k_blk_keys<<<grid_for(nnz, c->sms), 256, 0, c->stream>>>(nnz, cw, *col, keys, iota);
+    int end_bit = 1; while ((1 << end_bit) < nb) ++end_bit;
+    size_t tmp_bytes = 0;
+    BLK_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_out, iota, perm, nnz, 0, end_bit, c->stream));
+    BLK_CUDA(cudaMalloc(&tmp, std::max<size_t>(tmp_bytes, 16)));
+    BLK_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_out, iota, perm, nnz, 0, end_bit, c->stream));
+    BLK_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(keys); keys = nullptr; cudaFree(iota); iota = nullptr; cudaFree(tmp); tmp = nullptr;
+    BLK_CUDA(cudaMalloc((void**)&brow, nnz * sizeof(uint32_t)));
+    BLK_CUDA(cudaMalloc((void**)&bcol, nnz * sizeof(int32_t)));
+    BLK_CUDA(cudaMalloc(&bval, nnz * es));
+    const int g = grid_for(nnz, c->sms);
+    switch (kind) {
+        case KS: k_blk_gather<float><<<g, 256, 0, c->stream>>>(nnz, rows, *rowptr, perm, *col, (const float*)*val, bcol, (float*)bval, brow); break;
+        case KD: k_blk_gather<double><<<g, 256, 0, c->stream>>>(nnz, rows, *rowptr, perm, *col, (const double*)*val, bcol, (double*)bval, brow); break;
+        case KC: k_blk_gather<float2><<<g, 256, 0, c->stream>>>(nnz, rows, *rowptr, perm, *col, (const float2*)*val, bcol, (float2*)bval, brow); break;
+        default: k_blk_gather<double2><<<g, 256, 0, c->stream>>>(nnz, rows, *rowptr, perm, *col, (const double2*)*val, bcol, (double2*)bval, brow); break;
+    }
+    BLK_CUDA(cudaGetLastError());
+    BLK_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(perm); perm = nullptr;
+    BLK_CUDA(cudaMalloc((void**)&tab, (size_t)nb * (rows + 1) * sizeof(uint32_t)));
+    k_blk_table<<<grid_for(nnz + 1, c->sms), 256, 0, c->stream>>>(nnz, rows, nb, keys_out, brow, tab);
+    BLK_CUDA(cudaGetLastError());
+    BLK_CUDA(cudaStreamSynchronize(c->stream));
+#undef BLK_CUDA
+    free_tmp();
+    // the blocked copy replaces the plain arrays
+    cudaFree(*rowptr); cudaFree(*col); cudaFree(*val);
+    *rowptr = nullptr; *col = nullptr; *val = nullptr;
+    blk->nb = nb; blk->cw = cw; blk->rows = rows; blk->nnz = nnz; blk->tab = tab; blk->col = bcol; blk->val = bval;
     return 0;
 }
 

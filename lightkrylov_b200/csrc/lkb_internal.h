@@ -55,6 +55,7 @@ struct lkb_ctx_s {
     bool graphs = true;
     bool fused = true;
     bool fin = true;            // final CGS2 pass fused with normalisation + column update (k_multiaxpy_fin)
+    int csr_slice_kb = 48 * 1024, csr_block_min_kb = 96 * 1024;   // L2 blocking of CSR operators (lkb_csr.cu)
     bool write_intermediate = false;   // eigs / eighs / svds rewrite <solver>_output.txt every step (rank 0)
     bool fused_halo = true;     // P2P halo push fused into the kernel that finishes the next matvec input
     // in-kernel NVLink allreduce (CUDA IPC peer buffers); falls back to NCCL when not attached
@@ -91,6 +92,7 @@ struct lkb_op_s {
     // csr (+ explicit transpose for rmatvec)
     int64_t* rowptr = nullptr; int32_t* col = nullptr; void* val = nullptr; int lpr = 8;
     int64_t* t_rowptr = nullptr; int32_t* t_col = nullptr; void* t_val = nullptr; int t_lpr = 8;
+    lkb::CsrBlocked blk, t_blk;                   // L2-blocked layouts (nb > 0: they replace the plain arrays above)
     // row-sharded csr: full-length gather / scatter buffers and every rank's (offset, count) of the column and row spaces
     bool dist = false; int64_t m_global = 0, n_global = 0;
     void* x_full = nullptr; void* y_full = nullptr; void* y_red = nullptr;

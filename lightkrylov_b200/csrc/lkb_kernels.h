@@ -134,6 +134,13 @@ void launch_wadd(int kind, cudaStream_t s, const void* a, const void* b, void* o
 // dst (E type) = src (W type) narrowed, length n
 void launch_narrow(int kind, cudaStream_t s, const void* src, void* dst, int n, const int* flags);
 
+// L2-blocked CSR (lkb_csr.cu): non-zeros sorted by column block; tab[b * (rows + 1) + r] = first entry of (block b, row r)
+struct CsrBlocked {
+    int nb = 0; int64_t cw = 0, rows = 0, nnz = 0;
+    uint32_t* tab = nullptr; int32_t* col = nullptr; void* val = nullptr;
+};
+// y = A x over the blocked layout: one sweep per column block, y accumulated across the blocks
+void launch_csr_blocked(int kind, cudaStream_t s, const CsrBlocked& b, const void* x, void* y, bool conj_vals, const int* flags, int sms);
 void launch_stencil(int kind, cudaStream_t s, const StencilArgs& a, const void* x, void* y, bool trans,
                     const int* flags, int sms);
 // CSR SpMV y = A x (vector-per-row); conj_vals: use conj(A) values (for the explicit-transpose rmatvec)

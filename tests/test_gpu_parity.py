@@ -816,3 +816,40 @@ def test_basis_level_helpers(lk, ctx, oracle, kind):
     Q0 = X0h.copy(order="F"); oracle.qr(Q0)
     Kg = K.get()
     assert rel_normwise(Kg[:, :2], Q0) < tol_for(kind) and not Kg[:, 2:].any()
+
+
+@pytest.mark.parametrize("kind", ["z", "d", "s"])
+def test_csr_l2_blocked_layout_matches_plain(lk, ctx, oracle, kind):
+    """The L2-blocked CSR layout (column blocks, used when the gathered vector exceeds L2: C5 at BASELINE size) forced on a
+    small matrix: matvec / rmatvec agree with the oracle and with the plain layout, run-to-run bitwise, and a
+    bidiagonalization through it matches the oracle at 1e-10."""
+    dt = lk.DTYPES[kind]; m, n, pr = 9001, 7003, 12
+    rp, ci, va = oracle.csr_random(kind, m, n, pr, 46)
+    Ao = oracle.Op.csr(m, n, rp, ci, va)
+    xh = oracle.fill(n, kind, "normal", 3); uh = oracle.fill(m, kind, "normal", 4)
+    x = lk.Vector(ctx, kind, n).put(xh); u = lk.Vector(ctx, kind, m).put(uh)
+    res = {}
+    for blocked in (1, 0):
+        ctx.set_option("csr_slice_kb", 8 if blocked else 0)          # 8 KB slices: 512-2048 columns per block
+        ctx.set_option("csr_block_min_kb", 0)
+        A = lk.LinOp.csr(ctx, m, n, rp, ci, va)
+        y = lk.Vector(ctx, kind, m).put(np.full(m, np.nan, dtype=dt)); v = lk.Vector(ctx, kind, n).put(np.full(n, np.nan, dtype=dt))
+        A.matvec(x, y); A.rmatvec(u, v)
+        res[blocked] = (y.get(), v.get())
+        if blocked:
+            y2 = lk.Vector(ctx, kind, m); A.matvec(x, y2)
+            assert np.array_equal(y2.get(), res[1][0])                  # deterministic
+            kd = 12
+            U = lk.Basis(ctx, kind, m, kd + 1); V = lk.Basis(ctx, kind, n, kd + 1)
+            u0 = U.col(0).fill_random("normal", 47); u0.scal(1.0 / u0.norm())
+            B = np.zeros((kd + 1, kd), dtype=dt, order="F")
+            assert lk.bidiagonalization(A, U, V, B) == 0
+            Uo = np.zeros((m, kd + 1), dtype=dt, order="F"); Uo[:, 0] = oracle.fill(m, kind, "normal", 47); oracle.normalize(Uo[:, 0])
+            Vo = np.zeros((n, kd + 1), dtype=dt, order="F"); Bo = np.zeros_like(B)
+            assert oracle.bidiag(Ao, Uo, Vo, Bo) == 0
+            assert rel_normwise(B, Bo) < tol_for(kind)
+    ctx.set_option("csr_slice_kb", 48 * 1024); ctx.set_option("csr_block_min_kb", 96 * 1024)
+    tol = dict(rtol=1e-4, atol=1e-4) if kind == "s" else dict(rtol=1e-11, atol=1e-11)
+    for blocked in (1, 0):
+        np.testing.assert_allclose(res[blocked][0], Ao.apply(xh), **tol)
+        np.testing.assert_allclose(res[blocked][1], Ao.apply(uh, trans=True), **tol)
