@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "csrc", "liblkb.so")
+# LKB_SO: an alternative build of the SAME library for kernel A/B experiments (profiles/*.sh); never a different backend
+SO_PATH = os.environ.get("LKB_SO") or os.path.join(_HERE, "csrc", "liblkb.so")
 _lib = None
 
 

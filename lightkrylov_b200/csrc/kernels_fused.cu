@@ -92,7 +92,6 @@ k_axpy_dot(const __grid_constant__ CUtensorMap tmap, int j, int tp, int nst, int
     using W = typename Tr<K>::W;
     constexpr int EPP = Tr<K>::EPP;
     using P = Pack<E, EPP>;
-    if (flags && flags[F_STOP]) return;
 
     extern __shared__ __align__(1024) unsigned char smem[];
     const int jp = j + 1;
@@ -127,8 +126,51 @@ k_axpy_dot(const __grid_constant__ CUtensorMap tmap, int j, int tp, int nst, int
     const bool worker = wv < nchunk * rs;
     const int q = worker ? wv % nchunk : 0;
     const int slice = worker ? wv / nchunk : 0;
-    // this warp's 16 coefficients of pass 1 and its 16 accumulators of pass 2
     E c1r[FZ_CB], acc[FZ_CB];
+#pragma unroll
+    for (int i = 0; i < FZ_CB; ++i) { c1r[i] = zero_v(E()); acc[i] = zero_v(E()); }
+    double wwacc = 0.0;
+
+    if (wv == FZ_NW) {
+        // ---- producer warp: one elected lane streams tiles through the ring (one 2-D TMA box of
+        // tp packs x jc columns plus one 1-D bulk copy of the w packs per tile) ----
+        // The first ring-full of tiles is issued BEFORE griddepcontrol.wait: V(:, 0:j) is not written by anyone in
+        // this step and w was completed by the predecessor's predecessor (the matvec; the predecessor -- the pass-1
+        // multi-dot -- only reads it), see lkb_types.cuh.  With a programmatic launch the ring (~200 KB per SM)
+        // therefore fills while the multi-dot's last CTAs, its reduction tree and its NVLink allreduce still run.
+        auto issue = [&](int it) {
+            const int s = it % nst;
+            const uint32_t bar = smem_u32(&bars[s]);
+            const int64_t pk0 = (t0 + it) * tp;
+            const uint32_t wbytes = (uint32_t)min((int64_t)tp, npk - pk0) * 16u;
+            mbar_expect_tx(bar, stage_bytes + wbytes);
+            tma_load_2d(smem_u32(smem + (size_t)s * stage_bytes), &tmap, (int)pk0 * elt_per_pack, 0, bar);
+            bulk_load_1d(smem_u32(wst + (size_t)s * tp), w + pk0 * EPP, wbytes, bar);
+        };
+        const int pre = min(nmine, nst);
+        if (lane == 0)
+            for (int it = 0; it < pre; ++it) issue(it);
+        pdl_wait();
+        pdl_trigger();
+        const bool stop = flags && flags[F_STOP];
+        if (lane == 0) {
+            if (stop) {
+                // breakdown raised by an earlier step: nobody consumes the tiles, but a CTA must not retire with
+                // bulk copies in flight
+                for (int it = 0; it < pre; ++it) mbar_wait(smem_u32(&bars[it]), 0u);
+            } else {
+                for (int it = pre; it < nmine; ++it) {
+                    mbar_wait(smem_u32(&ebars[it % nst]), (uint32_t)((it / nst - 1) & 1));
+                    issue(it);
+                }
+            }
+        }
+        if (stop) return;
+    } else {
+    pdl_wait();                                  // c1 and the stop flag come from the predecessor
+    pdl_trigger();
+    if (flags && flags[F_STOP]) return;
+    // this warp's 16 coefficients of pass 1 and its 16 accumulators of pass 2
 #pragma unroll
     for (int i = 0; i < FZ_CB; ++i) {
         const int col = q * FZ_CB + i;
@@ -136,25 +178,6 @@ k_axpy_dot(const __grid_constant__ CUtensorMap tmap, int j, int tp, int nst, int
         if (col < j) narrow(c1[col], c1r[i]);
         acc[i] = zero_v(E());
     }
-    double wwacc = 0.0;
-
-    if (wv == FZ_NW) {
-        // ---- producer warp: one elected lane streams tiles through the ring (one 2-D TMA box of
-        // tp packs x jc columns plus one 1-D bulk copy of the w packs per tile) ----
-        if (lane == 0) {
-            for (int it = 0; it < nmine; ++it) {
-                const int s = it % nst;
-                const int use = it / nst;
-                if (use > 0) mbar_wait(smem_u32(&ebars[s]), (uint32_t)((use - 1) & 1));
-                const uint32_t bar = smem_u32(&bars[s]);
-                const int64_t pk0 = (t0 + it) * tp;
-                const uint32_t wbytes = (uint32_t)min((int64_t)tp, npk - pk0) * 16u;
-                mbar_expect_tx(bar, stage_bytes + wbytes);
-                tma_load_2d(smem_u32(smem + (size_t)s * stage_bytes), &tmap, (int)pk0 * elt_per_pack, 0, bar);
-                bulk_load_1d(smem_u32(wst + (size_t)s * tp), w + pk0 * EPP, wbytes, bar);
-            }
-        }
-    } else
     for (int it = 0; it < nmine; ++it) {
         const int s = it % nst;
         const uint32_t parity = (uint32_t)((it / nst) & 1);
@@ -225,6 +248,7 @@ k_axpy_dot(const __grid_constant__ CUtensorMap tmap, int j, int tp, int nst, int
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&ebars[s]));
     }
+    }   // consumer warps
 
     // ---- stage 1: one partial row per CTA; the rs row-slice warps of a chunk are summed in fixed order ----
     const int fold_idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
@@ -321,7 +345,7 @@ static bool axpy_dot_t(cudaStream_t s, const void* V, int64_t ld, int j, const v
     int64_t nb = sms;
     if (nb > ntiles) nb = ntiles;
     if (nb > RT_MAXROWS) nb = RT_MAXROWS;
-    k_axpy_dot<K><<<(int)nb, FZ_THREADS, sh, s>>>(tmap, j, tp, nst, elt_per_pack, (const W*)c1, (E*)w, n, (W*)partial, (W*)out, counter, flags, p2p ? *p2p : P2P());
+    launch_ex(k_axpy_dot<K>, (unsigned)nb, FZ_THREADS, sh, s, pdl_take(4), tmap, j, tp, nst, elt_per_pack, (const W*)c1, (E*)w, n, (W*)partial, (W*)out, counter, flags, p2p ? *p2p : P2P());
     return true;
 }
 

@@ -129,13 +129,15 @@ k_multidot(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j,
     constexpr int CB = MD_CB;
     constexpr int NW = MD_THREADS / 32;
     static_assert(CB == 16, "warp_fold16 assumes 16 columns per chunk");
-    if (flags && flags[F_STOP]) return;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     W* sacc = reinterpret_cast<W*>(smem_raw);   // [NW][jp]
     const int jp = j + 1;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < NW * jp; i += MD_THREADS) sacc[i] = zero_v(W());
+    pdl_wait();                                  // w (and the stop flag) come from the predecessor
+    pdl_trigger();
+    if (flags && flags[F_STOP]) return;
     __syncthreads();
     W* myacc = sacc + wid * jp;
     const int fold_idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
@@ -358,6 +360,8 @@ k_dot2(const typename Tr<K>::E* __restrict__ x, const typename Tr<K>::E* __restr
     constexpr int EPP = Tr<K>::EPP;
     constexpr int U = 4;
     using P = Pack<E, EPP>;
+    pdl_wait();
+    pdl_trigger();
     if (flags && flags[F_STOP]) return;
     const int64_t npk = n / EPP;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -411,6 +415,8 @@ k_multiaxpy(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j,
     constexpr int EPP = Tr<K>::EPP;
     constexpr int UA = 8;
     using P = Pack<E, EPP>;
+    pdl_wait();
+    pdl_trigger();
     if (flags && flags[F_STOP]) return;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -525,6 +531,8 @@ k_multiaxpy_fin(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j,
     constexpr int EPP = Tr<K>::EPP;
     constexpr int UA = 8;
     using P = Pack<E, EPP>;
+    pdl_wait();                                  // c2 / w' / flags come from the predecessor
+    pdl_trigger();
     if (fp.flags[F_STOP]) return;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -684,7 +692,7 @@ static void multidot_t(cudaStream_t s, const void* V, int64_t ld, int j, const v
         if (nb1 < 1) nb1 = 1;
         if (nb1 > 4 * (int64_t)sms) nb1 = 4 * (int64_t)sms;
         if (nb1 > RT_MAXROWS) nb1 = RT_MAXROWS;
-        k_dot2<K><<<(int)nb1, 256, 0, s>>>((const E*)V, (const E*)w, n, (W*)partial, (W*)out, counter, flags, p2p ? *p2p : P2P());
+        launch_ex(k_dot2<K>, (unsigned)nb1, 256, 0, s, pdl_take(2), (const E*)V, (const E*)w, n, (W*)partial, (W*)out, counter, flags, p2p ? *p2p : P2P());
         return;
     }
     const int64_t npk = n / Tr<K>::EPP;
@@ -700,7 +708,7 @@ static void multidot_t(cudaStream_t s, const void* V, int64_t ld, int j, const v
     const size_t sh = (size_t)(MD_THREADS / 32) * (size_t)(j + 1) * sizeof(W);
     static const SmemAttrOnce attr((const void*)k_multidot<K>, 160 * 1024);
     attr.ensure();
-    k_multidot<K><<<(int)nb, MD_THREADS, sh, s>>>((const E*)V, ld, j, (const E*)w, n, (W*)partial, (W*)out, counter, flags, pp);
+    launch_ex(k_multidot<K>, (unsigned)nb, MD_THREADS, sh, s, pdl_take(2), (const E*)V, ld, j, (const E*)w, n, (W*)partial, (W*)out, counter, flags, pp);
 }
 void launch_multidot(int kind, cudaStream_t s, const void* V, int64_t ld, int j, const void* w, int64_t n,
                      void* partial, void* out, unsigned* counter, const int* flags, int sms, const P2P* p2p) {
@@ -724,10 +732,11 @@ static void multiaxpy_t(cudaStream_t s, const void* V, int64_t ld, int j, const 
     if (nb > 2 * sms * 2) nb = 2 * sms * 2;
     if (nb > MAX_ROWBLOCKS) nb = MAX_ROWBLOCKS;
     const size_t sh = (size_t)(j > 0 ? j : 1) * sizeof(E);
+    const bool pdl = pdl_take(8);
     if (want_norm)
-        k_multiaxpy<K, true><<<(int)nb, 256, sh, s>>>((const E*)V, ld, j, (const W*)c, (E*)w, n, (double*)partial, (W*)nrm2_out, counter, flags, pp);
+        launch_ex(k_multiaxpy<K, true>, (unsigned)nb, 256, sh, s, pdl, (const E*)V, ld, j, (const W*)c, (E*)w, n, (double*)partial, (W*)nrm2_out, counter, flags, pp);
     else
-        k_multiaxpy<K, false><<<(int)nb, 256, sh, s>>>((const E*)V, ld, j, (const W*)c, (E*)w, n, (double*)partial, (W*)nrm2_out, counter, flags, pp);
+        launch_ex(k_multiaxpy<K, false>, (unsigned)nb, 256, sh, s, pdl, (const E*)V, ld, j, (const W*)c, (E*)w, n, (double*)partial, (W*)nrm2_out, counter, flags, pp);
 }
 void launch_multiaxpy(int kind, cudaStream_t s, const void* V, int64_t ld, int j, const void* c, void* w, int64_t n,
                       bool want_norm, void* partial, void* nrm2_out, unsigned* counter, const int* flags, int sms,
@@ -754,8 +763,8 @@ static void multiaxpy_fin_t(cudaStream_t s, const void* V, int64_t ld, int j, co
     FinParams fp;
     fp.c1 = c1; fp.hcol = hcol; fp.tol = tol; fp.atol = atol; fp.inv_dev = (double*)inv_dev; fp.flags = flags;
     fp.kstep = kstep; fp.mode = mode;
-    k_multiaxpy_fin<K><<<(int)nb, 256, sh, s>>>((const E*)V, ld, j, (const W*)c2, (E*)w, n, (double*)partial, (W*)nrm2_out, counter,
-                                               fp, p2p ? *p2p : P2P(), hp ? *hp : HaloP2P());
+    launch_ex(k_multiaxpy_fin<K>, (unsigned)nb, 256, sh, s, pdl_take(8), (const E*)V, ld, j, (const W*)c2, (E*)w, n, (double*)partial,
+              (W*)nrm2_out, counter, fp, p2p ? *p2p : P2P(), hp ? *hp : HaloP2P());
 }
 void launch_multiaxpy_fin(int kind, cudaStream_t s, const void* V, int64_t ld, int j, const void* c1, const void* c2, void* w,
                           int64_t n, void* partial, void* nrm2_out, unsigned* counter, void* hcol, double tol, double atol,

@@ -15,7 +15,7 @@ template <typename E> struct Coef7 { E c[7]; };
 template <typename E, int PW> struct PackOps {
     using P = Pack<E, PW>;
     static LKB_DI P ld(const E* p) {
-        if constexpr (sizeof(P) == 16) return ld_pack_nc<P>(p);
+        if constexpr (sizeof(P) == 16) return ld_pack_l1<P>(p);
         else { P r;
 #pragma unroll
             for (int e = 0; e < PW; ++e) r.v[e] = __ldg(p + e);
@@ -89,6 +89,8 @@ k_stencil(const typename Tr<K>::E* __restrict__ x, typename Tr<K>::E* __restrict
 {
     using E = typename Tr<K>::E;
     using PO = PackOps<E, PW>;
+    pdl_wait();            // x, the stop flag and the halo epoch come from the predecessor
+    pdl_trigger();
     if (flags && flags[F_STOP]) return;
     if (halo_epoch) {      // double-buffered p2p halos: pick the parity of the current epoch
         const int64_t off = (int64_t)(*halo_epoch & 1u) * halo_parity_stride;
@@ -208,6 +210,8 @@ k_stencil_smem(const typename Tr<K>::E* __restrict__ x, typename Tr<K>::E* __res
     using E = typename Tr<K>::E;
     using P = Pack<E, PW>;
     constexpr int PB = PW * (int)sizeof(E);       // payload bytes (Pack is padded to 16 B)
+    pdl_wait();
+    pdl_trigger();
     if (flags && flags[F_STOP]) return;
     if (halo_epoch) {
         const int64_t off = (int64_t)(*halo_epoch & 1u) * halo_parity_stride;
@@ -318,6 +322,8 @@ k_stencil3d_zmarch(const typename Tr<K>::E* __restrict__ x, typename Tr<K>::E* _
     using E = typename Tr<K>::E;
     using PO = PackOps<E, PW>;
     using P = typename PO::P;
+    pdl_wait();
+    pdl_trigger();
     if (flags && flags[F_STOP]) return;
     if (halo_epoch) {
         const int64_t off = (int64_t)(*halo_epoch & 1u) * halo_parity_stride;
@@ -392,7 +398,7 @@ static void stencil_launch(cudaStream_t s, const StencilArgs& a, const void* x, 
             constexpr int LZ = 32;
             const int64_t ncbx = (npk_row + ZT_TX - 1) / ZT_TX, ncby = (a.ny + ZT_TY - 1) / ZT_TY, nzc = (a.nz + LZ - 1) / LZ;
             const unsigned grid = (unsigned)(ncbx * ncby * nzc);
-            k_stencil3d_zmarch<K, PW, LZ><<<grid, ZT_TX * ZT_TY, 0, s>>>((const E*)x, (E*)y, a.nx, a.ny, a.nz, cf,
+            launch_ex(k_stencil3d_zmarch<K, PW, LZ>, grid, ZT_TX * ZT_TY, 0, s, pdl_take(1), (const E*)x, (E*)y, a.nx, a.ny, a.nz, cf,
                 (const E*)a.halo_lo, (const E*)a.halo_hi, a.halo_epoch, a.halo_parity_stride, a.flag_lo, a.flag_hi, ncbx, ncby, flags);
             return;
         }
@@ -404,7 +410,7 @@ static void stencil_launch(cudaStream_t s, const StencilArgs& a, const void* x, 
             const unsigned grid_ = (unsigned)(nyb_ * (DIM == 3 ? a.nz : 1) * ncb_); \
             const size_t sh_ = (size_t)((RY_ + 2) + (DIM == 3 ? 2 * RY_ : 0)) * ST_TX * sizeof(Pack<E, PW>); \
             static const SmemAttrOnce once_((const void*)k_stencil_smem<K, PW, DIM, RY_>, 96 * 1024); once_.ensure(); \
-            k_stencil_smem<K, PW, DIM, RY_><<<grid_, ST_TX, sh_, s>>>((const E*)x, (E*)y, a.nx, a.ny, a.nz, cf, \
+            launch_ex(k_stencil_smem<K, PW, DIM, RY_>, grid_, ST_TX, sh_, s, pdl_take(1), (const E*)x, (E*)y, a.nx, a.ny, a.nz, cf, \
                 (const E*)a.halo_lo, (const E*)a.halo_hi, a.halo_epoch, a.halo_parity_stride, a.flag_lo, a.flag_hi, ncb_, flags); }
         if (variant == 3) LKB_STS(4) else LKB_STS(8)
 #undef LKB_STS
@@ -417,9 +423,8 @@ static void stencil_launch(cudaStream_t s, const StencilArgs& a, const void* x, 
     const int64_t nyb = (a.ny + RY - 1) / RY;
     const int64_t ncb = (npk_row + 255) / 256;
     const unsigned grid = (unsigned)(nyb * (DIM == 3 ? a.nz : 1) * ncb);
-    k_stencil<K, PW, DIM, RY, 1, false><<<grid, 256, 0, s>>>((const E*)x, (E*)y, a.nx, a.ny, a.nz, cf,
-                                                             (const E*)a.halo_lo, (const E*)a.halo_hi, a.halo_epoch,
-                                                             a.halo_parity_stride, a.flag_lo, a.flag_hi, ncb, flags);
+    launch_ex(k_stencil<K, PW, DIM, RY, 1, false>, grid, 256, 0, s, pdl_take(1), (const E*)x, (E*)y, a.nx, a.ny, a.nz, cf,
+              (const E*)a.halo_lo, (const E*)a.halo_hi, a.halo_epoch, a.halo_parity_stride, a.flag_lo, a.flag_hi, ncb, flags);
 }
 
 template <int K>

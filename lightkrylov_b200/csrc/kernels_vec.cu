@@ -107,6 +107,8 @@ k_scale_dev(typename Tr<K>::E* __restrict__ x, int64_t n, const double* __restri
     using Rl = typename Tr<K>::Rl;
     constexpr int EPP = Tr<K>::EPP;
     using P = Pack<E, EPP>;
+    pdl_wait();
+    pdl_trigger();
     if (flags) {
         if (flags[F_SCALED]) return;
         if (flags[F_STOP] && flags[F_INFO] != kstep) return;
@@ -457,7 +459,7 @@ void launch_scale_dev(int kind, cudaStream_t s, void* x, int64_t n, const void* 
     const HaloP2P h = hp ? *hp : HaloP2P();
     LKB_DISPATCH(kind, {
         using E = typename Tr<K>::E;
-        k_scale_dev<K><<<ew_grid(n / Tr<K>::EPP, sms), 256, 0, s>>>((E*)x, n, (const double*)inv_dev, flags, kstep, h);
+        launch_ex(k_scale_dev<K>, (unsigned)ew_grid(n / Tr<K>::EPP, sms), 256, 0, s, pdl_take(16), (E*)x, n, (const double*)inv_dev, flags, kstep, h);
     });
 }
 void launch_copy_gated(int kind, cudaStream_t s, const void* src, void* dst, int64_t n, const int* flags, int sms) {

@@ -125,8 +125,16 @@ int allreduce_w(lkb_ctx_s* c, void* buf, size_t ndoubles) {
     NcclApi* api = nccl_api();
     if (!api) return LKB_ERR_NCCL;
     LKB_NCCL(api->AllReduce(buf, buf, ndoubles, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->comm, c->stream));
+    pdl_rearm();                                       // the next kernel follows an NCCL operation: normal launch
     return 0;
 }
+int& pdl_state() { static thread_local int s = 0; return s; }
+// Which kernel classes are launched programmatically (bits: 1 matvec, 2 multi-dot, 4 fused axpy+dot, 8 multi-axpy, 16 scale).
+// Default 4: only the TMA kernel.  Measured on B200 (profiles/r02_pdl2.sh .. r02_pdl4.sh): a programmatically launched
+// kernel inherits the predecessor's L1 / shared-memory carve-out, which costs the LDG-based multi-dot / multi-axpy
+// kernels up to 11 % (4096 x 512: all classes 1729 steps/s, none 1870, fused only 1876); the TMA kernel is carve-out
+// neutral and gains from filling its ring during the multi-dot's tail (reduction tree + NVLink allreduce).
+int pdl_mask() { static const int m = getenv("LKB_PDL_MASK") ? atoi(getenv("LKB_PDL_MASK")) : 4; return m; }
 // Stream-ordered allocation of vectors / bases / solver work space from the device's default memory pool with an
 // unlimited release threshold: freed blocks stay cached in the pool, so the GB-sized work bases that gmres / cg /
 // eigs allocate per call (`allocate(V(kdim+1), source=b)` in the reference) cost a pool lookup instead of a
@@ -325,6 +333,7 @@ int lkb_set_option(lkb_ctx_t c, const char* name, int value) {
     if (!strcmp(name, "graphs")) c->graphs = value != 0;
     else if (!strcmp(name, "fused")) c->fused = value != 0;
     else if (!strcmp(name, "fin")) c->fin = value != 0;
+    else if (!strcmp(name, "pdl")) c->pdl = value != 0;
     else if (!strcmp(name, "write_intermediate")) c->write_intermediate = value != 0;
     else if (!strcmp(name, "csr_slice_kb")) c->csr_slice_kb = value;            // 0 disables the L2 blocking
     else if (!strcmp(name, "csr_block_min_kb")) c->csr_block_min_kb = value;
@@ -801,6 +810,7 @@ int op_apply_enqueue(lkb_op_s* A, const void* x, void* y, bool trans, const int*
                 LKB_NCCL(api->Recv(A->halo_hi, cnt, dt, c->rank + 1, c->comm, c->stream));
             }
             LKB_NCCL(api->GroupEnd());
+            pdl_rearm();
         }
         launch_stencil(A->kind, c->stream, A->st, x, y, trans, flags, c->sms);
     } else if (A->type == 3 && A->dist) {
@@ -852,6 +862,9 @@ int op_apply_enqueue(lkb_op_s* A, const void* x, void* y, bool trans, const int*
         if (r != 0) { set_error("user matvec callback returned %d", r); return LKB_ERR_ARG; }
         nl = 0;
     }
+    // anything but our own plain kernels (NCCL gathers / reductions, device-to-device copies, a user callback) breaks
+    // the programmatic-launch chain: the next PDL-aware kernel is launched normally
+    if (!(A->type == 1 || A->type == 0 || (A->type == 3 && !A->dist))) pdl_rearm();
     prof_end(c, PC_MATVEC, nl);
     return check_launch(c, "matvec");
 }

@@ -47,6 +47,34 @@ struct SmemAttrOnce {
     }
 };
 
+// ---- programmatic dependent launch (PDL) of the step-loop kernels ------------------------------------------
+// The Krylov step loops chain 5 kernels per step whose tails (two-stage reduction, in-kernel allreduce) leave the GPU
+// idle for 5-15 us; with PDL the next kernel's CTAs are scheduled as SMs drain, run their prologue (k_axpy_dot: fill
+// the TMA ring) and block in griddepcontrol.wait until the predecessor has completed.  Host side: a per-thread state
+// armed by the step loop (PdlScope); the launchers of PDL-aware kernels ask pdl_take().  State 1 = "armed": the next
+// aware launch is a normal one (its predecessor in the stream is not one of our kernels: memset, NCCL, user
+// callback), afterwards the chain is on.  pdl_rearm() after anything that is not a kernel of this library.
+int& pdl_state();
+// cls: kernel class bit for the LKB_PDL_MASK experiment switch (1 matvec, 2 multi-dot, 4 fused, 8 multi-axpy, 16 scale)
+int pdl_mask();
+inline bool pdl_take(int cls = 0xff) { int& s = pdl_state(); if (s == 2) return (pdl_mask() & cls) != 0; if (s == 1) s = 2; return false; }
+inline void pdl_rearm() { int& s = pdl_state(); if (s == 2) s = 1; }
+struct PdlScope {
+    int prev;
+    explicit PdlScope(bool on) : prev(pdl_state()) { pdl_state() = on ? 1 : 0; }
+    ~PdlScope() { pdl_state() = prev; }
+};
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_ex(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, bool pdl, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1); cfg.blockDim = dim3(block, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1u : 0u;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 struct StencilArgs {
     int64_t nx, ny, nz;        // local slab: nx fastest; the slowest axis is the sharded one
     Scalar coef[7];            // center, -x, +x, -y, +y, -z, +z

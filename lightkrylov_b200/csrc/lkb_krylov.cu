@@ -447,6 +447,7 @@ int arnoldi_enqueue(lkb_op_s* A, lkb_basis_s* X, int kstart, int kend, double to
     LKB_TRY(ensure_ws(c, kend + 1));
     auto body = [&]() -> int {
         LKB_TRY(reset_flags(c));
+        PdlScope pdl(c->pdl && !c->profile);      // the kernels of the step loop overlap their heads with the predecessors' tails
         bool pushed = false;       // X(k-1)'s boundary rows already sit in the neighbours' halo buffers
         for (int k = kstart; k <= kend; ++k) {
             void* w = col_ptr(X, k);
@@ -606,6 +607,7 @@ int lanczos_enqueue(lkb_op_s* A, lkb_basis_s* X, int kstart, int kend, double to
     const size_t ndw = 2 * (size_t)(kind_cplx(kind) ? 2 : 1);
     auto body = [&]() -> int {
         LKB_TRY(reset_flags(c));
+        PdlScope pdl(c->pdl && !c->profile);
         bool pushed = false;
         for (int k = kstart; k <= kend; ++k) {
             void* w = col_ptr(X, k);
@@ -694,6 +696,7 @@ int bidiag_enqueue(lkb_op_s* A, lkb_basis_s* U, lkb_basis_s* V, int kstart, int 
     LKB_TRY(ensure_ws(c, kend + 1));
     auto body = [&]() -> int {
         LKB_TRY(reset_flags(c));
+        PdlScope pdl(c->pdl && !c->profile);
         for (int k = kstart; k <= kend; ++k) {
             char* bcol = (char*)c->Hd + (size_t)ldbd * (k - 1) * es;
             void* vk = col_ptr(V, k - 1);

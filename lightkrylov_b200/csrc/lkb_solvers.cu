@@ -137,6 +137,7 @@ static int gmres_impl(lkb_op_t A, lkb_vec_t b, lkb_vec_t x, int32_t* info, doubl
     auto enqueue_cycle = [&]() -> int {
         char* gcs = (char*)ge + (size_t)(kdim + 1) * 16; char* gsn = gcs + (size_t)kdim * 16;
         const bool fin_ok = c->fin && (c->world == 1 || c->p2p_active);
+        PdlScope pdl(c->pdl && !c->profile);
         bool pushed = false;
         for (int kk = 1; kk <= kdim; ++kk) {
             void* w = col_ptr(V, kk);

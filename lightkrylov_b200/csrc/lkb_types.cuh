@@ -23,6 +23,17 @@ static inline int kind_epp(int k) { return k == KS ? 4 : (k == KZ ? 1 : 2); }
 static inline bool kind_cplx(int k) { return k >= KC; }
 
 #define LKB_DI __device__ __forceinline__
+
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start while its predecessor in the stream is still draining.  pdl_wait() blocks until every predecessor grid has
+// COMPLETED and its memory is visible (no-op for a normally launched kernel); pdl_trigger() lets the runtime launch
+// this kernel's own dependent once all CTAs have executed it.  Every PDL-aware kernel here runs
+//     [work that touches nothing the predecessor writes]  pdl_wait();  pdl_trigger();  [everything else]
+// so a dependent's pre-wait code only ever runs once the predecessor's predecessor is complete.
+#if defined(__CUDACC__)
+LKB_DI void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+LKB_DI void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 #define LKB_HDI __host__ __device__ __forceinline__
 
 // ---- scalar algebra, overloaded on the element type ---------------------------------------
@@ -113,12 +124,31 @@ LKB_HDI void from_scalar(Scalar s, double2& o) { o = make_double2(s.re, s.im); }
 // ---- 16-byte packs ---------------------------------------------------------------------------
 template <typename E, int EPP> struct alignas(16) Pack { E v[EPP]; };
 
-template <typename P> LKB_DI P ld_pack_nc(const void* p) {   // read-only streaming path (LDG.E.128.CONSTANT)
+// Streaming 128-bit loads.  Every Gram-Schmidt / vector kernel reads each byte exactly once, so an L1 line allocated
+// for it is pure overhead: with L1::no_allocate the multi-dot / multi-axpy kernels run 4-5 % faster at the per-GPU
+// share of N = 8 (measured round 2, profiles/r02_pdl3.sh: 1828 -> 1917 Arnoldi steps/s at 4096 x 512) and no longer
+// depend on the SM's L1 / shared-memory carve-out (a max-shared carve-out cost the allocating version 11 %).
+// ld_pack_l1 keeps the allocating read-only path for the stencils, whose x-neighbours are re-read through L1.
+template <typename P> LKB_DI P ld_pack_l1(const void* p) {   // read-only path with L1 allocation (LDG.E.128.CONSTANT)
     int4 r = __ldg(reinterpret_cast<const int4*>(p));
     return *reinterpret_cast<P*>(&r);
 }
-template <typename P> LKB_DI P ld_pack(const void* p) {
+template <typename P> LKB_DI P ld_pack_nc(const void* p) {   // read-only streaming path, no L1 allocation
+#ifdef LKB_L1_ALLOC
+    return ld_pack_l1<P>(p);
+#else
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return *reinterpret_cast<P*>(&r);
+#endif
+}
+template <typename P> LKB_DI P ld_pack(const void* p) {      // coherent streaming load (the vector is rewritten by this kernel)
+#ifdef LKB_L1_ALLOC
     int4 r = *reinterpret_cast<const int4*>(p);
+#else
+    int4 r;
+    asm volatile("ld.global.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+#endif
     return *reinterpret_cast<P*>(&r);
 }
 template <typename P> LKB_DI void st_pack(void* p, const P& v) {

@@ -266,6 +266,43 @@ def test_arnoldi_kstart_kend_resume_and_graph_equivalence(lk, ctx, oracle):
     assert np.array_equal(H, res[0][0])
 
 
+@pytest.mark.parametrize("kind,proc", [("d", "arnoldi"), ("z", "arnoldi"), ("s", "arnoldi"), ("d", "lanczos")])
+def test_programmatic_launch_chain_is_bitwise_neutral(lk, ctx, oracle, kind, proc):
+    """The step-loop kernels are launched programmatically (PDL: heads overlap the predecessors' tails, k_axpy_dot
+    fills its TMA ring before griddepcontrol.wait).  Option "pdl" = 0 restores plain stream order: H / T, the basis
+    and info must be bitwise identical with graphs on and off, also through a breakdown (stop flag)."""
+    dt = lk.DTYPES[kind]
+    nx, ny, kdim = 256, 192, 40; n = nx * ny
+    coef = CONVDIFF7[:5] if proc == "arnoldi" else (4.0, -1.0, -1.0, -1.0, -1.0)
+    A = lk.LinOp.stencil5(ctx, kind, nx, ny, coef)
+    x0 = oracle.fill(n, kind, "uniform", 9); oracle.normalize(x0)
+    res = []
+    for pdl in (1, 0):
+        for graphs in (True, False):
+            ctx.set_option("pdl", pdl); ctx.set_graphs(graphs)
+            X = lk.Basis(ctx, kind, n, kdim + 1).put(x0)
+            H = np.zeros((kdim + 1, kdim), dtype=dt, order="F")
+            info = lk.arnoldi(A, X, H) if proc == "arnoldi" else lk.lanczos(A, X, H)
+            res.append((info, H.copy(), X.get()))
+    ctx.set_option("pdl", 1); ctx.set_graphs(True)
+    assert res[0][0] == 0
+    for info, H, Xg in res[1:]:
+        assert info == res[0][0] and np.array_equal(H, res[0][1]) and np.array_equal(Xg, res[0][2])
+    # breakdown inside a captured chain: x0 spans a 3-dimensional invariant subspace of a diagonal operator
+    if proc == "arnoldi" and kind == "d":
+        m = 4096
+        Ah = np.asfortranarray(np.diag(np.arange(1, m + 1)).astype(dt))
+        Ad = lk.LinOp.dense(ctx, Ah)
+        y0 = np.zeros(m, dtype=dt); y0[:3] = 1 / np.sqrt(3.0)
+        out = []
+        for pdl in (1, 0):
+            ctx.set_option("pdl", pdl)
+            X = lk.Basis(ctx, kind, m, 11).put(y0); H = np.zeros((11, 10), dtype=dt, order="F")
+            out.append((lk.arnoldi(Ad, X, H, tol=1e-12), H.copy()))
+        ctx.set_option("pdl", 1)
+        assert out[0][0] == out[1][0] == 3 and np.array_equal(out[0][1], out[1][1])
+
+
 def test_arnoldi_transpose(lk, ctx, oracle):
     nx, ny, kdim = 64, 64, 20; n = nx * ny
     A = lk.LinOp.stencil5(ctx, "d", nx, ny, CONVDIFF7[:5]); Ao = oracle.Op.stencil("d", (nx, ny), CONVDIFF7[:5])
