@@ -571,6 +571,7 @@ void launch_csr(int kind, cudaStream_t s, int64_t m, const int64_t* rowptr, cons
 // streamed operands (table, col, val, y) are marked evict_first so that they do not push the slice out.
 LKB_DI uint64_t l2_policy_evict_last() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
 LKB_DI uint64_t l2_policy_evict_first() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+LKB_DI uint64_t l2_policy_evict_normal() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p)); return p; }
 template <typename T> LKB_DI T ld_hint(const T* p, uint64_t pol);
 template <> LKB_DI float ld_hint<float>(const float* p, uint64_t pol) {
     float v; asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol)); return v; }
@@ -589,11 +590,11 @@ template <int K>
 __global__ void __launch_bounds__(256)
 k_csr_blocked(int64_t rows, const uint32_t* __restrict__ tab, const int32_t* __restrict__ col,
               const typename Tr<K>::E* __restrict__ val, const typename Tr<K>::E* __restrict__ x,
-              typename Tr<K>::E* __restrict__ y, bool conj_vals, bool first, const int* __restrict__ flags)
+              typename Tr<K>::E* __restrict__ y, bool conj_vals, bool first, const int* __restrict__ flags, bool stream_first)
 {
     using E = typename Tr<K>::E;
     if (flags && flags[F_STOP]) return;
-    const uint64_t keep = l2_policy_evict_last(), stream = l2_policy_evict_first();
+    const uint64_t keep = l2_policy_evict_last(), stream = stream_first ? l2_policy_evict_first() : l2_policy_evict_normal();
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t q0 = ld_hint<uint32_t>(tab + r, stream), q1 = ld_hint<uint32_t>(tab + r + 1, stream);
         if (q0 == q1 && !first) continue;                       // nothing in this block for row r
@@ -606,17 +607,125 @@ k_csr_blocked(int64_t rows, const uint32_t* __restrict__ tab, const int32_t* __r
         y[r] = acc;
     }
 }
+// "CSR-stream" variant (default): a CTA owns CS_ROWS consecutive rows of the block, whose entries are ONE contiguous
+// run [tab[r0], tab[r0 + CS_ROWS]) of the blocked arrays.  Phase 1: all threads stride over that run -- perfectly
+// coalesced col / val streams, CS_U independent gathers of x in flight per thread -- and park the products in shared
+// memory; phase 2: every thread sums the products of its rows in position order (the same fixed order as the
+// thread-per-row kernel) and updates y.  The thread-per-row kernel chains tab -> col -> x -> fma with 2-3 entries per
+// row and ran latency-bound (~3.3 TB/s of DRAM traffic on C5); here the three dependent loads of a chain are issued
+// for CS_U entries at a time.  Streamed operands: L1::no_allocate + L2 evict_first; x gathers: L2 evict_last.
+enum { CS_ROWS = 512, CS_CH = 2048 };
+template <typename T> LKB_DI T ld_stream(const T* p, uint64_t pol);
+template <> LKB_DI float ld_stream<float>(const float* p, uint64_t pol) {
+    float v; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol)); return v; }
+template <> LKB_DI double ld_stream<double>(const double* p, uint64_t pol) {
+    double v; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol)); return v; }
+template <> LKB_DI float2 ld_stream<float2>(const float2* p, uint64_t pol) {
+    float2 v; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol)); return v; }
+template <> LKB_DI double2 ld_stream<double2>(const double2* p, uint64_t pol) {
+    double2 v; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol)); return v; }
+template <> LKB_DI int32_t ld_stream<int32_t>(const int32_t* p, uint64_t pol) {
+    int32_t v; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol)); return v; }
+template <> LKB_DI uint32_t ld_stream<uint32_t>(const uint32_t* p, uint64_t pol) {
+    uint32_t v; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol)); return v; }
+
+template <int K, int CS_U, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+k_csr_blocked_stream(int64_t rows, const uint32_t* __restrict__ tab, const int32_t* __restrict__ col,
+                     const typename Tr<K>::E* __restrict__ val, const typename Tr<K>::E* __restrict__ x,
+                     typename Tr<K>::E* __restrict__ y, bool conj_vals, bool first, const int* __restrict__ flags)
+{
+    using E = typename Tr<K>::E;
+    constexpr int RPT = CS_ROWS / 256;                      // rows per thread
+    if (flags && flags[F_STOP]) return;
+    extern __shared__ __align__(16) unsigned char cs_smem[];
+    E* prod = reinterpret_cast<E*>(cs_smem);                // [CS_CH]
+    const uint64_t keep = l2_policy_evict_last(), stream = l2_policy_evict_first();
+    const int tid = threadIdx.x;
+    for (int64_t r0 = (int64_t)blockIdx.x * CS_ROWS; r0 < rows; r0 += (int64_t)gridDim.x * CS_ROWS) {
+        const int64_t rend = min(rows, r0 + CS_ROWS);
+        uint32_t qa[RPT], qb[RPT];
+        E acc[RPT];
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+            const int64_t r = r0 + tid + 256 * i;
+            qa[i] = qb[i] = 0u; acc[i] = zero_v(E());
+            if (r < rend) {
+                qa[i] = ld_stream<uint32_t>(tab + r, stream); qb[i] = ld_stream<uint32_t>(tab + r + 1, stream);
+                if (!first && qa[i] != qb[i]) acc[i] = y[r];
+            }
+        }
+        const uint32_t qs = ld_stream<uint32_t>(tab + r0, stream), qe = ld_stream<uint32_t>(tab + rend, stream);
+        for (uint32_t c0 = qs; c0 < qe; c0 += CS_CH) {
+            const uint32_t c1 = min(c0 + (uint32_t)CS_CH, qe);
+            // ---- phase 1: products of the run [c0, c1) into shared memory ----
+            for (uint32_t e0 = c0 + tid; e0 < c1; e0 += 256 * CS_U) {
+                int32_t cj[CS_U]; E a[CS_U], xv[CS_U];
+#pragma unroll
+                for (int u = 0; u < CS_U; ++u) { const uint32_t e = e0 + 256 * u; if (e < c1) cj[u] = ld_stream<int32_t>(col + e, stream); }
+#pragma unroll
+                for (int u = 0; u < CS_U; ++u) { const uint32_t e = e0 + 256 * u; if (e < c1) a[u] = ld_stream<E>(val + e, stream); }
+#pragma unroll
+                for (int u = 0; u < CS_U; ++u) { const uint32_t e = e0 + 256 * u; if (e < c1) xv[u] = ld_hint<E>(x + cj[u], keep); }
+#pragma unroll
+                for (int u = 0; u < CS_U; ++u) {
+                    const uint32_t e = e0 + 256 * u;
+                    if (e < c1) prod[e - c0] = mul_v(conj_vals ? conj_v(a[u]) : a[u], xv[u]);
+                }
+            }
+            __syncthreads();
+            // ---- phase 2: row sums in position order ----
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) {
+                const uint32_t lo = max(qa[i], c0), hi = min(qb[i], c1);
+                for (uint32_t q = lo; q < hi; ++q) acc[i] = add_v(acc[i], prod[q - c0]);
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+            const int64_t r = r0 + tid + 256 * i;
+            if (r < rend && (first || qa[i] != qb[i])) y[r] = acc[i];
+        }
+    }
+}
 void launch_csr_blocked(int kind, cudaStream_t s, const CsrBlocked& b, const void* x, void* y, bool conj_vals, const int* flags, int sms) {
+    // Variants measured on the full-size C5 matrix (B200, profiles/spmv_ab.py, gpurun_out/r02_spmv_ab*.jsonl; ncu in
+    // profiles/r02_ncu_summary.md), matvec ms per sweep at 48 MB slices:
+    //   0  thread-per-row, streams evict_first    17.2   DRAM 6.9 GB / block at 5.3 TB/s: bandwidth-bound on ACTUAL traffic,
+    //                                                    of which ~3 GB are x-gather sectors that missed L2
+    //   2  thread-per-row, streams evict_normal   16.4   (default)
+    //   1  CSR-stream                             19.5   DRAM 4.9 GB / block (x misses 0.9 GB) but latency-bound at 64 regs,
+    //                                                    4 CTAs / SM; forcing 5-6 CTAs / SM spills and doubles the time
+    // A persisting-L2 set-aside (cudaLimitPersistingL2CacheSize 64 / 79 MB) changed none of them by more than 2 %.
+    static const int variant = getenv("LKB_CSR_BLOCKED_VARIANT") ? atoi(getenv("LKB_CSR_BLOCKED_VARIANT")) : 2;
+    if (variant == 1) {
+        static const int cfg = getenv("LKB_CSR_STREAM_CFG") ? atoi(getenv("LKB_CSR_STREAM_CFG")) : 0;
+        int64_t nbs = (b.rows + CS_ROWS - 1) / CS_ROWS;
+        if (nbs < 1) nbs = 1;
+        if (nbs > (int64_t)sms * 6) nbs = (int64_t)sms * 6;
+        const size_t sh = (size_t)CS_CH * kind_size(kind);
+        for (int blk = 0; blk < b.nb; ++blk) {
+            const uint32_t* tab = b.tab + (size_t)blk * (b.rows + 1);
+#define LKB_CSS(K_, E_, U_, M_) k_csr_blocked_stream<K_, U_, M_><<<(int)nbs, 256, sh, s>>>(b.rows, tab, b.col, (const E_*)b.val, (const E_*)x, (E_*)y, conj_vals, blk == 0, flags)
+#define LKB_CSS_K(U_, M_) switch (kind) { case KS: LKB_CSS(KS, float, U_, M_); break; case KD: LKB_CSS(KD, double, U_, M_); break; \
+                                          case KC: LKB_CSS(KC, float2, U_, M_); break; default: LKB_CSS(KZ, double2, U_, M_); break; }
+            if (cfg == 1) LKB_CSS_K(2, 6) else if (cfg == 2) LKB_CSS_K(5, 3) else if (cfg == 3) LKB_CSS_K(3, 5) else LKB_CSS_K(4, 4)
+#undef LKB_CSS_K
+#undef LKB_CSS
+        }
+        return;
+    }
     int64_t nb = (b.rows + 255) / 256;
     if (nb < 1) nb = 1;
     if (nb > (int64_t)sms * 16) nb = (int64_t)sms * 16;
     for (int blk = 0; blk < b.nb; ++blk) {
         const uint32_t* tab = b.tab + (size_t)blk * (b.rows + 1);
         switch (kind) {
-            case KS: k_csr_blocked<KS><<<(int)nb, 256, 0, s>>>(b.rows, tab, b.col, (const float*)b.val, (const float*)x, (float*)y, conj_vals, blk == 0, flags); break;
-            case KD: k_csr_blocked<KD><<<(int)nb, 256, 0, s>>>(b.rows, tab, b.col, (const double*)b.val, (const double*)x, (double*)y, conj_vals, blk == 0, flags); break;
-            case KC: k_csr_blocked<KC><<<(int)nb, 256, 0, s>>>(b.rows, tab, b.col, (const float2*)b.val, (const float2*)x, (float2*)y, conj_vals, blk == 0, flags); break;
-            default: k_csr_blocked<KZ><<<(int)nb, 256, 0, s>>>(b.rows, tab, b.col, (const double2*)b.val, (const double2*)x, (double2*)y, conj_vals, blk == 0, flags); break;
+            case KS: k_csr_blocked<KS><<<(int)nb, 256, 0, s>>>(b.rows, tab, b.col, (const float*)b.val, (const float*)x, (float*)y, conj_vals, blk == 0, flags, variant == 0); break;
+            case KD: k_csr_blocked<KD><<<(int)nb, 256, 0, s>>>(b.rows, tab, b.col, (const double*)b.val, (const double*)x, (double*)y, conj_vals, blk == 0, flags, variant == 0); break;
+            case KC: k_csr_blocked<KC><<<(int)nb, 256, 0, s>>>(b.rows, tab, b.col, (const float2*)b.val, (const float2*)x, (float2*)y, conj_vals, blk == 0, flags, variant == 0); break;
+            default: k_csr_blocked<KZ><<<(int)nb, 256, 0, s>>>(b.rows, tab, b.col, (const double2*)b.val, (const double2*)x, (double2*)y, conj_vals, blk == 0, flags, variant == 0); break;
         }
     }
 }

@@ -10,6 +10,7 @@
 // summation order of A^H u -- and hence the result -- is a fixed function of the matrix, identical to the host
 // counting sort of round 1.  1.6e9 nnz (C5 at BASELINE size) transpose in well under a second; the round-1 host
 // build needed minutes and ~70 GB of host memory.
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
