@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1)
 k_axpy_dot(const __grid_constant__ CUtensorMap tmap, int j, int tp, int nst, int elt_per_pack,
            const typename Tr<K>::W* __restrict__ c1, typename Tr<K>::E* __restrict__ w, int64_t n,
            typename Tr<K>::W* __restrict__ partial, typename Tr<K>::W* __restrict__ out,
-           unsigned* __restrict__ counter, const int* __restrict__ flags, const P2P p2p)
+           unsigned* __restrict__ counter, const int* __restrict__ flags, const P2P p2p, const int desc)
 {
     using E = typename Tr<K>::E;
     using W = typename Tr<K>::W;
@@ -108,9 +108,13 @@ k_axpy_dot(const __grid_constant__ CUtensorMap tmap, int j, int tp, int nst, int
     const int tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
     const int64_t npk = n / EPP;
     const int64_t ntiles = (npk + tp - 1) / tp;
-    const int64_t t0 = ((int64_t)blockIdx.x * ntiles) / gridDim.x;          // balanced to within one tile
-    const int64_t t1 = (((int64_t)blockIdx.x + 1) * ntiles) / gridDim.x;
-    const int nmine = (int)max((int64_t)0, t1 - t0);
+    // tiles are dealt round-robin (one global sweep over the rows, lkb_kernels.h "serpentine sweeps"), balanced to within
+    // one tile; desc walks the same deal from the top
+    const int nmine = (int)(((int64_t)blockIdx.x < ntiles) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
+    auto tile_of = [&](int it) -> int64_t {
+        const int64_t t = (int64_t)it * gridDim.x + blockIdx.x;
+        return desc ? ntiles - 1 - t : t;
+    };
 
     ktime_cta(p2p, 0);
     if (tid == 0) {
@@ -141,7 +145,7 @@ k_axpy_dot(const __grid_constant__ CUtensorMap tmap, int j, int tp, int nst, int
         auto issue = [&](int it) {
             const int s = it % nst;
             const uint32_t bar = smem_u32(&bars[s]);
-            const int64_t pk0 = (t0 + it) * tp;
+            const int64_t pk0 = tile_of(it) * tp;
             const uint32_t wbytes = (uint32_t)min((int64_t)tp, npk - pk0) * 16u;
             mbar_expect_tx(bar, stage_bytes + wbytes);
             tma_load_2d(smem_u32(smem + (size_t)s * stage_bytes), &tmap, (int)pk0 * elt_per_pack, 0, bar);
@@ -184,7 +188,7 @@ k_axpy_dot(const __grid_constant__ CUtensorMap tmap, int j, int tp, int nst, int
         const P* tile = reinterpret_cast<const P*>(smem + (size_t)s * stage_bytes);
         // this tile's packs of w arrive with the V tile (1-D bulk copy on the same mbarrier)
         const bool own = tid < tp;
-        const int64_t pk = (t0 + it) * tp + tid;
+        const int64_t pk = tile_of(it) * tp + tid;
         const bool inb = own && pk < npk;
 
         mbar_wait(smem_u32(&bars[s]), parity);
@@ -345,7 +349,7 @@ static bool axpy_dot_t(cudaStream_t s, const void* V, int64_t ld, int j, const v
     int64_t nb = sms;
     if (nb > ntiles) nb = ntiles;
     if (nb > RT_MAXROWS) nb = RT_MAXROWS;
-    launch_ex(k_axpy_dot<K>, (unsigned)nb, FZ_THREADS, sh, s, pdl_take(4), tmap, j, tp, nst, elt_per_pack, (const W*)c1, (E*)w, n, (W*)partial, (W*)out, counter, flags, p2p ? *p2p : P2P());
+    launch_ex(k_axpy_dot<K>, (unsigned)nb, FZ_THREADS, sh, s, pdl_take(4), tmap, j, tp, nst, elt_per_pack, (const W*)c1, (E*)w, n, (W*)partial, (W*)out, counter, flags, p2p ? *p2p : P2P(), sweep_dir());
     return true;
 }
 

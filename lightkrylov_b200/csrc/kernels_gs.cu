@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(MD_THREADS, 2)
 k_multidot(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j,
            const typename Tr<K>::E* __restrict__ w, int64_t n,
            typename Tr<K>::W* __restrict__ partial, typename Tr<K>::W* __restrict__ out,
-           unsigned* __restrict__ counter, const int* __restrict__ flags, const P2P p2p)
+           unsigned* __restrict__ counter, const int* __restrict__ flags, const P2P p2p, const int desc)
 {
     using E = typename Tr<K>::E;
     using W = typename Tr<K>::W;
@@ -143,21 +143,36 @@ k_multidot(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j,
     const int fold_idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
     ktime_cta(p2p, 0);
 
-    // Row split: every CTA owns a contiguous range [p0, p1) of 32-pack groups, balanced to within ONE group (512 B)
-    // for any n.  The range is walked in tiles of 4 packs per thread (one warp fold per 64 loads); what is left is
-    // walked in 1-pack tiles and only the final < 256 packs take the masked path.  (Round 1 split whole tiles and
-    // shrank ALL tiles to 1 pack per thread at 1/8 of C2 per GPU to stay balanced; a first round-2 version kept
-    // 4-pack tiles and masked the remainder -- 13 % of a CTA's rows there -- which was slower still.)
+    // Row walk = one global sweep (lkb_kernels.h "serpentine sweeps"): `nfull` rounds of big tiles (4 packs per thread:
+    // one warp fold per 64 loads), round r covering the band [r, r + 1) * gridDim.x * 1024 packs with one tile per CTA,
+    // then the remainder region split over the CTAs in 32-pack groups (balanced to within ONE group = 512 B for any n)
+    // and walked in 1-pack tiles, only the final < 256 packs of a CTA taking the masked path.  desc = the same tiles in
+    // the opposite order.  (Round 1 split whole tiles and shrank ALL tiles to 1 pack per thread at 1/8 of C2 per GPU to
+    // stay balanced; a first round-2 version kept 4-pack tiles and masked the remainder -- 13 % of a CTA's rows there --
+    // which was slower still.)
     const int64_t npk = n / EPP;
-    const int64_t ngroups = (npk + 31) / 32;
-    const int64_t p0 = (((int64_t)blockIdx.x * ngroups) / gridDim.x) * 32;
-    const int64_t p1 = min(npk, ((((int64_t)blockIdx.x + 1) * ngroups) / gridDim.x) * 32);
+    constexpr int64_t BIG = 4 * MD_THREADS;
+    const int64_t nfull = npk / (BIG * gridDim.x);
+    const int64_t rem0 = nfull * BIG * gridDim.x;
+    const int64_t rgroups = (npk - rem0 + 31) / 32;
+    const int64_t q0 = rem0 + (((int64_t)blockIdx.x * rgroups) / gridDim.x) * 32;
+    const int64_t q1 = min(npk, rem0 + ((((int64_t)blockIdx.x + 1) * rgroups) / gridDim.x) * 32);
     const int nchunk = (j + CB - 1) / CB;
     E accw = zero_v(E());
-    int64_t tb = p0;
-    for (; tb + 4 * MD_THREADS <= p1; tb += 4 * MD_THREADS) md_tile<K, 4, true>(V, ld, j, nchunk, w, tb, p1, myacc, accw, lane, fold_idx);
-    for (; tb + MD_THREADS <= p1; tb += MD_THREADS) md_tile<K, 1, true>(V, ld, j, nchunk, w, tb, p1, myacc, accw, lane, fold_idx);
-    if (tb < p1) md_tile<K, 1, false>(V, ld, j, nchunk, w, tb, p1, myacc, accw, lane, fold_idx);
+    auto remainder = [&]() {
+        int64_t tb = q0;
+        for (; tb + MD_THREADS <= q1; tb += MD_THREADS) md_tile<K, 1, true>(V, ld, j, nchunk, w, tb, q1, myacc, accw, lane, fold_idx);
+        if (tb < q1) md_tile<K, 1, false>(V, ld, j, nchunk, w, tb, q1, myacc, accw, lane, fold_idx);
+    };
+    if (!desc) {
+        for (int64_t r = 0; r < nfull; ++r)
+            md_tile<K, 4, true>(V, ld, j, nchunk, w, (r * gridDim.x + blockIdx.x) * BIG, npk, myacc, accw, lane, fold_idx);
+        remainder();
+    } else {
+        remainder();
+        for (int64_t r = nfull - 1; r >= 0; --r)
+            md_tile<K, 4, true>(V, ld, j, nchunk, w, (r * gridDim.x + blockIdx.x) * BIG, npk, myacc, accw, lane, fold_idx);
+    }
     // ragged tail (n not a multiple of the pack width): one thread of CTA 0
     __syncwarp();
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -523,7 +538,7 @@ __global__ void __launch_bounds__(256, 2)
 k_multiaxpy_fin(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j,
                 const typename Tr<K>::W* __restrict__ c, typename Tr<K>::E* __restrict__ w, int64_t n,
                 double* __restrict__ partial, typename Tr<K>::W* __restrict__ nrm2_out,
-                unsigned* __restrict__ counter, const FinParams fp, const P2P p2p, const HaloP2P hp)
+                unsigned* __restrict__ counter, const FinParams fp, const P2P p2p, const HaloP2P hp, const int desc)
 {
     using E = typename Tr<K>::E;
     using W = typename Tr<K>::W;
@@ -573,9 +588,27 @@ k_multiaxpy_fin(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j,
     const int64_t hi0 = n - hp.he;
     ktime_cta(p2p, 0);
 
+    // Row walk = one global sweep in time (lkb_kernels.h "serpentine sweeps").  The grid is two waves of CTAs (the second
+    // wave is picked up by whichever SMs finish first: dynamic balance); the CTAs of the first wave (low blockIdx) stride
+    // over the half of the rows the sweep visits first, those of the second wave over the other half.
     const int64_t npk = n / EPP;
     double nrm = 0.0;
-    for (int64_t pk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pk < npk; pk += (int64_t)gridDim.x * blockDim.x) {
+    int64_t h0 = 0, h1 = npk;
+    int idx = (int)blockIdx.x, cnt = (int)gridDim.x;
+    if (gridDim.x >= 2) {
+        const int half = ((int)gridDim.x + 1) / 2;
+        const bool second = (int)blockIdx.x >= half;
+        const int64_t mid = min(npk, ((npk / 2) + 31) / 32 * 32);
+        const bool upper = (second != (desc != 0));             // which half of the rows this CTA strides over
+        h0 = upper ? mid : 0; h1 = upper ? npk : mid;
+        idx = second ? (int)blockIdx.x - half : (int)blockIdx.x;
+        cnt = second ? (int)gridDim.x - half : half;
+    }
+    const int64_t stride1 = (int64_t)cnt * blockDim.x;
+    const int64_t first1 = h0 + (int64_t)idx * blockDim.x + threadIdx.x;
+    const int64_t nit1 = first1 < h1 ? (h1 - first1 + stride1 - 1) / stride1 : 0;
+    for (int64_t it = 0; it < nit1; ++it) {
+        const int64_t pk = first1 + (desc ? nit1 - 1 - it : it) * stride1;
         const int64_t off = pk * EPP;
         P a = ld_pack<P>(w + off);
         const E* vp = V + off;
@@ -708,7 +741,7 @@ static void multidot_t(cudaStream_t s, const void* V, int64_t ld, int j, const v
     const size_t sh = (size_t)(MD_THREADS / 32) * (size_t)(j + 1) * sizeof(W);
     static const SmemAttrOnce attr((const void*)k_multidot<K>, 160 * 1024);
     attr.ensure();
-    launch_ex(k_multidot<K>, (unsigned)nb, MD_THREADS, sh, s, pdl_take(2), (const E*)V, ld, j, (const E*)w, n, (W*)partial, (W*)out, counter, flags, pp);
+    launch_ex(k_multidot<K>, (unsigned)nb, MD_THREADS, sh, s, pdl_take(2), (const E*)V, ld, j, (const E*)w, n, (W*)partial, (W*)out, counter, flags, pp, sweep_dir());
 }
 void launch_multidot(int kind, cudaStream_t s, const void* V, int64_t ld, int j, const void* w, int64_t n,
                      void* partial, void* out, unsigned* counter, const int* flags, int sms, const P2P* p2p) {
@@ -764,7 +797,7 @@ static void multiaxpy_fin_t(cudaStream_t s, const void* V, int64_t ld, int j, co
     fp.c1 = c1; fp.hcol = hcol; fp.tol = tol; fp.atol = atol; fp.inv_dev = (double*)inv_dev; fp.flags = flags;
     fp.kstep = kstep; fp.mode = mode;
     launch_ex(k_multiaxpy_fin<K>, (unsigned)nb, 256, sh, s, pdl_take(8), (const E*)V, ld, j, (const W*)c2, (E*)w, n, (double*)partial,
-              (W*)nrm2_out, counter, fp, p2p ? *p2p : P2P(), hp ? *hp : HaloP2P());
+              (W*)nrm2_out, counter, fp, p2p ? *p2p : P2P(), hp ? *hp : HaloP2P(), sweep_dir());
 }
 void launch_multiaxpy_fin(int kind, cudaStream_t s, const void* V, int64_t ld, int j, const void* c1, const void* c2, void* w,
                           int64_t n, void* partial, void* nrm2_out, unsigned* counter, void* hcol, double tol, double atol,

@@ -129,6 +129,7 @@ int allreduce_w(lkb_ctx_s* c, void* buf, size_t ndoubles) {
     return 0;
 }
 int& pdl_state() { static thread_local int s = 0; return s; }
+int& sweep_dir() { static thread_local int d = 0; return d; }
 // Which kernel classes are launched programmatically (bits: 1 matvec, 2 multi-dot, 4 fused axpy+dot, 8 multi-axpy, 16 scale).
 // Default 4: only the TMA kernel.  Measured on B200 (profiles/r02_pdl2.sh .. r02_pdl4.sh): a programmatically launched
 // kernel inherits the predecessor's L1 / shared-memory carve-out, which costs the LDG-based multi-dot / multi-axpy
@@ -334,6 +335,7 @@ int lkb_set_option(lkb_ctx_t c, const char* name, int value) {
     else if (!strcmp(name, "fused")) c->fused = value != 0;
     else if (!strcmp(name, "fin")) c->fin = value != 0;
     else if (!strcmp(name, "pdl")) c->pdl = value != 0;
+    else if (!strcmp(name, "serpentine")) c->serpentine = value != 0;
     else if (!strcmp(name, "write_intermediate")) c->write_intermediate = value != 0;
     else if (!strcmp(name, "csr_slice_kb")) c->csr_slice_kb = value;            // 0 disables the L2 blocking
     else if (!strcmp(name, "csr_block_min_kb")) c->csr_block_min_kb = value;

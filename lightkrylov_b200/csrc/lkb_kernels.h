@@ -64,6 +64,18 @@ struct PdlScope {
     explicit PdlScope(bool on) : prev(pdl_state()) { pdl_state() = on ? 1 : 0; }
     ~PdlScope() { pdl_state() = prev; }
 };
+// ---- serpentine sweeps (L2 reuse between consecutive kernels of a step) ---------------------------------------------
+// The three Gram-Schmidt kernels of a step each stream V(:, 0:j) once.  All of them walk the rows as ONE global sweep
+// (at any time every CTA works inside the same narrow band of rows), and consecutive kernels sweep in opposite
+// directions: a kernel starts on the rows its predecessor read last, which are still L2-resident (126 MB L2: ~10 % of
+// a kernel's bytes at the per-GPU share of N = 8, ~1 % at N = 1).  The direction is a pure function of the step index
+// (dgs_enqueue), so results stay bitwise reproducible (graphs on / off, one-shot vs step-by-step, any launch timing).
+int& sweep_dir();      // 0 ascending, 1 descending: read by launch_multidot / launch_axpy_dot / launch_multiaxpy_fin
+struct SweepDir {
+    int prev;
+    explicit SweepDir(int d) : prev(sweep_dir()) { sweep_dir() = d; }
+    ~SweepDir() { sweep_dir() = prev; }
+};
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_ex(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, bool pdl, Args&&... args) {
     cudaLaunchConfig_t cfg = {};

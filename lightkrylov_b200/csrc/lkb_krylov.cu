@@ -27,9 +27,13 @@ int dgs_enqueue(lkb_ctx_s* c, int kind, const void* V, int64_t ld, int j, void* 
     LKB_TRY(ensure_ws(c, j + 1));
     const size_t nd = (size_t)(j + 1) * (kind_cplx(kind) ? 2 : 1);
     const size_t wsz = kind_cplx(kind) ? 16 : 8;
+    // serpentine sweeps: pass-1 dot, fused middle and final update walk the rows in alternating directions, and the
+    // first direction alternates with the step index (the previous step's final update ended where this one starts)
+    const int d0 = (c->serpentine && fin) ? (fin->kstep & 1) : 0;
+    const int d1 = (c->serpentine && fin) ? 1 - d0 : 0;
     // pass 1 coefficients
     prof_begin(c, PC_DOT);
-    launch_multidot(kind, c->stream, V, ld, j, w, n, c->partial, c->c1, c->counter, flags, c->sms, c->p2p_arg());
+    { SweepDir sd(d0); launch_multidot(kind, c->stream, V, ld, j, w, n, c->partial, c->c1, c->counter, flags, c->sms, c->p2p_arg()); }
     prof_end(c, PC_DOT, 1);
     LKB_TRY(check_launch(c, "multidot"));
     LKB_TRY(allreduce_w(c, c->c1, nd));
@@ -37,7 +41,7 @@ int dgs_enqueue(lkb_ctx_s* c, int kind, const void* V, int64_t ld, int j, void* 
     bool fused = false;
     if (c->fused) {
         prof_begin(c, PC_FUSED);
-        fused = launch_axpy_dot(kind, c->stream, V, ld, j, c->c1, w, n, c->partial, c->c2, c->counter, flags, c->sms, c->p2p_arg());
+        { SweepDir sd(d1); fused = launch_axpy_dot(kind, c->stream, V, ld, j, c->c1, w, n, c->partial, c->c2, c->counter, flags, c->sms, c->p2p_arg()); }
         prof_end(c, PC_FUSED, fused ? 1 : 0);
         if (!fused && c->profile && !c->capturing) { cudaEventDestroy(c->prof_evs.back().a); cudaEventDestroy(c->prof_evs.back().b); c->prof_evs.pop_back(); }
         LKB_TRY(check_launch(c, "axpy_dot"));
@@ -59,6 +63,7 @@ int dgs_enqueue(lkb_ctx_s* c, int kind, const void* V, int64_t ld, int j, void* 
     if (fin) {
         // pass-2 update + predicted-norm normalisation + H/T/B column + (optional) halo push in ONE kernel
         prof_begin(c, PC_AXPY);
+        SweepDir sd(d0);
         launch_multiaxpy_fin(kind, c->stream, V, ld, j, fin->with_c1 ? c->c1 : nullptr, c->c2, w, n, c->partial, c->nrm2, c->counter,
                              fin->hcol, fin->tol, atol_of(kind), c->inv, flags, fin->kstep, fin->mode, c->sms, c->p2p_arg(), fin->hp);
         prof_end(c, PC_AXPY, 1);

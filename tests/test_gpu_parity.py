@@ -303,6 +303,36 @@ def test_programmatic_launch_chain_is_bitwise_neutral(lk, ctx, oracle, kind, pro
         assert out[0][0] == out[1][0] == 3 and np.array_equal(out[0][1], out[1][1])
 
 
+@pytest.mark.parametrize("kind", ["d", "z", "s"])
+def test_serpentine_sweeps_parity_and_determinism(lk, ctx, oracle, kind):
+    """Consecutive Gram-Schmidt kernels of a step sweep the rows in opposite directions (L2 reuse); the direction is a
+    pure function of the step index.  Both settings match the oracle at the parity tolerance, the default is bitwise
+    reproducible run to run and step-by-step == one-shot, and sizes that exercise every branch of the row walks
+    (remainder-only, one big round + remainder, ragged tail) agree with option "serpentine" = 0 to rounding."""
+    dt = lk.DTYPES[kind]; tol = tol_for(kind)
+    for (nx, ny, kdim) in ((64, 37, 12), (1024, 600, 20), (1000, 333, 9)):
+        n = nx * ny
+        A = lk.LinOp.stencil5(ctx, kind, nx, ny, CONVDIFF7[:5]); Ao = oracle.Op.stencil(kind, (nx, ny), CONVDIFF7[:5])
+        x0 = oracle.fill(n, kind, "uniform", 11); oracle.normalize(x0)
+        Xo = np.zeros((n, kdim + 1), dtype=dt, order="F"); Xo[:, 0] = x0; Ho = np.zeros((kdim + 1, kdim), dtype=dt, order="F")
+        assert oracle.arnoldi(Ao, Xo, Ho) == 0
+        out = {}
+        for serp in (1, 0):
+            ctx.set_option("serpentine", serp)
+            X = lk.Basis(ctx, kind, n, kdim + 1).put(x0); H = np.zeros((kdim + 1, kdim), dtype=dt, order="F")
+            assert lk.arnoldi(A, X, H) == 0
+            assert rel_normwise(H, Ho) < tol
+            G = X.get(); G = G.conj().T @ G
+            assert np.abs(G - np.eye(kdim + 1)).max() < (1e-12 if kind in "dz" else 1e-5)
+            out[serp] = (H.copy(), X.get())
+        ctx.set_option("serpentine", 1)
+        X = lk.Basis(ctx, kind, n, kdim + 1).put(x0); H = np.zeros((kdim + 1, kdim), dtype=dt, order="F")
+        for k in range(1, kdim + 1):
+            assert lk.arnoldi(A, X, H, kstart=k, kend=k) == 0
+        assert np.array_equal(H, out[1][0]) and np.array_equal(X.get(), out[1][1])
+        assert rel_normwise(out[0][0], out[1][0]) < tol
+
+
 def test_arnoldi_transpose(lk, ctx, oracle):
     nx, ny, kdim = 64, 64, 20; n = nx * ny
     A = lk.LinOp.stencil5(ctx, "d", nx, ny, CONVDIFF7[:5]); Ao = oracle.Op.stencil("d", (nx, ny), CONVDIFF7[:5])
