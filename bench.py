@@ -361,7 +361,8 @@ def run_ours(args):
         try:   # DRAM bytes of ONE captured launch (j = 101) from the committed ncu capture, with its algorithmic bytes
             import glob
             tf = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))[-1]
-            t = json.load(open(tf)).get({"multidot": "multidot", "multiaxpy": "multiaxpy", "fused_axpy_dot": "axpy_dot"}[dom])
+            tj = json.load(open(tf))
+            t = tj.get({"multidot": "multidot", "multiaxpy": "multiaxpy_fin", "fused_axpy_dot": "axpy_dot"}[dom]) or tj.get(dom)
             if t and world == 1 and (nx, ny) == (4096, 4096):
                 jcap = 101
                 alg = {"multidot": jcap + 1, "multiaxpy": jcap + 2, "fused_axpy_dot": jcap + 2}[dom] * nloc * 8
@@ -422,6 +423,9 @@ def run_ours(args):
                        "partition": f"grid rows over {world} rank(s), {nloc} rows/rank",
                        "l2": "working set 17.3 GB/GPU-share >> 126 MB L2 (inputs larger than L2, no flush needed)",
                        "cuda_graph": True, "fused_cgs2": not args.no_fused,
+                       "step_kernels": "matvec, multi-dot, fused axpy+dot (TMA ring, programmatic launch), final multi-axpy "
+                                       "(predicted norm + normalisation + H column [+ halo push]), gated scale (no-op on the fast path); "
+                                       "serpentine row sweeps, L1::no_allocate streaming loads",
                        "allreduce": ("in-kernel NVLink p2p" if ctx.p2p else "ncclAllReduce") if world > 1 else "none"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps,

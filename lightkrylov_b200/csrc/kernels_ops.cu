@@ -390,11 +390,13 @@ static void stencil_launch(cudaStream_t s, const StencilArgs& a, const void* x, 
     // Measured on B200 (profiles/stencil_ab.py, fp64): 2-D 4096^2 -- shared-memory kernel RY=8 5.64 TB/s vs
     // register march 5.24 TB/s; 3-D 384^3 -- shared-memory kernel 2.1-3.0 TB/s (3RY+2 staged rows per CTA cut
     // the occupancy) vs register march 4.62 TB/s; a z-march with the plane staged in shared memory (two block
-    // barriers per plane) reached only 2.8 TB/s and was dropped.  Default: shared-memory staging in 2-D,
-    // register march in 3-D.
-    static const int variant = getenv("LKB_STENCIL_VARIANT") ? atoi(getenv("LKB_STENCIL_VARIANT")) : (DIM == 2 ? 1 : 4);
+    // barriers per plane) reached only 2.8 TB/s and was dropped; a register z-march (variant 4, k_stencil3d_zmarch) 3.95 TB/s.
+    // Default: shared-memory staging in 2-D, register y-march in 3-D.
+    // 3-D: the z-march (variant 4) measured 3.95 TB/s against 4.32 TB/s for the y-march at 384^3 in three separate runs
+    // (gpurun_out/r02_stencil_ab*.txt) -- the y-march stays the default
+    static const int variant = getenv("LKB_STENCIL_VARIANT") ? atoi(getenv("LKB_STENCIL_VARIANT")) : (DIM == 2 ? 1 : 0);
     if constexpr (DIM == 3) {
-        if (variant == 4) {      // z-march with register planes (default in 3-D since round 2)
+        if (variant == 4) {      // z-march with register planes (A/B only)
             constexpr int LZ = 32;
             const int64_t ncbx = (npk_row + ZT_TX - 1) / ZT_TX, ncby = (a.ny + ZT_TY - 1) / ZT_TY, nzc = (a.nz + LZ - 1) / LZ;
             const unsigned grid = (unsigned)(ncbx * ncby * nzc);

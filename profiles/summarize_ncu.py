@@ -79,6 +79,8 @@ for rep in sorted(glob.glob(os.path.join(ROOT, "profiles", f"{tag}_*_raw.csv")))
         i = hdr.index(m); return float(r[i].replace(",", "")) * UNIT.get(units[i], 1.0)
     traffic[kname] = {"dram_bytes_read": val("dram__bytes_read.sum"), "dram_bytes_write": val("dram__bytes_write.sum"),
                       "duration_s": val("gpu__time_duration.sum"), "grid": r[hdr.index("launch__grid_size")],
-                      "capture": "ncu --set full --clock-control none, launch #100 of the class in bench.py (j = 101)"}
+                      "capture": ("ncu --set full --clock-control none, launch #101 of the class in bench.py (j = 101)"
+                                  if kname in ("multidot", "axpy_dot", "multiaxpy", "multiaxpy_fin", "stencil", "stencil_smem")
+                                  else "ncu --set full --clock-control none, profiles/ncu_targets.py " + kname)}
 json.dump(traffic, open(os.path.join(ROOT, "profiles", f"{tag}_traffic.json"), "w"), indent=1)
 print("\n".join(out_md))
