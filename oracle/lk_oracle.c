@@ -7,10 +7,17 @@
  * It is a plain-C restatement of the reference's per-vector algorithm (see
  * lko_body.inc for the file:line map).  The Fortran reference cannot be compiled in
  * this image (no Fortran compiler, fpm, fypp or stdlib), so there
- * is no oracle/_ref.  Parity pinning: the reference holds no golden vectors; the
- * oracle is pinned by the reference's own property / known-answer assertions
- * (test/TestKrylov.fypp:194-514, test/TestIterativeSolvers.fypp:59-725), which
- * tests/test_oracle_pins.py re-runs against this code.
+ * is no oracle/_ref.
+ *
+ * PARITY UNPINNED against an execution of the reference: the reference holds no golden
+ * vectors or fixtures for this path (its tests are property / known-answer checks on
+ * unseeded random inputs) and it cannot be run here or on the GPU box (both probed:
+ * no gfortran / flang / ifx / nvfortran / fpm / fypp).  What pins the oracle instead:
+ * (1) the reference's own property / known-answer assertions (test/TestKrylov.fypp:194-514,
+ * test/TestIterativeSolvers.fypp:59-725), re-run against this code by
+ * tests/test_oracle_pins.py; (2) an independent evaluation of the Hessenberg entries in
+ * 80-bit extended precision (test_arnoldi_entries_match_extended_precision); (3) line-by-
+ * line citation of the reference sources in lko_body.inc.
  *
  * Build:  make -C oracle      (gcc -O3 -march=native -fopenmp -shared)
  */

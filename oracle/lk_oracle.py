@@ -14,6 +14,10 @@ on top of the C primitives, following
   src/IterativeSolvers/EIGHS/eighs.fypp:29-126
   src/IterativeSolvers/SVDS/svd_solvers.fypp:28-121
   src/Utilities/submodule_utility_functions.fypp:55-117, 169-204
+
+PARITY UNPINNED against an execution of the reference (no Fortran toolchain here or on the GPU box, no golden vectors
+in the reference): pinned by the reference's own property / known-answer assertions and by an independent
+extended-precision evaluation instead (tests/test_oracle_pins.py); see the header of lk_oracle.c and DESIGN.md section 4.
 """
 from __future__ import annotations
 
