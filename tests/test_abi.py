@@ -59,7 +59,8 @@ def test_product_never_imports_oracle():
 
 
 def test_sass_has_128bit_loads(so_path):
-    """The GS kernels must move data with 128-bit loads (LDG.E.128), checked on the built cubin."""
+    """The GS kernels must move data with 128-bit loads, checked on the built cubin: LDG.E.NA.128[.CONSTANT] since round 2
+    (NA = L1::no_allocate streaming loads), LDG.E.128 before."""
     import shutil, subprocess
     if not shutil.which("cuobjdump"):
         pytest.skip("cuobjdump not available")
@@ -69,7 +70,9 @@ def test_sass_has_128bit_loads(so_path):
     for fn in ("k_multidot", "k_multiaxpy"):
         chunks = [c for c in out.split("Function : ")[1:] if fn in c.split("\n", 1)[0]]
         assert chunks, fn
-        assert all("LDG.E.128" in c for c in chunks), fn
+        assert all(("LDG.E.NA.128" in c) or ("LDG.E.128" in c) for c in chunks), fn
+    assert "LDG.E.NA.128.CONSTANT" in out          # the streaming loads do not allocate in L1
+    assert "ACQBULK" in out and "PREEXIT" in out   # griddepcontrol.wait / launch_dependents (programmatic dependent launch)
 
 
 def _build_c_demo(so_path, tmp_path):
