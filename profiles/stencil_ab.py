@@ -8,7 +8,8 @@ if len(sys.argv) > 1:
     ext = torch.cuda.ExternalStream(ctx.stream)
     out = {}
     for name, mk, n in (("2d_4096", lambda: lk.LinOp.stencil5(ctx, "d", 4096, 4096, (4., -1., -1., -1., -1.)), 4096 * 4096),
-                        ("3d_384", lambda: lk.LinOp.stencil7(ctx, "d", 384, 384, 384, (6., -1., -1., -1., -1., -1., -1.)), 384 ** 3)):
+                        ("3d_384", lambda: lk.LinOp.stencil7(ctx, "d", 384, 384, 384, (6., -1., -1., -1., -1., -1., -1.)), 384 ** 3),
+                        ("3d_512", lambda: lk.LinOp.stencil7(ctx, "d", 512, 512, 512, (6., -1.3, -0.7, -1.2, -0.8, -1.1, -0.9)), 512 ** 3)):
         A = mk(); x = lk.Vector(ctx, "d", n).fill_random("uniform", 1); y = lk.Vector(ctx, "d", n)
         for _ in range(5): A.matvec(x, y)
         ctx.sync()
