@@ -704,8 +704,11 @@ void launch_csr_blocked(int kind, cudaStream_t s, const CsrBlocked& b, const voi
     //   2  thread-per-row, streams evict_normal   16.4   (default)
     //   1  CSR-stream                             19.5   DRAM 4.9 GB / block (x misses 0.9 GB) but latency-bound at 64 regs,
     //                                                    4 CTAs / SM; forcing 5-6 CTAs / SM spills and doubles the time
-    // A persisting-L2 set-aside (cudaLimitPersistingL2CacheSize 64 / 79 MB) changed none of them by more than 2 %.
-    static const int variant = getenv("LKB_CSR_BLOCKED_VARIANT") ? atoi(getenv("LKB_CSR_BLOCKED_VARIANT")) : 2;
+    //   3  warp-pipelined CSR-stream (cp.async-staged col / val per warp, no block barrier; removed again)   20.7
+    // All stream forms land at 19-21 ms whatever hides the col / val latency: the L2 gather rate (~100 G sectors/s), not the
+    // streams, is what they wait for.  A persisting-L2 set-aside (64 / 79 MB) changed none of them by more than 2 %.
+    static const int env_variant = getenv("LKB_CSR_BLOCKED_VARIANT") ? atoi(getenv("LKB_CSR_BLOCKED_VARIANT")) : -1;
+    const int variant = env_variant >= 0 ? env_variant : b.variant;
     if (variant == 1) {
         static const int cfg = getenv("LKB_CSR_STREAM_CFG") ? atoi(getenv("LKB_CSR_STREAM_CFG")) : 0;
         int64_t nbs = (b.rows + CS_ROWS - 1) / CS_ROWS;

@@ -339,6 +339,7 @@ int lkb_set_option(lkb_ctx_t c, const char* name, int value) {
     else if (!strcmp(name, "write_intermediate")) c->write_intermediate = value != 0;
     else if (!strcmp(name, "csr_slice_kb")) c->csr_slice_kb = value;            // 0 disables the L2 blocking
     else if (!strcmp(name, "csr_block_min_kb")) c->csr_block_min_kb = value;
+    else if (!strcmp(name, "csr_blocked_variant")) c->csr_variant = value;
     else if (!strcmp(name, "fused_halo")) c->fused_halo = value != 0;
     else if (!strcmp(name, "p2p")) c->p2p_active = (value != 0) && c->p2p.world > 1;
     else { set_error("unknown option %s", name); return LKB_ERR_ARG; }

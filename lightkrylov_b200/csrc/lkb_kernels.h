@@ -177,6 +177,7 @@ void launch_narrow(int kind, cudaStream_t s, const void* src, void* dst, int n, 
 // L2-blocked CSR (lkb_csr.cu): non-zeros sorted by column block; tab[b * (rows + 1) + r] = first entry of (block b, row r)
 struct CsrBlocked {
     int nb = 0; int64_t cw = 0, rows = 0, nnz = 0;
+    int variant = 2;           // kernel: 2 thread-per-row (default), 0 same with evict_first streams, 1 CSR-stream (kernels_ops.cu)
     uint32_t* tab = nullptr; int32_t* col = nullptr; void* val = nullptr;
 };
 // y = A x over the blocked layout: one sweep per column block, y accumulated across the blocks

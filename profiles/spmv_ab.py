@@ -36,7 +36,7 @@ if os.environ.get("SPMV_AB_CHILD"):
 else:
     scale = sys.argv[1] if len(sys.argv) > 1 else "1.0"
     slices = sys.argv[2:] or ["48"]
-    for v, cfg in (("0", "0"), ("2", "0"), ("1", "0")):
+    for v, cfg in (("2", "0"), ("1", "0"), ("3", "0")):
         env = dict(os.environ, LKB_CSR_BLOCKED_VARIANT=v, LKB_CSR_STREAM_CFG=cfg, SPMV_AB_CHILD="1")
         print("variant", v, "stream cfg", cfg, flush=True)
         subprocess.run([sys.executable, __file__, scale] + slices, env=env)

@@ -896,8 +896,12 @@ def test_csr_l2_blocked_layout_matches_plain(lk, ctx, oracle, kind):
     xh = oracle.fill(n, kind, "normal", 3); uh = oracle.fill(m, kind, "normal", 4)
     x = lk.Vector(ctx, kind, n).put(xh); u = lk.Vector(ctx, kind, m).put(uh)
     res = {}
-    for blocked in (1, 0):
-        ctx.set_option("csr_slice_kb", 8 if blocked else 0)          # 8 KB slices: 512-2048 columns per block
+    for blocked in (3, 2, 1, 0):
+        # blocked = 3: the CSR-stream kernel variant (kept for A/B), 64 KB slices
+        ctx.set_option("csr_blocked_variant", 1 if blocked == 3 else 2)
+        # 8 KB slices: 512-2048 columns per block (~1 entry per row and block); 64 KB slices: 2-4 blocks with 3-6 entries per
+        # row and block (runs longer than the staging buffer of the pipelined kernel)
+        ctx.set_option("csr_slice_kb", {3: 64, 2: 64, 1: 8, 0: 0}[blocked])
         ctx.set_option("csr_block_min_kb", 0)
         A = lk.LinOp.csr(ctx, m, n, rp, ci, va)
         y = lk.Vector(ctx, kind, m).put(np.full(m, np.nan, dtype=dt)); v = lk.Vector(ctx, kind, n).put(np.full(n, np.nan, dtype=dt))
@@ -905,7 +909,7 @@ def test_csr_l2_blocked_layout_matches_plain(lk, ctx, oracle, kind):
         res[blocked] = (y.get(), v.get())
         if blocked:
             y2 = lk.Vector(ctx, kind, m); A.matvec(x, y2)
-            assert np.array_equal(y2.get(), res[1][0])                  # deterministic
+            assert np.array_equal(y2.get(), res[blocked][0])            # deterministic
             kd = 12
             U = lk.Basis(ctx, kind, m, kd + 1); V = lk.Basis(ctx, kind, n, kd + 1)
             u0 = U.col(0).fill_random("normal", 47); u0.scal(1.0 / u0.norm())
@@ -917,6 +921,6 @@ def test_csr_l2_blocked_layout_matches_plain(lk, ctx, oracle, kind):
             assert rel_normwise(B, Bo) < tol_for(kind)
     ctx.set_option("csr_slice_kb", 48 * 1024); ctx.set_option("csr_block_min_kb", 96 * 1024)
     tol = dict(rtol=1e-4, atol=1e-4) if kind == "s" else dict(rtol=1e-11, atol=1e-11)
-    for blocked in (1, 0):
+    for blocked in (3, 2, 1, 0):
         np.testing.assert_allclose(res[blocked][0], Ao.apply(xh), **tol)
         np.testing.assert_allclose(res[blocked][1], Ao.apply(uh, trans=True), **tol)
