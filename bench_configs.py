@@ -6,7 +6,7 @@ These are NOT the headline bench lines (bench.py measures configs[1]); they show
 the hot path working at (or near) the named sizes and report steps/s plus achieved GB/s against
 the official per-step algorithmic bytes.  One JSON line per config.
 
-    python bench_configs.py [--full] [--only c2,c3,c4,c5]
+    python bench_configs.py [--full] [--only c2,c2b,c3,c4,c5]
 """
 from __future__ import annotations
 
@@ -65,6 +65,34 @@ def c2_gmres(ctx, full):
          final_residual=rn, res_first=meta["res"][0], res_last=meta["res"][-1],
          res_history_sha=__import__("hashlib").sha1(np.asarray(meta["res"]).tobytes()).hexdigest()[:12],
          res_every_50=[float(v) for v in meta["res"][::50]])
+
+
+def c2_block(ctx, full):
+    """Block Arnoldi (blksize = 2, 4) on the C2 operator: 129-132 basis columns as in the headline config.
+    Official bytes per block step with j = k p existing vectors: p matvecs + 4 j n s per block COLUMN (the reference's
+    innerprod_matrix / linear_combination_matrix re-read X for every column of Y) + the in-block QR."""
+    nx = ny = 4096 if full else 2048
+    n = nx * ny
+    A = lk.LinOp.stencil5(ctx, "d", nx, ny, POISSON5)
+    if ctx.world > 1:
+        return
+    for p, kdim in ((2, 64), (4, 32)):
+        X = lk.Basis(ctx, "d", n, (kdim + 1) * p)
+        for i in range(p):
+            X.col(i).fill_random("uniform", 42 + i)
+        X.orthonormalize(0, p)
+        H = np.zeros(((kdim + 1) * p, kdim * p), order="F")
+        lk.arnoldi(A, X, H, blksize=p, kend=2)                                   # warm-up
+        (info, dt) = timed(ctx, lambda: lk.arnoldi(A, X, H, blksize=p))
+        byts = sum(p * 2 * n * 8 + p * 4 * (k * p) * n * 8 for k in range(1, kdim + 1))
+        actual = sum(p * 2 * n * 8 + (p // 2) * 4 * (k * p + 2) * n * 8 for k in range(1, kdim + 1))
+        G = X.innerprod((kdim + 1) * p, X, wcol0=(kdim + 1) * p - 4, p=4)
+        E = np.eye((kdim + 1) * p)[:, -4:]
+        emit(config="C2 block arnoldi(blksize=%d, kdim=%d) 5-pt Poisson %dx%d fp64" % (p, kdim, nx, ny), info=int(info), seconds=dt,
+             block_steps_per_s=kdim / dt, vectors_per_s=kdim * p / dt, official_GBps=byts / dt / 1e9,
+             frac_of_measured_hbm_official=byts / dt / 1e9 / PEAK, sweep_GBps=actual / dt / 1e9,
+             orth_err_last4=float(np.abs(G - E).max()), H_block_hessenberg=bool(np.abs(np.tril(H, -p - 1)).max() == 0.0))
+        del X
 
 
 def c3_eigs(ctx, full):
@@ -134,6 +162,8 @@ def c5_svds(ctx, full):
     m, n = (50_000_000, 40_000_000) if full else (5_000_000, 4_000_000)
     per_row = 32
     lk.set_lapack_from_scipy()
+    if ctx.world > 1:
+        return c5_sharded(ctx, m, n, per_row)
     t0 = time.perf_counter()
     A = lk.LinOp.csr_random(ctx, "z", m, n, per_row, 46)
     ctx.sync()
@@ -191,10 +221,57 @@ def c5_svds(ctx, full):
          S0_over_edge=float(S[0] / mp_edge))
 
 
+def c5_sharded(ctx, m, n, per_row):
+    """Config 5 row-sharded over the ranks (lkb_op_csr_create_dist_device): every rank generates, transposes and L2-blocks its
+    row block on its own GPU; matvec gathers x over NVLink (grouped ncclBroadcast), rmatvec reduces A_loc^H u_loc onto the
+    owners (grouped ncclReduce)."""
+    t0 = time.perf_counter()
+    A = lk.LinOp.csr_random_dist(ctx, "z", m, n, per_row, 46)
+    ctx.sync()
+    tgen = time.perf_counter() - t0
+    r0, ml = lk.partition(m, ctx.world, ctx.rank); c0, nl = lk.partition(n, ctx.world, ctx.rank)
+    nnz, es = m * per_row, 16
+    spmv = nnz * (es + 4) + 8 * (m + 1) + (n + m) * es
+    x = lk.Vector(ctx, "z", nl, n_global=n, row0=c0).fill_random("normal", 1)
+    y = lk.Vector(ctx, "z", ml, n_global=m, row0=r0).fill_random("normal", 2)
+    rates = {}
+    for name, fn in (("matvec", lambda: A.matvec(x, y)), ("rmatvec", lambda: A.rmatvec(y, x))):
+        fn(); ctx.sync()
+        t1 = time.perf_counter()
+        for _ in range(10):
+            fn()
+        ctx.sync()
+        rates[name] = spmv / ((time.perf_counter() - t1) / 10) / 1e9
+    del x, y
+    kdim, nsv = 32, 8
+    U = lk.Basis(ctx, "z", ml, kdim + 1, n_global=m, row0=r0); V = lk.Basis(ctx, "z", nl, kdim + 1, n_global=n, row0=c0)
+    u0 = U.col(0).fill_random("normal", 47); u0.scal(1.0 / u0.norm())
+    B = np.zeros((kdim + 1, kdim), dtype=np.complex128, order="F")
+    lk.bidiagonalization(A, U, V, B)
+    (info, dt) = timed(ctx, lambda: lk.bidiagonalization(A, U, V, B))
+    byts = sum(2 * spmv + 4 * (k - 1) * n * es + 4 * k * m * es for k in range(1, kdim + 1))
+    Gu = U.innerprod(kdim + 1, U, wcol0=0, p=4); Gv = V.innerprod(kdim, V, wcol0=0, p=4)
+    orth = float(max(np.abs(Gu - np.eye(kdim + 1)[:, :4]).max(), np.abs(Gv - np.eye(kdim)[:, :4]).max()))
+    del U, V
+    Us = lk.Basis(ctx, "z", ml, nsv, n_global=m, row0=r0); Vs = lk.Basis(ctx, "z", nl, nsv, n_global=n, row0=c0)
+    u0 = lk.Vector(ctx, "z", ml, n_global=m, row0=r0).fill_random("normal", 47)
+    (res, dts) = timed(ctx, lambda: lk.svds(A, Us, Vs, nsv, u0=u0, kdim=32, tolerance=1e-6))
+    S, resid, sinfo = res
+    if ctx.rank != 0:
+        return
+    emit(config="C5 bidiagonalization(kdim=32) random CSR %dx%d, 32 nnz/row, cdp, row-sharded over %d GPU(s)" % (m, n, ctx.world),
+         info=int(info), seconds=dt, steps_per_s=kdim / dt, alg_GBps_total=byts / dt / 1e9,
+         device_generation_transpose_blocking_s=tgen, spmv_alg_GBps_total=rates, nnz=nnz,
+         B_diag_first=[float(abs(B[i, i])) for i in range(4)], orth_err_first4=orth,
+         B_off_band_max=float(np.abs(np.triu(B, 1)).max() + np.abs(np.tril(B, -2)).max()))
+    emit(config="C5 svds(nsv=8, kdim=32), row-sharded over %d GPU(s)" % ctx.world, info_k=int(sinfo), seconds=dts,
+         S=[float(v) for v in S], residuals=[float(r) for r in resid])
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true", help="BASELINE.json sizes (C3 512^3, C4 384^3, C5 50Mx40M)")
-    ap.add_argument("--only", default="c2,c3,c4,c5")
+    ap.add_argument("--only", default="c2,c2b,c3,c4,c5")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:                                   # torchrun: only the sharded config (C3) is meaningful
@@ -204,10 +281,10 @@ def main():
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         ctx = lk.Context.from_torch_distributed(local)
-        args.only = ",".join(c for c in args.only.split(",") if c in ("c2", "c3"))      # the row-sharded configs
+        args.only = ",".join(c for c in args.only.split(",") if c in ("c2", "c3", "c5"))      # the row-sharded configs
     else:
         ctx = lk.Context(0)
-    for name, fn in (("c2", c2_gmres), ("c3", c3_eigs), ("c4", c4_sym), ("c5", c5_svds)):
+    for name, fn in (("c2", c2_gmres), ("c2b", c2_block), ("c3", c3_eigs), ("c4", c4_sym), ("c5", c5_svds)):
         if name in args.only.split(","):
             try:
                 fn(ctx, args.full)

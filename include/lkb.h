@@ -137,6 +137,12 @@ int lkb_op_csr_create_device(lkb_ctx_t ctx, int kind, int64_t m, int64_t n, int6
 int lkb_op_csr_create_dist(lkb_ctx_t ctx, int kind, int64_t m_global, int64_t n_global, int64_t row0, int64_t m_local,
                            int64_t col0, int64_t n_local, const int64_t* rowptr_local, const int32_t* col_global,
                            const void* val, lkb_op_t* A);
+/* The same from local CSR arrays that already live on this GPU (cudaMalloc'ed, e.g. lkb_csr_random_device); the library
+ * takes ownership (adopt must be non-zero; on failure the arrays stay with the caller).  Lets BASELINE config 5
+ * (1.6e9 non-zeros) be built row-sharded without ever touching the host. */
+int lkb_op_csr_create_dist_device(lkb_ctx_t ctx, int kind, int64_t m_global, int64_t n_global, int64_t row0, int64_t m_local,
+                                  int64_t col0, int64_t n_local, int64_t* rowptr_dev, int32_t* col_dev, void* val_dev,
+                                  int32_t adopt, lkb_op_t* A);
 int lkb_op_dense_create(lkb_ctx_t ctx, int kind, int64_t m, int64_t n, const void* a_colmajor, lkb_op_t* A);
 /* user-supplied device matvec (a Fortran/C extension of abstract_linop): fn launches on `stream` */
 typedef int (*lkb_matvec_fn)(void* user, const void* x_dev, void* y_dev, int32_t trans, void* stream);

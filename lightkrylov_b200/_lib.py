@@ -91,6 +91,7 @@ SIGNATURES = {
     "lkb_csr_random_device": (_i, [_vp, _i, _i64, _i64, _i64, _i32, _u64, _P(_vp), _P(_vp), _P(_vp)]),
     "lkb_dev_free": (_i, [_vp]),
     "lkb_op_csr_create_dist": (_i, [_vp, _i, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _P(_vp)]),
+    "lkb_op_csr_create_dist_device": (_i, [_vp, _i, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _i32, _P(_vp)]),
     "lkb_op_dense_create": (_i, [_vp, _i, _i64, _i64, _vp, _P(_vp)]),
     "lkb_op_callback_create": (_i, [_vp, _i, _i64, _i64, MATVEC_FN, _vp, _i32, _P(_vp)]),
     "lkb_op_destroy": (_i, [_vp]),

@@ -371,6 +371,26 @@ class LinOp:
         return op
 
     @classmethod
+    def csr_random_dist(cls, ctx: Context, kind: str, m: int, n: int, per_row: int, seed: int) -> "LinOp":
+        """The config-5 matrix ROW-SHARDED over the ranks of ctx: every rank generates its row block on its own GPU
+        (same counter RNG keyed on the global row, so the global matrix equals `csr_random`'s) and hands it to
+        lkb_op_csr_create_dist_device.  Collective."""
+        r0, ml = partition(m, ctx.world, ctx.rank)
+        c0, nl = partition(n, ctx.world, ctx.rank)
+        rp, ci, va = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(ctx.lib.lkb_csr_random_device(ctx.h, KINDS[kind], ml, r0, n, per_row, seed, C.byref(rp), C.byref(ci), C.byref(va)), "csr_random")
+        h = C.c_void_p()
+        rc = ctx.lib.lkb_op_csr_create_dist_device(ctx.h, KINDS[kind], m, n, r0, ml, c0, nl, rp, ci, va, 1, C.byref(h))
+        if rc != 0:
+            for ptr in (rp, ci, va):
+                ctx.lib.lkb_dev_free(ptr)
+            check(rc, "csr_create_dist_device")
+        op = cls(ctx, kind, h, ml, nl)
+        op.row0, op.n_global = c0, n
+        op.out_row0, op.m_global = r0, m
+        return op
+
+    @classmethod
     def csr_dist(cls, ctx: Context, m: int, n: int, rowptr_local, col_global, val, row_slab=None, col_slab=None) -> "LinOp":
         """Row-sharded CSR: this rank passes ITS rows (local rowptr, global column indices).  Collective."""
         kind = kind_of(val.dtype)

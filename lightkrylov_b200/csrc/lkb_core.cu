@@ -697,17 +697,9 @@ int lkb_op_stencil7_create(lkb_ctx_t c, int kind, int64_t nx, int64_t ny, int64_
 //   matvec : all ranks' slabs of x are gathered into a full-length buffer (grouped ncclBroadcast, ragged slabs
 //            allowed), then the local SpMV runs;   rmatvec: the local A_loc^H u_loc contributes to all n_global
 //            entries, each slab is summed onto its owner (grouped ncclReduce).  Creation is collective.
-int lkb_op_csr_create_dist(lkb_ctx_t c, int kind, int64_t m_global, int64_t n_global, int64_t row0, int64_t m_local,
-                           int64_t col0, int64_t n_local, const int64_t* rowptr_local, const int32_t* col_global,
-                           const void* val, lkb_op_t* A) {
-    if (!c || !A || !rowptr_local || m_local < 0 || n_local < 0 || m_global < 1 || n_global < 1) return LKB_ERR_ARG;
-    cudaSetDevice(c->dev);
+// slab bookkeeping + gather / reduce buffers of a row-sharded CSR operator whose local arrays are already in place
+static int csr_dist_finish(lkb_ctx_t c, lkb_op_s* op, int kind, int64_t n_global, int64_t row0, int64_t m_local, int64_t col0, int64_t n_local) {
     const size_t es = kind_size(kind);
-    lkb_op_s* op = new lkb_op_s();
-    op->ctx = c; op->type = 3; op->kind = kind; op->m = m_local; op->n = n_local; op->uid = next_uid();
-    op->dist = true; op->m_global = m_global; op->n_global = n_global;
-    int r = csr_build(c, op, kind, m_local, n_global, rowptr_local, col_global, val);
-    if (r) { lkb_op_destroy(op); return r; }
     // every rank's slab of the column and row spaces
     const int W = c->world;
     op->col_off.assign(W, 0); op->col_cnt.assign(W, 0); op->row_off.assign(W, 0); op->row_cnt.assign(W, 0);
@@ -715,7 +707,7 @@ int lkb_op_csr_create_dist(lkb_ctx_t c, int kind, int64_t m_global, int64_t n_gl
         op->col_off[0] = col0; op->col_cnt[0] = n_local; op->row_off[0] = row0; op->row_cnt[0] = m_local;
     } else {
         NcclApi* api = nccl_api();
-        if (!api) { lkb_op_destroy(op); return LKB_ERR_NCCL; }
+        if (!api) return LKB_ERR_NCCL;
         void* dbuf = nullptr;
         const int64_t mine[4] = {col0, n_local, row0, m_local};
         std::vector<int64_t> all(4 * (size_t)W);
@@ -725,14 +717,49 @@ int lkb_op_csr_create_dist(lkb_ctx_t c, int kind, int64_t m_global, int64_t n_gl
                   cudaMemcpyAsync(all.data(), dbuf, 32 * (size_t)W, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess &&
                   cudaStreamSynchronize(c->stream) == cudaSuccess;
         if (dbuf) cudaFree(dbuf);
-        if (!ok) { set_error("csr_create_dist: slab exchange failed"); lkb_op_destroy(op); return LKB_ERR_NCCL; }
+        if (!ok) { set_error("csr_create_dist: slab exchange failed"); return LKB_ERR_NCCL; }
         for (int q = 0; q < W; ++q) { op->col_off[q] = all[4 * q]; op->col_cnt[q] = all[4 * q + 1]; op->row_off[q] = all[4 * q + 2]; op->row_cnt[q] = all[4 * q + 3]; }
     }
     if (cudaMalloc(&op->x_full, std::max<size_t>((size_t)n_global * es, 16)) != cudaSuccess ||
         cudaMalloc(&op->y_full, std::max<size_t>((size_t)n_global * es, 16)) != cudaSuccess ||
         cudaMalloc(&op->y_red, std::max<size_t>((size_t)n_local * es, 16)) != cudaSuccess) {
         set_error("csr_create_dist: cudaMalloc of the gather / reduce buffers failed"); cudaGetLastError();
-        lkb_op_destroy(op); return LKB_ERR_ALLOC;
+        return LKB_ERR_ALLOC;
+    }
+    return 0;
+}
+int lkb_op_csr_create_dist(lkb_ctx_t c, int kind, int64_t m_global, int64_t n_global, int64_t row0, int64_t m_local,
+                           int64_t col0, int64_t n_local, const int64_t* rowptr_local, const int32_t* col_global,
+                           const void* val, lkb_op_t* A) {
+    if (!c || !A || !rowptr_local || m_local < 0 || n_local < 0 || m_global < 1 || n_global < 1) return LKB_ERR_ARG;
+    cudaSetDevice(c->dev);
+    lkb_op_s* op = new lkb_op_s();
+    op->ctx = c; op->type = 3; op->kind = kind; op->m = m_local; op->n = n_local; op->uid = next_uid();
+    op->dist = true; op->m_global = m_global; op->n_global = n_global;
+    int r = csr_build(c, op, kind, m_local, n_global, rowptr_local, col_global, val);
+    if (r == 0) r = csr_dist_finish(c, op, kind, n_global, row0, m_local, col0, n_local);
+    if (r) { lkb_op_destroy(op); return r; }
+    *A = op;
+    return 0;
+}
+// The same from local CSR arrays that already live on this GPU (e.g. lkb_csr_random_device); adopt as in lkb_op_csr_create_device.
+int lkb_op_csr_create_dist_device(lkb_ctx_t c, int kind, int64_t m_global, int64_t n_global, int64_t row0, int64_t m_local,
+                                  int64_t col0, int64_t n_local, int64_t* rowptr_dev, int32_t* col_dev, void* val_dev,
+                                  int32_t adopt, lkb_op_t* A) {
+    if (!c || !A || !rowptr_dev || !col_dev || !val_dev || m_local < 1 || n_local < 0 || m_global < 1 || n_global < 1 || kind < 0 || kind > 3)
+        { set_error("csr_create_dist_device: bad arguments"); return LKB_ERR_ARG; }
+    if (!adopt) { set_error("csr_create_dist_device: only adopt != 0 is supported"); return LKB_ERR_ARG; }
+    cudaSetDevice(c->dev);
+    lkb_op_s* op = new lkb_op_s();
+    op->ctx = c; op->type = 3; op->kind = kind; op->m = m_local; op->n = n_local; op->uid = next_uid();
+    op->dist = true; op->m_global = m_global; op->n_global = n_global;
+    op->rowptr = rowptr_dev; op->col = col_dev; op->val = val_dev;
+    int r = csr_finish_device(c, op, kind, m_local, n_global);
+    if (r == 0) r = csr_dist_finish(c, op, kind, n_global, row0, m_local, col0, n_local);
+    if (r) {
+        op->rowptr = nullptr; op->col = nullptr; op->val = nullptr;      // the caller keeps ownership on failure
+        lkb_op_destroy(op);
+        return r;
     }
     *A = op;
     return 0;
@@ -833,7 +860,8 @@ int op_apply_enqueue(lkb_op_s* A, const void* x, void* y, bool trans, const int*
             } else {
                 LKB_CUDA(cudaMemcpyAsync((char*)A->x_full + (size_t)A->col_off[0] * es, x, (size_t)A->n * es, cudaMemcpyDeviceToDevice, c->stream));
             }
-            launch_csr(A->kind, c->stream, A->m, A->rowptr, A->col, A->val, A->x_full, y, false, flags, c->sms | (A->lpr << 16));
+            if (A->blk.nb > 0) { launch_csr_blocked(A->kind, c->stream, A->blk, A->x_full, y, false, flags, c->sms); nl = A->blk.nb; }
+            else launch_csr(A->kind, c->stream, A->m, A->rowptr, A->col, A->val, A->x_full, y, false, flags, c->sms | (A->lpr << 16));
         } else {
             // local A_loc^H u_loc over the whole column space, then every slab is summed onto its owner
             launch_csr(A->kind, c->stream, A->n_global, A->t_rowptr, A->t_col, A->t_val, x, A->y_full, true, flags, c->sms | (A->t_lpr << 16));

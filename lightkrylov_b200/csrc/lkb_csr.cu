@@ -221,11 +221,10 @@ int csr_finish_device(lkb_ctx_s* c, lkb_op_s* op, int kind, int64_t rows, int64_
     CSR_CUDA(cudaStreamSynchronize(c->stream));
 #undef CSR_CUDA
     free_tmp();
-    if (!op->dist) {
-        // L2 blocking of both orientations when the gathered vector exceeds L2 (no-op otherwise)
-        LKB_TRY(csr_block_device(c, kind, rows, ncols_index, &op->rowptr, &op->col, &op->val, &op->blk));
-        LKB_TRY(csr_block_device(c, kind, ncols_index, rows, &op->t_rowptr, &op->t_col, &op->t_val, &op->t_blk));
-    }
+    // L2 blocking when the gathered vector exceeds L2 (no-op otherwise).  Row-sharded operator: only the forward
+    // orientation (it gathers from the full-length x_full; the transposed one gathers from this rank's slab of u)
+    LKB_TRY(csr_block_device(c, kind, rows, ncols_index, &op->rowptr, &op->col, &op->val, &op->blk));
+    if (!op->dist) LKB_TRY(csr_block_device(c, kind, ncols_index, rows, &op->t_rowptr, &op->t_col, &op->t_val, &op->t_blk));
     return 0;
 }
 

@@ -151,6 +151,23 @@ def main():
             Vo = np.zeros((n5, kd5 + 1), dtype=dt, order="F"); Bo = np.zeros_like(B5)
             assert binfo == lo.bidiag(lo.Op.csr(m5, n5, S.indptr, S.indices, S.data.astype(dt)), Uo, Vo, Bo) == 0
             assert rel_normwise(B5, Bo) < 1e-10
+    # ---- the same operator type generated ON THE DEVICE per rank (lkb_csr_random_device + lkb_op_csr_create_dist_device), with
+    # the L2-blocked forward layout forced: must equal the oracle's twin of the global matrix ----
+    for kind in ("z",):
+        dt = lk.DTYPES[kind]
+        m6, n6, pr6 = 2003, 1501, 9
+        ctx.set_option("csr_slice_kb", 4); ctx.set_option("csr_block_min_kb", 0)
+        Ad = lk.LinOp.csr_random_dist(ctx, kind, m6, n6, pr6, 46)
+        ctx.set_option("csr_slice_kb", 48 * 1024); ctx.set_option("csr_block_min_kb", 96 * 1024)
+        rp6, ci6, va6 = lo.csr_random(kind, m6, n6, pr6, 46)
+        Ao6 = lo.Op.csr(m6, n6, rp6, ci6, va6)
+        r0, ml = lk.partition(m6, world, rank); c0, nl = lk.partition(n6, world, rank)
+        x6 = lo.fill(n6, kind, "normal", 5); u6 = lo.fill(m6, kind, "normal", 6)
+        xv = lk.Vector(ctx, kind, nl, n_global=n6, row0=c0).put(x6[c0:c0 + nl]); uv = lk.Vector(ctx, kind, ml, n_global=m6, row0=r0).put(u6[r0:r0 + ml])
+        yv = lk.Vector(ctx, kind, ml, n_global=m6, row0=r0); vv = lk.Vector(ctx, kind, nl, n_global=n6, row0=c0)
+        Ad.matvec(xv, yv); Ad.rmatvec(uv, vv)
+        assert np.allclose(yv.get(), Ao6.apply(x6)[r0:r0 + ml], rtol=1e-11, atol=1e-11)
+        assert np.allclose(vv.get(), Ao6.apply(u6, trans=True)[c0:c0 + nl], rtol=1e-11, atol=1e-11)
     if rank == 0:
         Xo = np.zeros((n3, kd + 1), order="F"); Xo[:, 0] = lo.fill(n3, "d", "uniform", 45); lo.normalize(Xo[:, 0])
         To = np.zeros_like(T)
