@@ -216,8 +216,8 @@ k_multidot(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j,
 //   columns of Y, re-reading X for each; here a pair of columns shares one read of every V pack, so a
 //   block step with p = 2 moves the same bytes as a single-vector step.  Same tile walk, transposing fold
 //   and deterministic two-stage reduction as k_multidot; out / partial are laid out [2][j+1].
-template <int K>
-__global__ void __launch_bounds__(MD_THREADS, 1)
+template <int K, int PT, int MINB>
+__global__ void __launch_bounds__(MD_THREADS, MINB)
 k_multidot2(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j,
             const typename Tr<K>::E* __restrict__ w0, const typename Tr<K>::E* __restrict__ w1, int64_t n,
             typename Tr<K>::W* __restrict__ partial, typename Tr<K>::W* __restrict__ out,
@@ -226,7 +226,7 @@ k_multidot2(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j,
     using E = typename Tr<K>::E;
     using W = typename Tr<K>::W;
     constexpr int EPP = Tr<K>::EPP;
-    constexpr int CB = MD_CB, PT = 2, NW = MD_THREADS / 32;
+    constexpr int CB = MD_CB, NW = MD_THREADS / 32;
     using P = Pack<E, EPP>;
     if (flags && flags[F_STOP]) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -335,12 +335,12 @@ k_multiaxpy2(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j, const t
         P a0 = ld_pack<P>(w0 + off), a1 = ld_pack<P>(w1 + off);
         const E* vp = V + off;
         int i = 0;
-        for (; i + 4 <= j; i += 4) {
-            P v[4];
+        for (; i + 8 <= j; i += 8) {
+            P v[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = ld_pack_nc<P>(vp + (int64_t)(i + u) * ld);
+            for (int u = 0; u < 8; ++u) v[u] = ld_pack_nc<P>(vp + (int64_t)(i + u) * ld);
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < 8; ++u)
 #pragma unroll
                 for (int e = 0; e < EPP; ++e) { fnma(a0.v[e], v[u].v[e], cs[i + u]); fnma(a1.v[e], v[u].v[e], cs[j + i + u]); }
         }
@@ -815,15 +815,26 @@ static void multidot2_t(cudaStream_t s, const void* V, int64_t ld, int j, const 
                         void* partial, void* out, unsigned* counter, const int* flags, int sms, const P2P* p2p) {
     using E = typename Tr<K>::E; using W = typename Tr<K>::W;
     const int64_t npk = n / Tr<K>::EPP;
-    const int64_t ntiles = (npk + (int64_t)MD_THREADS * 2 - 1) / ((int64_t)MD_THREADS * 2);
-    int64_t nb = sms;
+    // cfg 1 (default): 2 CTAs per SM, one pack of each w per thread (110 registers); cfg 0: the round-1 shape, 1 CTA per SM with
+    // 2 packs per thread (158 registers).  Block Arnoldi on the C2 operator, blksize 2: 233 -> 287 vectors/s (gpurun_out/r02_blk.log)
+    static const int cfg = getenv("LKB_MULTIDOT2_CFG") ? atoi(getenv("LKB_MULTIDOT2_CFG")) : 1;
+    const int pt = cfg == 1 ? 1 : 2;
+    const int64_t ntiles = (npk + (int64_t)MD_THREADS * pt - 1) / ((int64_t)MD_THREADS * pt);
+    int64_t nb = cfg == 1 ? 2 * (int64_t)sms : sms;
     if (nb > ntiles) nb = ntiles;
     if (nb < 1) nb = 1;
     const size_t sh = (size_t)(MD_THREADS / 32) * 2 * (size_t)(j + 1) * sizeof(W);
-    static const SmemAttrOnce attr((const void*)k_multidot2<K>, 200 * 1024);
-    attr.ensure();
-    k_multidot2<K><<<(int)nb, MD_THREADS, sh, s>>>((const E*)V, ld, j, (const E*)w0, (const E*)w1, n, (W*)partial, (W*)out,
-                                                   counter, flags, p2p ? *p2p : P2P());
+    if (cfg == 1) {
+        static const SmemAttrOnce attr((const void*)k_multidot2<K, 1, 2>, 100 * 1024);
+        attr.ensure();
+        k_multidot2<K, 1, 2><<<(int)nb, MD_THREADS, sh, s>>>((const E*)V, ld, j, (const E*)w0, (const E*)w1, n, (W*)partial, (W*)out,
+                                                             counter, flags, p2p ? *p2p : P2P());
+    } else {
+        static const SmemAttrOnce attr((const void*)k_multidot2<K, 2, 1>, 200 * 1024);
+        attr.ensure();
+        k_multidot2<K, 2, 1><<<(int)nb, MD_THREADS, sh, s>>>((const E*)V, ld, j, (const E*)w0, (const E*)w1, n, (W*)partial, (W*)out,
+                                                             counter, flags, p2p ? *p2p : P2P());
+    }
 }
 void launch_multidot2(int kind, cudaStream_t s, const void* V, int64_t ld, int j, const void* w0, const void* w1, int64_t n,
                       void* partial, void* out, unsigned* counter, const int* flags, int sms, const P2P* p2p) {
