@@ -50,6 +50,10 @@ LKB_DI void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+LKB_DI void bulk_load_1d_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
 LKB_DI void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
@@ -86,12 +90,15 @@ __global__ void __launch_bounds__(FZ_THREADS, 1)
 k_axpy_dot(const __grid_constant__ CUtensorMap tmap, int j, int tp, int nst, int elt_per_pack,
            const typename Tr<K>::W* __restrict__ c1, typename Tr<K>::E* __restrict__ w, int64_t n,
            typename Tr<K>::W* __restrict__ partial, typename Tr<K>::W* __restrict__ out,
-           unsigned* __restrict__ counter, const int* __restrict__ flags, const P2P p2p, const int desc)
+           unsigned* __restrict__ counter, const int* __restrict__ flags, const P2P p2p, const int desc_mode)
 {
     using E = typename Tr<K>::E;
     using W = typename Tr<K>::W;
     constexpr int EPP = Tr<K>::EPP;
     using P = Pack<E, EPP>;
+    const int desc = desc_mode & 1;
+    const bool keep = (desc_mode & 2) != 0;       // w is small: keep it L2-resident (lkb_types.cuh)
+    const uint64_t pol = keep ? pol_evict_last() : 0ULL;
 
     extern __shared__ __align__(1024) unsigned char smem[];
     const int jp = j + 1;
@@ -149,7 +156,8 @@ k_axpy_dot(const __grid_constant__ CUtensorMap tmap, int j, int tp, int nst, int
             const uint32_t wbytes = (uint32_t)min((int64_t)tp, npk - pk0) * 16u;
             mbar_expect_tx(bar, stage_bytes + wbytes);
             tma_load_2d(smem_u32(smem + (size_t)s * stage_bytes), &tmap, (int)pk0 * elt_per_pack, 0, bar);
-            bulk_load_1d(smem_u32(wst + (size_t)s * tp), w + pk0 * EPP, wbytes, bar);
+            if (keep) bulk_load_1d_hint(smem_u32(wst + (size_t)s * tp), w + pk0 * EPP, wbytes, bar, pol);
+            else bulk_load_1d(smem_u32(wst + (size_t)s * tp), w + pk0 * EPP, wbytes, bar);
         };
         const int pre = min(nmine, nst);
         if (lane == 0)
@@ -229,7 +237,7 @@ k_axpy_dot(const __grid_constant__ CUtensorMap tmap, int j, int tp, int nst, int
                     wp.v[e] = add_v(wp.v[e], rscale(sum.v[e], (typename Tr<K>::Rl)(-1)));
                     wwacc += abs2_w(wp.v[e]);
                 }
-                st_pack(w + pk * EPP, wp);
+                st_pack_w(w + pk * EPP, wp, keep, pol);
             }
             wnew[tid] = wp;
         }
@@ -349,7 +357,8 @@ static bool axpy_dot_t(cudaStream_t s, const void* V, int64_t ld, int j, const v
     int64_t nb = sms;
     if (nb > ntiles) nb = ntiles;
     if (nb > RT_MAXROWS) nb = RT_MAXROWS;
-    launch_ex(k_axpy_dot<K>, (unsigned)nb, FZ_THREADS, sh, s, pdl_take(4), tmap, j, tp, nst, elt_per_pack, (const W*)c1, (E*)w, n, (W*)partial, (W*)out, counter, flags, p2p ? *p2p : P2P(), sweep_dir());
+    launch_ex(k_axpy_dot<K>, (unsigned)nb, FZ_THREADS, sh, s, pdl_take(4), tmap, j, tp, nst, elt_per_pack, (const W*)c1, (E*)w, n, (W*)partial, (W*)out, counter, flags, p2p ? *p2p : P2P(),
+              sweep_dir() | (((size_t)n * sizeof(E) <= w_keep_bytes()) ? 2 : 0));
     return true;
 }
 

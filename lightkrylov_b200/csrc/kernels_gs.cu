@@ -56,7 +56,8 @@ template <typename E> LKB_DI void warp_fold16(E (&acc)[16], int lane) {
 template <int K, int PT, bool FULL>
 LKB_DI void md_tile(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j, int nchunk,
                     const typename Tr<K>::E* __restrict__ w, int64_t tb, int64_t p1,
-                    typename Tr<K>::W* __restrict__ myacc, typename Tr<K>::E& accw, int lane, int fold_idx)
+                    typename Tr<K>::W* __restrict__ myacc, typename Tr<K>::E& accw, int lane, int fold_idx,
+                    bool keep = false, uint64_t pol = 0)
 {
     using E = typename Tr<K>::E;
     constexpr int EPP = Tr<K>::EPP;
@@ -67,7 +68,7 @@ LKB_DI void md_tile(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j, 
 #pragma unroll
     for (int q = 0; q < PT; ++q) {
         const int64_t pk = base + (int64_t)q * MD_THREADS;
-        if (FULL || pk < p1) wv[q] = ld_pack_nc<P>(w + pk * EPP);
+        if (FULL || pk < p1) wv[q] = ld_pack_nc_w<P>(w + pk * EPP, keep, pol);
         else {
 #pragma unroll
             for (int e = 0; e < EPP; ++e) wv[q].v[e] = zero_v(E());
@@ -150,6 +151,9 @@ k_multidot(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j,
     // the opposite order.  (Round 1 split whole tiles and shrank ALL tiles to 1 pack per thread at 1/8 of C2 per GPU to
     // stay balanced; a first round-2 version kept 4-pack tiles and masked the remainder -- 13 % of a CTA's rows there --
     // which was slower still.)
+    const bool keep = (desc & 2) != 0;            // w is small: keep it L2-resident (lkb_types.cuh)
+    const uint64_t pol = keep ? pol_evict_last() : 0ULL;
+    const bool down = (desc & 1) != 0;
     const int64_t npk = n / EPP;
     constexpr int64_t BIG = 4 * MD_THREADS;
     const int64_t nfull = npk / (BIG * gridDim.x);
@@ -161,17 +165,17 @@ k_multidot(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j,
     E accw = zero_v(E());
     auto remainder = [&]() {
         int64_t tb = q0;
-        for (; tb + MD_THREADS <= q1; tb += MD_THREADS) md_tile<K, 1, true>(V, ld, j, nchunk, w, tb, q1, myacc, accw, lane, fold_idx);
-        if (tb < q1) md_tile<K, 1, false>(V, ld, j, nchunk, w, tb, q1, myacc, accw, lane, fold_idx);
+        for (; tb + MD_THREADS <= q1; tb += MD_THREADS) md_tile<K, 1, true>(V, ld, j, nchunk, w, tb, q1, myacc, accw, lane, fold_idx, keep, pol);
+        if (tb < q1) md_tile<K, 1, false>(V, ld, j, nchunk, w, tb, q1, myacc, accw, lane, fold_idx, keep, pol);
     };
-    if (!desc) {
+    if (!down) {
         for (int64_t r = 0; r < nfull; ++r)
-            md_tile<K, 4, true>(V, ld, j, nchunk, w, (r * gridDim.x + blockIdx.x) * BIG, npk, myacc, accw, lane, fold_idx);
+            md_tile<K, 4, true>(V, ld, j, nchunk, w, (r * gridDim.x + blockIdx.x) * BIG, npk, myacc, accw, lane, fold_idx, keep, pol);
         remainder();
     } else {
         remainder();
         for (int64_t r = nfull - 1; r >= 0; --r)
-            md_tile<K, 4, true>(V, ld, j, nchunk, w, (r * gridDim.x + blockIdx.x) * BIG, npk, myacc, accw, lane, fold_idx);
+            md_tile<K, 4, true>(V, ld, j, nchunk, w, (r * gridDim.x + blockIdx.x) * BIG, npk, myacc, accw, lane, fold_idx, keep, pol);
     }
     // ragged tail (n not a multiple of the pack width): one thread of CTA 0
     __syncwarp();
@@ -538,7 +542,7 @@ __global__ void __launch_bounds__(256, 2)
 k_multiaxpy_fin(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j,
                 const typename Tr<K>::W* __restrict__ c, typename Tr<K>::E* __restrict__ w, int64_t n,
                 double* __restrict__ partial, typename Tr<K>::W* __restrict__ nrm2_out,
-                unsigned* __restrict__ counter, const FinParams fp, const P2P p2p, const HaloP2P hp, const int desc)
+                unsigned* __restrict__ counter, const FinParams fp, const P2P p2p, const HaloP2P hp, const int desc_mode)
 {
     using E = typename Tr<K>::E;
     using W = typename Tr<K>::W;
@@ -588,6 +592,9 @@ k_multiaxpy_fin(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j,
     const int64_t hi0 = n - hp.he;
     ktime_cta(p2p, 0);
 
+    const bool keep = (desc_mode & 2) != 0;
+    const uint64_t pol = keep ? pol_evict_last() : 0ULL;
+    const int desc = desc_mode & 1;
     // Row walk = one global sweep in time (lkb_kernels.h "serpentine sweeps").  The grid is two waves of CTAs (the second
     // wave is picked up by whichever SMs finish first: dynamic balance); the CTAs of the first wave (low blockIdx) stride
     // over the half of the rows the sweep visits first, those of the second wave over the other half.
@@ -610,7 +617,7 @@ k_multiaxpy_fin(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j,
     for (int64_t it = 0; it < nit1; ++it) {
         const int64_t pk = first1 + (desc ? nit1 - 1 - it : it) * stride1;
         const int64_t off = pk * EPP;
-        P a = ld_pack<P>(w + off);
+        P a = ld_pack_w<P>(w + off, keep, pol);
         const E* vp = V + off;
         int i = 0;
         for (; i + UA <= j; i += UA) {
@@ -637,7 +644,7 @@ k_multiaxpy_fin(const typename Tr<K>::E* __restrict__ V, int64_t ld, int j,
 #pragma unroll
             for (int e = 0; e < EPP; ++e) a.v[e] = rscale(a.v[e], inv);
         }
-        st_pack(w + off, a);
+        st_pack_w(w + off, a, keep, pol);
         if (push_lo && off < hp.he) {
 #pragma unroll
             for (int e = 0; e < EPP; ++e) if (off + e < hp.he) push_lo[off + e] = a.v[e];
@@ -741,7 +748,8 @@ static void multidot_t(cudaStream_t s, const void* V, int64_t ld, int j, const v
     const size_t sh = (size_t)(MD_THREADS / 32) * (size_t)(j + 1) * sizeof(W);
     static const SmemAttrOnce attr((const void*)k_multidot<K>, 160 * 1024);
     attr.ensure();
-    launch_ex(k_multidot<K>, (unsigned)nb, MD_THREADS, sh, s, pdl_take(2), (const E*)V, ld, j, (const E*)w, n, (W*)partial, (W*)out, counter, flags, pp, sweep_dir());
+    launch_ex(k_multidot<K>, (unsigned)nb, MD_THREADS, sh, s, pdl_take(2), (const E*)V, ld, j, (const E*)w, n, (W*)partial, (W*)out, counter, flags, pp,
+              sweep_dir() | (((size_t)n * sizeof(E) <= w_keep_bytes()) ? 2 : 0));
 }
 void launch_multidot(int kind, cudaStream_t s, const void* V, int64_t ld, int j, const void* w, int64_t n,
                      void* partial, void* out, unsigned* counter, const int* flags, int sms, const P2P* p2p) {
@@ -797,7 +805,8 @@ static void multiaxpy_fin_t(cudaStream_t s, const void* V, int64_t ld, int j, co
     fp.c1 = c1; fp.hcol = hcol; fp.tol = tol; fp.atol = atol; fp.inv_dev = (double*)inv_dev; fp.flags = flags;
     fp.kstep = kstep; fp.mode = mode;
     launch_ex(k_multiaxpy_fin<K>, (unsigned)nb, 256, sh, s, pdl_take(8), (const E*)V, ld, j, (const W*)c2, (E*)w, n, (double*)partial,
-              (W*)nrm2_out, counter, fp, p2p ? *p2p : P2P(), hp ? *hp : HaloP2P(), sweep_dir());
+              (W*)nrm2_out, counter, fp, p2p ? *p2p : P2P(), hp ? *hp : HaloP2P(),
+              sweep_dir() | (((size_t)n * sizeof(E) <= w_keep_bytes()) ? 2 : 0));
 }
 void launch_multiaxpy_fin(int kind, cudaStream_t s, const void* V, int64_t ld, int j, const void* c1, const void* c2, void* w,
                           int64_t n, void* partial, void* nrm2_out, unsigned* counter, void* hcol, double tol, double atol,

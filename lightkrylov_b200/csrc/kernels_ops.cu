@@ -15,8 +15,11 @@ template <typename E> struct Coef7 { E c[7]; };
 
 template <typename E, int PW> struct PackOps {
     using P = Pack<E, PW>;
+    // Pack is alignas(16), so sizeof(P) == 16 even for a partial pack (PW elements < 16 bytes: rows whose length is not a
+    // multiple of the pack width): only a FULL pack may be moved with one 128-bit access
+    static constexpr bool FULL = (PW * sizeof(E) == 16);
     static LKB_DI P ld(const E* p) {
-        if constexpr (sizeof(P) == 16) return ld_pack_l1<P>(p);
+        if constexpr (FULL) return ld_pack_l1<P>(p);
         else { P r;
 #pragma unroll
             for (int e = 0; e < PW; ++e) r.v[e] = __ldg(p + e);
@@ -24,18 +27,23 @@ template <typename E, int PW> struct PackOps {
     }
     // halo data written by a peer GPU during this kernel's lifetime: bypass L1 (ld.global.cg)
     static LKB_DI P ld_cg(const E* p) {
-        if constexpr (sizeof(P) == 16) { int4 r = __ldcg(reinterpret_cast<const int4*>(p)); return *reinterpret_cast<P*>(&r); }
+        if constexpr (FULL) { int4 r = __ldcg(reinterpret_cast<const int4*>(p)); return *reinterpret_cast<P*>(&r); }
         else { P r;
 #pragma unroll
             for (int e = 0; e < PW; ++e) r.v[e] = __ldcg(p + e);
             return r; }
     }
     static LKB_DI void st(E* p, const P& v) {
-        if constexpr (sizeof(P) == 16) st_pack(p, v);
+        if constexpr (FULL) st_pack(p, v);
         else {
 #pragma unroll
             for (int e = 0; e < PW; ++e) p[e] = v.v[e];
         }
+    }
+    // the matvec output is the work vector w of the step that follows: small slices are stored with L2 evict_last (lkb_types.cuh)
+    static LKB_DI void st_w(E* p, const P& v, bool keep, uint64_t pol) {
+        if constexpr (FULL) st_pack_w(p, v, keep, pol);
+        else st(p, v);
     }
     static LKB_DI P zero() { P r;
 #pragma unroll
@@ -86,10 +94,12 @@ k_stencil(const typename Tr<K>::E* __restrict__ x, typename Tr<K>::E* __restrict
           int64_t nx, int64_t ny, int64_t nz, Coef7<typename Tr<K>::E> cf,
           const typename Tr<K>::E* __restrict__ halo_lo, const typename Tr<K>::E* __restrict__ halo_hi,
           const unsigned* __restrict__ halo_epoch, int64_t halo_parity_stride, const unsigned* __restrict__ flag_lo,
-          const unsigned* __restrict__ flag_hi, int64_t ncb, const int* __restrict__ flags)
+          const unsigned* __restrict__ flag_hi, int64_t ncb, const int* __restrict__ flags, const int keep_w)
 {
     using E = typename Tr<K>::E;
     using PO = PackOps<E, PW>;
+    const bool keep = keep_w != 0;
+    const uint64_t pol = keep ? pol_evict_last() : 0ULL;
     pdl_wait();            // x, the stop flag and the halo epoch come from the predecessor
     pdl_trigger();
     if (flags && flags[F_STOP]) return;
@@ -158,7 +168,7 @@ k_stencil(const typename Tr<K>::E* __restrict__ x, typename Tr<K>::E* __restrict
             if (DIM == 3) { fmacc(s, down.v[e], cf.c[5]); fmacc(s, up.v[e], cf.c[6]); }
             out.v[e] = s;
         }
-        if (active) PO::st(y + k * plane + p, out);
+        if (active) PO::st_w(y + k * plane + p, out, keep, pol);
     };
 
     P south = getrow(j0 - 1), center = getrow(j0);
@@ -206,11 +216,13 @@ k_stencil_smem(const typename Tr<K>::E* __restrict__ x, typename Tr<K>::E* __res
                int64_t nx, int64_t ny, int64_t nz, Coef7<typename Tr<K>::E> cf,
                const typename Tr<K>::E* __restrict__ halo_lo, const typename Tr<K>::E* __restrict__ halo_hi,
                const unsigned* __restrict__ halo_epoch, int64_t halo_parity_stride, const unsigned* __restrict__ flag_lo,
-               const unsigned* __restrict__ flag_hi, int64_t ncb, const int* __restrict__ flags)
+               const unsigned* __restrict__ flag_hi, int64_t ncb, const int* __restrict__ flags, const int keep_w)
 {
     using E = typename Tr<K>::E;
     using P = Pack<E, PW>;
     constexpr int PB = PW * (int)sizeof(E);       // payload bytes (Pack is padded to 16 B)
+    const bool keep = keep_w != 0;
+    const uint64_t pol = keep ? pol_evict_last() : 0ULL;
     pdl_wait();
     pdl_trigger();
     if (flags && flags[F_STOP]) return;
@@ -295,7 +307,7 @@ k_stencil_smem(const typename Tr<K>::E* __restrict__ x, typename Tr<K>::E* __res
             }
             out.v[e] = sacc;
         }
-        PackOps<E, PW>::st(y + k * plane + p, out);
+        PackOps<E, PW>::st_w(y + k * plane + p, out, keep, pol);
     }
 }
 
@@ -388,6 +400,7 @@ static void stencil_launch(cudaStream_t s, const StencilArgs& a, const void* x, 
     }
     for (int q = 0; q < 7; ++q) from_scalar(c[q], cf.c[q]);
     const int64_t npk_row = a.nx / PW;
+    const int keep_w = ((size_t)a.nx * (size_t)a.ny * (size_t)(DIM == 3 ? a.nz : 1) * sizeof(E) <= w_keep_bytes()) ? 1 : 0;
     // Measured on B200 (profiles/stencil_ab.py, fp64): 2-D 4096^2 -- shared-memory kernel RY=8 5.64 TB/s vs
     // register march 5.24 TB/s; 3-D 384^3 -- shared-memory kernel 2.1-3.0 TB/s (3RY+2 staged rows per CTA cut
     // the occupancy) vs register march 4.62 TB/s; a z-march with the plane staged in shared memory (two block
@@ -414,7 +427,7 @@ static void stencil_launch(cudaStream_t s, const StencilArgs& a, const void* x, 
             const size_t sh_ = (size_t)((RY_ + 2) + (DIM == 3 ? 2 * RY_ : 0)) * ST_TX * sizeof(Pack<E, PW>); \
             static const SmemAttrOnce once_((const void*)k_stencil_smem<K, PW, DIM, RY_>, 96 * 1024); once_.ensure(); \
             launch_ex(k_stencil_smem<K, PW, DIM, RY_>, grid_, ST_TX, sh_, s, pdl_take(1), (const E*)x, (E*)y, a.nx, a.ny, a.nz, cf, \
-                (const E*)a.halo_lo, (const E*)a.halo_hi, a.halo_epoch, a.halo_parity_stride, a.flag_lo, a.flag_hi, ncb_, flags); }
+                (const E*)a.halo_lo, (const E*)a.halo_hi, a.halo_epoch, a.halo_parity_stride, a.flag_lo, a.flag_hi, ncb_, flags, keep_w); }
         if (variant == 3) LKB_STS(4) else LKB_STS(8)
 #undef LKB_STS
         return;
@@ -431,7 +444,7 @@ static void stencil_launch(cudaStream_t s, const StencilArgs& a, const void* x, 
     const unsigned bs = (unsigned)std::min<int64_t>(256, ((npk_row + ncb - 1) / ncb + 31) / 32 * 32);
     const unsigned grid = (unsigned)(nyb * (DIM == 3 ? a.nz : 1) * ncb);
     launch_ex(k_stencil<K, PW, DIM, RY, 1, false>, grid, bs, 0, s, pdl_take(1), (const E*)x, (E*)y, a.nx, a.ny, a.nz, cf,
-              (const E*)a.halo_lo, (const E*)a.halo_hi, a.halo_epoch, a.halo_parity_stride, a.flag_lo, a.flag_hi, ncb, flags);
+              (const E*)a.halo_lo, (const E*)a.halo_hi, a.halo_epoch, a.halo_parity_stride, a.flag_lo, a.flag_hi, ncb, flags, keep_w);
 }
 
 template <int K>

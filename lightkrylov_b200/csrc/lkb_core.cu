@@ -130,6 +130,7 @@ int allreduce_w(lkb_ctx_s* c, void* buf, size_t ndoubles) {
 }
 int& pdl_state() { static thread_local int s = 0; return s; }
 int& sweep_dir() { static thread_local int d = 0; return d; }
+size_t w_keep_bytes() { static const size_t b = (size_t)(getenv("LKB_W_KEEP_MB") ? atoi(getenv("LKB_W_KEEP_MB")) : 48) << 20; return b; }
 // Which kernel classes are launched programmatically (bits: 1 matvec, 2 multi-dot, 4 fused axpy+dot, 8 multi-axpy, 16 scale).
 // Default 4: only the TMA kernel.  Measured on B200 (profiles/r02_pdl2.sh .. r02_pdl4.sh): a programmatically launched
 // kernel inherits the predecessor's L1 / shared-memory carve-out, which costs the LDG-based multi-dot / multi-axpy

@@ -70,6 +70,7 @@ struct PdlScope {
 // directions: a kernel starts on the rows its predecessor read last, which are still L2-resident (126 MB L2: ~10 % of
 // a kernel's bytes at the per-GPU share of N = 8, ~1 % at N = 1).  The direction is a pure function of the step index
 // (dgs_enqueue), so results stay bitwise reproducible (graphs on / off, one-shot vs step-by-step, any launch timing).
+size_t w_keep_bytes(); // slices of w up to this size are kept L2-resident (evict_last), LKB_W_KEEP_MB, default 48; lkb_types.cuh
 int& sweep_dir();      // 0 ascending, 1 descending: read by launch_multidot / launch_axpy_dot / launch_multiaxpy_fin
 struct SweepDir {
     int prev;

@@ -152,6 +152,29 @@ template <typename P> LKB_DI P ld_pack(const void* p) {      // coherent streami
 #endif
     return *reinterpret_cast<P*>(&r);
 }
+// Accesses of the WORK VECTOR w of a Krylov step.  When a GPU's slice of w is small (<= w_keep_bytes(), default 48 MB: the
+// 1/4 and 1/8 shares of C2) every access of w carries an L2 evict_last policy, so w survives the j columns of V that
+// stream through L2 between its uses (matvec writes it, the multi-dot, the fused kernel and the final axpy read it):
+// 4096 x 512 1917 -> 1943 steps/s (+1.4 %, the fused kernel +5 %).  At full size (134 MB per vector > L2) the hint costs
+// 0.9 %, hence the size switch (profiles/r02_l2hint.sh with the -DLKB_W_EVICT_LAST experiment build, round 2).
+LKB_DI uint64_t pol_evict_last() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
+template <typename P> LKB_DI P ld_pack_w(const void* p, bool keep, uint64_t pol) {          // coherent (w is rewritten by the kernel)
+    if (!keep) return ld_pack<P>(p);
+    int4 r;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.s32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol) : "memory");
+    return *reinterpret_cast<P*>(&r);
+}
+template <typename P> LKB_DI P ld_pack_nc_w(const void* p, bool keep, uint64_t pol) {       // read-only
+    if (!keep) return ld_pack_nc<P>(p);
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+    return *reinterpret_cast<P*>(&r);
+}
+template <typename P> LKB_DI void st_pack_w(void* p, const P& v, bool keep, uint64_t pol) {
+    if (!keep) { *reinterpret_cast<int4*>(p) = *reinterpret_cast<const int4*>(&v); return; }
+    const int4 r = *reinterpret_cast<const int4*>(&v);
+    asm volatile("st.global.L2::cache_hint.v4.s32 [%0], {%1, %2, %3, %4}, %5;" :: "l"(p), "r"(r.x), "r"(r.y), "r"(r.z), "r"(r.w), "l"(pol) : "memory");
+}
 template <typename P> LKB_DI void st_pack(void* p, const P& v) {
     *reinterpret_cast<int4*>(p) = *reinterpret_cast<const int4*>(&v);
 }
