@@ -824,26 +824,17 @@ static void multidot2_t(cudaStream_t s, const void* V, int64_t ld, int j, const 
                         void* partial, void* out, unsigned* counter, const int* flags, int sms, const P2P* p2p) {
     using E = typename Tr<K>::E; using W = typename Tr<K>::W;
     const int64_t npk = n / Tr<K>::EPP;
-    // cfg 1 (default): 2 CTAs per SM, one pack of each w per thread (110 registers); cfg 0: the round-1 shape, 1 CTA per SM with
-    // 2 packs per thread (158 registers).  Block Arnoldi on the C2 operator, blksize 2: 233 -> 287 vectors/s (gpurun_out/r02_blk.log)
-    static const int cfg = getenv("LKB_MULTIDOT2_CFG") ? atoi(getenv("LKB_MULTIDOT2_CFG")) : 1;
-    const int pt = cfg == 1 ? 1 : 2;
-    const int64_t ntiles = (npk + (int64_t)MD_THREADS * pt - 1) / ((int64_t)MD_THREADS * pt);
-    int64_t nb = cfg == 1 ? 2 * (int64_t)sms : sms;
+    // 2 CTAs per SM, one pack of each w per thread (110 registers).  The round-1 shape (1 CTA per SM, 2 packs per thread, 158
+    // registers) ran block Arnoldi on the C2 operator at 233 vectors/s (blksize 2) against 287 now (gpurun_out/r02_blk.log).
+    const int64_t ntiles = (npk + (int64_t)MD_THREADS - 1) / (int64_t)MD_THREADS;
+    int64_t nb = 2 * (int64_t)sms;
     if (nb > ntiles) nb = ntiles;
     if (nb < 1) nb = 1;
     const size_t sh = (size_t)(MD_THREADS / 32) * 2 * (size_t)(j + 1) * sizeof(W);
-    if (cfg == 1) {
-        static const SmemAttrOnce attr((const void*)k_multidot2<K, 1, 2>, 100 * 1024);
-        attr.ensure();
-        k_multidot2<K, 1, 2><<<(int)nb, MD_THREADS, sh, s>>>((const E*)V, ld, j, (const E*)w0, (const E*)w1, n, (W*)partial, (W*)out,
-                                                             counter, flags, p2p ? *p2p : P2P());
-    } else {
-        static const SmemAttrOnce attr((const void*)k_multidot2<K, 2, 1>, 200 * 1024);
-        attr.ensure();
-        k_multidot2<K, 2, 1><<<(int)nb, MD_THREADS, sh, s>>>((const E*)V, ld, j, (const E*)w0, (const E*)w1, n, (W*)partial, (W*)out,
-                                                             counter, flags, p2p ? *p2p : P2P());
-    }
+    static const SmemAttrOnce attr((const void*)k_multidot2<K, 1, 2>, 100 * 1024);
+    attr.ensure();
+    k_multidot2<K, 1, 2><<<(int)nb, MD_THREADS, sh, s>>>((const E*)V, ld, j, (const E*)w0, (const E*)w1, n, (W*)partial, (W*)out,
+                                                         counter, flags, p2p ? *p2p : P2P());
 }
 void launch_multidot2(int kind, cudaStream_t s, const void* V, int64_t ld, int j, const void* w0, const void* w1, int64_t n,
                       void* partial, void* out, unsigned* counter, const int* flags, int sms, const P2P* p2p) {

@@ -408,7 +408,8 @@ static void stencil_launch(cudaStream_t s, const StencilArgs& a, const void* x, 
     // Default: shared-memory staging in 2-D, register y-march in 3-D.
     // 3-D: the z-march (variant 4) measured 3.95 TB/s against 4.32 TB/s for the y-march at 384^3 in three separate runs
     // (gpurun_out/r02_stencil_ab*.txt) -- the y-march stays the default
-    static const int variant = getenv("LKB_STENCIL_VARIANT") ? atoi(getenv("LKB_STENCIL_VARIANT")) : (DIM == 2 ? 1 : 0);
+    static const int env_variant = getenv("LKB_STENCIL_VARIANT") ? atoi(getenv("LKB_STENCIL_VARIANT")) : -1;
+    const int variant = env_variant >= 0 ? env_variant : (a.variant >= 0 ? a.variant : (DIM == 2 ? 1 : 0));
     if constexpr (DIM == 3) {
         if (variant == 4) {      // z-march with register planes (A/B only)
             constexpr int LZ = 32;
@@ -723,7 +724,6 @@ void launch_csr_blocked(int kind, cudaStream_t s, const CsrBlocked& b, const voi
     static const int env_variant = getenv("LKB_CSR_BLOCKED_VARIANT") ? atoi(getenv("LKB_CSR_BLOCKED_VARIANT")) : -1;
     const int variant = env_variant >= 0 ? env_variant : b.variant;
     if (variant == 1) {
-        static const int cfg = getenv("LKB_CSR_STREAM_CFG") ? atoi(getenv("LKB_CSR_STREAM_CFG")) : 0;
         int64_t nbs = (b.rows + CS_ROWS - 1) / CS_ROWS;
         if (nbs < 1) nbs = 1;
         if (nbs > (int64_t)sms * 6) nbs = (int64_t)sms * 6;
@@ -733,7 +733,7 @@ void launch_csr_blocked(int kind, cudaStream_t s, const CsrBlocked& b, const voi
 #define LKB_CSS(K_, E_, U_, M_) k_csr_blocked_stream<K_, U_, M_><<<(int)nbs, 256, sh, s>>>(b.rows, tab, b.col, (const E_*)b.val, (const E_*)x, (E_*)y, conj_vals, blk == 0, flags)
 #define LKB_CSS_K(U_, M_) switch (kind) { case KS: LKB_CSS(KS, float, U_, M_); break; case KD: LKB_CSS(KD, double, U_, M_); break; \
                                           case KC: LKB_CSS(KC, float2, U_, M_); break; default: LKB_CSS(KZ, double2, U_, M_); break; }
-            if (cfg == 1) LKB_CSS_K(2, 6) else if (cfg == 2) LKB_CSS_K(5, 3) else if (cfg == 3) LKB_CSS_K(3, 5) else LKB_CSS_K(4, 4)
+            LKB_CSS_K(4, 4)      // 4 gathers in flight per thread, 4 CTAs / SM (64 registers); 2 x 6 and 3 x 5 spill and run 2x slower
 #undef LKB_CSS_K
 #undef LKB_CSS
         }

@@ -341,6 +341,7 @@ int lkb_set_option(lkb_ctx_t c, const char* name, int value) {
     else if (!strcmp(name, "csr_slice_kb")) c->csr_slice_kb = value;            // 0 disables the L2 blocking
     else if (!strcmp(name, "csr_block_min_kb")) c->csr_block_min_kb = value;
     else if (!strcmp(name, "csr_blocked_variant")) c->csr_variant = value;
+    else if (!strcmp(name, "stencil_variant")) c->stencil_variant = value;
     else if (!strcmp(name, "fused_halo")) c->fused_halo = value != 0;
     else if (!strcmp(name, "p2p")) c->p2p_active = (value != 0) && c->p2p.world > 1;
     else { set_error("unknown option %s", name); return LKB_ERR_ARG; }
@@ -843,6 +844,7 @@ int op_apply_enqueue(lkb_op_s* A, const void* x, void* y, bool trans, const int*
             LKB_NCCL(api->GroupEnd());
             pdl_rearm();
         }
+        A->st.variant = c->stencil_variant;
         launch_stencil(A->kind, c->stream, A->st, x, y, trans, flags, c->sms);
     } else if (A->type == 3 && A->dist) {
         const int dt = (A->kind == KS || A->kind == KC) ? 7 : 8;            // ncclFloat32 / ncclFloat64

@@ -94,6 +94,7 @@ struct StencilArgs {
     const void* halo_lo;       // previous slab's last row/plane (nullptr = Dirichlet boundary)
     const void* halo_hi;       // next slab's first row/plane
     int dim;                   // 2 or 3
+    int variant = -1;          // kernel variant (kernels_ops.cu: 0 register y-march, 1-3 shared-memory staging, 4 register z-march); -1 = default
     // p2p halo exchange: halo_lo / halo_hi point at parity 0 of double-buffered regions; the kernel adds
     // (epoch & 1) * halo_parity_stride elements, epoch being the device counter of the push kernel
     const unsigned* halo_epoch = nullptr;
