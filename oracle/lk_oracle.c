@@ -17,7 +17,9 @@
  * test/TestIterativeSolvers.fypp:59-725), re-run against this code by
  * tests/test_oracle_pins.py; (2) an independent evaluation of the Hessenberg entries in
  * 80-bit extended precision (test_arnoldi_entries_match_extended_precision); (3) line-by-
- * line citation of the reference sources in lko_body.inc.
+ * line citation of the reference sources in lko_body.inc; (4) a second, independent numpy
+ * restatement written from the Fortran sources (tests/test_oracle_second_opinion.py) that
+ * must agree with this code entry by entry.
  *
  * Build:  make -C oracle      (gcc -O3 -march=native -fopenmp -shared)
  */
