@@ -226,3 +226,153 @@ def test_bidiagonalization_two_restatements_agree(oracle, kind):
     Vo = np.zeros_like(V2); Bo = np.zeros_like(B2)
     assert oracle.bidiag(oracle.Op.dense(A), Uo, Vo, Bo) == 0
     assert rel_normwise(Bo, B2) < _tol(kind)
+
+
+# ---- solver shells: gmres (GMRES/gmres.fypp:100-238 + submodule_utility_functions.fypp:167-204) and cg (CG/CG.fypp:96-179) ----
+RTOL = {k: np.sqrt(v) for k, v in ATOL.items()}                  # src/Constants.f90: rtol = sqrt(atol)
+
+
+def apply_givens_rotation(h, c, s):
+    """h(1:k+1) = new Hessenberg column; c, s = rotations so far, entry k is produced here."""
+    k = h.size - 1
+    if np.iscomplexobj(h):
+        for i in range(k - 1):                                   # hand-rolled: NO conjugates (literal restatement)
+            t = c[i] * h[i] + s[i] * h[i + 1]
+            h[i + 1] = -s[i] * h[i] + c[i] * h[i + 1]
+            h[i] = t
+        nrm = np.sqrt(abs(h[k - 1]) ** 2 + abs(h[k]) ** 2)       # g = x / norm(x, 2)
+        c[k - 1], s[k - 1] = h[k - 1] / nrm, h[k] / nrm
+        h[k - 1] = c[k - 1] * h[k - 1] + s[k - 1] * h[k]
+        h[k] = 0
+    else:
+        for j in range(k - 1):                                   # lasr('L', 'V', 'F'): P(k-1) ... P(1) from the left
+            t = h[j + 1]
+            h[j + 1] = c[j] * t - s[j] * h[j]
+            h[j] = s[j] * t + c[j] * h[j]
+        f, g = h[k - 1], h[k]                                    # lartg (LAPACK 3.10: r = sign(f) sqrt(f^2 + g^2), c >= 0)
+        if g == 0:
+            c[k - 1], s[k - 1], r = 1.0, 0.0, f
+        elif f == 0:
+            c[k - 1], s[k - 1], r = 0.0, np.sign(g), abs(g)
+        else:
+            d = np.sqrt(f * f + g * g)
+            c[k - 1] = abs(f) / d
+            r = np.copysign(d, f)
+            s[k - 1] = g / r
+        h[k - 1] = r
+        h[k] = 0
+
+
+def gmres(apply_A, b, x, kind, kdim=30, maxiter=10):
+    dt = b.dtype
+    tol = ATOL[kind] + RTOL[kind] * v_norm(b)
+    n = b.size
+    res, n_iter, n_inner, n_outer, converged = [], 0, 0, 0, False
+    while (not converged) and n_outer <= maxiter:
+        H = np.zeros((kdim + 1, kdim), dtype=dt); V = np.zeros((n, kdim + 1), dtype=dt, order="F")
+        if v_norm(x) != 0:
+            V[:, 0] = apply_A(x)
+        v_axpby(-1, b, 1, V[:, 0]); V[:, 0] *= -1                # sub(b) ; chsgn()
+        e = np.zeros(kdim + 1, dtype=dt)
+        beta = v_norm(V[:, 0]); e[0] = beta
+        V[:, 0] *= dt.type(1) / dt.type(beta)
+        c = np.zeros(kdim, dtype=dt); s = np.zeros(kdim, dtype=dt)
+        if n_outer == 0:
+            res.append(abs(beta))
+        k = 0
+        for k in range(1, kdim + 1):
+            V[:, k] = apply_A(V[:, k - 1])
+            H[:k, k - 1], _ = dgs_vector(V[:, k], V[:, :k], kind)
+            H[k, k - 1] = v_norm(V[:, k])
+            if abs(H[k, k - 1]) > tol:
+                V[:, k] *= dt.type(1) / H[k, k - 1]
+            apply_givens_rotation(H[:k + 1, k - 1], c[:k], s[:k])
+            e[k] = -s[k - 1] * e[k - 1]; e[k - 1] = c[k - 1] * e[k - 1]
+            beta = abs(e[k])
+            n_iter += 1; n_inner += 1; res.append(abs(beta))
+            if abs(beta) < tol:
+                converged = True
+                break
+        else:
+            k = kdim + 1                                         # Fortran: the loop variable ends at kdim + 1
+        k = min(k, kdim)
+        y = np.linalg.solve(np.triu(H[:k, :k]), e[:k])           # trtrs('u', 'n', 'n')
+        dx = linear_combination(V[:, :k], y.astype(dt))
+        v_axpby(1, dx, 1, x)
+        V[:, 0] = apply_A(x); v_axpby(-1, b, 1, V[:, 0]); V[:, 0] *= -1
+        beta = v_norm(V[:, 0])
+        n_iter += 1; n_outer += 1; res.append(abs(beta))
+        if abs(beta) < tol:
+            converged = True
+            break
+    return (n_iter if converged else -n_iter), dict(n_iter=n_iter, n_inner=n_inner, n_outer=n_outer, res=res, converged=converged)
+
+
+def cg(apply_A, b, x, kind, maxiter=100):
+    dt = b.dtype
+    tol = ATOL[kind] + RTOL[kind] * v_norm(b)
+    r = np.zeros_like(b)
+    if v_norm(x) > 0:
+        r = apply_A(x)
+    v_axpby(-1, b, 1, r); r *= -1
+    p = r.copy(); rr_old = v_dot(r, r)
+    res, n_iter, converged = [np.sqrt(abs(rr_old))], 0, False
+    for _ in range(maxiter):
+        Ap = apply_A(p)
+        alpha = rr_old / v_dot(p, Ap)
+        v_axpby(alpha, p, 1, x)
+        v_axpby(-alpha, Ap, 1, r)
+        rr_new = v_dot(r, r)
+        residual = np.sqrt(abs(rr_new))
+        n_iter += 1; res.append(residual)
+        if residual < tol:
+            converged = True
+            break
+        beta = rr_new / rr_old
+        v_axpby(1, r, beta, p)
+        rr_old = rr_new
+    return (n_iter if converged else -n_iter), dict(n_iter=n_iter, res=res, converged=converged)
+
+
+@pytest.mark.parametrize("kind", ["d", "z"])
+def test_gmres_two_restatements_agree(oracle, kind):
+    """Restarted GMRES with several outer cycles: identical info / iteration counters, residual history and solution."""
+    dt = DT[kind]; n = 200
+    rng = np.random.default_rng(5)
+    A = np.asfortranarray((np.eye(n) * 6 + randn(rng, (n, n), dt) * 0.25).astype(dt))
+    b = randn(rng, n, dt)
+    x2 = np.zeros(n, dtype=dt); xo = np.zeros(n, dtype=dt)
+    # kind "z": the reference's hand-rolled complex rotation (submodule_utility_functions.fypp:173-190) uses c and s WITHOUT
+    # conjugates, so it is not unitary and |e(k+1)| is not the true residual: on this non-Hermitian matrix the restarted
+    # iteration stalls and later diverges (rounding differences between two evaluations are then amplified with it).
+    # Both restatements reproduce that literally; they are compared over the first three cycles, entry by entry relative to
+    # each entry.  (The product is tested against the same literal behaviour: test_gmres_vs_oracle[z].)
+    maxiter = 30 if kind == "d" else 2
+    info2, m2 = gmres(lambda v: (A @ v).astype(dt), b, x2, kind, kdim=12, maxiter=maxiter)
+    infoo, mo = oracle.gmres(oracle.Op.dense(A), b, xo, kdim=12, maxiter=maxiter)
+    assert info2 == infoo and m2["n_outer"] == mo["n_outer"] >= 2 and m2["n_inner"] == mo["n_inner"]
+    assert len(m2["res"]) == len(mo["res"])
+    r2, ro = np.array(m2["res"]), np.array(mo["res"])
+    assert (np.abs(r2 - ro) / np.abs(ro)).max() < 1e-8
+    assert np.linalg.norm(x2 - xo) < 1e-8 * np.linalg.norm(xo)
+    if kind == "d":
+        assert info2 > 0 and np.linalg.norm(A @ x2 - b) < 1e-6 * np.linalg.norm(b)
+    else:
+        # literal behaviour: the recomputed residual at the end of every cycle (entries 13, 26, 39) is LARGER than the last
+        # inner estimate |e(k+1)| -- the rotation is not norm-preserving
+        assert info2 < 0 and ro[13] > ro[12] and ro[26] > ro[25] and ro[39] > ro[38]
+
+
+@pytest.mark.parametrize("kind", ["d", "z"])
+def test_cg_two_restatements_agree(oracle, kind):
+    dt = DT[kind]; n = 160
+    rng = np.random.default_rng(6)
+    M = randn(rng, (n, n), dt)
+    A = np.asfortranarray((M @ M.conj().T / n + np.eye(n)).astype(dt))         # SPD / HPD
+    b = randn(rng, n, dt)
+    x2 = np.zeros(n, dtype=dt); xo = np.zeros(n, dtype=dt)
+    info2, m2 = cg(lambda v: (A @ v).astype(dt), b, x2, kind, maxiter=200)
+    infoo, mo = oracle.cg(oracle.Op.dense(A), b, xo, maxiter=200)
+    assert info2 == infoo > 0
+    assert np.abs(np.array(m2["res"]) - np.array(mo["res"])).max() < 1e-11 * mo["res"][0]
+    assert np.linalg.norm(x2 - xo) < 1e-11 * np.linalg.norm(xo)
