@@ -367,6 +367,9 @@ int lkb_eigs(lkb_op_t A, lkb_basis_t X, int nev, double* eigvals, double* residu
                 break;
             }
         }
+        // KNOWN DEVIATION: the reference's `exit arnoldi_factorization` leaves only the inner loop, so it
+        // restarts once more after convergence and post-processes the restarted H; here the converged factorisation is
+        // post-processed directly (same niter, same eigenvalues to rounding for k >= n, residuals of the returned pairs).
         if (conv >= nev) break;
         // Krylov-Schur restart (IterativeSolvers.fypp:1096-1100); note the loop index is kd+1 here
         int32_t nk = 0;

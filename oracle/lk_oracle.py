@@ -460,7 +460,11 @@ def krylov_schur(X: np.ndarray, H: np.ndarray):
 
 
 def eigs(A: Op, n: int, nev: int, x0: np.ndarray, kdim=None, tolerance=None, trans=False, max_restarts=200):
-    """IterativeSolvers.fypp:972-1143.  Returns (eigvals[nev], residuals[nev], X[n, nev], info=niter)."""
+    """IterativeSolvers.fypp:972-1143.  Returns (eigvals[nev], residuals[nev], X[n, nev], info=niter).
+    KNOWN DEVIATION from the literal control flow: the reference runs krylov_schur once more after
+    convergence and post-processes the restarted H; this restatement (like the product) post-processes the converged
+    factorisation.  Same niter, same eigenvalues to rounding whenever k >= n; tests/test_oracle_second_opinion.py holds the
+    literal flow and pins the equivalence."""
     kind = kind_of(x0.dtype)
     dt = DTYPES[kind]
     cplx = kind in "cz"

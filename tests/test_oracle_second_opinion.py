@@ -376,3 +376,186 @@ def test_cg_two_restatements_agree(oracle, kind):
     assert info2 == infoo > 0
     assert np.abs(np.array(m2["res"]) - np.array(mo["res"])).max() < 1e-11 * mo["res"][0]
     assert np.linalg.norm(x2 - xo) < 1e-11 * np.linalg.norm(xo)
+
+
+# ---- eighs (EIGHS/eighs.fypp:60-125) and svds (SVDS/svd_solvers.fypp:60-121): one Krylov step + one small dense factorisation
+# per iteration, residual = |beta * last row of the Ritz vectors| (IterativeSolvers.fypp:930-939), stop when nev converged ----
+def eighs(apply_A, n, nev, x0, kind, kdim, tol):
+    dt = DT[kind]
+    Xw = np.zeros((n, kdim + 1), dtype=dt, order="F"); Xw[:, 0] = x0 / v_norm(x0)
+    T = np.zeros((kdim + 1, kdim), dtype=dt)
+    ev = np.zeros(kdim); res = np.zeros(kdim); vec = np.zeros((kdim, kdim), dtype=dt)
+    k = 0
+    for k in range(1, kdim + 1):
+        # lanczos(A, Xwrk, T, info, kstart = k, kend = k): ONE step of the loop above
+        Xw[:, k] = apply_A(Xw[:, k - 1])
+        for i in range(max(1, k - 1), k + 1):
+            T[i - 1, k - 1] = v_dot(Xw[:, i - 1], Xw[:, k])
+            v_axpby(-T[i - 1, k - 1], Xw[:, i - 1], 1, Xw[:, k])
+        dgs_vector(Xw[:, k], Xw[:, :k], kind)
+        beta = v_norm(Xw[:, k]); T[k, k - 1] = beta
+        Xw[:, k] *= dt(1) / dt(beta)
+        ev[:] = 0; vec[:] = 0
+        Tk = T[:k, :k]
+        w, v = np.linalg.eigh(np.tril(Tk) + np.tril(Tk, -1).conj().T)          # eigh reads one triangle (lower here, as syev 'L')
+        ev[:k] = w; vec[:k, :k] = v
+        res[:k] = np.abs(beta * vec[k - 1, :k])
+        if int((res[:k] < tol).sum()) >= nev:
+            break
+    idx = np.argsort(ev, kind="stable")[::-1]                                   # sort_index(reverse = .true.)
+    k = min(k, kdim)
+    return ev[idx[:nev]], res[idx[:nev]], k
+
+
+def svds(A, nsv, u0, kind, kdim, tol):
+    dt = DT[kind]; m, n = A.shape
+    Uw = np.zeros((m, kdim + 1), dtype=dt, order="F"); Uw[:, 0] = u0 / v_norm(u0)
+    Vw = np.zeros((n, kdim + 1), dtype=dt, order="F"); B = np.zeros((kdim + 1, kdim), dtype=dt)
+    sv = np.zeros(kdim); res = np.zeros(kdim)
+    k = 0
+    for k in range(1, kdim + 1):
+        # bidiagonalization(A, Uwrk, Vwrk, B, info, kstart = k, kend = k, tol = tol): ONE step
+        Vw[:, k - 1] = (A.conj().T @ Uw[:, k - 1]).astype(dt)
+        if k > 1:
+            dgs_vector(Vw[:, k - 1], Vw[:, :k - 1], kind)
+        alpha = v_norm(Vw[:, k - 1]); B[k - 1, k - 1] = alpha
+        assert abs(alpha) > tol
+        Vw[:, k - 1] *= dt(1) / dt(alpha)
+        Uw[:, k] = (A @ Vw[:, k - 1]).astype(dt)
+        dgs_vector(Uw[:, k], Uw[:, :k], kind)
+        beta = v_norm(Uw[:, k]); B[k, k - 1] = beta
+        assert abs(beta) > tol
+        Uw[:, k] *= dt(1) / dt(beta)
+        u, s, vh = np.linalg.svd(B[:k, :k])
+        vmat = vh.conj().T                                                      # vmat = hermitian(vmat)
+        sv[:] = 0; sv[:k] = s
+        res[:k] = np.abs(B[k, k - 1] * vmat[k - 1, :k])
+        if int((res[:k] < tol).sum()) >= nsv:
+            break
+    k = min(k, kdim)
+    return sv[:nsv].copy(), res[:nsv].copy(), k
+
+
+@pytest.mark.parametrize("kind", ["d", "z"])
+def test_eighs_two_restatements_agree(oracle, kind):
+    dt = DT[kind]; n, nev, kdim = 150, 4, 60
+    rng = np.random.default_rng(7)
+    Q, _ = np.linalg.qr(randn(rng, (n, n), dt))
+    lam = np.concatenate([[40.0, 33.0, 27.0, 22.0], np.linspace(0.0, 10.0, n - 4)])
+    A = np.asfortranarray(((Q * lam) @ Q.conj().T).astype(dt)); A = np.asfortranarray(((A + A.conj().T) / 2).astype(dt))
+    x0 = randn(rng, n, dt)
+    ev2, res2, k2 = eighs(lambda v: (A @ v).astype(dt), n, nev, x0.copy(), kind, kdim, 1e-8)
+    evo, reso, _, ko = oracle.eighs(oracle.Op.dense(A), n, nev, x0.copy(), kdim=kdim, tolerance=1e-8)
+    assert k2 == ko < kdim                                      # same iteration count (= info), converged before kdim
+    assert np.abs(ev2 - evo).max() < 1e-11 * np.abs(evo).max()
+    assert np.abs(ev2 - lam[:4]).max() < 1e-7                   # and the known answer
+    assert np.abs(res2 - reso).max() < 1e-9
+
+
+@pytest.mark.parametrize("kind", ["d", "z"])
+def test_svds_two_restatements_agree(oracle, kind):
+    dt = DT[kind]; m, n, nsv, kdim = 140, 100, 3, 60
+    rng = np.random.default_rng(8)
+    U, _ = np.linalg.qr(randn(rng, (m, n), dt)); V, _ = np.linalg.qr(randn(rng, (n, n), dt))
+    sig = np.concatenate([[30.0, 24.0, 19.0], np.linspace(8.0, 0.5, n - 3)])
+    A = np.asfortranarray(((U * sig) @ V.conj().T).astype(dt))
+    u0 = randn(rng, m, dt)
+    s2, res2, k2 = svds(A, nsv, u0.copy(), kind, kdim, 1e-8)
+    so, reso, _, _, ko = oracle.svds(oracle.Op.dense(A), nsv, u0.copy(), kdim=kdim, tolerance=1e-8)
+    assert k2 == ko < kdim
+    assert np.abs(s2 - so).max() < 1e-11 * so.max() and np.abs(s2 - sig[:3]).max() < 1e-7
+    assert np.abs(res2 - reso).max() < 1e-9
+
+
+# ---- eigs with Krylov-Schur restarts, LITERAL control flow of IterativeSolvers.fypp:1052-1131 + BaseKrylov.fypp:782-834 --------
+def _eig_real_pair(Hk):
+    """stdlib `eig` on a real matrix = geev: complex eigenvalues, eigenvectors in LAPACK's real-pair storage."""
+    from scipy.linalg import lapack
+    wr, wi, vl, vr, info = lapack.dgeev(np.asfortranarray(Hk), compute_vl=0, compute_vr=1)
+    assert info == 0
+    return wr + 1j * wi, vr
+
+
+def _krylov_schur_literal(X, H):
+    from scipy.linalg import lapack
+    kdim = X.shape[1] - 1
+    cplx = np.iscomplexobj(H)
+    Hk = np.asfortranarray(H[:kdim, :kdim])
+    if cplx:
+        T, sdim, w, Z, work, info = lapack.zgees(lambda x: False, Hk, sort_t=0); ev = w
+    else:
+        T, sdim, wr, wi, Z, work, info = lapack.dgees(lambda x, y: False, Hk, sort_t=0); ev = wr + 1j * wi
+    assert info == 0
+    selected = np.abs(ev) > np.median(np.abs(ev))                 # median_selector, IterativeSolvers.fypp:1136-1141
+    n = int(selected.sum())
+    out = (lapack.ztrsen if cplx else lapack.dtrsen)(selected.astype(np.int32), T, Z, job="N", wantq=1)
+    T, Z = out[0], out[1]
+    assert out[-1] == 0
+    Xn = X[:, :kdim] @ Z[:, :n]                                    # linear_combination(Xwrk, X(:kdim), Z(:, :n))
+    b = H[kdim, :] @ Z
+    X[:, :n] = Xn; X[:, n] = X[:, kdim]; X[:, n + 1:] = 0
+    H[:kdim, :] = T; H[n, :] = b; H[n + 1:, :] = 0; H[:, n:] = 0
+    return n
+
+
+def eigs_literal(apply_A, n, nev, x0, kind, kdim, tol):
+    dt = DT[kind]; cplx = kind in "cz"
+    Xw = np.zeros((n, kdim + 1), dtype=dt, order="F"); Xw[:, 0] = x0 / v_norm(x0)
+    H = np.zeros((kdim + 1, kdim), dtype=dt)
+    kstart, conv, niter, k = 1, 0, 0, 0
+    while conv < nev:
+        for k in range(kstart, kdim + 1):
+            Xw[:, k] = apply_A(Xw[:, k - 1])                       # arnoldi(A, Xwrk, H, info, kstart = k, kend = k)
+            H[:k, k - 1], _ = dgs_vector(Xw[:, k], Xw[:, :k], kind)
+            beta = v_norm(Xw[:, k]); H[k, k - 1] = beta
+            Xw[:, k] *= dt(1) / dt(beta)
+            if cplx:
+                vals, vecs = np.linalg.eig(H[:k, :k])
+                res = np.abs(beta * vecs[k - 1, :k])
+            else:
+                vals, vecs = _eig_real_pair(H[:k, :k])
+                res = np.zeros(k)
+                for i in range(k):
+                    if vals[i].imag > 0:
+                        alpha = abs(complex(vecs[k - 1, i], vecs[k - 1, i + 1]))
+                    elif vals[i].imag < 0:
+                        alpha = abs(complex(vecs[k - 1, i - 1], vecs[k - 1, i]))
+                    else:
+                        alpha = abs(vecs[k - 1, i])
+                    res[i] = abs(beta * alpha)
+            niter += 1
+            conv = int((res < tol).sum())
+            if conv >= nev:
+                break
+        else:
+            k = kdim + 1
+        # NOTE the reference restarts ONCE MORE after convergence: `exit arnoldi_factorization` leaves only the inner loop, the
+        # krylov_schur call below it still runs before `do while (conv < nev)` is re-evaluated (IterativeSolvers.fypp:1088-1099)
+        kstart = _krylov_schur_literal(Xw, H) + 1
+    k = min(k, kdim)
+    vals = np.linalg.eigvals(H[:k, :k])                            # eig of the RESTARTED matrix (:1108-1110)
+    order = np.argsort(np.abs(vals), kind="stable")[::-1]
+    return vals[order[:nev]], niter, k, kstart - 1
+
+
+@pytest.mark.parametrize("kind", ["d", "z"])
+def test_eigs_literal_flow_vs_oracle(oracle, kind):
+    """The oracle (and the product, lkb_eig.cu) post-process the CONVERGED factorisation; the reference restarts once more
+    first and post-processes the restarted Hessenberg matrix ("known deviations").  When the iteration
+    converges at a step k >= n (n = size of the retained Schur block -- always the case after the first restart) the two
+    flows return the same eigenvalues to rounding and the same info = niter; this test pins exactly that."""
+    dt = DT[kind]; n, nev, kdim = 120, 4, 24
+    rng = np.random.default_rng(9)
+    Q, _ = np.linalg.qr(randn(rng, (n, n), dt))
+    lam = np.concatenate([[9.0, -8.2, 7.1, 6.3], np.linspace(-3.0, 3.0, n - 4)]).astype(dt)
+    Npart = np.triu(randn(rng, (n, n), dt), 1) * 0.02               # non-normal part: a genuinely nonsymmetric operator
+    A = np.asfortranarray((Q @ (np.diag(lam) + Npart) @ Q.conj().T).astype(dt))
+    x0 = randn(rng, n, dt)
+    ev2, niter2, k2, nkeep = eigs_literal(lambda v: (A @ v).astype(dt), n, nev, x0.copy(), kind, kdim, 1e-9)
+    evo, reso, _, niter_o = oracle.eigs(oracle.Op.dense(A), n, nev, x0.copy(), kdim=kdim, tolerance=1e-9)
+    assert niter2 == niter_o > kdim                                 # several Krylov-Schur cycles, identical iteration count
+    assert k2 >= nkeep                                              # the regime the statement above is about
+    key = lambda z: (-round(abs(z), 6), round(z.imag, 6))
+    a = np.array(sorted(ev2, key=key)); b = np.array(sorted(evo, key=key))
+    assert np.abs(a - b).max() < 1e-9 * np.abs(b).max()
+    assert np.abs(np.sort(np.abs(b))[::-1] - np.array([9.0, 8.2, 7.1, 6.3])).max() < 1e-6
