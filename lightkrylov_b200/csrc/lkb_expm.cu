@@ -164,7 +164,11 @@ int lkb_kexpm_vec(lkb_vec_t cvec, lkb_op_t A, lkb_vec_t b, double tau, double to
         for (int j = 0; j < kp; ++j)
             for (int i = 0; i < kp; ++i) Hk[i + (size_t)kp * j] = tau * load_kind(kind, H.data(), (size_t)i + (size_t)ldh * j);
         if (!dense_expm(kp, Hk, E)) { set_error("kexpm_vec: singular Pade denominator"); return cleanup(LKB_ERR_LAPACK); }
-        err_est = breakdown ? 0.0 : std::abs(E[(size_t)(kp - 1)] * beta);           // |E(kp,1) beta| (:213)
+        // |E(kp,1) beta| (:213).  The reference writes merge(0, abs(E(kp,1)*beta), info == k), but `info` was overwritten with -2
+        // three lines earlier when the breakdown was detected (:201), so the estimate is NOT zeroed on breakdown: the loop goes
+        // on with the refilled vector and stops two steps later, where E(kp,1) is exactly zero (H(k+1,k) = 0 decouples the
+        // blocks).  Reproduced literally: info = k + 2 after a breakdown at step k unless |E(k,1) beta| <= tol already.
+        err_est = std::abs(E[(size_t)(kp - 1)] * beta);
         KX_TRY(bcast_host(c, &err_est, sizeof(double)));
         if (err_est <= tol || k == nk) {
             // c = beta * X(:kp) E(:kp,1)   (:209-210; the reference forms it every step, only the last one survives)

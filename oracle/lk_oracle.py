@@ -621,7 +621,9 @@ def kexpm_vec(A: Op, b: np.ndarray, tau: float, tol: float, trans: bool = False,
             kp = k
         E = expm_pade10(tau * H[:kp, :kp])
         c = (beta * (X[:, :kp] @ E[:kp, 0])).astype(dt)
-        err_est = 0.0 if breakdown else abs(E[kp - 1, 0] * beta)
+        # merge(0, abs(E(kp,1)*beta), info == k) with info already overwritten by -2 on breakdown (ExpmLib.fypp:199-213):
+        # the estimate is NOT zeroed on breakdown (literal; tests/test_oracle_second_opinion.py)
+        err_est = abs(E[kp - 1, 0] * beta)
         if err_est <= tol:
             break
     return c, (kp if err_est <= tol else -1)

@@ -190,3 +190,21 @@ def test_kexpm_vec_vs_oracle(lk, ctx, oracle, kind):
     ct = lk.Vector(ctx, kind, n)
     assert lk.kexpm(ct, A, b, 0.1, tol, trans=True) == info
     assert np.linalg.norm(ct.get() - co) < (1e-10 if kind in "dz" else 1e-4) * np.linalg.norm(co)
+
+
+@pytest.mark.parametrize("kind", ["d", "z"])
+def test_kexpm_vec_breakdown_literal_info(lk, ctx, oracle, kind):
+    """Arnoldi breakdown inside kexpm_vec: b spans a 3-dimensional invariant subspace of a diagonal operator.  The reference
+    overwrites `info` with -2 before its merge(0, ..., info == k), so the error estimate is not zeroed at the breakdown step;
+    the loop continues on the refilled vector and stops two steps later with info = kp = 5 and the exact vector
+    (ExpmLib.fypp:199-226; literal flow pinned on the CPU by tests/test_oracle_second_opinion.py)."""
+    dt = lk.DTYPES[kind]; n = 96
+    D = np.asfortranarray(np.diag(np.arange(1, n + 1)).astype(dt))
+    A = lk.LinOp.dense(ctx, D); Ao = oracle.Op.dense(D)
+    bh = np.zeros(n, dtype=dt); bh[:3] = [1.0, 2.0, -1.5]
+    b = lk.Vector(ctx, kind, n).put(bh); c = lk.Vector(ctx, kind, n)
+    info = lk.kexpm(c, A, b, 0.2, 1e-12)
+    co, oinfo = oracle.kexpm_vec(Ao, bh, 0.2, 1e-12)
+    assert info == oinfo == 5
+    exact = np.exp(0.2 * np.arange(1, n + 1)) * bh
+    assert np.linalg.norm(c.get() - exact) < 1e-12 * np.linalg.norm(exact)

@@ -559,3 +559,62 @@ def test_eigs_literal_flow_vs_oracle(oracle, kind):
     a = np.array(sorted(ev2, key=key)); b = np.array(sorted(evo, key=key))
     assert np.abs(a - b).max() < 1e-9 * np.abs(b).max()
     assert np.abs(np.sort(np.abs(b))[::-1] - np.array([9.0, 8.2, 7.1, 6.3])).max() < 1e-6
+
+
+# ---- kexpm_vec, LITERAL control flow of src/Expm/ExpmLib.fypp:176-230 (dense expm = scipy's here, not the oracle's Pade-10) ----
+def kexpm_vec_literal(apply_A, b, tau, tol, kind, nk=100):
+    import scipy.linalg as sla
+    dt = DT[kind]; n = b.size
+    beta = v_norm(b)
+    X = np.zeros((n, nk + 1), dtype=dt, order="F"); X[:, 0] = b / dt(beta)
+    H = np.zeros((nk + 1, nk + 1), dtype=dt)
+    c = np.zeros(n, dtype=dt); err_est = 0.0; kp = 1
+    rng = np.random.default_rng(99)
+    for k in range(1, nk + 1):
+        kp = k + 1
+        # arnoldi(A, X, H, info, kstart = k, kend = k): one step, incl. qr_no_pivoting's refill on breakdown (qr.fypp:146-162)
+        X[:, k] = apply_A(X[:, k - 1])
+        H[:k, k - 1], _ = dgs_vector(X[:, k], X[:, :k], kind)
+        bk = v_norm(X[:, k]); info = 0
+        if bk < ATOL[kind]:
+            H[k, k - 1] = 0
+            X[:, k] = randn(rng, n, dt)
+            dgs_vector(X[:, k], X[:, :k], kind)
+            X[:, k] /= dt(v_norm(X[:, k]))
+            info = k                                              # arnoldi: |H(k+1,k)| < tol => info = k
+        else:
+            H[k, k - 1] = bk
+            X[:, k] *= dt(1) / dt(bk)
+        if info == k:
+            kp = k
+            info = -2
+        E = sla.expm(tau * H[:kp, :kp])
+        c = (dt(beta) * (X[:, :kp] @ E[:kp, 0])).astype(dt)
+        err_est = 0.0 if info == k else abs(E[kp - 1, 0] * beta)   # merge(0, abs(E(kp,1)*beta), info == k): info is -2 by now
+        if err_est <= tol:
+            break
+    return c, (kp if err_est <= tol else -1)
+
+
+@pytest.mark.parametrize("kind", ["d", "z"])
+def test_kexpm_vec_two_restatements_agree(oracle, kind):
+    import scipy.linalg as sla
+    dt = DT[kind]; n = 90
+    rng = np.random.default_rng(10)
+    A = np.asfortranarray((randn(rng, (n, n), dt) / np.sqrt(n) - 0.5 * np.eye(n)).astype(dt))
+    b = randn(rng, n, dt)
+    c2, info2 = kexpm_vec_literal(lambda v: (A @ v).astype(dt), b, 0.3, 1e-10, kind)
+    co, infoo = oracle.kexpm_vec(oracle.Op.dense(A), b, 0.3, 1e-10)
+    assert info2 == infoo and 1 < info2 < 60
+    assert np.linalg.norm(c2 - co) < 1e-10 * np.linalg.norm(co)
+    assert np.linalg.norm(co - sla.expm(0.3 * A) @ b) < 1e-8 * np.linalg.norm(co)
+    # breakdown: b inside a 3-dimensional invariant subspace of a diagonal operator.  Literal behaviour: the estimate is not
+    # zeroed at the breakdown step k = 3 (|E(3,1) beta| ~ 0.1 > tol), the loop continues on the refilled vector and stops at
+    # step 4 with kp = 5, where E(kp,1) is exactly zero -- both restatements, same info, same (exact) vector
+    D = np.asfortranarray(np.diag(np.arange(1, n + 1)).astype(dt))
+    b3 = np.zeros(n, dtype=dt); b3[:3] = [1.0, 2.0, -1.5]
+    c2, info2 = kexpm_vec_literal(lambda v: (D @ v).astype(dt), b3, 0.2, 1e-12, kind)
+    co, infoo = oracle.kexpm_vec(oracle.Op.dense(D), b3, 0.2, 1e-12)
+    assert info2 == infoo == 5
+    exact = np.exp(0.2 * np.arange(1, n + 1)) * b3
+    assert np.linalg.norm(c2 - exact) < 1e-12 * np.linalg.norm(exact) and np.linalg.norm(co - exact) < 1e-12 * np.linalg.norm(exact)
