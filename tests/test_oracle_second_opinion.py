@@ -263,7 +263,8 @@ def apply_givens_rotation(h, c, s):
         h[k] = 0
 
 
-def gmres(apply_A, b, x, kind, kdim=30, maxiter=10):
+def gmres(apply_A, b, x, kind, kdim=30, maxiter=10, precond=None, flexible=False):
+    """gmres.fypp:125-238; flexible = fgmres.fypp:130-215 (Z(k) = M_k^-1 V(k) stored, dx = Z(:k) y, no post-application)."""
     dt = b.dtype
     tol = ATOL[kind] + RTOL[kind] * v_norm(b)
     n = b.size
@@ -280,8 +281,13 @@ def gmres(apply_A, b, x, kind, kdim=30, maxiter=10):
         if n_outer == 0:
             res.append(abs(beta))
         k = 0
+        Z = np.zeros((n, kdim), dtype=dt, order="F")
         for k in range(1, kdim + 1):
-            V[:, k] = apply_A(V[:, k - 1])
+            wrk = V[:, k - 1].copy()                               # wrk = V(k)   /   copy(Z(k), V(k))
+            if precond is not None:
+                wrk = precond(wrk, k)                              # preconditioner%apply(wrk, k, beta, tol)
+            Z[:, k - 1] = wrk
+            V[:, k] = apply_A(wrk)
             H[:k, k - 1], _ = dgs_vector(V[:, k], V[:, :k], kind)
             H[k, k - 1] = v_norm(V[:, k])
             if abs(H[k, k - 1]) > tol:
@@ -297,7 +303,9 @@ def gmres(apply_A, b, x, kind, kdim=30, maxiter=10):
             k = kdim + 1                                         # Fortran: the loop variable ends at kdim + 1
         k = min(k, kdim)
         y = np.linalg.solve(np.triu(H[:k, :k]), e[:k])           # trtrs('u', 'n', 'n')
-        dx = linear_combination(V[:, :k], y.astype(dt))
+        dx = linear_combination((Z if flexible else V)[:, :k], y.astype(dt))
+        if precond is not None and not flexible:
+            dx = precond(dx, 0)                                    # preconditioner%apply(dx)
         v_axpby(1, dx, 1, x)
         V[:, 0] = apply_A(x); v_axpby(-1, b, 1, V[:, 0]); V[:, 0] *= -1
         beta = v_norm(V[:, 0])
@@ -618,3 +626,27 @@ def test_kexpm_vec_two_restatements_agree(oracle, kind):
     assert info2 == infoo == 5
     exact = np.exp(0.2 * np.arange(1, n + 1)) * b3
     assert np.linalg.norm(c2 - exact) < 1e-12 * np.linalg.norm(exact) and np.linalg.norm(co - exact) < 1e-12 * np.linalg.norm(exact)
+
+
+@pytest.mark.parametrize("mode", ["right-preconditioned gmres", "fgmres"])
+def test_preconditioned_gmres_two_restatements_agree(oracle, mode):
+    """gmres with a (fixed) right preconditioner and fgmres with a preconditioner that changes with the inner step k
+    (gmres.fypp:153-156, 205-206; fgmres.fypp:158-161, 205-206)."""
+    kind, dt, n = "d", np.float64, 180
+    rng = np.random.default_rng(11)
+    dg = np.linspace(1.0, 40.0, n)
+    A = np.asfortranarray(np.diag(dg) + 0.4 * randn(rng, (n, n), dt))
+    b = randn(rng, n, dt)
+    flexible = mode == "fgmres"
+    scale = (lambda k: 1.0 + 0.2 * (k % 3)) if flexible else (lambda k: 1.0)
+    prec2 = lambda v, k: (v / dg) * scale(k)
+
+    def prec_o(v, k=0):
+        v[:] = (v / dg) * scale(k)
+    x2 = np.zeros(n); xo = np.zeros(n)
+    info2, m2 = gmres(lambda v: A @ v, b, x2, kind, kdim=10, maxiter=40, precond=prec2, flexible=flexible)
+    infoo, mo = oracle.gmres(oracle.Op.dense(A), b, xo, kdim=10, maxiter=40, precond=prec_o, flexible=flexible)
+    assert info2 == infoo > 0 and m2["n_outer"] == mo["n_outer"] >= 2
+    assert np.abs(np.array(m2["res"]) - np.array(mo["res"])).max() < 1e-10 * mo["res"][0]
+    assert np.linalg.norm(x2 - xo) < 1e-10 * np.linalg.norm(xo)
+    assert np.linalg.norm(A @ x2 - b) < 1e-6 * np.linalg.norm(b)
