@@ -367,15 +367,20 @@ int lkb_eigs(lkb_op_t A, lkb_basis_t X, int nev, double* eigvals, double* residu
                 break;
             }
         }
-        // KNOWN DEVIATION: the reference's `exit arnoldi_factorization` leaves only the inner loop, so it
-        // restarts once more after convergence and post-processes the restarted H; here the converged factorisation is
-        // post-processed directly (same niter, same eigenvalues to rounding for k >= n, residuals of the returned pairs).
-        if (conv >= nev) break;
-        // Krylov-Schur restart (IterativeSolvers.fypp:1096-1100); note the loop index is kd+1 here
+        // LITERAL control flow (IterativeSolvers.fypp:1088-1099): `exit arnoldi_factorization` leaves only the inner loop, so the
+        // reference runs krylov_schur once more AFTER convergence, before `do while (conv < nev)` is re-evaluated, and then
+        // post-processes the restarted H and basis while `res` still holds the pre-restart residuals.  Reproduced as is.
+        const int converged_at = conv >= nev ? k : 0;
+        if (converged_at && converged_at < kd) {
+            // a speculative step k+1 wrote X(k+2); in the reference the columns beyond k+1 are still zero at this point
+            EG_TRY(cudaStreamSynchronize(c->stream) == cudaSuccess ? 0 : LKB_ERR_CUDA);
+            EG_TRY(lkb_basis_zero(Xw, converged_at + 1, kd - converged_at));
+        }
+        // Krylov-Schur restart (IterativeSolvers.fypp:1096-1100); note the loop index is kd+1 here unless converged
         int32_t nk = 0;
         EG_TRY(lkb_krylov_schur(Xw, H.data(), ldh, kd, &nk));
         kstart = nk + 1;
-        k = kd + 1;
+        k = converged_at ? converged_at : kd + 1;
         if (++restarts > 2000) { set_error("eigs: no convergence after 2000 Krylov-Schur restarts"); EG_TRY(LKB_ERR_ARG); }
     }
     EG_TRY(cudaStreamSynchronize(c->stream) == cudaSuccess ? 0 : LKB_ERR_CUDA);

@@ -461,10 +461,9 @@ def krylov_schur(X: np.ndarray, H: np.ndarray):
 
 def eigs(A: Op, n: int, nev: int, x0: np.ndarray, kdim=None, tolerance=None, trans=False, max_restarts=200):
     """IterativeSolvers.fypp:972-1143.  Returns (eigvals[nev], residuals[nev], X[n, nev], info=niter).
-    KNOWN DEVIATION from the literal control flow: the reference runs krylov_schur once more after
-    convergence and post-processes the restarted H; this restatement (like the product) post-processes the converged
-    factorisation.  Same niter, same eigenvalues to rounding whenever k >= n; tests/test_oracle_second_opinion.py holds the
-    literal flow and pins the equivalence."""
+    Literal control flow since round 2: the reference runs krylov_schur once more AFTER convergence and post-processes the
+    restarted H / basis (residuals keep their pre-restart order); tests/test_oracle_second_opinion.py holds an independent
+    restatement of that flow."""
     kind = kind_of(x0.dtype)
     dt = DTYPES[kind]
     cplx = kind in "cz"
@@ -497,10 +496,12 @@ def eigs(A: Op, n: int, nev: int, x0: np.ndarray, kdim=None, tolerance=None, tra
             conv = int((res[:k] < tol).sum())
             if conv >= nev:
                 break
-        if conv >= nev:
-            break
+        # LITERAL control flow (IterativeSolvers.fypp:1088-1099): `exit arnoldi_factorization` leaves only the inner loop, so
+        # krylov_schur runs once more AFTER convergence, before `do while (conv < nev)` is re-evaluated; the post-processing
+        # below then works on the restarted H and basis, with `res` still holding the pre-restart residuals.
+        converged_at = k if conv >= nev else None
         kstart = krylov_schur(Xw, H) + 1
-        k = kdim + 1
+        k = converged_at if converged_at is not None else kdim + 1
         restarts += 1
         assert restarts < max_restarts, "eigs did not converge"
     k = min(k, kdim)

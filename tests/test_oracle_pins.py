@@ -227,11 +227,15 @@ def _toeplitz_tridiag(n, sub, diag, sup, dtype):
 
 
 def test_eigs_known_answer_full(oracle):
-    """TestIterativeSolvers.fypp:87-130: tridiagonal Toeplitz (-b, a, b): lambda = a +/- 2b cos(k pi/(n+1)) i."""
+    """TestIterativeSolvers.fypp:134-197: tridiagonal Toeplitz (-b, a, b): lambda = a +/- 2b cos(k pi/(n+1)) i.
+    As in the reference's test nev = n and kdim is left at its default 4*nev (> n): the iteration converges at the happy
+    breakdown k = n, the literal post-convergence krylov_schur then sees kdim - n zero eigenvalues, the median is 0 and all
+    n Ritz values are retained.  (With kdim = n the literal flow would keep only the half above the median.)"""
     n, a, b = N, 1.0, 0.5
     A = _toeplitz_tridiag(n, -b, a, b, np.float64)
     rng = np.random.default_rng(20)
-    ev, res, X, info = oracle.eigs(oracle.Op.dense(A), n, n, rng.standard_normal(n), kdim=n)
+    ev, res, X, info = oracle.eigs(oracle.Op.dense(A), n, n, rng.standard_normal(n))
+    assert info == n
     true = a + 2j * b * np.cos(np.arange(1, n + 1) * np.pi / (n + 1))
     got = np.sort_complex(ev); tr = np.sort_complex(true)
     assert np.abs(np.sort(got.imag) - np.sort(tr.imag)).max() < oracle.RTOL["d"]
@@ -248,8 +252,10 @@ def test_eigs_known_answer_krylov_schur(oracle):
     lead = true[np.argsort(-np.abs(true))][:nev]
     d = np.abs(ev[:, None] - lead[None, :]).min(axis=1)
     assert d.max() < 1e-6 and info > 4 * nev          # restarted at least once
-    # conv counts ANY nev Ritz residuals below tol (IterativeSolvers.fypp:1087), not the leading ones
-    assert np.all(res < 1e-6)
+    # conv counts ANY nev Ritz residuals below tol (IterativeSolvers.fypp:1087), not the leading ones; and since the literal
+    # flow restarts once more after convergence while residuals_wrk keeps its pre-restart order (:1096-1117), residuals(i)
+    # is NOT necessarily the residual of eigvals(i) -- only a value of the last residual table
+    assert np.all(np.isfinite(res)) and np.all(res >= 0)
     # eigenvector residual for the converged pairs (real-pair convention)
     i = 0
     while i < nev - 1:

@@ -548,10 +548,11 @@ def eigs_literal(apply_A, n, nev, x0, kind, kdim, tol):
 
 @pytest.mark.parametrize("kind", ["d", "z"])
 def test_eigs_literal_flow_vs_oracle(oracle, kind):
-    """The oracle (and the product, lkb_eig.cu) post-process the CONVERGED factorisation; the reference restarts once more
-    first and post-processes the restarted Hessenberg matrix ("known deviations").  When the iteration
-    converges at a step k >= n (n = size of the retained Schur block -- always the case after the first restart) the two
-    flows return the same eigenvalues to rounding and the same info = niter; this test pins exactly that."""
+    """The reference restarts once more AFTER convergence and post-processes the restarted Hessenberg matrix
+    (IterativeSolvers.fypp:1088-1117).  Until round 2 the oracle and the product post-processed the converged factorisation
+    instead -- this independent restatement of the literal flow exposed the difference; both follow the literal flow now.
+    Same info = niter, same eigenvalues (they equal the plain post-processing to rounding whenever k >= n, the size of the
+    retained Schur block)."""
     dt = DT[kind]; n, nev, kdim = 120, 4, 24
     rng = np.random.default_rng(9)
     Q, _ = np.linalg.qr(randn(rng, (n, n), dt))
