@@ -115,6 +115,10 @@ int lkb_orthogonalize_against_basis(lkb_basis_t X, int j, lkb_basis_t W, int wco
                                     int32_t if_chk_orthonormal, void* beta, int ldbeta, int32_t* info);
 /* qr(Q(:p), R, info, tol)  no pivoting   src/Krylov/qr.fypp:116-167, BaseKrylov.fypp:395-417 */
 int lkb_qr(lkb_basis_t Q, int col0, int p, void* R, int ldr, double tol, int32_t* info);
+/* qr(Q(:p), R, perm, info, tol)  with column pivoting   src/Krylov/qr.fypp:32-107 (+ swap_columns :174-201), BaseKrylov.fypp:395-417.
+ * In place on columns [col0, col0+p): A(:, perm) = Q R.  perm (p entries) is 1-based as the reference returns it.  info = j > 0:
+ * numerical rank j-1, the remaining columns are a random orthonormal completion and their R entries are zero. */
+int lkb_qr_pivoting(lkb_basis_t Q, int col0, int p, void* R, int ldr, int32_t* perm, double tol, int32_t* info);
 
 /* ---- abstract_linop : src/AbstractTypes/AbstractLinops.fypp:58-87, 204-256, 391-461 ----- */
 /* coef = (center, -x, +x, -y, +y[, -z, +z]) of kind `kind`; (nx, ny[, nz]) is the GLOBAL grid,
@@ -217,6 +221,11 @@ int lkb_svds(lkb_op_t A, lkb_basis_t U, double* S, lkb_basis_t V, int nsv, doubl
  * the (k+1) x (k+1) extended Hessenberg matrix (stdlib_linalg `expm`: Pade 10 + scaling and squaring, restated on the host).
  * info = dimension used when |E(kp,1) beta| <= tol, -1 when not converged within kdim (<= 0: 100) steps. */
 int lkb_kexpm_vec(lkb_vec_t c, lkb_op_t A, lkb_vec_t b, double tau, double tol, int32_t* info, int32_t trans, int32_t kdim);
+/* kexpm_mat(C, A, B, tau, tol, info, trans, kdim)  src/Expm/ExpmLib.fypp:234-362: C(:, :p) = exp(tau A) B(:, :p) by block Arnoldi with
+ * blksize p = size(B) (pivoting QR of B, dense expm of the extended block-Hessenberg matrix per block step, error estimate
+ * ||E(kp+1:kpp, :p) R||_F).  info = dimension used when the estimate is <= tol, -1 when not converged within kdim*p block steps
+ * (kdim <= 0: 100) -- the reference's loop bound; the work basis holds p*(kdim*p + 1) vectors, as the reference allocates. */
+int lkb_kexpm_mat(lkb_basis_t C, lkb_op_t A, lkb_basis_t B, int p, double tau, double tol, int32_t* info, int32_t trans, int32_t kdim);
 /* on-disk formats of the spectral solvers (IterativeSolvers.fypp:882-963).  write_results: the text table the reference
  * rewrites every step as eigs_output.txt / eighs_output.txt / svds_output.txt ('(I6,4(2X,E16.9),2X,L4)'); vals = k reals or
  * k (re, im) pairs, res is sorted ascending in place as the reference does.  save_eigenspectrum: NPY 1.0, Fortran order,

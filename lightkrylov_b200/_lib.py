@@ -84,6 +84,7 @@ SIGNATURES = {
     "lkb_dgs_step": (_i, [_vp, _i, _vp, _i, _i, _i32, _vp, _i, _P(_i32)]),
     "lkb_orthogonalize_against_basis": (_i, [_vp, _i, _vp, _i, _i, _i32, _vp, _i, _P(_i32)]),
     "lkb_qr": (_i, [_vp, _i, _i, _vp, _i, _d, _P(_i32)]),
+    "lkb_qr_pivoting": (_i, [_vp, _i, _i, _vp, _i, _P(_i32), _d, _P(_i32)]),
     "lkb_op_stencil5_create": (_i, [_vp, _i, _i64, _i64, _vp, _i64, _i64, _P(_vp)]),
     "lkb_op_stencil7_create": (_i, [_vp, _i, _i64, _i64, _i64, _vp, _i64, _i64, _P(_vp)]),
     "lkb_op_csr_create": (_i, [_vp, _i, _i64, _i64, _vp, _vp, _vp, _P(_vp)]),
@@ -112,6 +113,7 @@ SIGNATURES = {
     "lkb_eighs": (_i, [_vp, _vp, _i, _P(_d), _P(_d), _P(_i32), _vp, _i32, _d]),
     "lkb_svds": (_i, [_vp, _vp, _P(_d), _vp, _i, _P(_d), _P(_i32), _vp, _i32, _d]),
     "lkb_kexpm_vec": (_i, [_vp, _vp, _vp, _d, _d, _P(_i32), _i32, _i32]),
+    "lkb_kexpm_mat": (_i, [_vp, _vp, _vp, _i, _d, _d, _P(_i32), _i32, _i32]),
     "lkb_write_results": (_i, [C.c_char_p, _i32, _P(_d), _P(_d), _i32, _d]),
     "lkb_save_eigenspectrum": (_i, [C.c_char_p, _i32, _i32, _P(_d), _P(_d), _i32]),
     "lkb_set_lapack": (_i, [C.c_char_p, C.c_char_p, C.c_char_p]),

@@ -505,6 +505,18 @@ def qr(Q: Basis, col0: int = 0, p: Optional[int] = None, tol: float = -1.0):
     return info.value, R
 
 
+def qr_pivoting(Q: Basis, col0: int = 0, p: Optional[int] = None, tol: float = -1.0):
+    """qr(Q, R, perm, info, tol) with column pivoting (src/Krylov/qr.fypp:32-107): in place, A[:, perm] = Q R.
+    Returns (info, R, perm) with perm 0-based (the C ABI / the reference return it 1-based)."""
+    p = Q.ncols - col0 if p is None else p
+    R = np.zeros((p, p), dtype=DTYPES[Q.kind], order="F")
+    perm = np.zeros(p, dtype=np.int32)
+    info = C.c_int32()
+    check(Q.ctx.lib.lkb_qr_pivoting(Q.h, col0, p, R.ctypes.data, p, perm.ctypes.data_as(C.POINTER(C.c_int32)), tol,
+                                    C.byref(info)), "qr_pivoting")
+    return info.value, R, perm.astype(np.int64) - 1
+
+
 def _wrap_precond(preconditioner):
     """preconditioner(vec_ptr, n_local, iter, current_residual, target_residual, stream) -> None/int"""
     return _lib.PRECOND_FN(lambda user, v, n, it, cur, tgt, stream: int(preconditioner(v, n, it, cur, tgt, stream) or 0))
@@ -613,6 +625,15 @@ def kexpm(c: Vector, A: LinOp, b: Vector, tau: float, tol: float, trans: bool = 
     """kexpm_vec(c, A, b, tau, tol, info, trans, kdim)  (src/Expm/ExpmLib.fypp:128-232): c = exp(tau A) b; returns info."""
     info = C.c_int32()
     check(A.ctx.lib.lkb_kexpm_vec(c.h, A.h, b.h, float(tau), float(tol), C.byref(info), int(trans), int(kdim)), "kexpm_vec")
+    return info.value
+
+
+def kexpm_mat(Cb: Basis, A: LinOp, B: Basis, tau: float, tol: float, trans: bool = False, kdim: int = 0, p: Optional[int] = None) -> int:
+    """kexpm_mat(C, A, B, tau, tol, info, trans, kdim)  (src/Expm/ExpmLib.fypp:234-362): C = exp(tau A) B by block Arnoldi with
+    blksize p = size(B); returns info (dimension used, or -1)."""
+    p = B.ncols if p is None else p
+    info = C.c_int32()
+    check(A.ctx.lib.lkb_kexpm_mat(Cb.h, A.h, B.h, int(p), float(tau), float(tol), C.byref(info), int(trans), int(kdim)), "kexpm_mat")
     return info.value
 
 

@@ -184,6 +184,98 @@ int lkb_kexpm_vec(lkb_vec_t cvec, lkb_op_t A, lkb_vec_t b, double tau, double to
     return cleanup(0);
 }
 
+// kexpm_mat(C, A, B, tau, tol, info, trans, kdim)       src/Expm/ExpmLib.fypp:234-362
+//   C(:, :p) = exp(tau A) B(:, :p) by block Arnoldi with blksize p = size(B).  B = Q R by the pivoting QR (qr.fypp:32-107),
+//   the columns of R are permuted back (:295); each block step exponentiates the extended block-Hessenberg matrix and
+//   estimates the error by norm(matmul(E(kp+1:kpp, :p), R), 2) -- stdlib's `norm` of a rank-2 array is the 2-norm over ALL
+//   elements (Frobenius).  Literal details: the loop runs up to nk = kdim*p BLOCK steps and the basis holds p*(nk+1) vectors
+//   (:279, :289); on Arnoldi breakdown kpp = kp, the section E(kp+1:kpp, :) is empty, the estimate is 0 and the loop exits.
+//   info = kpp (dimension used) when err_est <= tol, -1 otherwise; kdim <= 0 = kmax = 100.  The reference forms
+//   C = (X E(:, :p)) R every step; only the last one survives, so it is formed once, as X (E(:, :p) R).
+int lkb_kexpm_mat(lkb_basis_t Cb, lkb_op_t A, lkb_basis_t B, int p, double tau, double tol, int32_t* info, int32_t trans, int32_t kdim) {
+    if (!Cb || !A || !B || !info || p < 1 || B->ncols < p || Cb->ncols < p || Cb->n != B->n || Cb->kind != B->kind ||
+        A->kind != B->kind || A->m != B->n || A->n != B->n) { set_error("kexpm_mat: bad arguments"); return LKB_ERR_ARG; }
+    lkb_ctx_s* c = B->ctx;
+    const int kind = B->kind;
+    const size_t es = kind_size(kind);
+    const int nsteps = kdim > 0 ? kdim : 100;
+    const int nk = nsteps * p;
+    *info = 0;
+    lkb_basis_t Xwrk = nullptr, X = nullptr;
+    int rc = 0;
+    auto cleanup = [&](int r) { if (X) lkb_basis_destroy(X); if (Xwrk) lkb_basis_destroy(Xwrk); return r; };
+#define KM_TRY(call) do { rc = (call); if (rc) return cleanup(rc); } while (0)
+    KM_TRY(lkb_basis_create(c, kind, B->n, B->n_global, B->row0, p, &Xwrk));
+    const double one_d[2] = {1.0, 0.0}, zero_d[2] = {0.0, 0.0};
+    const float one_f[2] = {1.f, 0.f}, zero_f[2] = {0.f, 0.f};
+    const bool sp = (kind == KS || kind == KC);
+    KM_TRY(lkb_basis_axpby(sp ? (const void*)one_f : (const void*)one_d, B, 0, sp ? (const void*)zero_f : (const void*)zero_d, Xwrk, 0, p));
+    // B = Q R P^T : pivoting QR, then permcols(R, invperm(perm))   (:295)
+    std::vector<char> Rp((size_t)p * p * es, 0);
+    std::vector<int32_t> perm(p, 0), invp(p, 0);
+    int32_t qinfo = 0;
+    KM_TRY(lkb_qr_pivoting(Xwrk, 0, p, Rp.data(), p, perm.data(), -1.0, &qinfo));
+    for (int i = 0; i < p; ++i) invp[perm[i] - 1] = i;
+    std::vector<cd> R((size_t)p * p);
+    double fro2 = 0.0;
+    for (int q = 0; q < p; ++q)
+        for (int i = 0; i < p; ++i) {
+            R[i + (size_t)p * q] = load_kind(kind, Rp.data(), (size_t)i + (size_t)p * invp[q]);
+            fro2 += std::norm(R[i + (size_t)p * q]);
+        }
+    double err_est = 0.0;
+    int kpp = p;
+    if (fro2 == 0.0) {                                             // input is zero => output is zero (:297-300)
+        KM_TRY(lkb_basis_zero(Cb, 0, p));
+    } else {
+        KM_TRY(lkb_basis_create(c, kind, B->n, B->n_global, B->row0, p * (nk + 1), &X));
+        KM_TRY(lkb_initialize_krylov_subspace(X, Xwrk, 0, p));
+        const int ldh = p * (nk + 1);
+        std::vector<char> H((size_t)ldh * ldh * es, 0);            // (p(nk+1))^2 as in the reference (:281)
+        std::vector<cd> Hk, E, M;
+        std::vector<char> coef;
+        for (int k = 1; k <= nk; ++k) {
+            const int kp = k * p;
+            kpp = kp + p;
+            int32_t ainfo = 0;
+            KM_TRY(lkb_arnoldi(A, X, H.data(), ldh, &ainfo, k, k, -1.0, trans, p));
+            if (ainfo == kp) kpp = kp;                             // breakdown: do not consider the extended matrix (:314-318)
+            Hk.assign((size_t)kpp * kpp, cd(0));
+            for (int j = 0; j < kpp; ++j)
+                for (int i = 0; i < kpp; ++i) Hk[i + (size_t)kpp * j] = tau * load_kind(kind, H.data(), (size_t)i + (size_t)ldh * j);
+            if (!dense_expm(kpp, Hk, E)) { set_error("kexpm_mat: singular Pade denominator"); return cleanup(LKB_ERR_LAPACK); }
+            // M = E(:kpp, :p) R ; err_est = || M(kp+1:kpp, :) ||_F   (:338-346; the section is empty after a breakdown)
+            M.assign((size_t)kpp * p, cd(0));
+            for (int q = 0; q < p; ++q)
+                for (int l = 0; l < p; ++l) {
+                    const cd r = R[l + (size_t)p * q];
+                    if (r == cd(0)) continue;
+                    for (int i = 0; i < kpp; ++i) M[i + (size_t)kpp * q] += E[i + (size_t)kpp * l] * r;
+                }
+            double e2 = 0.0;
+            for (int q = 0; q < p; ++q) for (int i = kp; i < kpp; ++i) e2 += std::norm(M[i + (size_t)kpp * q]);
+            err_est = sqrt(e2);
+            KM_TRY(bcast_host(c, &err_est, sizeof(double)));
+            if (err_est <= tol || k == nk) {
+                coef.resize((size_t)kpp * es);
+                for (int q = 0; q < p; ++q) {
+                    for (int i = 0; i < kpp; ++i) store_kind(kind, coef.data(), (size_t)i, M[i + (size_t)kpp * q]);
+                    lkb_vec_t cq = nullptr;
+                    KM_TRY(lkb_basis_col(Cb, q, &cq));
+                    rc = lkb_basis_lincomb(X, kpp, coef.data(), cq);
+                    lkb_vec_destroy(cq);
+                    if (rc) return cleanup(rc);
+                }
+                if (err_est <= tol) break;
+            }
+        }
+    }
+    KM_TRY(lkb_sync(c));
+    *info = (err_est <= tol) ? kpp : -1;
+#undef KM_TRY
+    return cleanup(0);
+}
+
 // write_results(filename, vals, res, tol)                IterativeSolvers.fypp:882-924
 //   vals: k reals (is_complex = 0) or k (re, im) pairs; res is sorted ascending IN PLACE, as the reference does.
 int lkb_write_results(const char* filename, int32_t is_complex, const double* vals, double* res, int32_t k, double tol) {

@@ -379,6 +379,99 @@ int lkb_qr(lkb_basis_t Q, int col0, int p, void* R, int ldr, double tol, int32_t
     return 0;
 }
 
+// qr_with_pivoting: src/Krylov/qr.fypp:32-107 (+ swap_columns :174-201), interface BaseKrylov.fypp:395-417.
+// Greedy column pivoting on the down-dated squared norms Rii.  Literal details kept: Rii (SQUARED norms) is compared with
+// `tol` unsquared; the down-date is Rii(i) - R(j,i)**2, a complex square for the complex kinds; `info = j` set before the
+// refill of a cancelled column is overwritten by the Gram-Schmidt call that follows; a Gram-Schmidt step against the empty
+// section Q(:0) is a no-op with info = 0.  perm is 1-based, as the reference returns it.
+int lkb_qr_pivoting(lkb_basis_t Q, int col0, int p, void* R, int ldr, int32_t* perm, double tol, int32_t* info) {
+    if (!Q || !R || !perm || !info || col0 < 0 || p < 1 || col0 + p > Q->ncols || ldr < p) { set_error("qr_pivoting: bad arguments"); return LKB_ERR_ARG; }
+    lkb_ctx_s* c = Q->ctx;
+    const int kind = Q->kind;
+    const size_t es = kind_size(kind);
+    const bool sp = (kind == KS || kind == KC), cplx = kind_cplx(kind);
+    if (tol < 0) tol = atol_of(kind);
+    *info = 0;
+    auto Rat = [&](int i, int j) { return (char*)R + ((size_t)i + (size_t)ldr * j) * es; };
+    auto qcol = [&](int i) { return col_ptr(Q, col0 + i); };
+    auto round_kind = [&](Scalar s) { if (sp) { s.re = (double)(float)s.re; s.im = (double)(float)s.im; } if (!cplx) s.im = 0.0; return s; };
+    for (int j = 0; j < p; ++j) for (int i = 0; i < p; ++i) memset(Rat(i, j), 0, es);
+    std::vector<Scalar> Rii(p, Scalar{0, 0}), col;
+    int hf[F_COUNT];
+    for (int i = 0; i < p; ++i) {
+        perm[i] = i + 1;
+        LKB_TRY(vec_dot_sync(c, kind, qcol(i), qcol(i), Q->n, &Rii[i]));
+        Rii[i] = round_kind(Rii[i]);
+    }
+    struct Tmp { lkb_ctx_s* c; void* d; ~Tmp() { if (d) dev_free(c, d); } } tmp{c, nullptr};
+    // Q(i) <- rand ; double_gram_schmidt_step(Q(i), Q(:i-1)) ; returns the step's info and the norm afterwards
+    auto refill = [&](int i, int32_t* ginfo, double* beta) -> int {
+        launch_fill(kind, c->stream, qcol(i), Q->n, Q->row0, LKB_DIST_NORMAL, next_seed(c), c->sms);
+        c->launches++;
+        double nrm2 = 0;
+        LKB_TRY(reset_flags(c));
+        LKB_TRY(dgs_enqueue(c, kind, qcol(0), Q->ld, i, qcol(i), Q->n, c->flags, true, true));
+        LKB_TRY(fetch_coeffs(c, kind, i, true, col, &nrm2, hf));
+        *ginfo = (i > 0 && hf[F_GSINFO]) ? 1 : 0;
+        *beta = sqrt(fabs(nrm2));
+        return 0;
+    };
+    for (int j = 0; j < p; ++j) {
+        int idx = 0; double best = -1.0;                                    // maxloc(abs(Rii)): first maximum
+        for (int i = 0; i < p; ++i) { const double a = hypot(Rii[i].re, Rii[i].im); if (a > best) { best = a; idx = i; } }
+        if (best < tol) {                                                   // rank exhausted: random orthonormal completion (:55-66)
+            for (int i = j; i < p; ++i) {
+                int32_t g = 0; double beta = 0;
+                LKB_TRY(refill(i, &g, &beta));
+                launch_scal(kind, c->stream, Scalar{1.0 / beta, 0.0}, qcol(i), Q->n, c->sms);
+                c->launches++;
+                LKB_TRY(check_launch(c, "qr_pivoting completion"));
+            }
+            *info = j + 1;
+            break;
+        }
+        // swap_columns(Q, R, Rii, perm, j, idx)
+        if (idx != j) {
+            const size_t bytes = (size_t)Q->n * es;
+            if (!tmp.d && bytes) LKB_TRY(dev_alloc(c, &tmp.d, bytes));
+            if (bytes) {
+                LKB_CUDA(cudaMemcpyAsync(tmp.d, qcol(j), bytes, cudaMemcpyDeviceToDevice, c->stream));
+                LKB_CUDA(cudaMemcpyAsync(qcol(j), qcol(idx), bytes, cudaMemcpyDeviceToDevice, c->stream));
+                LKB_CUDA(cudaMemcpyAsync(qcol(idx), tmp.d, bytes, cudaMemcpyDeviceToDevice, c->stream));
+            }
+            std::swap(Rii[j], Rii[idx]);
+            std::swap(perm[j], perm[idx]);
+            char t[16];
+            for (int r = 0; r < j; ++r) { memcpy(t, Rat(r, j), es); memcpy(Rat(r, j), Rat(r, idx), es); memcpy(Rat(r, idx), t, es); }
+        }
+        double beta = 0;
+        LKB_TRY(vec_norm_sync(c, kind, qcol(j), Q->n, &beta));
+        if (beta != beta) { set_error("|beta| = NaN detected! Abort"); return LKB_ERR_NAN; }
+        if (beta < tol) {                                                   // cancelled column (:80-87)
+            int32_t g = 0;
+            LKB_TRY(refill(j, &g, &beta));
+            *info = g;                                                      // `info = j` is overwritten by the DGS call
+        } else {
+            scalar_store(kind, Scalar{beta, 0.0}, Rat(j, j));
+        }
+        launch_scal(kind, c->stream, Scalar{1.0 / beta, 0.0}, qcol(j), Q->n, c->sms);
+        c->launches++;
+        for (int i = j + 1; i < p; ++i) {                                   // orthogonalise the trailing columns (:93-97)
+            Scalar b{0, 0};
+            LKB_TRY(vec_dot_sync(c, kind, qcol(j), qcol(i), Q->n, &b));
+            b = round_kind(b);
+            launch_axpby(kind, c->stream, Scalar{-b.re, -b.im}, qcol(j), Scalar{1.0, 0.0}, qcol(i), Q->n, c->sms);
+            c->launches++;
+            scalar_store(kind, b, Rat(j, i));
+            Rii[i] = round_kind(Scalar{Rii[i].re - (b.re * b.re - b.im * b.im), Rii[i].im - 2.0 * b.re * b.im});
+        }
+        LKB_TRY(check_launch(c, "qr_pivoting"));
+        Rii[j] = Scalar{0, 0};
+    }
+    LKB_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 // orthonormalize_basis (src/Krylov/utilities.fypp:70-81): in-place QR of X(:, col0 : col0 + p), R discarded
 int lkb_orthonormalize_basis(lkb_basis_t X, int col0, int p, int32_t* info) {
     if (!X || !info || p < 1) { set_error("orthonormalize_basis: bad arguments"); return LKB_ERR_ARG; }

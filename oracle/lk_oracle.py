@@ -226,6 +226,59 @@ def qr(Q: np.ndarray, tol=None, seed: int = 1000):
     return int(info), Rm
 
 
+def qr_with_pivoting(Q: np.ndarray, tol=None, seed: int = 1000):
+    """qr_with_pivoting (src/Krylov/qr.fypp:32-107, swap_columns :174-201).  In place on Q; returns (info, R, perm) with
+    perm 0-based (the reference's perm minus one).  Literal details kept: Rii holds SQUARED norms but is compared with `tol`
+    unsquared; the down-date is `Rii(i) - R(j,i)**2` (a complex square, not |.|^2, for the complex kinds); `info = j` set
+    before the refill of a cancelled column is overwritten by the Gram-Schmidt call that follows.  A Gram-Schmidt step
+    against the empty section Q(:0) is a no-op returning info = 0."""
+    _check_basis(Q)
+    kind = kind_of(Q.dtype); dt = Q.dtype
+    n, kdim = Q.shape
+    tol = ATOL[kind] if tol is None else tol
+    R = np.zeros((kdim, kdim), dtype=dt, order="F")
+    perm = np.arange(kdim)
+    Rii = np.array([dot(Q[:, i], Q[:, i]) for i in range(kdim)], dtype=dt)
+    info = 0
+    state = {"seed": seed}
+
+    def refill(i):
+        Q[:, i] = fill(n, kind, "normal", state["seed"]); state["seed"] += 1
+        return dgs_vec(Q[:, i], Q, i, want_beta=False)[0] if i > 0 else 0
+
+    for j in range(kdim):
+        idx = int(np.argmax(np.abs(Rii)))                       # maxloc: first maximum
+        if abs(Rii[idx]) < tol:
+            for i in range(j, kdim):
+                refill(i)
+                beta = norm(Q[:, i]); Q[:, i] *= dt.type(1.0 / beta)
+            info = j + 1
+            break
+        if idx != j:
+            Q[:, [j, idx]] = Q[:, [idx, j]]
+        Rii[[j, idx]] = Rii[[idx, j]]; perm[[j, idx]] = perm[[idx, j]]
+        if j > 0:
+            R[:j, [j, idx]] = R[:j, [idx, j]]
+        beta = norm(Q[:, j])
+        if np.isnan(beta):
+            raise FloatingPointError("|beta| = NaN detected! Abort")
+        if abs(beta) < tol:
+            info = j + 1
+            R[j, j] = 0
+            info = refill(j)
+            beta = norm(Q[:, j])
+        else:
+            R[j, j] = beta
+        Q[:, j] *= dt.type(1.0 / beta)
+        for i in range(j + 1, kdim):
+            b = dot(Q[:, j], Q[:, i])
+            axpby(-b, Q[:, j], 1.0, Q[:, i])
+            R[j, i] = b
+        Rii[j] = 0
+        Rii[j + 1:] = Rii[j + 1:] - R[j, j + 1:] ** 2
+    return info, R, perm
+
+
 def arnoldi(A: Op, X: np.ndarray, H: np.ndarray, kstart=1, kend=None, tol=None, trans=False,
             blksize=1, seed=1000):
     """arnoldi(A, X, H, info, kstart, kend, tol, transpose, blksize); X, H updated in place."""
@@ -628,3 +681,39 @@ def kexpm_vec(A: Op, b: np.ndarray, tau: float, tol: float, trans: bool = False,
         if err_est <= tol:
             break
     return c, (kp if err_est <= tol else -1)
+
+
+def kexpm_mat(A: Op, B: np.ndarray, tau: float, tol: float, trans: bool = False, kdim: int = 100, seed: int = 1000):
+    """kexpm_mat (src/Expm/ExpmLib.fypp:234-362): C = exp(tau A) B by block Arnoldi (blksize = p = number of columns of B).
+    Returns (C, info): info = kpp (dimension used) when the estimate is <= tol, -1 otherwise.  Literal details: the loop runs
+    up to nk = kdim*p BLOCK steps (:279, :300); B = Q R by the pivoting QR with the columns of R permuted back (:295);
+    err_est = norm(matmul(E(kp+1:kpp, :p), R), 2) where stdlib's `norm` of a rank-2 array is the 2-norm of ALL its elements
+    (Frobenius); on Arnoldi breakdown kpp = kp, the section is empty, the estimate is 0 and the loop exits (:311-346)."""
+    _check_basis(B)
+    dt = B.dtype
+    n, p = B.shape
+    nk = kdim * p
+    Xwrk = np.asfortranarray(B.copy())
+    _, R, perm = qr_with_pivoting(Xwrk, seed=seed)
+    inv = np.empty(p, dtype=np.int64); inv[perm] = np.arange(p)
+    R = np.asfortranarray(R[:, inv])                                  # permcols(R, invperm(perm))
+    if np.linalg.norm(R) == 0.0:
+        return np.zeros((n, p), dtype=dt, order="F"), p
+    X = np.zeros((n, p * (nk + 1)), dtype=dt, order="F")
+    X[:, :p] = Xwrk
+    qr(X[:, :p], seed=seed + 500)                                     # initialize_krylov_subspace: orthonormalize_basis
+    H = np.zeros((p * (nk + 1), p * (nk + 1)), dtype=dt, order="F")
+    Cm = np.zeros((n, p), dtype=dt, order="F")
+    err_est, kpp = 0.0, p
+    for k in range(1, nk + 1):
+        kp = k * p; kpp = kp + p
+        info = arnoldi(A, X, H, kstart=k, kend=k, trans=trans, blksize=p, seed=seed + 1000 + k)
+        if info == kp:
+            kpp = kp
+        E = expm_pade10(tau * H[:kpp, :kpp])
+        Xw = X[:, :kpp] @ E[:kpp, :p]
+        Cm = np.asfortranarray((Xw @ R).astype(dt))
+        err_est = float(np.linalg.norm(E[kp:kpp, :p] @ R))
+        if err_est <= tol:
+            break
+    return Cm, (kpp if err_est <= tol else -1)

@@ -181,7 +181,9 @@ def test_fortran_shim_interfaces_match_header(so_path):
                          ("svds", "A, U, S, V, residuals, info, u0, kdim, tolerance, write_intermediate"),
                          ("dgs_vector", "y, X, info, if_chk_orthonormal, beta"), ("dgs_basis", "Y, X, info, if_chk_orthonormal, beta"),
                          ("orthogonalize_vector", "y, X, info, if_chk_orthonormal, beta"),
-                         ("orthogonalize_basis", "Y, X, info, if_chk_orthonormal, beta")):
+                         ("orthogonalize_basis", "Y, X, info, if_chk_orthonormal, beta"),
+                         ("qr_pivoting", "Q, R, perm, info, tol"), ("kexpm_vec", "c, A, b, tau, tol, info, trans, kdim"),
+                         ("kexpm_mat", "C, A, B, tau, tol, info, trans, kdim")):
             assert f"function lkb_try_{fn}_{sfx}({args}) result(done)" in src, (fn, sfx)
     # no component of the device vector is default-initialised (intent(out) dummies must not reset the handle)
     for sfx in ("rsp", "rdp", "csp", "cdp"):

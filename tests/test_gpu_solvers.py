@@ -4,7 +4,7 @@ the C ABI, plus entrywise comparison with the numpy/scipy oracle shells on ident
 import numpy as np
 import pytest
 
-from helpers import CONVDIFF7, LAPLACE7, POISSON5, randn, random_csr, rel_normwise
+from helpers import CONVDIFF7, LAPLACE7, POISSON5, randn, random_csr, rel_normwise, tol_for
 
 pytestmark = pytest.mark.gpu
 N = 128
@@ -209,3 +209,88 @@ def test_kexpm_vec_breakdown_literal_info(lk, ctx, oracle, kind):
     assert info == oinfo == 5
     exact = np.exp(0.2 * np.arange(1, n + 1)) * bh
     assert np.linalg.norm(c.get() - exact) < 1e-12 * np.linalg.norm(exact)
+
+
+# ---- pivoting QR and block Krylov exponential (block Arnoldi's caller `kexpm_mat` with pivoting QR) ----------
+@pytest.mark.parametrize("kind", ["d", "z", "s", "c"])
+def test_qr_pivoting_vs_oracle(lk, ctx, oracle, kind):
+    """qr_with_pivoting (src/Krylov/qr.fypp:32-107) on the device vs the oracle restatement: same pivot order, same R, same Q;
+    plus the reference's own assertions (TestKrylov.f90:245-318) on a matrix with 5 exactly-zero columns."""
+    dt = lk.DTYPES[kind]; p = 12
+    Ah = randn(np.random.default_rng(33), (N, p), dt)
+    Q = lk.Basis(ctx, kind, N, p).put(Ah)
+    info, R, perm = lk.qr_pivoting(Q)
+    Qo = Ah.copy(order="F"); infoo, Ro, permo = oracle.qr_with_pivoting(Qo)
+    assert info == infoo == 0 and perm.tolist() == permo.tolist()
+    perm_full = permo.copy()
+    assert rel_normwise(R, Ro) < tol_for(kind) and rel_normwise(Q.get(), Qo) < tol_for(kind)
+    assert np.abs(Ah[:, perm] - Q.get() @ R).max() < lk.RTOL[kind]
+    # exact rank deficiency: kdim = 20, 5 zero columns
+    kdim, nzero = 20, 5
+    rng = np.random.default_rng(34)
+    Bh = randn(rng, (N, kdim), dt); Bh[:, rng.choice(kdim, nzero, replace=False)] = 0
+    Q = lk.Basis(ctx, kind, N, kdim).put(Bh)
+    info, R, perm = lk.qr_pivoting(Q)
+    Qo = Bh.copy(order="F"); infoo, Ro, permo = oracle.qr_with_pivoting(Qo)
+    rk = kdim - nzero
+    assert info == infoo == rk + 1 and perm.tolist() == permo.tolist()
+    Qg = Q.get()
+    assert rel_normwise(R, Ro) < tol_for(kind) and rel_normwise(Qg[:, :rk], Qo[:, :rk]) < tol_for(kind)
+    assert np.abs(Bh[:, perm] - Qg @ R).max() < lk.RTOL[kind]
+    assert np.linalg.norm(Qg.conj().T @ Qg - np.eye(kdim)) < lk.RTOL[kind]      # incl. the random orthonormal completion
+    assert not R[rk:, :].any()
+    # a column section of a larger basis (col0 > 0) leaves the other columns alone
+    W = lk.Basis(ctx, kind, N, p + 3).put(np.concatenate([np.ones((N, 2), dtype=dt), Ah, np.ones((N, 1), dtype=dt)], axis=1))
+    info, R2, perm2 = lk.qr_pivoting(W, col0=2, p=p)
+    Wg = W.get()
+    assert info == 0 and perm2.tolist() == perm_full.tolist()
+    assert (Wg[:, :2] == 1).all() and (Wg[:, -1] == 1).all() and np.abs(Ah[:, perm2] - Wg[:, 2:2 + p] @ R2).max() < lk.RTOL[kind]
+
+
+@pytest.mark.parametrize("kind", ["d", "z", "s"])
+@pytest.mark.parametrize("p", [1, 3])
+def test_kexpm_mat_vs_oracle(lk, ctx, oracle, kind, p):
+    """kexpm_mat (src/Expm/ExpmLib.fypp:234-362): C = exp(tau A) B by block Arnoldi on the device vs the oracle restatement:
+    same `info` (dimension used), same block; and against the dense exponential (TestExpmlib.f90:334-419)."""
+    import scipy.linalg as sla
+    dims = (24, 20); n = 480
+    coef = (-4.0, 1.0, 0.8, 1.0, 1.2)
+    A = lk.LinOp.stencil5(ctx, kind, *dims, coef); Ao = oracle.Op.stencil(kind, dims, coef)
+    Bh = np.asfortranarray(np.stack([oracle.fill(n, kind, "uniform", 5 + i) for i in range(p)], axis=1))
+    B = lk.Basis(ctx, kind, n, p).put(Bh); Cb = lk.Basis(ctx, kind, n, p)
+    tol = 1e-10 if kind in "dz" else 1e-5
+    info = lk.kexpm_mat(Cb, A, B, 0.1, tol, kdim=15)
+    Co, oinfo = oracle.kexpm_mat(Ao, Bh, 0.1, tol, kdim=15)
+    assert info == oinfo and info >= 2 * p
+    assert np.linalg.norm(Cb.get() - Co) < tol_for(kind) * np.linalg.norm(Co)
+    Ad = np.stack([Ao.apply(e) for e in np.eye(n, dtype=lk.DTYPES[kind])], axis=1).astype(np.complex128)
+    ref = sla.expm(0.1 * Ad) @ Bh
+    assert np.linalg.norm(Cb.get() - ref) < (1e-9 if kind in "dz" else 1e-4) * np.linalg.norm(ref)
+    # transpose flag: exp(tau A^H) B
+    Ct = lk.Basis(ctx, kind, n, p)
+    tinfo = lk.kexpm_mat(Ct, A, B, 0.1, tol, trans=True, kdim=15)
+    Cto, otinfo = oracle.kexpm_mat(Ao, Bh, 0.1, tol, trans=True, kdim=15)
+    assert tinfo == otinfo
+    assert np.linalg.norm(Ct.get() - Cto) < tol_for(kind) * np.linalg.norm(Cto)
+    # zero input => zero output, info = p (ExpmLib.fypp:297-300)
+    Z = lk.Basis(ctx, kind, n, p); C2 = lk.Basis(ctx, kind, n, p).put(Bh)
+    assert lk.kexpm_mat(C2, A, Z, 0.1, tol, kdim=15) == p
+    assert not C2.get().any()
+
+
+def test_kexpm_mat_breakdown_exits(lk, ctx, oracle):
+    """Block-Arnoldi breakdown inside kexpm_mat: the columns of B span a 4-dimensional invariant subspace of a diagonal operator
+    (p = 2).  After two block steps the new block is numerically zero, arnoldi returns info = kp, the extended matrix is not
+    considered, the error estimate is the norm of an EMPTY section = 0 and the loop exits with info = kp and the exact
+    result (ExpmLib.fypp:314-346) -- unlike kexpm_vec, where the estimate is not zeroed."""
+    n = 96
+    D = np.asfortranarray(np.diag(np.arange(1, n + 1)).astype(np.float64))
+    A = lk.LinOp.dense(ctx, D); Ao = oracle.Op.dense(D)
+    Bh = np.zeros((n, 2), order="F"); Bh[:4, 0] = [1.0, 2.0, -1.5, 0.5]; Bh[:4, 1] = [0.3, -1.0, 2.0, 1.0]
+    B = lk.Basis(ctx, "d", n, 2).put(Bh); Cb = lk.Basis(ctx, "d", n, 2)
+    info = lk.kexpm_mat(Cb, A, B, 0.2, 1e-12)
+    Co, oinfo = oracle.kexpm_mat(Ao, Bh, 0.2, 1e-12)
+    assert info == oinfo == 4
+    exact = np.exp(0.2 * np.arange(1, n + 1))[:, None] * Bh
+    assert np.linalg.norm(Cb.get() - exact) < 1e-12 * np.linalg.norm(exact)
+    assert np.linalg.norm(Co - exact) < 1e-12 * np.linalg.norm(exact)

@@ -364,3 +364,43 @@ def test_arnoldi_entries_match_extended_precision(oracle):
     err = np.abs(H - Hl.astype(np.float64)).max() / np.abs(H).max()
     assert err < 1e-12, err
     assert np.abs(X - V.astype(np.float64)).max() < 1e-11
+
+
+# ---- pivoting QR and block Krylov exponential (`kexpm_mat` with pivoting QR) ---------------------------------
+@pytest.mark.parametrize("kind", ["s", "d", "c", "z"])
+def test_pivoting_qr_exact_rank_deficiency(oracle, kind):
+    """test/TestKrylov.fypp `test_pivoting_qr_exact_rank_deficiency_*` (TestKrylov.f90:245-318): kdim = 20 random columns, 5 of
+    them zeroed at random places; A(:, perm) = Q R and Q^H Q = I, both < rtol."""
+    dt = oracle.DTYPES[kind]; kdim, nzero = 20, 5
+    rng = np.random.default_rng(31)
+    A = rng.standard_normal((N, kdim)) + (1j * rng.standard_normal((N, kdim)) if kind in "cz" else 0)
+    A = np.asfortranarray(A.astype(dt))
+    A[:, rng.choice(kdim, nzero, replace=False)] = 0
+    Q = A.copy(order="F")
+    info, R, perm = oracle.qr_with_pivoting(Q)
+    assert info == kdim - nzero + 1                       # breakdown at step rk + 1 (qr.fypp:55-66)
+    assert sorted(perm.tolist()) == list(range(kdim))
+    assert np.abs(A[:, perm] - Q @ R).max() < oracle.RTOL[kind]
+    assert np.linalg.norm(Q.conj().T @ Q - np.eye(kdim)) < oracle.RTOL[kind]
+    assert not np.tril(R, -1).any() and not R[kdim - nzero:, :].any()
+
+
+@pytest.mark.parametrize("kind", ["s", "d", "c", "z"])
+def test_block_kexpm_known_answer(oracle, kind):
+    """test/TestExpmlib.fypp `test_block_kexptA_*` (TestExpmlib.f90:334-419): p = 3, nkmax = 15, tau = 0.1, tol = rtol; the block
+    result and the column-by-column kexpm_vec results both match the dense exponential."""
+    import scipy.linalg as sla
+    dt = oracle.DTYPES[kind]; p, nkmax, tau = 3, 15, 0.1
+    rng = np.random.default_rng(32)
+    c = (lambda s: rng.standard_normal(s) + (1j * rng.standard_normal(s) if kind in "cz" else 0))
+    Am = np.asfortranarray(c((N, N)).astype(dt)); B = np.asfortranarray(c((N, p)).astype(dt))
+    tol = oracle.RTOL[kind]
+    ref = sla.expm(tau * Am.astype(np.complex128)) @ B
+    Cb, info = oracle.kexpm_mat(oracle.Op.dense(Am), B, tau, tol, kdim=nkmax)
+    assert info > 0 and info % p == 0
+    assert np.linalg.norm(Cb - ref) < 10 * tol * np.linalg.norm(ref)
+    Cv = np.stack([oracle.kexpm_vec(oracle.Op.dense(Am), np.ascontiguousarray(B[:, i]), tau, tol, kdim=nkmax * p)[0] for i in range(p)], axis=1)
+    assert np.linalg.norm(Cv - ref) < 10 * tol * np.linalg.norm(ref)
+    # zero input => zero output, info = p (ExpmLib.fypp:297-300, :353)
+    Z, zinfo = oracle.kexpm_mat(oracle.Op.dense(Am), np.zeros_like(B), tau, tol, kdim=nkmax)
+    assert not Z.any() and zinfo == p
