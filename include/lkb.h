@@ -224,7 +224,8 @@ int lkb_kexpm_vec(lkb_vec_t c, lkb_op_t A, lkb_vec_t b, double tau, double tol, 
 /* kexpm_mat(C, A, B, tau, tol, info, trans, kdim)  src/Expm/ExpmLib.fypp:234-362: C(:, :p) = exp(tau A) B(:, :p) by block Arnoldi with
  * blksize p = size(B) (pivoting QR of B, dense expm of the extended block-Hessenberg matrix per block step, error estimate
  * ||E(kp+1:kpp, :p) R||_F).  info = dimension used when the estimate is <= tol, -1 when not converged within kdim*p block steps
- * (kdim <= 0: 100) -- the reference's loop bound; the work basis holds p*(kdim*p + 1) vectors, as the reference allocates. */
+ * (kdim <= 0: 100) -- the reference's loop bound.  The work basis starts with room for 8 block steps and doubles on demand
+ * (the reference allocates all p*(kdim*p + 1) vectors up front). */
 int lkb_kexpm_mat(lkb_basis_t C, lkb_op_t A, lkb_basis_t B, int p, double tau, double tol, int32_t* info, int32_t trans, int32_t kdim);
 /* on-disk formats of the spectral solvers (IterativeSolvers.fypp:882-963).  write_results: the text table the reference
  * rewrites every step as eigs_output.txt / eighs_output.txt / svds_output.txt ('(I6,4(2X,E16.9),2X,L4)'); vals = k reals or

@@ -188,8 +188,11 @@ int lkb_kexpm_vec(lkb_vec_t cvec, lkb_op_t A, lkb_vec_t b, double tau, double to
 //   C(:, :p) = exp(tau A) B(:, :p) by block Arnoldi with blksize p = size(B).  B = Q R by the pivoting QR (qr.fypp:32-107),
 //   the columns of R are permuted back (:295); each block step exponentiates the extended block-Hessenberg matrix and
 //   estimates the error by norm(matmul(E(kp+1:kpp, :p), R), 2) -- stdlib's `norm` of a rank-2 array is the 2-norm over ALL
-//   elements (Frobenius).  Literal details: the loop runs up to nk = kdim*p BLOCK steps and the basis holds p*(nk+1) vectors
-//   (:279, :289); on Arnoldi breakdown kpp = kp, the section E(kp+1:kpp, :) is empty, the estimate is 0 and the loop exits.
+//   elements (Frobenius).  Literal details: the loop runs up to nk = kdim*p BLOCK steps (:279, :300); on Arnoldi breakdown
+//   kpp = kp, the section E(kp+1:kpp, :) is empty, the estimate is 0 and the loop exits.  The reference allocates all
+//   p*(nk+1) basis vectors and the (p(nk+1))^2 matrices H and E up front (:281-289) -- 903 vectors for p = 3 and the default
+//   kdim; here the basis and H start with room for 8 block steps and double on demand (new columns are zero, as zero_basis
+//   leaves them), so the memory follows the steps actually taken.
 //   info = kpp (dimension used) when err_est <= tol, -1 otherwise; kdim <= 0 = kmax = 100.  The reference forms
 //   C = (X E(:, :p)) R every step; only the last one survives, so it is formed once, as X (E(:, :p) R).
 int lkb_kexpm_mat(lkb_basis_t Cb, lkb_op_t A, lkb_basis_t B, int p, double tau, double tol, int32_t* info, int32_t trans, int32_t kdim) {
@@ -228,13 +231,29 @@ int lkb_kexpm_mat(lkb_basis_t Cb, lkb_op_t A, lkb_basis_t B, int p, double tau, 
     if (fro2 == 0.0) {                                             // input is zero => output is zero (:297-300)
         KM_TRY(lkb_basis_zero(Cb, 0, p));
     } else {
-        KM_TRY(lkb_basis_create(c, kind, B->n, B->n_global, B->row0, p * (nk + 1), &X));
+        int cap = std::min(nk, 8);                                 // block steps the basis / H currently have room for
+        KM_TRY(lkb_basis_create(c, kind, B->n, B->n_global, B->row0, p * (cap + 1), &X));
         KM_TRY(lkb_initialize_krylov_subspace(X, Xwrk, 0, p));
-        const int ldh = p * (nk + 1);
-        std::vector<char> H((size_t)ldh * ldh * es, 0);            // (p(nk+1))^2 as in the reference (:281)
+        int ldh = p * (cap + 1);
+        std::vector<char> H((size_t)ldh * ldh * es, 0);
         std::vector<cd> Hk, E, M;
         std::vector<char> coef;
+        const void* one = sp ? (const void*)one_f : (const void*)one_d;
+        const void* zero = sp ? (const void*)zero_f : (const void*)zero_d;
         for (int k = 1; k <= nk; ++k) {
+            if (k > cap) {                                         // double the room: copy the basis and re-lay H
+                const int cap2 = std::min(nk, 2 * cap), ld2 = p * (cap2 + 1);
+                lkb_basis_t X2 = nullptr;
+                KM_TRY(lkb_basis_create(c, kind, B->n, B->n_global, B->row0, p * (cap2 + 1), &X2));
+                rc = lkb_basis_axpby(one, X, 0, zero, X2, 0, p * (cap + 1));
+                if (rc) { lkb_basis_destroy(X2); return cleanup(rc); }
+                lkb_basis_destroy(X);
+                X = X2;
+                std::vector<char> H2((size_t)ld2 * ld2 * es, 0);
+                for (int j = 0; j < ldh; ++j) memcpy(&H2[(size_t)j * ld2 * es], &H[(size_t)j * ldh * es], (size_t)ldh * es);
+                H.swap(H2);
+                ldh = ld2; cap = cap2;
+            }
             const int kp = k * p;
             kpp = kp + p;
             int32_t ainfo = 0;

@@ -651,3 +651,122 @@ def test_preconditioned_gmres_two_restatements_agree(oracle, mode):
     assert np.abs(np.array(m2["res"]) - np.array(mo["res"])).max() < 1e-10 * mo["res"][0]
     assert np.linalg.norm(x2 - xo) < 1e-10 * np.linalg.norm(xo)
     assert np.linalg.norm(A @ x2 - b) < 1e-6 * np.linalg.norm(b)
+
+
+# ---- qr_with_pivoting (src/Krylov/qr.fypp:32-107, swap_columns :174-201) and kexpm_mat (src/Expm/ExpmLib.fypp:234-362) -------
+def qr_with_pivoting_literal(Q, kind, tol=None):
+    """Written from the Fortran with 1-based loop variables, no breakdown branch exercised except the rank-exhausted exit."""
+    dt = Q.dtype
+    tolerance = ATOL[kind] if tol is None else tol
+    kdim = Q.shape[1]
+    R = np.zeros((kdim, kdim), dtype=dt)
+    perm = np.zeros(kdim, dtype=int)
+    Rii = np.zeros(kdim, dtype=dt)
+    info = 0
+    rng = np.random.default_rng(123)
+    for i in range(1, kdim + 1):
+        perm[i - 1] = i
+        Rii[i - 1] = v_dot(Q[:, i - 1], Q[:, i - 1])
+    for j in range(1, kdim + 1):
+        idx = int(np.argmax(np.abs(Rii))) + 1                       # maxloc(abs(Rii))
+        if abs(Rii[idx - 1]) < tolerance:
+            for i in range(j, kdim + 1):
+                Q[:, i - 1] = randn(rng, Q.shape[0], dt)
+                if i > 1:
+                    dgs_vector(Q[:, i - 1], Q[:, :i - 1], kind)
+                Q[:, i - 1] *= dt.type(1) / dt.type(v_norm(Q[:, i - 1]))
+            info = j
+            break
+        # swap_columns(Q, R, Rii, perm, j, idx): n = min(j, idx) - 1 = j - 1 leading rows of R
+        Q[:, [j - 1, idx - 1]] = Q[:, [idx - 1, j - 1]]
+        Rii[[j - 1, idx - 1]] = Rii[[idx - 1, j - 1]]
+        perm[[j - 1, idx - 1]] = perm[[idx - 1, j - 1]]
+        n = min(j, idx) - 1
+        if n > 0:
+            R[:n, [j - 1, idx - 1]] = R[:n, [idx - 1, j - 1]]
+        beta = v_norm(Q[:, j - 1])
+        assert np.isfinite(beta) and beta >= tolerance, "these inputs must not cancel"
+        R[j - 1, j - 1] = beta
+        Q[:, j - 1] *= dt.type(1) / dt.type(beta)
+        for i in range(j + 1, kdim + 1):
+            b = v_dot(Q[:, j - 1], Q[:, i - 1])
+            v_axpby(-b, Q[:, j - 1], 1, Q[:, i - 1])
+            R[j - 1, i - 1] = b
+        Rii[j - 1] = 0
+        for i in range(j + 1, kdim + 1):
+            Rii[i - 1] = Rii[i - 1] - R[j - 1, i - 1] ** 2
+    return R, perm, info
+
+
+@pytest.mark.parametrize("kind", ["s", "d", "c", "z"])
+def test_qr_with_pivoting_two_restatements_agree(oracle, kind):
+    dt = DT[kind]
+    rng = np.random.default_rng(40)
+    A = randn(rng, (100, 14), dt)
+    A[:, 5] = 0; A[:, 11] = 0                                        # exact rank deficiency 2: exit at step 13
+    Q2 = A.copy(order="F"); R2, perm2, info2 = qr_with_pivoting_literal(Q2, kind)
+    Qo = A.copy(order="F"); infoo, Ro, permo = oracle.qr_with_pivoting(Qo)
+    assert info2 == infoo == 13
+    assert (perm2 - 1).tolist() == permo.tolist()                    # the oracle returns perm 0-based
+    assert rel_normwise(R2, Ro) < _tol(kind) and rel_normwise(Q2[:, :12], Qo[:, :12]) < _tol(kind)
+    for Q, R, perm in ((Q2, R2, perm2 - 1), (Qo, Ro, permo)):
+        assert np.abs(A[:, perm] - Q @ R).max() < 100 * _tol(kind)
+        assert np.abs(Q.conj().T @ Q - np.eye(14)).max() < 100 * _tol(kind)
+
+
+def kexpm_mat_literal(apply_A, B, tau, tol, kind, kdim=100):
+    """ExpmLib.fypp:234-362 with its own pivoting QR, block Arnoldi step (arnoldi.fypp:34-73 for one k) and scipy's expm."""
+    import scipy.linalg as sla
+    dt = DT[kind]
+    n, p = B.shape
+    nsteps = kdim; nk = nsteps * p
+    Xwrk = B.copy(order="F")
+    R, perm, _ = qr_with_pivoting_literal(Xwrk, kind)
+    inv_perm = np.zeros(p, dtype=int); inv_perm[perm - 1] = np.arange(1, p + 1)         # invperm (utilities.fypp:21-27)
+    R = R[:, inv_perm - 1]                                                              # permcols(R, invperm(perm))
+    if np.sqrt((np.abs(R) ** 2).sum()) == 0:                                            # mnorm(R, "fro") == 0
+        return np.zeros((n, p), dtype=dt), p
+    X = np.zeros((n, p * (nk + 1)), dtype=dt, order="F")
+    X[:, :p] = Xwrk
+    qr_no_pivoting(X[:, :p], kind)                                                      # initialize_krylov_subspace
+    H = np.zeros((p * (nk + 1), p * (nk + 1)), dtype=dt)
+    C = np.zeros((n, p), dtype=dt); err_est = 0.0; kpp = p
+    for k in range(1, nk + 1):
+        kpm = (k - 1) * p; kp = kpm + p; kpp = kp + p
+        # arnoldi(A, X, H, info, kstart = k, kend = k, blksize = p)
+        for i in range(p):
+            X[:, kp + i] = apply_A(X[:, kpm + i])
+        if p == 1:
+            H[:kp, kpm], _ = dgs_vector(X[:, kp], X[:, :kp], kind)
+        else:
+            H[:kp, kpm:kp], _ = dgs_basis(X[:, kp:kpp], X[:, :kp], kind)
+        Rb, _ = qr_no_pivoting(X[:, kp:kpp], kind)                                      # (no breakdown in these inputs)
+        H[kp:kpp, kpm:kp] = Rb
+        E = sla.expm(tau * H[:kpp, :kpp])
+        Xw = np.zeros((n, p), dtype=dt)
+        for i in range(p):
+            for j in range(kpp):
+                v_axpby(E[j, i], X[:, j], 1, Xw[:, i])
+        C[:] = 0
+        for i in range(p):
+            for j in range(p):
+                v_axpby(R[j, i], Xw[:, j], 1, C[:, i])
+        err_est = np.sqrt((np.abs(E[kp:kpp, :p] @ R[:p, :p]) ** 2).sum())               # norm(matmul(...), 2): all elements
+        if err_est <= tol:
+            break
+    return C, (kpp if err_est <= tol else -1)
+
+
+@pytest.mark.parametrize("kind", ["d", "z"])
+@pytest.mark.parametrize("p", [1, 2, 3])
+def test_kexpm_mat_two_restatements_agree(oracle, kind, p):
+    import scipy.linalg as sla
+    dt = DT[kind]; n = 90
+    rng = np.random.default_rng(41)
+    A = np.asfortranarray((randn(rng, (n, n), dt) / np.sqrt(n) - 0.5 * np.eye(n)).astype(dt))
+    B = randn(rng, (n, p), dt)
+    C2, info2 = kexpm_mat_literal(lambda v: (A @ v).astype(dt), B, 0.3, 1e-10, kind, kdim=12)
+    Co, infoo = oracle.kexpm_mat(oracle.Op.dense(A), B, 0.3, 1e-10, kdim=12)
+    assert info2 == infoo and info2 > p
+    assert np.linalg.norm(C2 - Co) < 1e-10 * np.linalg.norm(Co)
+    assert np.linalg.norm(Co - sla.expm(0.3 * A) @ B) < 1e-8 * np.linalg.norm(Co)
