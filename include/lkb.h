@@ -227,6 +227,9 @@ int lkb_kexpm_vec(lkb_vec_t c, lkb_op_t A, lkb_vec_t b, double tau, double tol, 
  * (kdim <= 0: 100) -- the reference's loop bound.  The work basis starts with room for 8 block steps and doubles on demand
  * (the reference allocates all p*(kdim*p + 1) vectors up front). */
 int lkb_kexpm_mat(lkb_basis_t C, lkb_op_t A, lkb_basis_t B, int p, double tau, double tol, int32_t* info, int32_t trans, int32_t kdim);
+/* krylov_exptA(vec_out, A, vec_in, tau, info, trans)  src/Expm/ExpmLib.fypp:364-392: kexpm_vec with tol = atol_kind, kdim = 30
+ * (the procedure the reference plugs into abstract_exptA_linop, AbstractLinops.fypp:105-123). */
+int lkb_krylov_expta(lkb_vec_t vec_out, lkb_op_t A, lkb_vec_t vec_in, double tau, int32_t* info, int32_t trans);
 /* on-disk formats of the spectral solvers (IterativeSolvers.fypp:882-963).  write_results: the text table the reference
  * rewrites every step as eigs_output.txt / eighs_output.txt / svds_output.txt ('(I6,4(2X,E16.9),2X,L4)'); vals = k reals or
  * k (re, im) pairs, res is sorted ascending in place as the reference does.  save_eigenspectrum: NPY 1.0, Fortran order,
@@ -235,10 +238,10 @@ int lkb_kexpm_mat(lkb_basis_t C, lkb_op_t A, lkb_basis_t B, int p, double tau, d
 int lkb_write_results(const char* filename, int32_t is_complex, const double* vals, double* res, int32_t k, double tol);
 int lkb_save_eigenspectrum(const char* fname, int32_t is_complex, int32_t single_precision, const double* lambda,
                            const double* residuals, int32_t k);
-/* host LAPACK provider for the k x k algebra of eigs/eighs/svds/krylov_schur (geev, gees, trsen,
- * syev/heev, gesvd): a shared library exporting Fortran-ABI LAPACK, symbol = prefix + name + suffix
- * (e.g. scipy's bundled OpenBLAS: prefix "scipy_", suffix "_").  The reference gets these from
- * stdlib_linalg_lapack (submodule_utility_functions.fypp:55-117). */
+/* host LAPACK provider for the k x k algebra of eigs/eighs/svds/krylov_schur ({s,d,c,z}geev, gees, trsen,
+ * {s,d}syev / {c,z}heev, gesdd -- each kind runs the routines of its own precision, as the reference does): a shared
+ * library exporting Fortran-ABI LAPACK, symbol = prefix + name + suffix (e.g. scipy's bundled OpenBLAS: prefix
+ * "scipy_", suffix "_").  The reference gets these from stdlib_linalg_lapack (submodule_utility_functions.fypp:55-117). */
 int lkb_set_lapack(const char* path, const char* prefix, const char* suffix);
 
 /* ---- measurement helpers ----------------------------------------------------------------- */

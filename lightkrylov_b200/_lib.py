@@ -114,6 +114,7 @@ SIGNATURES = {
     "lkb_svds": (_i, [_vp, _vp, _P(_d), _vp, _i, _P(_d), _P(_i32), _vp, _i32, _d]),
     "lkb_kexpm_vec": (_i, [_vp, _vp, _vp, _d, _d, _P(_i32), _i32, _i32]),
     "lkb_kexpm_mat": (_i, [_vp, _vp, _vp, _i, _d, _d, _P(_i32), _i32, _i32]),
+    "lkb_krylov_expta": (_i, [_vp, _vp, _vp, _d, _P(_i32), _i32]),
     "lkb_write_results": (_i, [C.c_char_p, _i32, _P(_d), _P(_d), _i32, _d]),
     "lkb_save_eigenspectrum": (_i, [C.c_char_p, _i32, _i32, _P(_d), _P(_d), _i32]),
     "lkb_set_lapack": (_i, [C.c_char_p, C.c_char_p, C.c_char_p]),

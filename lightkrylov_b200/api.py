@@ -637,6 +637,13 @@ def kexpm_mat(Cb: Basis, A: LinOp, B: Basis, tau: float, tol: float, trans: bool
     return info.value
 
 
+def krylov_exptA(vec_out: Vector, A: LinOp, vec_in: Vector, tau: float, trans: bool = False) -> int:
+    """krylov_exptA (src/Expm/ExpmLib.fypp:364-392): kexpm_vec with tol = atol_kind and kdim = 30; returns info."""
+    info = C.c_int32()
+    check(A.ctx.lib.lkb_krylov_expta(vec_out.h, A.h, vec_in.h, float(tau), C.byref(info), int(trans)), "krylov_exptA")
+    return info.value
+
+
 def write_results(filename: str, vals: np.ndarray, res: np.ndarray, tol: float) -> np.ndarray:
     """write_results (IterativeSolvers.fypp:882-924); returns the residuals in the sorted order the reference leaves them in."""
     v = np.ascontiguousarray(vals)

@@ -9,9 +9,10 @@
 // The k x k algebra (k <= kdim) stays on the host as in the reference, which gets it from
 // stdlib_linalg_lapack (geev, gees, trsen, syev/heev, gesdd; fortran-lang/stdlib, version unpinned
 // in fpm.toml:25).  Here a Fortran-ABI LAPACK is resolved at run time with dlopen
-// (lkb_set_lapack); matrices of the single-precision kinds are promoted to double for these
-// O(k^3) host steps and rounded back.  All O(n) work (basis update X Z, Ritz-vector assembly) is
-// the tall-skinny device GEMM in kernels_gemm.cu.
+// (lkb_set_lapack) and called IN THE PRECISION OF THE KIND, as stdlib's eig / schur / eigh / svd dispatch
+// (sgeev / cgeev ... for rsp / csp, dgeev / zgeev ... for rdp / cdp); the surrounding bookkeeping (residuals,
+// sorting) is done on the returned values in double.  All O(n) work (basis update X Z, Ritz-vector assembly)
+// is the tall-skinny device GEMM in kernels_gemm.cu.
 #include <dlfcn.h>
 #include <math.h>
 #include <stdlib.h>
@@ -30,31 +31,38 @@ typedef int lint;   // LP64 LAPACK
 
 namespace {
 
+// One table per precision: the reference calls the LAPACK routines OF THE KIND (stdlib eig / schur / eigh / svd dispatch to
+// sgeev / cgeev ... for rsp / csp and dgeev / zgeev ... for rdp / cdp), so the fp32 kinds run the s / c routines here too.
+template <typename R> struct LaP {
+    typedef std::complex<R> C;
+    void (*geev)(const char*, const char*, const lint*, R*, const lint*, R*, R*, R*, const lint*, R*, const lint*, R*,
+                 const lint*, lint*, size_t, size_t) = nullptr;
+    void (*cgeev)(const char*, const char*, const lint*, C*, const lint*, C*, C*, const lint*, C*, const lint*, C*,
+                  const lint*, R*, lint*, size_t, size_t) = nullptr;
+    void (*gees)(const char*, const char*, void*, const lint*, R*, const lint*, lint*, R*, R*, R*, const lint*, R*,
+                 const lint*, lint*, lint*, size_t, size_t) = nullptr;
+    void (*cgees)(const char*, const char*, void*, const lint*, C*, const lint*, lint*, C*, C*, const lint*, C*,
+                  const lint*, R*, lint*, lint*, size_t, size_t) = nullptr;
+    void (*trsen)(const char*, const char*, const lint*, const lint*, R*, const lint*, R*, const lint*, R*, R*, lint*,
+                  R*, R*, R*, const lint*, lint*, const lint*, lint*, size_t, size_t) = nullptr;
+    void (*ctrsen)(const char*, const char*, const lint*, const lint*, C*, const lint*, C*, const lint*, C*, lint*, R*,
+                   R*, C*, const lint*, lint*, size_t, size_t) = nullptr;
+    void (*syev)(const char*, const char*, const lint*, R*, const lint*, R*, R*, const lint*, lint*, size_t, size_t) = nullptr;
+    void (*heev)(const char*, const char*, const lint*, C*, const lint*, R*, C*, const lint*, R*, lint*, size_t, size_t) = nullptr;
+    void (*gesdd)(const char*, const lint*, const lint*, R*, const lint*, R*, R*, const lint*, R*, const lint*, R*,
+                  const lint*, lint*, lint*, size_t) = nullptr;
+    void (*cgesdd)(const char*, const lint*, const lint*, C*, const lint*, R*, C*, const lint*, C*, const lint*, C*,
+                   const lint*, R*, lint*, lint*, size_t) = nullptr;
+};
 struct Lapack {
     void* h = nullptr;
-    void (*dgeev)(const char*, const char*, const lint*, double*, const lint*, double*, double*, double*, const lint*,
-                  double*, const lint*, double*, const lint*, lint*, size_t, size_t) = nullptr;
-    void (*zgeev)(const char*, const char*, const lint*, cd*, const lint*, cd*, cd*, const lint*, cd*, const lint*,
-                  cd*, const lint*, double*, lint*, size_t, size_t) = nullptr;
-    void (*dgees)(const char*, const char*, void*, const lint*, double*, const lint*, lint*, double*, double*, double*,
-                  const lint*, double*, const lint*, lint*, lint*, size_t, size_t) = nullptr;
-    void (*zgees)(const char*, const char*, void*, const lint*, cd*, const lint*, lint*, cd*, cd*, const lint*, cd*,
-                  const lint*, double*, lint*, lint*, size_t, size_t) = nullptr;
-    void (*dtrsen)(const char*, const char*, const lint*, const lint*, double*, const lint*, double*, const lint*,
-                   double*, double*, lint*, double*, double*, double*, const lint*, lint*, const lint*, lint*, size_t,
-                   size_t) = nullptr;
-    void (*ztrsen)(const char*, const char*, const lint*, const lint*, cd*, const lint*, cd*, const lint*, cd*, lint*,
-                   double*, double*, cd*, const lint*, lint*, size_t, size_t) = nullptr;
-    void (*dsyev)(const char*, const char*, const lint*, double*, const lint*, double*, double*, const lint*, lint*,
-                  size_t, size_t) = nullptr;
-    void (*zheev)(const char*, const char*, const lint*, cd*, const lint*, double*, cd*, const lint*, double*, lint*,
-                  size_t, size_t) = nullptr;
-    void (*dgesdd)(const char*, const lint*, const lint*, double*, const lint*, double*, double*, const lint*, double*,
-                   const lint*, double*, const lint*, lint*, lint*, size_t) = nullptr;
-    void (*zgesdd)(const char*, const lint*, const lint*, cd*, const lint*, double*, cd*, const lint*, cd*, const lint*,
-                   cd*, const lint*, double*, lint*, lint*, size_t) = nullptr;
+    LaP<double> d;
+    LaP<float> s;
 };
 Lapack g_la;
+template <typename R> const LaP<R>& la_of();
+template <> const LaP<double>& la_of<double>() { return g_la.d; }
+template <> const LaP<float>& la_of<float>() { return g_la.s; }
 
 int lapack_open(const char* path, const char* prefix, const char* suffix) {
     void* h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
@@ -64,8 +72,11 @@ int lapack_open(const char* path, const char* prefix, const char* suffix) {
         std::string s = std::string(prefix ? prefix : "") + name + (suffix ? suffix : "");
         return dlsym(h, s.c_str());
     };
-#define LA(f) *(void**)(&la.f) = sym(#f); if (!la.f) { set_error("LAPACK provider %s lacks %s%s%s", path, prefix ? prefix : "", #f, suffix ? suffix : ""); dlclose(h); return LKB_ERR_LAPACK; }
-    LA(dgeev) LA(zgeev) LA(dgees) LA(zgees) LA(dtrsen) LA(ztrsen) LA(dsyev) LA(zheev) LA(dgesdd) LA(zgesdd)
+#define LA(field, name) *(void**)(&la.field) = sym(name); if (!la.field) { set_error("LAPACK provider %s lacks %s%s%s", path, prefix ? prefix : "", name, suffix ? suffix : ""); dlclose(h); return LKB_ERR_LAPACK; }
+    LA(d.geev, "dgeev") LA(d.cgeev, "zgeev") LA(d.gees, "dgees") LA(d.cgees, "zgees") LA(d.trsen, "dtrsen") LA(d.ctrsen, "ztrsen")
+    LA(d.syev, "dsyev") LA(d.heev, "zheev") LA(d.gesdd, "dgesdd") LA(d.cgesdd, "zgesdd")
+    LA(s.geev, "sgeev") LA(s.cgeev, "cgeev") LA(s.gees, "sgees") LA(s.cgees, "cgees") LA(s.trsen, "strsen") LA(s.ctrsen, "ctrsen")
+    LA(s.syev, "ssyev") LA(s.heev, "cheev") LA(s.gesdd, "sgesdd") LA(s.cgesdd, "cgesdd")
 #undef LA
     g_la = la;
     return 0;
@@ -100,25 +111,139 @@ void store_kind(int kind, void* H, size_t idx, cd v) {
 }
 
 // eig(A(:k,:k)) -> vals (complex), vecs in LAPACK layout: for real kinds the REAL-pair convention
-// (column i = Re, i+1 = Im of the pair), stored in the real parts of `vecs`.
-int host_eig(bool cplx, int k, const std::vector<cd>& A, int lda, std::vector<cd>& vals, std::vector<cd>& vecs) {
-    LKB_TRY(lapack_ready());
+// (column i = Re, i+1 = Im of the pair), stored in the real parts of `vecs`.  R = precision of the kind.
+template <typename R>
+int host_eig_t(bool cplx, int k, const std::vector<cd>& A, int lda, std::vector<cd>& vals, std::vector<cd>& vecs) {
+    typedef std::complex<R> C;
+    const LaP<R>& la = la_of<R>();
     vals.assign(k, cd(0)); vecs.assign((size_t)k * k, cd(0));
     lint n = k, ldvl = 1, ldvr = k, info = 0;
     if (cplx) {
-        std::vector<cd> a((size_t)k * k), work(std::max(1, 4 * k)); std::vector<double> rwork(2 * k);
-        for (int j = 0; j < k; ++j) for (int i = 0; i < k; ++i) a[i + (size_t)k * j] = A[i + (size_t)lda * j];
-        cd vl; lint lwork = (lint)work.size();
-        g_la.zgeev("N", "V", &n, a.data(), &n, vals.data(), &vl, &ldvl, vecs.data(), &ldvr, work.data(), &lwork, rwork.data(), &info, 1, 1);
+        std::vector<C> a((size_t)k * k), w(k), vr((size_t)k * k), work(std::max(1, 4 * k)); std::vector<R> rwork(2 * k);
+        for (int j = 0; j < k; ++j) for (int i = 0; i < k; ++i) a[i + (size_t)k * j] = C(A[i + (size_t)lda * j]);
+        C vl; lint lwork = (lint)work.size();
+        la.cgeev("N", "V", &n, a.data(), &n, w.data(), &vl, &ldvl, vr.data(), &ldvr, work.data(), &lwork, rwork.data(), &info, 1, 1);
+        for (int i = 0; i < k; ++i) vals[i] = cd(w[i]);
+        for (size_t t = 0; t < vr.size(); ++t) vecs[t] = cd(vr[t]);
     } else {
-        std::vector<double> a((size_t)k * k), wr(k), wi(k), vr((size_t)k * k), work(std::max(1, 8 * k));
-        for (int j = 0; j < k; ++j) for (int i = 0; i < k; ++i) a[i + (size_t)k * j] = A[i + (size_t)lda * j].real();
-        double vl; lint lwork = (lint)work.size();
-        g_la.dgeev("N", "V", &n, a.data(), &n, wr.data(), wi.data(), &vl, &ldvl, vr.data(), &ldvr, work.data(), &lwork, &info, 1, 1);
+        std::vector<R> a((size_t)k * k), wr(k), wi(k), vr((size_t)k * k), work(std::max(1, 8 * k));
+        for (int j = 0; j < k; ++j) for (int i = 0; i < k; ++i) a[i + (size_t)k * j] = (R)A[i + (size_t)lda * j].real();
+        R vl; lint lwork = (lint)work.size();
+        la.geev("N", "V", &n, a.data(), &n, wr.data(), wi.data(), &vl, &ldvl, vr.data(), &ldvr, work.data(), &lwork, &info, 1, 1);
         for (int i = 0; i < k; ++i) vals[i] = cd(wr[i], wi[i]);
         for (size_t t = 0; t < vr.size(); ++t) vecs[t] = cd(vr[t], 0.0);
     }
     if (info != 0) { set_error("GEEV failed, info = %d", (int)info); return LKB_ERR_LAPACK; }
+    return 0;
+}
+int host_eig(int kind, int k, const std::vector<cd>& A, int lda, std::vector<cd>& vals, std::vector<cd>& vecs) {
+    LKB_TRY(lapack_ready());
+    return (kind == KS || kind == KC) ? host_eig_t<float>(kind_cplx(kind), k, A, lda, vals, vecs)
+                                      : host_eig_t<double>(kind_cplx(kind), k, A, lda, vals, vecs);
+}
+
+// schur(H) + median selector + ordschur (BaseKrylov.fypp:806-814, IterativeSolvers.fypp:1136-1141): T, Z (k x k) and the
+// number of selected eigenvalues, in the precision of the kind.  H given as k x k complex doubles.
+template <typename R>
+int host_schur_select_t(bool cplx, int k, const std::vector<cd>& Hk, std::vector<cd>& Tc, std::vector<cd>& Zc, int32_t* nkeep) {
+    typedef std::complex<R> C;
+    const LaP<R>& la = la_of<R>();
+    lint n = k, sdim = 0, info = 0, m = 0;
+    std::vector<lint> sel(k, 0);
+    std::vector<R> av(k);
+    R s_ = 0, sep = 0;
+    auto select = [&]() {
+        std::vector<R> srt(av); std::sort(srt.begin(), srt.end());
+        const R med = (k % 2) ? srt[k / 2] : (R)0.5 * (srt[k / 2 - 1] + srt[k / 2]);
+        int cnt = 0; for (int i = 0; i < k; ++i) { sel[i] = av[i] > med; cnt += sel[i]; }
+        *nkeep = cnt;
+    };
+    Tc.assign((size_t)k * k, cd(0)); Zc.assign((size_t)k * k, cd(0));
+    if (cplx) {
+        std::vector<C> T((size_t)k * k), Z((size_t)k * k), ev(k), work(std::max(1, 4 * k)); std::vector<R> rwork(k);
+        for (size_t t = 0; t < T.size(); ++t) T[t] = C(Hk[t]);
+        lint lwork = (lint)work.size(); lint bwork = 0;
+        la.cgees("V", "N", nullptr, &n, T.data(), &n, &sdim, ev.data(), Z.data(), &n, work.data(), &lwork, rwork.data(), &bwork, &info, 1, 1);
+        if (info != 0) { set_error("GEES failed, info = %d", (int)info); return LKB_ERR_LAPACK; }
+        for (int i = 0; i < k; ++i) av[i] = std::abs(ev[i]);
+        select();
+        std::vector<C> w(k), wk(std::max(1, k)); lint lw = (lint)wk.size();
+        la.ctrsen("N", "V", sel.data(), &n, T.data(), &n, Z.data(), &n, w.data(), &m, &s_, &sep, wk.data(), &lw, &info, 1, 1);
+        if (info != 0) { set_error("TRSEN failed, info = %d", (int)info); return LKB_ERR_LAPACK; }
+        for (size_t t = 0; t < T.size(); ++t) { Tc[t] = cd(T[t]); Zc[t] = cd(Z[t]); }
+    } else {
+        std::vector<R> T((size_t)k * k), Z((size_t)k * k), wr(k), wi(k), work(std::max(1, 8 * k));
+        for (size_t t = 0; t < T.size(); ++t) T[t] = (R)Hk[t].real();
+        lint lwork = (lint)work.size(); lint bwork = 0;
+        la.gees("V", "N", nullptr, &n, T.data(), &n, &sdim, wr.data(), wi.data(), Z.data(), &n, work.data(), &lwork, &bwork, &info, 1, 1);
+        if (info != 0) { set_error("GEES failed, info = %d", (int)info); return LKB_ERR_LAPACK; }
+        for (int i = 0; i < k; ++i) av[i] = std::abs(C(wr[i], wi[i]));
+        select();
+        std::vector<R> wk(std::max(1, k)); lint lw = (lint)wk.size(); std::vector<lint> iwork(std::max(1, k)); lint liw = 1;
+        la.trsen("N", "V", sel.data(), &n, T.data(), &n, Z.data(), &n, wr.data(), wi.data(), &m, &s_, &sep, wk.data(), &lw, iwork.data(), &liw, &info, 1, 1);
+        if (info != 0) { set_error("TRSEN failed, info = %d", (int)info); return LKB_ERR_LAPACK; }
+        for (size_t t = 0; t < T.size(); ++t) { Tc[t] = cd(T[t], 0.0); Zc[t] = cd(Z[t], 0.0); }
+    }
+    return 0;
+}
+
+// eigh(A(:k,:k)) on the lower triangle (syev / heev): eigenvalues ascending, eigenvectors as k x k (ld k)
+template <typename R>
+int host_eigh_t(bool cplx, int k, const std::vector<cd>& Ak, double* ev, std::vector<cd>& vk) {
+    typedef std::complex<R> C;
+    const LaP<R>& la = la_of<R>();
+    lint n = k, linf = 0;
+    std::vector<R> w(k);
+    vk.assign((size_t)k * k, cd(0));
+    if (cplx) {
+        std::vector<C> a((size_t)k * k), work(std::max(1, 4 * k)); std::vector<R> rwork(std::max(1, 3 * k));
+        for (size_t t = 0; t < a.size(); ++t) a[t] = C(Ak[t]);
+        lint lwork = (lint)work.size();
+        la.heev("V", "L", &n, a.data(), &n, w.data(), work.data(), &lwork, rwork.data(), &linf, 1, 1);
+        for (size_t t = 0; t < a.size(); ++t) vk[t] = cd(a[t]);
+    } else {
+        std::vector<R> a((size_t)k * k), work(std::max(1, 8 * k));
+        for (size_t t = 0; t < a.size(); ++t) a[t] = (R)Ak[t].real();
+        lint lwork = (lint)work.size();
+        la.syev("V", "L", &n, a.data(), &n, w.data(), work.data(), &lwork, &linf, 1, 1);
+        for (size_t t = 0; t < a.size(); ++t) vk[t] = cd(a[t], 0.0);
+    }
+    if (linf != 0) { set_error("SYEV/HEEV failed, info = %d", (int)linf); return LKB_ERR_LAPACK; }
+    for (int i = 0; i < k; ++i) ev[i] = (double)w[i];
+    return 0;
+}
+
+// svd(A(:k,:k)) by gesdd: singular values, U and V = hermitian(VT) as k x k (ld k)
+template <typename R>
+int host_svd_t(bool cplx, int k, const std::vector<cd>& Ak, double* sv, std::vector<cd>& uk, std::vector<cd>& vk) {
+    typedef std::complex<R> C;
+    const LaP<R>& la = la_of<R>();
+    lint n = k, linf = 0;
+    std::vector<lint> iwork(8 * k);
+    std::vector<R> s(k);
+    uk.assign((size_t)k * k, cd(0)); vk.assign((size_t)k * k, cd(0));
+    if (cplx) {
+        std::vector<C> a((size_t)k * k), u((size_t)k * k), vt((size_t)k * k), work(std::max(1, 4 * k * k + 8 * k));
+        std::vector<R> rwork(std::max(1, 8 * k * k + 8 * k));
+        for (size_t t = 0; t < a.size(); ++t) a[t] = C(Ak[t]);
+        lint lwork = (lint)work.size();
+        la.cgesdd("A", &n, &n, a.data(), &n, s.data(), u.data(), &n, vt.data(), &n, work.data(), &lwork, rwork.data(), iwork.data(), &linf, 1);
+        for (int j = 0; j < k; ++j) for (int i = 0; i < k; ++i) {
+            uk[i + (size_t)k * j] = cd(u[i + (size_t)k * j]);
+            vk[i + (size_t)k * j] = std::conj(cd(vt[j + (size_t)k * i]));      // V = hermitian(VT)
+        }
+    } else {
+        std::vector<R> a((size_t)k * k), u((size_t)k * k), vt((size_t)k * k), work(std::max(1, 8 * k * k + 16 * k));
+        for (size_t t = 0; t < a.size(); ++t) a[t] = (R)Ak[t].real();
+        lint lwork = (lint)work.size();
+        la.gesdd("A", &n, &n, a.data(), &n, s.data(), u.data(), &n, vt.data(), &n, work.data(), &lwork, iwork.data(), &linf, 1);
+        for (int j = 0; j < k; ++j) for (int i = 0; i < k; ++i) {
+            uk[i + (size_t)k * j] = cd(u[i + (size_t)k * j], 0.0);
+            vk[i + (size_t)k * j] = cd(vt[j + (size_t)k * i], 0.0);
+        }
+    }
+    if (linf != 0) { set_error("GESDD failed, info = %d", (int)linf); return LKB_ERR_LAPACK; }
+    for (int i = 0; i < k; ++i) sv[i] = (double)s[i];
     return 0;
 }
 
@@ -201,41 +326,10 @@ int lkb_krylov_schur(lkb_basis_t X, void* H, int ldh, int kdim, int32_t* nkeep) 
     const bool cplx = kind_cplx(kind);
     const size_t es = kind_size(kind);
     const int k = kdim;
-    lint n = k, sdim = 0, info = 0, m = 0;
-    std::vector<cd> ev(k), Zc((size_t)k * k), Tc((size_t)k * k);
-    std::vector<lint> sel(k, 0);
-    double s_ = 0, sep = 0;
-    if (cplx) {
-        std::vector<cd> T((size_t)k * k), Z((size_t)k * k), work(std::max(1, 4 * k)); std::vector<double> rwork(k);
-        for (int j = 0; j < k; ++j) for (int i = 0; i < k; ++i) T[i + (size_t)k * j] = load_kind(kind, H, (size_t)i + (size_t)ldh * j);
-        lint lwork = (lint)work.size(); lint bwork = 0;
-        g_la.zgees("V", "N", nullptr, &n, T.data(), &n, &sdim, ev.data(), Z.data(), &n, work.data(), &lwork, rwork.data(), &bwork, &info, 1, 1);
-        if (info != 0) { set_error("GEES failed, info = %d", (int)info); return LKB_ERR_LAPACK; }
-        std::vector<double> av(k); for (int i = 0; i < k; ++i) av[i] = std::abs(ev[i]);
-        std::vector<double> srt(av); std::sort(srt.begin(), srt.end());
-        const double med = (k % 2) ? srt[k / 2] : 0.5 * (srt[k / 2 - 1] + srt[k / 2]);
-        int cnt = 0; for (int i = 0; i < k; ++i) { sel[i] = av[i] > med; cnt += sel[i]; }
-        *nkeep = cnt;
-        std::vector<cd> w(k), wk(std::max(1, k)); lint lw = (lint)wk.size();
-        g_la.ztrsen("N", "V", sel.data(), &n, T.data(), &n, Z.data(), &n, w.data(), &m, &s_, &sep, wk.data(), &lw, &info, 1, 1);
-        if (info != 0) { set_error("TRSEN failed, info = %d", (int)info); return LKB_ERR_LAPACK; }
-        Tc = T; Zc = Z;
-    } else {
-        std::vector<double> T((size_t)k * k), Z((size_t)k * k), wr(k), wi(k), work(std::max(1, 8 * k));
-        for (int j = 0; j < k; ++j) for (int i = 0; i < k; ++i) T[i + (size_t)k * j] = load_kind(kind, H, (size_t)i + (size_t)ldh * j).real();
-        lint lwork = (lint)work.size(); lint bwork = 0;
-        g_la.dgees("V", "N", nullptr, &n, T.data(), &n, &sdim, wr.data(), wi.data(), Z.data(), &n, work.data(), &lwork, &bwork, &info, 1, 1);
-        if (info != 0) { set_error("GEES failed, info = %d", (int)info); return LKB_ERR_LAPACK; }
-        std::vector<double> av(k); for (int i = 0; i < k; ++i) av[i] = hypot(wr[i], wi[i]);
-        std::vector<double> srt(av); std::sort(srt.begin(), srt.end());
-        const double med = (k % 2) ? srt[k / 2] : 0.5 * (srt[k / 2 - 1] + srt[k / 2]);
-        int cnt = 0; for (int i = 0; i < k; ++i) { sel[i] = av[i] > med; cnt += sel[i]; }
-        *nkeep = cnt;
-        std::vector<double> wk(std::max(1, k)); lint lw = (lint)wk.size(); std::vector<lint> iwork(std::max(1, k)); lint liw = 1;
-        g_la.dtrsen("N", "V", sel.data(), &n, T.data(), &n, Z.data(), &n, wr.data(), wi.data(), &m, &s_, &sep, wk.data(), &lw, iwork.data(), &liw, &info, 1, 1);
-        if (info != 0) { set_error("TRSEN failed, info = %d", (int)info); return LKB_ERR_LAPACK; }
-        for (size_t t = 0; t < T.size(); ++t) { Tc[t] = T[t]; Zc[t] = Z[t]; }
-    }
+    const bool sp = (kind == KS || kind == KC);
+    std::vector<cd> Hk((size_t)k * k), Zc, Tc;
+    for (int j = 0; j < k; ++j) for (int i = 0; i < k; ++i) Hk[i + (size_t)k * j] = load_kind(kind, H, (size_t)i + (size_t)ldh * j);
+    LKB_TRY(sp ? host_schur_select_t<float>(cplx, k, Hk, Tc, Zc, nkeep) : host_schur_select_t<double>(cplx, k, Hk, Tc, Zc, nkeep));
     {   // rank 0's Schur data is authoritative (see bcast_host)
         LKB_TRY(bcast_host(c, Zc.data(), Zc.size() * sizeof(cd)));
         LKB_TRY(bcast_host(c, Tc.data(), Tc.size() * sizeof(cd)));
@@ -342,7 +436,7 @@ int lkb_eigs(lkb_op_t A, lkb_basis_t X, int nev, double* eigvals, double* residu
             EG_TRY(arnoldi_collect(A, Xw, H.data(), ldh, &ainfo, k, k, tr, slots[k & 1]));
             if (ainfo == 0 && k < kd) { EG_TRY(enqueue_step(k + 1)); inflight = k + 1; }   // speculative
             load_Hc(k);
-            EG_TRY(host_eig(cplx, k, Hc, kd, vals, vecs));
+            EG_TRY(host_eig(kind, k, Hc, kd, vals, vecs));
             const cd beta = load_kind(kind, H.data(), (size_t)k + (size_t)ldh * (k - 1));
             std::fill(res.begin(), res.end(), 0.0);
             for (int i = 0; i < k; ++i) {
@@ -390,7 +484,7 @@ int lkb_eigs(lkb_op_t A, lkb_basis_t X, int nev, double* eigvals, double* residu
     // post-process (:1108-1132)
     k = std::min(k, kd);
     load_Hc(k);
-    EG_TRY(host_eig(cplx, k, Hc, kd, vals, vecs));
+    EG_TRY(host_eig(kind, k, Hc, kd, vals, vecs));
     EG_TRY(bcast_host(c, vals.data(), vals.size() * sizeof(cd)));
     EG_TRY(bcast_host(c, vecs.data(), vecs.size() * sizeof(cd)));
     std::vector<double> av(kd, 0.0);
@@ -430,7 +524,8 @@ int lkb_eighs(lkb_op_t A, lkb_basis_t X, int nev, double* eigvals, double* resid
     const int ldt = kd + 1;
     std::vector<char> T((size_t)ldt * kd * es, 0);
     std::vector<double> ev(kd, 0.0), res(kd, 0.0);
-    std::vector<cd> vecs((size_t)kd * kd, cd(0));
+    std::vector<cd> vecs((size_t)kd * kd, cd(0)), Tk, vk;
+    const bool sp = (kind == KS || kind == KC);
     int k = 1, conv = 0;
     // Host/device overlap as in eigs: step k+1 is enqueued speculatively before the host runs syev / heev on T_k
     // (eighs.fypp:84-100); Xwrk and T are internal work arrays, a speculative step past convergence is discarded.
@@ -453,21 +548,10 @@ int lkb_eighs(lkb_op_t A, lkb_basis_t X, int nev, double* eigvals, double* resid
         EH_TRY(lanczos_collect(A, Xw, T.data(), ldt, &linfo, k, k, ss.slot[k & 1]));
         if (linfo == 0 && k < kd) { EH_TRY(enqueue_step(k + 1)); inflight = k + 1; }      // speculative
         std::fill(ev.begin(), ev.end(), 0.0); std::fill(vecs.begin(), vecs.end(), cd(0));
-        lint n = k, linf = 0;
-        if (cplx) {
-            std::vector<cd> a((size_t)k * k), work(std::max(1, 4 * k)); std::vector<double> rwork(std::max(1, 3 * k));
-            for (int j = 0; j < k; ++j) for (int i = 0; i < k; ++i) a[i + (size_t)k * j] = load_kind(kind, T.data(), (size_t)i + (size_t)ldt * j);
-            lint lwork = (lint)work.size();
-            g_la.zheev("V", "L", &n, a.data(), &n, ev.data(), work.data(), &lwork, rwork.data(), &linf, 1, 1);
-            for (int j = 0; j < k; ++j) for (int i = 0; i < k; ++i) vecs[i + (size_t)kd * j] = a[i + (size_t)k * j];
-        } else {
-            std::vector<double> a((size_t)k * k), work(std::max(1, 8 * k));
-            for (int j = 0; j < k; ++j) for (int i = 0; i < k; ++i) a[i + (size_t)k * j] = load_kind(kind, T.data(), (size_t)i + (size_t)ldt * j).real();
-            lint lwork = (lint)work.size();
-            g_la.dsyev("V", "L", &n, a.data(), &n, ev.data(), work.data(), &lwork, &linf, 1, 1);
-            for (int j = 0; j < k; ++j) for (int i = 0; i < k; ++i) vecs[i + (size_t)kd * j] = a[i + (size_t)k * j];
-        }
-        if (linf != 0) { set_error("SYEV/HEEV failed, info = %d", (int)linf); EH_TRY(LKB_ERR_LAPACK); }
+        Tk.assign((size_t)k * k, cd(0));
+        for (int j = 0; j < k; ++j) for (int i = 0; i < k; ++i) Tk[i + (size_t)k * j] = load_kind(kind, T.data(), (size_t)i + (size_t)ldt * j);
+        EH_TRY(sp ? host_eigh_t<float>(cplx, k, Tk, ev.data(), vk) : host_eigh_t<double>(cplx, k, Tk, ev.data(), vk));
+        for (int j = 0; j < k; ++j) for (int i = 0; i < k; ++i) vecs[i + (size_t)kd * j] = vk[i + (size_t)k * j];
         const cd beta = load_kind(kind, T.data(), (size_t)k + (size_t)ldt * (k - 1));
         std::fill(res.begin(), res.end(), 0.0);
         for (int i = 0; i < k; ++i) res[i] = std::abs(beta * vecs[(k - 1) + (size_t)kd * i]);
@@ -520,7 +604,8 @@ int lkb_svds(lkb_op_t A, lkb_basis_t U, double* S, lkb_basis_t V, int nsv, doubl
     const int ldb = kd + 1;
     std::vector<char> B((size_t)ldb * kd * es, 0);
     std::vector<double> sv(kd, 0.0), res(kd, 0.0);
-    std::vector<cd> umat((size_t)kd * kd), vmat((size_t)kd * kd);
+    std::vector<cd> umat((size_t)kd * kd), vmat((size_t)kd * kd), Bk, uk, vk;
+    const bool sp = (kind == KS || kind == KC);
     *info = 0;
     int k = 1, conv = 0;
     // speculative step k+1 overlapped with the host gesdd of B_k (svd_solvers.fypp:85-101), as in eigs / eighs
@@ -543,29 +628,13 @@ int lkb_svds(lkb_op_t A, lkb_basis_t U, double* S, lkb_basis_t V, int nsv, doubl
         if (binfo == 0 && k < kd) { SV_TRY(enqueue_step(k + 1)); inflight = k + 1; }      // speculative
         std::fill(sv.begin(), sv.end(), 0.0);
         std::fill(umat.begin(), umat.end(), cd(0)); std::fill(vmat.begin(), vmat.end(), cd(0));
-        lint n = k, linf = 0;
-        std::vector<lint> iwork(8 * k);
-        if (cplx) {
-            std::vector<cd> a((size_t)k * k), u((size_t)k * k), vt((size_t)k * k), work(std::max(1, 4 * k * k + 8 * k));
-            std::vector<double> rwork(std::max(1, 8 * k * k + 8 * k));
-            for (int j = 0; j < k; ++j) for (int i = 0; i < k; ++i) a[i + (size_t)k * j] = load_kind(kind, B.data(), (size_t)i + (size_t)ldb * j);
-            lint lwork = (lint)work.size();
-            g_la.zgesdd("A", &n, &n, a.data(), &n, sv.data(), u.data(), &n, vt.data(), &n, work.data(), &lwork, rwork.data(), iwork.data(), &linf, 1);
-            for (int j = 0; j < k; ++j) for (int i = 0; i < k; ++i) {
-                umat[i + (size_t)kd * j] = u[i + (size_t)k * j];
-                vmat[i + (size_t)kd * j] = std::conj(vt[j + (size_t)k * i]);      // vmat = hermitian(vt)
-            }
-        } else {
-            std::vector<double> a((size_t)k * k), u((size_t)k * k), vt((size_t)k * k), work(std::max(1, 8 * k * k + 16 * k));
-            for (int j = 0; j < k; ++j) for (int i = 0; i < k; ++i) a[i + (size_t)k * j] = load_kind(kind, B.data(), (size_t)i + (size_t)ldb * j).real();
-            lint lwork = (lint)work.size();
-            g_la.dgesdd("A", &n, &n, a.data(), &n, sv.data(), u.data(), &n, vt.data(), &n, work.data(), &lwork, iwork.data(), &linf, 1);
-            for (int j = 0; j < k; ++j) for (int i = 0; i < k; ++i) {
-                umat[i + (size_t)kd * j] = u[i + (size_t)k * j];
-                vmat[i + (size_t)kd * j] = vt[j + (size_t)k * i];
-            }
+        Bk.assign((size_t)k * k, cd(0));
+        for (int j = 0; j < k; ++j) for (int i = 0; i < k; ++i) Bk[i + (size_t)k * j] = load_kind(kind, B.data(), (size_t)i + (size_t)ldb * j);
+        SV_TRY(sp ? host_svd_t<float>(cplx, k, Bk, sv.data(), uk, vk) : host_svd_t<double>(cplx, k, Bk, sv.data(), uk, vk));
+        for (int j = 0; j < k; ++j) for (int i = 0; i < k; ++i) {
+            umat[i + (size_t)kd * j] = uk[i + (size_t)k * j];
+            vmat[i + (size_t)kd * j] = vk[i + (size_t)k * j];
         }
-        if (linf != 0) { set_error("GESDD failed, info = %d", (int)linf); SV_TRY(LKB_ERR_LAPACK); }
         const cd beta = load_kind(kind, B.data(), (size_t)k + (size_t)ldb * (k - 1));
         std::fill(res.begin(), res.end(), 0.0);
         for (int i = 0; i < k; ++i) res[i] = std::abs(beta * vmat[(k - 1) + (size_t)kd * i]);

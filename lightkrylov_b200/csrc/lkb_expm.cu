@@ -295,6 +295,13 @@ int lkb_kexpm_mat(lkb_basis_t Cb, lkb_op_t A, lkb_basis_t B, int p, double tau, 
     return cleanup(0);
 }
 
+// krylov_exptA(vec_out, A, vec_in, tau, info, trans)    src/Expm/ExpmLib.fypp:364-392: the wrapper that conforms to the
+// abstract_exptA interface (AbstractLinops.fypp:105-123): kexpm_vec with tol = atol_kind and kdim = 30.
+int lkb_krylov_expta(lkb_vec_t vec_out, lkb_op_t A, lkb_vec_t vec_in, double tau, int32_t* info, int32_t trans) {
+    if (!vec_in) { set_error("krylov_exptA: bad arguments"); return LKB_ERR_ARG; }
+    return lkb_kexpm_vec(vec_out, A, vec_in, tau, atol_of(vec_in->kind), info, trans, 30);
+}
+
 // write_results(filename, vals, res, tol)                IterativeSolvers.fypp:882-924
 //   vals: k reals (is_complex = 0) or k (re, im) pairs; res is sorted ascending IN PLACE, as the reference does.
 int lkb_write_results(const char* filename, int32_t is_complex, const double* vals, double* res, int32_t k, double tol) {

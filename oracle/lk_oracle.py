@@ -462,18 +462,20 @@ def cg(A: Op, b: np.ndarray, x: np.ndarray, rtol=None, atol=None, maxiter=100, p
 
 
 # ------------------------------------------------------------------------------------------
-# eigs / krylov_schur / eighs / svds  (host LAPACK through scipy, double precision for the
-# k x k algebra exactly like the product's host shells)
+# eigs / krylov_schur / eighs / svds  (host LAPACK through scipy IN THE PRECISION OF THE KIND, as the reference's stdlib
+# eig / schur / eigh / svd dispatch: s/c routines for rsp/csp, d/z for rdp/cdp -- exactly like the product's host shells)
 # ------------------------------------------------------------------------------------------
 
 def _host_eig(Hk: np.ndarray):
     """eig = geev('N','V') (submodule_utility_functions.fypp:55-85); real kinds keep LAPACK's
     real-pair eigenvector layout."""
     from scipy.linalg import lapack
+    pre = {"s": "s", "d": "d", "c": "c", "z": "z"}[kind_of(Hk.dtype)]
+    geev = getattr(lapack, pre + "geev")
     if np.iscomplexobj(Hk):
-        w, vl, vr, info = lapack.zgeev(Hk.astype(np.complex128), compute_vl=0, compute_vr=1)
+        w, vl, vr, info = geev(np.asfortranarray(Hk), compute_vl=0, compute_vr=1)
         return w, vr
-    wr, wi, vl, vr, info = lapack.dgeev(Hk.astype(np.float64), compute_vl=0, compute_vr=1)
+    wr, wi, vl, vr, info = geev(np.asfortranarray(Hk), compute_vl=0, compute_vr=1)
     return wr + 1j * wi, vr
 
 
@@ -487,17 +489,20 @@ def krylov_schur(X: np.ndarray, H: np.ndarray):
     from scipy.linalg import lapack
     kdim = X.shape[1] - 1
     cplx = np.iscomplexobj(H)
-    Hk = np.asfortranarray(H[:kdim, :kdim]).astype(np.complex128 if cplx else np.float64)
+    pre = kind_of(H.dtype)
+    Hk = np.asfortranarray(H[:kdim, :kdim]).copy(order="F")
+    gees = getattr(lapack, pre + "gees")
     if cplx:
-        T, sdim, w, Z, work, info = lapack.zgees(lambda x: False, Hk, sort_t=0)
+        T, sdim, w, Z, work, info = gees(lambda x: False, Hk, sort_t=0)
         ev = w
     else:
-        T, sdim, wr, wi, Z, work, info = lapack.dgees(lambda x, y: False, Hk, sort_t=0)
+        T, sdim, wr, wi, Z, work, info = gees(lambda x, y: False, Hk, sort_t=0)
         ev = wr + 1j * wi
     assert info == 0
-    sel = np.abs(ev) > np.median(np.abs(ev))
+    av = np.abs(ev)                                                # abs / median in the precision of the kind
+    sel = av > np.median(av)
     n = int(sel.sum())
-    trsen = lapack.ztrsen if cplx else lapack.dtrsen
+    trsen = getattr(lapack, pre + "trsen")
     out = trsen(sel.astype(np.int32), T, Z, job="N", wantq=1)
     T2, Z2 = out[0], out[1]
     assert out[-1] == 0
@@ -585,7 +590,7 @@ def eighs(A: Op, n: int, nev: int, x0: np.ndarray, kdim=None, tolerance=None):
     for k in range(1, kdim + 1):
         lanczos(A, Xw, T, kstart=k, kend=k)
         ev[:] = 0; vecs[:] = 0; res[:] = 0
-        w, v = sla.eigh(T[:k, :k].astype(vecs.dtype), lower=True, driver="ev")
+        w, v = sla.eigh(np.asfortranarray(T[:k, :k]), lower=True, driver="ev")      # ssyev / cheev for the fp32 kinds
         ev[:k] = w; vecs[:k, :k] = v
         res[:k] = np.abs(T[k, k - 1] * vecs[k - 1, :k])
         if int((res[:k] < tol).sum()) >= nev:
@@ -612,7 +617,7 @@ def svds(A: Op, nsv: int, u0: np.ndarray, kdim=None, tolerance=None):
     k = 1
     for k in range(1, kdim + 1):
         bidiag(A, Uw, Vw, B, kstart=k, kend=k, tol=tol)
-        u, s, vt = sla.svd(B[:k, :k].astype(wd), lapack_driver="gesdd")
+        u, s, vt = sla.svd(np.asfortranarray(B[:k, :k]), lapack_driver="gesdd")           # sgesdd / cgesdd for the fp32 kinds
         vm = vt.conj().T
         sv[:] = 0; res[:] = 0
         sv[:k] = s

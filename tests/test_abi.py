@@ -183,7 +183,8 @@ def test_fortran_shim_interfaces_match_header(so_path):
                          ("orthogonalize_vector", "y, X, info, if_chk_orthonormal, beta"),
                          ("orthogonalize_basis", "Y, X, info, if_chk_orthonormal, beta"),
                          ("qr_pivoting", "Q, R, perm, info, tol"), ("kexpm_vec", "c, A, b, tau, tol, info, trans, kdim"),
-                         ("kexpm_mat", "C, A, B, tau, tol, info, trans, kdim")):
+                         ("kexpm_mat", "C, A, B, tau, tol, info, trans, kdim"),
+                         ("krylov_exptA", "vec_out, A, vec_in, tau, info, trans")):
             assert f"function lkb_try_{fn}_{sfx}({args}) result(done)" in src, (fn, sfx)
     # no component of the device vector is default-initialised (intent(out) dummies must not reset the handle)
     for sfx in ("rsp", "rdp", "csp", "cdp"):

@@ -191,6 +191,11 @@ def test_kexpm_vec_vs_oracle(lk, ctx, oracle, kind):
     ct = lk.Vector(ctx, kind, n)
     assert lk.kexpm(ct, A, b, 0.1, tol, trans=True) == info
     assert np.linalg.norm(ct.get() - co) < (1e-10 if kind in "dz" else 1e-4) * np.linalg.norm(co)
+    # krylov_exptA (ExpmLib.fypp:364-392) = kexpm_vec with tol = atol_kind, kdim = 30
+    ce = lk.Vector(ctx, kind, n); ck = lk.Vector(ctx, kind, n)
+    einfo = lk.krylov_exptA(ce, A, b, 0.1)
+    assert einfo == lk.kexpm(ck, A, b, 0.1, lk.ATOL[kind], kdim=30) and np.array_equal(ce.get(), ck.get())
+    assert einfo == oracle.kexpm_vec(Ao, bh, 0.1, oracle.ATOL[kind], kdim=30)[1]
 
 
 @pytest.mark.parametrize("kind", ["d", "z"])
