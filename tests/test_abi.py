@@ -136,7 +136,9 @@ def test_fortran_shim_interfaces_match_header(so_path):
     must be `value` with the matching c_* kind; a C pointer is either `type(c_ptr), value` or a by-reference dummy."""
     import subprocess, sys
     subprocess.check_call([sys.executable, os.path.join(ROOT, "fortran", "gen_shim.py")], stdout=subprocess.DEVNULL)
-    src = open(os.path.join(ROOT, "fortran", "lightkrylov_cuda.f90")).read()
+    raw = open(os.path.join(ROOT, "fortran", "lightkrylov_cuda.f90")).read()
+    assert max(len(ln) for ln in raw.splitlines()) <= 132, "free-form Fortran lines are limited to 132 columns"
+    src = re.sub(r"&[ \t]*\n[ \t]*", "", raw)                      # join continuation lines
     protos = _c_prototypes()
     lib = ctypes.CDLL(so_path)
     blocks = re.findall(r"function (lkb_[a-z0-9_]+)\(([^)]*)\) bind\(C, name='(lkb_[a-z0-9_]+)'\)(.*?)end function", src, flags=re.S)
@@ -191,3 +193,125 @@ def test_fortran_shim_interfaces_match_header(so_path):
         tdef = src[src.index(f":: cuda_vector_{sfx}\n"):]
         tdef = tdef[:tdef.index("contains")]
         assert "=" not in tdef.replace("=>", ""), tdef
+
+
+def _strip_fortran_comment(line):
+    q = None
+    for i, ch in enumerate(line):
+        if q:
+            if ch == q:
+                q = None
+        elif ch in "'\"":
+            q = ch
+        elif ch == "!":
+            return line[:i]
+    return line
+
+
+def _fortran_block_lint(raw):
+    """Returns the number of block constructs; raises AssertionError on an unmatched / mismatched / unclosed construct."""
+    lines = [_strip_fortran_comment(ln).rstrip() for ln in raw.splitlines()]
+    joined, cur = [], ""
+    for ln in lines:
+        if not ln.strip():
+            continue
+        if ln.endswith("&"):
+            cur += ln[:-1].strip() + " "
+            continue
+        joined.append((cur + ln.strip()).lower()); cur = ""
+    assert cur == "", "dangling continuation at the end of the file"
+    openers = [
+        ("module", re.compile(r"^module (?!procedure)\w+$")),
+        ("function", re.compile(r"^(\w+(\([\w=, ]+\))? )*function \w+ ?\(")),
+        ("subroutine", re.compile(r"^((pure|elemental|recursive|impure) )*subroutine \w+")),
+        ("interface", re.compile(r"^(abstract )?interface( \w+)?$")),
+        ("type", re.compile(r"^type(,[^:]*)? :: \w+$|^type \w+$")),
+        ("select", re.compile(r"^select (type|case) ?\(")),
+        ("if", re.compile(r"^if ?\(.*\) ?then$")),
+        ("do", re.compile(r"^do( |$)")),
+        ("block", re.compile(r"^block$")),
+    ]
+    ender = re.compile(r"^end ?(module|function|subroutine|interface|type|select|if|do|block)\b")
+    stack, n_blocks = [], 0
+    for ln in joined:
+        m = ender.match(ln)
+        if m:
+            assert stack, "unmatched: " + ln
+            kind, opened = stack.pop()
+            assert kind == m.group(1), f"`{ln}` closes `{opened}`"
+            continue
+        assert not ln.startswith("end "), "unknown end statement: " + ln
+        for kind, rx in openers:
+            if rx.match(ln):
+                stack.append((kind, ln)); n_blocks += 1
+                break
+    assert not stack, "left open: " + repr(stack[-3:])
+    return n_blocks
+
+
+def test_fortran_shim_block_structure():
+    """No Fortran compiler exists here or on the GPU box, so the generated module is at least checked mechanically for
+    well-formedness: every module / function / subroutine / interface / type / select / if-then / do / block construct is
+    closed by the matching `end`, in order, and nothing is left open; continuation lines are well-formed.  The linter itself
+    is checked on mutated copies (a dropped `end if`, a dropped `end select`, a swapped `end function`)."""
+    import subprocess, sys
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "fortran", "gen_shim.py")], stdout=subprocess.DEVNULL)
+    raw = open(os.path.join(ROOT, "fortran", "lightkrylov_cuda.f90")).read()
+    assert _fortran_block_lint(raw) > 400          # 4 kinds x (types, TBPs, try-functions) + ~58 bind(C) interfaces
+    for victim, repl in (("            end if\n", "\n"), ("            end select\n", "\n"), ("    end function\n", "    end subroutine\n")):
+        assert victim in raw
+        with pytest.raises(AssertionError):
+            _fortran_block_lint(raw.replace(victim, repl, 1))
+
+
+def _shim_code_without_comments():
+    raw = open(os.path.join(ROOT, "fortran", "lightkrylov_cuda.f90")).read()
+    src = re.sub(r"&[ \t]*\n[ \t]*", "", raw)
+    return "\n".join(_strip_fortran_comment(ln) for ln in src.splitlines())
+
+
+def _call_arg_counts(code, name):
+    """number of top-level arguments of every `name(...)` reference in `code` (balanced parentheses, literals skipped)"""
+    counts = []
+    for m in re.finditer(r"\b" + re.escape(name) + r"\s*\(", code):
+        i, depth, nargs, q, empty = m.end(), 1, 1, None, True
+        while depth:
+            ch = code[i]
+            if q:
+                if ch == q:
+                    q = None
+            elif ch in "'\"":
+                q = ch; empty = False
+            elif ch == "(":
+                depth += 1; empty = False
+            elif ch == ")":
+                depth -= 1
+            elif ch == "," and depth == 1:
+                nargs += 1
+            elif not ch.isspace():
+                empty = False
+            i += 1
+        counts.append(0 if empty else nargs)
+    return counts
+
+
+def test_fortran_shim_calls_match_interfaces():
+    """Every liblkb entry point the shim calls is declared in its bind(C) interface block, and every call passes exactly
+    as many arguments as the interface (= include/lkb.h, checked above) declares."""
+    import subprocess, sys
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "fortran", "gen_shim.py")], stdout=subprocess.DEVNULL)
+    code = _shim_code_without_comments()
+    iface = {m.group(1): len([d for d in m.group(2).split(",") if d.strip()])
+             for m in re.finditer(r"function (lkb_[a-z0-9_]+)\(([^)]*)\) bind\(C", code)}
+    defined = set(re.findall(r"(?:function|subroutine) (lkb_\w+)", code))
+    used = set(re.findall(r"\b(lkb_[A-Za-z0-9_]+)\s*\(", re.sub(r"'[^']*'", "", code)))
+    assert not (used - set(iface) - defined), sorted(used - set(iface) - defined)
+    n_calls = 0
+    nolit = re.sub(r"'[^']*'", "''", code)                   # 'lkb_vec_axpby(copy)' is a message, not a call
+    for name, nargs in iface.items():
+        counts = _call_arg_counts(nolit, name)
+        assert counts, name                                     # at least the declaration itself
+        for c in counts:
+            assert c == nargs, f"{name}: a reference passes {c} arguments, the interface declares {nargs}"
+        n_calls += len(counts) - 1
+    assert n_calls > 200
