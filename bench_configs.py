@@ -6,7 +6,7 @@ These are NOT the headline bench lines (bench.py measures configs[1]); they show
 the hot path working at (or near) the named sizes and report steps/s plus achieved GB/s against
 the official per-step algorithmic bytes.  One JSON line per config.
 
-    python bench_configs.py [--full] [--only c2,c2b,c3,c4,c5]
+    python bench_configs.py [--full] [--only c2,c2b,c2e,c3,c4,c5]
 """
 from __future__ import annotations
 
@@ -93,6 +93,34 @@ def c2_block(ctx, full):
              frac_of_measured_hbm_official=byts / dt / 1e9 / PEAK, sweep_GBps=actual / dt / 1e9,
              orth_err_last4=float(np.abs(G - E).max()), H_block_hessenberg=bool(np.abs(np.tril(H, -p - 1)).max() == 0.0))
         del X
+
+
+def c2_expm(ctx, full):
+    """Block Krylov exponential kexpm_mat (p = 3) on the C2 operator (block Arnoldi's caller), checked against
+    kexpm_vec column by column.  exp(-tau L) with L = the 5-point operator (spectrum in (0, 8)), tau = 0.25, tol = 1e-9."""
+    nx = ny = 4096 if full else 2048
+    n = nx * ny
+    if ctx.world > 1:
+        return
+    A = lk.LinOp.stencil5(ctx, "d", nx, ny, POISSON5)
+    p, tau, tol, kdim = 3, -0.25, 1e-9, 20
+    B = lk.Basis(ctx, "d", n, p); Cb = lk.Basis(ctx, "d", n, p); Cv = lk.Basis(ctx, "d", n, p)
+    for i in range(p):
+        B.col(i).fill_random("uniform", 50 + i)
+    lk.kexpm_mat(Cb, A, B, tau, tol, kdim=kdim)                                   # warm-up (allocation pool)
+    info, dt = timed(ctx, lambda: lk.kexpm_mat(Cb, A, B, tau, tol, kdim=kdim))
+    vinfo, dtv = timed(ctx, lambda: [lk.kexpm(Cv.col(i), A, B.col(i), tau, tol, kdim=kdim * p) for i in range(p)])
+    num = den = 0.0
+    for i in range(p):
+        d = Cv.col(i); den += d.norm() ** 2
+        d.sub(Cb.col(i)); num += d.norm() ** 2
+    ksteps = info // p - 1 if info > 0 else kdim * p
+    # official bytes of the block steps taken (as c2_block) + the final assembly X(:, :kpp) M (p sweeps of kpp vectors)
+    byts = sum(p * 2 * n * 8 + p * 4 * (k * p) * n * 8 for k in range(1, ksteps + 1)) + p * (max(info, p) + 1) * n * 8
+    emit(config="C2 kexpm_mat(p=%d, tau=%g, tol=%g) 5-pt Poisson %dx%d fp64" % (p, tau, tol, nx, ny), info=int(info),
+         block_steps=int(ksteps), seconds=dt, official_GBps=byts / dt / 1e9, frac_of_measured_hbm_official=byts / dt / 1e9 / PEAK,
+         kexpm_vec_infos=[int(v) for v in vinfo], kexpm_vec_seconds_3cols=dtv,
+         rel_diff_block_vs_columnwise=float(np.sqrt(num / den)))
 
 
 def c3_eigs(ctx, full):
@@ -271,7 +299,7 @@ def c5_sharded(ctx, m, n, per_row):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true", help="BASELINE.json sizes (C3 512^3, C4 384^3, C5 50Mx40M)")
-    ap.add_argument("--only", default="c2,c2b,c3,c4,c5")
+    ap.add_argument("--only", default="c2,c2b,c2e,c3,c4,c5")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:                                   # torchrun: only the sharded config (C3) is meaningful
@@ -284,7 +312,7 @@ def main():
         args.only = ",".join(c for c in args.only.split(",") if c in ("c2", "c3", "c5"))      # the row-sharded configs
     else:
         ctx = lk.Context(0)
-    for name, fn in (("c2", c2_gmres), ("c2b", c2_block), ("c3", c3_eigs), ("c4", c4_sym), ("c5", c5_svds)):
+    for name, fn in (("c2", c2_gmres), ("c2b", c2_block), ("c2e", c2_expm), ("c3", c3_eigs), ("c4", c4_sym), ("c5", c5_svds)):
         if name in args.only.split(","):
             try:
                 fn(ctx, args.full)
