@@ -247,12 +247,14 @@ int host_svd_t(bool cplx, int k, const std::vector<cd>& Ak, double* sv, std::vec
     return 0;
 }
 
-// stable ascending sort + reversal == stdlib sort_index(..., reverse=.true.)
+// stdlib sort_index(array, index, reverse=.true.): "non-increasing values in stable order" -- stdlib reverses the array,
+// merge-sorts it (stable, ascending) and reverses again, so ties keep their ORIGINAL order: a conjugate pair stays (+, -) as
+// LAPACK returns it and the eigenvector columns keep the (Re, Im) layout.  Pinned by the reference's own test, which compares
+// eigvals with the analytic spectrum elementwise in the order (a + iw, a - iw) (test/TestIterativeSolvers.fypp:176-186).
 std::vector<int> sort_index_reverse(const std::vector<double>& key) {
     std::vector<int> idx(key.size());
     std::iota(idx.begin(), idx.end(), 0);
-    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return key[a] < key[b]; });
-    std::reverse(idx.begin(), idx.end());
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return key[a] > key[b]; });
     return idx;
 }
 

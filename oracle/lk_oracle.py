@@ -480,8 +480,16 @@ def _host_eig(Hk: np.ndarray):
 
 
 def _sort_index_reverse(key):
-    """stdlib sort_index(reverse=.true.): stable ascending sort, then reversal."""
-    return np.argsort(key, kind="stable")[::-1]
+    """stdlib sort_index(array, index, reverse=.true.): "non-increasing values in STABLE order" -- stdlib reverses the array,
+    runs its stable ascending merge sort and reverses again, so TIES KEEP THEIR ORIGINAL ORDER (a conjugate pair stays
+    (+, -) as LAPACK returns it).  Pinned by the reference's own test: test_evp_r* compares eigvals with the analytic
+    spectrum ELEMENTWISE in the order (a + i w, a - i w) (test/TestIterativeSolvers.fypp:176-186); until round 2 this was
+    restated as ascending-then-reversed, which flips the ties."""
+    key = np.asarray(key)
+    n = key.size
+    pre = np.arange(n)[::-1]                                       # reverse_segment(array, index)
+    order = np.argsort(key[pre], kind="stable")                    # stable ascending merge sort
+    return pre[order][::-1]                                        # reverse_segment(array, index)
 
 
 def krylov_schur(X: np.ndarray, H: np.ndarray):

@@ -44,5 +44,11 @@ template <typename R> int run(bool cplx, const char* tag) {
 }
 int main(int argc, char** argv) {
     if (lapack_open(argv[1], "scipy_", "_")) { printf("open failed: %s\n", lkb_last_error()); return 1; }
+    {   // sort_index(reverse=.true.): non-increasing, ties keep their original order
+        const std::vector<double> key = {1.0, 3.0, 3.0, 2.0, 0.0, 0.0, 3.0};
+        printf("sortidx");
+        for (int i : sort_index_reverse(key)) printf(" %d", i);
+        printf("\n");
+    }
     return run<double>(false, "d") | run<double>(true, "z") | run<float>(false, "s") | run<float>(true, "c");
 }

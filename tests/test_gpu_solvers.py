@@ -48,6 +48,16 @@ def test_eigs_known_answer_full(lk, ctx, oracle):
     evo, reso, Xo, infoo = oracle.eigs(oracle.Op.dense(Ah), N, N, x0h)
     assert info == infoo
     assert _match(ev, evo) < 1e-10
+    # the reference's literal assertion: ELEMENTWISE against (a + iw_1, a - iw_1, a + iw_2, ...) -- pins the tie order of
+    # sort_index(abs, reverse=.true.) (stable: a conjugate pair stays (+, -)) and with it the (Re, Im) column layout
+    tref = np.zeros(N, dtype=np.complex128)
+    for k in range(1, N // 2 + 1):
+        tref[2 * k - 2] = a + 2j * b * np.cos(k * np.pi / (N + 1)); tref[2 * k - 1] = np.conj(tref[2 * k - 2])
+    assert np.max(np.abs(ev - tref) / np.abs(tref)) < lk.RTOL["d"]
+    assert np.max(np.abs(evo - tref) / np.abs(tref)) < lk.RTOL["d"]
+    Xg = X.get()
+    v = Xg[:, 0] + 1j * Xg[:, 1]
+    assert ev[0].imag > 0 and np.linalg.norm(Ah @ v - ev[0] * v) < 1e-6 * np.linalg.norm(v)
 
 
 @pytest.mark.parametrize("kind", ["d", "z", "s"])

@@ -27,6 +27,8 @@ def test_host_lapack_layer_all_four_kinds(tmp_path):
     blas = glob.glob(os.path.join(os.path.dirname(os.path.dirname(scipy.__file__)), "scipy.libs", "libscipy_openblas*.so"))[0]
     out = subprocess.run([exe, blas], check=True, capture_output=True, text=True).stdout
     lines = [ln.split() for ln in out.strip().splitlines()]
+    assert lines[0] == ["sortidx", "1", "2", "6", "3", "0", "4", "5"], out     # stable non-increasing order (stdlib sort_index)
+    lines = lines[1:]
     assert len(lines) == 16, out
     seen = set()
     for ln in lines:

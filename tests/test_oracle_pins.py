@@ -404,3 +404,85 @@ def test_block_kexpm_known_answer(oracle, kind):
     # zero input => zero output, info = p (ExpmLib.fypp:297-300, :353)
     Z, zinfo = oracle.kexpm_mat(oracle.Op.dense(Am), np.zeros_like(B), tau, tol, kdim=nkmax)
     assert not Z.any() and zinfo == p
+
+
+# ---- the reference's solver tests for ALL FOUR kinds, with its literal assertions (test/TestIterativeSolvers.fypp) ----------
+def _kac(n, dt):
+    """A(i,i) = n, A(i,i+1) = i sqrt(i (n-i)), A(i+1,i) = -A(i,i+1): Hermitian, eigenvalues / singular values 2(n-i+1)-1
+    (TestIterativeSolvers.fypp:158-168, the complex kinds' test matrix)."""
+    A = np.zeros((n, n), dtype=dt)
+    for i in range(1, n + 1):
+        A[i - 1, i - 1] = n
+        if i < n:
+            A[i - 1, i] = 1j * np.sqrt(1.0 * i * (n - i)); A[i, i - 1] = -A[i - 1, i]
+    return np.asfortranarray(A)
+
+
+def _rvec(rng, n, dt):
+    x = rng.standard_normal(n) + (1j * rng.standard_normal(n) if np.dtype(dt).kind == "c" else 0)
+    return x.astype(dt)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_reference_evp_all_kinds(oracle, kind):
+    """test_evp_* (TestIterativeSolvers.fypp:134-225): nev = n = 128, kdim left at 4*nev, tolerance = atol_kind;
+    err = maxval(abs(eigvals - true_eigvals) / abs(true_eigvals)) < rtol_kind with the eigenvalues compared ELEMENTWISE, i.e.
+    in the order sort_index(abs, reverse=.true.) returns them: conjugate pairs as (a + iw, a - iw) -- this pins the tie order of
+    the stable descending sort; complex kinds also check A X = X diag(E) entrywise."""
+    dt = oracle.DTYPES[kind]; rt = oracle.RTOL[kind]; n = N
+    rng = np.random.default_rng(60)
+    if kind in "sd":
+        a_, b_ = rng.random(), abs(rng.random())
+        A = _toeplitz_tridiag(n, -b_, a_, b_, dt)
+        true = np.zeros(n, dtype=np.complex128)
+        for k in range(1, n // 2 + 1):
+            true[2 * k - 2] = a_ + 2j * b_ * np.cos(k * np.pi / (n + 1)); true[2 * k - 1] = np.conj(true[2 * k - 2])
+    else:
+        A = _kac(n, dt)
+        true = np.array([2 * (n - i + 1) - 1 for i in range(1, n + 1)], dtype=np.complex128)
+    ev, res, X, info = oracle.eigs(oracle.Op.dense(A), n, n, _rvec(rng, n, dt), tolerance=oracle.ATOL[kind])
+    assert info > 0
+    assert np.max(np.abs(ev - true) / np.abs(true)) < rt
+    if kind in "cz":
+        assert np.abs(A.astype(np.complex128) @ X - X * ev[None, :]).max() < rt
+    else:
+        # real kinds: columns (i, i+1) of a pair hold (Re, Im) of the eigenvector of the FIRST eigenvalue (LAPACK layout kept)
+        v = X[:, 0].astype(np.complex128) + 1j * X[:, 1]
+        assert np.linalg.norm(A.astype(np.complex128) @ v - ev[0] * v) < 10 * rt * np.linalg.norm(v)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_reference_sym_evp_all_kinds(oracle, kind):
+    """test_sym_evp_r* / test_hermitian_evp_c* (TestIterativeSolvers.fypp:254-336): nev = kdim = n, tolerance = atol_kind;
+    eigenvalues, A X = X diag(E) and X^H X = I, all < rtol_kind."""
+    dt = oracle.DTYPES[kind]; rt = oracle.RTOL[kind]; n = N
+    rng = np.random.default_rng(61)
+    if kind in "sd":
+        a_, b_ = rng.random(), -abs(rng.random())
+        A = _toeplitz_tridiag(n, b_, a_, b_, dt)
+        true = a_ + 2 * abs(b_) * np.cos(np.arange(1, n + 1) * np.pi / (n + 1))
+    else:
+        A = _kac(n, dt)
+        true = np.array([2 * (n - i + 1) - 1 for i in range(1, n + 1)], dtype=np.float64)
+    ev, res, X, info = oracle.eighs(oracle.Op.dense(A), n, n, _rvec(rng, n, dt), kdim=n, tolerance=oracle.ATOL[kind])
+    assert np.abs(true - ev).max() < rt
+    assert np.abs(A @ X - X * ev.astype(dt)).max() < rt
+    assert np.abs(X.conj().T @ X - np.eye(n)).max() < rt
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_reference_svd_all_kinds(oracle, kind):
+    """test_svd_* (TestIterativeSolvers.fypp:420-505): nsv = n, kdim left at 4*nsv, tolerance = atol_kind: singular values,
+    A V = U S, U^H U = I, V^H V = I, all < rtol_kind."""
+    dt = oracle.DTYPES[kind]; rt = oracle.RTOL[kind]; n = N
+    rng = np.random.default_rng(62)
+    if kind in "sd":
+        A = _toeplitz_tridiag(n, -1.0, 2.0, -1.0, dt)
+        true = 2 * (1 + np.cos(np.arange(1, n + 1) * np.pi / (n + 1)))
+    else:
+        A = _kac(n, dt)
+        true = np.array([2 * (n - i + 1) - 1 for i in range(1, n + 1)], dtype=np.float64)
+    S, res, U, V, info = oracle.svds(oracle.Op.dense(A), n, _rvec(rng, n, dt), tolerance=oracle.ATOL[kind])
+    assert np.abs(S - true).max() < rt
+    assert np.abs(A @ V - U * S.astype(dt)).max() < rt
+    assert np.abs(U.conj().T @ U - np.eye(n)).max() < rt and np.abs(V.conj().T @ V - np.eye(n)).max() < rt

@@ -410,7 +410,7 @@ def eighs(apply_A, n, nev, x0, kind, kdim, tol):
         res[:k] = np.abs(beta * vec[k - 1, :k])
         if int((res[:k] < tol).sum()) >= nev:
             break
-    idx = np.argsort(ev, kind="stable")[::-1]                                   # sort_index(reverse = .true.)
+    idx = np.argsort(-ev, kind="stable")                                        # sort_index(reverse = .true.): non-increasing, ties in original order
     k = min(k, kdim)
     return ev[idx[:nev]], res[idx[:nev]], k
 
@@ -542,7 +542,7 @@ def eigs_literal(apply_A, n, nev, x0, kind, kdim, tol):
         kstart = _krylov_schur_literal(Xw, H) + 1
     k = min(k, kdim)
     vals = np.linalg.eigvals(H[:k, :k])                            # eig of the RESTARTED matrix (:1108-1110)
-    order = np.argsort(np.abs(vals), kind="stable")[::-1]
+    order = np.argsort(-np.abs(vals), kind="stable")           # sort_index(reverse = .true.): non-increasing, ties in original order
     return vals[order[:nev]], niter, k, kstart - 1
 
 
