@@ -486,3 +486,74 @@ def test_reference_svd_all_kinds(oracle, kind):
     assert np.abs(S - true).max() < rt
     assert np.abs(A @ V - U * S.astype(dt)).max() < rt
     assert np.abs(U.conj().T @ U - np.eye(n)).max() < rt and np.abs(V.conj().T @ V - np.eye(n)).max() < rt
+
+
+@pytest.mark.parametrize("kind", ["s", "d"])
+def test_reference_ks_evp_real_kinds(oracle, kind):
+    """test_ks_evp_r* (TestIterativeSolvers.fypp:59-130): nev = 8, kdim at its default 32, tolerance = atol_kind (1e-15 in
+    fp64: some 300 Arnoldi steps with Krylov-Schur restarts); err = maxval(abs(eigvals - true_eigvals(:nev))) < rtol_kind,
+    ELEMENTWISE, conjugate pairs as (a + iw, a - iw).  (The complex kinds' body is empty in the reference.)"""
+    dt = oracle.DTYPES[kind]; n, nev = N, 8
+    for seed in (70, 71):
+        rng = np.random.default_rng(seed)
+        a_, b_ = rng.random(), abs(rng.random())
+        A = _toeplitz_tridiag(n, -b_, a_, b_, dt)
+        true = np.zeros(n, dtype=np.complex128)
+        for k in range(1, n // 2 + 1):
+            true[2 * k - 2] = a_ + 2j * b_ * np.cos(k * np.pi / (n + 1)); true[2 * k - 1] = np.conj(true[2 * k - 2])
+        ev, res, X, info = oracle.eigs(oracle.Op.dense(A), n, nev, rng.standard_normal(n).astype(dt),
+                                      tolerance=oracle.ATOL[kind], max_restarts=400)
+        assert info > 32                                           # restarted
+        assert np.abs(ev - true[:nev]).max() < oracle.RTOL[kind]
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_reference_kexptA_all_kinds(oracle, kind):
+    """test_kexptA_* (test/TestExpmlib.fypp, TestExpmlib.f90:280-332): A = N(0,1) entries (n = 128), random Q, tau = 0.1,
+    kdim = 64, tol = rtol_kind: || kexpm(A, Q) - expm(tau A) Q || / || expm(tau A) Q || < rtol_kind."""
+    import scipy.linalg as sl
+    dt = oracle.DTYPES[kind]; rt = oracle.RTOL[kind]; n = N
+    rng = np.random.default_rng(63)
+    c = (lambda s: rng.standard_normal(s) + (1j * rng.standard_normal(s) if kind in "cz" else 0))
+    A = np.asfortranarray(c((n, n)).astype(dt)); q = c(n).astype(dt)
+    ref = sl.expm(0.1 * A.astype(np.complex128)) @ q
+    x, info = oracle.kexpm_vec(oracle.Op.dense(A), q, 0.1, rt, kdim=64)
+    assert 1 < info <= 65
+    assert np.linalg.norm(x - ref) / np.linalg.norm(ref) < rt
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_reference_krylov_schur_all_kinds(oracle, kind):
+    """test_krylov_schur_* (test/TestKrylov.fypp:298-347): A = N(0,1) / ||A||_F (n = 128), kdim = 100, Arnoldi with
+    tol = atol_kind, krylov_schur with the median selector (LAPACK gees + trsen in the precision of the kind):
+    max |A X(:, :n) - X(:, :n+1) H(:n+1, :n)| < rtol_kind."""
+    dt = oracle.DTYPES[kind]; n, kdim = N, 100
+    rng = np.random.default_rng(64)
+    A = _randn(rng, (n, n), dt); A = np.asfortranarray(A / np.sqrt((np.abs(A) ** 2).sum()).astype(A.real.dtype))
+    X = _start(rng, n, kdim + 1, dt, oracle)
+    H = np.zeros((kdim + 1, kdim), dtype=dt, order="F")
+    assert oracle.arnoldi(oracle.Op.dense(A), X, H, tol=oracle.ATOL[kind]) == 0
+    nk = oracle.krylov_schur(X, H)
+    assert 0 < nk < kdim
+    assert np.abs(A @ X[:, :nk] - X[:, :nk + 1] @ H[:nk + 1, :nk]).max() < oracle.RTOL[kind]
+    assert not X[:, nk + 1:].any() and not H[nk + 1:, :].any() and not H[:, nk:].any()
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_reference_gmres_and_cg_all_kinds(oracle, kind):
+    """test_gmres_* (TestIterativeSolvers.f90:1363-1393, 1537-1571): A, b = U[0,1) entries (real and imaginary parts for the
+    complex kinds), n = 128, kdim = 128, default maxiter, rtol = rtol_kind, atol = atol_kind: ||A x - b|| < ||b|| rtol_kind.
+    test_cg_* (:1847-1881): A = D D^H / n + 0.01 I with D = N(0,1), maxiter = 2 n, same assertion.  Literal bounds (no slack)."""
+    dt = oracle.DTYPES[kind]; rt = oracle.RTOL[kind]; at = oracle.ATOL[kind]; n = N
+    rng = np.random.default_rng(80)
+    cu = (lambda s: rng.random(s) + (1j * rng.random(s) if kind in "cz" else 0))
+    cn = (lambda s: rng.standard_normal(s) + (1j * rng.standard_normal(s) if kind in "cz" else 0))
+    A = np.asfortranarray(cu((n, n)).astype(dt)); b = cu(n).astype(dt); x = np.zeros(n, dtype=dt)
+    info, meta = oracle.gmres(oracle.Op.dense(A), b, x, rtol=rt, atol=at, kdim=n, maxiter=10)
+    assert info > 0 and meta["converged"]
+    assert np.linalg.norm(A @ x - b) < np.linalg.norm(b) * rt
+    D = cn((n, n))
+    S = np.asfortranarray((D @ D.conj().T / n + 0.01 * np.eye(n)).astype(dt)); b = cn(n).astype(dt); x = np.zeros(n, dtype=dt)
+    info, meta = oracle.cg(oracle.Op.dense(S), b, x, rtol=rt, atol=at, maxiter=2 * n)
+    assert info > 0
+    assert np.linalg.norm(S @ x - b) < np.linalg.norm(b) * rt
