@@ -552,6 +552,10 @@ def test_reference_gmres_and_cg_all_kinds(oracle, kind):
     info, meta = oracle.gmres(oracle.Op.dense(A), b, x, rtol=rt, atol=at, kdim=n, maxiter=10)
     assert info > 0 and meta["converged"]
     assert np.linalg.norm(A @ x - b) < np.linalg.norm(b) * rt
+    xf = np.zeros(n, dtype=dt)                                       # test_fgmres_* (:1670-1700): same inputs, no preconditioner
+    finfo, fmeta = oracle.gmres(oracle.Op.dense(A), b, xf, rtol=rt, atol=at, kdim=n, maxiter=10, flexible=True)
+    assert finfo > 0 and fmeta["converged"]
+    assert np.linalg.norm(A @ xf - b) < np.linalg.norm(b) * rt
     D = cn((n, n))
     S = np.asfortranarray((D @ D.conj().T / n + 0.01 * np.eye(n)).astype(dt)); b = cn(n).astype(dt); x = np.zeros(n, dtype=dt)
     info, meta = oracle.cg(oracle.Op.dense(S), b, x, rtol=rt, atol=at, maxiter=2 * n)
