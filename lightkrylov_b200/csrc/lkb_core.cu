@@ -330,6 +330,7 @@ int lkb_set_seed(lkb_ctx_t c, uint64_t seed) { c->seed = seed; c->seed_calls = 0
 int lkb_set_graphs(lkb_ctx_t c, int enable) { c->graphs = enable != 0; return 0; }
 int lkb_set_option(lkb_ctx_t c, const char* name, int value) {
     if (!c || !name) return LKB_ERR_ARG;
+    if (!strcmp(name, "write_intermediate")) { c->write_intermediate = value != 0; return 0; }     // host-side only: graphs stay valid
     cudaStreamSynchronize(c->stream);
     invalidate_graphs(c, 0);          // cached step graphs were captured with the previous settings
     if (!strcmp(name, "graphs")) c->graphs = value != 0;

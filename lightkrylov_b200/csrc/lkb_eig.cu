@@ -451,12 +451,22 @@ int lkb_eigs(lkb_op_t A, lkb_basis_t X, int nev, double* eigvals, double* residu
             }
             niter++;
             EG_TRY(bcast_host(c, res.data(), (size_t)k * sizeof(double)));
-            if (c->write_intermediate && c->rank == 0) {          // write_results_c(eigs_output, ...)  (:1091)
-                std::vector<double> vv(2 * (size_t)k), rr(res.begin(), res.begin() + k);
-                for (int i = 0; i < k; ++i) { vv[2 * i] = vals[i].real(); vv[2 * i + 1] = vals[i].imag(); }
-                lkb_write_results("eigs_output.txt", 1, vv.data(), rr.data(), k, tol);
-            }
             conv = 0; for (int i = 0; i < k; ++i) conv += res[i] < tol;
+            if (c->write_intermediate) {                          // write_results_c(eigs_output, ...)  (:1091)
+                // LITERAL side effect: write_results sorts its `res` argument IN PLACE (`call sort_index(res, indices)`, intent(inout),
+                // IterativeSolvers.fypp:907), so with write_intermediate (the reference's DEFAULT for eigs) residuals_wrk(:k) is left
+                // in ascending order and the residuals returned at the end are entries of that sorted table.  The reference does this
+                // on the I/O rank only (its other ranks keep the unsorted table); here every rank applies the same sort.
+                std::vector<double> rr(res.begin(), res.begin() + k);
+                if (c->rank == 0) {
+                    std::vector<double> vv(2 * (size_t)k);
+                    for (int i = 0; i < k; ++i) { vv[2 * i] = vals[i].real(); vv[2 * i + 1] = vals[i].imag(); }
+                    EG_TRY(lkb_write_results("eigs_output.txt", 1, vv.data(), rr.data(), k, tol));
+                } else {
+                    std::stable_sort(rr.begin(), rr.end());
+                }
+                std::copy(rr.begin(), rr.end(), res.begin());
+            }
             if (conv >= nev) {
                 // a speculative step k+1 may still be running: it is discarded (never collected, so the
                 // operator's matvec counter does not include it); the sync below waits for it
@@ -558,11 +568,13 @@ int lkb_eighs(lkb_op_t A, lkb_basis_t X, int nev, double* eigvals, double* resid
         std::fill(res.begin(), res.end(), 0.0);
         for (int i = 0; i < k; ++i) res[i] = std::abs(beta * vecs[(k - 1) + (size_t)kd * i]);
         EH_TRY(bcast_host(c, res.data(), (size_t)k * sizeof(double)));
-        if (c->write_intermediate && c->rank == 0) {              // write_results_r(eighs_output, ...)  (eighs.fypp:99)
-            std::vector<double> rr(res.begin(), res.begin() + k);
-            lkb_write_results("eighs_output.txt", 0, ev.data(), rr.data(), k, tol);
-        }
         conv = 0; for (int i = 0; i < k; ++i) conv += res[i] < tol;
+        if (c->write_intermediate) {                              // write_results_r(eighs_output, ...)  (eighs.fypp:99)
+            std::vector<double> rr(res.begin(), res.begin() + k); // sorts the residual table in place, see lkb_eigs
+            if (c->rank == 0) EH_TRY(lkb_write_results("eighs_output.txt", 0, ev.data(), rr.data(), k, tol));
+            else std::stable_sort(rr.begin(), rr.end());
+            std::copy(rr.begin(), rr.end(), res.begin());
+        }
         if (conv >= nev) break;
     }
     EH_TRY(cudaStreamSynchronize(c->stream) == cudaSuccess ? 0 : LKB_ERR_CUDA);     // a discarded speculative step may still run
@@ -641,11 +653,13 @@ int lkb_svds(lkb_op_t A, lkb_basis_t U, double* S, lkb_basis_t V, int nsv, doubl
         std::fill(res.begin(), res.end(), 0.0);
         for (int i = 0; i < k; ++i) res[i] = std::abs(beta * vmat[(k - 1) + (size_t)kd * i]);
         SV_TRY(bcast_host(c, res.data(), (size_t)k * sizeof(double)));
-        if (c->write_intermediate && c->rank == 0) {              // write_results_r(svds_output, ...)  (svd_solvers.fypp:100)
-            std::vector<double> rr(res.begin(), res.begin() + k);
-            lkb_write_results("svds_output.txt", 0, sv.data(), rr.data(), k, tol);
-        }
         conv = 0; for (int i = 0; i < k; ++i) conv += res[i] < tol;
+        if (c->write_intermediate) {                              // write_results_r(svds_output, ...)  (svd_solvers.fypp:100)
+            std::vector<double> rr(res.begin(), res.begin() + k); // sorts the residual table in place, see lkb_eigs
+            if (c->rank == 0) SV_TRY(lkb_write_results("svds_output.txt", 0, sv.data(), rr.data(), k, tol));
+            else std::stable_sort(rr.begin(), rr.end());
+            std::copy(rr.begin(), rr.end(), res.begin());
+        }
         if (conv >= nsv) break;
     }
     SV_TRY(cudaStreamSynchronize(c->stream) == cudaSuccess ? 0 : LKB_ERR_CUDA);

@@ -525,11 +525,14 @@ def krylov_schur(X: np.ndarray, H: np.ndarray):
     return n
 
 
-def eigs(A: Op, n: int, nev: int, x0: np.ndarray, kdim=None, tolerance=None, trans=False, max_restarts=200):
+def eigs(A: Op, n: int, nev: int, x0: np.ndarray, kdim=None, tolerance=None, trans=False, max_restarts=200,
+         write_intermediate=False):
     """IterativeSolvers.fypp:972-1143.  Returns (eigvals[nev], residuals[nev], X[n, nev], info=niter).
     Literal control flow since round 2: the reference runs krylov_schur once more AFTER convergence and post-processes the
     restarted H / basis (residuals keep their pre-restart order); tests/test_oracle_second_opinion.py holds an independent
-    restatement of that flow."""
+    restatement of that flow.  write_intermediate=True (the reference's DEFAULT for eigs, :1025) reproduces the side effect of
+    write_results (:882-924): `call sort_index(res, indices)` sorts the residual table IN PLACE every step (no file is written
+    here), so the returned residuals are entries of the ascending table."""
     kind = kind_of(x0.dtype)
     dt = DTYPES[kind]
     cplx = kind in "cz"
@@ -560,6 +563,8 @@ def eigs(A: Op, n: int, nev: int, x0: np.ndarray, kdim=None, tolerance=None, tra
                 res[i] = abs(beta) * alpha
             niter += 1
             conv = int((res[:k] < tol).sum())
+            if write_intermediate:
+                res[:k] = np.sort(res[:k], kind="stable")
             if conv >= nev:
                 break
         # LITERAL control flow (IterativeSolvers.fypp:1088-1099): `exit arnoldi_factorization` leaves only the inner loop, so
@@ -585,7 +590,7 @@ def eigs(A: Op, n: int, nev: int, x0: np.ndarray, kdim=None, tolerance=None, tra
     return eigvals, residuals, Xout, niter
 
 
-def eighs(A: Op, n: int, nev: int, x0: np.ndarray, kdim=None, tolerance=None):
+def eighs(A: Op, n: int, nev: int, x0: np.ndarray, kdim=None, tolerance=None, write_intermediate=False):
     """EIGHS/eighs.fypp:29-126.  eigh = syev/heev on the lower triangle."""
     import scipy.linalg as sla
     kind = kind_of(x0.dtype); dt = DTYPES[kind]
@@ -601,7 +606,10 @@ def eighs(A: Op, n: int, nev: int, x0: np.ndarray, kdim=None, tolerance=None):
         w, v = sla.eigh(np.asfortranarray(T[:k, :k]), lower=True, driver="ev")      # ssyev / cheev for the fp32 kinds
         ev[:k] = w; vecs[:k, :k] = v
         res[:k] = np.abs(T[k, k - 1] * vecs[k - 1, :k])
-        if int((res[:k] < tol).sum()) >= nev:
+        conv = int((res[:k] < tol).sum())
+        if write_intermediate:                                       # write_results sorts `res` in place (see eigs)
+            res[:k] = np.sort(res[:k], kind="stable")
+        if conv >= nev:
             break
     idx = _sort_index_reverse(ev)
     k = min(k, kdim)
@@ -610,7 +618,7 @@ def eighs(A: Op, n: int, nev: int, x0: np.ndarray, kdim=None, tolerance=None):
     return eigvals, residuals, Xout, k
 
 
-def svds(A: Op, nsv: int, u0: np.ndarray, kdim=None, tolerance=None):
+def svds(A: Op, nsv: int, u0: np.ndarray, kdim=None, tolerance=None, write_intermediate=False):
     """SVDS/svd_solvers.fypp:28-121.  svd = gesdd."""
     import scipy.linalg as sla
     kind = kind_of(u0.dtype); dt = DTYPES[kind]
@@ -630,7 +638,10 @@ def svds(A: Op, nsv: int, u0: np.ndarray, kdim=None, tolerance=None):
         sv[:] = 0; res[:] = 0
         sv[:k] = s
         res[:k] = np.abs(B[k, k - 1] * vm[k - 1, :k])
-        if int((res[:k] < tol).sum()) >= nsv:
+        conv = int((res[:k] < tol).sum())
+        if write_intermediate:                                       # write_results sorts `res` in place (see eigs)
+            res[:k] = np.sort(res[:k], kind="stable")
+        if conv >= nsv:
             break
     k = min(k, kdim)
     U = np.asfortranarray((Uw[:, :k].astype(wd) @ u[:k, :nsv]).astype(dt))

@@ -309,3 +309,41 @@ def test_kexpm_mat_breakdown_exits(lk, ctx, oracle):
     exact = np.exp(0.2 * np.arange(1, n + 1))[:, None] * Bh
     assert np.linalg.norm(Cb.get() - exact) < 1e-12 * np.linalg.norm(exact)
     assert np.linalg.norm(Co - exact) < 1e-12 * np.linalg.norm(exact)
+
+
+def test_write_intermediate_sorts_the_residual_table(lk, ctx, oracle, tmp_path):
+    """write_results sorts its residual argument IN PLACE (`call sort_index(res, indices)`, intent(inout),
+    IterativeSolvers.fypp:882-924), so with write_intermediate (option "write_intermediate"; the reference's default for eigs)
+    the residuals a solver returns are entries of the ASCENDING table: for eighs the nev largest ones in non-increasing
+    order.  Same `info` and eigenvalues as without the option; the oracle restates the side effect; the table files appear."""
+    import os
+    nev = 4
+    rng = np.random.default_rng(26)
+    D = np.diag(np.concatenate([np.linspace(0, 1, N - 4), [2.0, 2.5, 3.0, 4.0]])); Q, _ = np.linalg.qr(rng.standard_normal((N, N)))
+    Ah = Q @ D @ Q.T; Ah = np.asfortranarray((Ah + Ah.T) / 2)             # four separated leading eigenvalues: converges at k ~ 16
+    x0h = randn(np.random.default_rng(25), N, np.float64)
+    A = lk.LinOp.dense(ctx, Ah); x0 = lk.Vector(ctx, "d", N).put(x0h)
+    X = lk.Basis(ctx, "d", N, nev)
+    ev0, res0, info0 = lk.eighs(A, X, nev, x0=x0, kdim=60, tolerance=1e-6)
+    Ag = lk.LinOp.dense(ctx, _toeplitz(N, -0.5, 1.0, 0.5)); Xg = lk.Basis(ctx, "d", N, nev)
+    evg0, resg0, infog0 = lk.eigs(Ag, Xg, nev, x0=x0, kdim=4 * nev)
+    cwd = os.getcwd()
+    try:
+        os.chdir(tmp_path)
+        ctx.set_option("write_intermediate", 1)
+        ev1, res1, info1 = lk.eighs(A, X, nev, x0=x0, kdim=60, tolerance=1e-6)
+        evg1, resg1, infog1 = lk.eigs(Ag, Xg, nev, x0=x0, kdim=4 * nev)
+    finally:
+        ctx.set_option("write_intermediate", 0)
+        os.chdir(cwd)
+    assert info1 == info0 and 4 < info1 < 60 and np.allclose(ev1, ev0, rtol=1e-13, atol=0)
+    assert infog1 == infog0 and np.allclose(evg1, evg0, rtol=1e-13, atol=1e-13)
+    assert np.all(res0 < 1e-6)                                               # without the option: the residuals of the returned pairs
+    assert np.all(np.diff(res1) <= 0) and res1[-1] > 1e-3                    # with it: the largest entries of the sorted table, descending
+    evo, reso, Xo, ko = oracle.eighs(oracle.Op.dense(Ah), N, nev, x0h, kdim=60, tolerance=1e-6, write_intermediate=True)
+    assert ko == info1
+    np.testing.assert_allclose(res1, reso, rtol=1e-6)
+    lines = open(tmp_path / "eighs_output.txt").read().splitlines()
+    assert len(lines) == info1 + 1 and lines[0].split() == ["Iter", "value", "residual", "conv"]
+    glines = open(tmp_path / "eigs_output.txt").read().splitlines()
+    assert glines[0].split() == ["Iter", "Re", "Im", "modulus", "residual", "conv"] and len(glines) >= 2
