@@ -219,12 +219,14 @@ static int reset_flags(lkb_ctx_s* c) {
     return 0;
 }
 
-// is_orthonormal (src/Krylov/utilities.fypp:90-98): Gram(X) vs I with the hard-wired rtol_sp
+// is_orthonormal (src/Krylov/utilities.fypp:90-98): mnorm(Gram(X) - I, "Fro") > rtol_sp (hard-wired, all kinds) => not orthonormal
 static int check_orthonormal(lkb_basis_s* X, int j, bool* ok) {
     lkb_ctx_s* c = X->ctx;
     *ok = true;
     std::vector<Scalar> col;
-    for (int q = 0; q < j && *ok; ++q) {
+    double fro2 = 0.0;                                         // squared Frobenius norm of G - I, column by column
+    const double lim2 = 1e-3 * 1e-3;                           // rtol_sp = sqrt(atol_sp) = 1e-3
+    for (int q = 0; q < j && fro2 <= lim2; ++q) {
         LKB_TRY(ensure_ws(c, j + 1));
         launch_multidot(X->kind, c->stream, X->d, X->ld, j, col_ptr(X, q), X->n, c->partial, c->c1, c->counter, nullptr, c->sms, c->p2p_arg());
         c->launches++;
@@ -233,9 +235,10 @@ static int check_orthonormal(lkb_basis_s* X, int j, bool* ok) {
         LKB_TRY(fetch_coeffs(c, X->kind, j, false, col, nullptr, nullptr));
         for (int i = 0; i < j; ++i) {
             const double re = col[i].re - (i == q ? 1.0 : 0.0);
-            if (hypot(re, col[i].im) > 1e-3 /* rtol_sp */) { *ok = false; break; }
+            fro2 += re * re + col[i].im * col[i].im;
         }
     }
+    *ok = !(fro2 > lim2);
     return 0;
 }
 
