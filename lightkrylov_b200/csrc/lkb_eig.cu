@@ -461,7 +461,8 @@ int lkb_eigs(lkb_op_t A, lkb_basis_t X, int nev, double* eigvals, double* residu
                 if (c->rank == 0) {
                     std::vector<double> vv(2 * (size_t)k);
                     for (int i = 0; i < k; ++i) { vv[2 * i] = vals[i].real(); vv[2 * i + 1] = vals[i].imag(); }
-                    EG_TRY(lkb_write_results("eigs_output.txt", 1, vv.data(), rr.data(), k, tol));
+                    (void)lkb_write_results("eigs_output.txt", 1, vv.data(), rr.data(), k, tol);   // rr is sorted even if the file cannot be written;
+                                                                                                  // an I/O failure on one rank must not desynchronise the ranks
                 } else {
                     std::stable_sort(rr.begin(), rr.end());
                 }
@@ -571,7 +572,7 @@ int lkb_eighs(lkb_op_t A, lkb_basis_t X, int nev, double* eigvals, double* resid
         conv = 0; for (int i = 0; i < k; ++i) conv += res[i] < tol;
         if (c->write_intermediate) {                              // write_results_r(eighs_output, ...)  (eighs.fypp:99)
             std::vector<double> rr(res.begin(), res.begin() + k); // sorts the residual table in place, see lkb_eigs
-            if (c->rank == 0) EH_TRY(lkb_write_results("eighs_output.txt", 0, ev.data(), rr.data(), k, tol));
+            if (c->rank == 0) (void)lkb_write_results("eighs_output.txt", 0, ev.data(), rr.data(), k, tol);
             else std::stable_sort(rr.begin(), rr.end());
             std::copy(rr.begin(), rr.end(), res.begin());
         }
@@ -656,7 +657,7 @@ int lkb_svds(lkb_op_t A, lkb_basis_t U, double* S, lkb_basis_t V, int nsv, doubl
         conv = 0; for (int i = 0; i < k; ++i) conv += res[i] < tol;
         if (c->write_intermediate) {                              // write_results_r(svds_output, ...)  (svd_solvers.fypp:100)
             std::vector<double> rr(res.begin(), res.begin() + k); // sorts the residual table in place, see lkb_eigs
-            if (c->rank == 0) SV_TRY(lkb_write_results("svds_output.txt", 0, sv.data(), rr.data(), k, tol));
+            if (c->rank == 0) (void)lkb_write_results("svds_output.txt", 0, sv.data(), rr.data(), k, tol);
             else std::stable_sort(rr.begin(), rr.end());
             std::copy(rr.begin(), rr.end(), res.begin());
         }
