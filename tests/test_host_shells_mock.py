@@ -1,0 +1,268 @@
+"""The product's host shells (lightkrylov_b200/csrc/lkb_eig.cu: eigs incl. the literal post-convergence Krylov-Schur restart,
+eighs, svds, krylov_schur; LAPACK in the precision of the kind; stable descending sort_index; write_intermediate side effect)
+run WITHOUT a GPU: tests/host_shells_mock.cu includes that translation unit verbatim and replaces the device underneath it
+-- CUDA runtime calls by host memory, the Krylov steps by the C oracle -- so the C++ control flow sees exactly the
+Hessenberg / tridiagonal / bidiagonal columns the Python oracle shells see, and the two must agree (same `info`, same
+eigenvalue ORDER, same residuals, same vectors).  The real device path is checked by the -m gpu tests; this suite is the CPU
+regression net of the host logic (it is how changes to the shells are verified when no GPU is at hand)."""
+import ctypes as C
+import glob
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import randn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "lightkrylov_b200", "csrc")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+KINDS = {"s": 0, "d": 1, "c": 2, "z": 3}
+N = 128
+
+pytestmark = pytest.mark.skipif(not os.path.exists(NVCC) and shutil.which("nvcc") is None, reason="needs nvcc to compile the harness")
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    from oracle import lk_oracle
+    lk_oracle.lib()
+    return lk_oracle
+
+
+@pytest.fixture(scope="module")
+def mock(tmp_path_factory, oracle):
+    import scipy
+    import __graft_entry__
+    __graft_entry__.build()
+    out = str(tmp_path_factory.mktemp("mock") / "libhost_shells_mock.so")
+    nvcc = NVCC if os.path.exists(NVCC) else shutil.which("nvcc")
+    odir = os.path.join(ROOT, "oracle")
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O1", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
+                           "-diag-suppress", "174", "-I", CSRC, os.path.join(ROOT, "tests", "host_shells_mock.cu"), "-o", out,
+                           "-L", CSRC, "-llkb", "-L", odir, "-llk_oracle", "-ldl", "-Xlinker", "-rpath=" + CSRC,
+                           "-Xlinker", "-rpath=" + odir, "-Xlinker", "-Bsymbolic"], stderr=subprocess.DEVNULL)
+    lib = C.CDLL(out)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    lib.mock_ctx_new.restype = vp; lib.mock_ctx_new.argtypes = [C.c_int]
+    lib.mock_ctx_free.argtypes = [vp]
+    lib.mock_op_new.restype = vp; lib.mock_op_new.argtypes = [vp, C.c_int, i64, i64, vp]
+    lib.mock_op_free.argtypes = [vp]
+    lib.mock_vec_new.restype = vp; lib.mock_vec_new.argtypes = [vp, C.c_int, i64, vp]
+    lib.mock_vec_free.argtypes = [vp]
+    lib.mock_basis_get.argtypes = [vp, vp]; lib.mock_basis_put.argtypes = [vp, vp]
+    lib.mock_last_error.restype = C.c_char_p
+    lib.lkb_basis_create.argtypes = [vp, C.c_int, i64, i64, i64, C.c_int, C.POINTER(vp)]
+    lib.lkb_basis_destroy.argtypes = [vp]
+    lib.lkb_set_lapack.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p]
+    lib.lkb_eigs.argtypes = [vp, vp, C.c_int, vp, vp, C.POINTER(i32), vp, i32, dbl, i32]
+    lib.lkb_eighs.argtypes = [vp, vp, C.c_int, vp, vp, C.POINTER(i32), vp, i32, dbl]
+    lib.lkb_svds.argtypes = [vp, vp, vp, vp, C.c_int, vp, C.POINTER(i32), vp, i32, dbl]
+    lib.lkb_krylov_schur.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(i32)]
+    blas = glob.glob(os.path.join(os.path.dirname(os.path.dirname(scipy.__file__)), "scipy.libs", "libscipy_openblas*.so"))[0]
+    assert lib.lkb_set_lapack(blas.encode(), b"scipy_", b"_") == 0, lib.mock_last_error()
+    return lib
+
+
+class Shells:
+    """thin driver of the C++ shells on host memory"""
+
+    def __init__(self, lib, kind, write_intermediate=False):
+        self.lib, self.kind, self.dt = lib, kind, {"s": np.float32, "d": np.float64, "c": np.complex64, "z": np.complex128}[kind]
+        self.ctx = lib.mock_ctx_new(int(write_intermediate))
+        self.keep = []
+
+    def close(self):
+        self.lib.mock_ctx_free(self.ctx)
+
+    def op(self, oracle_op):
+        self.keep.append(oracle_op)
+        return self.lib.mock_op_new(self.ctx, KINDS[self.kind], oracle_op.m, oracle_op.n, C.addressof(oracle_op.st))
+
+    def basis(self, n, ncols, data=None):
+        h = C.c_void_p()
+        assert self.lib.lkb_basis_create(self.ctx, KINDS[self.kind], n, n, 0, ncols, C.byref(h)) == 0
+        if data is not None:
+            a = np.asfortranarray(data, dtype=self.dt); self.lib.mock_basis_put(h, a.ctypes.data)
+        return h
+
+    def get(self, h, n, ncols):
+        out = np.zeros((n, ncols), dtype=self.dt, order="F")
+        self.lib.mock_basis_get(h, out.ctypes.data)
+        return out
+
+    def vec(self, x):
+        a = np.ascontiguousarray(x, dtype=self.dt); self.keep.append(a)
+        return self.lib.mock_vec_new(self.ctx, KINDS[self.kind], a.size, a.ctypes.data)
+
+    def check(self, rc):
+        assert rc == 0, self.lib.mock_last_error()
+
+    def eigs(self, A, n, nev, x0, kdim=0, tol=-1.0, trans=False):
+        X = self.basis(n, nev); ev = np.zeros(2 * nev); res = np.zeros(nev); info = C.c_int32()
+        self.check(self.lib.lkb_eigs(A, X, nev, ev.ctypes.data, res.ctypes.data, C.byref(info), self.vec(x0), kdim, tol, int(trans)))
+        return ev[0::2] + 1j * ev[1::2], res, self.get(X, n, nev), info.value
+
+    def eighs(self, A, n, nev, x0, kdim=0, tol=-1.0):
+        X = self.basis(n, nev); ev = np.zeros(nev); res = np.zeros(nev); info = C.c_int32()
+        self.check(self.lib.lkb_eighs(A, X, nev, ev.ctypes.data, res.ctypes.data, C.byref(info), self.vec(x0), kdim, tol))
+        return ev, res, self.get(X, n, nev), info.value
+
+    def svds(self, A, m, n, nsv, u0, kdim=0, tol=-1.0):
+        U = self.basis(m, nsv); V = self.basis(n, nsv); S = np.zeros(nsv); res = np.zeros(nsv); info = C.c_int32()
+        self.check(self.lib.lkb_svds(A, U, S.ctypes.data, V, nsv, res.ctypes.data, C.byref(info), self.vec(u0), kdim, tol))
+        return S, res, self.get(U, m, nsv), self.get(V, n, nsv), info.value
+
+
+def _toeplitz(n, sub, diag, sup, dt):
+    A = np.zeros((n, n), dtype=dt); i = np.arange(n)
+    A[i, i] = diag; A[i[1:], i[:-1]] = sub; A[i[:-1], i[1:]] = sup
+    return np.asfortranarray(A)
+
+
+def _tol(kind):
+    return 1e-11 if kind in "dz" else 2e-4
+
+
+def _aligned(X, Xo, ev, kind):
+    """Ritz vectors agree up to the complex phase LAPACK's normalisation leaves open ("largest component real" flips between two
+    components of nearly equal modulus under rounding-level perturbations): 1 - |<v, vo>| / (|v| |vo|) per eigenvector; real
+    kinds: columns (i, i+1) of a conjugate pair hold (Re, Im) of the first eigenvalue's vector."""
+    worst, i, nev = 0.0, 0, X.shape[1]
+    while i < nev:
+        if kind in "cz" or ev[i].imag == 0:
+            v, vo = X[:, i].astype(np.complex128), Xo[:, i].astype(np.complex128); i += 1
+        elif i + 1 < nev:
+            v, vo = X[:, i] + 1j * X[:, i + 1], Xo[:, i] + 1j * Xo[:, i + 1]; i += 2
+        else:
+            break
+        worst = max(worst, abs(1.0 - abs(np.vdot(v, vo)) / (np.linalg.norm(v) * np.linalg.norm(vo))))
+        worst = max(worst, abs(np.linalg.norm(v) - np.linalg.norm(vo)))
+    return worst
+
+
+@pytest.mark.parametrize("kind", ["d", "z", "s", "c"])
+def test_eigs_shell_matches_oracle_shell(mock, oracle, kind):
+    """nev = 8, kdim = 32: Krylov-Schur restarts, the literal extra restart after convergence, stable descending sort --
+    same niter, same eigenvalues IN THE SAME ORDER, same residual entries, same Ritz vectors."""
+    dt = oracle.DTYPES[kind]; nev = 8
+    Ah = _toeplitz(N, -0.5, 1.0, 0.5, dt) if kind in "sd" else np.asfortranarray(
+        (_toeplitz(N, -0.5, 1.0, 0.5, dt) + 0.3j * np.diag(np.linspace(-1, 1, N))).astype(dt))
+    x0 = randn(np.random.default_rng(21), N, dt)
+    sh = Shells(mock, kind)
+    ev, res, X, info = sh.eigs(sh.op(oracle.Op.dense(Ah)), N, nev, x0, kdim=4 * nev)
+    evo, reso, Xo, infoo = oracle.eigs(oracle.Op.dense(Ah), N, nev, x0, kdim=4 * nev)
+    sh.close()
+    assert info == infoo and info > 4 * nev
+    assert np.abs(ev - evo).max() < _tol(kind) * np.abs(evo).max()              # elementwise: same order
+    np.testing.assert_allclose(res, reso, rtol=1e-6 if kind in "dz" else 5e-2, atol=1e-12 if kind in "dz" else 1e-6)
+    assert _aligned(X, Xo, ev, kind) < (1e-8 if kind in "dz" else 5e-3)
+    if kind in "sd":
+        assert ev[0].imag > 0 and ev[1] == np.conj(ev[0])                       # a conjugate pair stays (+, -)
+
+
+def test_eigs_full_spectrum_default_kdim(mock, oracle):
+    """the reference's test_evp_rdp: nev = n, kdim = 4 nev > n; elementwise against the analytic spectrum (pair order)."""
+    a, b = 1.0, 0.5
+    Ah = _toeplitz(N, -b, a, b, np.float64); x0 = np.random.default_rng(20).standard_normal(N)
+    sh = Shells(mock, "d")
+    ev, res, X, info = sh.eigs(sh.op(oracle.Op.dense(Ah)), N, N, x0)
+    sh.close()
+    true = np.zeros(N, dtype=np.complex128)
+    for k in range(1, N // 2 + 1):
+        true[2 * k - 2] = a + 2j * b * np.cos(k * np.pi / (N + 1)); true[2 * k - 1] = np.conj(true[2 * k - 2])
+    assert info == N
+    assert np.max(np.abs(ev - true) / np.abs(true)) < oracle.RTOL["d"]
+    v = X[:, 0] + 1j * X[:, 1]
+    assert np.linalg.norm(Ah @ v - ev[0] * v) < 1e-8 * np.linalg.norm(v)         # columns (Re, Im) of the pair's first eigenvalue
+
+
+@pytest.mark.parametrize("kind", ["d", "z", "s", "c"])
+def test_eighs_and_svds_shells_match_oracle_shells(mock, oracle, kind):
+    dt = oracle.DTYPES[kind]; nev = 6
+    rng = np.random.default_rng(26)
+    D = np.diag(np.concatenate([np.linspace(0, 1, N - 4), [2.0, 2.5, 3.0, 4.0]])); Q, _ = np.linalg.qr(randn(rng, (N, N), np.complex128 if kind in "cz" else np.float64))
+    Ah = Q @ D @ Q.conj().T; Ah = np.asfortranarray(((Ah + Ah.conj().T) / 2).astype(dt))
+    x0 = randn(np.random.default_rng(25), N, dt)
+    sh = Shells(mock, kind)
+    ev, res, X, info = sh.eighs(sh.op(oracle.Op.dense(Ah)), N, nev, x0, kdim=80)
+    evo, reso, Xo, infoo = oracle.eighs(oracle.Op.dense(Ah), N, nev, x0, kdim=80)
+    assert info == infoo and 4 < info < 80
+    assert np.abs(ev - evo).max() < _tol(kind) * np.abs(evo).max()
+    np.testing.assert_allclose(res, reso, rtol=1e-5 if kind in "dz" else 5e-2, atol=1e-13 if kind in "dz" else 1e-6)
+    assert np.abs(X - Xo).max() < (1e-8 if kind in "dz" else 5e-3)
+    # svds on a rectangular operator
+    m, n, nsv = 90, 70, 5
+    M = np.asfortranarray(randn(rng, (m, n), dt)); u0 = randn(rng, m, dt)
+    S, sres, U, V, sinfo = sh.svds(sh.op(oracle.Op.dense(M)), m, n, nsv, u0, kdim=40)
+    So, sreso, Uo, Vo, sinfoo = oracle.svds(oracle.Op.dense(M), nsv, u0, kdim=40)
+    sh.close()
+    assert sinfo == sinfoo
+    assert np.abs(S - So).max() < _tol(kind) * So.max()
+    np.testing.assert_allclose(sres, sreso, rtol=1e-5 if kind in "dz" else 5e-2, atol=1e-13 if kind in "dz" else 1e-6)
+    assert np.abs(U - Uo).max() < (1e-8 if kind in "dz" else 5e-3) and np.abs(V - Vo).max() < (1e-8 if kind in "dz" else 5e-3)
+
+
+def test_write_intermediate_side_effect_in_the_shells(mock, oracle, tmp_path):
+    """write_results sorts the residual table in place (IterativeSolvers.fypp:882-924): with the option on, the C++ shells
+    return the same residuals as the oracle restatement of that side effect, write the table files, and keep info / values."""
+    kind, nev = "d", 4
+    rng = np.random.default_rng(26)
+    D = np.diag(np.concatenate([np.linspace(0, 1, N - 4), [2.0, 2.5, 3.0, 4.0]])); Q, _ = np.linalg.qr(rng.standard_normal((N, N)))
+    Ah = Q @ D @ Q.T; Ah = np.asfortranarray((Ah + Ah.T) / 2)
+    x0 = randn(np.random.default_rng(25), N, np.float64)
+    Ag = _toeplitz(N, -0.5, 1.0, 0.5, np.float64)
+    off = Shells(mock, kind); on = Shells(mock, kind, write_intermediate=True)
+    ev0, res0, X0, info0 = off.eighs(off.op(oracle.Op.dense(Ah)), N, nev, x0, kdim=60, tol=1e-6)
+    evg0, resg0, Xg0, infog0 = off.eigs(off.op(oracle.Op.dense(Ag)), N, nev, x0, kdim=16)
+    cwd = os.getcwd()
+    try:
+        os.chdir(tmp_path)
+        ev1, res1, X1, info1 = on.eighs(on.op(oracle.Op.dense(Ah)), N, nev, x0, kdim=60, tol=1e-6)
+        evg1, resg1, Xg1, infog1 = on.eigs(on.op(oracle.Op.dense(Ag)), N, nev, x0, kdim=16)
+        M = np.asfortranarray(randn(rng, (60, 50), np.float64)); u0 = randn(rng, 60, np.float64)
+        S1, sres1, U1, V1, sinfo1 = on.svds(on.op(oracle.Op.dense(M)), 60, 50, 3, u0, kdim=30)
+    finally:
+        os.chdir(cwd)
+    off.close(); on.close()
+    assert info1 == info0 and np.allclose(ev1, ev0, rtol=1e-13) and 4 < info1 < 60
+    assert infog1 == infog0 and np.allclose(evg1, evg0, rtol=1e-13, atol=1e-13)
+    assert np.all(res0 < 1e-6) and np.all(np.diff(res1) <= 0) and res1[-1] > 1e-3
+    _, reso, _, ko = oracle.eighs(oracle.Op.dense(Ah), N, nev, x0, kdim=60, tolerance=1e-6, write_intermediate=True)
+    assert ko == info1
+    np.testing.assert_allclose(res1, reso, rtol=1e-8)
+    _, resgo, _, infogo = oracle.eigs(oracle.Op.dense(Ag), N, nev, x0, kdim=16, write_intermediate=True)
+    assert infogo == infog1
+    np.testing.assert_allclose(resg1, resgo, rtol=1e-6, atol=1e-14)
+    assert not np.allclose(resg1, resg0)                                        # the side effect is visible in eigs as well
+    _, sreso, _, _, sinfoo = oracle.svds(oracle.Op.dense(M), 3, u0, kdim=30, write_intermediate=True)
+    assert sinfoo == sinfo1
+    np.testing.assert_allclose(sres1, sreso, rtol=1e-8, atol=1e-14)
+    lines = open(tmp_path / "eighs_output.txt").read().splitlines()
+    assert len(lines) == info1 + 1 and lines[0].split() == ["Iter", "value", "residual", "conv"]
+    assert open(tmp_path / "eigs_output.txt").read().splitlines()[0].split() == ["Iter", "Re", "Im", "modulus", "residual", "conv"]
+    assert len(open(tmp_path / "svds_output.txt").read().splitlines()) == sinfo1 + 1
+
+
+@pytest.mark.parametrize("kind", ["d", "z", "s"])
+def test_krylov_schur_shell_matches_oracle(mock, oracle, kind):
+    """lkb_krylov_schur (BaseKrylov.fypp:782-834) on a full Arnoldi factorisation: same n, same restarted H and basis."""
+    dt = oracle.DTYPES[kind]; kdim = 32
+    rng = np.random.default_rng(22)
+    Ah = np.asfortranarray((randn(rng, (N, N), dt) / np.sqrt(N)).astype(dt))
+    X = np.zeros((N, kdim + 1), dtype=dt, order="F"); X[:, 0] = randn(rng, N, dt); oracle.normalize(X[:, 0])
+    H = np.zeros((kdim + 1, kdim), dtype=dt, order="F")
+    assert oracle.arnoldi(oracle.Op.dense(Ah), X, H) == 0
+    Xo, Ho = X.copy(order="F"), H.copy(order="F")
+    nko = oracle.krylov_schur(Xo, Ho)
+    sh = Shells(mock, kind)
+    hX = sh.basis(N, kdim + 1, X); Hc = H.copy(order="F"); nk = C.c_int32()
+    sh.check(mock.lkb_krylov_schur(hX, Hc.ctypes.data, kdim + 1, kdim, C.byref(nk)))
+    Xc = sh.get(hX, N, kdim + 1)
+    sh.close()
+    assert nk.value == nko and 0 < nko < kdim
+    tol = 1e-10 if kind in "dz" else 1e-3
+    assert np.abs(Hc - Ho).max() < tol and np.abs(Xc - Xo).max() < tol
+    assert np.abs(Ah @ Xc[:, :nko] - Xc[:, :nko + 1] @ Hc[:nko + 1, :nko]).max() < oracle.RTOL[kind]
