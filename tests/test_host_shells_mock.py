@@ -148,8 +148,10 @@ def test_eigs_shell_matches_oracle_shell(mock, oracle, kind):
     """nev = 8, kdim = 32: Krylov-Schur restarts, the literal extra restart after convergence, stable descending sort --
     same niter, same eigenvalues IN THE SAME ORDER, same residual entries, same Ritz vectors."""
     dt = oracle.DTYPES[kind]; nev = 8
+    # complex kinds: a diagonal ramp breaks the +/- symmetry of the spectrum, so no two Ritz values have (nearly) equal moduli --
+    # the order of near-ties would be decided by rounding noise
     Ah = _toeplitz(N, -0.5, 1.0, 0.5, dt) if kind in "sd" else np.asfortranarray(
-        (_toeplitz(N, -0.5, 1.0, 0.5, dt) + 0.3j * np.diag(np.linspace(-1, 1, N))).astype(dt))
+        (_toeplitz(N, -0.5, 1.0, 0.5, dt) + np.diag((0.2 + 0.3j) * np.linspace(0, 1, N))).astype(dt))
     x0 = randn(np.random.default_rng(21), N, dt)
     sh = Shells(mock, kind)
     ev, res, X, info = sh.eigs(sh.op(oracle.Op.dense(Ah)), N, nev, x0, kdim=4 * nev)
@@ -157,7 +159,8 @@ def test_eigs_shell_matches_oracle_shell(mock, oracle, kind):
     sh.close()
     assert info == infoo and info > 4 * nev
     assert np.abs(ev - evo).max() < _tol(kind) * np.abs(evo).max()              # elementwise: same order
-    np.testing.assert_allclose(res, reso, rtol=1e-6 if kind in "dz" else 5e-2, atol=1e-12 if kind in "dz" else 1e-6)
+    # residuals of converged pairs are tiny numbers with few accurate digits: compared on the scale of the solver tolerance
+    np.testing.assert_allclose(res, reso, rtol=1e-3 if kind in "dz" else 0.3, atol=(1e-3 if kind in "dz" else 0.1) * oracle.RTOL[kind])
     assert _aligned(X, Xo, ev, kind) < (1e-8 if kind in "dz" else 5e-3)
     if kind in "sd":
         assert ev[0].imag > 0 and ev[1] == np.conj(ev[0])                       # a conjugate pair stays (+, -)
@@ -191,7 +194,7 @@ def test_eighs_and_svds_shells_match_oracle_shells(mock, oracle, kind):
     evo, reso, Xo, infoo = oracle.eighs(oracle.Op.dense(Ah), N, nev, x0, kdim=80)
     assert info == infoo and 4 < info < 80
     assert np.abs(ev - evo).max() < _tol(kind) * np.abs(evo).max()
-    np.testing.assert_allclose(res, reso, rtol=1e-5 if kind in "dz" else 5e-2, atol=1e-13 if kind in "dz" else 1e-6)
+    np.testing.assert_allclose(res, reso, rtol=1e-3 if kind in "dz" else 0.3, atol=(1e-3 if kind in "dz" else 0.1) * oracle.RTOL[kind])
     assert np.abs(X - Xo).max() < (1e-8 if kind in "dz" else 5e-3)
     # svds on a rectangular operator
     m, n, nsv = 90, 70, 5
@@ -201,7 +204,7 @@ def test_eighs_and_svds_shells_match_oracle_shells(mock, oracle, kind):
     sh.close()
     assert sinfo == sinfoo
     assert np.abs(S - So).max() < _tol(kind) * So.max()
-    np.testing.assert_allclose(sres, sreso, rtol=1e-5 if kind in "dz" else 5e-2, atol=1e-13 if kind in "dz" else 1e-6)
+    np.testing.assert_allclose(sres, sreso, rtol=1e-3 if kind in "dz" else 0.3, atol=(1e-3 if kind in "dz" else 0.1) * oracle.RTOL[kind])
     assert np.abs(U - Uo).max() < (1e-8 if kind in "dz" else 5e-3) and np.abs(V - Vo).max() < (1e-8 if kind in "dz" else 5e-3)
 
 
