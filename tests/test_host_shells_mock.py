@@ -168,6 +168,27 @@ def test_eigs_shell_matches_oracle_shell(mock, oracle, kind):
         assert ev[0].imag > 0 and ev[1] == np.conj(ev[0])                       # a conjugate pair stays (+, -)
 
 
+def test_eigs_shell_transpose_and_random_start(mock, oracle):
+    """transpose = .true. runs the factorisation on A^H (same spectrum for a real matrix, other Ritz vectors); x0 absent =
+    normalised random start vector (no comparison possible: the shell must converge to the same leading eigenvalues)."""
+    nev = 4
+    rng = np.random.default_rng(30)
+    Ah = np.asfortranarray(np.diag(np.concatenate([np.linspace(0, 1, N - 4), [2.0, 2.5, 3.0, 4.0]])) + 0.05 * rng.standard_normal((N, N)))
+    x0 = randn(rng, N, np.float64)
+    sh = Shells(mock, "d")
+    A = sh.op(oracle.Op.dense(Ah))
+    ev, res, X, info = sh.eigs(A, N, nev, x0, kdim=24, trans=True)
+    evo, reso, Xo, infoo = oracle.eigs(oracle.Op.dense(Ah), N, nev, x0, kdim=24, trans=True)
+    assert info == infoo and np.abs(ev - evo).max() < 1e-10 * np.abs(evo).max()
+    assert np.all(ev.imag == 0) and np.abs(Ah.T @ X - X * ev.real[None, :]).max() < 1e-6      # left eigenvectors: A^T X = X diag(E)
+    # no start vector: lkb_eigs(..., x0 = NULL, ...)
+    Xh = sh.basis(N, nev); evr = np.zeros(2 * nev); resr = np.zeros(nev); infor = C.c_int32()
+    sh.check(mock.lkb_eigs(A, Xh, nev, evr.ctypes.data, resr.ctypes.data, C.byref(infor), None, 24, -1.0, 0))
+    sh.close()
+    lead = np.sort(np.abs(np.linalg.eigvals(Ah)))[::-1][:nev]
+    assert infor.value > 0 and np.abs(np.sort(np.hypot(evr[0::2], evr[1::2]))[::-1] - lead).max() < 1e-6
+
+
 def test_eigs_full_spectrum_default_kdim(mock, oracle):
     """the reference's test_evp_rdp: nev = n, kdim = 4 nev > n; elementwise against the analytic spectrum (pair order)."""
     a, b = 1.0, 0.5
