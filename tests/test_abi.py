@@ -315,3 +315,99 @@ def test_fortran_shim_calls_match_interfaces():
             assert c == nargs, f"{name}: a reference passes {c} arguments, the interface declares {nargs}"
         n_calls += len(counts) - 1
     assert n_calls > 200
+
+
+_F_KEYWORDS = set("""if then else elseif end endif do enddo call return select type class is case default function subroutine result
+contains module use only implicit none external intrinsic integer real complex logical character len kind intent in out inout optional
+target pointer allocatable value import interface procedure pass public private save parameter bind c name allocate deallocate present
+size int cmplx merge max min abs sqrt aimag conjg true false and or not eq ne lt gt le ge error stop source mold stat block associated
+extends abstract generic assignment null trim shape reshape allocated exit cycle while contiguous transfer ubound lbound
+c_loc c_funloc c_associated c_null_ptr c_null_char c_null_funptr c_ptr c_funptr c_int c_int32_t c_int64_t c_double c_float c_char c_f_pointer
+sp dp""".split())
+
+
+def _fortran_undeclared(code):
+    """identifiers used in executable statements that are neither dummies, locals, results, module-level entities, `use`d names
+    nor keywords / intrinsics: [(procedure, identifier, statement)]"""
+    lines = code.splitlines()
+    text = "\n".join(lines)
+    module_level = set(m.lower() for m in re.findall(r"^[ \t]*(?!end\b)(?:[\w()=, ]+ )?(?:function|subroutine)[ \t]+(\w+)", text, flags=re.M | re.I))
+    module_level |= set(m.lower() for m in re.findall(r"^[ \t]*type(?:[ \t]*,[^:\n]*)?[ \t]*::[ \t]*(\w+)", text, flags=re.M | re.I))
+    for m in re.finditer(r"^[ \t]*use[ \t]+[\w, :]*only[ \t]*:(.*)$", text, flags=re.M | re.I):
+        module_level |= set(w.lower() for w in re.findall(r"\w+", m.group(1)))
+    proc_re = re.compile(r"^\s*(?:[\w()=, ]+\s)?(function|subroutine)\s+(\w+)\s*\(([^)]*)\)(?:\s*result\s*\((\w+)\))?", re.I)
+
+    def declared_names(decl_lines):
+        names = set()
+        for b in decl_lines:
+            right = b.split("::", 1)[1]
+            for _ in range(3):
+                right = re.sub(r"\([^()]*\)", "", right)                       # drop dimensions / initialisers' call parentheses
+            for part in right.split(","):
+                nm = part.split("=")[0].strip()
+                if re.fullmatch(r"\w+", nm):
+                    names.add(nm.lower())
+        return names
+
+    # module-level variables / parameters: declarations outside any procedure and outside derived-type definitions
+    depth_proc, in_type, in_iface, mod_decls = 0, False, False, []
+    i, procs = 0, []
+    while i < len(lines):
+        ls = lines[i].strip().lower()
+        if re.match(r"^(abstract\s+)?interface\b", ls):
+            in_iface = True
+        elif ls.startswith("end interface"):
+            in_iface = False
+        m = proc_re.match(lines[i])
+        if m and not ls.startswith("end") and not in_iface:
+            j = i + 1
+            while not re.match(r"^\s*end (function|subroutine)", lines[j], re.I):
+                j += 1
+            procs.append((m, lines[i + 1:j])); i = j + 1
+            continue
+        if re.match(r"^type(\s*,[^:]*)?\s*::\s*\w+$", ls):
+            in_type = True
+        elif ls.startswith("end type"):
+            in_type = False
+        elif "::" in ls and not in_type and not in_iface:
+            mod_decls.append(lines[i])
+        i += 1
+    module_level |= declared_names(mod_decls)
+    assert len(procs) > 150 and {"lkb_ctx", "lkb_magic", "this_module"} <= module_level
+
+    problems = []
+    for m, body in procs:
+        known = {a.strip().lower() for a in m.group(3).split(",") if a.strip()} | {m.group(2).lower()}
+        if m.group(4):
+            known.add(m.group(4).lower())
+        known |= declared_names([b for b in body if "::" in b])
+        for b in body:
+            if "::" in b:
+                continue
+            t = re.sub(r"%\s*\w+", "", b)                                          # component references
+            t = re.sub(r"([(,]\s*)\w+\s*=(?!=)", r"\1", t)                         # keyword arguments
+            t = re.sub(r"(?<![\w.])\d+(\.\d*)?([ed][+-]?\d+)?(_\w+)?", "", t, flags=re.I)   # literals with kind suffixes
+            t = re.sub(r"\.\w+\.", " ", t)                                         # .true. .and. ...
+            for tok in re.findall(r"[A-Za-z_]\w*", t):
+                tl = tok.lower()
+                if tl in _F_KEYWORDS or tl in known or tl in module_level:
+                    continue
+                problems.append((m.group(2), tok, b.strip()[:100]))
+    return problems
+
+
+def test_fortran_shim_identifiers_are_declared():
+    """`implicit none` in a module nobody can compile here: every identifier used in the executable part of a procedure must be a
+    dummy argument, a local declaration, the function result, a module-level entity (procedure, type, parameter, variable, bind(C)
+    interface), a name imported by `use ..., only:`, or a Fortran keyword / intrinsic.  Catches typos and forgotten declarations;
+    the checker itself is checked on a copy with one local declaration removed and on one with a misspelt call."""
+    import subprocess, sys
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "fortran", "gen_shim.py")], stdout=subprocess.DEVNULL)
+    code = re.sub(r"'[^']*'", "''", _shim_code_without_comments())
+    assert _fortran_undeclared(code) == []
+    victim = "        integer(c_int32_t) :: kd, tr, cinfo\n"
+    assert victim in code
+    bad = _fortran_undeclared(code.replace(victim, "        integer(c_int32_t) :: kd, cinfo\n", 1))
+    assert bad and all(p[1] == "tr" for p in bad)
+    bad = _fortran_undeclared(code.replace("call chk(lkb_vec_zero(", "call chk(lkb_vec_zer0(", 1))
+    assert [p[1] for p in bad] == ["lkb_vec_zer0"]
