@@ -381,6 +381,14 @@ def _fortran_undeclared(code):
         if m.group(4):
             known.add(m.group(4).lower())
         known |= declared_names([b for b in body if "::" in b])
+        # Fortran is case-insensitive: a local that differs from a dummy (or another local) only by case is a duplicate declaration
+        seen = {}
+        for b in body:
+            if "::" in b:
+                for nm in declared_names([b]):
+                    if nm in seen:
+                        problems.append((m.group(2), nm, "declared twice: `%s` and `%s`" % (seen[nm].strip()[:60], b.strip()[:60])))
+                    seen[nm] = b
         for b in body:
             if "::" in b:
                 continue
@@ -411,3 +419,79 @@ def test_fortran_shim_identifiers_are_declared():
     assert bad and all(p[1] == "tr" for p in bad)
     bad = _fortran_undeclared(code.replace("call chk(lkb_vec_zero(", "call chk(lkb_vec_zer0(", 1))
     assert [p[1] for p in bad] == ["lkb_vec_zer0"]
+
+
+REFERENCE = "/root/reference/src"
+_REF_ROUTINES = {          # try-function -> (reference file, reference routine)
+    "arnoldi": ("Krylov/BaseKrylov.fypp", "arnoldi"), "lanczos": ("Krylov/BaseKrylov.fypp", "lanczos_tridiagonalization"),
+    "bidiagonalization": ("Krylov/BaseKrylov.fypp", "lanczos_bidiagonalization"), "qr": ("Krylov/BaseKrylov.fypp", "qr_no_pivoting"),
+    "qr_pivoting": ("Krylov/BaseKrylov.fypp", "qr_with_pivoting"),
+    "orthogonalize_vector": ("Krylov/BaseKrylov.fypp", "orthogonalize_vector_against_basis"),
+    "orthogonalize_basis": ("Krylov/BaseKrylov.fypp", "orthogonalize_basis_against_basis"),
+    "dgs_vector": ("Krylov/BaseKrylov.fypp", "DGS_vector_against_basis"), "dgs_basis": ("Krylov/BaseKrylov.fypp", "DGS_basis_against_basis"),
+    "gmres": ("IterativeSolvers/IterativeSolvers.fypp", "gmres"), "fgmres": ("IterativeSolvers/IterativeSolvers.fypp", "fgmres"),
+    "cg": ("IterativeSolvers/IterativeSolvers.fypp", "cg"), "eigs": ("IterativeSolvers/IterativeSolvers.fypp", "eigs"),
+    "eighs": ("IterativeSolvers/IterativeSolvers.fypp", "eighs"), "svds": ("IterativeSolvers/IterativeSolvers.fypp", "svds"),
+    "kexpm_vec": ("Expm/ExpmLib.fypp", "kexpm_vec"), "kexpm_mat": ("Expm/ExpmLib.fypp", "kexpm_mat"),
+    "krylov_exptA": ("Expm/ExpmLib.fypp", "krylov_exptA"),
+}
+
+
+def _dummy_attributes(header_and_body, names):
+    """{dummy: (base type keyword, optional?, rank)} from the declaration lines of a procedure"""
+    out = {}
+    for ln in header_and_body:
+        if "::" not in ln:
+            continue
+        left, right = ln.split("::", 1)
+        left = left.strip().lower()
+        base = re.match(r"[a-z]+", left).group(0)
+        for _ in range(3):
+            right_flat = re.sub(r"\([^()]*\)", lambda m: "(" + ":" * (m.group(0).count(",") + 1) + ")" if ":" in m.group(0) or "size" in m.group(0).lower() else "", right)
+            right = right_flat
+        for part in re.split(r",(?![^()]*\))", right):
+            nm = re.match(r"\s*(\w+)", part)
+            if nm and nm.group(1).lower() in names:
+                rank = part.count(":") if "(" in part else (left.count(":") if "dimension" in left else 0)
+                out[nm.group(1).lower()] = (base, "optional" in left, rank)
+    return out
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="the reference tree is only present in the build container")
+def test_fortran_shim_matches_the_reference_signatures():
+    """Drop-in check against the reference's own sources (read here only; neither the GPU tests nor the bench touch them): every
+    `lkb_try_<routine>_<kind>` has the reference routine's dummy arguments -- same names, same order (Fortran is case-insensitive)
+    -- and every dummy agrees in base type (class / real / complex / integer / logical), optional-ness and rank."""
+    import subprocess, sys
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "fortran", "gen_shim.py")], stdout=subprocess.DEVNULL)
+    code = _shim_code_without_comments().splitlines()
+    checked = 0
+    for fn, (rel, routine) in _REF_ROUTINES.items():
+        ref = open(os.path.join(REFERENCE, rel)).read().splitlines()
+        pat = re.compile(r"^\s*(?:module\s+)?subroutine\s+" + routine + r"_\$\{type\[0\]\}\$\$\{kind\}\$\s*\(([^)]*)\)", re.I)
+        hits = [(i, pat.match(ln)) for i, ln in enumerate(ref) if pat.match(ln)]
+        assert hits, routine
+        i0, m = hits[0]
+        ref_args = [a.strip().lower() for a in m.group(1).split(",")]
+        j = i0 + 1
+        while not re.match(r"^\s*end\s+subroutine", ref[j], re.I) and j < i0 + 80:
+            j += 1
+        ref_body = [re.sub(r"\$\{type\}\$", "real(dp)", re.sub(r"\$\{type\[0\]\}\$\$\{kind\}\$", "rdp", re.sub(r"\$\{kind\}\$", "dp", ln.split("!")[0])))
+                    for ln in ref[i0 + 1:j]]
+        ref_attr = _dummy_attributes(ref_body, set(ref_args))
+        assert set(ref_attr) == set(ref_args), (routine, sorted(set(ref_args) - set(ref_attr)))
+        # the shim's function for rdp
+        spat = re.compile(r"^\s*logical function lkb_try_" + fn + r"_rdp\(([^)]*)\) result\(done\)", re.I)
+        shits = [(i, spat.match(ln)) for i, ln in enumerate(code) if spat.match(ln)]
+        assert shits, fn
+        s0, sm = shits[0]
+        shim_args = [a.strip().lower() for a in sm.group(1).split(",")]
+        assert shim_args == ref_args, (fn, shim_args, ref_args)
+        k = s0 + 1
+        while not re.match(r"^\s*end function", code[k], re.I):
+            k += 1
+        shim_attr = _dummy_attributes(code[s0 + 1:k], set(shim_args))
+        for a in ref_args:
+            assert shim_attr[a] == ref_attr[a], (fn, a, shim_attr[a], ref_attr[a])
+            checked += 1
+    assert checked > 100
