@@ -495,3 +495,59 @@ def test_fortran_shim_matches_the_reference_signatures():
             assert shim_attr[a] == ref_attr[a], (fn, a, shim_attr[a], ref_attr[a])
             checked += 1
     assert checked > 100
+
+
+_REF_TBPS = {   # shim procedure (rdp instance) -> (reference file, abstract interface the deferred binding must conform to)
+    "cuda_zero": ("AbstractTypes/AbstractVectors.fypp", "abstract_zero"), "cuda_rand": ("AbstractTypes/AbstractVectors.fypp", "abstract_rand"),
+    "cuda_scal": ("AbstractTypes/AbstractVectors.fypp", "abstract_scal"), "cuda_axpby": ("AbstractTypes/AbstractVectors.fypp", "abstract_axpby"),
+    "cuda_dot": ("AbstractTypes/AbstractVectors.fypp", "abstract_dot"), "cuda_get_size": ("AbstractTypes/AbstractVectors.fypp", "abstract_get_size"),
+    "cuda_matvec": ("AbstractTypes/AbstractLinops.fypp", "abstract_matvec"), "cuda_rmatvec": ("AbstractTypes/AbstractLinops.fypp", "abstract_matvec"),
+    "cuda_sym_matvec": ("AbstractTypes/AbstractLinops.fypp", "abstract_sym_matvec"),
+}
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="the reference tree is only present in the build container")
+def test_fortran_shim_type_bound_procedures_conform():
+    """The deferred bindings of abstract_vector_* / abstract_linop_* / abstract_sym_linop_* (AbstractVectors.fypp:295-381,
+    AbstractLinops.fypp:58-87, 204-256): an overriding procedure must have the abstract interface's dummy arguments -- same names,
+    order, base type, optional-ness, rank, and the same intent except for the passed object's class."""
+    import subprocess, sys
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "fortran", "gen_shim.py")], stdout=subprocess.DEVNULL)
+    code = _shim_code_without_comments().splitlines()
+
+    def intents(body, names):
+        out = {}
+        for ln in body:
+            if "::" in ln:
+                left, right = ln.split("::", 1)
+                m = re.search(r"intent\s*\(\s*(\w+)\s*\)", left, re.I)
+                for nm in re.findall(r"\w+", re.sub(r"\([^()]*\)", "", right)):
+                    if nm.lower() in names:
+                        out[nm.lower()] = m.group(1).lower() if m else None
+        return out
+
+    checked = 0
+    for proc, (rel, iface) in _REF_TBPS.items():
+        ref = open(os.path.join(REFERENCE, rel)).read().splitlines()
+        pat = re.compile(r"^\s*(?:subroutine|function)\s+" + iface + r"_\$\{type\[0\]\}\$\$\{kind\}\$\s*\(([^)]*)\)", re.I)
+        i0, m = [(i, pat.match(ln)) for i, ln in enumerate(ref) if pat.match(ln)][0]
+        ref_args = [a.strip().lower() for a in m.group(1).split(",")]
+        j = i0 + 1
+        while not re.match(r"^\s*end\s+(subroutine|function)", ref[j], re.I):
+            j += 1
+        ref_body = [re.sub(r"\$\{type\}\$", "real(dp)", re.sub(r"\$\{type\[0\]\}\$\$\{kind\}\$", "rdp", re.sub(r"\$\{kind\}\$", "dp", ln.split("!")[0])))
+                    for ln in ref[i0 + 1:j]]
+        spat = re.compile(r"^\s*(?:[\w()]+\s+)?(?:subroutine|function)\s+" + proc + r"_rdp\s*\(([^)]*)\)", re.I)
+        s0, sm = [(i, spat.match(ln)) for i, ln in enumerate(code) if spat.match(ln)][0]
+        shim_args = [a.strip().lower() for a in sm.group(1).split(",")]
+        assert shim_args == ref_args, (proc, shim_args, ref_args)
+        k = s0 + 1
+        while not re.match(r"^\s*end (subroutine|function)", code[k], re.I):
+            k += 1
+        ra, sa = _dummy_attributes(ref_body, set(ref_args)), _dummy_attributes(code[s0 + 1:k], set(shim_args))
+        ri, si = intents(ref_body, set(ref_args)), intents(code[s0 + 1:k], set(shim_args))
+        for a in ref_args:
+            assert sa[a] == ra[a], (proc, a, sa[a], ra[a])
+            assert si[a] == ri[a], (proc, a, "intent", si[a], ri[a])
+            checked += 1
+    assert checked >= 20
