@@ -36,40 +36,11 @@ static cudaError_t mock_memcpy2d(void* dst, size_t dpitch, const void* src, size
 
 #include "lkb_eig.cu"        // the product's host shells, verbatim
 
-// ---- the C oracle (oracle/lk_oracle.c): one Krylov step at a time -----------------------------------------------------------
-extern "C" {
-#define ORACLE_DECL(sfx, R)                                                                                                   \
-    int lko_arnoldi_##sfx(void* A, int64_t n, void* X, int64_t ldx, void* H, int ldh, int kdim, int kstart, int kend, R tol,   \
-                          int trans, int p, uint64_t* seed);                                                                  \
-    int lko_lanczos_##sfx(void* A, int64_t n, void* X, int64_t ldx, void* T, int ldt, int kdim, int kstart, int kend, R tol);   \
-    int lko_bidiag_##sfx(void* A, int64_t m, int64_t n, void* U, int64_t ldu, void* V, int64_t ldv, void* B, int ldb, int kdim, \
-                         int kstart, int kend, R tol);                                                                        \
-    void lko_fill_##sfx(int64_t n, void* x, int dist, uint64_t seed, int64_t row0);
-ORACLE_DECL(s, float) ORACLE_DECL(d, double) ORACLE_DECL(c, float) ORACLE_DECL(z, double)
-#undef ORACLE_DECL
-}
+#include "host_mock_common.inc"
 
 namespace {
-char g_err[512] = "";
 std::vector<char> g_col;          // the H / T / B column of the step enqueued last (one step is in flight at a time)
 int g_info = 0;
-uint64_t g_oracle_seed = 1000;
-uint64_t g_uid = 0;
-
-template <typename F> void dispatch(int kind, F f) {
-    switch (kind) {
-        case KS: f((float*)nullptr); break;
-        case KD: f((double*)nullptr); break;
-        case KC: f((std::complex<float>*)nullptr); break;
-        default: f((std::complex<double>*)nullptr); break;
-    }
-}
-template <typename E> E mk_elem(Scalar s);
-template <> float mk_elem<float>(Scalar s) { return (float)s.re; }
-template <> double mk_elem<double>(Scalar s) { return s.re; }
-template <> std::complex<float> mk_elem<std::complex<float>>(Scalar s) { return {(float)s.re, (float)s.im}; }
-template <> std::complex<double> mk_elem<std::complex<double>>(Scalar s) { return {s.re, s.im}; }
-
 void stash_column(const void* H, int ldh, int col, size_t es) {
     g_col.assign((size_t)ldh * es, 0);
     memcpy(g_col.data(), (const char*)H + (size_t)ldh * col * es, (size_t)ldh * es);
@@ -78,58 +49,6 @@ void stash_column(const void* H, int ldh, int col, size_t es) {
 
 namespace lkb {
 
-void set_error(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap); }
-int bcast_host(lkb_ctx_s*, void*, size_t) { return 0; }
-void prof_begin(lkb_ctx_s*, int) {}
-void prof_end(lkb_ctx_s*, int, int) {}
-int check_launch(lkb_ctx_s*, const char*) { return 0; }
-uint64_t next_seed(lkb_ctx_s* c) { return c->seed + 0x9E3779B97F4A7C15ULL * (++c->seed_calls); }
-int dev_alloc(lkb_ctx_s*, void** p, size_t bytes) { *p = calloc(1, bytes ? bytes : 16); return *p ? 0 : LKB_ERR_ALLOC; }
-void dev_free(lkb_ctx_s*, void* p) { free(p); }
-int ensure_hstage(lkb_ctx_s* c, size_t bytes) {
-    if (c->hstage_bytes >= bytes) return 0;
-    free(c->hstage); c->hstage = calloc(1, bytes); c->hstage_bytes = bytes;
-    return 0;
-}
-int ensure_coefd(lkb_ctx_s* c, size_t bytes) {
-    if (c->coefd_bytes >= bytes) return 0;
-    free(c->coefd); c->coefd = calloc(1, bytes); c->coefd_bytes = bytes;
-    return 0;
-}
-
-void launch_fill(int kind, cudaStream_t, void* x, int64_t n, int64_t row0, int dist, uint64_t seed, int) {
-    switch (kind) {
-        case KS: lko_fill_s(n, x, dist, seed, row0); break;
-        case KD: lko_fill_d(n, x, dist, seed, row0); break;
-        case KC: lko_fill_c(n, x, dist, seed, row0); break;
-        default: lko_fill_z(n, x, dist, seed, row0); break;
-    }
-}
-void launch_scal(int kind, cudaStream_t, Scalar alpha, void* x, int64_t n, int) {
-    dispatch(kind, [&](auto* tag) {
-        typedef typename std::remove_pointer<decltype(tag)>::type E;
-        const E a = mk_elem<E>(alpha); E* v = (E*)x;
-        for (int64_t i = 0; i < n; ++i) v[i] = a * v[i];
-    });
-}
-void launch_axpby(int kind, cudaStream_t, Scalar alpha, const void* x, Scalar beta, void* y, int64_t n, int) {
-    dispatch(kind, [&](auto* tag) {
-        typedef typename std::remove_pointer<decltype(tag)>::type E;
-        const E a = mk_elem<E>(alpha), b = mk_elem<E>(beta); const E* u = (const E*)x; E* v = (E*)y;
-        const bool overwrite = (beta.re == 0.0 && beta.im == 0.0);                 // beta == 0: y is not read (copy)
-        for (int64_t i = 0; i < n; ++i) v[i] = overwrite ? a * u[i] : a * u[i] + b * v[i];
-    });
-}
-int vec_norm_sync(lkb_ctx_s*, int kind, const void* w, int64_t n, double* out) {
-    double s = 0.0;
-    dispatch(kind, [&](auto* tag) {
-        typedef typename std::remove_pointer<decltype(tag)>::type E;
-        const E* v = (const E*)w;
-        for (int64_t i = 0; i < n; ++i) s += std::norm(std::complex<double>(v[i]));
-    });
-    *out = sqrt(s);
-    return 0;
-}
 // Y(:, q) = sum_i X(:, i) Z(i, q)
 void launch_basis_gemm(int kind, cudaStream_t, const void* X, int64_t ldx, int k, const void* Z, int ldz, int p, void* Y, int64_t ldy,
                        int64_t n, int) {
@@ -216,45 +135,3 @@ int bidiag_collect(lkb_op_s* A, lkb_basis_s* U, void* B, int ldb, int32_t* info,
 }
 
 }  // namespace lkb
-
-// ---- the few C-ABI entry points lkb_eig.cu calls, on host memory ------------------------------------------------------------------
-extern "C" {
-
-int lkb_basis_create(lkb_ctx_t c, int kind, int64_t n_local, int64_t n_global, int64_t row0, int ncols, lkb_basis_t* b) {
-    const int64_t ld = std::max<int64_t>(n_local, 1);
-    lkb_basis_s* h = new lkb_basis_s{c, kind, n_local, n_global, row0, ld, ncols, nullptr, ++g_uid};
-    h->d = calloc((size_t)ld * ncols, kind_size(kind));
-    *b = h;
-    return 0;
-}
-int lkb_basis_destroy(lkb_basis_t b) { if (!b) return LKB_ERR_ARG; if (b->owns) free(b->d); delete b; return 0; }
-int lkb_basis_zero(lkb_basis_t b, int col0, int ncols) {
-    if (col0 < 0 || col0 + ncols > b->ncols) return LKB_ERR_ARG;
-    memset(col_ptr(b, col0), 0, (size_t)b->ld * ncols * kind_size(b->kind));
-    return 0;
-}
-int lkb_sync(lkb_ctx_t) { return 0; }
-
-// ---- harness API for tests/test_host_shells_mock.py ---------------------------------------------------------------------------------
-const char* mock_last_error(void) { return g_err; }
-void* mock_ctx_new(int write_intermediate) { lkb_ctx_s* c = new lkb_ctx_s(); c->write_intermediate = write_intermediate != 0; return c; }
-void mock_ctx_free(void* c) { lkb_ctx_s* x = (lkb_ctx_s*)c; free(x->hstage); free(x->coefd); delete x; }
-// operator = a pointer to the oracle's lko_op struct of the same kind (kept alive by the caller)
-void* mock_op_new(void* ctx, int kind, int64_t m, int64_t n, void* oracle_op) {
-    lkb_op_s* A = new lkb_op_s();
-    A->ctx = (lkb_ctx_s*)ctx; A->type = 9; A->kind = kind; A->m = m; A->n = n; A->user = oracle_op;
-    return A;
-}
-void mock_op_free(void* A) { delete (lkb_op_s*)A; }
-void* mock_vec_new(void* ctx, int kind, int64_t n, const void* host) {
-    lkb_vec_s* v = new lkb_vec_s{(lkb_ctx_s*)ctx, kind, n, n, 0, nullptr, true};
-    v->d = malloc((size_t)std::max<int64_t>(n, 1) * kind_size(kind));
-    memcpy(v->d, host, (size_t)n * kind_size(kind));
-    return v;
-}
-void mock_vec_free(void* v) { free(((lkb_vec_s*)v)->d); delete (lkb_vec_s*)v; }
-void mock_basis_get(void* b, void* host) { lkb_basis_s* B = (lkb_basis_s*)b; memcpy(host, B->d, (size_t)B->ld * B->ncols * kind_size(B->kind)); }
-void mock_basis_put(void* b, const void* host) { lkb_basis_s* B = (lkb_basis_s*)b; memcpy(B->d, host, (size_t)B->ld * B->ncols * kind_size(B->kind)); }
-void mock_set_oracle_seed(uint64_t s) { g_oracle_seed = s; }
-
-}  // extern "C"

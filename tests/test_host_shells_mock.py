@@ -290,3 +290,142 @@ def test_krylov_schur_shell_matches_oracle(mock, oracle, kind):
     tol = 1e-10 if kind in "dz" else 1e-3
     assert np.abs(Hc - Ho).max() < tol and np.abs(Xc - Xo).max() < tol
     assert np.abs(Ah @ Xc[:, :nko] - Xc[:, :nko + 1] @ Hc[:nko + 1, :nko]).max() < oracle.RTOL[kind]
+
+
+# ---- the Krylov-exponential shells (lkb_expm.cu) on the mocked device ------------------------------------------------------------------
+_QR_CB = C.CFUNCTYPE(C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.c_double,
+                     C.POINTER(C.c_int32))
+
+
+@pytest.fixture(scope="module")
+def expm_mock(tmp_path_factory, oracle):
+    import __graft_entry__
+    __graft_entry__.build()
+    out = str(tmp_path_factory.mktemp("expm_mock") / "libhost_expm_mock.so")
+    nvcc = NVCC if os.path.exists(NVCC) else shutil.which("nvcc")
+    odir = os.path.join(ROOT, "oracle")
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O1", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
+                           "-diag-suppress", "174", "-I", CSRC, os.path.join(ROOT, "tests", "host_expm_mock.cu"), "-o", out,
+                           "-L", odir, "-llk_oracle", "-ldl", "-Xlinker", "-rpath=" + odir, "-Xlinker", "-Bsymbolic"],
+                          stderr=subprocess.DEVNULL)
+    lib = C.CDLL(out)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    lib.mock_ctx_new.restype = vp; lib.mock_ctx_new.argtypes = [C.c_int]
+    lib.mock_ctx_free.argtypes = [vp]
+    lib.mock_op_new.restype = vp; lib.mock_op_new.argtypes = [vp, C.c_int, i64, i64, vp]
+    lib.mock_vec_new.restype = vp; lib.mock_vec_new.argtypes = [vp, C.c_int, i64, vp]
+    lib.mock_basis_get.argtypes = [vp, vp]; lib.mock_basis_put.argtypes = [vp, vp]
+    lib.mock_last_error.restype = C.c_char_p
+    lib.lkb_basis_create.argtypes = [vp, C.c_int, i64, i64, i64, C.c_int, C.POINTER(vp)]
+    lib.lkb_kexpm_vec.argtypes = [vp, vp, vp, dbl, dbl, C.POINTER(i32), i32, i32]
+    lib.lkb_kexpm_mat.argtypes = [vp, vp, vp, C.c_int, dbl, dbl, C.POINTER(i32), i32, i32]
+    lib.lkb_krylov_expta.argtypes = [vp, vp, vp, dbl, C.POINTER(i32), i32]
+    dts = {0: np.float32, 1: np.float64, 2: np.complex64, 3: np.complex128}
+
+    def qr_pivoting(kind, n, p, Qp, ld, Rp, ldr, permp, tol, infop):          # lkb_qr_pivoting -> oracle.qr_with_pivoting, in place
+        dt = np.dtype(dts[kind])
+        assert ld == n
+        Q = np.frombuffer((C.c_char * (n * p * dt.itemsize)).from_address(Qp), dtype=dt).reshape((n, p), order="F")
+        info, R, perm = oracle.qr_with_pivoting(Q, tol=None if tol < 0 else tol)
+        Rout = np.frombuffer((C.c_char * (ldr * p * dt.itemsize)).from_address(Rp), dtype=dt).reshape((ldr, p), order="F")
+        Rout[:p, :p] = R
+        for i in range(p):
+            permp[i] = int(perm[i]) + 1
+        infop[0] = info
+        return 0
+
+    lib._cb = _QR_CB(qr_pivoting)                                              # keep the trampoline alive
+    lib.mock_set_qr_pivoting.argtypes = [_QR_CB]
+    lib.mock_set_qr_pivoting(lib._cb)
+    return lib
+
+
+class ExpmShells(Shells):
+    def kexpm(self, A, b, tau, tol, trans=False, kdim=0):
+        n = b.size
+        c = self.vec(np.zeros(n, dtype=self.dt)); info = C.c_int32()
+        self.check(self.lib.lkb_kexpm_vec(c, A, self.vec(b), tau, tol, C.byref(info), int(trans), kdim))
+        return self._vec_get(c, n), info.value
+
+    def exptA(self, A, b, tau, trans=False):
+        n = b.size
+        c = self.vec(np.zeros(n, dtype=self.dt)); info = C.c_int32()
+        self.check(self.lib.lkb_krylov_expta(c, A, self.vec(b), tau, C.byref(info), int(trans)))
+        return self._vec_get(c, n), info.value
+
+    def kexpm_mat(self, A, B, tau, tol, trans=False, kdim=0):
+        n, p = B.shape
+        hB = self.basis(n, p, B); hC = self.basis(n, p); info = C.c_int32()
+        self.check(self.lib.lkb_kexpm_mat(hC, A, hB, p, tau, tol, C.byref(info), int(trans), kdim))
+        return self.get(hC, n, p), info.value
+
+    def _vec_get(self, v, n):
+        # lkb_vec_s { ctx, kind, n, n_global, row0, d, owns }: the data pointer is the 6th 8-byte field
+        d = C.cast(v, C.POINTER(C.c_void_p))[5]
+        return np.frombuffer((C.c_char * (n * np.dtype(self.dt).itemsize)).from_address(d), dtype=self.dt).copy()
+
+
+@pytest.mark.parametrize("kind", ["d", "z", "s", "c"])
+def test_kexpm_vec_shell_matches_oracle_shell(expm_mock, oracle, kind):
+    """lkb_kexpm_vec / lkb_krylov_expta (ExpmLib.fypp:128-232, 364-392) on the mocked device vs oracle.kexpm_vec: same info (dimension
+    used), same vector -- incl. the literal behaviour on Arnoldi breakdown (info = k + 2) and the zero input."""
+    dt = oracle.DTYPES[kind]; dims = (24, 20); n = 480
+    Ao = oracle.Op.stencil(kind, dims, (-4.0, 1.0, 0.8, 1.0, 1.2))
+    b = oracle.fill(n, kind, "uniform", 3)
+    tol = 1e-10 if kind in "dz" else 1e-5
+    sh = ExpmShells(expm_mock, kind)
+    A = sh.op(Ao)
+    c, info = sh.kexpm(A, b, 0.1, tol)
+    co, infoo = oracle.kexpm_vec(Ao, b, 0.1, tol)
+    assert info == infoo and info > 1
+    assert np.linalg.norm(c - co) < (1e-12 if kind in "dz" else 1e-5) * np.linalg.norm(co)
+    ct, tinfo = sh.kexpm(A, b, 0.1, tol, trans=True)
+    cto, tinfoo = oracle.kexpm_vec(Ao, b, 0.1, tol, trans=True)
+    assert tinfo == tinfoo and np.linalg.norm(ct - cto) < (1e-12 if kind in "dz" else 1e-5) * np.linalg.norm(cto)
+    ce, einfo = sh.exptA(A, b, 0.1)
+    ceo, einfoo = oracle.kexpm_vec(Ao, b, 0.1, oracle.ATOL[kind], kdim=30)
+    assert einfo == einfoo and np.linalg.norm(ce - ceo) < (1e-12 if kind in "dz" else 1e-5) * np.linalg.norm(ceo)
+    z, zinfo = sh.kexpm(A, np.zeros(n, dtype=dt), 0.1, tol)
+    assert zinfo == 1 and not z.any()
+    if kind in "dz":                                                            # breakdown: 3-dimensional invariant subspace
+        m = 96
+        D = np.asfortranarray(np.diag(np.arange(1, m + 1)).astype(dt))
+        b3 = np.zeros(m, dtype=dt); b3[:3] = [1.0, 2.0, -1.5]
+        c3, i3 = sh.kexpm(sh.op(oracle.Op.dense(D)), b3, 0.2, 1e-12)
+        exact = np.exp(0.2 * np.arange(1, m + 1)) * b3
+        assert i3 == 5 == oracle.kexpm_vec(oracle.Op.dense(D), b3, 0.2, 1e-12)[1]
+        assert np.linalg.norm(c3 - exact) < 1e-12 * np.linalg.norm(exact)
+    sh.close()
+
+
+@pytest.mark.parametrize("kind", ["d", "z", "s"])
+@pytest.mark.parametrize("p", [1, 3])
+def test_kexpm_mat_shell_matches_oracle_shell(expm_mock, oracle, kind, p):
+    """lkb_kexpm_mat (ExpmLib.fypp:234-362) on the mocked device vs oracle.kexpm_mat: same info, same block; the work basis grows
+    on demand (info = 30 for p = 3 means 9 block steps > the initial room for 8); transpose; zero input; breakdown exit."""
+    dt = oracle.DTYPES[kind]; dims = (24, 20); n = 480
+    Ao = oracle.Op.stencil(kind, dims, (-4.0, 1.0, 0.8, 1.0, 1.2))
+    B = np.asfortranarray(np.stack([oracle.fill(n, kind, "uniform", 5 + i) for i in range(p)], axis=1))
+    tol = 1e-10 if kind in "dz" else 1e-5
+    sh = ExpmShells(expm_mock, kind)
+    A = sh.op(Ao)
+    Cm, info = sh.kexpm_mat(A, B, 0.1, tol, kdim=15)
+    Co, infoo = oracle.kexpm_mat(Ao, B, 0.1, tol, kdim=15)
+    assert info == infoo and info >= 2 * p
+    if kind in "dz":
+        assert info // p - 1 > 8                                                # the growth path was taken
+    assert np.linalg.norm(Cm - Co) < (1e-11 if kind in "dz" else 1e-4) * np.linalg.norm(Co)
+    Ct, tinfo = sh.kexpm_mat(A, B, 0.1, tol, trans=True, kdim=15)
+    Cto, tinfoo = oracle.kexpm_mat(Ao, B, 0.1, tol, trans=True, kdim=15)
+    assert tinfo == tinfoo and np.linalg.norm(Ct - Cto) < (1e-11 if kind in "dz" else 1e-4) * np.linalg.norm(Cto)
+    Z, zinfo = sh.kexpm_mat(A, np.zeros_like(B), 0.1, tol, kdim=15)
+    assert zinfo == p and not Z.any()
+    if kind == "d" and p == 3:                                                  # breakdown: p = 2 columns in a 4-dimensional invariant subspace
+        m = 96
+        D = np.asfortranarray(np.diag(np.arange(1, m + 1)).astype(dt))
+        Bh = np.zeros((m, 2), order="F"); Bh[:4, 0] = [1.0, 2.0, -1.5, 0.5]; Bh[:4, 1] = [0.3, -1.0, 2.0, 1.0]
+        Cb, binfo = sh.kexpm_mat(sh.op(oracle.Op.dense(D)), Bh, 0.2, 1e-12)
+        exact = np.exp(0.2 * np.arange(1, m + 1))[:, None] * Bh
+        assert binfo == 4 == oracle.kexpm_mat(oracle.Op.dense(D), Bh, 0.2, 1e-12)[1]
+        assert np.linalg.norm(Cb - exact) < 1e-12 * np.linalg.norm(exact)
+    sh.close()
