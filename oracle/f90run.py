@@ -537,6 +537,7 @@ class Proc:
         self.result_ts = None
         self.elemental = "elemental" in prefixes
         self.file = None
+        self.internals = {}           # internal procedure name -> global (mangled) name
 
     def dummy(self, name):
         return self.decls.get(name)
@@ -738,7 +739,7 @@ class Program:
             target = e[2][1] if len(e) >= 3 and e[1] == ("op", "=>") else (None if deferred else bname)
             td.bindings[bname] = (target, passname, deferred, nopass)
 
-    def _parse_proc(self, lines, i, module, interface_only):
+    def _parse_proc(self, lines, i, module, interface_only, host=None):
         no, s = lines[i]
         toks = tokenize(s)
         names = [t[1] for t in toks if t[0] == "name"]
@@ -766,6 +767,9 @@ class Program:
                 if j < len(toks) and toks[j] == ("name", "result"):
                     inner, j = _paren_group(toks, j + 1)
                     result = inner[0][1]
+        if host is not None:
+            host.internals[name] = host.name + "::" + name
+            name = host.name + "::" + name
         proc = Proc(name, kind, args, result, prefixes, module)
         proc.result_ts = result_ts
         proc.file = self._file
@@ -839,7 +843,15 @@ class Program:
             if t0 in ("use", "implicit", "import", "external", "intrinsic", "save"):
                 continue
             if t0 == "contains":
-                raise FortranError(f"{self._file}:{no}: internal procedures are not supported")
+                # internal procedures: registered as "<host>::<name>"; host association is NOT provided (they may only use
+                # their own dummies / locals and module entities -- enough for the selector functions the reference passes around)
+                while True:
+                    no2, s2 = lines[i]
+                    low2 = re.sub(r"\s+", " ", s2.lower())
+                    if re.match(r"^end ?(subroutine|function|procedure)\b", low2) or low2 == "end":
+                        self._term = ("end_proc", tokenize(s2), s2)
+                        return stmts, i + 1
+                    i = self._parse_proc(lines, i, proc.module, interface_only=False, host=proc)
             if t0 in _TYPE_KW and _find_top(toks, "::") >= 0 and not (t0 == "type" and toks[1] != ("op", "(")):
                 ds = parse_declaration(toks, s)
                 for d in ds:
@@ -1195,6 +1207,8 @@ class Interp:
             return e[1]
         if k == "name":
             nm = e[1]
+            if sc.proc is not None and nm in sc.proc.internals and nm not in sc.vars:
+                return ("procref", sc.proc.internals[nm])
             if not self.has_var(nm, sc) and (nm in self.p.procs or nm in self.natives or nm in self.p.generics):
                 return ("procref", nm)                  # procedure passed as an actual argument
             return self.lookup(nm, sc)
@@ -1542,6 +1556,8 @@ class Interp:
         return out
 
     def call_named(self, nm, args, sc, want_result):
+        if sc.proc is not None and nm in sc.proc.internals:
+            nm = sc.proc.internals[nm]
         if nm == "present":
             return self.ev(args[0][1], sc) is not ABSENT
         if nm == "allocated":
