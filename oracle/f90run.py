@@ -2291,6 +2291,23 @@ def _n_random_number(interp, x):
     return ("__out__", {0: rng.random()})
 
 
+def _n_hermitian(interp, a):
+    return np.asfortranarray(np.conj(a).T)
+
+
+def _n_normal(interp, loc, scale):
+    """stdlib_stats_distribution_normal rvs_normal(loc, scale): only used to (re)fill vectors with random numbers, so the
+    stream is implementation-defined anyway (seeded numpy generator interp.rng)"""
+    rng = interp.rng
+    shape = np.shape(loc)
+    dt = np.asarray(loc).dtype
+    if np.issubdtype(dt, np.complexfloating):
+        r = np.real(loc) + np.real(scale) * rng.standard_normal(shape) + 1j * (np.imag(loc) + np.imag(scale) * rng.standard_normal(shape))
+    else:
+        r = loc + scale * rng.standard_normal(shape)
+    return np.asarray(r, dtype=dt) if shape else dt.type(r)
+
+
 def _n_type_error(interp, *a, **k):
     raise StopError(f"type_error{a}")
 
@@ -2305,5 +2322,5 @@ NATIVES = {
     # fortran-stdlib
     "optval": _n_optval, "eye": _n_eye, "mnorm": _n_mnorm, "norm": _n_norm,
     "scal": _n_scal, "axpy": _n_axpy, "dot": _n_dot, "dotc": _n_dotc, "nrm2": _n_nrm2, "gemv": _n_gemv,
-    "random_number": _n_random_number,
+    "random_number": _n_random_number, "hermitian": _n_hermitian, "normal": _n_normal,
 }
