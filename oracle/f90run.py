@@ -1909,7 +1909,21 @@ class Interp:
         elif k in ("io", "nop"):
             pass
         elif k == "ptr_assign":
-            self.raw_store(st[1], self.ev(st[2], sc), sc)
+            tgt, val = st[1], self.ev(st[2], sc)
+            if tgt[0] == "call" and tgt[1][0] == "name" and all(a[0] == "slice" for _, a in tgt[2]):
+                # bounds-remapping pointer assignment  p(1:k, 1:1) => e(:k): a reshaped VIEW of the target
+                shape = []
+                for _, a in tgt[2]:
+                    lo, hi = int(self.ev(a[1], sc)), int(self.ev(a[2], sc))
+                    if lo != 1:
+                        raise FortranError("pointer bounds remapping with a lower bound other than 1")
+                    shape.append(hi)
+                view = val.reshape(tuple(shape), order="F")
+                if view.size and not np.shares_memory(view, val):
+                    raise FortranError("pointer bounds remapping of a non-contiguous target")
+                sc.vars[tgt[1][1]] = view
+            else:
+                self.raw_store(tgt, val, sc)
         elif k == "return":
             raise _Return()
         elif k == "exit":
@@ -2308,6 +2322,159 @@ def _n_normal(interp, loc, scale):
     return np.asarray(r, dtype=dt) if shape else dt.type(r)
 
 
+def _lapack(name, *arrays):
+    from scipy.linalg import get_lapack_funcs
+    return get_lapack_funcs(name, arrays)
+
+
+def _n_lasr(interp, side, pivot, direct, m, n, c, s, a, lda):
+    """LAPACK xLASR, the one variant the reference uses: SIDE = L, PIVOT = V, DIRECT = F (restated from the LAPACK source)"""
+    if (side.upper(), pivot.upper(), direct.upper()) != ("L", "V", "F"):
+        raise FortranError("lasr: only side=L, pivot=V, direct=F is provided")
+    for j in range(m - 1):
+        ct, st = c[j], s[j]
+        if ct != 1 or st != 0:
+            for i in range(n):
+                temp = a[j + 1, i]
+                a[j + 1, i] = ct * temp - st * a[j, i]
+                a[j, i] = st * temp + ct * a[j, i]
+
+
+def _n_lartg(interp, f, g, c, s, r):
+    fn = _lapack("lartg", np.asarray(f))
+    cs, sn, rr = fn(f, g)
+    t = np.asarray(f).dtype.type
+    return ("__out__", {2: t(cs), 3: t(sn), 4: t(rr)})
+
+
+def _n_trtrs(interp, uplo, trans, diag, n, nrhs, a, lda, b, ldb, info):
+    fn = _lapack("trtrs", a)
+    x, inf = fn(a[:n, :n], b[:n, :nrhs], lower=int(uplo.upper() == "L"),
+                trans={"N": 0, "T": 1, "C": 2}[trans.upper()], unitdiag=int(diag.upper() == "U"))
+    b[:n, :nrhs] = x
+    return ("__out__", {9: int(inf)})
+
+
+def _n_geev(interp, jobvl, jobvr, n, a, lda, *rest):
+    fn = _lapack("geev", a)
+    if np.iscomplexobj(a):
+        w, vl, ldvl, vr, ldvr, work, lwork, rwork, info = rest
+        wv, vlv, vrv, inf = fn(a[:n, :n], compute_vl=int(jobvl.upper() == "V"), compute_vr=int(jobvr.upper() == "V"))
+        w[:n] = wv
+        pos_info = 13
+    else:
+        wr, wi, vl, ldvl, vr, ldvr, work, lwork, info = rest
+        wrv, wiv, vlv, vrv, inf = fn(a[:n, :n], compute_vl=int(jobvl.upper() == "V"), compute_vr=int(jobvr.upper() == "V"))
+        wr[:n], wi[:n] = wrv, wiv
+        pos_info = 13
+    if jobvr.upper() == "V":
+        vr[:n, :n] = vrv
+    if jobvl.upper() == "V":
+        vl[:n, :n] = vlv
+    return ("__out__", {pos_info: int(inf)})
+
+
+def _n_eigh(interp, a, lambda_, vectors=None, upper_a=None, overwrite_a=None, err=None, **k):
+    """stdlib_linalg eigh(A, lambda, vectors): xSYEV / xHEEV, lower triangle by default"""
+    fn = _lapack("heev" if np.iscomplexobj(a) else "syev", a)
+    lower = 0 if (upper_a is not None and upper_a is not ABSENT and upper_a) else 1
+    w, v, inf = fn(a, compute_v=1, lower=lower)
+    if inf != 0:
+        raise StopError(f"eigh: info = {inf}")
+    lambda_[...] = w
+    if vectors is not None and vectors is not ABSENT:
+        vectors[...] = v
+
+
+def _n_svd(interp, a, s, u=None, vt=None, **k):
+    """stdlib_linalg svd(A, s, u, vt): xGESDD"""
+    fn = _lapack("gesdd", a)
+    uu, ss, vvt, inf = fn(a, compute_uv=1, full_matrices=1)
+    if inf != 0:
+        raise StopError(f"svd: info = {inf}")
+    s[...] = ss[:s.shape[0]]
+    if u is not None and u is not ABSENT:
+        u[...] = uu[:u.shape[0], :u.shape[1]]
+    if vt is not None and vt is not ABSENT:
+        vt[...] = vvt[:vt.shape[0], :vt.shape[1]]
+
+
+def _n_schur(interp, a, t, z=None, eigvals=None, **k):
+    """stdlib_linalg schur(A, T, Z, eigvals): xGEES (real kinds: real quasi-triangular form)"""
+    import scipy.linalg as sla
+    tt, zz = sla.schur(np.array(a), output="complex" if np.iscomplexobj(a) else "real")
+    t[...] = tt
+    if z is not None and z is not ABSENT:
+        z[...] = zz
+    if eigvals is not None and eigvals is not ABSENT:
+        n = tt.shape[0]
+        if np.iscomplexobj(tt):
+            eigvals[...] = np.diag(tt)
+        else:                                   # eigenvalues of the 1x1 / 2x2 diagonal blocks, as xGEES returns (wr, wi)
+            w = np.zeros(n, dtype=np.complex128)
+            i = 0
+            while i < n:
+                if i + 1 < n and tt[i + 1, i] != 0:
+                    a11, a12, a21, a22 = tt[i, i], tt[i, i + 1], tt[i + 1, i], tt[i + 1, i + 1]
+                    im = np.sqrt(abs(a12)) * np.sqrt(abs(a21))              # standardised block: a11 == a22, a12 * a21 < 0
+                    w[i], w[i + 1] = complex(a11, im), complex(a22, -im)
+                    i += 2
+                else:
+                    w[i] = tt[i, i]
+                    i += 1
+            eigvals[...] = w
+
+
+def _n_trsen(interp, job, compq, select, n, t, ldt, q, ldq, *rest):
+    fn = _lapack("trsen", t)
+    sel = np.asarray(select, dtype=np.int32)
+    if np.iscomplexobj(t):
+        w, m, s, sep, work, lwork, info = rest
+        ts, qs, wv, mm, ss, sp_, inf = fn(sel, np.array(t[:n, :n]), np.array(q[:n, :n]), job=job.upper(), wantq=int(compq.upper() == "V"))
+        w[:n] = wv
+        out = {9: int(mm), 10: ss, 11: sp_, 14: int(inf)}
+    else:
+        wr, wi, m, s, sep, work, lwork, iwork, liwork, info = rest
+        ts, qs, wrv, wiv, mm, ss, sp_, inf = fn(sel, np.array(t[:n, :n]), np.array(q[:n, :n]), job=job.upper(), wantq=int(compq.upper() == "V"))
+        wr[:n], wi[:n] = wrv, wiv
+        out = {10: int(mm), 11: ss, 12: sp_, 17: int(inf)}
+    t[:n, :n] = ts
+    q[:n, :n] = qs
+    return ("__out__", out)
+
+
+def _n_expm(interp, a, *rest, **k):
+    """stdlib_linalg expm (third-party, not in the reference tree): Pade approximant with scaling and squaring"""
+    import scipy.linalg as sla
+    return np.asfortranarray(sla.expm(np.asarray(a, dtype=np.complex128 if np.iscomplexobj(a) else np.float64)).astype(a.dtype))
+
+
+def _n_sort_index(interp, array, index, work=None, iwork=None, reverse=None):
+    """stdlib_sorting sort_index: STABLE sort of `array` in place, `index` (1-based) = the permutation applied"""
+    rev = reverse is not None and reverse is not ABSENT and bool(reverse)
+    key = np.array(array)
+    if rev:
+        order = np.argsort(-key, kind="stable") if not np.iscomplexobj(key) else None
+        # a stable DEcreasing sort keeps ties in their original order
+        order = np.array(sorted(range(len(key)), key=lambda i: -key[i]), dtype=np.int64)
+    else:
+        order = np.argsort(key, kind="stable")
+    array[...] = key[order]
+    index[...] = order + 1
+
+
+def _n_median(interp, a, *rest, **k):
+    return np.asarray(a).dtype.type(np.median(a))
+
+
+def _n_diag(interp, v, k=0):
+    return np.asfortranarray(np.diag(v, int(k)))
+
+
+def _n_inv(interp, a, *rest, **k):
+    return np.asfortranarray(np.linalg.inv(a).astype(a.dtype))
+
+
 def _n_type_error(interp, *a, **k):
     raise StopError(f"type_error{a}")
 
@@ -2323,4 +2490,9 @@ NATIVES = {
     "optval": _n_optval, "eye": _n_eye, "mnorm": _n_mnorm, "norm": _n_norm,
     "scal": _n_scal, "axpy": _n_axpy, "dot": _n_dot, "dotc": _n_dotc, "nrm2": _n_nrm2, "gemv": _n_gemv,
     "random_number": _n_random_number, "hermitian": _n_hermitian, "normal": _n_normal,
+    "diag": _n_diag, "inv": _n_inv, "median": _n_median, "sort_index": _n_sort_index, "expm": _n_expm,
+    "eigh": _n_eigh, "svd": _n_svd,
+    # LAPACK (stdlib_linalg_lapack generic names)
+    "lasr": _n_lasr, "lartg": _n_lartg, "trtrs": _n_trtrs, "geev": _n_geev, "trsen": _n_trsen, "schur": _n_schur,
+    "save_npy": _n_noop, "padr": lambda interp, s, n, *a: str(s).ljust(int(n)),
 }

@@ -48,9 +48,9 @@ def general_matrix(kind, seed=1):
     return pseudo((N, N), seed, kind)                       # entries in [-0.5, 0.5): spectral radius ~ 3.3
 
 
-def sym_matrix(kind, seed=3):
+def sym_matrix(kind, seed=3, shift=0.01):
     M = pseudo((N, N), seed, kind).astype(np.complex128 if kind in "cz" else np.float64)
-    S = M @ M.conj().T / N + 0.01 * np.eye(N)
+    S = M @ M.conj().T / N + shift * np.eye(N)
     return np.asfortranarray(((S + S.conj().T) / 2).astype(DTYPE[kind]))
 
 
@@ -187,7 +187,87 @@ CASES = {
 }
 
 
-SOLVER_CASES = {}
+
+# ------------------------------------------------------------------------------------------------------------------ solvers
+def _real(kind):
+    return np.float32 if kind in "sc" else np.float64
+
+
+def well_conditioned(kind, seed=201):
+    """A = 1.5 I + M * 2 / sqrt(N) (entries of M in [-0.5, 0.5)): gmres(10) needs several restarts"""
+    M = pseudo((N, N), seed, kind)
+    A = (1.5 * np.eye(N) + M * (2.0 / np.sqrt(N))).astype(DTYPE[kind])
+    return np.asfortranarray(A)
+
+
+def gmres_solve(kind, be):
+    A = be.linop(kind, well_conditioned(kind))
+    b = be.basis(kind, 1, unit(pseudo((N,), 202, kind)))
+    x = be.basis(kind, 1)
+    info, meta = be.gmres(A, b, x, kdim=10, maxiter=20)
+    return {"info": info, "x": be.data(x)[:, 0].copy(), "res": np.asarray(meta["res"], dtype=np.float64),
+            "n_iter": meta["n_iter"], "n_inner": meta["n_inner"], "n_outer": meta["n_outer"]}
+
+
+def cg_solve(kind, be):
+    # shift 0.1: condition number ~ 4: the CG recurrence (not backward stable) stays within rounding of itself across
+    # implementations for the whole history; with the 0.01 shift of the reference's own test operator the iterates of two
+    # implementations drift apart by 20 % after 45 steps and the iteration counts differ by one
+    A = be.linop(kind, sym_matrix(kind, 211, shift=0.1), sym=True)
+    b = be.basis(kind, 1, unit(pseudo((N,), 212, kind)))
+    x = be.basis(kind, 1)
+    info, meta = be.cg(A, b, x, maxiter=300)
+    return {"info": info, "x": be.data(x)[:, 0].copy(), "res": np.asarray(meta["res"], dtype=np.float64),
+            "n_iter": meta["n_iter"]}
+
+
+def eighs_solve(kind, be):
+    nev = 4
+    A = be.linop(kind, sym_matrix(kind, 221), sym=True)
+    x0 = unit(pseudo((N,), 222, kind))
+    ev, res, X, info = be.eighs(A, nev, x0, kdim=64, tolerance=1e-3 if kind in "sc" else 1e-9)
+    return {"info": info, "eigvals": np.asarray(ev, dtype=np.float64), "absvecs": np.abs(X)}       # eigenvectors up to a phase
+
+
+def svds_solve(kind, be):
+    nsv = 3
+    A = be.linop(kind, general_matrix(kind, 231))
+    u0 = unit(pseudo((N,), 232, kind))
+    S, res, U, V, info = be.svds(A, nsv, u0, kdim=64, tolerance=1e-3 if kind in "sc" else 1e-9)
+    return {"info": info, "S": np.asarray(S, dtype=np.float64), "absU": np.abs(U), "absV": np.abs(V)}
+
+
+def dominant_matrix(kind, seed=251):
+    """non-normal matrix with four well separated leading eigenvalues (the rest inside a disc of radius ~ 0.6)"""
+    A = pseudo((N, N), seed, kind) * DTYPE[kind](2.0 / np.sqrt(N))
+    for i, d in enumerate((3.0, 2.5, -2.2, 1.9)):
+        A[i, i] += DTYPE[kind](d)
+    return np.asfortranarray(A.astype(DTYPE[kind]))
+
+
+def eigs_solve(kind, be):
+    nev = 4
+    A = be.linop(kind, dominant_matrix(kind))
+    x0 = unit(pseudo((N,), 252, kind))
+    ev, res, X, info = be.eigs(A, nev, x0, kdim=24, tolerance=1e-3 if kind in "sc" else 1e-9)
+    out = {"info": info, "eigvals": np.asarray(ev, dtype=np.complex128)}
+    if kind in "sd":
+        out["X"] = X                      # real kinds: (Re, Im) column pairs, normalised by xGEEV -- directly comparable
+    else:
+        out["absX"] = np.abs(X)           # complex kinds: eigenvectors are defined up to a phase
+    return out
+
+
+def kexpm_solve(kind, be):
+    A = be.linop(kind, general_matrix(kind, 241))
+    b = be.basis(kind, 1, unit(pseudo((N,), 242, kind)))
+    c = be.basis(kind, 1)
+    info = be.kexpm(c, A, b, tau=0.1, tol=1e-4 if kind in "sc" else 1e-10, kdim=40)
+    return {"info": info, "c": be.data(c)[:, 0].copy()}
+
+
+SOLVER_CASES = {"eigs_solve": eigs_solve, "gmres_solve": gmres_solve, "cg_solve": cg_solve, "eighs_solve": eighs_solve, "svds_solve": svds_solve,
+                "kexpm_solve": kexpm_solve}
 
 
 def applies(name, kind):
@@ -262,6 +342,70 @@ class RefBackend:
         return int(o[2]), beta
 
 
+    # ---- solvers
+    def _meta(self, name, kind):
+        it = self.rx.interp()
+        return it.new_inst(f"{name}_{'sp' if kind in 'sc' else 'dp'}_metadata")
+
+    def _kind(self, X):
+        return {np.dtype(np.float32): "s", np.dtype(np.float64): "d", np.dtype(np.complex64): "c",
+                np.dtype(np.complex128): "z"}[X[0].f["data"].dtype]
+
+    def gmres(self, A, b, x, kdim, maxiter):
+        kind = self._kind(b)
+        it = self.rx.interp()
+        opts = it.new_inst(f"gmres_{'sp' if kind in 'sc' else 'dp'}_opts")
+        opts.f["kdim"], opts.f["maxiter"] = kdim, maxiter
+        meta = self._meta("gmres", kind)
+        _, o = self.rx.call("gmres", A, b[0], x[0], 0, options=opts, meta=meta)
+        m = meta.f
+        return int(o[3]), {"res": np.array(m["res"][:m["n_iter"] + 1]), "n_iter": int(m["n_iter"]), "n_inner": int(m["n_inner"]),
+                           "n_outer": int(m["n_outer"]), "converged": bool(m["converged"])}
+
+    def cg(self, A, b, x, maxiter):
+        kind = self._kind(b)
+        it = self.rx.interp()
+        opts = it.new_inst(f"cg_{'sp' if kind in 'sc' else 'dp'}_opts")
+        opts.f["maxiter"] = maxiter
+        meta = self._meta("cg", kind)
+        _, o = self.rx.call("cg", A, b[0], x[0], 0, options=opts, meta=meta)
+        m = meta.f
+        return int(o[3]), {"res": np.array(m["res"][:m["n_iter"] + 1]), "n_iter": int(m["n_iter"])}
+
+    def eighs(self, A, nev, x0, kdim, tolerance):
+        kind = {np.dtype(np.float32): "s", np.dtype(np.float64): "d", np.dtype(np.complex64): "c",
+                np.dtype(np.complex128): "z"}[x0.dtype]
+        X = self.basis(kind, nev)
+        x0v = self.rx.vector(kind, x0)
+        _, o = self.rx.call("eighs", A, X, None, None, 0, x0=x0v, kdim=kdim, tolerance=_real(kind)(tolerance),
+                            write_intermediate=False)
+        return np.array(o[2]), np.array(o[3]), self.data(X), int(o[4])
+
+    def eigs(self, A, nev, x0, kdim, tolerance):
+        kind = {np.dtype(np.float32): "s", np.dtype(np.float64): "d", np.dtype(np.complex64): "c",
+                np.dtype(np.complex128): "z"}[x0.dtype]
+        X = self.basis(kind, nev)
+        x0v = self.rx.vector(kind, x0)
+        _, o = self.rx.call("eigs", A, X, None, None, 0, x0=x0v, kdim=kdim, tolerance=_real(kind)(tolerance),
+                            write_intermediate=False)
+        return np.array(o[2]), np.array(o[3]), self.data(X), int(o[4])
+
+    def svds(self, A, nsv, u0, kdim, tolerance):
+        kind = {np.dtype(np.float32): "s", np.dtype(np.float64): "d", np.dtype(np.complex64): "c",
+                np.dtype(np.complex128): "z"}[u0.dtype]
+        U, V = self.basis(kind, nsv), self.basis(kind, nsv)
+        u0v = self.rx.vector(kind, u0)
+        _, o = self.rx.call("svds", A, U, None, V, None, 0, u0=u0v, kdim=kdim, tolerance=_real(kind)(tolerance),
+                            write_intermediate=False)
+        return np.array(o[2]), np.array(o[4]), self.data(U), self.data(V), int(o[5])
+
+    def kexpm(self, c, A, b, tau, tol, kdim):
+        kind = self._kind(b)
+        rt = _real(kind)
+        _, o = self.rx.call("kexpm", c[0], A, b[0], rt(tau), rt(tol), 0, kdim=kdim)
+        return int(o[5])
+
+
 class OracleBackend:
     """oracle/lk_oracle (C restatement) -- the thing the fixtures pin"""
     name = "oracle"
@@ -308,3 +452,29 @@ class OracleBackend:
 
     def dgs_bas(self, Y, X):
         return self.lo.dgs_bas(Y, X, X.shape[1])
+
+    # ---- solvers
+    def gmres(self, A, b, x, kdim, maxiter):
+        info, meta = self.lo.gmres(A, b[:, 0], x[:, 0], kdim=kdim, maxiter=maxiter)
+        return info, meta
+
+    def cg(self, A, b, x, maxiter):
+        info, meta = self.lo.cg(A, b[:, 0], x[:, 0], maxiter=maxiter)
+        return info, meta
+
+    def eighs(self, A, nev, x0, kdim, tolerance):
+        ev, res, X, k = self.lo.eighs(A, N, nev, x0, kdim=kdim, tolerance=tolerance)
+        return ev, res, X, k
+
+    def eigs(self, A, nev, x0, kdim, tolerance):
+        ev, res, X, niter = self.lo.eigs(A, N, nev, x0, kdim=kdim, tolerance=tolerance)
+        return ev, res, X, niter
+
+    def svds(self, A, nsv, u0, kdim, tolerance):
+        S, res, U, V, k = self.lo.svds(A, nsv, u0, kdim=kdim, tolerance=tolerance)
+        return S, res, U, V, k
+
+    def kexpm(self, c, A, b, tau, tol, kdim):
+        out, info = self.lo.kexpm_vec(A, b[:, 0].copy(), tau, tol, kdim=kdim)
+        c[:, 0] = out
+        return info
