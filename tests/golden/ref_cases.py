@@ -266,7 +266,47 @@ def kexpm_solve(kind, be):
     return {"info": info, "c": be.data(c)[:, 0].copy()}
 
 
-SOLVER_CASES = {"eigs_solve": eigs_solve, "gmres_solve": gmres_solve, "cg_solve": cg_solve, "eighs_solve": eighs_solve, "svds_solve": svds_solve,
+def eighs_write_intermediate(kind, be):
+    """write_results sorts its residual argument in place (IterativeSolvers.fypp:882-924): with write_intermediate the
+    residuals eighs returns are the LARGEST entries of the ascending table -- a literal side effect of the reference"""
+    nev = 4
+    A = be.linop(kind, sym_matrix(kind, 221), sym=True)
+    x0 = unit(pseudo((N,), 222, kind))
+    ev, res, X, info = be.eighs(A, nev, x0, kdim=64, tolerance=1e-3 if kind in "sc" else 1e-9, write_intermediate=True)
+    return {"info": info, "eigvals": np.asarray(ev, dtype=np.float64), "residuals": np.asarray(res, dtype=np.float64)}
+
+
+def svds_write_intermediate(kind, be):
+    nsv = 3
+    A = be.linop(kind, general_matrix(kind, 231))
+    u0 = unit(pseudo((N,), 232, kind))
+    S, res, U, V, info = be.svds(A, nsv, u0, kdim=64, tolerance=1e-3 if kind in "sc" else 1e-9, write_intermediate=True)
+    # the residuals svds returns are then the SMALLEST entries of the ascending table (~ tolerance): converged quantities
+    # with no relative accuracy, so only their bound is checked
+    return {"info": info, "S": np.asarray(S, dtype=np.float64),
+            "abs_residual_max": np.array(np.abs(res).max() * (1e-9 if kind in "dz" else 1e-3), dtype=np.float64)}
+
+
+def fgmres_solve(kind, be):
+    A = be.linop(kind, well_conditioned(kind, 261))
+    b = be.basis(kind, 1, unit(pseudo((N,), 262, kind)))
+    x = be.basis(kind, 1)
+    info, meta = be.gmres(A, b, x, kdim=8, maxiter=30, flexible=True)
+    return {"info": info, "x": be.data(x)[:, 0].copy(), "res": np.asarray(meta["res"], dtype=np.float64),
+            "n_iter": meta["n_iter"], "n_inner": meta["n_inner"], "n_outer": meta["n_outer"]}
+
+
+def kexpm_block(kind, be):
+    p = 3
+    A = be.linop(kind, general_matrix(kind, 271))
+    B = be.basis(kind, p, pseudo((N, p), 272, kind))
+    Cb = be.basis(kind, p)
+    info = be.kexpm_mat(Cb, A, B, tau=0.1, tol=1e-4 if kind in "sc" else 1e-10, kdim=20)
+    return {"info": info, "C": be.data(Cb)}
+
+
+SOLVER_CASES = {"eighs_write_intermediate": eighs_write_intermediate, "svds_write_intermediate": svds_write_intermediate,
+                "fgmres_solve": fgmres_solve, "kexpm_block": kexpm_block, "eigs_solve": eigs_solve, "gmres_solve": gmres_solve, "cg_solve": cg_solve, "eighs_solve": eighs_solve, "svds_solve": svds_solve,
                 "kexpm_solve": kexpm_solve}
 
 
@@ -351,13 +391,14 @@ class RefBackend:
         return {np.dtype(np.float32): "s", np.dtype(np.float64): "d", np.dtype(np.complex64): "c",
                 np.dtype(np.complex128): "z"}[X[0].f["data"].dtype]
 
-    def gmres(self, A, b, x, kdim, maxiter):
+    def gmres(self, A, b, x, kdim, maxiter, flexible=False):
         kind = self._kind(b)
         it = self.rx.interp()
-        opts = it.new_inst(f"gmres_{'sp' if kind in 'sc' else 'dp'}_opts")
+        name = "fgmres" if flexible else "gmres"
+        opts = it.new_inst(f"{name}_{'sp' if kind in 'sc' else 'dp'}_opts")
         opts.f["kdim"], opts.f["maxiter"] = kdim, maxiter
-        meta = self._meta("gmres", kind)
-        _, o = self.rx.call("gmres", A, b[0], x[0], 0, options=opts, meta=meta)
+        meta = self._meta(name, kind)
+        _, o = self.rx.call(name, A, b[0], x[0], 0, options=opts, meta=meta)
         m = meta.f
         return int(o[3]), {"res": np.array(m["res"][:m["n_iter"] + 1]), "n_iter": int(m["n_iter"]), "n_inner": int(m["n_inner"]),
                            "n_outer": int(m["n_outer"]), "converged": bool(m["converged"])}
@@ -372,13 +413,13 @@ class RefBackend:
         m = meta.f
         return int(o[3]), {"res": np.array(m["res"][:m["n_iter"] + 1]), "n_iter": int(m["n_iter"])}
 
-    def eighs(self, A, nev, x0, kdim, tolerance):
+    def eighs(self, A, nev, x0, kdim, tolerance, write_intermediate=False):
         kind = {np.dtype(np.float32): "s", np.dtype(np.float64): "d", np.dtype(np.complex64): "c",
                 np.dtype(np.complex128): "z"}[x0.dtype]
         X = self.basis(kind, nev)
         x0v = self.rx.vector(kind, x0)
         _, o = self.rx.call("eighs", A, X, None, None, 0, x0=x0v, kdim=kdim, tolerance=_real(kind)(tolerance),
-                            write_intermediate=False)
+                            write_intermediate=write_intermediate)
         return np.array(o[2]), np.array(o[3]), self.data(X), int(o[4])
 
     def eigs(self, A, nev, x0, kdim, tolerance):
@@ -390,19 +431,24 @@ class RefBackend:
                             write_intermediate=False)
         return np.array(o[2]), np.array(o[3]), self.data(X), int(o[4])
 
-    def svds(self, A, nsv, u0, kdim, tolerance):
+    def svds(self, A, nsv, u0, kdim, tolerance, write_intermediate=False):
         kind = {np.dtype(np.float32): "s", np.dtype(np.float64): "d", np.dtype(np.complex64): "c",
                 np.dtype(np.complex128): "z"}[u0.dtype]
         U, V = self.basis(kind, nsv), self.basis(kind, nsv)
         u0v = self.rx.vector(kind, u0)
         _, o = self.rx.call("svds", A, U, None, V, None, 0, u0=u0v, kdim=kdim, tolerance=_real(kind)(tolerance),
-                            write_intermediate=False)
+                            write_intermediate=write_intermediate)
         return np.array(o[2]), np.array(o[4]), self.data(U), self.data(V), int(o[5])
 
     def kexpm(self, c, A, b, tau, tol, kdim):
         kind = self._kind(b)
         rt = _real(kind)
         _, o = self.rx.call("kexpm", c[0], A, b[0], rt(tau), rt(tol), 0, kdim=kdim)
+        return int(o[5])
+
+    def kexpm_mat(self, Cb, A, B, tau, tol, kdim):
+        rt = _real(self._kind(B))
+        _, o = self.rx.call("kexpm", Cb, A, B, rt(tau), rt(tol), 0, kdim=kdim)
         return int(o[5])
 
 
@@ -454,27 +500,32 @@ class OracleBackend:
         return self.lo.dgs_bas(Y, X, X.shape[1])
 
     # ---- solvers
-    def gmres(self, A, b, x, kdim, maxiter):
-        info, meta = self.lo.gmres(A, b[:, 0], x[:, 0], kdim=kdim, maxiter=maxiter)
+    def gmres(self, A, b, x, kdim, maxiter, flexible=False):
+        info, meta = self.lo.gmres(A, b[:, 0], x[:, 0], kdim=kdim, maxiter=maxiter, flexible=flexible)
         return info, meta
 
     def cg(self, A, b, x, maxiter):
         info, meta = self.lo.cg(A, b[:, 0], x[:, 0], maxiter=maxiter)
         return info, meta
 
-    def eighs(self, A, nev, x0, kdim, tolerance):
-        ev, res, X, k = self.lo.eighs(A, N, nev, x0, kdim=kdim, tolerance=tolerance)
+    def eighs(self, A, nev, x0, kdim, tolerance, write_intermediate=False):
+        ev, res, X, k = self.lo.eighs(A, N, nev, x0, kdim=kdim, tolerance=tolerance, write_intermediate=write_intermediate)
         return ev, res, X, k
 
     def eigs(self, A, nev, x0, kdim, tolerance):
         ev, res, X, niter = self.lo.eigs(A, N, nev, x0, kdim=kdim, tolerance=tolerance)
         return ev, res, X, niter
 
-    def svds(self, A, nsv, u0, kdim, tolerance):
-        S, res, U, V, k = self.lo.svds(A, nsv, u0, kdim=kdim, tolerance=tolerance)
+    def svds(self, A, nsv, u0, kdim, tolerance, write_intermediate=False):
+        S, res, U, V, k = self.lo.svds(A, nsv, u0, kdim=kdim, tolerance=tolerance, write_intermediate=write_intermediate)
         return S, res, U, V, k
 
     def kexpm(self, c, A, b, tau, tol, kdim):
         out, info = self.lo.kexpm_vec(A, b[:, 0].copy(), tau, tol, kdim=kdim)
         c[:, 0] = out
+        return info
+
+    def kexpm_mat(self, Cb, A, B, tau, tol, kdim):
+        out, info = self.lo.kexpm_mat(A, np.asfortranarray(B.copy()), tau, tol, kdim=kdim)
+        Cb[...] = out
         return info
