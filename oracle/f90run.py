@@ -1134,7 +1134,7 @@ class Interp:
         dt = ts.dtype()
         if dt is object:
             a = np.empty(shape, dtype=object, order="F")
-            if ts.base == "type":
+            if ts.tname in self.p.types:      # class(T) elements allocated without source= have the declared type as dynamic type
                 for ix in np.ndindex(*shape):
                     a[ix] = self.new_inst(ts.tname)
             return a
@@ -1477,6 +1477,9 @@ class Interp:
             self.assign_slot(holder[nm], value, decl, lambda v: holder.__setitem__(nm, v))
         elif k == "comp":
             obj = self.ev(target[1], sc)
+            if isinstance(obj, np.ndarray) and np.iscomplexobj(obj) and target[2] in ("re", "im"):
+                (obj.real if target[2] == "re" else obj.imag)[...] = value          # z%re = ... on a complex array (a view)
+                return
             if not isinstance(obj, Inst):
                 raise FortranError("component assignment on a non-derived value")
             decl = self.component_decl(obj.tname, target[2])
@@ -1508,6 +1511,10 @@ class Interp:
             holder[nm] = value
         elif k == "comp":
             obj = self.ev(target[1], sc)
+            if isinstance(obj, _CPLX_TYPES) and target[2] in ("re", "im"):
+                new = type(obj)(complex(value, obj.imag) if target[2] == "re" else complex(obj.real, value))
+                self.raw_store(target[1], new, sc)
+                return
             obj.f[target[2]] = value
         elif k == "call":
             arr = self.ev(target[1], sc)
@@ -1566,7 +1573,13 @@ class Interp:
         if nm in self.natives:
             return self.call_native(nm, self.natives[nm], actuals, sc)
         if nm in self.p.generics:
-            proc = self.resolve_generic(nm, self.p.generics[nm], actuals)
+            try:
+                proc = self.resolve_generic(nm, self.p.generics[nm], actuals)
+            except FortranError:
+                if nm not in self.p.types:
+                    raise
+                proc = None                     # generic named like a type: no specific matches -> the structure constructor
+        if nm in self.p.generics and proc is not None:
             if isinstance(proc, str):
                 return self.call_native(proc, self.natives[proc], actuals, sc)
             return self.call_proc(proc, actuals, sc)
@@ -2475,6 +2488,14 @@ def _n_inv(interp, a, *rest, **k):
     return np.asfortranarray(np.linalg.inv(a).astype(a.dtype))
 
 
+def _n_is_close(interp, a, b, rel_tol=None, abs_tol=None, equal_nan=None):
+    """stdlib_math is_close: |a - b| <= max(rel_tol * max(|a|, |b|), abs_tol), rel_tol = sqrt(epsilon) by default"""
+    eps = np.finfo(np.asarray(a).real.dtype if np.asarray(a).dtype.kind in "fc" else np.float64).eps
+    rt = np.sqrt(eps) if rel_tol is None or rel_tol is ABSENT else rel_tol
+    at = 0.0 if abs_tol is None or abs_tol is ABSENT else abs_tol
+    return np.abs(a - b) <= np.maximum(rt * np.maximum(np.abs(a), np.abs(b)), at)
+
+
 def _n_type_error(interp, *a, **k):
     raise StopError(f"type_error{a}")
 
@@ -2494,5 +2515,5 @@ NATIVES = {
     "eigh": _n_eigh, "svd": _n_svd,
     # LAPACK (stdlib_linalg_lapack generic names)
     "lasr": _n_lasr, "lartg": _n_lartg, "trtrs": _n_trtrs, "geev": _n_geev, "trsen": _n_trsen, "schur": _n_schur,
-    "save_npy": _n_noop, "padr": lambda interp, s, n, *a: str(s).ljust(int(n)),
+    "is_close": _n_is_close, "save_npy": _n_noop, "padr": lambda interp, s, n, *a: str(s).ljust(int(n)),
 }
