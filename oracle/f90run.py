@@ -144,12 +144,12 @@ def _parse_number(v):
     if "_" in v:
         v, kind = v.split("_", 1)
     if re.fullmatch(r"\d+", v):
-        return int(v)
+        return int(v)                      # integer literals of any kind (1_c_int64_t, ...)
     if "d" in v:
         return np.float64(v.replace("d", "e"))
-    if kind == "dp":
+    if kind in ("dp", "c_double", "real64"):
         return np.float64(v)
-    if kind in (None, "sp"):
+    if kind in (None, "sp", "c_float", "real32"):
         return np.float32(v)           # default real is single precision
     raise FortranError(f"unknown kind suffix _{kind}")
 
@@ -464,6 +464,8 @@ def _parse_typespec(toks, src):
             # (dp) | (kind=dp)
             ks = [t for t in inner if t[0] == "name" and t[1] != "kind"]
             kind = ks[0][1] if ks else None
+            kind = {"c_double": "dp", "c_float": "sp", "real64": "dp", "real32": "sp", "c_double_complex": "dp",
+                    "c_float_complex": "sp"}.get(kind, kind)
             if kind is None and inner and inner[0][0] == "num":
                 kind = {"4": "sp", "8": "dp"}.get(inner[0][1])
     ts = TypeSpec("class" if base == "class" else base, kind, tname)
@@ -554,6 +556,36 @@ class Inst:
         return f"<{self.tname} {list(self.f)}>"
 
 
+class CPtr:
+    """type(c_ptr) / type(c_funptr): `obj` is None (c_null_ptr), a numpy array (c_loc of an array: shared memory), a ScalarRef
+    (c_loc of a scalar variable) or any Python object a native handed out as an opaque handle.  Copying the Fortran value
+    copies the POINTER (shallow), also inside deep copies of derived-type values."""
+    __slots__ = ("obj",)
+
+    def __init__(self, obj=None):
+        self.obj = obj
+
+    def __deepcopy__(self, memo):
+        return CPtr(self.obj)
+
+    def __repr__(self):
+        return f"CPtr({type(self.obj).__name__})"
+
+
+class ScalarRef:
+    """c_loc(scalar variable): reads and writes go to the variable's slot in its scope"""
+    __slots__ = ("interp", "sc", "ast")
+
+    def __init__(self, interp, sc, ast):
+        self.interp, self.sc, self.ast = interp, sc, ast
+
+    def get(self):
+        return self.interp.ev(self.ast, self.sc)
+
+    def set(self, v):
+        self.interp.raw_store(self.ast, v, self.sc)
+
+
 class _Exit(Exception):
     def __init__(self, label):
         self.label = label
@@ -627,15 +659,28 @@ class Program:
 
     @staticmethod
     def _is_proc_header(toks):
-        names = [t[1] for t in toks[:8] if t[0] == "name"]
-        for k, nm in enumerate(names):
+        """[prefix]... subroutine|function name ...  |  module procedure name   (prefixes: pure, elemental, a type-spec, ...)"""
+        depth, prev = 0, None
+        for k, t in enumerate(toks):
+            if t[0] == "op" and t[1] == "(":
+                depth += 1
+                continue
+            if t[0] == "op" and t[1] == ")":
+                depth -= 1
+                continue
+            if depth:
+                continue
+            if t[0] != "name":
+                return False
+            nm = t[1]
             if nm in ("subroutine", "function"):
-                return True
-            if nm == "procedure" and k > 0 and names[k - 1] == "module" and len(toks) <= 4:
+                return k + 1 < len(toks) and toks[k + 1][0] == "name"
+            if nm == "procedure" and prev == "module" and len(toks) <= 4:
                 return True
             if nm not in ("module", "pure", "impure", "elemental", "recursive", "integer", "real", "logical", "complex",
-                          "dp", "sp", "kind", "type", "class", "character", "len"):
+                          "type", "class", "character", "double", "precision"):
                 return False
+            prev = nm
         return False
 
     def _parse_interface(self, lines, i, module):
@@ -764,9 +809,11 @@ class Program:
                 args = [t[1] for t in inner if t[0] == "name"]
             if kind == "function":
                 result = name
-                if j < len(toks) and toks[j] == ("name", "result"):
-                    inner, j = _paren_group(toks, j + 1)
+            while j < len(toks) and toks[j][0] == "name" and toks[j][1] in ("result", "bind"):
+                inner, j2 = _paren_group(toks, j + 1)
+                if toks[j][1] == "result":
                     result = inner[0][1]
+                j = j2
         if host is not None:
             host.internals[name] = host.name + "::" + name
             name = host.name + "::" + name
@@ -1061,9 +1108,15 @@ class Interp:
         self.natives.update(program.natives)
         self.trace = False
         self.call_depth = 0
+        self.hooks = {}               # reference procedure name -> logical function tried first (see run_proc_scalar)
+        self.hook_hits = {}
         gsc = Scope(None)
         gsc.vars = self.p.globals
         self.gscope = gsc
+        for name, val in (("c_null_ptr", CPtr(None)), ("c_null_funptr", CPtr(None)), ("c_double", "dp"), ("c_float", "sp"),
+                          ("c_int", "c_int"), ("c_int32_t", "c_int32_t"), ("c_int64_t", "c_int64_t"), ("c_size_t", "c_size_t"),
+                          ("c_bool", "c_bool"), ("c_char", "c_char"), ("ilp", "ilp"), ("c_null_char", "\x00")):
+            self.p.globals.setdefault(name, val)
         for d, src in self.p.pending_globals:
             self.p.global_decls[d.name] = d
             self._declare(d, gsc)
@@ -1158,6 +1211,8 @@ class Interp:
             return a
         if d.init is not None:
             return self.coerce(d.ts, self.ev(d.init, sc))
+        if d.ts.base == "type" and d.ts.tname in ("c_ptr", "c_funptr"):
+            return CPtr(None)
         if d.ts.base == "type":
             return self.new_inst(d.ts.tname) if d.ts.tname in self.p.types else Inst(d.ts.tname)
         if d.ts.base in ("class", "procedure"):
@@ -1402,6 +1457,17 @@ class Interp:
     def inst_assign(self, dst, src):
         if dst is src:
             return
+        found = self.find_binding(dst.tname, "assignment(=)")
+        if found is not None and found[0] == "generic":              # defined assignment: generic :: assignment(=) => proc
+            for b in found[1]:
+                f2 = self.find_binding(dst.tname, b)
+                proc = self.p.procs.get(f2[1][0]) if f2 and f2[0] == "specific" else None
+                if proc is None:
+                    continue
+                bound = self.bind_args(proc, [(None, dst, None), (None, src, None)])
+                if bound is not None:
+                    self.run_proc(proc, bound, self.gscope)
+                    return
         dst.tname = src.tname
         dst.f = copy.deepcopy(src.f)
 
@@ -1565,6 +1631,11 @@ class Interp:
     def call_named(self, nm, args, sc, want_result):
         if sc.proc is not None and nm in sc.proc.internals:
             nm = sc.proc.internals[nm]
+        if nm == "c_loc":
+            v = self.ev(args[0][1], sc)
+            return CPtr(v) if isinstance(v, np.ndarray) else CPtr(ScalarRef(self, sc, args[0][1]))
+        if nm == "c_funloc":
+            return CPtr(self.ev(args[0][1], sc))
         if nm == "present":
             return self.ev(args[0][1], sc) is not ABSENT
         if nm == "allocated":
@@ -1645,6 +1716,8 @@ class Interp:
             return True
         if isinstance(v, tuple) and v and v[0] == "procref":
             return d.ts.base == "procedure"
+        if isinstance(v, CPtr):
+            return d.ts.base == "type" and d.ts.tname in ("c_ptr", "c_funptr") and d.rank == 0
         base, kind, rank = _kind_of_value(v)
         if rank != d.rank and not (elemental and d.rank == 0):
             return False
@@ -1779,6 +1852,15 @@ class Interp:
         return self.run_proc_scalar(proc, bound, caller_sc)
 
     def run_proc_scalar(self, proc, bound, caller_sc):
+        hook = self.hooks.get(proc.name)
+        if hook is not None:
+            # emulates a one-line patch at the top of the procedure:   if (<hook>(<same dummies>)) return
+            tproc = self.p.procs[hook]
+            if len(tproc.args) != len(proc.args):
+                raise FortranError(f"hook {hook}: {len(tproc.args)} dummies for the {len(proc.args)} of {proc.name}")
+            if bool(self.run_proc(tproc, {tn: bound[rn] for tn, rn in zip(tproc.args, proc.args)}, caller_sc)):
+                self.hook_hits[proc.name] = self.hook_hits.get(proc.name, 0) + 1
+                return None
         sc = Scope(proc)
         for n, (v, lv) in bound.items():
             d = proc.decls[n]
@@ -1868,6 +1950,9 @@ class Interp:
                 sc.vars[assoc] = v
             chosen = None
             tn = v.tname if isinstance(v, Inst) else None
+            if isinstance(v, np.ndarray) and v.dtype == object:           # select type on an array: the type of its elements
+                first = next((x for x in v.ravel() if isinstance(x, Inst)), None)
+                tn = first.tname if first is not None else None
             for (gk, gname), blk in guards:
                 if gk == "type" and tn == gname:
                     chosen = blk
@@ -2194,6 +2279,17 @@ def _i_matmul(a, b):
     return np.asfortranarray(a @ b) if isinstance(a @ b, np.ndarray) and (a @ b).ndim == 2 else a @ b
 
 
+def _i_transfer(source, mold, size=None):
+    """transfer(character string, character array mold): the one use the shim makes of it"""
+    if isinstance(source, str) and isinstance(mold, np.ndarray):
+        n = mold.size if size is None else int(size)
+        a = np.empty(n, dtype=object)
+        for i in range(n):
+            a[i] = source[i] if i < len(source) else " "
+        return a
+    raise FortranError("transfer: only string -> character array is provided")
+
+
 def _i_kind(x):
     return "dp" if np.asarray(x).dtype in (np.float64, np.complex128) else "sp"
 
@@ -2219,7 +2315,7 @@ INTRINSICS = {
     "atan2": np.arctan2, "acos": np.arccos, "asin": np.arcsin, "tanh": np.tanh, "sinh": np.sinh, "cosh": np.cosh,
     "sign": _i_sign, "merge": _i_merge, "epsilon": _i_epsilon, "huge": _i_huge, "tiny": _i_tiny, "precision": _i_precision,
     "selected_real_kind": lambda p=6, r=37: "sp" if p <= 6 else "dp",
-    "kind": _i_kind, "reshape": _i_reshape,
+    "kind": _i_kind, "reshape": _i_reshape, "transfer": _i_transfer,
     "trim": lambda s: s.rstrip(), "adjustl": lambda s: s.lstrip(), "len": len, "len_trim": lambda s: len(s.rstrip()),
     "to_lower": lambda s: s.lower(),
     "spread": lambda a, dim, ncopies: np.repeat(np.expand_dims(np.asarray(a), int(dim) - 1), int(ncopies), axis=int(dim) - 1),
@@ -2496,6 +2592,19 @@ def _n_is_close(interp, a, b, rel_tol=None, abs_tol=None, equal_nan=None):
     return np.abs(a - b) <= np.maximum(rt * np.maximum(np.abs(a), np.abs(b)), at)
 
 
+def _n_c_associated(interp, p, q=None):
+    if q is None or q is ABSENT:
+        return p.obj is not None
+    return p.obj is not None and p.obj is q.obj
+
+
+def _n_c_f_pointer(interp, cptr, fptr, shape=None):
+    arr = cptr.obj
+    if shape is not None and shape is not ABSENT:
+        arr = arr.ravel(order="F")[:int(np.prod(shape))].reshape(tuple(int(x) for x in shape), order="F")
+    return ("__out__", {1: arr})
+
+
 def _n_type_error(interp, *a, **k):
     raise StopError(f"type_error{a}")
 
@@ -2515,5 +2624,5 @@ NATIVES = {
     "eigh": _n_eigh, "svd": _n_svd,
     # LAPACK (stdlib_linalg_lapack generic names)
     "lasr": _n_lasr, "lartg": _n_lartg, "trtrs": _n_trtrs, "geev": _n_geev, "trsen": _n_trsen, "schur": _n_schur,
-    "is_close": _n_is_close, "save_npy": _n_noop, "padr": lambda interp, s, n, *a: str(s).ljust(int(n)),
+    "is_close": _n_is_close, "save_npy": _n_noop, "c_associated": _n_c_associated, "c_f_pointer": _n_c_f_pointer, "padr": lambda interp, s, n, *a: str(s).ljust(int(n)),
 }

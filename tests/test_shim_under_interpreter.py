@@ -1,0 +1,306 @@
+"""The Fortran shim fortran/lightkrylov_cuda.f90, EXECUTED (it can be compiled nowhere: no Fortran compiler in this image or
+on the GPU box).  oracle/f90run.py interprets the reference's sources AND the shim; liblkb's C ABI is served on host memory by
+oracle/lkb_mock.py (Krylov entry points = the C oracle); the maintainer's one-line patches of INTEGRATION.md section 1
+(`if (lkb_try_X(<same arguments>)) return` at the top of each reference routine) are emulated by interpreter hooks.
+
+What is covered: the shim parses as Fortran; every try-function has the dummy list of the routine it patches; the reference's
+GENERIC entry points (`call arnoldi(A, X, H, info)`, `call gmres(...)`, ...) called with the shim's device types dispatch into
+the library and return what the oracle returns; the shim's type-bound procedures (lazy allocation, defined assignment, views)
+behave; device vectors in a layout the library cannot take fail loudly instead of silently corrupting the basis (a hazard this
+test found: the reference's generic Gram-Schmidt clones work vectors with `allocate(source=)`, a HANDLE copy for device types).
+What is not: the CUDA library behind the ABI (`-m gpu` tests).  Needs /root/reference: skipped on the GPU box.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import f90run, lk_oracle as lo, lkb_mock, ref_exec
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SHIM = os.path.join(os.path.dirname(HERE), "fortran", "lightkrylov_cuda.f90")
+import sys  # noqa: E402
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import ref_cases as rc  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not ref_exec.available(), reason="/root/reference not present on this box")
+
+SUF = {"s": "rsp", "d": "rdp", "c": "csp", "z": "cdp"}
+# reference routine -> try-function
+PAIRS = {
+    "arnoldi_{k}": "lkb_try_arnoldi_{k}", "lanczos_tridiagonalization_{k}": "lkb_try_lanczos_{k}",
+    "lanczos_bidiagonalization_{k}": "lkb_try_bidiagonalization_{k}", "qr_no_pivoting_{k}": "lkb_try_qr_{k}",
+    "qr_with_pivoting_{k}": "lkb_try_qr_pivoting_{k}",
+    "orthogonalize_vector_against_basis_{k}": "lkb_try_orthogonalize_vector_{k}",
+    "orthogonalize_basis_against_basis_{k}": "lkb_try_orthogonalize_basis_{k}",
+    "dgs_vector_against_basis_{k}": "lkb_try_dgs_vector_{k}", "dgs_basis_against_basis_{k}": "lkb_try_dgs_basis_{k}",
+    "gmres_{k}": "lkb_try_gmres_{k}", "fgmres_{k}": "lkb_try_fgmres_{k}", "cg_{k}": "lkb_try_cg_{k}",
+    "eigs_{k}": "lkb_try_eigs_{k}", "eighs_{k}": "lkb_try_eighs_{k}", "svds_{k}": "lkb_try_svds_{k}",
+    "kexpm_vec_{k}": "lkb_try_kexpm_vec_{k}", "kexpm_mat_{k}": "lkb_try_kexpm_mat_{k}",
+    "krylov_expta_{k}": "lkb_try_krylov_expta_{k}",
+}
+N = rc.N
+
+
+@pytest.fixture(scope="module")
+def shim():
+    it = ref_exec.interp()
+    if "lkb_start" not in it.p.procs:
+        it.p.load(SHIM)                              # the whole generated module goes through the Fortran front end
+        f90run.Interp(it.p)                          # module-level parameters / variables of the shim
+    stats = lkb_mock.install(it)
+    it.hooks = {}
+    for k in SUF.values():
+        for ref, tryf in PAIRS.items():
+            it.hooks[ref.format(k=k)] = tryf.format(k=k)
+    it.call("lkb_start", 0)
+    yield it, stats
+    it.hooks = {}
+
+
+def test_every_patch_point_exists_with_identical_dummies(shim):
+    it, _ = shim
+    assert len(it.hooks) == 4 * len(PAIRS)
+    for ref, tryf in it.hooks.items():
+        assert ref in it.p.procs, f"reference routine {ref} not found"
+        assert tryf in it.p.procs, f"shim function {tryf} not found"
+        assert it.p.procs[tryf].args == it.p.procs[ref].args, (ref, it.p.procs[tryf].args, it.p.procs[ref].args)
+        assert it.p.procs[tryf].result == "done"
+
+
+def _csr(A):
+    m, n = A.shape
+    return (np.arange(0, (m + 1) * n, n, dtype=np.int64), np.tile(np.arange(n, dtype=np.int32), m),
+            np.ascontiguousarray(A).ravel())
+
+
+def _op(it, kind, A, sym=False):
+    rp, cl, vl = _csr(A)
+    name = f"cuda_sym_csr_{SUF[kind]}" if sym and f"cuda_sym_csr_{SUF[kind]}" in it.p.procs else f"cuda_csr_{SUF[kind]}"
+    op, _ = it.call(name, A.shape[0], A.shape[1], rp, cl, vl)
+    return op
+
+
+def _basis(it, kind, ncols, first=None):
+    _, o = it.call(f"cuda_basis_allocate_{SUF[kind]}", None, N, N, 0, ncols)
+    X = o[0]
+    dev = X[0].f["basis"].obj.data
+    if first is not None:
+        first = np.asarray(first)
+        dev[:, :1 if first.ndim == 1 else first.shape[1]] = first.reshape(N, -1)
+    return X, dev
+
+
+def _tol(kind):
+    return 1e-12 if kind in "dz" else 5e-5
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+@pytest.mark.parametrize("kind", list("sdcz"))
+def test_generic_arnoldi_dispatches_and_matches_the_oracle(shim, kind):
+    it, stats = shim
+    kdim = 12
+    A = rc.general_matrix(kind, 1)
+    x0 = rc.unit(rc.pseudo((N,), 2, kind))
+    op = _op(it, kind, A)
+    X, dev = _basis(it, kind, kdim + 1, x0)
+    H = np.zeros((kdim + 1, kdim), dtype=A.dtype, order="F")
+    it.hook_hits = {}
+    before = dict(stats.calls)
+    _, o = it.call("arnoldi", op, X, H, 0, kstart=1, kend=kdim, transpose=False)          # the REFERENCE's generic name
+    assert it.hook_hits == {f"arnoldi_{SUF[kind]}": 1}
+    assert stats.calls["lkb_arnoldi"] == before.get("lkb_arnoldi", 0) + 1
+    assert stats.calls["lkb_basis_view"] - before.get("lkb_basis_view", 0) == 1           # one view made ...
+    assert stats.calls["lkb_basis_destroy"] - before.get("lkb_basis_destroy", 0) == 1     # ... and released
+    Ho = np.zeros_like(H)
+    Xo = np.zeros((N, kdim + 1), dtype=A.dtype, order="F")
+    Xo[:, 0] = x0
+    assert lo.arnoldi(lo.Op.dense(A), Xo, Ho) == int(o[3]) == 0
+    assert _rel(H, Ho) < _tol(kind) and _rel(dev, Xo) < _tol(kind)
+    # a section X(3:8) of the same basis is still a contiguous view: resume semantics through kstart / kend
+    H2 = np.zeros_like(H)
+    dev[:, 1:] = 0
+    it.call("arnoldi", op, X, H2, 0, kend=5)
+    it.call("arnoldi", op, X, H2, 0, kstart=6)
+    assert _rel(H2, Ho) < _tol(kind)
+
+
+@pytest.mark.parametrize("kind", list("dz"))
+def test_lanczos_bidiag_qr_dispatch(shim, kind):
+    it, stats = shim
+    kdim = 10
+    S = rc.sym_matrix(kind, 3)
+    x0 = rc.unit(rc.pseudo((N,), 52, kind))
+    k = SUF[kind]
+    # symmetric operator type: what lanczos requires
+    rp, cl, vl = _csr(S)
+    sym_ctor = [n for n in it.p.procs if n.startswith("cuda_sym_csr_") and n.endswith(k)]
+    if sym_ctor:
+        ops, _ = it.call(sym_ctor[0], N, N, rp, cl, vl)
+    else:                                           # no CSR constructor of the symmetric type: wrap the handle of a general one
+        gen = _op(it, kind, S)
+        ops = it.new_inst(f"cuda_sym_linop_{k}")
+        ops.f["h"] = gen.f["h"]
+    X, dev = _basis(it, kind, kdim + 1, x0)
+    T = np.zeros((kdim + 1, kdim), dtype=S.dtype, order="F")
+    it.hook_hits = {}
+    _, o = it.call("lanczos", ops, X, T, 0)
+    assert it.hook_hits == {f"lanczos_tridiagonalization_{k}": 1}
+    To = np.zeros_like(T)
+    Xo = np.zeros((N, kdim + 1), dtype=S.dtype, order="F")
+    Xo[:, 0] = x0
+    assert lo.lanczos(lo.Op.dense(S), Xo, To) == int(o[3])
+    assert _rel(T, To) < 1e-12 and _rel(dev, Xo) < 1e-11
+    # bidiagonalization
+    A = rc.general_matrix(kind, 61)
+    op = _op(it, kind, A)
+    U, udev = _basis(it, kind, kdim + 1, rc.unit(rc.pseudo((N,), 62, kind)))
+    V, vdev = _basis(it, kind, kdim + 1)
+    B = np.zeros((kdim + 1, kdim), dtype=A.dtype, order="F")
+    it.hook_hits = {}
+    _, o = it.call("bidiagonalization", op, U, V, B, 0)
+    assert it.hook_hits == {f"lanczos_bidiagonalization_{k}": 1}
+    Uo = np.zeros((N, kdim + 1), dtype=A.dtype, order="F")
+    Uo[:, 0] = rc.unit(rc.pseudo((N,), 62, kind))
+    Vo, Bo = np.zeros_like(Uo), np.zeros_like(B)
+    assert lo.bidiag(lo.Op.dense(A), Uo, Vo, Bo) == int(o[4])
+    assert _rel(B, Bo) < 1e-12 and _rel(udev, Uo) < 1e-11 and _rel(vdev, Vo) < 1e-11
+    # qr without and with pivoting on a section of a wider basis
+    M = rc.pseudo((N, 6), 71, kind)
+    Q, qdev = _basis(it, kind, 8)
+    qdev[:, 1:7] = M
+    R = np.zeros((6, 6), dtype=A.dtype, order="F")
+    it.hook_hits = {}
+    _, o = it.call("qr", Q[1:7], R, 0)
+    assert it.hook_hits == {f"qr_no_pivoting_{k}": 1}
+    Mo = M.copy(order="F")
+    info_o, Ro = lo.qr(Mo)
+    assert int(o[2]) == info_o and _rel(R, Ro) < 1e-12 and _rel(qdev[:, 1:7], Mo) < 1e-12
+    assert np.all(qdev[:, 0] == 0) and np.all(qdev[:, 7] == 0)             # the neighbours of the section are untouched
+    qdev[:, 1:7] = M
+    perm = np.zeros(6, dtype=np.int64)
+    _, o = it.call("qr", Q[1:7], R, perm, 0)
+    Mo = M.copy(order="F")
+    info_o, Ro, po = lo.qr_with_pivoting(Mo)
+    assert int(o[3]) == info_o and np.array_equal(perm - 1, po) and _rel(R, Ro) < 1e-12
+
+
+@pytest.mark.parametrize("kind", list("dz"))
+def test_type_bound_procedures_and_object_semantics(shim, kind):
+    """zero / rand / scal / axpby / dot / norm / add / sub / chsgn / get_size through the reference's abstract interface,
+    lazy allocation of an empty vector, defined assignment = deep copy, copy() into an intent(out) vector"""
+    it, stats = shim
+    k = SUF[kind]
+    a = rc.pseudo((N,), 301, kind)
+    b = rc.pseudo((N,), 302, kind)
+    X, dev = _basis(it, kind, 3, np.column_stack([a, b]))
+    sc = f90run.Scope(None)
+    w = it.new_inst(f"cuda_vector_{k}")                       # declared, never initialised: must be treated as empty
+    sc.vars.update(x=X, w=w, alpha=a.dtype.type(0.5), one=a.dtype.type(1.0))
+    assert not it.ev(f90run.parse_expr("w%is_live()"), sc)
+    assert it.ev(f90run.parse_expr("x(1)%get_size()"), sc) == N
+    assert abs(it.ev(f90run.parse_expr("x(1)%dot(x(2))"), sc) - np.vdot(a, b)) < 1e-12
+    assert abs(it.ev(f90run.parse_expr("x(2)%norm()"), sc) - np.linalg.norm(b)) < 1e-12
+
+    def run(stmt):
+        it.exec_stmt(("callsub", f90run.parse_expr(stmt), ("test", 0, stmt)), sc)
+    run("w%axpby(alpha, x(1), one)")                           # empty self: allocated like vec, beta ignored -> w = alpha a ?
+    created = stats.calls["lkb_vec_create"]
+    assert it.ev(f90run.parse_expr("w%is_live()"), sc) and w.f["owns"]
+    run("x(3)%axpby(one, x(1), alpha)")                        # x3 = a + 0.5 * 0
+    run("x(3)%add(x(2))")
+    run("x(3)%chsgn()")
+    run("x(3)%scal(alpha)")
+    assert _rel(dev[:, 2], -0.5 * (a + b)) < 1e-14
+    run("x(3)%sub(x(3))")
+    assert np.all(dev[:, 2] == 0)
+    # defined assignment: deep copy on the device, no new handle for a live target
+    it.assign(("call", ("name", "x"), [(None, ("lit", 3))]), X[0], sc)
+    assert np.array_equal(dev[:, 2], dev[:, 0]) and X[2].f["h"] is not X[0].f["h"] and X[2].f["col"] == 2
+    dev[:, 0] += 1
+    assert not np.array_equal(dev[:, 2], dev[:, 0])
+    # copy(out, from): `out` is intent(out) -- the handle must survive (no default initialisation of cuda_vector_*)
+    it.call("copy", X[2], X[1])
+    assert np.array_equal(dev[:, 2], dev[:, 1]) and X[2].f["col"] == 2 and stats.calls["lkb_vec_create"] == created
+    run("w%destroy()")
+    assert not it.ev(f90run.parse_expr("w%is_live()"), sc)
+
+
+@pytest.mark.parametrize("kind", list("dz"))
+def test_unsupported_layouts_fail_loudly(shim, kind):
+    """every second column of a basis is not a contiguous view: arnoldi's try-function declines, the reference's loop runs on
+    the type-bound procedures (matvec through the library) and reaches double_gram_schmidt_step, whose try-function must STOP:
+    falling through to the generic routine would zero X(1) through a handle copy"""
+    it, _ = shim
+    kdim = 4
+    A = rc.general_matrix(kind, 1)
+    op = _op(it, kind, A)
+    X, dev = _basis(it, kind, 2 * (kdim + 1), rc.unit(rc.pseudo((N,), 2, kind)))
+    x0 = dev[:, 0].copy()
+    H = np.zeros((kdim + 1, kdim), dtype=A.dtype, order="F")
+    with pytest.raises(f90run.StopError, match="columns of ONE device basis"):
+        it.call("arnoldi", op, X[::2], H, 0)
+    assert np.array_equal(dev[:, 0], x0)                       # nothing was corrupted before the stop
+
+
+@pytest.mark.parametrize("kind", list("dz"))
+def test_solvers_dispatch(shim, kind):
+    """gmres / fgmres / cg / eighs / svds / eigs / kexpm called by their reference names with device types"""
+    it, stats = shim
+    k = SUF[kind]
+    prec = "dp"
+    # gmres with options and metadata objects of the reference's own types
+    A = rc.well_conditioned(kind)
+    op = _op(it, kind, A)
+    bx, dev = _basis(it, kind, 2, rc.unit(rc.pseudo((N,), 202, kind)))
+    opts = it.new_inst(f"gmres_{prec}_opts")
+    opts.f["kdim"], opts.f["maxiter"] = 10, 20
+    meta = it.new_inst(f"gmres_{prec}_metadata")
+    it.hook_hits = {}
+    _, o = it.call("gmres", op, bx[0], bx[1], 0, options=opts, meta=meta)
+    assert it.hook_hits == {f"gmres_{k}": 1}
+    xo = np.zeros(N, dtype=A.dtype)
+    info_o, mo = lo.gmres(lo.Op.dense(A), dev[:, 0].copy(), xo, kdim=10, maxiter=20)
+    assert int(o[3]) == info_o > 10 and _rel(dev[:, 1], xo) < 1e-12
+    assert (meta.f["n_iter"], meta.f["n_inner"], meta.f["n_outer"]) == (mo["n_iter"], mo["n_inner"], mo["n_outer"])
+    assert bool(meta.f["converged"]) and np.allclose(meta.f["res"], mo["res"], rtol=1e-6, atol=0)     # tail entries ~ 1e-8: recomputed residual norms
+    # cg on the symmetric operator type
+    S = rc.sym_matrix(kind, 211, shift=0.1)
+    gen = _op(it, kind, S)
+    ops = it.new_inst(f"cuda_sym_linop_{k}")
+    ops.f["h"] = gen.f["h"]
+    dev[:, 1] = 0
+    cmeta = it.new_inst(f"cg_{prec}_metadata")
+    it.hook_hits = {}
+    _, o = it.call("cg", ops, bx[0], bx[1], 0, meta=cmeta)
+    assert it.hook_hits == {f"cg_{k}": 1}
+    xo = np.zeros(N, dtype=A.dtype)
+    info_o, mo = lo.cg(lo.Op.dense(S), dev[:, 0].copy(), xo)
+    assert int(o[3]) == info_o > 0 and _rel(dev[:, 1], xo) < 1e-12 and cmeta.f["n_iter"] == mo["n_iter"]
+    # eighs: X(:) is intent(out) in the reference -- the views must survive, eigvals / residuals are allocated by the shim
+    S2 = rc.sym_matrix(kind, 221)
+    gen2 = _op(it, kind, S2)
+    ops2 = it.new_inst(f"cuda_sym_linop_{k}")
+    ops2.f["h"] = gen2.f["h"]
+    nev = 3
+    Xe, edev = _basis(it, kind, nev)
+    x0h = rc.unit(rc.pseudo((N,), 222, kind))
+    x0v, x0dev = _basis(it, kind, 1, x0h)
+    it.hook_hits = {}
+    _, o = it.call("eighs", ops2, Xe, None, None, 0, x0=x0v[0], kdim=64, tolerance=np.float64(1e-9))
+    assert it.hook_hits == {f"eighs_{k}": 1}
+    evo, reso, Xo, ko = lo.eighs(lo.Op.dense(S2), N, nev, x0h, kdim=64, tolerance=1e-9)
+    assert int(o[4]) == ko and _rel(np.asarray(o[2]), evo) < 1e-12 and _rel(np.abs(edev), np.abs(Xo)) < 1e-9
+    assert np.asarray(o[3]).shape == (nev,) and Xe[0].f["col"] == 0 and Xe[2].f["col"] == 2
+    # kexpm (vector)
+    Ak = rc.general_matrix(kind, 241)
+    opk = _op(it, kind, Ak)
+    cb, cdev = _basis(it, kind, 2, rc.unit(rc.pseudo((N,), 242, kind)))
+    it.hook_hits = {}
+    _, o = it.call("kexpm", cb[1], opk, cb[0], np.float64(0.1), np.float64(1e-10), 0, kdim=40)
+    assert it.hook_hits == {f"kexpm_vec_{k}": 1}
+    co, info_o = lo.kexpm_vec(lo.Op.dense(Ak), cdev[:, 0].copy(), 0.1, 1e-10, kdim=40)
+    assert int(o[5]) == info_o and _rel(cdev[:, 1], co) < 1e-12
