@@ -9,17 +9,26 @@
  * this image (no Fortran compiler, fpm, fypp or stdlib), so there
  * is no oracle/_ref.
  *
- * PARITY UNPINNED against an execution of the reference: the reference holds no golden
- * vectors or fixtures for this path (its tests are property / known-answer checks on
- * unseeded random inputs) and it cannot be run here or on the GPU box (both probed:
- * no gfortran / flang / ifx / nvfortran / fpm / fypp).  What pins the oracle instead:
- * (1) the reference's own property / known-answer assertions (test/TestKrylov.fypp:194-514,
- * test/TestIterativeSolvers.fypp:59-725), re-run against this code by
- * tests/test_oracle_pins.py; (2) an independent evaluation of the Hessenberg entries in
- * 80-bit extended precision (test_arnoldi_entries_match_extended_precision); (3) line-by-
- * line citation of the reference sources in lko_body.inc; (4) a second, independent numpy
- * restatement written from the Fortran sources (tests/test_oracle_second_opinion.py) that
- * must agree with this code entry by entry.
+ * PINNING.  The reference holds no golden vectors or fixtures for this path (its tests are
+ * property / known-answer checks on unseeded random inputs) and it cannot be COMPILED here or
+ * on the GPU box (both probed: no gfortran / flang / ifx / nvfortran / fpm / fypp).  Since
+ * round 2 its source text is EXECUTED instead: oracle/f90run.py interprets the reference's
+ * pre-expanded .f90 files (modules, submodules, type-bound procedures, generics) on the
+ * reference's own TestUtils vector / operator types; tests/golden/ref_krylov.npz and
+ * ref_solvers.npz hold what its arnoldi / lanczos / bidiagonalization / qr / Gram-Schmidt /
+ * gmres / fgmres / cg / eigs / eighs / svds / kexpm code computed (generating script
+ * tests/golden/make_ref_golden.py), and tests/test_ref_golden.py requires THIS code to
+ * reproduce them in all four kinds (fp64 1e-12, fp32 5e-5; info, pivots, iteration counts
+ * exact).  The interpreter itself is qualified by the reference's own 112 unit tests
+ * passing under it (tests/test_reference_suite.py).  What that leaves open: it is an
+ * interpreter, not a compiled build -- intrinsics, stdlib BLAS / LAPACK / expm are supplied
+ * by numpy / scipy, so summation order inside a dot product is numpy's, not gfortran's.
+ * Earlier pins stay in place: (1) the reference's own property / known-answer assertions
+ * (test/TestKrylov.fypp:194-514, test/TestIterativeSolvers.fypp:59-725) re-run against this
+ * code by tests/test_oracle_pins.py; (2) an independent evaluation of the Hessenberg entries
+ * in 80-bit extended precision; (3) line-by-line citation of the reference in lko_body.inc;
+ * (4) a second numpy restatement written from the Fortran sources
+ * (tests/test_oracle_second_opinion.py) that must agree with this code entry by entry.
  *
  * Build:  make -C oracle      (gcc -O3 -march=native -fopenmp -shared)
  */

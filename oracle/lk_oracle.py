@@ -15,9 +15,12 @@ on top of the C primitives, following
   src/IterativeSolvers/SVDS/svd_solvers.fypp:28-121
   src/Utilities/submodule_utility_functions.fypp:55-117, 169-204
 
-PARITY UNPINNED against an execution of the reference (no Fortran toolchain here or on the GPU box, no golden vectors
-in the reference): pinned by the reference's own property / known-answer assertions and by an independent
-extended-precision evaluation instead (tests/test_oracle_pins.py); see the header of lk_oracle.c and DESIGN.md section 4.
+PINNING: no Fortran toolchain exists here or on the GPU box and the reference holds no golden vectors, so the reference cannot
+be COMPILED.  Its source text is EXECUTED instead, by the interpreter oracle/f90run.py: tests/golden/ref_krylov.npz and
+ref_solvers.npz are outputs of the reference's own arnoldi / lanczos / bidiagonalization / qr / Gram-Schmidt / gmres / fgmres /
+cg / eigs / eighs / svds / kexpm code, and tests/test_ref_golden.py requires this module to reproduce them (entries, bases, pivots,
+info, iteration counts, residual histories; four kinds).  Still not a compiled build of the reference: see the header of
+lk_oracle.c and DESIGN.md section 4 for what that leaves open.
 """
 from __future__ import annotations
 

@@ -1,8 +1,9 @@
 """A SECOND, independent restatement of the reference's step loops, used only to cross-check the C oracle (oracle/).
 
 The C oracle (oracle/lk_oracle.c + lko_body.inc) is what every GPU parity test compares against, and nothing in this
-environment can execute the Fortran reference (no compiler here or on the GPU box: parity is unpinned against an execution
-of the reference).  To reduce the risk that the oracle and the product share one misreading of the
+environment can COMPILE the Fortran reference (no compiler here or on the GPU box; since the end of round 2 its sources are
+executed by the interpreter oracle/f90run.py instead -- tests/test_ref_golden.py, DESIGN.md section 4 -- this file predates
+that and stays as a further, independent check).  To reduce the risk that the oracle and the product share one misreading of the
 Fortran, this file restates the same routines a second time -- in plain numpy, written directly from the reference sources
 cited below, sharing NO code with oracle/ -- and requires the two restatements to agree entry by entry:
 
