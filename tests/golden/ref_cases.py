@@ -305,13 +305,80 @@ def kexpm_block(kind, be):
     return {"info": info, "C": be.data(Cb)}
 
 
+# ---- the north-star operator family (BASELINE configs C2 / C3 / C4 at reduced size): constant-coefficient stencils written as
+# USER code against the reference's abstract types (tests/golden/user_stencil.f90), real(dp) only
+POISSON2D = (4.0, -1.0, -1.0, -1.0, -1.0)
+CONVDIFF2D = (6.0, -1.3, -0.7, -1.2, -0.8)
+POISSON3D = (6.0, -1.0, -1.0, -1.0, -1.0, -1.0, -1.0)
+CONVDIFF3D = (6.0, -1.4, -0.6, -1.3, -0.7, -1.2, -0.8)
+
+
+def stencil2d_arnoldi(kind, be):
+    """C2: arnoldi on the 5-point Poisson operator (48 x 40 here; 4096 x 4096 in the bench)"""
+    dims, kdim = (48, 40), 32
+    n = dims[0] * dims[1]
+    A = be.stencil(kind, dims, POISSON2D)
+    X = be.basis_n(kind, n, kdim + 1, unit(pseudo((n,), 402, kind)))
+    H = np.zeros((kdim + 1, kdim), dtype=DTYPE[kind], order="F")
+    info = be.arnoldi(A, X, H)
+    return {"info": info, "H": H, "X": be.data(X), "matvecs": be.counter(A)}
+
+
+def stencil2d_gmres(kind, be):
+    """C2 (gmres row): restarted gmres on a non-symmetric 5-point convection-diffusion stencil"""
+    dims = (40, 36)
+    n = dims[0] * dims[1]
+    A = be.stencil(kind, dims, CONVDIFF2D)
+    b = be.basis_n(kind, n, 1, unit(pseudo((n,), 412, kind)))
+    x = be.basis_n(kind, n, 1)
+    info, meta = be.gmres(A, b, x, kdim=15, maxiter=40)
+    return {"info": info, "x": be.data(x)[:, 0].copy(), "res": np.asarray(meta["res"], dtype=np.float64),
+            "n_iter": meta["n_iter"], "n_inner": meta["n_inner"], "n_outer": meta["n_outer"]}
+
+
+def stencil3d_lanczos(kind, be):
+    """C4: lanczos on the 7-point Poisson operator"""
+    dims, kdim = (12, 10, 8), 24
+    n = dims[0] * dims[1] * dims[2]
+    A = be.stencil(kind, dims, POISSON3D, sym=True)
+    X = be.basis_n(kind, n, kdim + 1, unit(pseudo((n,), 422, kind)))
+    T = np.zeros((kdim + 1, kdim), dtype=DTYPE[kind], order="F")
+    info = be.lanczos(A, X, T)
+    return {"info": info, "T": T, "X": be.data(X)}
+
+
+def stencil3d_cg(kind, be):
+    """C4 (cg row)"""
+    dims = (12, 10, 8)
+    n = dims[0] * dims[1] * dims[2]
+    A = be.stencil(kind, dims, POISSON3D, sym=True)
+    b = be.basis_n(kind, n, 1, unit(pseudo((n,), 432, kind)))
+    x = be.basis_n(kind, n, 1)
+    info, meta = be.cg(A, b, x, maxiter=200)
+    return {"info": info, "x": be.data(x)[:, 0].copy(), "res": np.asarray(meta["res"], dtype=np.float64),
+            "n_iter": meta["n_iter"]}
+
+
+def stencil3d_eigs(kind, be):
+    """C3: eigs (Krylov-Schur restarts) on a non-symmetric 7-point stencil"""
+    dims, nev = (8, 7, 6), 2
+    n = dims[0] * dims[1] * dims[2]
+    A = be.stencil(kind, dims, CONVDIFF3D)
+    ev, res, X, info = be.eigs(A, nev, unit(pseudo((n,), 442, kind)), kdim=20, tolerance=1e-8, n=n)
+    return {"info": info, "eigvals": np.asarray(ev, dtype=np.complex128), "X": X}
+
+
+STENCIL_CASES = {"stencil2d_arnoldi": stencil2d_arnoldi, "stencil2d_gmres": stencil2d_gmres,
+                 "stencil3d_lanczos": stencil3d_lanczos, "stencil3d_cg": stencil3d_cg, "stencil3d_eigs": stencil3d_eigs}
+
 SOLVER_CASES = {"eighs_write_intermediate": eighs_write_intermediate, "svds_write_intermediate": svds_write_intermediate,
                 "fgmres_solve": fgmres_solve, "kexpm_block": kexpm_block, "eigs_solve": eigs_solve, "gmres_solve": gmres_solve, "cg_solve": cg_solve, "eighs_solve": eighs_solve, "svds_solve": svds_solve,
                 "kexpm_solve": kexpm_solve}
+SOLVER_CASES.update(STENCIL_CASES)
 
 
 def applies(name, kind):
-    return True
+    return kind == "d" if name in STENCIL_CASES else True
 
 
 # ------------------------------------------------------------------------------------------------------------------ backends
@@ -332,6 +399,31 @@ class RefBackend:
 
     def data(self, X):
         return self.rx.basis_data(X)
+
+    def stencil(self, kind, dims, coef, sym=False):
+        """user-side operator type of tests/golden/user_stencil.f90 (real(dp))"""
+        it = self.rx.interp()
+        if "stencil_apply_rdp" not in it.p.procs:
+            import os
+            from oracle import f90run
+            it.p.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "user_stencil.f90"))
+            f90run.Interp(it.p)
+        op = it.new_inst("stencil_sym_linop_rdp" if sym else "stencil_linop_rdp")
+        d = list(dims) + [1] * (3 - len(dims))
+        op.f["nx"], op.f["ny"], op.f["nz"] = d
+        op.f["coef"][:len(coef)] = coef
+        return op
+
+    def basis_n(self, kind, n, ncols, first=None):
+        """the reference's own dense_vector_rdp (AbstractVectors.fypp:420-470), any length"""
+        X = np.empty(ncols, dtype=object)
+        for i in range(ncols):
+            X[i] = self.rx.call("dense_vector", np.zeros(n, dtype=DTYPE[kind]))[0]
+        if first is not None:
+            first = np.asarray(first).reshape(n, -1)
+            for i in range(first.shape[1]):
+                X[i].f["data"][...] = first[:, i]
+        return X
 
     def counter(self, A):
         return int(A.f["matvec_counter"])
@@ -422,11 +514,15 @@ class RefBackend:
                             write_intermediate=write_intermediate)
         return np.array(o[2]), np.array(o[3]), self.data(X), int(o[4])
 
-    def eigs(self, A, nev, x0, kdim, tolerance):
+    def eigs(self, A, nev, x0, kdim, tolerance, n=None):
         kind = {np.dtype(np.float32): "s", np.dtype(np.float64): "d", np.dtype(np.complex64): "c",
                 np.dtype(np.complex128): "z"}[x0.dtype]
-        X = self.basis(kind, nev)
-        x0v = self.rx.vector(kind, x0)
+        if n is None:
+            X = self.basis(kind, nev)
+            x0v = self.rx.vector(kind, x0)
+        else:
+            X = self.basis_n(kind, n, nev)
+            x0v = self.basis_n(kind, n, 1, x0)[0]
         _, o = self.rx.call("eigs", A, X, None, None, 0, x0=x0v, kdim=kdim, tolerance=_real(kind)(tolerance),
                             write_intermediate=False)
         return np.array(o[2]), np.array(o[3]), self.data(X), int(o[4])
@@ -475,6 +571,16 @@ class OracleBackend:
     def data(self, X):
         return X
 
+    def stencil(self, kind, dims, coef, sym=False):
+        return self.lo.Op.stencil(kind, tuple(dims), tuple(float(c) for c in coef))
+
+    def basis_n(self, kind, n, ncols, first=None):
+        X = np.zeros((n, ncols), dtype=DTYPE[kind], order="F")
+        if first is not None:
+            first = np.asarray(first).reshape(n, -1)
+            X[:, :first.shape[1]] = first
+        return X
+
     def counter(self, A):
         return int(A.n_matvec)
 
@@ -512,8 +618,8 @@ class OracleBackend:
         ev, res, X, k = self.lo.eighs(A, N, nev, x0, kdim=kdim, tolerance=tolerance, write_intermediate=write_intermediate)
         return ev, res, X, k
 
-    def eigs(self, A, nev, x0, kdim, tolerance):
-        ev, res, X, niter = self.lo.eigs(A, N, nev, x0, kdim=kdim, tolerance=tolerance)
+    def eigs(self, A, nev, x0, kdim, tolerance, n=None):
+        ev, res, X, niter = self.lo.eigs(A, N if n is None else n, nev, x0, kdim=kdim, tolerance=tolerance)
         return ev, res, X, niter
 
     def svds(self, A, nsv, u0, kdim, tolerance, write_intermediate=False):
