@@ -429,7 +429,7 @@ def lkb_eigs(interp, A, X, nev, eigvals, residuals, info, x0, kdim, tolerance, t
                                  tolerance=None if tolerance < 0 else float(tolerance), trans=bool(int(transpose)),
                                  write_intermediate=bool(Stats.options.get("write_intermediate", 0)))
     xb.data[:, :ne] = Xo
-    out = eigvals.obj.reshape(-1)
+    out = eigvals.obj.reshape(-1, order="F")                  # (2, nev) column-major = interleaved (re, im) pairs
     out[0:2 * ne:2], out[1:2 * ne:2] = np.real(ev), np.imag(ev)
     residuals.obj[:ne] = res
     return ("__out__", {5: int(niter)}, LKB_OK)

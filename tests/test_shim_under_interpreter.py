@@ -304,3 +304,44 @@ def test_solvers_dispatch(shim, kind):
     assert it.hook_hits == {f"kexpm_vec_{k}": 1}
     co, info_o = lo.kexpm_vec(lo.Op.dense(Ak), cdev[:, 0].copy(), 0.1, 1e-10, kdim=40)
     assert int(o[5]) == info_o and _rel(cdev[:, 1], co) < 1e-12
+
+
+@pytest.mark.parametrize("kind", list("dz"))
+def test_eigs_svds_dispatch(shim, kind):
+    """eigs (complex eigenvalues allocated by the shim, write_intermediate passed through as a context option) and svds"""
+    it, stats = shim
+    k = SUF[kind]
+    rt = np.float64
+    # svds: U(:) and V(:) are intent(out) views; S and residuals are allocated by the shim in the kind's precision
+    A = rc.general_matrix(kind, 231)
+    op = _op(it, kind, A)
+    nsv = 3
+    U, udev = _basis(it, kind, nsv)
+    V, vdev = _basis(it, kind, nsv)
+    u0h = rc.unit(rc.pseudo((N,), 232, kind))
+    u0, _ = _basis(it, kind, 1, u0h)
+    it.hook_hits = {}
+    _, o = it.call("svds", op, U, None, V, None, 0, u0=u0[0], kdim=64, tolerance=rt(1e-9), write_intermediate=False)
+    assert it.hook_hits == {f"svds_{k}": 1}
+    So, reso, Uo, Vo, ko = lo.svds(lo.Op.dense(A), nsv, u0h, kdim=64, tolerance=1e-9)
+    assert int(o[5]) == ko and _rel(np.asarray(o[2]), So) < 1e-12
+    assert _rel(np.abs(udev), np.abs(Uo)) < 1e-9 and _rel(np.abs(vdev), np.abs(Vo)) < 1e-9
+    assert np.asarray(o[2]).dtype == np.float64 and np.asarray(o[4]).shape == (nsv,)
+    assert stats.options.get("write_intermediate") == 0
+    # eigs
+    Ad = rc.dominant_matrix(kind)
+    opd = _op(it, kind, Ad)
+    nev = 4
+    X, xdev = _basis(it, kind, nev)
+    x0h = rc.unit(rc.pseudo((N,), 252, kind))
+    x0, _ = _basis(it, kind, 1, x0h)
+    it.hook_hits = {}
+    _, o = it.call("eigs", opd, X, None, None, 0, x0=x0[0], kdim=24, tolerance=rt(1e-9), write_intermediate=False)
+    assert it.hook_hits == {f"eigs_{k}": 1}
+    evo, reso, Xo, niter = lo.eigs(lo.Op.dense(Ad), N, nev, x0h, kdim=24, tolerance=1e-9)
+    ev = np.asarray(o[2])
+    assert int(o[4]) == niter and ev.dtype == np.complex128 and _rel(ev, evo) < 1e-12
+    assert _rel(np.abs(xdev), np.abs(Xo)) < 1e-9
+    # the reference's default for eigs is write_intermediate = .true. (IterativeSolvers.fypp:1025): absent -> option set
+    it.call("eigs", opd, X, None, None, 0, x0=x0[0], kdim=24, tolerance=rt(1e-9))
+    assert stats.options.get("write_intermediate") == 1
