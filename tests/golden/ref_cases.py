@@ -179,7 +179,32 @@ def dgs_basis(kind, be):
     return {"info": info, "beta": beta, "Y": be.data(Y)}
 
 
+def dgs_zero_vector(kind, be):
+    """orthogonalize_against_basis flags a vector whose norm is below atol (info = 1) -- the `info` of the Gram-Schmidt passes"""
+    j = 4
+    X = be.basis(kind, j, orthonormal_block(kind, j, 121))
+    y = be.basis(kind, 1)                                   # the zero vector
+    info, beta = be.dgs_vec(y, X)
+    return {"info": info, "beta": beta, "y": be.data(y)[:, 0].copy()}
+
+
+def qr_pivoting_deficient(kind, be):
+    """exact rank deficiency (cf. test_pivoting_qr_exact_rank_deficiency, test/TestKrylov.fypp): columns 3 and 6 of 6 are zero:
+    the pivoting order, info and the leading block of R are defined by the data; the refilled columns are random"""
+    p = 6
+    M = pseudo((N, p), 131, kind) * (1.0 + np.arange(p))[None, :].astype(DTYPE[kind])
+    M[:, 2] = 0
+    M[:, 5] = 0
+    Q = be.basis(kind, p, M.astype(DTYPE[kind]))
+    info, R, perm = be.qr_pivoting(Q)
+    Qd = be.data(Q)
+    G = Qd.conj().T @ Qd
+    return {"info": info, "R_lead": R[:4, :4].copy(), "perm_lead": np.asarray(perm, dtype=np.int64)[:4].copy(),
+            "Q_lead": Qd[:, :4].copy(), "abs_orth_err": np.array(np.abs(G - np.eye(p)).max(), dtype=np.float64)}
+
+
 CASES = {
+    "dgs_zero_vector": dgs_zero_vector, "qr_pivoting_deficient": qr_pivoting_deficient,
     "arnoldi_full": arnoldi_full, "arnoldi_transpose": arnoldi_transpose, "arnoldi_block": arnoldi_block,
     "arnoldi_resume": arnoldi_resume, "arnoldi_breakdown": arnoldi_breakdown, "lanczos_full": lanczos_full,
     "bidiag_full": bidiag_full, "qr_full": qr_full, "qr_deficient": qr_deficient, "qr_pivoting": qr_pivoting,
@@ -296,6 +321,18 @@ def fgmres_solve(kind, be):
             "n_iter": meta["n_iter"], "n_inner": meta["n_inner"], "n_outer": meta["n_outer"]}
 
 
+def kexpm_breakdown(kind, be):
+    """the Arnoldi factorisation inside kexpm breaks down (invariant subspace of dimension 4): literal `info` and result"""
+    m = 4
+    A = be.linop(kind, block_triangular(kind, m, seed=281))
+    b0 = pseudo((N,), 282, kind)
+    b0[m:] = 0
+    b = be.basis(kind, 1, unit(b0))
+    c = be.basis(kind, 1)
+    info = be.kexpm(c, A, b, tau=0.2, tol=1e-4 if kind in "sc" else 1e-10, kdim=20)
+    return {"info": info, "c": be.data(c)[:, 0].copy()}
+
+
 def kexpm_block(kind, be):
     p = 3
     A = be.linop(kind, general_matrix(kind, 271))
@@ -372,7 +409,7 @@ STENCIL_CASES = {"stencil2d_arnoldi": stencil2d_arnoldi, "stencil2d_gmres": sten
                  "stencil3d_lanczos": stencil3d_lanczos, "stencil3d_cg": stencil3d_cg, "stencil3d_eigs": stencil3d_eigs}
 
 SOLVER_CASES = {"eighs_write_intermediate": eighs_write_intermediate, "svds_write_intermediate": svds_write_intermediate,
-                "fgmres_solve": fgmres_solve, "kexpm_block": kexpm_block, "eigs_solve": eigs_solve, "gmres_solve": gmres_solve, "cg_solve": cg_solve, "eighs_solve": eighs_solve, "svds_solve": svds_solve,
+                "fgmres_solve": fgmres_solve, "kexpm_block": kexpm_block, "kexpm_breakdown": kexpm_breakdown, "eigs_solve": eigs_solve, "gmres_solve": gmres_solve, "cg_solve": cg_solve, "eighs_solve": eighs_solve, "svds_solve": svds_solve,
                 "kexpm_solve": kexpm_solve}
 SOLVER_CASES.update(STENCIL_CASES)
 

@@ -285,7 +285,7 @@ class ProductBackend:
 
 
 GPU_CASES = ["arnoldi_full", "arnoldi_transpose", "arnoldi_block", "arnoldi_resume", "arnoldi_breakdown", "lanczos_full",
-             "bidiag_full", "qr_full", "qr_pivoting", "stencil2d_arnoldi", "stencil3d_lanczos"]
+             "bidiag_full", "qr_full", "qr_pivoting", "qr_pivoting_deficient", "stencil2d_arnoldi", "stencil3d_lanczos"]
 
 
 @pytest.fixture(scope="module")
