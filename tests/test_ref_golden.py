@@ -41,7 +41,7 @@ def _compare(got: dict, fx, prefix: str, tol: float):
             assert np.array_equal(have, want), (full, have.tolist(), want.tolist())
         else:
             assert have.shape == want.shape, (full, have.shape, want.shape)
-            err = float(np.abs(have - want).max() / max(np.abs(want).max(), 1e-300))
+            err = float(np.abs(have - want).max()) / max(float(np.abs(want).max()), 1e-300)
             assert err < tol, (full, err)
 
 
