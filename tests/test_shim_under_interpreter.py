@@ -6,8 +6,9 @@ oracle/lkb_mock.py (Krylov entry points = the C oracle); the maintainer's one-li
 What is covered: the shim parses as Fortran; every try-function has the dummy list of the routine it patches; the reference's
 GENERIC entry points (`call arnoldi(A, X, H, info)`, `call gmres(...)`, ...) called with the shim's device types dispatch into
 the library and return what the oracle returns; the shim's type-bound procedures (lazy allocation, defined assignment, views)
-behave; device vectors in a layout the library cannot take fail loudly instead of silently corrupting the basis (a hazard this
-test found: the reference's generic Gram-Schmidt clones work vectors with `allocate(source=)`, a HANDLE copy for device types).
+behave; device vectors in a layout the library cannot take (owning vectors, strided columns) go through the type-bound
+procedures with the oracle's result instead of silently corrupting the basis (a hazard this test found: the reference's generic
+Gram-Schmidt clones work vectors with `allocate(source=)`, a HANDLE copy for device types, so the try-functions must not decline).
 What is not: the CUDA library behind the ABI (`-m gpu` tests).  Needs /root/reference: skipped on the GPU box.
 """
 import os
@@ -229,21 +230,52 @@ def test_type_bound_procedures_and_object_semantics(shim, kind):
     assert not it.ev(f90run.parse_expr("w%is_live()"), sc)
 
 
-@pytest.mark.parametrize("kind", list("dz"))
-def test_unsupported_layouts_fail_loudly(shim, kind):
-    """every second column of a basis is not a contiguous view: arnoldi's try-function declines, the reference's loop runs on
-    the type-bound procedures (matvec through the library) and reaches double_gram_schmidt_step, whose try-function must STOP:
-    falling through to the generic routine would zero X(1) through a handle copy"""
-    it, _ = shim
-    kdim = 4
+@pytest.mark.parametrize("kind", list("sdcz"))
+def test_other_layouts_take_the_type_bound_path(shim, kind):
+    """Every second column of a basis is not a contiguous view: arnoldi's try-function declines, the reference's own loop runs
+    (matvec / scal / copy through the type-bound procedures) and reaches double_gram_schmidt_step.  Its try-function must NOT
+    decline -- the reference's generic routine would clone its work vector with allocate(source=), a HANDLE copy, and zero X(1) --
+    it runs the same algorithm through the type-bound procedures.  Same H and basis as the oracle, untouched odd columns."""
+    it, stats = shim
+    k = SUF[kind]
+    kdim = 8
     A = rc.general_matrix(kind, 1)
     op = _op(it, kind, A)
-    X, dev = _basis(it, kind, 2 * (kdim + 1), rc.unit(rc.pseudo((N,), 2, kind)))
-    x0 = dev[:, 0].copy()
+    x0 = rc.unit(rc.pseudo((N,), 2, kind))
+    X, dev = _basis(it, kind, 2 * (kdim + 1), x0)
     H = np.zeros((kdim + 1, kdim), dtype=A.dtype, order="F")
-    with pytest.raises(f90run.StopError, match="columns of ONE device basis"):
-        it.call("arnoldi", op, X[::2], H, 0)
-    assert np.array_equal(dev[:, 0], x0)                       # nothing was corrupted before the stop
+    it.hook_hits = {}
+    created, destroyed = stats.calls.get("lkb_vec_create", 0), stats.calls.get("lkb_vec_destroy", 0)
+    _, o = it.call("arnoldi", op, X[::2], H, 0)
+    assert f"arnoldi_{k}" not in it.hook_hits                       # declined: the reference's loop ran
+    assert it.hook_hits.get(f"dgs_basis_against_basis_{k}") == kdim and it.hook_hits.get(f"qr_no_pivoting_{k}") == kdim
+    Ho = np.zeros_like(H)
+    Xo = np.zeros((N, kdim + 1), dtype=A.dtype, order="F")
+    Xo[:, 0] = x0
+    assert lo.arnoldi(lo.Op.dense(A), Xo, Ho) == int(o[3]) == 0
+    assert _rel(H, Ho) < _tol(kind) and _rel(dev[:, ::2], Xo) < 10 * _tol(kind)
+    assert np.all(dev[:, 1::2] == 0)
+    # one work vector per Gram-Schmidt call on the type-bound path (steps 2..kdim; X(:1) alone is a contiguous view), released again
+    assert stats.calls["lkb_vec_create"] - created == stats.calls["lkb_vec_destroy"] - destroyed == kdim - 1
+    # an OWNING vector (not a column of any basis) against a contiguous basis, with the orthonormality check switched on
+    Q, qdev = _basis(it, kind, 5, rc.orthonormal_block(kind, 5, 101))
+    y = it.new_inst(f"cuda_vector_{k}")
+    it.call(f"cuda_init_{k}", y, N)
+    yh = rc.pseudo((N,), 102, kind)
+    y.f["h"].obj.data[...] = yh
+    beta = np.zeros(5, dtype=A.dtype)
+    _, o = it.call("double_gram_schmidt_step", y, Q, 0, beta=beta)            # if_chk_orthonormal absent = .true.
+    yo = yh.copy()
+    info_o, bo = lo.dgs_vec(yo, np.asfortranarray(qdev.copy()), 5)
+    assert int(o[2]) == info_o == 0 and _rel(beta, bo) < _tol(kind) and _rel(y.f["h"].obj.data, yo) < _tol(kind)
+    # ... and the check fires on a basis that is not orthonormal (the reference stops with the same message)
+    qdev[:, 1] = qdev[:, 0]
+    with pytest.raises(f90run.StopError, match="not orthonormal"):
+        it.call("double_gram_schmidt_step", y, Q, 0)
+    # an EMPTY vector cannot be orthogonalised: loud stop, not a silent fall-through to the generic routine
+    empty = it.new_inst(f"cuda_vector_{k}")
+    with pytest.raises(f90run.StopError, match="before it was given a size"):
+        it.call("double_gram_schmidt_step", empty, Q, 0, if_chk_orthonormal=False)
 
 
 @pytest.mark.parametrize("kind", list("dz"))
