@@ -787,7 +787,6 @@ class Program:
     def _parse_proc(self, lines, i, module, interface_only, host=None):
         no, s = lines[i]
         toks = tokenize(s)
-        names = [t[1] for t in toks if t[0] == "name"]
         prefixes, result_ts = [], None
         j = 0
         while toks[j][1] not in ("subroutine", "function", "procedure"):
@@ -2185,8 +2184,7 @@ def _i_size(a, dim=None):
 
 
 def _i_abs(a):
-    r = np.abs(a)
-    return r
+    return np.abs(a)
 
 
 def _i_sqrt(a):
@@ -2276,7 +2274,8 @@ def _i_mod(a, p):
 
 
 def _i_matmul(a, b):
-    return np.asfortranarray(a @ b) if isinstance(a @ b, np.ndarray) and (a @ b).ndim == 2 else a @ b
+    r = a @ b
+    return np.asfortranarray(r) if isinstance(r, np.ndarray) and r.ndim == 2 else r
 
 
 def _i_transfer(source, mold, size=None):
@@ -2356,7 +2355,7 @@ def _n_axpy(interp, n, a, x, incx, y, incy):
 
 
 def _n_dot(interp, n, x, incx, y, incy):
-    return (np.dot(x[:n], y[:n])).astype(x.dtype)[()] if isinstance(np.dot(x[:n], y[:n]), np.ndarray) else x.dtype.type(np.dot(x[:n], y[:n]))
+    return x.dtype.type(np.dot(x[:n], y[:n]))
 
 
 def _n_dotc(interp, n, x, incx, y, incy):
@@ -2563,7 +2562,6 @@ def _n_sort_index(interp, array, index, work=None, iwork=None, reverse=None):
     rev = reverse is not None and reverse is not ABSENT and bool(reverse)
     key = np.array(array)
     if rev:
-        order = np.argsort(-key, kind="stable") if not np.iscomplexobj(key) else None
         # a stable DEcreasing sort keeps ties in their original order
         order = np.array(sorted(range(len(key)), key=lambda i: -key[i]), dtype=np.int64)
     else:

@@ -14,7 +14,7 @@ Only the entry points the shim declares are provided; every handle is an opaque 
 import numpy as np
 
 from . import lk_oracle as lo
-from .f90run import ABSENT, CPtr, FortranError, ScalarRef
+from .f90run import CPtr, FortranError, ScalarRef
 
 KINDS = "sdcz"                      # LKB_S = 0, LKB_D = 1, LKB_C = 2, LKB_Z = 3
 DT = {"s": np.float32, "d": np.float64, "c": np.complex64, "z": np.complex128}
