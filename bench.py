@@ -305,6 +305,9 @@ def run_ours(args):
             dist.all_gather_object(hs, H.tobytes())
             same = all(h == hs[0] for h in hs)
         parity = {"oracle": "tests/golden/c2_full_H.npz (CPU oracle, 128 steps, same start vector)",
+                  "oracle_pinned_by": "tests/golden/ref_*.npz: outputs of the reference's own Fortran sources executed by "
+                                      "oracle/f90run.py (no Fortran compiler exists here), reproduced by the oracle to 1e-12 "
+                                      "(tests/test_ref_golden.py; the 5-point stencil arnoldi case is stencil2d_arnoldi)",
                   "max_rel_err_H": herr, "max_rel_err_ritz": rerr, "orth_err_first_last_8_cols": orth,
                   "H_identical_on_all_ranks": bool(same), "tol": 1e-10, "orth_tol": 1e-12,
                   "ok": bool(herr < 1e-10 and rerr < 1e-10 and orth <= 1e-12 and same)}
