@@ -32,8 +32,9 @@ class MBasis:
 
 
 class MOp:
-    def __init__(self, kind, A):
-        self.kind, self.A, self.op = kind, np.asfortranarray(A), lo.Op.dense(np.asfortranarray(A))
+    def __init__(self, kind, A=None, op=None):
+        self.kind = kind
+        self.op = op if op is not None else lo.Op.dense(np.asfortranarray(A))
         self.n_matvec = self.n_rmatvec = 0
 
 
@@ -208,6 +209,26 @@ def lkb_op_csr_create(interp, ctx, kind, m, n, rowptr, col, val, A):
         for q in range(int(rp[i]), int(rp[i + 1])):
             M[i, int(cl[q])] += vl[q]
     return ("__out__", {7: CPtr(MOp(k, M))}, LKB_OK)
+
+
+def _coef(p, n, kind):
+    return tuple(DT[kind](v) for v in p.obj.reshape(-1)[:n])
+
+
+def lkb_op_stencil5_create(interp, ctx, kind, nx, ny, coef5, slow0, nslow_local, A):
+    _count("lkb_op_stencil5_create")
+    k = KINDS[int(kind)]
+    if int(slow0) != 0 or int(nslow_local) != int(ny):
+        return LKB_ERR_ARG                      # the mock is one rank
+    return ("__out__", {7: CPtr(MOp(k, op=lo.Op.stencil(k, (int(nx), int(ny)), _coef(coef5, 5, k))))}, LKB_OK)
+
+
+def lkb_op_stencil7_create(interp, ctx, kind, nx, ny, nz, coef7, slow0, nslow_local, A):
+    _count("lkb_op_stencil7_create")
+    k = KINDS[int(kind)]
+    if int(slow0) != 0 or int(nslow_local) != int(nz):
+        return LKB_ERR_ARG
+    return ("__out__", {8: CPtr(MOp(k, op=lo.Op.stencil(k, (int(nx), int(ny), int(nz)), _coef(coef7, 7, k))))}, LKB_OK)
 
 
 def lkb_op_destroy(interp, A):
@@ -442,6 +463,25 @@ def lkb_kexpm_vec(interp, c, A, b, tau, tol, info, trans, kdim):
                             kdim=100 if int(kdim) <= 0 else int(kdim))
     cv.data[...] = out
     return ("__out__", {5: int(inf)}, LKB_OK)
+
+
+def lkb_kexpm_mat(interp, C, A, B, p, tau, tol, info, trans, kdim):
+    _count("lkb_kexpm_mat")
+    cb, op, bb = _live(C, MBasis), _live_op(A), _live(B, MBasis)
+    pp = int(p)
+    out, inf = lo.kexpm_mat(op.op, np.asfortranarray(bb.data[:, :pp].copy()), float(tau), float(tol), trans=bool(int(trans)),
+                            kdim=100 if int(kdim) <= 0 else int(kdim))
+    cb.data[:, :pp] = out
+    return ("__out__", {6: int(inf)}, LKB_OK)
+
+
+def lkb_krylov_expta(interp, vec_out, A, vec_in, tau, info, trans):
+    """kexpm_vec with tol = atol of the kind and kdim = 30 (ExpmLib.fypp:364-392)"""
+    _count("lkb_krylov_expta")
+    ov, op, iv = _live(vec_out, MVec), _live_op(A), _live(vec_in, MVec)
+    out, inf = lo.kexpm_vec(op.op, np.ascontiguousarray(iv.data), float(tau), lo.ATOL[op.kind], trans=bool(int(trans)), kdim=30)
+    ov.data[...] = out
+    return ("__out__", {4: int(inf)}, LKB_OK)
 
 
 NATIVES = {name: fn for name, fn in globals().items() if name.startswith("lkb_") and callable(fn)}

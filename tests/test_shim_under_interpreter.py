@@ -377,3 +377,51 @@ def test_eigs_svds_dispatch(shim, kind):
     # the reference's default for eigs is write_intermediate = .true. (IterativeSolvers.fypp:1025): absent -> option set
     it.call("eigs", opd, X, None, None, 0, x0=x0[0], kdim=24, tolerance=rt(1e-9))
     assert stats.options.get("write_intermediate") == 1
+
+
+def test_stencil_constructors_block_expm_and_release(shim):
+    """cuda_stencil5 / cuda_sym_stencil7 constructors (coefficients cross as c_loc of the array), lanczos on the symmetric type,
+    the block Krylov exponential and krylov_exptA, and cuda_basis_release (every view handle and the basis are released once)"""
+    it, stats = shim
+    kind, k = "d", "rdp"
+    nx, ny, nz = 8, 6, 4
+    n3 = nx * ny * nz
+    # 7-point symmetric stencil -> lanczos
+    coef7 = np.array(rc.POISSON3D)
+    ops, _ = it.call(f"cuda_sym_stencil7_{k}", nx, ny, nz, coef7, 0, nz)
+    _, o = it.call(f"cuda_basis_allocate_{k}", None, n3, n3, 0, 9)
+    X = o[0]
+    dev = X[0].f["basis"].obj.data
+    x0 = rc.unit(rc.pseudo((n3,), 422, kind))
+    dev[:, 0] = x0
+    T = np.zeros((9, 8), order="F")
+    it.hook_hits = {}
+    _, o = it.call("lanczos", ops, X, T, 0)
+    assert it.hook_hits == {f"lanczos_tridiagonalization_{k}": 1}
+    To = np.zeros_like(T)
+    Xo = np.zeros((n3, 9), order="F")
+    Xo[:, 0] = x0
+    assert lo.lanczos(lo.Op.stencil(kind, (nx, ny, nz), rc.POISSON3D), Xo, To) == int(o[3]) == 0
+    assert _rel(T, To) < 1e-12 and _rel(dev, Xo) < 1e-11
+    # 5-point general stencil -> block Krylov exponential (kexpm with array arguments) and krylov_exptA
+    n2 = 12 * 10
+    op5, _ = it.call(f"cuda_stencil5_{k}", 12, 10, np.array(rc.CONVDIFF2D), 0, 10)
+    _, o = it.call(f"cuda_basis_allocate_{k}", None, n2, n2, 0, 6)
+    B = o[0]
+    bdev = B[0].f["basis"].obj.data
+    Bh = rc.pseudo((n2, 3), 272, kind)
+    bdev[:, :3] = Bh
+    it.hook_hits = {}
+    _, o = it.call("kexpm", B[3:6], op5, B[0:3], np.float64(-0.05), np.float64(1e-10), 0, kdim=20)
+    assert it.hook_hits == {f"kexpm_mat_{k}": 1}
+    Co, info_o = lo.kexpm_mat(lo.Op.stencil(kind, (12, 10), rc.CONVDIFF2D), Bh.copy(order="F"), -0.05, 1e-10, kdim=20)
+    assert int(o[5]) == info_o > 0 and _rel(bdev[:, 3:6], Co) < 1e-12 and np.array_equal(bdev[:, :3], Bh)
+    it.hook_hits = {}
+    _, o = it.call("krylov_expta", B[3], op5, B[0], np.float64(-0.05), 0)
+    assert it.hook_hits == {f"krylov_expta_{k}": 1}
+    co, info_o = lo.kexpm_vec(lo.Op.stencil(kind, (12, 10), rc.CONVDIFF2D), Bh[:, 0].copy(), -0.05, lo.ATOL[kind], kdim=30)
+    assert int(o[4]) == info_o and _rel(bdev[:, 3], co) < 1e-12
+    # release: 6 column views + the basis itself
+    vd, bd = stats.calls.get("lkb_vec_destroy", 0), stats.calls.get("lkb_basis_destroy", 0)
+    _, o = it.call(f"cuda_basis_release_{k}", B)
+    assert stats.calls["lkb_vec_destroy"] - vd == 6 and stats.calls["lkb_basis_destroy"] - bd == 1 and o[0] is None
