@@ -2598,6 +2598,8 @@ def _n_c_associated(interp, p, q=None):
 
 def _n_c_f_pointer(interp, cptr, fptr, shape=None):
     arr = cptr.obj
+    if isinstance(arr, ScalarRef):                     # c_loc of a scalar (derived-type) variable: the object itself
+        return ("__out__", {1: arr.get()})
     if shape is not None and shape is not ABSENT:
         arr = arr.ravel(order="F")[:int(np.prod(shape))].reshape(tuple(int(x) for x in shape), order="F")
     return ("__out__", {1: arr})

@@ -373,12 +373,27 @@ def _history(io, res):
     io.f["res_len"] = len(res)
 
 
-def _gmres(interp, A, b, x, info, rtol, atol, transpose, io, flexible):
+def _callback(interp, precond, user):
+    """the lkb_precond_fn the shim passes (c_funloc of its bind(C) trampoline): called like the library calls it, with the
+    'device pointer' of the vector to transform in place; iter / residuals = -1 (absent)"""
+    if precond.obj is None:
+        return None
+    tramp = precond.obj[1]
+
+    def pc(vec, k=None):
+        rc, _ = interp.call(tramp, user, CPtr(vec), int(vec.shape[0]), -1 if k is None else int(k), np.float64(-1.0),
+                            np.float64(-1.0), CPtr(None))
+        if rc != 0:
+            raise FortranError("mock: preconditioner callback failed")
+    return pc
+
+
+def _gmres(interp, A, b, x, info, rtol, atol, transpose, io, flexible, precond=None):
     op, bv, xv, st = _live_op(A), _live(b, MVec), _live(x, MVec), _io(io)
     xs = np.ascontiguousarray(xv.data)
     inf, meta = lo.gmres(op.op, np.ascontiguousarray(bv.data), xs, rtol=None if rtol < 0 else float(rtol),
                          atol=None if atol < 0 else float(atol), kdim=int(st.f["kdim"]), maxiter=int(st.f["maxiter"]),
-                         trans=bool(int(transpose)), flexible=flexible)
+                         trans=bool(int(transpose)), flexible=flexible, precond=precond)
     xv.data[...] = xs
     st.f["n_iter"], st.f["n_inner"], st.f["n_outer"] = meta["n_iter"], meta["n_inner"], meta["n_outer"]
     st.f["converged"], st.f["info"] = int(meta["converged"]), int(inf)
@@ -391,11 +406,24 @@ def lkb_gmres(interp, A, b, x, info, rtol, atol, transpose, io):
     return _gmres(interp, A, b, x, info, rtol, atol, transpose, io, False)
 
 
+def lkb_gmres_precond(interp, A, b, x, info, rtol, atol, transpose, io, precond, user):
+    _count("lkb_gmres_precond")
+    return _gmres(interp, A, b, x, info, rtol, atol, transpose, io, False, _callback(interp, precond, user))
+
+
 def lkb_fgmres(interp, A, b, x, info, rtol, atol, transpose, io, precond, user):
     _count("lkb_fgmres")
-    if precond.obj is not None:
-        raise FortranError("mock: preconditioner callbacks are not provided")
-    return _gmres(interp, A, b, x, info, rtol, atol, transpose, io, True)
+    return _gmres(interp, A, b, x, info, rtol, atol, transpose, io, True, _callback(interp, precond, user))
+
+
+def lkb_vec_wrap(interp, ctx, kind, n_local, n_global, row0, devptr, v):
+    """a vector handle over memory the library already owns (the callback's vec_dev)"""
+    _count("lkb_vec_wrap")
+    k = KINDS[int(kind)]
+    arr = devptr.obj
+    if not isinstance(arr, np.ndarray) or arr.dtype != DT[k] or arr.shape[0] != int(n_local):
+        return LKB_ERR_ARG
+    return ("__out__", {6: CPtr(MVec(k, arr))}, LKB_OK)
 
 
 def lkb_cg(interp, A, b, x, info, rtol, atol, io):

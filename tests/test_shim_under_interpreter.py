@@ -425,3 +425,51 @@ def test_stencil_constructors_block_expm_and_release(shim):
     vd, bd = stats.calls.get("lkb_vec_destroy", 0), stats.calls.get("lkb_basis_destroy", 0)
     _, o = it.call(f"cuda_basis_release_{k}", B)
     assert stats.calls["lkb_vec_destroy"] - vd == 6 and stats.calls["lkb_basis_destroy"] - bd == 1 and o[0] is None
+
+
+def test_preconditioned_gmres_through_the_c_trampoline(shim):
+    """A user preconditioner (tests/golden/user_precond.f90: extends the reference's abstract_precond_rdp) travels through
+    `void* user` as c_loc(box); the library calls the shim's bind(C) trampoline with the device pointer of the vector, which wraps
+    it (lkb_vec_wrap), calls `box%p%apply(v)` -- the user's Fortran -- and releases the wrapper.  Same iterates as the oracle with
+    the same scaling, and as the REFERENCE's own gmres run with the same preconditioner object on its CPU vector type."""
+    it, stats = shim
+    kind, k = "d", "rdp"
+    if "jacobi_apply_rdp" not in it.p.procs:
+        it.p.load(os.path.join(HERE, "golden", "user_precond.f90"))
+        f90run.Interp(it.p)
+    dims = (20, 16)
+    n = dims[0] * dims[1]
+    op, _ = it.call(f"cuda_stencil5_{k}", dims[0], dims[1], np.array(rc.CONVDIFF2D), 0, dims[1])
+    _, o = it.call(f"cuda_basis_allocate_{k}", None, n, n, 0, 2)
+    bx = o[0]
+    dev = bx[0].f["basis"].obj.data
+    bh = rc.unit(rc.pseudo((n,), 412, kind))
+    dev[:, 0] = bh
+    pre = it.new_inst("jacobi_precond_rdp")
+    pre.f["inv_diag"] = np.float64(1.0 / 6.0)
+    opts = it.new_inst("gmres_dp_opts")
+    opts.f["kdim"], opts.f["maxiter"] = 12, 30
+    meta = it.new_inst("gmres_dp_metadata")
+    it.hook_hits = {}
+    wraps = stats.calls.get("lkb_vec_wrap", 0)
+    _, o = it.call("gmres", op, bx[0], bx[1], 0, preconditioner=pre, options=opts, meta=meta)
+    assert it.hook_hits == {f"gmres_{k}": 1} and stats.calls["lkb_gmres_precond"] >= 1
+    xo = np.zeros(n)
+
+    def scale(v, kk=None):
+        v *= 1.0 / 6.0
+    info_o, mo = lo.gmres(lo.Op.stencil(kind, dims, rc.CONVDIFF2D), bh.copy(), xo, kdim=12, maxiter=30, precond=scale)
+    assert int(o[3]) == info_o > 12 and _rel(dev[:, 1], xo) < 1e-12
+    assert meta.f["n_iter"] == mo["n_iter"] and meta.f["n_outer"] == mo["n_outer"]
+    applied = int(pre.f["n_applied"])
+    assert applied == stats.calls["lkb_vec_wrap"] - wraps > 0            # one wrapper per callback, the user's counter moved
+    # the reference's own gmres (no hook: its CPU vector type declines) with the SAME preconditioner object
+    be = rc.RefBackend()
+    A_ref = be.stencil(kind, dims, rc.CONVDIFF2D)
+    b_ref, x_ref = be.basis_n(kind, n, 1, bh), be.basis_n(kind, n, 1)
+    meta_r = it.new_inst("gmres_dp_metadata")
+    it.hook_hits = {}
+    _, o = it.call("gmres", A_ref, b_ref[0], x_ref[0], 0, preconditioner=pre, options=opts, meta=meta_r)
+    assert it.hook_hits == {} and int(o[3]) == info_o
+    assert _rel(x_ref[0].f["data"], xo) < 1e-12 and meta_r.f["n_iter"] == mo["n_iter"]
+    assert int(pre.f["n_applied"]) == 2 * applied
