@@ -429,3 +429,114 @@ def test_kexpm_mat_shell_matches_oracle_shell(expm_mock, oracle, kind, p):
         assert binfo == 4 == oracle.kexpm_mat(oracle.Op.dense(D), Bh, 0.2, 1e-12)[1]
         assert np.linalg.norm(Cb - exact) < 1e-12 * np.linalg.norm(exact)
     sh.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# The same C++ shells against REFERENCE-PRODUCED fixtures (tests/golden/ref_solvers.npz: outputs of LightKrylov's own eigs / eighs /
+# svds code executed by oracle/f90run.py, see tests/test_ref_golden.py): the product's host control flow -- convergence tests, the
+# literal post-convergence Krylov-Schur restart, LAPACK post-processing, sort order, the write_intermediate side effect -- must
+# return the reference's `info`, spectra and vectors.  Direct product-vs-reference evidence that needs no GPU.
+# ------------------------------------------------------------------------------------------------------------------------------
+class _ShellsBackend:
+    """adapter of the cases in tests/golden/ref_cases.py onto the mocked-device shells (operators = oracle operators)"""
+
+    def __init__(self, lib, kind, oracle, write_intermediate=False):
+        self.sh, self.oracle, self.kind = Shells(lib, kind, write_intermediate=write_intermediate), oracle, kind
+
+    def linop(self, kind, A, sym=False):
+        return self.sh.op(self.oracle.Op.dense(np.asfortranarray(A)))
+
+    def stencil(self, kind, dims, coef, sym=False):
+        return self.sh.op(self.oracle.Op.stencil(kind, tuple(dims), tuple(float(c) for c in coef)))
+
+    def eigs(self, A, nev, x0, kdim, tolerance, n=None):
+        return self.sh.eigs(A, x0.shape[0], nev, x0, kdim=kdim, tol=tolerance)
+
+    def eighs(self, A, nev, x0, kdim, tolerance, write_intermediate=False):
+        return self.sh.eighs(A, x0.shape[0], nev, x0, kdim=kdim, tol=tolerance)
+
+    def svds(self, A, nsv, u0, kdim, tolerance, write_intermediate=False):
+        return self.sh.svds(A, u0.shape[0], u0.shape[0], nsv, u0, kdim=kdim, tol=tolerance)
+
+
+@pytest.mark.parametrize("kind", ["d", "z"])
+@pytest.mark.parametrize("case", ["eigs_solve", "eighs_solve", "svds_solve", "eighs_write_intermediate", "svds_write_intermediate",
+                                  "stencil3d_eigs"])
+def test_cpp_shells_reproduce_reference_outputs(mock, oracle, case, kind, tmp_path, monkeypatch):
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import ref_cases as rc
+    if not rc.applies(case, kind):
+        pytest.skip("case not defined for this kind")
+    monkeypatch.chdir(tmp_path)                                  # the table files of write_intermediate land here
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "ref_solvers.npz"))
+    be = _ShellsBackend(mock, kind, oracle, write_intermediate="write_intermediate" in case)
+    try:
+        got = rc.SOLVER_CASES[case](kind, be)
+    finally:
+        be.sh.close()
+    keys = [k for k in fx.files if k.startswith(f"{case}/{kind}/")]
+    assert keys
+    for full in keys:
+        key = full.split("/")[-1]
+        want, have = fx[full], np.asarray(got[key])
+        if key == "X" and "eigs" in case:
+            continue                                             # (Re, Im) pair layout: free phase, compared through the eigenvalues
+        if key.startswith("abs_"):
+            assert float(have) < 1e-9
+        elif want.dtype.kind in "iub":
+            assert np.array_equal(have, want), (full, have.tolist(), want.tolist())
+        else:
+            err = float(np.abs(have - want).max()) / max(float(np.abs(want).max()), 1e-300)
+            assert have.shape == want.shape and err < (1e-8 if key.startswith("abs") else 1e-10), (full, err)
+    if "write_intermediate" in case:
+        assert os.path.exists(tmp_path / ("eighs_output.txt" if case.startswith("eighs") else "svds_output.txt"))
+
+
+class _ExpmBackend:
+    """kexpm cases of tests/golden/ref_cases.py on the mocked-device exponential shells (lkb_expm.cu)"""
+
+    def __init__(self, lib, kind, oracle):
+        self.sh, self.oracle = ExpmShells(lib, kind), oracle
+
+    def linop(self, kind, A, sym=False):
+        return self.sh.op(self.oracle.Op.dense(np.asfortranarray(A)))
+
+    def basis(self, kind, ncols, first=None):
+        X = np.zeros((N, ncols), dtype=self.sh.dt, order="F")
+        if first is not None:
+            X[:, :np.asarray(first).reshape(N, -1).shape[1]] = np.asarray(first).reshape(N, -1)
+        return X
+
+    def data(self, X):
+        return X
+
+    def kexpm(self, c, A, b, tau, tol, kdim):
+        out, info = self.sh.kexpm(A, b[:, 0].copy(), tau, tol, kdim=kdim)
+        c[:, 0] = out
+        return info
+
+    def kexpm_mat(self, Cb, A, B, tau, tol, kdim):
+        out, info = self.sh.kexpm_mat(A, B, tau, tol, kdim=kdim)
+        Cb[...] = out
+        return info
+
+
+@pytest.mark.parametrize("kind", ["d", "z"])
+@pytest.mark.parametrize("case", ["kexpm_solve", "kexpm_block", "kexpm_breakdown"])
+def test_cpp_expm_shells_reproduce_reference_outputs(expm_mock, oracle, case, kind):
+    """lkb_kexpm_vec / lkb_kexpm_mat (C++ on the mocked device) against what the reference's own kexpm returned: same `info`
+    (incl. the literal k + 2 on Arnoldi breakdown), same vectors / block"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import ref_cases as rc
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "ref_solvers.npz"))
+    be = _ExpmBackend(expm_mock, kind, oracle)
+    try:
+        got = rc.SOLVER_CASES[case](kind, be)
+    finally:
+        be.sh.close()
+    assert int(got["info"]) == int(fx[f"{case}/{kind}/info"])
+    key = "C" if case == "kexpm_block" else "c"
+    want = fx[f"{case}/{kind}/{key}"]
+    assert float(np.abs(np.asarray(got[key]) - want).max()) / float(np.abs(want).max()) < 1e-10
