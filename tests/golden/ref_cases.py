@@ -203,7 +203,37 @@ def qr_pivoting_deficient(kind, be):
             "Q_lead": Qd[:, :4].copy(), "abs_orth_err": np.array(np.abs(G - np.eye(p)).max(), dtype=np.float64)}
 
 
+def krylov_schur_restart(kind, be):
+    """a full Arnoldi factorisation followed by ONE Krylov-Schur restart with eigs' median selector (BaseKrylov.fypp:782-834):
+    number of retained Ritz values, restarted H (Schur form + residual row), restarted basis"""
+    kdim = 16
+    A = be.linop(kind, dominant_matrix(kind))
+    X = be.basis(kind, kdim + 1, unit(pseudo((N,), 502, kind)))
+    H = np.zeros((kdim + 1, kdim), dtype=DTYPE[kind], order="F")
+    info = be.arnoldi(A, X, H)
+    n = be.krylov_schur(X, H)
+    Xd = be.data(X)
+    # the Schur vectors of a (quasi-)triangular form are defined up to a sign / phase per block: compare what is invariant
+    # ... and, for the real kinds, up to the orientation of each standardised 2 x 2 block ((q1, q2) -> (q2, -q1) is the same form):
+    # sorted moduli are invariant under both
+    return {"info": info, "n": n, "absH_diag": np.sort(np.abs(np.diag(H[:n, :n]))), "absres_row": np.sort(np.abs(H[n, :n])),
+            "H_fro": np.array(np.linalg.norm(H), dtype=np.float64),
+            "span_projector_diag": np.real(np.einsum("ij,ij->i", Xd[:, :n + 1], Xd[:, :n + 1].conj())).astype(np.float64)}
+
+
+def basis_helpers(kind, be):
+    """innerprod (vector and matrix), Gram, linear_combination (vector and matrix), axpby_basis, copy: AbstractVectors.fypp:571-730"""
+    j, p = 5, 3
+    Xh = pseudo((N, j), 511, kind)
+    Yh = pseudo((N, p), 512, kind)
+    Bm = pseudo((j, p), 513, kind)
+    X, Y = be.basis(kind, j, Xh), be.basis(kind, p, Yh)
+    out = be.helpers(kind, X, Y, Bm)
+    return out
+
+
 CASES = {
+    "krylov_schur_restart": krylov_schur_restart, "basis_helpers": basis_helpers,
     "dgs_zero_vector": dgs_zero_vector, "qr_pivoting_deficient": qr_pivoting_deficient,
     "arnoldi_full": arnoldi_full, "arnoldi_transpose": arnoldi_transpose, "arnoldi_block": arnoldi_block,
     "arnoldi_resume": arnoldi_resume, "arnoldi_breakdown": arnoldi_breakdown, "lanczos_full": lanczos_full,
@@ -419,6 +449,9 @@ def applies(name, kind):
 
 
 # ------------------------------------------------------------------------------------------------------------------ backends
+SUFFIX_OF = {"s": "rsp", "d": "rdp", "c": "csp", "z": "cdp"}
+
+
 class RefBackend:
     """the reference's own Fortran sources under oracle/f90run.py (container only: needs /root/reference)"""
     name = "reference"
@@ -497,6 +530,30 @@ class RefBackend:
         perm = np.zeros(len(Q), dtype=np.int64)
         _, o = self.rx.call("qr", Q, R, perm, 0)
         return int(o[3]), R, perm - 1                  # 0-based like the oracle
+
+    def krylov_schur(self, X, H):
+        kind = self._kind(X)
+        sel = ("procref", f"eigs_{SUFFIX_OF[kind]}::median_selector")       # the selector eigs passes (an internal procedure)
+        _, o = self.rx.call("krylov_schur", 0, X, H, sel)
+        return int(o[0])
+
+    def helpers(self, kind, X, Y, Bm):
+        call = self.rx.call
+        one, half = DTYPE[kind](1.0), DTYPE[kind](0.5)
+        out = {"innerprod_vec": np.array(call("innerprod", X, Y[0])[0]), "innerprod_mat": np.array(call("innerprod", X, Y)[0]),
+               "gram": np.array(call("gram", X)[0])}
+        _, o = call("linear_combination", None, X, np.ascontiguousarray(Bm[:, 0]))
+        out["lincomb_vec"] = o[0].f["data"].copy()
+        _, o = call("linear_combination", None, X, Bm)
+        Z = o[0]
+        out["lincomb_mat"] = self.data(Z)
+        call("axpby_basis", half, Y, one, Z)                       # Z = 0.5 * Y + Z   (axpby_basis(alpha, X, beta, Y): Y = alpha X + beta Y)
+        out["axpby_basis"] = self.data(Z)
+        call("copy", Z, Y)
+        out["copy"] = self.data(Z)
+        call("zero_basis", Z)
+        out["zero_basis"] = self.data(Z)
+        return out
 
     def dgs_vec(self, y, X):
         dt = X[0].f["data"].dtype
@@ -635,6 +692,38 @@ class OracleBackend:
 
     def qr_pivoting(self, Q):
         return self.lo.qr_with_pivoting(Q)
+
+    def krylov_schur(self, X, H):
+        return self.lo.krylov_schur(X, H)
+
+    def helpers(self, kind, X, Y, Bm):
+        """the same operation order as the reference's loops, on the oracle's dot / axpby primitives"""
+        lo, dt = self.lo, DTYPE[kind]
+        j, p = X.shape[1], Y.shape[1]
+        col = np.ascontiguousarray
+        ip = np.array([[lo.dot(col(X[:, i]), col(Y[:, q])) for q in range(p)] for i in range(j)], dtype=dt).reshape(j, p)
+        # LITERAL: gram_matrix_* fills the lower triangle with G(j, i) = G(i, j) -- NOT conjugated, also for the complex kinds
+        # (AbstractVectors.fypp:645-660), so the reference's complex Gram matrix is symmetric, not Hermitian.  Harmless where the
+        # reference uses it (is_orthonormal takes the Frobenius norm of G - I); device vectors inherit it, the reference's own
+        # Gram runs on their type-bound dot.
+        gram = np.zeros((j, j), dtype=dt)
+        for i in range(j):
+            for q in range(i, j):
+                gram[i, q] = lo.dot(col(X[:, i]), col(X[:, q]))
+                gram[q, i] = gram[i, q]
+        Z = np.zeros((N, p), dtype=dt, order="F")
+        for q in range(p):
+            z = np.zeros(N, dtype=dt)
+            for i in range(j):
+                lo.axpby(Bm[i, q], col(X[:, i]), 1.0, z)
+            Z[:, q] = z
+        out = {"innerprod_vec": ip[:, 0].copy(), "innerprod_mat": ip, "gram": gram, "lincomb_vec": Z[:, 0].copy(),
+               "lincomb_mat": Z.copy(order="F")}
+        Z2 = (dt(0.5) * Y + Z).astype(dt)
+        out["axpby_basis"] = Z2
+        out["copy"] = Y.copy(order="F")
+        out["zero_basis"] = np.zeros_like(Y)
+        return out
 
     def dgs_vec(self, y, X):
         return self.lo.dgs_vec(y[:, 0], X, X.shape[1])

@@ -4,7 +4,7 @@ types), executed statement by statement by oracle/f90run.py because no Fortran c
 (tests/golden/make_ref_golden.py is the generating script; tests/golden/ref_cases.py holds the cases and inputs).
 
   * CPU (`-m "not gpu"`): the C oracle reproduces every fixture (H / T / B / R entries, bases, pivots, info, counters);
-    where /root/reference is present the fixtures are re-generated and must come out bit-identical, and the interpreter's own
+    where /root/reference is present the fixtures are re-generated and must come out the same (1e-14; byte-identical in practice), and the interpreter's own
     semantics are unit-tested on small Fortran snippets.
   * GPU (`-m gpu`): the CUDA path, through the C ABI, against the same fixtures.
 
@@ -83,8 +83,10 @@ def test_fixtures_name_the_reference_text():
 
 
 @pytest.mark.parametrize("case", ["arnoldi_full", "lanczos_full", "bidiag_full", "qr_pivoting", "arnoldi_block"])
-def test_fixtures_regenerate_bit_identically(case):
-    """where the reference tree exists (this container, not the GPU box) the interpreter re-produces the committed numbers"""
+def test_fixtures_regenerate(case):
+    """where the reference tree exists (this container, not the GPU box) the interpreter re-produces the committed numbers: bit for
+    bit in practice (the .npz files are byte-identical across regenerations here); asserted to 1e-14 so that a BLAS that threads a
+    128 x 128 matrix-vector product differently cannot turn this into a flaky test"""
     from oracle import ref_exec
     if not ref_exec.available():
         pytest.skip("/root/reference not present on this box")
@@ -93,7 +95,12 @@ def test_fixtures_regenerate_bit_identically(case):
     for kind in "dz":
         got = rc.CASES[case](kind, be)
         for key, val in got.items():
-            assert np.array_equal(np.asarray(val), fx[f"{case}/{kind}/{key}"]), (case, kind, key)
+            want = fx[f"{case}/{kind}/{key}"]
+            val = np.asarray(val)
+            if want.dtype.kind in "iub":
+                assert np.array_equal(val, want), (case, kind, key)
+            else:
+                assert float(np.abs(val - want).max()) <= 1e-14 * max(float(np.abs(want).max()), 1e-300), (case, kind, key)
 
 
 # ------------------------------------------------------------------------------------------------ the interpreter itself
@@ -283,6 +290,9 @@ class ProductBackend:
     def bidiag(self, A, U, V, B):
         return self.lk.bidiagonalization(A, U, V, B)
 
+    def krylov_schur(self, X, H):
+        return self.lk.krylov_schur(X, H, X.ncols - 1)
+
     # ---- solvers (vectors = columns of one-column bases)
     def gmres(self, A, b, x, kdim, maxiter, flexible=False):
         fn = self.lk.fgmres if flexible else self.lk.gmres
@@ -334,7 +344,8 @@ class ProductBackend:
 
 
 GPU_CASES = ["arnoldi_full", "arnoldi_transpose", "arnoldi_block", "arnoldi_resume", "arnoldi_breakdown", "lanczos_full",
-             "bidiag_full", "qr_full", "qr_pivoting", "qr_pivoting_deficient", "stencil2d_arnoldi", "stencil3d_lanczos"]
+             "bidiag_full", "qr_full", "qr_pivoting", "qr_pivoting_deficient", "krylov_schur_restart", "stencil2d_arnoldi",
+             "stencil3d_lanczos"]
 
 
 @pytest.fixture(scope="module")
@@ -493,6 +504,11 @@ class _FakeLk:
     def qr_pivoting(self, Q):
         self._chk("qr_pivoting", Q)
         return self.lo.qr_with_pivoting(Q.data)
+
+    def krylov_schur(self, X, H, kdim):
+        self._chk("krylov_schur", X, H, kdim)
+        assert kdim == X.ncols - 1
+        return self.lo.krylov_schur(X.data, H)
 
     def gmres(self, A, b, x, **k):
         self._chk("gmres", A, b, x, **k)
