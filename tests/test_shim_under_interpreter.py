@@ -278,12 +278,15 @@ def test_other_layouts_take_the_type_bound_path(shim, kind):
         it.call("double_gram_schmidt_step", empty, Q, 0, if_chk_orthonormal=False)
 
 
-@pytest.mark.parametrize("kind", list("dz"))
+@pytest.mark.parametrize("kind", list("sdcz"))
 def test_solvers_dispatch(shim, kind):
     """gmres / fgmres / cg / eighs / svds / eigs / kexpm called by their reference names with device types"""
     it, stats = shim
     k = SUF[kind]
-    prec = "dp"
+    prec = "sp" if kind in "sc" else "dp"
+    rt = np.float32 if kind in "sc" else np.float64                     # real arguments must have the kind of the generic's specific
+    tol9 = 1e-3 if kind in "sc" else 1e-9
+    tol10 = 1e-4 if kind in "sc" else 1e-10
     # gmres with options and metadata objects of the reference's own types
     A = rc.well_conditioned(kind)
     op = _op(it, kind, A)
@@ -296,9 +299,9 @@ def test_solvers_dispatch(shim, kind):
     assert it.hook_hits == {f"gmres_{k}": 1}
     xo = np.zeros(N, dtype=A.dtype)
     info_o, mo = lo.gmres(lo.Op.dense(A), dev[:, 0].copy(), xo, kdim=10, maxiter=20)
-    assert int(o[3]) == info_o > 10 and _rel(dev[:, 1], xo) < 1e-12
+    assert int(o[3]) == info_o > 5 and _rel(dev[:, 1], xo) < _tol(kind)
     assert (meta.f["n_iter"], meta.f["n_inner"], meta.f["n_outer"]) == (mo["n_iter"], mo["n_inner"], mo["n_outer"])
-    assert bool(meta.f["converged"]) and np.allclose(meta.f["res"], mo["res"], rtol=1e-6, atol=0)     # tail entries ~ 1e-8: recomputed residual norms
+    assert bool(meta.f["converged"]) and np.allclose(meta.f["res"], mo["res"], rtol=1e-6 if kind in "dz" else 1e-3, atol=0)    # two runs of the (OpenMP) oracle: rounding
     # cg on the symmetric operator type
     S = rc.sym_matrix(kind, 211, shift=0.1)
     gen = _op(it, kind, S)
@@ -311,7 +314,7 @@ def test_solvers_dispatch(shim, kind):
     assert it.hook_hits == {f"cg_{k}": 1}
     xo = np.zeros(N, dtype=A.dtype)
     info_o, mo = lo.cg(lo.Op.dense(S), dev[:, 0].copy(), xo)
-    assert int(o[3]) == info_o > 0 and _rel(dev[:, 1], xo) < 1e-12 and cmeta.f["n_iter"] == mo["n_iter"]
+    assert int(o[3]) == info_o > 0 and _rel(dev[:, 1], xo) < _tol(kind) and cmeta.f["n_iter"] == mo["n_iter"]
     # eighs: X(:) is intent(out) in the reference -- the views must survive, eigvals / residuals are allocated by the shim
     S2 = rc.sym_matrix(kind, 221)
     gen2 = _op(it, kind, S2)
@@ -322,20 +325,21 @@ def test_solvers_dispatch(shim, kind):
     x0h = rc.unit(rc.pseudo((N,), 222, kind))
     x0v, x0dev = _basis(it, kind, 1, x0h)
     it.hook_hits = {}
-    _, o = it.call("eighs", ops2, Xe, None, None, 0, x0=x0v[0], kdim=64, tolerance=np.float64(1e-9))
+    _, o = it.call("eighs", ops2, Xe, None, None, 0, x0=x0v[0], kdim=64, tolerance=rt(tol9))
     assert it.hook_hits == {f"eighs_{k}": 1}
-    evo, reso, Xo, ko = lo.eighs(lo.Op.dense(S2), N, nev, x0h, kdim=64, tolerance=1e-9)
-    assert int(o[4]) == ko and _rel(np.asarray(o[2]), evo) < 1e-12 and _rel(np.abs(edev), np.abs(Xo)) < 1e-9
+    evo, reso, Xo, ko = lo.eighs(lo.Op.dense(S2), N, nev, x0h, kdim=64, tolerance=float(rt(tol9)))
+    assert int(o[4]) == ko and _rel(np.asarray(o[2]), evo) < _tol(kind) and _rel(np.abs(edev), np.abs(Xo)) < 1e3 * _tol(kind)
+    assert np.asarray(o[2]).dtype == rt
     assert np.asarray(o[3]).shape == (nev,) and Xe[0].f["col"] == 0 and Xe[2].f["col"] == 2
     # kexpm (vector)
     Ak = rc.general_matrix(kind, 241)
     opk = _op(it, kind, Ak)
     cb, cdev = _basis(it, kind, 2, rc.unit(rc.pseudo((N,), 242, kind)))
     it.hook_hits = {}
-    _, o = it.call("kexpm", cb[1], opk, cb[0], np.float64(0.1), np.float64(1e-10), 0, kdim=40)
+    _, o = it.call("kexpm", cb[1], opk, cb[0], rt(0.1), rt(tol10), 0, kdim=40)
     assert it.hook_hits == {f"kexpm_vec_{k}": 1}
-    co, info_o = lo.kexpm_vec(lo.Op.dense(Ak), cdev[:, 0].copy(), 0.1, 1e-10, kdim=40)
-    assert int(o[5]) == info_o and _rel(cdev[:, 1], co) < 1e-12
+    co, info_o = lo.kexpm_vec(lo.Op.dense(Ak), cdev[:, 0].copy(), float(rt(0.1)), float(rt(tol10)), kdim=40)
+    assert int(o[5]) == info_o and _rel(cdev[:, 1], co) < _tol(kind)
 
 
 @pytest.mark.parametrize("kind", list("dz"))
