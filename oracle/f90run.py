@@ -2223,10 +2223,19 @@ def _i_loc(fn):
     return f
 
 
+def _seq_sum(v):
+    """left-to-right summation in the precision of the array, as a compiled loop without -ffast-math does it (numpy's own sum
+    is pairwise); add.accumulate is sequential by definition"""
+    v = np.asarray(v)
+    if v.ndim != 1 or v.size == 0:
+        return np.sum(v)
+    return np.add.accumulate(v)[-1]
+
+
 def _i_dot_product(a, b):
     if np.iscomplexobj(a):
-        return np.sum(np.conj(a) * b)
-    return np.sum(a * b)
+        return _seq_sum(np.conj(a) * b)
+    return _seq_sum(a * b)
 
 
 def _i_merge(t, f, mask):
@@ -2304,7 +2313,8 @@ INTRINSICS = {
     "ceiling": lambda a: int(np.ceil(a)), "mod": _i_mod, "modulo": lambda a, p: a % p,
     "min": _i_minmax(lambda x, y: np.minimum(x, y) if isinstance(x, np.ndarray) or isinstance(y, np.ndarray) else (x if x <= y else y)),
     "max": _i_minmax(lambda x, y: np.maximum(x, y) if isinstance(x, np.ndarray) or isinstance(y, np.ndarray) else (x if x >= y else y)),
-    "minval": _reduce(np.min), "maxval": _reduce(np.max), "sum": _reduce(np.sum), "product": _reduce(np.prod),
+    "minval": _reduce(np.min), "maxval": _reduce(np.max), "product": _reduce(np.prod),
+    "sum": lambda a, dim=None, mask=None: _seq_sum(a) if dim is None and mask is None and np.ndim(a) == 1 else _reduce(np.sum)(a, dim, mask),
     "any": _reduce(np.any), "all": _reduce(np.all), "count": lambda a, dim=None: int(np.count_nonzero(a)),
     "maxloc": _i_loc(np.argmax), "minloc": _i_loc(np.argmin),
     "matmul": _i_matmul, "transpose": lambda a: np.asfortranarray(a.T), "dot_product": _i_dot_product,
@@ -2355,11 +2365,11 @@ def _n_axpy(interp, n, a, x, incx, y, incy):
 
 
 def _n_dot(interp, n, x, incx, y, incy):
-    return x.dtype.type(np.dot(x[:n], y[:n]))
+    return x.dtype.type(_seq_sum(x[:n] * y[:n]))             # reference BLAS xDOT: one running sum
 
 
 def _n_dotc(interp, n, x, incx, y, incy):
-    return x.dtype.type(np.vdot(x[:n], y[:n]))
+    return x.dtype.type(_seq_sum(np.conj(x[:n]) * y[:n]))
 
 
 def _n_nrm2(interp, n, x, incx):
