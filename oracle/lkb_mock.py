@@ -426,12 +426,17 @@ def lkb_vec_wrap(interp, ctx, kind, n_local, n_global, row0, devptr, v):
     return ("__out__", {6: CPtr(MVec(k, arr))}, LKB_OK)
 
 
-def lkb_cg(interp, A, b, x, info, rtol, atol, io):
+def lkb_cg_precond(interp, A, b, x, info, rtol, atol, io, precond, user):
+    _count("lkb_cg_precond")
+    return lkb_cg(interp, A, b, x, info, rtol, atol, io, _precond=_callback(interp, precond, user))
+
+
+def lkb_cg(interp, A, b, x, info, rtol, atol, io, _precond=None):
     _count("lkb_cg")
     op, bv, xv, st = _live_op(A), _live(b, MVec), _live(x, MVec), _io(io)
     xs = np.ascontiguousarray(xv.data)
     inf, meta = lo.cg(op.op, np.ascontiguousarray(bv.data), xs, rtol=None if rtol < 0 else float(rtol),
-                      atol=None if atol < 0 else float(atol), maxiter=int(st.f["maxiter"]))
+                      atol=None if atol < 0 else float(atol), maxiter=int(st.f["maxiter"]), precond=_precond)
     xv.data[...] = xs
     st.f["n_iter"], st.f["converged"], st.f["info"] = meta["n_iter"], int(meta["converged"]), int(inf)
     _history(st, meta["res"])

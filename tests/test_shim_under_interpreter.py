@@ -477,3 +477,65 @@ def test_preconditioned_gmres_through_the_c_trampoline(shim):
     assert it.hook_hits == {} and int(o[3]) == info_o
     assert _rel(x_ref[0].f["data"], xo) < 1e-12 and meta_r.f["n_iter"] == mo["n_iter"]
     assert int(pre.f["n_applied"]) == 2 * applied
+
+
+def test_preconditioned_fgmres_and_cg_through_the_c_trampoline(shim):
+    """the same user preconditioner through lkb_fgmres (flexible: the iteration index reaches the callback) and lkb_cg_precond"""
+    it, stats = shim
+    kind, k = "d", "rdp"
+    if "jacobi_apply_rdp" not in it.p.procs:
+        it.p.load(os.path.join(HERE, "golden", "user_precond.f90"))
+        f90run.Interp(it.p)
+
+    def scale(v, kk=None):
+        v *= 1.0 / 6.0
+    # fgmres on the non-symmetric 5-point stencil
+    dims = (20, 16)
+    n = dims[0] * dims[1]
+    op, _ = it.call(f"cuda_stencil5_{k}", dims[0], dims[1], np.array(rc.CONVDIFF2D), 0, dims[1])
+    _, o = it.call(f"cuda_basis_allocate_{k}", None, n, n, 0, 2)
+    bx = o[0]
+    dev = bx[0].f["basis"].obj.data
+    bh = rc.unit(rc.pseudo((n,), 412, kind))
+    dev[:, 0] = bh
+    pre = it.new_inst("jacobi_precond_rdp")
+    pre.f["inv_diag"] = np.float64(1.0 / 6.0)
+    opts = it.new_inst("fgmres_dp_opts")
+    opts.f["kdim"], opts.f["maxiter"] = 12, 30
+    meta = it.new_inst("fgmres_dp_metadata")
+    it.hook_hits = {}
+    _, o = it.call("fgmres", op, bx[0], bx[1], 0, preconditioner=pre, options=opts, meta=meta)
+    assert it.hook_hits == {f"fgmres_{k}": 1}
+    xo = np.zeros(n)
+    info_o, mo = lo.gmres(lo.Op.stencil(kind, dims, rc.CONVDIFF2D), bh.copy(), xo, kdim=12, maxiter=30, precond=scale, flexible=True)
+    assert int(o[3]) == info_o > 0 and _rel(dev[:, 1], xo) < 1e-12 and meta.f["n_iter"] == mo["n_iter"]
+    assert int(pre.f["n_applied"]) == mo["n_inner"]                       # one application per inner step
+    # cg on the symmetric 7-point stencil
+    d3 = (8, 6, 4)
+    n3 = d3[0] * d3[1] * d3[2]
+    ops, _ = it.call(f"cuda_sym_stencil7_{k}", d3[0], d3[1], d3[2], np.array(rc.POISSON3D), 0, d3[2])
+    _, o = it.call(f"cuda_basis_allocate_{k}", None, n3, n3, 0, 2)
+    cx = o[0]
+    cdev = cx[0].f["basis"].obj.data
+    ch = rc.unit(rc.pseudo((n3,), 432, kind))
+    cdev[:, 0] = ch
+    pre2 = it.new_inst("jacobi_precond_rdp")
+    pre2.f["inv_diag"] = np.float64(1.0 / 6.0)
+    cmeta = it.new_inst("cg_dp_metadata")
+    it.hook_hits = {}
+    _, o = it.call("cg", ops, cx[0], cx[1], 0, preconditioner=pre2, meta=cmeta)
+    assert it.hook_hits == {f"cg_{k}": 1} and stats.calls["lkb_cg_precond"] >= 1
+    xo = np.zeros(n3)
+    info_o, mo = lo.cg(lo.Op.stencil(kind, d3, rc.POISSON3D), ch.copy(), xo, precond=scale)
+    assert int(o[3]) == info_o > 0 and _rel(cdev[:, 1], xo) < 1e-12 and cmeta.f["n_iter"] == mo["n_iter"]
+    assert int(pre2.f["n_applied"]) > 0
+    # the reference's own cg with the same kind of preconditioner object on its CPU vectors gives the same iterates
+    be = rc.RefBackend()
+    A_ref = be.stencil(kind, d3, rc.POISSON3D, sym=True)
+    b_ref, x_ref = be.basis_n(kind, n3, 1, ch), be.basis_n(kind, n3, 1)
+    pre3 = it.new_inst("jacobi_precond_rdp")
+    pre3.f["inv_diag"] = np.float64(1.0 / 6.0)
+    it.hook_hits = {}
+    _, o = it.call("cg", A_ref, b_ref[0], x_ref[0], 0, preconditioner=pre3)
+    assert it.hook_hits == {} and int(o[3]) == info_o and _rel(x_ref[0].f["data"], xo) < 1e-12
+    assert int(pre3.f["n_applied"]) == int(pre2.f["n_applied"])
