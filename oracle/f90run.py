@@ -1109,6 +1109,7 @@ class Interp:
         self.call_depth = 0
         self.hooks = {}               # reference procedure name -> logical function tried first (see run_proc_scalar)
         self.hook_hits = {}
+        self.called = set()           # names of the interpreted procedures that ran (coverage of a test session)
         gsc = Scope(None)
         gsc.vars = self.p.globals
         self.gscope = gsc
@@ -1860,6 +1861,7 @@ class Interp:
             if bool(self.run_proc(tproc, {tn: bound[rn] for tn, rn in zip(tproc.args, proc.args)}, caller_sc)):
                 self.hook_hits[proc.name] = self.hook_hits.get(proc.name, 0) + 1
                 return None
+        self.called.add(proc.name)
         sc = Scope(proc)
         for n, (v, lv) in bound.items():
             d = proc.decls[n]

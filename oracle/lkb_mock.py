@@ -211,6 +211,15 @@ def lkb_op_csr_create(interp, ctx, kind, m, n, rowptr, col, val, A):
     return ("__out__", {7: CPtr(MOp(k, M))}, LKB_OK)
 
 
+def lkb_op_csr_create_dist(interp, ctx, kind, m_global, n_global, row0, m_local, col0, n_local, rowptr, col, val, A):
+    """row-sharded CSR: the mock is ONE rank, so the shard must be the whole matrix"""
+    _count("lkb_op_csr_create_dist")
+    if int(row0) != 0 or int(col0) != 0 or int(m_local) != int(m_global) or int(n_local) != int(n_global):
+        return LKB_ERR_ARG
+    res = lkb_op_csr_create(interp, ctx, kind, m_global, n_global, rowptr, col, val, A)
+    return ("__out__", {11: res[1][7]}, LKB_OK) if isinstance(res, tuple) else res
+
+
 def _coef(p, n, kind):
     return tuple(DT[kind](v) for v in p.obj.reshape(-1)[:n])
 

@@ -129,7 +129,7 @@ def test_generic_arnoldi_dispatches_and_matches_the_oracle(shim, kind):
     assert _rel(H2, Ho) < _tol(kind)
 
 
-@pytest.mark.parametrize("kind", list("dz"))
+@pytest.mark.parametrize("kind", list("sdcz"))
 def test_lanczos_bidiag_qr_dispatch(shim, kind):
     it, stats = shim
     kdim = 10
@@ -154,7 +154,7 @@ def test_lanczos_bidiag_qr_dispatch(shim, kind):
     Xo = np.zeros((N, kdim + 1), dtype=S.dtype, order="F")
     Xo[:, 0] = x0
     assert lo.lanczos(lo.Op.dense(S), Xo, To) == int(o[3])
-    assert _rel(T, To) < 1e-12 and _rel(dev, Xo) < 1e-11
+    assert _rel(T, To) < _tol(kind) and _rel(dev, Xo) < 10 * _tol(kind)
     # bidiagonalization
     A = rc.general_matrix(kind, 61)
     op = _op(it, kind, A)
@@ -168,7 +168,7 @@ def test_lanczos_bidiag_qr_dispatch(shim, kind):
     Uo[:, 0] = rc.unit(rc.pseudo((N,), 62, kind))
     Vo, Bo = np.zeros_like(Uo), np.zeros_like(B)
     assert lo.bidiag(lo.Op.dense(A), Uo, Vo, Bo) == int(o[4])
-    assert _rel(B, Bo) < 1e-12 and _rel(udev, Uo) < 1e-11 and _rel(vdev, Vo) < 1e-11
+    assert _rel(B, Bo) < _tol(kind) and _rel(udev, Uo) < 10 * _tol(kind) and _rel(vdev, Vo) < 10 * _tol(kind)
     # qr without and with pivoting on a section of a wider basis
     M = rc.pseudo((N, 6), 71, kind)
     Q, qdev = _basis(it, kind, 8)
@@ -179,17 +179,17 @@ def test_lanczos_bidiag_qr_dispatch(shim, kind):
     assert it.hook_hits == {f"qr_no_pivoting_{k}": 1}
     Mo = M.copy(order="F")
     info_o, Ro = lo.qr(Mo)
-    assert int(o[2]) == info_o and _rel(R, Ro) < 1e-12 and _rel(qdev[:, 1:7], Mo) < 1e-12
+    assert int(o[2]) == info_o and _rel(R, Ro) < _tol(kind) and _rel(qdev[:, 1:7], Mo) < _tol(kind)
     assert np.all(qdev[:, 0] == 0) and np.all(qdev[:, 7] == 0)             # the neighbours of the section are untouched
     qdev[:, 1:7] = M
     perm = np.zeros(6, dtype=np.int64)
     _, o = it.call("qr", Q[1:7], R, perm, 0)
     Mo = M.copy(order="F")
     info_o, Ro, po = lo.qr_with_pivoting(Mo)
-    assert int(o[3]) == info_o and np.array_equal(perm - 1, po) and _rel(R, Ro) < 1e-12
+    assert int(o[3]) == info_o and np.array_equal(perm - 1, po) and _rel(R, Ro) < _tol(kind)
 
 
-@pytest.mark.parametrize("kind", list("dz"))
+@pytest.mark.parametrize("kind", list("sdcz"))
 def test_type_bound_procedures_and_object_semantics(shim, kind):
     """zero / rand / scal / axpby / dot / norm / add / sub / chsgn / get_size through the reference's abstract interface,
     lazy allocation of an empty vector, defined assignment = deep copy, copy() into an intent(out) vector"""
@@ -203,8 +203,8 @@ def test_type_bound_procedures_and_object_semantics(shim, kind):
     sc.vars.update(x=X, w=w, alpha=a.dtype.type(0.5), one=a.dtype.type(1.0))
     assert not it.ev(f90run.parse_expr("w%is_live()"), sc)
     assert it.ev(f90run.parse_expr("x(1)%get_size()"), sc) == N
-    assert abs(it.ev(f90run.parse_expr("x(1)%dot(x(2))"), sc) - np.vdot(a, b)) < 1e-12
-    assert abs(it.ev(f90run.parse_expr("x(2)%norm()"), sc) - np.linalg.norm(b)) < 1e-12
+    assert abs(it.ev(f90run.parse_expr("x(1)%dot(x(2))"), sc) - np.vdot(a, b)) < 100 * _tol(kind)
+    assert abs(it.ev(f90run.parse_expr("x(2)%norm()"), sc) - np.linalg.norm(b)) < 100 * _tol(kind)
 
     def run(stmt):
         it.exec_stmt(("callsub", f90run.parse_expr(stmt), ("test", 0, stmt)), sc)
@@ -215,7 +215,7 @@ def test_type_bound_procedures_and_object_semantics(shim, kind):
     run("x(3)%add(x(2))")
     run("x(3)%chsgn()")
     run("x(3)%scal(alpha)")
-    assert _rel(dev[:, 2], -0.5 * (a + b)) < 1e-14
+    assert _rel(dev[:, 2], -0.5 * (a + b)) < (1e-14 if kind in "dz" else 1e-6)
     run("x(3)%sub(x(3))")
     assert np.all(dev[:, 2] == 0)
     # defined assignment: deep copy on the device, no new handle for a live target
@@ -342,12 +342,14 @@ def test_solvers_dispatch(shim, kind):
     assert int(o[5]) == info_o and _rel(cdev[:, 1], co) < _tol(kind)
 
 
-@pytest.mark.parametrize("kind", list("dz"))
+@pytest.mark.parametrize("kind", list("sdcz"))
 def test_eigs_svds_dispatch(shim, kind):
     """eigs (complex eigenvalues allocated by the shim, write_intermediate passed through as a context option) and svds"""
     it, stats = shim
     k = SUF[kind]
-    rt = np.float64
+    rt = np.float32 if kind in "sc" else np.float64
+    ct = np.complex64 if kind in "sc" else np.complex128
+    tol9 = 1e-3 if kind in "sc" else 1e-9
     # svds: U(:) and V(:) are intent(out) views; S and residuals are allocated by the shim in the kind's precision
     A = rc.general_matrix(kind, 231)
     op = _op(it, kind, A)
@@ -357,12 +359,12 @@ def test_eigs_svds_dispatch(shim, kind):
     u0h = rc.unit(rc.pseudo((N,), 232, kind))
     u0, _ = _basis(it, kind, 1, u0h)
     it.hook_hits = {}
-    _, o = it.call("svds", op, U, None, V, None, 0, u0=u0[0], kdim=64, tolerance=rt(1e-9), write_intermediate=False)
+    _, o = it.call("svds", op, U, None, V, None, 0, u0=u0[0], kdim=64, tolerance=rt(tol9), write_intermediate=False)
     assert it.hook_hits == {f"svds_{k}": 1}
-    So, reso, Uo, Vo, ko = lo.svds(lo.Op.dense(A), nsv, u0h, kdim=64, tolerance=1e-9)
-    assert int(o[5]) == ko and _rel(np.asarray(o[2]), So) < 1e-12
-    assert _rel(np.abs(udev), np.abs(Uo)) < 1e-9 and _rel(np.abs(vdev), np.abs(Vo)) < 1e-9
-    assert np.asarray(o[2]).dtype == np.float64 and np.asarray(o[4]).shape == (nsv,)
+    So, reso, Uo, Vo, ko = lo.svds(lo.Op.dense(A), nsv, u0h, kdim=64, tolerance=float(rt(tol9)))
+    assert int(o[5]) == ko and _rel(np.asarray(o[2]), So) < _tol(kind)
+    assert _rel(np.abs(udev), np.abs(Uo)) < 1e3 * _tol(kind) and _rel(np.abs(vdev), np.abs(Vo)) < 1e3 * _tol(kind)
+    assert np.asarray(o[2]).dtype == rt and np.asarray(o[4]).shape == (nsv,)
     assert stats.options.get("write_intermediate") == 0
     # eigs
     Ad = rc.dominant_matrix(kind)
@@ -372,14 +374,14 @@ def test_eigs_svds_dispatch(shim, kind):
     x0h = rc.unit(rc.pseudo((N,), 252, kind))
     x0, _ = _basis(it, kind, 1, x0h)
     it.hook_hits = {}
-    _, o = it.call("eigs", opd, X, None, None, 0, x0=x0[0], kdim=24, tolerance=rt(1e-9), write_intermediate=False)
+    _, o = it.call("eigs", opd, X, None, None, 0, x0=x0[0], kdim=24, tolerance=rt(tol9), write_intermediate=False)
     assert it.hook_hits == {f"eigs_{k}": 1}
-    evo, reso, Xo, niter = lo.eigs(lo.Op.dense(Ad), N, nev, x0h, kdim=24, tolerance=1e-9)
+    evo, reso, Xo, niter = lo.eigs(lo.Op.dense(Ad), N, nev, x0h, kdim=24, tolerance=float(rt(tol9)))
     ev = np.asarray(o[2])
-    assert int(o[4]) == niter and ev.dtype == np.complex128 and _rel(ev, evo) < 1e-12
-    assert _rel(np.abs(xdev), np.abs(Xo)) < 1e-9
+    assert int(o[4]) == niter and ev.dtype == ct and _rel(ev, evo) < _tol(kind)
+    assert _rel(np.abs(xdev), np.abs(Xo)) < 1e3 * _tol(kind)
     # the reference's default for eigs is write_intermediate = .true. (IterativeSolvers.fypp:1025): absent -> option set
-    it.call("eigs", opd, X, None, None, 0, x0=x0[0], kdim=24, tolerance=rt(1e-9))
+    it.call("eigs", opd, X, None, None, 0, x0=x0[0], kdim=24, tolerance=rt(tol9))
     assert stats.options.get("write_intermediate") == 1
 
 
@@ -539,3 +541,103 @@ def test_preconditioned_fgmres_and_cg_through_the_c_trampoline(shim):
     _, o = it.call("cg", A_ref, b_ref[0], x_ref[0], 0, preconditioner=pre3)
     assert it.hook_hits == {} and int(o[3]) == info_o and _rel(x_ref[0].f["data"], xo) < 1e-12
     assert int(pre3.f["n_applied"]) == int(pre2.f["n_applied"])
+
+
+@pytest.mark.parametrize("kind", list("sdcz"))
+def test_remaining_entry_points_in_every_kind(shim, kind):
+    """what the tests above leave untouched, in all four kinds (the shim is generated per kind from one template): rand, the
+    transpose / symmetric operator applications through the reference's apply_rmatvec / apply_matvec wrappers (counters), all four
+    stencil constructors, one-pass orthogonalize_against_basis (vector and basis), block exponential, krylov_exptA, fgmres, release"""
+    it, stats = shim
+    k = SUF[kind]
+    rt = np.float32 if kind in "sc" else np.float64
+    dt = rc.DTYPE[kind]
+    nx, ny, nz = 6, 5, 4
+    n2, n3 = nx * ny, nx * ny * nz
+    c5 = np.array(rc.CONVDIFF2D, dtype=dt)
+    c7 = np.array(rc.CONVDIFF3D, dtype=dt)
+    op5, _ = it.call(f"cuda_stencil5_{k}", nx, ny, c5, 0, ny)
+    op7, _ = it.call(f"cuda_stencil7_{k}", nx, ny, nz, c7, 0, nz)
+    s5, _ = it.call(f"cuda_sym_stencil5_{k}", nx, ny, np.array(rc.POISSON2D, dtype=dt), 0, ny)
+    s7, _ = it.call(f"cuda_sym_stencil7_{k}", nx, ny, nz, np.array(rc.POISSON3D, dtype=dt), 0, nz)
+    for op, dims, coef, n in ((op5, (nx, ny), rc.CONVDIFF2D, n2), (op7, (nx, ny, nz), rc.CONVDIFF3D, n3),
+                              (s5, (nx, ny), rc.POISSON2D, n2), (s7, (nx, ny, nz), rc.POISSON3D, n3)):
+        _, o = it.call(f"cuda_basis_allocate_{k}", None, n, n, 0, 3)
+        X = o[0]
+        dev = X[0].f["basis"].obj.data
+        sc = f90run.Scope(None)
+        sc.vars.update(x=X, a=op)
+        it.exec_stmt(("callsub", f90run.parse_expr("x(1)%rand(ifnorm=.true.)"), ("test", 0, "")), sc)
+        assert abs(np.linalg.norm(dev[:, 0]) - 1) < 1e-5 and abs(it.ev(f90run.parse_expr("x(1)%norm()"), sc) - 1) < 1e-5
+        it.exec_stmt(("callsub", f90run.parse_expr("a%apply_matvec(x(1), x(2))"), ("test", 0, "")), sc)
+        ref = lo.Op.stencil(kind, dims, coef)
+        assert _rel(dev[:, 1], ref.apply(dev[:, 0].copy())) < _tol(kind) and op.f["matvec_counter"] == 1
+        if "rmatvec_counter" in op.f and it.find_binding(op.tname, "apply_rmatvec") is not None:
+            it.exec_stmt(("callsub", f90run.parse_expr("a%apply_rmatvec(x(1), x(3))"), ("test", 0, "")), sc)
+            assert _rel(dev[:, 2], ref.apply(dev[:, 0].copy(), True)) < _tol(kind) and op.f["rmatvec_counter"] == 1
+        it.call(f"cuda_basis_release_{k}", X)
+    # one-pass orthogonalize_against_basis, vector and basis form, contiguous views -> the library entry point
+    Q, qdev = _basis(it, kind, 7, rc.orthonormal_block(kind, 4, 101))
+    Yh = rc.pseudo((N, 3), 112, kind)
+    qdev[:, 4:7] = Yh
+    beta = np.zeros(4, dtype=dt)
+    it.hook_hits = {}
+    _, o = it.call("orthogonalize_against_basis", Q[4], Q[:4], 0, if_chk_orthonormal=False, beta=beta)
+    assert it.hook_hits == {f"orthogonalize_vector_against_basis_{k}": 1} and int(o[2]) == 0
+    want = Yh[:, 0] - qdev[:, :4] @ (qdev[:, :4].conj().T @ Yh[:, 0])
+    assert _rel(qdev[:, 4], want) < 10 * _tol(kind) and _rel(beta, qdev[:, :4].conj().T @ Yh[:, 0]) < 10 * _tol(kind)
+    betam = np.zeros((4, 2), dtype=dt, order="F")
+    it.hook_hits = {}
+    _, o = it.call("orthogonalize_against_basis", Q[5:7], Q[:4], 0, if_chk_orthonormal=False, beta=betam)
+    assert it.hook_hits == {f"orthogonalize_basis_against_basis_{k}": 1} and int(o[2]) == 0
+    want = Yh[:, 1:3] - qdev[:, :4] @ (qdev[:, :4].conj().T @ Yh[:, 1:3])
+    assert _rel(qdev[:, 5:7], want) < 10 * _tol(kind)
+    # block exponential, krylov_exptA, fgmres without a preconditioner
+    B, bdev = _basis(it, kind, 4, rc.pseudo((N, 2), 272, kind))
+    Ak = rc.general_matrix(kind, 271)
+    opk = _op(it, kind, Ak)
+    tol = 1e-4 if kind in "sc" else 1e-10
+    it.hook_hits = {}
+    _, o = it.call("kexpm", B[2:4], opk, B[0:2], rt(0.1), rt(tol), 0, kdim=20)
+    assert it.hook_hits == {f"kexpm_mat_{k}": 1}
+    Co, info_o = lo.kexpm_mat(lo.Op.dense(Ak), np.asfortranarray(bdev[:, :2].copy()), float(rt(0.1)), float(rt(tol)), kdim=20)
+    assert int(o[5]) == info_o and _rel(bdev[:, 2:4], Co) < _tol(kind)
+    it.hook_hits = {}
+    _, o = it.call("krylov_expta", B[3], opk, B[0], rt(0.1), 0)
+    assert it.hook_hits == {f"krylov_expta_{k}": 1}
+    co, info_o = lo.kexpm_vec(lo.Op.dense(Ak), bdev[:, 0].copy(), float(rt(0.1)), lo.ATOL[kind], kdim=30)
+    assert int(o[4]) == info_o and _rel(bdev[:, 3], co) < _tol(kind)
+    Aw = rc.well_conditioned(kind, 261)
+    opw = _op(it, kind, Aw)
+    bx, dev = _basis(it, kind, 2, rc.unit(rc.pseudo((N,), 262, kind)))
+    prec = "sp" if kind in "sc" else "dp"
+    opts = it.new_inst(f"fgmres_{prec}_opts")
+    opts.f["kdim"], opts.f["maxiter"] = 8, 30
+    it.hook_hits = {}
+    _, o = it.call("fgmres", opw, bx[0], bx[1], 0, options=opts)
+    assert it.hook_hits == {f"fgmres_{k}": 1}
+    xo = np.zeros(N, dtype=dt)
+    info_o, _ = lo.gmres(lo.Op.dense(Aw), dev[:, 0].copy(), xo, kdim=8, maxiter=30, flexible=True)
+    assert int(o[3]) == info_o > 0 and _rel(dev[:, 1], xo) < _tol(kind)
+    # row-sharded CSR constructor (one rank: the shard is the whole matrix)
+    rp, cl, vl = _csr(Aw)
+    opd, _ = it.call(f"cuda_csr_dist_{k}", N, N, 0, N, 0, N, rp, cl, vl)
+    assert isinstance(opd.f["h"].obj, lkb_mock.MOp)
+    # lkb_stop / lkb_start: the context handle is dropped and re-created
+    it.call("lkb_stop")
+    assert it.p.globals["lkb_ctx"].obj is None
+    it.call("lkb_start", 0)
+    assert it.p.globals["lkb_ctx"].obj is not None
+
+
+def test_zz_shim_coverage(shim, request):
+    """runs last in this module: every procedure of the generated shim was EXECUTED by the tests above, except the C trampolines of
+    the three kinds for which no user preconditioner type is written here (same template as the rdp one that ran)"""
+    it, _ = shim
+    mine = [i for i in request.session.items if i.fspath == request.node.fspath]
+    if len(mine) < len(list(request.node.parent.collect())):
+        pytest.skip("only a selection of this module ran: coverage is meaningful for the whole module")
+    procs = [n for n, p in it.p.procs.items() if p.file and p.file.endswith("lightkrylov_cuda.f90")]
+    missing = sorted(n for n in procs if n not in it.called)
+    assert len(procs) > 200
+    assert missing == ["precond_tramp_cdp", "precond_tramp_csp", "precond_tramp_rsp"], missing
