@@ -1816,6 +1816,8 @@ class Interp:
                         v.f[d.name] = None
                     elif d.init is not None and not d.dims:
                         v.f[d.name] = self.coerce(d.ts, self.ev(d.init, self.gscope))
+                    elif d.init is not None and isinstance(v.f.get(d.name), np.ndarray):
+                        v.f[d.name][...] = self.ev(d.init, self.gscope)          # default-initialised array component
         elif isinstance(v, np.ndarray) and v.dtype == object:
             for x in v.ravel():
                 self.reset_intent_out(x)
