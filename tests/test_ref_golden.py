@@ -569,3 +569,95 @@ def test_gpu_harness_dry_run_on_the_cpu(oracle, case, kind, tmp_path, monkeypatc
         _compare(got, _fixture_of(case), f"{case}/{kind}", 1e-10)
     else:
         _compare(got, _fixture_of(case), f"{case}/{kind}", 1e-10, skip=("X",) if "eigs" in case else (), vec_tol=1e-8)
+
+
+SNIPPET2 = """
+module snip2
+    use, intrinsic :: iso_c_binding
+    implicit none
+    integer, parameter :: dp = selected_real_kind(15, 307)
+    type :: cell_t
+        real(dp) :: v(3) = 7.0_dp
+        integer :: hits = 0
+    contains
+        procedure, pass(lhs) :: cell_assign
+        generic :: assignment(=) => cell_assign
+    end type cell_t
+    interface
+        integer(c_int) function ext_fill(p, n) bind(C, name='ext_fill')
+            import
+            type(c_ptr), value :: p
+            integer(c_int), value :: n
+        end function
+    end interface
+contains
+    subroutine cell_assign(lhs, rhs)
+        class(cell_t), intent(inout) :: lhs
+        type(cell_t), intent(in) :: rhs
+        lhs%v = 2.0_dp * rhs%v
+        lhs%hits = lhs%hits + 1
+    end subroutine cell_assign
+    subroutine wipe(c)
+        type(cell_t), intent(out) :: c
+    end subroutine wipe
+    impure elemental subroutine bump(c, by)
+        type(cell_t), intent(inout) :: c
+        real(dp), intent(in) :: by
+        c%v = c%v + by
+    end subroutine bump
+    subroutine driver(cells, flat, total, rc)
+        type(cell_t), intent(inout) :: cells(:)
+        real(dp), target, intent(inout) :: flat(:)
+        real(dp), intent(out) :: total
+        integer, intent(out) :: rc
+        real(dp), pointer :: grid(:, :)
+        real(dp), target :: scratch(4)
+        integer :: i
+        call wipe(cells(1))
+        call bump(cells, 1.0_dp)
+        cells(2) = cells(1)
+        grid(1:2, 1:3) => flat(:6)
+        grid(2, 3) = -1.0_dp
+        rc = int(ext_fill(c_loc(scratch), 4_c_int))
+        total = twice(sum(scratch))
+        named: do i = 1, 10
+            if (i == 4) exit named
+        end do named
+        total = total + i
+    contains
+        function twice(x) result(y)
+            real(dp), intent(in) :: x
+            real(dp) :: y
+            y = 2.0_dp * x
+        end function twice
+    end subroutine driver
+end module snip2
+"""
+
+
+def test_interpreter_semantics_2(tmp_path):
+    """intent(out) re-initialises default-initialised components, elemental subroutine over an array of objects, defined
+    assignment, pointer bounds remapping is a view, a bind(C) function served by a native writing through c_loc, internal
+    procedure, the value of a do variable after exit"""
+    from oracle import f90run
+    src = tmp_path / "snip2.f90"
+    src.write_text(SNIPPET2)
+    prog = f90run.Program()
+    prog.load(str(src))
+    it = f90run.Interp(prog)
+
+    def ext_fill(interp, p, n):
+        p.obj[:int(n)] = np.arange(1, int(n) + 1)
+        return 0
+    it.natives["ext_fill"] = ext_fill
+    cells = np.empty(2, dtype=object)
+    for i in range(2):
+        cells[i] = it.new_inst("cell_t")
+    cells[0].f["v"][...] = [1.0, 2.0, 3.0]
+    cells[0].f["hits"] = 5
+    flat = np.arange(8, dtype=np.float64)
+    _, o = it.call("driver", cells, flat, np.float64(0), 0)
+    assert np.array_equal(cells[0].f["v"], [8.0, 8.0, 8.0]) and cells[0].f["hits"] == 0       # wiped to the defaults, then bumped
+    assert np.array_equal(cells[1].f["v"], [16.0, 16.0, 16.0]) and cells[1].f["hits"] == 1     # defined assignment ran once
+    assert flat[5] == -1.0 and flat[6] == 6.0                                                   # grid(2,3) is flat(6)
+    assert o[3] == 0 and o[2] == 2.0 * (1 + 2 + 3 + 4) + 4                                       # i == 4 after `exit`
