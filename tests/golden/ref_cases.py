@@ -435,6 +435,37 @@ def stencil3d_eigs(kind, be):
     return {"info": info, "eigvals": np.asarray(ev, dtype=np.complex128), "X": X}
 
 
+def toy_csr(kind, m=72, n=56, per_row=6):
+    """deterministic rectangular CSR: row i holds columns (3 i + q (n // per_row)) mod n, q < per_row (distinct), values from pseudo"""
+    col = np.array([sorted((3 * i + q * (n // per_row)) % n for q in range(per_row)) for i in range(m)], dtype=np.int32).ravel()
+    rowptr = np.arange(0, (m + 1) * per_row, per_row, dtype=np.int64)
+    val = pseudo((m * per_row,), 601, kind)
+    return m, n, rowptr, col, val
+
+
+def csr_bidiag(kind, be):
+    """C5: bidiagonalization of a rectangular complex CSR operator (72 x 56 here; 50M x 40M in bench_configs)"""
+    m, n, rowptr, col, val = toy_csr(kind)
+    kdim = 12
+    A = be.csr(kind, m, n, rowptr, col, val)
+    U = be.basis_n(kind, m, kdim + 1, unit(pseudo((m,), 602, kind)))
+    V = be.basis_n(kind, n, kdim + 1)
+    B = np.zeros((kdim + 1, kdim), dtype=DTYPE[kind], order="F")
+    info = be.bidiag(A, U, V, B)
+    return {"info": info, "B": B, "U": be.data(U), "V": be.data(V)}
+
+
+def csr_svds(kind, be):
+    """C5 (svds row)"""
+    m, n, rowptr, col, val = toy_csr(kind)
+    nsv = 3
+    A = be.csr(kind, m, n, rowptr, col, val)
+    S, res, U, V, info = be.svds(A, nsv, unit(pseudo((m,), 612, kind)), kdim=40, tolerance=1e-9, shape=(m, n))
+    return {"info": info, "S": np.asarray(S, dtype=np.float64), "absU": np.abs(U), "absV": np.abs(V)}
+
+
+CSR_CASES = {"csr_bidiag": csr_bidiag, "csr_svds": csr_svds}
+
 STENCIL_CASES = {"stencil2d_arnoldi": stencil2d_arnoldi, "stencil2d_gmres": stencil2d_gmres,
                  "stencil3d_lanczos": stencil3d_lanczos, "stencil3d_cg": stencil3d_cg, "stencil3d_eigs": stencil3d_eigs}
 
@@ -442,9 +473,12 @@ SOLVER_CASES = {"eighs_write_intermediate": eighs_write_intermediate, "svds_writ
                 "fgmres_solve": fgmres_solve, "kexpm_block": kexpm_block, "kexpm_breakdown": kexpm_breakdown, "eigs_solve": eigs_solve, "gmres_solve": gmres_solve, "cg_solve": cg_solve, "eighs_solve": eighs_solve, "svds_solve": svds_solve,
                 "kexpm_solve": kexpm_solve}
 SOLVER_CASES.update(STENCIL_CASES)
+SOLVER_CASES.update(CSR_CASES)
 
 
 def applies(name, kind):
+    if name in CSR_CASES:
+        return kind == "z"
     return kind == "d" if name in STENCIL_CASES else True
 
 
@@ -482,6 +516,20 @@ class RefBackend:
         d = list(dims) + [1] * (3 - len(dims))
         op.f["nx"], op.f["ny"], op.f["nz"] = d
         op.f["coef"][:len(coef)] = coef
+        return op
+
+    def csr(self, kind, m, n, rowptr, col, val):
+        """user-side operator type of tests/golden/user_csr.f90 (complex(dp))"""
+        it = self.rx.interp()
+        if "csr_matvec_cdp" not in it.p.procs:
+            import os
+            from oracle import f90run
+            it.p.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "user_csr.f90"))
+            f90run.Interp(it.p)
+        op = it.new_inst("csr_linop_cdp")
+        op.f["m"], op.f["n"] = m, n
+        op.f["rowptr"], op.f["col"] = np.array(rowptr, dtype=np.int64), np.array(col, dtype=np.int64)
+        op.f["val"] = np.array(val, dtype=np.complex128)
         return op
 
     def basis_n(self, kind, n, ncols, first=None):
@@ -621,11 +669,15 @@ class RefBackend:
                             write_intermediate=False)
         return np.array(o[2]), np.array(o[3]), self.data(X), int(o[4])
 
-    def svds(self, A, nsv, u0, kdim, tolerance, write_intermediate=False):
+    def svds(self, A, nsv, u0, kdim, tolerance, write_intermediate=False, shape=None):
         kind = {np.dtype(np.float32): "s", np.dtype(np.float64): "d", np.dtype(np.complex64): "c",
                 np.dtype(np.complex128): "z"}[u0.dtype]
-        U, V = self.basis(kind, nsv), self.basis(kind, nsv)
-        u0v = self.rx.vector(kind, u0)
+        if shape is None:
+            U, V = self.basis(kind, nsv), self.basis(kind, nsv)
+            u0v = self.rx.vector(kind, u0)
+        else:
+            U, V = self.basis_n(kind, shape[0], nsv), self.basis_n(kind, shape[1], nsv)
+            u0v = self.basis_n(kind, shape[0], 1, u0)[0]
         _, o = self.rx.call("svds", A, U, None, V, None, 0, u0=u0v, kdim=kdim, tolerance=_real(kind)(tolerance),
                             write_intermediate=write_intermediate)
         return np.array(o[2]), np.array(o[4]), self.data(U), self.data(V), int(o[5])
@@ -667,6 +719,9 @@ class OracleBackend:
 
     def stencil(self, kind, dims, coef, sym=False):
         return self.lo.Op.stencil(kind, tuple(dims), tuple(float(c) for c in coef))
+
+    def csr(self, kind, m, n, rowptr, col, val):
+        return self.lo.Op.csr(m, n, rowptr, col, val)
 
     def basis_n(self, kind, n, ncols, first=None):
         X = np.zeros((n, ncols), dtype=DTYPE[kind], order="F")
@@ -748,7 +803,7 @@ class OracleBackend:
         ev, res, X, niter = self.lo.eigs(A, N if n is None else n, nev, x0, kdim=kdim, tolerance=tolerance)
         return ev, res, X, niter
 
-    def svds(self, A, nsv, u0, kdim, tolerance, write_intermediate=False):
+    def svds(self, A, nsv, u0, kdim, tolerance, write_intermediate=False, shape=None):
         S, res, U, V, k = self.lo.svds(A, nsv, u0, kdim=kdim, tolerance=tolerance, write_intermediate=write_intermediate)
         return S, res, U, V, k
 

@@ -455,13 +455,16 @@ class _ShellsBackend:
     def eighs(self, A, nev, x0, kdim, tolerance, write_intermediate=False):
         return self.sh.eighs(A, x0.shape[0], nev, x0, kdim=kdim, tol=tolerance)
 
-    def svds(self, A, nsv, u0, kdim, tolerance, write_intermediate=False):
-        return self.sh.svds(A, u0.shape[0], u0.shape[0], nsv, u0, kdim=kdim, tol=tolerance)
+    def csr(self, kind, m, n, rowptr, col, val):
+        return self.sh.op(self.oracle.Op.csr(m, n, rowptr, col, val))
+
+    def svds(self, A, nsv, u0, kdim, tolerance, write_intermediate=False, shape=None):
+        return self.sh.svds(A, u0.shape[0], u0.shape[0] if shape is None else shape[1], nsv, u0, kdim=kdim, tol=tolerance)
 
 
 @pytest.mark.parametrize("kind", ["d", "z"])
 @pytest.mark.parametrize("case", ["eigs_solve", "eighs_solve", "svds_solve", "eighs_write_intermediate", "svds_write_intermediate",
-                                  "stencil3d_eigs"])
+                                  "stencil3d_eigs", "csr_svds"])
 def test_cpp_shells_reproduce_reference_outputs(mock, oracle, case, kind, tmp_path, monkeypatch):
     import sys
     sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))

@@ -270,6 +270,9 @@ class ProductBackend:
             return self.lk.LinOp.stencil5(self.ctx, kind, dims[0], dims[1], tuple(coef))
         return self.lk.LinOp.stencil7(self.ctx, kind, dims[0], dims[1], dims[2], tuple(coef))
 
+    def csr(self, kind, m, n, rowptr, col, val):
+        return self.lk.LinOp.csr(self.ctx, m, n, rowptr, col, val)
+
     def basis_n(self, kind, n, ncols, first=None):
         X = self.lk.Basis(self.ctx, kind, n, ncols)
         X.zero()
@@ -317,10 +320,10 @@ class ProductBackend:
                 self.ctx.set_option("write_intermediate", 0)
         return ev, res, X.get(), info
 
-    def svds(self, A, nsv, u0, kdim, tolerance, write_intermediate=False):
+    def svds(self, A, nsv, u0, kdim, tolerance, write_intermediate=False, shape=None):
         kind, v = self._start(u0)
         U = self.lk.Basis(self.ctx, kind, u0.shape[0], nsv)
-        V = self.lk.Basis(self.ctx, kind, u0.shape[0], nsv)
+        V = self.lk.Basis(self.ctx, kind, u0.shape[0] if shape is None else shape[1], nsv)
         S, res, info = self.lk.svds(A, U, V, nsv, u0=v, kdim=kdim, tolerance=tolerance)
         return S, res, U.get(), V.get(), info
 
@@ -345,7 +348,7 @@ class ProductBackend:
 
 GPU_CASES = ["arnoldi_full", "arnoldi_transpose", "arnoldi_block", "arnoldi_resume", "arnoldi_breakdown", "lanczos_full",
              "bidiag_full", "qr_full", "qr_pivoting", "qr_pivoting_deficient", "krylov_schur_restart", "stencil2d_arnoldi",
-             "stencil3d_lanczos"]
+             "stencil3d_lanczos", "csr_bidiag"]
 
 
 @pytest.fixture(scope="module")
@@ -371,7 +374,7 @@ def test_gpu_matches_reference_outputs(gpu_ctx, case, kind):
 
 GPU_SOLVER_CASES = ["gmres_solve", "fgmres_solve", "cg_solve", "eighs_solve", "svds_solve", "eigs_solve", "kexpm_solve",
                     "kexpm_block", "kexpm_breakdown", "eighs_write_intermediate", "stencil2d_gmres", "stencil3d_cg",
-                    "stencil3d_eigs"]
+                    "stencil3d_eigs", "csr_svds"]
 
 
 @pytest.mark.gpu
@@ -458,6 +461,11 @@ class _FakeLk:
             def dense(ctx, A):
                 bound(api.LinOp.dense.__func__, None, ctx, A)
                 return LinOp(fake.lo.Op.dense(np.asfortranarray(A)))
+
+            @staticmethod
+            def csr(ctx, m, n, rowptr, col, val):
+                bound(api.LinOp.csr.__func__, None, ctx, m, n, rowptr, col, val)
+                return LinOp(fake.lo.Op.csr(m, n, rowptr, col, val))
 
             @staticmethod
             def stencil5(ctx, kind, nx, ny, coef, *a, **k):
