@@ -165,9 +165,6 @@ class _P:
     def at(self, v):
         return self.peek() == ("op", v)
 
-    def at_name(self, v):
-        return self.peek() == ("name", v)
-
     def eat(self, v=None):
         tok = self.peek()
         if v is not None and tok != ("op", v):
