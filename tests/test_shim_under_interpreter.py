@@ -630,6 +630,21 @@ def test_remaining_entry_points_in_every_kind(shim, kind):
     assert it.p.globals["lkb_ctx"].obj is not None
 
 
+def test_documented_hazard_direct_linear_combination_aliases_x1(shim):
+    """`linear_combination` (LightKrylov_AbstractVectors, below the shim in the module graph, hence not
+    patchable) clones its result with allocate(y, source=X(1)) -- for a device vector an intrinsic copy of the HANDLE.  Called
+    DIRECTLY with device vectors the result aliases X(1) and `call y%zero()` wipes it.  This test pins that reading of the Fortran
+    semantics (and that the interpreter models it); no solver path gets here (see the dispatch tests above)."""
+    it, _ = shim
+    X, dev = _basis(it, "d", 3, rc.pseudo((N, 3), 701, "d"))
+    before = dev.copy()
+    _, o = it.call("linear_combination", None, X, np.array([1.0, 2.0, 3.0]))
+    y = o[0]
+    assert y.f["h"].obj is X[0].f["h"].obj                         # the clone shares the device buffer of X(1)
+    assert not np.array_equal(dev[:, 0], before[:, 0])             # ... which the routine then overwrote
+    assert np.array_equal(dev[:, 1:], before[:, 1:])
+
+
 def test_zz_shim_coverage(shim, request):
     """runs last in this module: every procedure of the generated shim was EXECUTED by the tests above, except the C trampolines of
     the three kinds for which no user preconditioner type is written here (same template as the rdp one that ran)"""
