@@ -296,6 +296,53 @@ class ProductBackend:
     def krylov_schur(self, X, H):
         return self.lk.krylov_schur(X, H, X.ncols - 1)
 
+    # ---- Gram-Schmidt and the basis-level helpers: X and the vectors to treat are put side by side in ONE basis (columns
+    # [0, j) and [j, j + p)), the layout Arnoldi itself uses and the one every other GPU test of these entry points uses
+    def _side_by_side(self, X, Y):
+        j, p = X.ncols, Y.ncols
+        Bc = self.lk.Basis(self.ctx, X.kind, X.n, j + p)
+        Bc.put(X.get())
+        Bc.put(Y.get(), col0=j)
+        return Bc, j, p
+
+    def dgs_vec(self, y, X):
+        Bc, j, p = self._side_by_side(X, y)
+        info, beta = self.lk.double_gram_schmidt_step(Bc, j, 1, Bc, j, if_chk_orthonormal=False)
+        y.put(Bc.get(j, 1))
+        return info, beta[:, 0].copy()
+
+    def dgs_bas(self, Y, X):
+        Bc, j, p = self._side_by_side(X, Y)
+        info, beta = self.lk.double_gram_schmidt_step(Bc, j, p, Bc, j, if_chk_orthonormal=False)
+        Y.put(Bc.get(j, p))
+        return info, beta
+
+    def helpers(self, kind, X, Y, Bm):
+        lk = self.lk
+        Bc, j, p = self._side_by_side(X, Y)
+        ip = Bc.innerprod(j, Bc, wcol0=j, p=p)
+        G = Bc.innerprod(j, Bc, wcol0=0, p=j)
+        # the reference fills the lower triangle of Gram(X) with the UNCONJUGATED upper one: same layout here
+        G = np.triu(G) + np.triu(G, 1).T
+        out = {"innerprod_vec": ip[:, 0].copy(), "innerprod_mat": ip, "gram": G}
+        yv = lk.Vector(self.ctx, kind, X.n)
+        cols = []
+        for q in range(p):
+            Bc.linear_combination(j, np.ascontiguousarray(Bm[:, q]), yv)
+            cols.append(yv.get())
+        out["lincomb_vec"] = cols[0].copy()
+        L = np.asfortranarray(np.column_stack(cols))
+        out["lincomb_mat"] = L
+        Z = lk.Basis(self.ctx, kind, X.n, p)
+        Z.put(L)
+        Z.axpby(0.5, Y, 1.0)
+        out["axpby_basis"] = Z.get()
+        Z.copy_from(Y)
+        out["copy"] = Z.get()
+        Z.zero()
+        out["zero_basis"] = Z.get()
+        return out
+
     # ---- solvers (vectors = columns of one-column bases)
     def gmres(self, A, b, x, kdim, maxiter, flexible=False):
         fn = self.lk.fgmres if flexible else self.lk.gmres
@@ -348,7 +395,7 @@ class ProductBackend:
 
 GPU_CASES = ["arnoldi_full", "arnoldi_transpose", "arnoldi_block", "arnoldi_resume", "arnoldi_breakdown", "lanczos_full",
              "bidiag_full", "qr_full", "qr_pivoting", "qr_pivoting_deficient", "krylov_schur_restart", "stencil2d_arnoldi",
-             "stencil3d_lanczos", "csr_bidiag"]
+             "stencil3d_lanczos", "csr_bidiag", "dgs_vector", "dgs_basis", "dgs_zero_vector", "basis_helpers"]
 
 
 @pytest.fixture(scope="module")
@@ -442,13 +489,35 @@ class _FakeLk:
                 self.data[:, col0:col0 + h.shape[1]] = h
                 return self
 
-            def get(self, *a, **k):
-                bound(api.Basis.get, None, *a, **k)
-                return self.data.copy(order="F")
+            def get(self, col0=0, ncols=None):
+                bound(api.Basis.get, None, col0, ncols)
+                ncols = self.ncols - col0 if ncols is None else ncols
+                return self.data[:, col0:col0 + ncols].copy(order="F")
 
             def col(self, i):
                 bound(api.Basis.col, None, i)
                 return Vector(None, self.kind, self.n, _view=self.data[:, i])
+
+            def innerprod(self, j, W, **k):
+                bound(api.Basis.innerprod, None, j, W, **k)
+                c0, p = k.get("wcol0", 0), k.get("p", 1)
+                col = np.ascontiguousarray
+                return np.array([[fake.lo.dot(col(self.data[:, i]), col(W.data[:, c0 + q])) for q in range(p)] for i in range(j)],
+                                dtype=self.data.dtype).reshape(j, p)
+
+            def linear_combination(self, j, coef, y):
+                bound(api.Basis.linear_combination, None, j, coef, y)
+                y.data[...] = 0
+                for i in range(j):
+                    fake.lo.axpby(coef[i], np.ascontiguousarray(self.data[:, i]), 1.0, y.data)
+
+            def axpby(self, alpha, X, beta, **k):
+                bound(api.Basis.axpby, None, alpha, X, beta, **k)
+                self.data[...] = (self.data.dtype.type(alpha) * X.data + self.data.dtype.type(beta) * self.data)
+
+            def copy_from(self, X, **k):
+                bound(api.Basis.copy_from, None, X, **k)
+                self.data[...] = X.data
 
         class LinOp:
             def __init__(self, op):
@@ -512,6 +581,14 @@ class _FakeLk:
     def qr_pivoting(self, Q):
         self._chk("qr_pivoting", Q)
         return self.lo.qr_with_pivoting(Q.data)
+
+    def double_gram_schmidt_step(self, W, wcol0, p, X, j, **k):
+        self._chk("double_gram_schmidt_step", W, wcol0, p, X, j, **k)
+        Xs = np.asfortranarray(X.data[:, :j].copy())
+        Ws = np.asfortranarray(W.data[:, wcol0:wcol0 + p].copy())
+        info, beta = self.lo.dgs_bas(Ws, Xs, j)
+        W.data[:, wcol0:wcol0 + p] = Ws
+        return info, beta
 
     def krylov_schur(self, X, H, kdim):
         self._chk("krylov_schur", X, H, kdim)
