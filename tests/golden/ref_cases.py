@@ -123,6 +123,30 @@ def lanczos_full(kind, be):
     return {"info": info, "T": T, "X": be.data(X)}
 
 
+def lanczos_resume(kind, be):
+    """kstart / kend: five steps, then the rest -- same T and basis as one call (lanczos.fypp:7-64)"""
+    kdim = 12
+    A = be.linop(kind, sym_matrix(kind, 53), sym=True)
+    X = be.basis(kind, kdim + 1, unit(pseudo((N,), 54, kind)))
+    T = np.zeros((kdim + 1, kdim), dtype=DTYPE[kind], order="F")
+    info1 = be.lanczos(A, X, T, kend=5)
+    T5 = T.copy()
+    info2 = be.lanczos(A, X, T, kstart=6, kend=12)
+    return {"info1": info1, "info2": info2, "T_after_5": T5, "T": T, "X": be.data(X)}
+
+
+def bidiag_resume(kind, be):
+    kdim = 10
+    A = be.linop(kind, general_matrix(kind, 63))
+    U = be.basis(kind, kdim + 1, unit(pseudo((N,), 64, kind)))
+    V = be.basis(kind, kdim + 1)
+    B = np.zeros((kdim + 1, kdim), dtype=DTYPE[kind], order="F")
+    info1 = be.bidiag(A, U, V, B, kend=4)
+    B4 = B.copy()
+    info2 = be.bidiag(A, U, V, B, kstart=5, kend=10)
+    return {"info1": info1, "info2": info2, "B_after_4": B4, "B": B, "U": be.data(U), "V": be.data(V)}
+
+
 def bidiag_full(kind, be):
     kdim = 16
     A = be.linop(kind, general_matrix(kind, 61))
@@ -233,7 +257,7 @@ def basis_helpers(kind, be):
 
 
 CASES = {
-    "krylov_schur_restart": krylov_schur_restart, "basis_helpers": basis_helpers,
+    "lanczos_resume": lanczos_resume, "bidiag_resume": bidiag_resume, "krylov_schur_restart": krylov_schur_restart, "basis_helpers": basis_helpers,
     "dgs_zero_vector": dgs_zero_vector, "qr_pivoting_deficient": qr_pivoting_deficient,
     "arnoldi_full": arnoldi_full, "arnoldi_transpose": arnoldi_transpose, "arnoldi_block": arnoldi_block,
     "arnoldi_resume": arnoldi_resume, "arnoldi_breakdown": arnoldi_breakdown, "lanczos_full": lanczos_full,
@@ -557,12 +581,12 @@ class RefBackend:
                                                                  blksize=blksize))
         return int(o[3])
 
-    def lanczos(self, A, X, T):
-        _, o = self.rx.call("lanczos", A, X, T, 0)
+    def lanczos(self, A, X, T, kstart=None, kend=None):
+        _, o = self.rx.call("lanczos", A, X, T, 0, **self._opt(kstart=kstart, kend=kend))
         return int(o[3])
 
-    def bidiag(self, A, U, V, B):
-        _, o = self.rx.call("bidiagonalization", A, U, V, B, 0)
+    def bidiag(self, A, U, V, B, kstart=None, kend=None):
+        _, o = self.rx.call("bidiagonalization", A, U, V, B, 0, **self._opt(kstart=kstart, kend=kend))
         return int(o[4])
 
     def qr(self, Q, tol=None):
@@ -736,11 +760,11 @@ class OracleBackend:
     def arnoldi(self, A, X, H, kstart=None, kend=None, tol=None, transpose=None, blksize=None):
         return self.lo.arnoldi(A, X, H, kstart=kstart or 1, kend=kend, tol=tol, trans=bool(transpose), blksize=blksize or 1)
 
-    def lanczos(self, A, X, T):
-        return self.lo.lanczos(A, X, T)
+    def lanczos(self, A, X, T, kstart=None, kend=None):
+        return self.lo.lanczos(A, X, T, kstart=kstart or 1, kend=kend)
 
-    def bidiag(self, A, U, V, B):
-        return self.lo.bidiag(A, U, V, B)
+    def bidiag(self, A, U, V, B, kstart=None, kend=None):
+        return self.lo.bidiag(A, U, V, B, kstart=kstart or 1, kend=kend)
 
     def qr(self, Q, tol=None):
         return self.lo.qr(Q, tol=tol)

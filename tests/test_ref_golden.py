@@ -287,11 +287,11 @@ class ProductBackend:
         return self.lk.arnoldi(A, X, H, kstart=kstart or 0, kend=kend or 0, tol=-1.0 if tol is None else tol,
                                transpose=bool(transpose), blksize=blksize or 1)
 
-    def lanczos(self, A, X, T):
-        return self.lk.lanczos(A, X, T)
+    def lanczos(self, A, X, T, kstart=None, kend=None):
+        return self.lk.lanczos(A, X, T, kstart=kstart or 0, kend=kend or 0)
 
-    def bidiag(self, A, U, V, B):
-        return self.lk.bidiagonalization(A, U, V, B)
+    def bidiag(self, A, U, V, B, kstart=None, kend=None):
+        return self.lk.bidiagonalization(A, U, V, B, kstart=kstart or 0, kend=kend or 0)
 
     def krylov_schur(self, X, H):
         return self.lk.krylov_schur(X, H, X.ncols - 1)
@@ -395,7 +395,7 @@ class ProductBackend:
 
 GPU_CASES = ["arnoldi_full", "arnoldi_transpose", "arnoldi_block", "arnoldi_resume", "arnoldi_breakdown", "lanczos_full",
              "bidiag_full", "qr_full", "qr_pivoting", "qr_pivoting_deficient", "krylov_schur_restart", "stencil2d_arnoldi",
-             "stencil3d_lanczos", "csr_bidiag", "dgs_vector", "dgs_basis", "dgs_zero_vector", "basis_helpers"]
+             "stencil3d_lanczos", "csr_bidiag", "lanczos_resume", "bidiag_resume", "dgs_vector", "dgs_basis", "dgs_zero_vector", "basis_helpers"]
 
 
 @pytest.fixture(scope="module")
@@ -566,13 +566,13 @@ class _FakeLk:
                                tol=None if k.get("tol", -1.0) < 0 else k["tol"], trans=k.get("transpose", False),
                                blksize=k.get("blksize", 1))
 
-    def lanczos(self, A, X, T):
-        self._chk("lanczos", A, X, T)
-        return self.lo.lanczos(A.op, X.data, T)
+    def lanczos(self, A, X, T, **k):
+        self._chk("lanczos", A, X, T, **k)
+        return self.lo.lanczos(A.op, X.data, T, kstart=k.get("kstart", 0) or 1, kend=k.get("kend", 0) or None)
 
-    def bidiagonalization(self, A, U, V, B):
-        self._chk("bidiagonalization", A, U, V, B)
-        return self.lo.bidiag(A.op, U.data, V.data, B)
+    def bidiagonalization(self, A, U, V, B, **k):
+        self._chk("bidiagonalization", A, U, V, B, **k)
+        return self.lo.bidiag(A.op, U.data, V.data, B, kstart=k.get("kstart", 0) or 1, kend=k.get("kend", 0) or None)
 
     def qr(self, Q, **k):
         self._chk("qr", Q, **k)
