@@ -415,6 +415,22 @@ def stencil2d_arnoldi(kind, be):
     return {"info": info, "H": H, "X": be.data(X), "matvecs": be.counter(A)}
 
 
+def stencil2d_arnoldi_large(kind, be):
+    """C2 at a size where the product's tiling is fully engaged (n = 786432 rows, 64 steps: many CTAs per kernel, j > 16 so that
+    the staged TMA ring and all chunk warps of the fused Gram-Schmidt kernel are live): every Hessenberg entry against the
+    reference's own arnoldi.  Only H, the head of the last basis vector and an orthonormality figure are stored."""
+    dims, kdim = (1024, 768), 64
+    n = dims[0] * dims[1]
+    A = be.stencil(kind, dims, POISSON2D)
+    X = be.basis_n(kind, n, kdim + 1, unit(pseudo((n,), 452, kind)))
+    H = np.zeros((kdim + 1, kdim), dtype=DTYPE[kind], order="F")
+    info = be.arnoldi(A, X, H)
+    Xd = be.data(X)
+    G = Xd[:, -8:].conj().T @ Xd[:, -8:]
+    return {"info": info, "H": H, "x_last_head": Xd[:256, kdim].copy(), "matvecs": be.counter(A),
+            "abs_orth_err": np.array(np.abs(G - np.eye(8)).max(), dtype=np.float64)}
+
+
 def stencil2d_gmres(kind, be):
     """C2 (gmres row): restarted gmres on a non-symmetric 5-point convection-diffusion stencil"""
     dims = (40, 36)
@@ -490,7 +506,7 @@ def csr_svds(kind, be):
 
 CSR_CASES = {"csr_bidiag": csr_bidiag, "csr_svds": csr_svds}
 
-STENCIL_CASES = {"stencil2d_arnoldi": stencil2d_arnoldi, "stencil2d_gmres": stencil2d_gmres,
+STENCIL_CASES = {"stencil2d_arnoldi": stencil2d_arnoldi, "stencil2d_arnoldi_large": stencil2d_arnoldi_large, "stencil2d_gmres": stencil2d_gmres,
                  "stencil3d_lanczos": stencil3d_lanczos, "stencil3d_cg": stencil3d_cg, "stencil3d_eigs": stencil3d_eigs}
 
 SOLVER_CASES = {"eighs_write_intermediate": eighs_write_intermediate, "svds_write_intermediate": svds_write_intermediate,

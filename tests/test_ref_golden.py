@@ -395,7 +395,7 @@ class ProductBackend:
 
 GPU_CASES = ["arnoldi_full", "arnoldi_transpose", "arnoldi_block", "arnoldi_resume", "arnoldi_breakdown", "lanczos_full",
              "bidiag_full", "qr_full", "qr_pivoting", "qr_pivoting_deficient", "krylov_schur_restart", "stencil2d_arnoldi",
-             "stencil3d_lanczos", "csr_bidiag", "lanczos_resume", "bidiag_resume", "dgs_vector", "dgs_basis", "dgs_zero_vector", "basis_helpers"]
+             "stencil2d_arnoldi_large", "stencil3d_lanczos", "csr_bidiag", "lanczos_resume", "bidiag_resume", "dgs_vector", "dgs_basis", "dgs_zero_vector", "basis_helpers"]
 
 
 @pytest.fixture(scope="module")
