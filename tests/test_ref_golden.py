@@ -746,3 +746,21 @@ def test_interpreter_semantics_2(tmp_path):
     assert np.array_equal(cells[1].f["v"], [16.0, 16.0, 16.0]) and cells[1].f["hits"] == 1     # defined assignment ran once
     assert flat[5] == -1.0 and flat[6] == 6.0                                                   # grid(2,3) is flat(6)
     assert o[3] == 0 and o[2] == 2.0 * (1 + 2 + 3 + 4) + 4                                       # i == 4 after `exit`
+
+
+def test_full_size_c2_golden_is_pinned_to_the_reference():
+    """tests/golden/ref_c2_full_H.npz = the 129 x 128 Hessenberg matrix of BASELINE configs[1] at FULL size (5-point Poisson 4096^2,
+    n = 16.8M, kdim = 128, the start vector of bench.py) computed by the REFERENCE's own arnoldi sources under oracle/f90run.py
+    (tests/golden/make_ref_golden_c2.py).  c2_full_H.npz is the oracle's matrix that every bench.py line -- at 1, 2, 4 and 8 GPUs --
+    and test_arnoldi_full_size_c2 compare the CUDA path with: the two must agree, so the headline parity record rests on the
+    reference's code at the headline size."""
+    path = os.path.join(GOLD, "ref_c2_full_H.npz")
+    if not os.path.exists(path):
+        pytest.skip("ref_c2_full_H.npz not generated (python tests/golden/make_ref_golden_c2.py, ~30 min in the container)")
+    r, g = np.load(path), _fixture("c2_full_H.npz")
+    assert int(r["info"]) == int(g["info"]) == 0 and int(r["matvecs"]) == 128 and int(r["kdim"]) == 128 and int(r["nx"]) == 4096
+    assert np.array_equal(r["x0_head"], g["x0_head"])                                   # the same start vector, bit for bit
+    assert r["H"].shape == g["H"].shape == (129, 128)
+    assert float(np.abs(r["H"] - g["H"]).max()) < 1e-12 * float(np.abs(g["H"]).max())
+    assert float(np.abs(r["ritz"] - g["ritz"]).max()) < 1e-12 * float(np.abs(g["ritz"]).max())
+    assert float(np.abs(r["xlast_head"] - g["xlast_head"]).max()) < 1e-9 * float(np.abs(g["xlast_head"]).max())
