@@ -304,10 +304,21 @@ def run_ours(args):
             hs = [None] * world
             dist.all_gather_object(hs, H.tobytes())
             same = all(h == hs[0] for h in hs)
+        # the same workload computed by the REFERENCE's own arnoldi sources (tests/golden/make_ref_golden_c2.py, executed by the
+        # interpreter oracle/f90run.py): a second, independent comparison of this run's H (data file only -- nothing is executed)
+        ref_err = None
+        ref_path = os.path.join(ROOT, "tests", "golden", "ref_c2_full_H.npz")
+        if os.path.exists(ref_path):
+            try:
+                Hr = np.load(ref_path)["H"]
+                ref_err = float(np.abs(H - Hr).max() / np.abs(Hr).max())
+            except Exception:                 # a damaged fixture must not take the benchmark down
+                ref_err = None
         parity = {"oracle": "tests/golden/c2_full_H.npz (CPU oracle, 128 steps, same start vector)",
-                  "oracle_pinned_by": "tests/golden/ref_*.npz: outputs of the reference's own Fortran sources executed by "
-                                      "oracle/f90run.py (no Fortran compiler exists here), reproduced by the oracle to 1e-12 "
-                                      "(tests/test_ref_golden.py; the 5-point stencil arnoldi case is stencil2d_arnoldi)",
+                  "oracle_pinned_by": "tests/golden/ref_c2_full_H.npz: this workload at full size computed by the reference's own Fortran "
+                                      "sources executed by oracle/f90run.py (no Fortran compiler exists here); agrees with the oracle matrix "
+                                      "to 1.1e-14 (tests/test_ref_golden.py)",
+                  "max_rel_err_H_vs_reference_sources": ref_err,
                   "max_rel_err_H": herr, "max_rel_err_ritz": rerr, "orth_err_first_last_8_cols": orth,
                   "H_identical_on_all_ranks": bool(same), "tol": 1e-10, "orth_tol": 1e-12,
                   "ok": bool(herr < 1e-10 and rerr < 1e-10 and orth <= 1e-12 and same)}
